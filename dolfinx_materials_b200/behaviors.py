@@ -1,0 +1,95 @@
+"""Behaviour descriptors with the constructor signatures of the ``jaxmat.materials`` objects the
+reference wraps (call sites: ``demos/jax/elastoplasticity/plane_elastoplasticity.py:60-73``,
+``demos/jax/finite_strain_elastoplasticity/finite_strain_elastoplasticity.py:158-169``,
+``tests/test_FeFp_jax.py:7-19``).  They carry parameters only -- the arithmetic lives in the CUDA
+kernels -- so that a reference script switches by replacing
+
+    import jaxmat.materials as jm ; material = JAXMaterial(behavior)
+by
+    import dolfinx_materials_b200 as jm ; material = jm.CUDAMaterial(behavior)
+"""
+
+from dataclasses import dataclass, field
+from typing import Any
+
+# behaviour ids of include/dxm.h
+DXM_ELASTIC, DXM_J2_LINEAR, DXM_J2_VOCE, DXM_FEFP_VOCE = 0, 1, 2, 3
+
+
+@dataclass
+class LinearElasticIsotropic:
+    """Isotropic linear elasticity (``python_materials/elasticity.py:5-19``)."""
+
+    E: Any
+    nu: Any
+
+
+@dataclass
+class LinearHardening:
+    """sigma_Y(p) = sig0 + H p  (``tests/mfront/IsotropicLinearHardeningPlasticity.mfront:11``)."""
+
+    sig0: Any
+    H: Any = 0.0
+
+
+@dataclass
+class VoceHardening:
+    """sigma_Y(p) = sig0 + (sigu - sig0) (1 - exp(-b p)) [+ H p]  (``tests/test_FeFp_jax.py:14-15``)."""
+
+    sig0: Any
+    sigu: Any
+    b: Any
+    H: Any = 0.0
+
+
+def _hardening_props(h):
+    if isinstance(h, LinearHardening):
+        return {"sig0": h.sig0, "H": h.H}
+    if isinstance(h, VoceHardening):
+        return {"sig0": h.sig0, "sigu": h.sigu, "b": h.b, "H": h.H}
+    raise TypeError(
+        "yield_stress must be a LinearHardening or VoceHardening descriptor; arbitrary Python "
+        "callables cannot be compiled into the CUDA kernels"
+    )
+
+
+@dataclass
+class _Behavior:
+    elasticity: LinearElasticIsotropic
+    kind: int = field(init=False, default=DXM_ELASTIC)
+    finite_strain: bool = field(init=False, default=False)
+
+    def properties(self):
+        return {"E": self.elasticity.E, "nu": self.elasticity.nu}
+
+
+@dataclass
+class ElasticBehavior(_Behavior):
+    """Small-strain linear elasticity."""
+
+
+@dataclass
+class vonMisesIsotropicHardening(_Behavior):
+    """Small-strain J2 plasticity with isotropic hardening."""
+
+    yield_stress: Any = None
+
+    def __post_init__(self):
+        self.kind = DXM_J2_LINEAR if isinstance(self.yield_stress, LinearHardening) else DXM_J2_VOCE
+
+    def properties(self):
+        return {**super().properties(), **_hardening_props(self.yield_stress)}
+
+
+@dataclass
+class FeFpJ2Plasticity(_Behavior):
+    """Finite-strain multiplicative (Fe.Fp) J2 plasticity, state ``be_bar`` + ``p``."""
+
+    yield_stress: Any = None
+
+    def __post_init__(self):
+        self.kind = DXM_FEFP_VOCE
+        self.finite_strain = True
+
+    def properties(self):
+        return {**super().properties(), **_hardening_props(self.yield_stress)}

@@ -1,0 +1,64 @@
+"""In-tree build of ``lib/libdxm_cuda.so`` with nvcc for sm_100a (the only target)."""
+
+import os
+import pathlib
+import shutil
+import subprocess
+
+ROOT = pathlib.Path(__file__).resolve().parent
+CSRC = ROOT / "csrc"
+LIB = ROOT / "lib" / "libdxm_cuda.so"
+
+NVCC_FLAGS = [
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-O3",
+    "-std=c++17",
+    # no fused multiply-add: every fp64 operation is individually rounded, in the order written,
+    # which is what makes kernel results bit-comparable with the CPU oracle
+    "-fmad=false",
+    "-Xcompiler",
+    "-fPIC",
+    "-shared",
+]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: cannot build libdxm_cuda.so")
+    return exe
+
+
+def sources():
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "dxm.h"]
+
+
+def needs_build():
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    return any(s.stat().st_mtime > t for s in sources())
+
+
+def build_library(force=False, verbose=False):
+    """Compile the CUDA library if it is missing or older than its sources."""
+    if not force and not needs_build():
+        return LIB
+    LIB.parent.mkdir(parents=True, exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "dxm_api.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,947 @@
+// libdxm_cuda.so -- C ABI (include/dxm.h) over the sm_100a constitutive-update kernels.
+// Host side only: handle / buffer management, the chunked host<->device pipeline, statistics.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dxm.h"
+#include "dxm_fefp.cuh"
+#include "dxm_layout.cuh"
+#include "dxm_small_strain.cuh"
+
+using namespace dxm;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(const std::string& msg) {
+  g_err = msg;
+  return -1;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                  std::to_string(__LINE__) + ")");                                            \
+    }                                                                                         \
+  } while (0)
+
+#define LAUNCH_CHECK()            \
+  do {                            \
+    g_launches.fetch_add(1);      \
+    CK(cudaGetLastError());       \
+  } while (0)
+
+constexpr int64_t kChunk = 1 << 19;  // points per pipeline chunk on the host path
+constexpr int kNProp = 6;
+const char* kPropNames[kNProp] = {"E", "nu", "sig0", "H", "sigu", "b"};
+
+struct Field {
+  const char* name;
+  int row;  // first SoA row inside a generation block
+  int dim;
+};
+
+}  // namespace
+
+struct dxm_handle {
+  int behaviour = 0, device = 0;
+  int64_t n = 0, ld = 0;
+  int ngrad = 0, nflux = 0, nisv = 0, nrows = 0, nct = 0;
+  std::vector<Field> fields;
+  double* gen[2] = {nullptr, nullptr};  // device SoA blocks [nrows][ld]
+  int i0 = 0;                           // gen[i0] is s0, gen[1-i0] is s1
+  bool s1_valid = false;                // false => s1 reads alias s0 (after update/revert)
+  double* ct = nullptr;                 // [nct][ld]
+  // properties
+  double uni[kNProp] = {0, 0, 0, 0, 0, 0};
+  bool set[kNProp] = {false, false, false, false, false, false};
+  bool perpoint = false;
+  double* pp = nullptr;  // [kNProp][ld]
+  // statistics
+  StatSlot* d_stats = nullptr;
+  StatSlot* h_stats = nullptr;  // pinned
+  dxm_stats last{};
+  bool stats_pending = false;
+  // streams / events
+  cudaStream_t stream = nullptr, own_stream = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr},
+              ev_packed[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> ev_k;  // kernel timing event pairs
+  int n_ev_used = 0;
+  // staging (device AoS), allocated lazily
+  int64_t chunk = 0;
+  double* d_in[2] = {nullptr, nullptr};
+  double* d_out[2] = {nullptr, nullptr};
+  // diagnostics
+  bool diag = false;
+  uint8_t *d_flag = nullptr, *d_fail = nullptr;
+  int32_t* d_iter = nullptr;
+  double* d_resid = nullptr;
+  int num_sms = 148;
+  int ppt = 2;
+  int minb = 2;
+  std::atomic<int> refs{1};
+};
+
+namespace {
+
+const Field* find_field(const dxm_handle* h, const char* name) {
+  for (const Field& f : h->fields)
+    if (std::strcmp(f.name, name) == 0) return &f;
+  return nullptr;
+}
+
+int set_device(const dxm_handle* h) {
+  CK(cudaSetDevice(h->device));
+  return 0;
+}
+
+double* field_ptr(dxm_handle* h, int gen, const Field* f, bool for_read) {
+  int g = gen == 0 ? h->i0 : 1 - h->i0;
+  if (gen == 1 && for_read && !h->s1_valid) g = h->i0;
+  return h->gen[g] + (int64_t)f->row * h->ld;
+}
+
+int grid_for(const void* kernel, int block, size_t smem, int num_sms, int64_t ntile) {
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t g = (int64_t)per_sm * num_sms;
+  if (g > ntile) g = ntile;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int launch_aos_to_soa(dxm_handle* h, cudaStream_t st, const double* src, int64_t rs, int c0,
+                      double* dst, int64_t d0, int64_t count, int D) {
+  if (count <= 0) return 0;
+  const size_t smem = (size_t)kTile * (D | 1) * sizeof(double);
+  const int64_t ntile = (count + kTile - 1) / kTile;
+  const int grid = (int)std::min<int64_t>(ntile, (int64_t)h->num_sms * 8);
+  aos_to_soa_kernel<<<grid, 256, smem, st>>>(src, rs, c0, dst, h->ld, d0, count, D);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_soa_to_aos(dxm_handle* h, cudaStream_t st, const double* src, int64_t s0, double* dst,
+                      int64_t rs, int c0, int64_t count, int D) {
+  if (count <= 0) return 0;
+  const size_t smem = (size_t)kTile * (D | 1) * sizeof(double);
+  const int64_t ntile = (count + kTile - 1) / kTile;
+  const int grid = (int)std::min<int64_t>(ntile, (int64_t)h->num_sms * 4);
+  soa_to_aos_kernel<<<grid, 256, smem, st>>>(src, h->ld, s0, dst, rs, c0, count, D);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int ensure_staging(dxm_handle* h) {
+  if (h->chunk) return 0;
+  h->chunk = std::min<int64_t>(kChunk, (h->n + 1) & ~int64_t(1));
+  if (h->chunk < 2) h->chunk = 2;
+  const int64_t nout = h->nflux + h->nisv + h->nct;
+  for (int s = 0; s < 2; ++s) {
+    CK(cudaMalloc(&h->d_in[s], sizeof(double) * h->chunk * h->ngrad));
+    CK(cudaMalloc(&h->d_out[s], sizeof(double) * h->chunk * nout));
+  }
+  return 0;
+}
+
+template <int HARD, bool PERPOINT, int PPT, bool DIAG, int MINB = 2>
+int launch_small_strain(dxm_handle* h, const SmallStrainArgs& a) {
+  const void* k = (const void*)dxm_small_strain_kernel<HARD, PERPOINT, PPT, DIAG, MINB>;
+  const int block = 256;
+  const int64_t ntile = (a.count + (int64_t)block * PPT - 1) / ((int64_t)block * PPT);
+  const int grid = grid_for(k, block, 0, h->num_sms, ntile);
+  dxm_small_strain_kernel<HARD, PERPOINT, PPT, DIAG, MINB><<<grid, block, 0, h->stream>>>(a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+template <int HARD, bool PERPOINT>
+int dispatch_small_strain2(dxm_handle* h, const SmallStrainArgs& a) {
+  // tuning knob (DXM_MINB: resident blocks per SM the register allocation targets) for the
+  // production kernel only; see profiles/ for the sweep that picked the defaults
+  if (HARD == HARD_GENERAL && !PERPOINT && !h->diag && h->minb != 2) {
+    if (h->ppt == 2) {
+      if (h->minb == 1) return launch_small_strain<HARD_GENERAL, false, 2, false, 1>(h, a);
+      if (h->minb == 3) return launch_small_strain<HARD_GENERAL, false, 2, false, 3>(h, a);
+    } else {
+      if (h->minb == 1) return launch_small_strain<HARD_GENERAL, false, 1, false, 1>(h, a);
+      if (h->minb == 3) return launch_small_strain<HARD_GENERAL, false, 1, false, 3>(h, a);
+      if (h->minb == 4) return launch_small_strain<HARD_GENERAL, false, 1, false, 4>(h, a);
+    }
+  }
+  if (h->ppt == 2) {
+    return h->diag ? launch_small_strain<HARD, PERPOINT, 2, true>(h, a)
+                   : launch_small_strain<HARD, PERPOINT, 2, false>(h, a);
+  }
+  return h->diag ? launch_small_strain<HARD, PERPOINT, 1, true>(h, a)
+                 : launch_small_strain<HARD, PERPOINT, 1, false>(h, a);
+}
+
+double prop(const dxm_handle* h, int i) {
+  if (i == 4 && !h->set[4]) return h->uni[2];  // sigu defaults to sig0 (no saturation term)
+  return h->uni[i];
+}
+
+// launches the constitutive kernel for points [start, start+count) on h->stream
+int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
+  (void)dt;  // rate-independent behaviours (the reference's FE path never passes dt: quadrature_map.py:321)
+  if (count <= 0) return 0;
+  double* s0 = h->gen[h->i0];
+  double* s1 = h->gen[1 - h->i0];
+  const int64_t ld = h->ld;
+  if (h->behaviour == DXM_FEFP_VOCE) {
+    FeFpArgs a{};
+    a.F = s1;
+    a.P = s1 + 9 * ld;
+    a.p = s1 + 18 * ld;
+    a.be = s1 + 19 * ld;
+    a.ct = h->ct;
+    a.F_old = s0;
+    a.p_old = s0 + 18 * ld;
+    a.be_old = s0 + 19 * ld;
+    a.ld = ld;
+    a.start = start;
+    a.count = count;
+    a.perpoint = h->perpoint;
+    const double E = prop(h, 0), nu = prop(h, 1);
+    a.E = E;
+    a.mu = E / 2 / (1 + nu);
+    a.kappa = E / (3 * (1 - 2 * nu));
+    a.sig0 = prop(h, 2);
+    a.H = prop(h, 3);
+    const double d = prop(h, 4) - prop(h, 2);
+    a.dsu = std::isfinite(d) ? d : 0.0;
+    a.b = prop(h, 5);
+    for (int i = 0; i < kNProp; ++i) a.pp[i] = h->pp ? h->pp + (int64_t)i * ld : nullptr;
+    a.stats = h->d_stats;
+    a.d_flag = h->d_flag;
+    a.d_iter = h->d_iter;
+    a.d_resid = h->d_resid;
+    a.d_fail = h->d_fail;
+    return launch_fefp(a, h->diag, h->num_sms, h->stream, &g_launches);
+  }
+  SmallStrainArgs a{};
+  a.eps = s1;
+  a.sig = s1 + 6 * ld;
+  a.p = s1 + 12 * ld;
+  a.epsp = s1 + 13 * ld;
+  a.ct = h->ct;
+  a.eps_old = s0;
+  a.sig_old = s0 + 6 * ld;
+  a.p_old = s0 + 12 * ld;
+  a.epsp_old = s0 + 13 * ld;
+  a.ld = ld;
+  a.start = start;
+  a.count = count;
+  const double E = prop(h, 0), nu = prop(h, 1);
+  a.lam = E * nu / (1 + nu) / (1 - 2 * nu);
+  a.mu = E / 2 / (1 + nu);
+  a.sig0 = prop(h, 2);
+  a.H = prop(h, 3);
+  const double d = prop(h, 4) - prop(h, 2);
+  a.dsu = std::isfinite(d) ? d : 0.0;
+  a.b = prop(h, 5);
+  if (h->pp) {
+    a.pE = h->pp;
+    a.pnu = h->pp + ld;
+    a.psig0 = h->pp + 2 * ld;
+    a.pH = h->pp + 3 * ld;
+    a.psigu = h->pp + 4 * ld;
+    a.pb = h->pp + 5 * ld;
+  }
+  a.stats = h->d_stats;
+  a.d_flag = h->d_flag;
+  a.d_iter = h->d_iter;
+  a.d_resid = h->d_resid;
+  a.d_fail = h->d_fail;
+  if (h->perpoint) {
+    switch (h->behaviour) {
+      case DXM_ELASTIC: return dispatch_small_strain2<HARD_NONE, true>(h, a);
+      case DXM_J2_LINEAR: return dispatch_small_strain2<HARD_LINEAR, true>(h, a);
+      default: return dispatch_small_strain2<HARD_GENERAL, true>(h, a);
+    }
+  }
+  switch (h->behaviour) {
+    case DXM_ELASTIC: return dispatch_small_strain2<HARD_NONE, false>(h, a);
+    case DXM_J2_LINEAR: return dispatch_small_strain2<HARD_LINEAR, false>(h, a);
+    default: return dispatch_small_strain2<HARD_GENERAL, false>(h, a);
+  }
+}
+
+int next_event_pair(dxm_handle* h, cudaEvent_t** pair) {
+  if ((size_t)h->n_ev_used + 2 > h->ev_k.size()) {
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    h->ev_k.push_back(a);
+    h->ev_k.push_back(b);
+  }
+  *pair = &h->ev_k[h->n_ev_used];
+  h->n_ev_used += 2;
+  return 0;
+}
+
+int timed_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
+  cudaEvent_t* ev = nullptr;
+  if (next_event_pair(h, &ev)) return -1;
+  CK(cudaEventRecord(ev[0], h->stream));
+  if (launch_update(h, start, count, dt)) return -1;
+  CK(cudaEventRecord(ev[1], h->stream));
+  return 0;
+}
+
+int finish_stats(dxm_handle* h) {
+  if (!h->stats_pending) return 0;
+  CK(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(StatSlot) * kStatSlots, cudaMemcpyDeviceToHost,
+                     h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  dxm_stats s{};
+  s.n_points = h->last.n_points;
+  unsigned long long rb = 0;
+  for (int i = 0; i < kStatSlots; ++i) {
+    s.n_plastic += (int64_t)h->h_stats[i].n_plastic;
+    s.n_fail += (int64_t)h->h_stats[i].n_fail;
+    s.max_iter = std::max<int64_t>(s.max_iter, (int64_t)h->h_stats[i].max_iter);
+    rb = std::max(rb, h->h_stats[i].max_resid_bits);
+  }
+  std::memcpy(&s.max_residual, &rb, sizeof(double));
+  double ms = 0;
+  for (int i = 0; i + 1 < h->n_ev_used; i += 2) {
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, h->ev_k[i], h->ev_k[i + 1]));
+    ms += t;
+  }
+  s.kernel_ms = ms;
+  h->last = s;
+  h->stats_pending = false;
+  return 0;
+}
+
+}  // namespace
+
+// ---- DLPack (ABI of dlpack.h v0.8; redeclared here, no external headers) -----------------------
+extern "C" {
+typedef struct {
+  int32_t device_type;
+  int32_t device_id;
+} DxmDLDevice;
+typedef struct {
+  uint8_t code;
+  uint8_t bits;
+  uint16_t lanes;
+} DxmDLDataType;
+typedef struct {
+  void* data;
+  DxmDLDevice device;
+  int32_t ndim;
+  DxmDLDataType dtype;
+  int64_t* shape;
+  int64_t* strides;
+  uint64_t byte_offset;
+} DxmDLTensor;
+typedef struct DxmDLManagedTensor {
+  DxmDLTensor dl_tensor;
+  void* manager_ctx;
+  void (*deleter)(struct DxmDLManagedTensor* self);
+} DxmDLManagedTensor;
+}
+
+namespace {
+struct DlCtx {
+  dxm_handle* h;
+  int64_t shape[2];
+  int64_t strides[2];
+};
+
+void release_handle(dxm_handle* h);
+
+void dxm_dl_deleter(DxmDLManagedTensor* self) {
+  DlCtx* ctx = static_cast<DlCtx*>(self->manager_ctx);
+  release_handle(ctx->h);
+  delete ctx;
+  delete self;
+}
+
+void free_handle(dxm_handle* h) {
+  cudaSetDevice(h->device);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  for (int g = 0; g < 2; ++g) cudaFree(h->gen[g]);
+  cudaFree(h->ct);
+  cudaFree(h->pp);
+  cudaFree(h->d_stats);
+  cudaFreeHost(h->h_stats);
+  for (int s = 0; s < 2; ++s) {
+    cudaFree(h->d_in[s]);
+    cudaFree(h->d_out[s]);
+    if (h->ev_in[s]) cudaEventDestroy(h->ev_in[s]);
+    if (h->ev_in_free[s]) cudaEventDestroy(h->ev_in_free[s]);
+    if (h->ev_packed[s]) cudaEventDestroy(h->ev_packed[s]);
+    if (h->ev_out_free[s]) cudaEventDestroy(h->ev_out_free[s]);
+  }
+  for (cudaEvent_t e : h->ev_k) cudaEventDestroy(e);
+  cudaFree(h->d_flag);
+  cudaFree(h->d_fail);
+  cudaFree(h->d_iter);
+  cudaFree(h->d_resid);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
+  delete h;
+}
+
+void release_handle(dxm_handle* h) {
+  if (h->refs.fetch_sub(1) == 1) free_handle(h);
+}
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* dxm_last_error(void) { return g_err.c_str(); }
+const char* dxm_version(void) { return "dxm-b200 0.1 (sm_100a, fp64, -fmad=false)"; }
+int64_t dxm_launch_count(void) { return g_launches.load(); }
+
+int dxm_create(int behaviour, int device, int64_t n, dxm_handle** out) {
+  if (!out) return fail("dxm_create: out is NULL");
+  *out = nullptr;
+  if (n <= 0) return fail("dxm_create: n must be positive");
+  if (behaviour < DXM_ELASTIC || behaviour > DXM_FEFP_VOCE)
+    return fail("dxm_create: unknown behaviour " + std::to_string(behaviour));
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev)
+    return fail("dxm_create: no CUDA device " + std::to_string(device) +
+                " (this library has no CPU fallback)");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(std::string("dxm_create: device is sm_") + std::to_string(prop.major) +
+                std::to_string(prop.minor) + ", this library is built for sm_100a only");
+  dxm_handle* h = new dxm_handle();
+  h->behaviour = behaviour;
+  h->device = device;
+  h->n = n;
+  h->ld = (n + 63) & ~int64_t(63);
+  h->num_sms = prop.multiProcessorCount;
+  const char* env = std::getenv("DXM_PPT");
+  h->ppt = (env && std::atoi(env) == 1) ? 1 : 2;
+  env = std::getenv("DXM_MINB");
+  h->minb = env ? std::atoi(env) : 2;
+  if (behaviour == DXM_FEFP_VOCE) {
+    h->ngrad = 9;
+    h->nflux = 9;
+    h->nisv = 7;
+    h->fields = {{"F", 0, 9}, {"PK1", 9, 9}, {"p", 18, 1}, {"be_bar", 19, 6}};
+  } else {
+    h->ngrad = 6;
+    h->nflux = 6;
+    h->nisv = 7;
+    h->fields = {{"strain", 0, 6}, {"stress", 6, 6}, {"p", 12, 1}, {"epsp", 13, 6}};
+  }
+  h->nrows = h->ngrad + h->nflux + h->nisv;
+  h->nct = h->nflux * h->ngrad;
+  auto bail = [&](int) {
+    std::string keep = g_err;
+    free_handle(h);
+    g_err = keep;
+    return -1;
+  };
+#define CKH(call)                                                                    \
+  do {                                                                               \
+    cudaError_t e_ = (call);                                                         \
+    if (e_ != cudaSuccess) {                                                         \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (dxm_create)"; \
+      return bail(0);                                                                \
+    }                                                                                \
+  } while (0)
+  const size_t gen_bytes = sizeof(double) * h->nrows * h->ld;
+  for (int g = 0; g < 2; ++g) {
+    CKH(cudaMalloc(&h->gen[g], gen_bytes));
+    CKH(cudaMemset(h->gen[g], 0, gen_bytes));
+  }
+  CKH(cudaMalloc(&h->ct, sizeof(double) * h->nct * h->ld));
+  CKH(cudaMemset(h->ct, 0, sizeof(double) * h->nct * h->ld));
+  CKH(cudaMalloc(&h->d_stats, sizeof(StatSlot) * kStatSlots));
+  CKH(cudaMemset(h->d_stats, 0, sizeof(StatSlot) * kStatSlots));
+  CKH(cudaMallocHost(&h->h_stats, sizeof(StatSlot) * kStatSlots));
+  CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CKH(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+  CKH(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  for (int s = 0; s < 2; ++s) {
+    CKH(cudaEventCreateWithFlags(&h->ev_in[s], cudaEventDisableTiming));
+    CKH(cudaEventCreateWithFlags(&h->ev_in_free[s], cudaEventDisableTiming));
+    CKH(cudaEventCreateWithFlags(&h->ev_packed[s], cudaEventDisableTiming));
+    CKH(cudaEventCreateWithFlags(&h->ev_out_free[s], cudaEventDisableTiming));
+  }
+  if (behaviour == DXM_FEFP_VOCE) {
+    // virgin finite-strain state: F = I, be_bar = I (jaxmat init_state; demo
+    // finite_strain_elastoplasticity.py:181 sets be_bar to the identity explicitly)
+    for (int g = 0; g < 2; ++g) {
+      for (int r : {0, 1, 2, 19, 20, 21}) {
+        fill_kernel<<<h->num_sms, 256, 0, h->stream>>>(h->gen[g] + (int64_t)r * h->ld, h->ld, 1.0);
+        g_launches.fetch_add(1);
+      }
+    }
+    CKH(cudaGetLastError());
+    CKH(cudaStreamSynchronize(h->stream));
+  }
+#undef CKH
+  *out = h;
+  return 0;
+}
+
+int dxm_destroy(dxm_handle* h) {
+  if (!h) return 0;
+  release_handle(h);
+  return 0;
+}
+
+int dxm_set_stream(dxm_handle* h, void* cuda_stream) {
+  if (!h) return fail("dxm_set_stream: NULL handle");
+  if (set_device(h)) return -1;
+  CK(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return 0;
+}
+
+int64_t dxm_ld(const dxm_handle* h) { return h ? h->ld : -1; }
+int64_t dxm_npoints(const dxm_handle* h) { return h ? h->n : -1; }
+
+int dxm_field_dim(const dxm_handle* h, const char* field) {
+  if (!h || !field) return -1;
+  if (std::strcmp(field, "Ct") == 0) return h->nct;
+  const Field* f = find_field(h, field);
+  return f ? f->dim : -1;
+}
+
+int dxm_set_property(dxm_handle* h, const char* name, const double* v, int64_t count, int mem) {
+  if (!h || !name || !v) return fail("dxm_set_property: NULL argument");
+  int idx = -1;
+  for (int i = 0; i < kNProp; ++i)
+    if (std::strcmp(name, kPropNames[i]) == 0) idx = i;
+  if (idx < 0) return fail(std::string("dxm_set_property: unknown property '") + name + "'");
+  if (count != 1 && count != h->n)
+    return fail(std::string("dxm_set_property: '") + name + "' needs 1 or n=" +
+                std::to_string(h->n) + " values, got " + std::to_string(count));
+  if (set_device(h)) return -1;
+  if (count == 1 && !h->perpoint) {
+    double val;
+    if (mem == DXM_MEM_HOST)
+      val = v[0];
+    else
+      CK(cudaMemcpy(&val, v, sizeof(double), cudaMemcpyDeviceToHost));
+    h->uni[idx] = val;
+    h->set[idx] = true;
+    return 0;
+  }
+  // switch to (or stay in) per-point mode: all six rows live on the device
+  if (!h->pp) {
+    CK(cudaMalloc(&h->pp, sizeof(double) * kNProp * h->ld));
+    for (int i = 0; i < kNProp; ++i) {
+      fill_kernel<<<h->num_sms, 256, 0, h->stream>>>(h->pp + (int64_t)i * h->ld, h->ld, prop(h, i));
+      LAUNCH_CHECK();
+    }
+    h->perpoint = true;
+  }
+  double* row = h->pp + (int64_t)idx * h->ld;
+  if (count == 1) {
+    double val;
+    if (mem == DXM_MEM_HOST)
+      val = v[0];
+    else
+      CK(cudaMemcpy(&val, v, sizeof(double), cudaMemcpyDeviceToHost));
+    h->uni[idx] = val;
+    fill_kernel<<<h->num_sms, 256, 0, h->stream>>>(row, h->ld, val);
+    LAUNCH_CHECK();
+  } else {
+    CK(cudaMemcpyAsync(row, v, sizeof(double) * h->n,
+                       mem == DXM_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                       h->stream));
+  }
+  // an unset sigu follows sig0 (also per point)
+  if (idx == 2 && !h->set[4]) {
+    CK(cudaMemcpyAsync(h->pp + 4 * h->ld, h->pp + 2 * h->ld, sizeof(double) * h->ld,
+                       cudaMemcpyDeviceToDevice, h->stream));
+  }
+  h->set[idx] = true;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int dxm_set_state(dxm_handle* h, int gen, const char* field, const double* v, int mem) {
+  if (!h || !field || !v) return fail("dxm_set_state: NULL argument");
+  if (gen != 0 && gen != 1) return fail("dxm_set_state: gen must be 0 or 1");
+  const Field* f = find_field(h, field);
+  if (!f) return fail(std::string("dxm_set_state: unknown field '") + field + "'");
+  if (set_device(h)) return -1;
+  if (gen == 1 && !h->s1_valid) {  // materialise the alias before a partial write
+    CK(cudaMemcpyAsync(h->gen[1 - h->i0], h->gen[h->i0], sizeof(double) * h->nrows * h->ld,
+                       cudaMemcpyDeviceToDevice, h->stream));
+    h->s1_valid = true;
+  }
+  double* dst = field_ptr(h, gen, f, false);
+  if (mem == DXM_MEM_RESIDENT) return fail("dxm_set_state: RESIDENT is not a source");
+  if (mem == DXM_MEM_DEVICE) {
+    if (launch_aos_to_soa(h, h->stream, v, f->dim, 0, dst, 0, h->n, f->dim)) return -1;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  if (ensure_staging(h)) return -1;
+  const int64_t rows_per = (h->chunk * (h->nflux + h->nisv + h->nct)) / f->dim;
+  for (int64_t s = 0; s < h->n; s += rows_per) {
+    const int64_t m = std::min(rows_per, h->n - s);
+    CK(cudaMemcpyAsync(h->d_out[0], v + s * f->dim, sizeof(double) * m * f->dim,
+                       cudaMemcpyHostToDevice, h->stream));
+    if (launch_aos_to_soa(h, h->stream, h->d_out[0], f->dim, 0, dst, s, m, f->dim)) return -1;
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+int dxm_get_state(dxm_handle* h, int gen, const char* field, double* out, int mem) {
+  if (!h || !field || !out) return fail("dxm_get_state: NULL argument");
+  if (gen != 0 && gen != 1) return fail("dxm_get_state: gen must be 0 or 1");
+  if (set_device(h)) return -1;
+  const double* src;
+  int dim;
+  if (std::strcmp(field, "Ct") == 0) {
+    src = h->ct;
+    dim = h->nct;
+  } else {
+    const Field* f = find_field(h, field);
+    if (!f) return fail(std::string("dxm_get_state: unknown field '") + field + "'");
+    src = field_ptr(h, gen, f, true);
+    dim = f->dim;
+  }
+  if (mem == DXM_MEM_RESIDENT) return fail("dxm_get_state: RESIDENT is not a destination");
+  if (mem == DXM_MEM_DEVICE) {
+    if (launch_soa_to_aos(h, h->stream, src, 0, out, dim, 0, h->n, dim)) return -1;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  if (ensure_staging(h)) return -1;
+  const int64_t rows_per = (h->chunk * (h->nflux + h->nisv + h->nct)) / dim;
+  for (int64_t s = 0; s < h->n; s += rows_per) {
+    const int64_t m = std::min(rows_per, h->n - s);
+    if (launch_soa_to_aos(h, h->stream, src, s, h->d_out[0], dim, 0, m, dim)) return -1;
+    CK(cudaMemcpyAsync(out + s * dim, h->d_out[0], sizeof(double) * m * dim, cudaMemcpyDeviceToHost,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+int dxm_device_ptr(dxm_handle* h, int gen, const char* field, double** ptr) {
+  if (!h || !field || !ptr) return fail("dxm_device_ptr: NULL argument");
+  if (std::strcmp(field, "Ct") == 0) {
+    *ptr = h->ct;
+    return 0;
+  }
+  const Field* f = find_field(h, field);
+  if (!f) return fail(std::string("dxm_device_ptr: unknown field '") + field + "'");
+  // the gradient buffer of s1 is writable by the caller even while s1 aliases s0
+  const bool is_grad = f->row == 0;
+  *ptr = field_ptr(h, gen, f, !(gen == 1 && is_grad));
+  return 0;
+}
+
+int dxm_export_dlpack(dxm_handle* h, int gen, const char* field, void** out) {
+  if (!out) return fail("dxm_export_dlpack: out is NULL");
+  double* p = nullptr;
+  if (dxm_device_ptr(h, gen, field, &p)) return -1;
+  const int dim = dxm_field_dim(h, field);
+  DlCtx* ctx = new DlCtx{h, {dim, h->n}, {h->ld, 1}};
+  DxmDLManagedTensor* t = new DxmDLManagedTensor();
+  t->dl_tensor.data = p;
+  t->dl_tensor.device = {2 /* kDLCUDA */, h->device};
+  t->dl_tensor.ndim = 2;
+  t->dl_tensor.dtype = {2 /* kDLFloat */, 64, 1};
+  t->dl_tensor.shape = ctx->shape;
+  t->dl_tensor.strides = ctx->strides;
+  t->dl_tensor.byte_offset = 0;
+  t->manager_ctx = ctx;
+  t->deleter = dxm_dl_deleter;
+  h->refs.fetch_add(1);
+  *out = t;
+  return 0;
+}
+
+int dxm_last_stats(dxm_handle* h, dxm_stats* stats) {
+  if (!h || !stats) return fail("dxm_last_stats: NULL argument");
+  if (set_device(h)) return -1;
+  if (finish_stats(h)) return -1;
+  *stats = h->last;
+  return 0;
+}
+
+int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double* flux, double* isv,
+                  double* ct, int out_mem, dxm_stats* stats) {
+  if (!h) return fail("dxm_integrate: NULL handle");
+  if (set_device(h)) return -1;
+  if (!h->set[0] || !h->set[1]) return fail("dxm_integrate: properties E and nu must be set");
+  if (h->behaviour != DXM_ELASTIC && !h->set[2])
+    return fail("dxm_integrate: property sig0 must be set");
+  if (mem != DXM_MEM_RESIDENT && !grad) return fail("dxm_integrate: grad is NULL");
+  if (finish_stats(h)) return -1;  // drain a previous asynchronous call
+  CK(cudaMemsetAsync(h->d_stats, 0, sizeof(StatSlot) * kStatSlots, h->stream));
+  h->n_ev_used = 0;
+  h->last = dxm_stats{};
+  h->last.n_points = h->n;
+  double* s1 = h->gen[1 - h->i0];
+  const int64_t ld = h->ld, n = h->n;
+  const int isv_row = h->ngrad + h->nflux;
+  const bool any_out = flux || isv || ct;
+
+  if (mem == DXM_MEM_RESIDENT || mem == DXM_MEM_DEVICE) {
+    if (mem == DXM_MEM_DEVICE)
+      if (launch_aos_to_soa(h, h->stream, grad, h->ngrad, 0, s1, 0, n, h->ngrad)) return -1;
+    if (timed_update(h, 0, n, dt)) return -1;
+    h->s1_valid = true;
+    if (any_out) {
+      if (out_mem == DXM_MEM_DEVICE) {
+        if (flux && launch_soa_to_aos(h, h->stream, s1 + (int64_t)h->ngrad * ld, 0, flux, h->nflux,
+                                      0, n, h->nflux))
+          return -1;
+        if (isv && launch_soa_to_aos(h, h->stream, s1 + (int64_t)isv_row * ld, 0, isv, h->nisv, 0,
+                                     n, h->nisv))
+          return -1;
+        if (ct && launch_soa_to_aos(h, h->stream, h->ct, 0, ct, h->nct, 0, n, h->nct)) return -1;
+      } else if (out_mem == DXM_MEM_HOST) {
+        h->stats_pending = true;
+        if (finish_stats(h)) return -1;
+        const dxm_stats keep = h->last;
+        if (flux && dxm_get_state(h, 1, h->fields[1].name, flux, DXM_MEM_HOST)) return -1;
+        if (isv) {
+          // isv = [p | second field] rows are contiguous in the SoA block: one (n, nisv) gather
+          if (ensure_staging(h)) return -1;
+          const int64_t rows_per = (h->chunk * (h->nflux + h->nisv + h->nct)) / h->nisv;
+          for (int64_t s = 0; s < n; s += rows_per) {
+            const int64_t m = std::min(rows_per, n - s);
+            if (launch_soa_to_aos(h, h->stream, s1 + (int64_t)isv_row * ld, s, h->d_out[0], h->nisv,
+                                  0, m, h->nisv))
+              return -1;
+            CK(cudaMemcpyAsync(isv + s * h->nisv, h->d_out[0], sizeof(double) * m * h->nisv,
+                               cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+          }
+        }
+        if (ct && dxm_get_state(h, 1, "Ct", ct, DXM_MEM_HOST)) return -1;
+        h->last = keep;
+      }
+    }
+  } else if (mem == DXM_MEM_HOST) {
+    if (any_out && out_mem != DXM_MEM_HOST)
+      return fail("dxm_integrate: host gradients require host outputs");
+    if (ensure_staging(h)) return -1;
+    // 3-stage pipeline over chunks: H2D (s_in) | transpose + update + pack (stream) | D2H (s_out)
+    const int64_t CH = h->chunk;
+    const int nf = h->nflux, ni = h->nisv, nc = h->nct;
+    // make the copy streams wait for whatever precedes on the compute stream
+    CK(cudaEventRecord(h->ev_in_free[0], h->stream));
+    CK(cudaEventRecord(h->ev_in_free[1], h->stream));
+    CK(cudaEventRecord(h->ev_out_free[0], h->stream));
+    CK(cudaEventRecord(h->ev_out_free[1], h->stream));
+    int64_t c = 0;
+    for (int64_t s = 0; s < n; s += CH, ++c) {
+      const int64_t m = std::min(CH, n - s);
+      const int b = (int)(c & 1);
+      CK(cudaStreamWaitEvent(h->s_in, h->ev_in_free[b], 0));
+      CK(cudaMemcpyAsync(h->d_in[b], grad + s * h->ngrad, sizeof(double) * m * h->ngrad,
+                         cudaMemcpyHostToDevice, h->s_in));
+      CK(cudaEventRecord(h->ev_in[b], h->s_in));
+      CK(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
+      if (launch_aos_to_soa(h, h->stream, h->d_in[b], h->ngrad, 0, s1, s, m, h->ngrad)) return -1;
+      CK(cudaEventRecord(h->ev_in_free[b], h->stream));
+      if (timed_update(h, s, m, dt)) return -1;
+      if (any_out) {
+        CK(cudaStreamWaitEvent(h->stream, h->ev_out_free[b], 0));
+        double* o = h->d_out[b];
+        if (flux && launch_soa_to_aos(h, h->stream, s1 + (int64_t)h->ngrad * ld, s, o, nf, 0, m, nf))
+          return -1;
+        if (isv && launch_soa_to_aos(h, h->stream, s1 + (int64_t)isv_row * ld, s, o + CH * nf, ni, 0,
+                                     m, ni))
+          return -1;
+        if (ct && launch_soa_to_aos(h, h->stream, h->ct, s, o + CH * (nf + ni), nc, 0, m, nc))
+          return -1;
+        CK(cudaEventRecord(h->ev_packed[b], h->stream));
+        CK(cudaStreamWaitEvent(h->s_out, h->ev_packed[b], 0));
+        if (flux)
+          CK(cudaMemcpyAsync(flux + s * nf, o, sizeof(double) * m * nf, cudaMemcpyDeviceToHost,
+                             h->s_out));
+        if (isv)
+          CK(cudaMemcpyAsync(isv + s * ni, o + CH * nf, sizeof(double) * m * ni,
+                             cudaMemcpyDeviceToHost, h->s_out));
+        if (ct)
+          CK(cudaMemcpyAsync(ct + s * nc, o + CH * (nf + ni), sizeof(double) * m * nc,
+                             cudaMemcpyDeviceToHost, h->s_out));
+        CK(cudaEventRecord(h->ev_out_free[b], h->s_out));
+      }
+    }
+    h->s1_valid = true;
+    CK(cudaStreamSynchronize(h->s_out));
+    CK(cudaStreamSynchronize(h->stream));
+  } else {
+    return fail("dxm_integrate: bad mem kind");
+  }
+  h->stats_pending = true;
+  if (!stats) return 0;  // asynchronous: fetch later with dxm_last_stats
+  if (finish_stats(h)) return -1;
+  *stats = h->last;
+  return (int)std::min<int64_t>(h->last.n_fail, 0x7fffffff);
+}
+
+int dxm_update(dxm_handle* h) {
+  if (!h) return fail("dxm_update: NULL handle");
+  if (h->s1_valid) {
+    h->i0 = 1 - h->i0;  // s0 <- s1 by swapping generations; s1 now aliases s0 until rewritten
+    h->s1_valid = false;
+  }
+  return 0;
+}
+
+int dxm_revert(dxm_handle* h) {
+  if (!h) return fail("dxm_revert: NULL handle");
+  h->s1_valid = false;  // s1 <- s0
+  return 0;
+}
+
+int dxm_enable_diagnostics(dxm_handle* h, int on) {
+  if (!h) return fail("dxm_enable_diagnostics: NULL handle");
+  if (set_device(h)) return -1;
+  if (on && !h->d_flag) {
+    CK(cudaMalloc(&h->d_flag, h->ld));
+    CK(cudaMalloc(&h->d_fail, h->ld));
+    CK(cudaMalloc(&h->d_iter, sizeof(int32_t) * h->ld));
+    CK(cudaMalloc(&h->d_resid, sizeof(double) * h->ld));
+    CK(cudaMemset(h->d_flag, 0, h->ld));
+    CK(cudaMemset(h->d_fail, 0, h->ld));
+    CK(cudaMemset(h->d_iter, 0, sizeof(int32_t) * h->ld));
+    CK(cudaMemset(h->d_resid, 0, sizeof(double) * h->ld));
+  }
+  h->diag = on != 0;
+  return 0;
+}
+
+int dxm_get_diagnostics(dxm_handle* h, uint8_t* flag, int32_t* n_iter, double* resid,
+                        uint8_t* failed) {
+  if (!h) return fail("dxm_get_diagnostics: NULL handle");
+  if (!h->d_flag) return fail("dxm_get_diagnostics: diagnostics were never enabled");
+  if (set_device(h)) return -1;
+  CK(cudaStreamSynchronize(h->stream));
+  if (flag) CK(cudaMemcpy(flag, h->d_flag, h->n, cudaMemcpyDeviceToHost));
+  if (failed) CK(cudaMemcpy(failed, h->d_fail, h->n, cudaMemcpyDeviceToHost));
+  if (n_iter) CK(cudaMemcpy(n_iter, h->d_iter, sizeof(int32_t) * h->n, cudaMemcpyDeviceToHost));
+  if (resid) CK(cudaMemcpy(resid, h->d_resid, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int dxm_synth_gradients(dxm_handle* h, int recipe, uint64_t seed, double amp, int k, int K,
+                        int64_t start) {
+  if (!h) return fail("dxm_synth_gradients: NULL handle");
+  if (recipe != 0 && recipe != 1) return fail("dxm_synth_gradients: recipe must be 0 or 1");
+  if ((recipe == 0) != (h->ngrad == 6))
+    return fail("dxm_synth_gradients: recipe does not match the behaviour's gradient");
+  if (K <= 0) return fail("dxm_synth_gradients: K must be positive");
+  if (set_device(h)) return -1;
+  const double kfrac = (double)k / (double)K;
+  synth_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->gen[1 - h->i0], h->ld, h->n, h->ngrad,
+                                                       recipe, seed, amp, kfrac, start);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int dxm_host_alloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes < 0) return fail("dxm_host_alloc: bad argument");
+  CK(cudaMallocHost(ptr, (size_t)(bytes ? bytes : 1)));
+  return 0;
+}
+
+int dxm_host_free(void* ptr) {
+  if (ptr) CK(cudaFreeHost(ptr));
+  return 0;
+}
+
+int dxm_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail("dxm_fp64_peak: NULL argument");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  CK(cudaGetDeviceProperties(&prop, device));
+  double* d = nullptr;
+  CK(cudaMalloc(&d, 8));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  const int iters = 1 << 15, block = 256, grid = prop.multiProcessorCount * 8;
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(a));
+    fp64_fma_kernel<<<grid, block>>>(d, iters, 1.0);
+    LAUNCH_CHECK();
+    CK(cudaEventRecord(b));
+    CK(cudaEventSynchronize(b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    const double fl = 2.0 * 8.0 * iters * (double)block * grid;
+    best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  *tflops = best;
+  return 0;
+}
+
+int dxm_copy_peak(int device, int64_t bytes, double* gbs) {
+  if (!gbs || bytes < 16) return fail("dxm_copy_peak: bad argument");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  CK(cudaGetDeviceProperties(&prop, device));
+  double2 *s = nullptr, *d = nullptr;
+  CK(cudaMalloc(&s, bytes));
+  CK(cudaMalloc(&d, bytes));
+  CK(cudaMemset(s, 0, bytes));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  double best = 0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CK(cudaEventRecord(a));
+    copy_kernel<<<prop.multiProcessorCount * 16, 256>>>(s, d, bytes / 16);
+    LAUNCH_CHECK();
+    CK(cudaEventRecord(b));
+    CK(cudaEventSynchronize(b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    best = std::max(best, 2.0 * bytes / (ms * 1e-3) / 1e9);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(s);
+  cudaFree(d);
+  *gbs = best;
+  return 0;
+}
+
+}  // extern "C"
+
+namespace dxm {
+int launch_fefp(const FeFpArgs&, bool, int, cudaStream_t, std::atomic<long long>*) {
+  g_err = "FeFp kernel not built yet";
+  return -1;
+}
+}  // namespace dxm

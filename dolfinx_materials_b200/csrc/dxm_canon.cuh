@@ -1,0 +1,122 @@
+// Canonical fp64 building blocks.  The whole library is compiled with -fmad=false: every
+// expression below is a sequence of correctly rounded IEEE-754 operations in a fixed order, which
+// is what makes the kernels bit-comparable with the CPU oracle (oracle/canon.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dxm {
+
+constexpr double kLog2e = 1.4426950408889634;
+constexpr double kLn2Hi = 6.93147180369123816490e-01;
+constexpr double kLn2Lo = 1.90821492927058770002e-10;
+constexpr double kExpClamp = 700.0;
+
+// exp(x): Cody-Waite reduction, degree-13 Horner (mul + add, never fused), exact 2^k scaling.
+__device__ __forceinline__ double exp_c(double x) {
+  const bool inr = (x >= -kExpClamp) && (x <= kExpClamp);
+  const double xs = inr ? x : 0.0;
+  const double k = rint(xs * kLog2e);
+  const double r = (xs - k * kLn2Hi) - k * kLn2Lo;
+  double y = 1.0 / 6227020800.0;
+  y = y * r + 1.0 / 479001600.0;
+  y = y * r + 1.0 / 39916800.0;
+  y = y * r + 1.0 / 3628800.0;
+  y = y * r + 1.0 / 362880.0;
+  y = y * r + 1.0 / 40320.0;
+  y = y * r + 1.0 / 5040.0;
+  y = y * r + 1.0 / 720.0;
+  y = y * r + 1.0 / 120.0;
+  y = y * r + 1.0 / 24.0;
+  y = y * r + 1.0 / 6.0;
+  y = y * r + 0.5;
+  y = y * r + 1.0;
+  y = y * r + 1.0;
+  // |k| <= 1010 and y in [0.7, 1.5]: 2^k is a normal double and the product is exact
+  const int ki = (int)k;
+  y = y * __hiloint2double((ki + 1023) << 20, 0);
+  if (x < -kExpClamp) y = 0.0;
+  if (x > kExpClamp) y = __longlong_as_double(0x7ff0000000000000LL);
+  if (x != x) y = x;
+  return y;
+}
+
+// streaming (evict-first) vector loads / stores of PPT consecutive points
+template <int PPT>
+__device__ __forceinline__ void ldv(const double* __restrict__ p, double (&v)[PPT]);
+template <>
+__device__ __forceinline__ void ldv<1>(const double* __restrict__ p, double (&v)[1]) {
+  v[0] = __ldcs(p);
+}
+template <>
+__device__ __forceinline__ void ldv<2>(const double* __restrict__ p, double (&v)[2]) {
+  const double2 t = __ldcs(reinterpret_cast<const double2*>(p));
+  v[0] = t.x;
+  v[1] = t.y;
+}
+template <int PPT>
+__device__ __forceinline__ void stv(double* __restrict__ p, const double (&v)[PPT]);
+template <>
+__device__ __forceinline__ void stv<1>(double* __restrict__ p, const double (&v)[1]) {
+  __stcs(p, v[0]);
+}
+template <>
+__device__ __forceinline__ void stv<2>(double* __restrict__ p, const double (&v)[2]) {
+  __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[1]));
+}
+
+// ---- per-block statistics -------------------------------------------------------------------
+constexpr int kStatSlots = 32;  // atomics are spread over 32 slots, summed on the host
+struct StatSlot {
+  unsigned long long n_plastic, n_fail, max_iter, max_resid_bits;
+};
+
+struct PointStats {
+  unsigned n_plastic = 0, n_fail = 0, max_iter = 0;
+  double max_resid = 0.0;
+};
+
+__device__ __forceinline__ void block_reduce_stats(const PointStats& s, StatSlot* slots) {
+  unsigned np = __reduce_add_sync(0xffffffffu, s.n_plastic);
+  unsigned nf = __reduce_add_sync(0xffffffffu, s.n_fail);
+  unsigned mi = __reduce_max_sync(0xffffffffu, s.max_iter);
+  // residuals are >= 0 (or NaN-free by construction): order of doubles == order of their bits
+  unsigned long long rb = (unsigned long long)__double_as_longlong(s.max_resid);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, rb, o);
+    rb = other > rb ? other : rb;
+  }
+  __shared__ unsigned long long sh[4][32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    sh[0][w] = np;
+    sh[1][w] = nf;
+    sh[2][w] = mi;
+    sh[3][w] = rb;
+  }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    unsigned long long a = l < nw ? sh[0][l] : 0ull, b = l < nw ? sh[1][l] : 0ull,
+                       c = l < nw ? sh[2][l] : 0ull, d = l < nw ? sh[3][l] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+      unsigned long long c2 = __shfl_xor_sync(0xffffffffu, c, o);
+      c = c2 > c ? c2 : c;
+      unsigned long long d2 = __shfl_xor_sync(0xffffffffu, d, o);
+      d = d2 > d ? d2 : d;
+    }
+    if (l == 0) {
+      StatSlot* s2 = slots + (blockIdx.x % kStatSlots);
+      if (a) atomicAdd(&s2->n_plastic, a);
+      if (b) atomicAdd(&s2->n_fail, b);
+      if (c) atomicMax(&s2->max_iter, c);
+      if (d) atomicMax(&s2->max_resid_bits, d);
+    }
+  }
+}
+
+}  // namespace dxm

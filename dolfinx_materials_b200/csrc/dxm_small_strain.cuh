@@ -1,0 +1,282 @@
+// Small-strain hot path: linear elasticity and J2 plasticity (linear / Voce / mixed hardening).
+//
+// Replaces the per-point arithmetic behind JAXMaterial.integrate (dolfinx_materials/jaxmat.py:208-234,
+// jaxmat `vonMisesIsotropicHardening`) and LinearElasticIsotropic.constitutive_update
+// (python_materials/elasticity.py:21-24); closed form per
+// tests/mfront/IsotropicLinearHardeningPlasticity.mfront:49-77.  Operation order == oracle/small_strain.py.
+//
+// Layout: SoA, one Gauss point per thread-lane, PPT consecutive points per thread (PPT=2 -> 16-byte
+// double2 accesses).  Per point the kernel reads 25 doubles (eps 6, eps_old 6, sig_old 6, p_old 1,
+// epsp_old 6) and writes 49 (sig 6, p 1, epsp 6, Ct 36): 592 B, all coalesced streaming accesses.
+// The tangent is never materialised: Ct = A 1x1 + B I - gamma n x n is formed entry by entry at
+// store time from 3 scalars and the flow direction.
+#pragma once
+#include "dxm_canon.cuh"
+
+namespace dxm {
+
+constexpr int kNewtonCap = 25;
+constexpr double kNewtonRtol = 1e-12;
+
+enum Hardening { HARD_NONE = 0, HARD_LINEAR = 1, HARD_GENERAL = 2 };
+
+struct SmallStrainArgs {
+  // s1 (written) -- eps is read from s1.strain (the gradient buffer)
+  const double* eps;
+  double* sig;
+  double* p;
+  double* epsp;
+  double* ct;
+  // s0 (read)
+  const double* eps_old;
+  const double* sig_old;
+  const double* p_old;
+  const double* epsp_old;
+  int64_t ld;     // SoA leading dimension
+  int64_t start;  // first point of this launch (multiple of 2)
+  int64_t count;  // number of points
+  // uniform properties (PERPOINT == false)
+  double lam, mu, sig0, H, dsu, b;
+  // per-point properties (PERPOINT == true), each [ld]
+  const double *pE, *pnu, *psig0, *pH, *psigu, *pb;
+  StatSlot* stats;
+  // optional diagnostics (DIAG == true)
+  uint8_t* d_flag;
+  int32_t* d_iter;
+  double* d_resid;
+  uint8_t* d_fail;
+};
+
+struct PointProps {
+  double lam, mu, sig0, H, dsu, b;
+};
+
+// One Gauss point.  Returns results through references; everything stays in registers.
+template <int HARD>
+__device__ __forceinline__ void j2_point(const PointProps& m, const double (&eps)[6],
+                                         const double (&e_old)[6], const double (&s_old)[6],
+                                         const double p_old, const double (&ep_old)[6],
+                                         double (&sig)[6], double& p_new, double (&epsp)[6],
+                                         double (&nrm)[6], double& A, double& B, double& gamma,
+                                         bool& flag, int& n_iter, double& resid, bool& fail) {
+  const double twomu = 2.0 * m.mu;
+  const double threemu = 3.0 * m.mu;
+  double de[6], st[6], s[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) de[i] = eps[i] - e_old[i];
+  const double tr = (de[0] + de[1]) + de[2];
+  const double ltr = m.lam * tr;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) st[i] = s_old[i] + (ltr + twomu * de[i]);
+#pragma unroll
+  for (int i = 3; i < 6; ++i) st[i] = s_old[i] + twomu * de[i];
+  const double pm = ((st[0] + st[1]) + st[2]) / 3.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) s[i] = st[i] - pm;
+#pragma unroll
+  for (int i = 3; i < 6; ++i) s[i] = st[i];
+  double ss = s[0] * s[0] + s[1] * s[1];
+#pragma unroll
+  for (int i = 2; i < 6; ++i) ss = ss + s[i] * s[i];
+  const double seq = sqrt(1.5 * ss);
+
+  double dp = 0.0;
+  double Hp = m.H;
+  flag = false;
+  n_iter = 0;
+  resid = 0.0;
+  fail = false;
+
+  if (HARD != HARD_NONE) {
+    const double bdsu = m.b * m.dsu;
+    double ecur = 1.0;
+    double sy0;
+    if (HARD == HARD_GENERAL) {
+      ecur = exp_c(-(m.b * p_old));
+      sy0 = (m.sig0 + m.H * p_old) + m.dsu * (1.0 - ecur);
+    } else {
+      sy0 = m.sig0 + m.H * p_old;
+    }
+    const double f = seq - sy0;
+    flag = f > 0.0;
+    if (flag) {
+      if (HARD == HARD_LINEAR || bdsu == 0.0) {
+        dp = f / (threemu + m.H);  // closed-form radial return (mfront :57-60)
+      } else {
+        const double tol = kNewtonRtol * seq;
+        for (int it = 0;; ++it) {
+          const double p = p_old + dp;
+          const double sy = (m.sig0 + m.H * p) + m.dsu * (1.0 - ecur);
+          const double r = (seq - threemu * dp) - sy;
+          if (fabs(r) <= tol) {
+            resid = fabs(r);
+            break;
+          }
+          if (it == kNewtonCap) {
+            resid = fabs(r);
+            fail = true;
+            break;
+          }
+          const double dsy = m.H + bdsu * ecur;
+          dp = dp + r / (threemu + dsy);
+          ecur = exp_c(-(m.b * (p_old + dp)));
+          ++n_iter;
+        }
+      }
+    }
+    if (HARD == HARD_GENERAL) Hp = m.H + bdsu * ecur;
+  }
+
+  double q = 0.0;
+  gamma = 0.0;
+  if (flag) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) nrm[i] = (1.5 * s[i]) / seq;
+    q = dp / seq;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) nrm[i] = 0.0;
+    dp = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const double depsp = dp * nrm[i];
+    sig[i] = st[i] - twomu * depsp;
+    epsp[i] = ep_old[i] + depsp;
+  }
+  p_new = p_old + dp;
+
+  const double fourmu2 = (4.0 * m.mu) * m.mu;
+  const double beta = fourmu2 * q;
+  if (flag) {
+    const double cste = 1.0 / (threemu + Hp);
+    gamma = fourmu2 * (cste - q);
+  }
+  A = m.lam + 0.5 * beta;
+  B = twomu - 1.5 * beta;
+
+  double chk = (seq + fabs(pm)) + p_new;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) chk = chk + fabs(epsp[i]);
+  if (!isfinite(chk)) fail = true;
+}
+
+template <int HARD, bool PERPOINT, int PPT, bool DIAG, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+    dxm_small_strain_kernel(const SmallStrainArgs a) {
+  const int64_t ld = a.ld;
+  const int64_t ntile = (a.count + (int64_t)blockDim.x * PPT - 1) / ((int64_t)blockDim.x * PPT);
+  PointStats acc;
+
+  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int64_t loc = (tile * blockDim.x + threadIdx.x) * PPT;  // local index within launch
+    if (loc >= a.count) continue;
+    const int64_t i0 = a.start + loc;
+
+    double eps[6][PPT], e_old[6][PPT], s_old[6][PPT], ep_old[6][PPT], p_old[PPT];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ldv<PPT>(a.eps + c * ld + i0, eps[c]);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ldv<PPT>(a.eps_old + c * ld + i0, e_old[c]);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ldv<PPT>(a.sig_old + c * ld + i0, s_old[c]);
+    ldv<PPT>(a.p_old + i0, p_old);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ldv<PPT>(a.epsp_old + c * ld + i0, ep_old[c]);
+
+    double vE[PPT], vnu[PPT], vs0[PPT], vH[PPT], vsu[PPT], vb[PPT];
+    if (PERPOINT) {
+      ldv<PPT>(a.pE + i0, vE);
+      ldv<PPT>(a.pnu + i0, vnu);
+      ldv<PPT>(a.psig0 + i0, vs0);
+      ldv<PPT>(a.pH + i0, vH);
+      ldv<PPT>(a.psigu + i0, vsu);
+      ldv<PPT>(a.pb + i0, vb);
+    }
+
+    double sig[6][PPT], epsp[6][PPT], nrm[6][PPT], p_new[PPT], A[PPT], B[PPT], gamma[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      PointProps m;
+      if (PERPOINT) {
+        m.lam = vE[k] * vnu[k] / (1.0 + vnu[k]) / (1.0 - 2.0 * vnu[k]);
+        m.mu = vE[k] / 2.0 / (1.0 + vnu[k]);
+        m.sig0 = vs0[k];
+        m.H = vH[k];
+        const double d = vsu[k] - vs0[k];
+        m.dsu = isfinite(d) ? d : 0.0;
+        m.b = vb[k];
+      } else {
+        m.lam = a.lam;
+        m.mu = a.mu;
+        m.sig0 = a.sig0;
+        m.H = a.H;
+        m.dsu = a.dsu;
+        m.b = a.b;
+      }
+      double e1[6], e0[6], s0[6], ep0[6], so[6], epo[6], nn[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        e1[c] = eps[c][k];
+        e0[c] = e_old[c][k];
+        s0[c] = s_old[c][k];
+        ep0[c] = ep_old[c][k];
+      }
+      bool flag, fail;
+      int n_iter;
+      double resid;
+      j2_point<HARD>(m, e1, e0, s0, p_old[k], ep0, so, p_new[k], epo, nn, A[k], B[k], gamma[k],
+                     flag, n_iter, resid, fail);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        sig[c][k] = so[c];
+        epsp[c][k] = epo[c];
+        nrm[c][k] = nn[c];
+      }
+      const bool valid = (loc + k) < a.count;
+      if (valid) {
+        acc.n_plastic += flag ? 1u : 0u;
+        acc.n_fail += fail ? 1u : 0u;
+        acc.max_iter = n_iter > (int)acc.max_iter ? (unsigned)n_iter : acc.max_iter;
+        acc.max_resid = resid > acc.max_resid ? resid : acc.max_resid;
+        if (resid != resid) acc.max_resid = resid;
+        if (DIAG) {
+          a.d_flag[i0 + k] = flag ? 1 : 0;
+          a.d_iter[i0 + k] = n_iter;
+          a.d_resid[i0 + k] = resid;
+          a.d_fail[i0 + k] = fail ? 1 : 0;
+        }
+      }
+    }
+
+    // ---- stores: state then the 36 tangent entries (row-major j*6+i, symmetric) ---------------
+#pragma unroll
+    for (int c = 0; c < 6; ++c) stv<PPT>(a.sig + c * ld + i0, sig[c]);
+    stv<PPT>(a.p + i0, p_new);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) stv<PPT>(a.epsp + c * ld + i0, epsp[c]);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+#pragma unroll
+      for (int i = j; i < 6; ++i) {
+        double v[PPT];
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          double base;
+          if (i == j)
+            base = (i < 3) ? (A[k] + B[k]) : B[k];
+          else if (i < 3 && j < 3)
+            base = A[k];
+          else
+            base = 0.0;
+          v[k] = base - gamma[k] * (nrm[i][k] * nrm[j][k]);
+        }
+        stv<PPT>(a.ct + (int64_t)(j * 6 + i) * ld + i0, v);
+        if (i != j) stv<PPT>(a.ct + (int64_t)(i * 6 + j) * ld + i0, v);
+      }
+    }
+  }
+  block_reduce_stats(acc, a.stats);
+}
+
+}  // namespace dxm

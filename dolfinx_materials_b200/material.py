@@ -1,0 +1,354 @@
+"""``CUDAMaterial``: the CUDA-backed ``Material`` of the reference protocol.
+
+Mirrors, name for name, what ``QuadratureMap`` and the solvers call on a material
+(reference ``dolfinx_materials/generic.py:103-201`` and ``jaxmat.py:141-234``; call sites
+``quadrature_map.py:84-137,160-172,231-233,279-360``): ``gradients`` / ``fluxes`` /
+``internal_state_variables`` / ``tangent_blocks`` / ``variables`` / ``*_names`` / ``rotation_matrix`` /
+``material_properties`` / ``update_material_property`` / ``set_data_manager`` / ``integrate`` /
+``get_initial_state_dict`` / ``get_final_state_dict`` / ``set_initial_state_dict`` /
+``data_manager.update()`` / ``data_manager.revert()``.
+
+State lives on the device in SoA buffers owned by ``libdxm_cuda.so``; ``integrate`` hands back host
+``(flux, isv, Ct)`` arrays exactly like the reference, and the ``*_resident`` methods expose the
+zero-copy device path (DLPack) for callers that keep gradients on the GPU.
+"""
+
+import ctypes
+import warnings
+import weakref
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import PerformanceWarning, _lib
+from ._lib import MEM_DEVICE, MEM_HOST, MEM_RESIDENT, Stats, check
+
+
+@dataclass
+class IntegrationStats:
+    """Per-call statistics reduced on the device (fused replacement of the host NaN scans,
+    reference ``quadrature_map.py:322-324``)."""
+
+    n_points: int = 0
+    n_plastic: int = 0
+    n_fail: int = 0
+    max_iter: int = 0
+    max_residual: float = 0.0
+    kernel_ms: float = 0.0
+
+    @classmethod
+    def from_c(cls, s):
+        return cls(s.n_points, s.n_plastic, s.n_fail, s.max_iter, s.max_residual, s.kernel_ms)
+
+
+class _Pinned:
+    """A page-locked host array (``dxm_host_alloc``) viewed as numpy; freed with the object."""
+
+    def __init__(self, shape):
+        lib = _lib.load()
+        size = int(np.prod(shape))
+        ptr = ctypes.c_void_p()
+        check(lib.dxm_host_alloc(ctypes.byref(ptr), size * 8), "dxm_host_alloc")
+        self.ptr = ptr.value
+        buf = (ctypes.c_double * max(size, 1)).from_address(self.ptr)
+        self.array = np.ctypeslib.as_array(buf)[:size].reshape(shape)
+        self._fin = weakref.finalize(self, lib.dxm_host_free, ctypes.c_void_p(self.ptr))
+
+
+PinnedArray = _Pinned  # public name: ``PinnedArray(shape).array`` is a page-locked ndarray view
+
+
+class _StateView:
+    """Dict-like view of one state generation (``s0`` / ``s1``); values are fetched from the device
+    on access, shape ``(n, dim)`` like ``MaterialStateManager.__getitem__`` (``generic.py:260-271``)."""
+
+    def __init__(self, material, gen):
+        self._m = material
+        self._gen = gen
+
+    def keys(self):
+        return list(self._m.variables.keys())
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return len(self.keys())
+
+    def __contains__(self, key):
+        return key in self._m.variables
+
+    def __getitem__(self, key):
+        if isinstance(key, slice):  # generic.py:195 uses s0[:]
+            return {k: self._m._get_state(self._gen, k) for k in self.keys()}
+        return self._m._get_state(self._gen, key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+
+class DeviceDataManager:
+    """Device-resident counterpart of ``DataManager`` (``generic.py:204-216``, ``jaxmat.py:30-43``):
+    two state generations, ``update()`` = s0 <- s1 and ``revert()`` = s1 <- s0, both O(1) swaps."""
+
+    def __init__(self, material, ngauss):
+        self._m = material
+        self.n = int(ngauss)
+        num_gradients = sum(material.gradients.values())
+        num_fluxes = sum(material.fluxes.values())
+        self.K = np.zeros((num_fluxes, num_gradients))
+        self.s0 = _StateView(material, 0)
+        self.s1 = _StateView(material, 1)
+
+    def update(self):
+        check(_lib.load().dxm_update(self._m._h), "dxm_update")
+
+    def revert(self):
+        check(_lib.load().dxm_revert(self._m._h), "dxm_revert")
+
+
+class CUDAMaterial:
+    """Converts a behaviour descriptor into a dolfinx_materials-compatible material running on a
+    B200 (the role ``JAXMaterial(behavior)`` plays in the reference, ``jaxmat.py:141-156``)."""
+
+    def __init__(self, behavior, device=0, warn_on_failure=True):
+        self.behavior = behavior
+        self.device = int(device)
+        self.warn_on_failure = warn_on_failure
+        self.material_properties = dict(behavior.properties())
+        self._h = None
+        self._n = 0
+        self._out = None
+        self._fin = None
+        self.data_manager = None
+        self.last_stats = IntegrationStats()
+
+    # ---- protocol: description ---------------------------------------------------------------
+    @property
+    def name(self):
+        return self.behavior.__class__.__name__
+
+    @property
+    def rotation_matrix(self):
+        return None
+
+    @property
+    def gradients(self):
+        return {"F": 9} if self.behavior.finite_strain else {"strain": 6}
+
+    @property
+    def fluxes(self):
+        return {"PK1": 9} if self.behavior.finite_strain else {"stress": 6}
+
+    @property
+    def internal_state_variables(self):
+        return {"p": 1, "be_bar": 6} if self.behavior.finite_strain else {"p": 1, "epsp": 6}
+
+    @property
+    def tangent_blocks(self):
+        return {
+            (kf, kg): (vf, vg)
+            for (kf, vf), (kg, vg) in zip(self.fluxes.items(), self.gradients.items())
+        }
+
+    @property
+    def variables(self):
+        return {**self.gradients, **self.fluxes, **self.internal_state_variables}
+
+    @property
+    def gradient_names(self):
+        return list(self.gradients.keys())
+
+    @property
+    def flux_names(self):
+        return list(self.fluxes.keys())
+
+    @property
+    def internal_state_variable_names(self):
+        return list(self.internal_state_variables.keys())
+
+    # ---- protocol: properties ----------------------------------------------------------------
+    def update_material_property(self, key, value):
+        """Scalar (0-d) or per-Gauss-point array, as ``QuadratureMap.update_material_properties``
+        passes them (``quadrature_map.py:160-172``)."""
+        if key not in self.material_properties:
+            raise KeyError(f"'{key}' is not a property of {self.name}: {list(self.material_properties)}")
+        self.material_properties[key] = value
+        if self._h is not None:
+            self._push_property(key, value)
+
+    def _push_property(self, key, value):
+        lib = _lib.load()
+        v = np.ascontiguousarray(np.asarray(value, dtype=np.float64).ravel())
+        if v.size not in (1, self._n):
+            raise ValueError(f"property '{key}' has {v.size} values, expected 1 or {self._n}")
+        check(
+            lib.dxm_set_property(self._h, key.encode(), v.ctypes.data_as(ctypes.c_void_p), v.size, MEM_HOST),
+            "dxm_set_property",
+        )
+
+    # ---- protocol: data manager --------------------------------------------------------------
+    def set_data_manager(self, ngauss):
+        lib = _lib.load()
+        if self._fin is not None:
+            self._fin()
+        h = ctypes.c_void_p()
+        check(lib.dxm_create(self.behavior.kind, self.device, int(ngauss), ctypes.byref(h)), "dxm_create")
+        self._h = h
+        self._n = int(ngauss)
+        self._fin = weakref.finalize(self, lib.dxm_destroy, h)
+        self._out = None
+        self.data_manager = DeviceDataManager(self, ngauss)
+        for key, value in self.material_properties.items():
+            self._push_property(key, value)
+
+    def _require_handle(self):
+        if self._h is None:
+            raise RuntimeError("set_data_manager(ngauss) must be called before using the material")
+
+    # ---- protocol: state ---------------------------------------------------------------------
+    def _get_state(self, gen, key):
+        self._require_handle()
+        lib = _lib.load()
+        dim = lib.dxm_field_dim(self._h, key.encode())
+        if dim < 0:
+            raise KeyError(key)
+        out = np.empty((self._n, dim))
+        check(lib.dxm_get_state(self._h, gen, key.encode(), out.ctypes.data_as(ctypes.c_void_p), MEM_HOST), "dxm_get_state")
+        return out
+
+    def _set_state(self, gen, state):
+        self._require_handle()
+        lib = _lib.load()
+        unknown = [k for k in state if k not in self.variables]
+        assert len(unknown) == 0, "Material state contains unknown field to update with."
+        for key, value in state.items():
+            dim = self.variables[key]
+            v = np.ascontiguousarray(np.asarray(value, dtype=np.float64).reshape(self._n, dim))
+            check(lib.dxm_set_state(self._h, gen, key.encode(), v.ctypes.data_as(ctypes.c_void_p), MEM_HOST), "dxm_set_state")
+
+    def get_initial_state_dict(self):
+        return self.data_manager.s0[:]
+
+    def get_final_state_dict(self):
+        return self.data_manager.s1[:]
+
+    def set_initial_state_dict(self, state):
+        return self._set_state(0, state)
+
+    # ---- protocol: the hot call --------------------------------------------------------------
+    def _outputs(self):
+        if self._out is None:
+            nf = sum(self.fluxes.values())
+            ng = sum(self.gradients.values())
+            ni = sum(self.internal_state_variables.values())
+            self._out = (_Pinned((self._n, nf)), _Pinned((self._n, ni)), _Pinned((self._n, nf, ng)))
+        return self._out
+
+    def _finish(self, rc, stats):
+        check(rc, "dxm_integrate")
+        self.last_stats = IntegrationStats.from_c(stats)
+        if rc > 0 and self.warn_on_failure:
+            warnings.warn(
+                f"{rc} Gauss point(s) failed their local constitutive solve "
+                f"(max residual {stats.max_residual:.3e})",
+                PerformanceWarning,
+            )
+
+    def integrate(self, gradients, dt=0):
+        """``(flux, isv, Ct) = integrate(gradients, dt)`` with host arrays, reference semantics
+        (``generic.py:176-189``, ``jaxmat.py:208-234``): reads s0, writes s1.  The returned arrays are
+        page-locked buffers owned by the material and overwritten by the next call (as the reference's
+        ``s1.fluxes`` / ``s1.internal_state_variables`` are)."""
+        self._require_handle()
+        lib = _lib.load()
+        ng = sum(self.gradients.values())
+        g = np.ascontiguousarray(np.asarray(gradients, dtype=np.float64))
+        if g.shape != (self._n, ng):
+            raise ValueError(f"gradients must have shape {(self._n, ng)}, got {g.shape}")
+        flux, isv, ct = self._outputs()
+        stats = Stats()
+        rc = lib.dxm_integrate(
+            self._h, g.ctypes.data_as(ctypes.c_void_p), MEM_HOST, float(dt),
+            ctypes.c_void_p(flux.ptr), ctypes.c_void_p(isv.ptr), ctypes.c_void_p(ct.ptr), MEM_HOST,
+            ctypes.byref(stats),
+        )
+        self._finish(rc, stats)
+        return flux.array, isv.array, ct.array
+
+    # ---- device-resident extensions ------------------------------------------------------------
+    def integrate_resident(self, dt=0, wait=True):
+        """Run the update on gradients already written into ``gradient_buffer()``; results stay in
+        the SoA device buffers (``device_view``).  ``wait=False`` returns without synchronising."""
+        self._require_handle()
+        lib = _lib.load()
+        stats = Stats()
+        rc = lib.dxm_integrate(self._h, None, MEM_RESIDENT, float(dt), None, None, None, MEM_RESIDENT,
+                               ctypes.byref(stats) if wait else None)
+        if wait:
+            self._finish(rc, stats)
+            return self.last_stats
+        check(rc, "dxm_integrate")
+        return None
+
+    def fetch_stats(self):
+        self._require_handle()
+        stats = Stats()
+        check(_lib.load().dxm_last_stats(self._h, ctypes.byref(stats)), "dxm_last_stats")
+        self.last_stats = IntegrationStats.from_c(stats)
+        return self.last_stats
+
+    def device_view(self, field, gen=1):
+        """Zero-copy ``torch`` view (shape ``(dim, n)``, SoA) of a device-resident field via DLPack.
+        Views of generation buffers are invalidated by ``data_manager.update()``."""
+        self._require_handle()
+        import torch
+
+        lib = _lib.load()
+        mt = ctypes.c_void_p()
+        check(lib.dxm_export_dlpack(self._h, gen, field.encode(), ctypes.byref(mt)), "dxm_export_dlpack")
+        new = ctypes.pythonapi.PyCapsule_New
+        new.restype = ctypes.py_object
+        new.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
+        capsule = new(mt, b"dltensor", None)
+        return torch.from_dlpack(capsule)
+
+    def gradient_buffer(self):
+        """Where a device-resident caller writes this step's gradients (SoA, shape ``(dim, n)``)."""
+        return self.device_view(self.gradient_names[0], gen=1)
+
+    def synth_gradients(self, seed, amp, k, K, start=0):
+        """Fill the gradient buffer with the counter-based synthetic history (bench / tests)."""
+        self._require_handle()
+        recipe = 1 if self.behavior.finite_strain else 0
+        check(_lib.load().dxm_synth_gradients(self._h, recipe, int(seed), float(amp), int(k), int(K), int(start)),
+              "dxm_synth_gradients")
+
+    def set_stream(self, cuda_stream):
+        self._require_handle()
+        check(_lib.load().dxm_set_stream(self._h, ctypes.c_void_p(cuda_stream)), "dxm_set_stream")
+
+    def enable_diagnostics(self, on=True):
+        self._require_handle()
+        check(_lib.load().dxm_enable_diagnostics(self._h, int(on)), "dxm_enable_diagnostics")
+
+    def diagnostics(self):
+        """Per-point ``(flag, n_iter, resid, fail)`` of the last integrate (parity tests)."""
+        self._require_handle()
+        flag = np.empty(self._n, dtype=np.uint8)
+        fail = np.empty(self._n, dtype=np.uint8)
+        n_iter = np.empty(self._n, dtype=np.int32)
+        resid = np.empty(self._n)
+        check(
+            _lib.load().dxm_get_diagnostics(
+                self._h, flag.ctypes.data_as(ctypes.c_void_p), n_iter.ctypes.data_as(ctypes.c_void_p),
+                resid.ctypes.data_as(ctypes.c_void_p), fail.ctypes.data_as(ctypes.c_void_p)),
+            "dxm_get_diagnostics",
+        )
+        return flag, n_iter, resid, fail

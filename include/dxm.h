@@ -1,0 +1,128 @@
+/*
+ * dxm.h -- C ABI of libdxm_cuda.so: the B200-native batched constitutive update behind the
+ * dolfinx_materials `Material` protocol.
+ *
+ * The reference (bleyerj/dolfinx_materials v0.4.0) is pure Python and has no FFI of its own for
+ * this path; each entry point below names the reference interface it replaces
+ * (paths relative to the upstream tree).  The closest native precedent in the reference is the
+ * MGIS call `mgis_bv.integrate(data_manager, type, dt, begin, end) -> int status`
+ * (dolfinx_materials/mfront.py:266-272), whose "status < 1 => warning" convention is kept.
+ *
+ * Conventions
+ *  - every function returns 0 on success, < 0 on a hard error (text via dxm_last_error()),
+ *    dxm_integrate additionally returns > 0 = number of Gauss points whose local solve failed
+ *    (iteration cap or non-finite result; replaces the host NaN scans of quadrature_map.py:322-324).
+ *  - nothing throws or aborts across the ABI; plain pointers and sizes only.
+ *  - the library owns all device buffers of a handle (two state generations, tangent, staging);
+ *    the caller owns every array it passes, borrowed for the duration of the call.
+ *  - host/“AoS” arrays are C-contiguous (n, dim) float64 exactly as QuadratureMap builds and consumes
+ *    them (quadrature_map.py:313, :331-334; utils.py:136-143).  Device-resident fields are SoA:
+ *    component c of point i at  base[c * ld + i],  ld = dxm_ld(h).
+ *  - tensor conventions: symmetric tensors are Mandel 6-vectors [11,22,33,r2*12,r2*13,r2*23]
+ *    (utils.py:146-165), non-symmetric ones [11,22,33,12,21,13,31,23,32] (utils.py:168-190);
+ *    the tangent is row-major d flux_j / d grad_i at j*ngrad+i (quadrature_map.py:94-104).
+ */
+#ifndef DXM_H
+#define DXM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dxm_handle dxm_handle;
+
+/* behaviours (reference: the jaxmat behaviours wrapped by JAXMaterial, jaxmat.py:141-234, and
+ * python_materials/elasticity.py:5-24) */
+enum {
+  DXM_ELASTIC = 0,   /* LinearElasticIsotropic: E, nu                                              */
+  DXM_J2_LINEAR = 1, /* J2 + linear isotropic hardening, closed form: E, nu, sig0, H                */
+  DXM_J2_VOCE = 2,   /* J2 + sig0 + H p + (sigu-sig0)(1-exp(-b p)), scalar Newton: E,nu,sig0,sigu,b,H */
+  DXM_FEFP_VOCE = 3  /* finite-strain FeFp J2 plasticity, same hardening law                        */
+};
+
+/* where a caller-supplied array lives */
+enum {
+  DXM_MEM_HOST = 0,    /* host (n, dim) AoS; pinned memory is DMA'd directly, pageable is staged   */
+  DXM_MEM_DEVICE = 1,  /* device (n, dim) AoS on the handle's device                               */
+  DXM_MEM_RESIDENT = 2 /* the handle's own SoA buffers (zero copy); pointers are ignored           */
+};
+
+typedef struct dxm_stats {
+  int64_t n_points;     /* points processed by the call                                           */
+  int64_t n_plastic;    /* active set size (f_trial > 0)                                          */
+  int64_t n_fail;       /* local solves that hit the iteration cap or produced non-finite values   */
+  int64_t max_iter;     /* maximum local Newton iteration count                                   */
+  double max_residual;  /* max |r| of the local solve at exit                                     */
+  double kernel_ms;     /* device time of the constitutive kernel(s) of this call (CUDA events)   */
+} dxm_stats;
+
+/* life cycle -- replaces Material.set_data_manager(ngauss) (generic.py:172-174, jaxmat.py:195-197) */
+int dxm_create(int behaviour, int device, int64_t n, dxm_handle** out);
+int dxm_destroy(dxm_handle* h);
+int dxm_set_stream(dxm_handle* h, void* cuda_stream); /* run on the caller's stream (default: own) */
+int64_t dxm_ld(const dxm_handle* h);                  /* SoA leading dimension (>= n)              */
+int64_t dxm_npoints(const dxm_handle* h);
+
+/* material properties -- replaces Material.update_material_property(name, values)
+ * (generic.py:119-120, called from quadrature_map.py:160-172 with a 0-d or per-point array).
+ * count is 1 (uniform) or n (per Gauss point). names: "E","nu","sig0","H","sigu","b". */
+int dxm_set_property(dxm_handle* h, const char* name, const double* v, int64_t count, int mem);
+
+/* state -- replaces set_initial_state_dict / get_initial_state_dict / get_final_state_dict
+ * (generic.py:194-201; MaterialStateManager.set_item / __getitem__, generic.py:260-292).
+ * gen 0 = s0 (start of step), gen 1 = s1 (last integrate).  field: small strain
+ * "strain","stress","p","epsp"; finite strain "F","PK1","p","be_bar"; also "Ct" (gen ignored). */
+int dxm_field_dim(const dxm_handle* h, const char* field); /* components, <0 if unknown          */
+int dxm_set_state(dxm_handle* h, int gen, const char* field, const double* v, int mem);
+int dxm_get_state(dxm_handle* h, int gen, const char* field, double* out, int mem);
+/* raw SoA device pointer of a field (gen 1 "strain"/"F" is where a resident caller writes the
+ * gradients before dxm_integrate(..., DXM_MEM_RESIDENT, ...)); invalidated by dxm_update */
+int dxm_device_ptr(dxm_handle* h, int gen, const char* field, double** ptr);
+/* DLPack view (shape (dim, n), strides (ld, 1), kDLCUDA float64) of the same buffer; *out is a
+ * DLManagedTensor* whose deleter drops a reference on the handle */
+int dxm_export_dlpack(dxm_handle* h, int gen, const char* field, void** out);
+
+/* the hot call -- replaces Material.integrate(gradients, dt) -> (flux, isv, Ct)
+ * (generic.py:176-189, jaxmat.py:208-234), reading s0 and writing s1.
+ *  grad : (n, ngrad) gradients in `mem`;  flux (n, nflux), isv (n, nisv), ct (n, nflux*ngrad) in
+ *  `out_mem`; any output pointer may be NULL (not transferred).  With DXM_MEM_RESIDENT the
+ *  gradients are read from s1's gradient buffer and results stay in the SoA buffers. */
+int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double* flux, double* isv,
+                  double* ct, int out_mem, dxm_stats* stats);
+
+/* statistics of the last dxm_integrate (synchronises the handle's stream); use it after a call made
+ * with stats == NULL, which returns without waiting for the device */
+int dxm_last_stats(dxm_handle* h, dxm_stats* stats);
+
+/* DataManager.update() / revert() (generic.py:212-216, jaxmat.py:39-43): O(1) generation swap */
+int dxm_update(dxm_handle* h);
+int dxm_revert(dxm_handle* h);
+
+/* per-point diagnostics for parity tests: active-set flag, local iteration count, final residual */
+int dxm_enable_diagnostics(dxm_handle* h, int on);
+int dxm_get_diagnostics(dxm_handle* h, uint8_t* flag, int32_t* n_iter, double* resid, uint8_t* fail);
+
+/* synthetic gradient histories written straight into s1's gradient buffer (bench / tests);
+ * bit-identical to oracle/synth.py.  recipe 0 = strain (6), 1 = deformation gradient (9);
+ * `start` = global index of this handle's first point (multi-GPU shards) */
+int dxm_synth_gradients(dxm_handle* h, int recipe, uint64_t seed, double amp, int k, int K,
+                        int64_t start);
+
+/* pinned host memory helpers (the Python wrapper allocates its output arrays with these) */
+int dxm_host_alloc(void** ptr, int64_t bytes);
+int dxm_host_free(void* ptr);
+
+/* measurement support */
+int64_t dxm_launch_count(void);                       /* kernels launched by this library so far */
+int dxm_fp64_peak(int device, double* tflops);        /* register-resident DFMA microbenchmark   */
+int dxm_copy_peak(int device, int64_t bytes, double* gbs); /* device copy bandwidth (read+write)  */
+
+const char* dxm_last_error(void);
+const char* dxm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DXM_H */
