@@ -89,7 +89,7 @@ struct dxm_handle {
   int32_t* d_iter = nullptr;
   double* d_resid = nullptr;
   int num_sms = 148;
-  int ppt = 2;
+  int ppt = 1;
   int minb = 2;
   std::atomic<int> refs{1};
 };
@@ -438,7 +438,8 @@ int dxm_create(int behaviour, int device, int64_t n, dxm_handle** out) {
   h->ld = (n + 63) & ~int64_t(63);
   h->num_sms = prop.multiProcessorCount;
   const char* env = std::getenv("DXM_PPT");
-  h->ppt = (env && std::atoi(env) == 1) ? 1 : 2;
+  // scalar 8-byte accesses measured faster than double2 on B200 (profiles/r01_variant_sweep.json)
+  h->ppt = (env && std::atoi(env) == 2) ? 2 : 1;
   env = std::getenv("DXM_MINB");
   h->minb = env ? std::atoi(env) : 2;
   if (behaviour == DXM_FEFP_VOCE) {

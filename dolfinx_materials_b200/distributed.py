@@ -1,0 +1,45 @@
+"""Multi-GPU plumbing: one process per GPU, Gauss points partitioned by contiguous cell blocks.
+
+The constitutive update has no inter-point dependency (reference: ``jax.vmap`` over points,
+``jaxmat.py:147-151``; DOLFINx already partitions cells per MPI rank, ``quadrature_map.py:66-70``), so
+the data path has no collective at all.  The only exchange is the reduction of the per-call
+statistics -- SUM of failed / plastic points, MAX of the local iteration count and residual -- done
+with NCCL (``torch.distributed``, backend "nccl") over NVLink; ``gloo`` works for CPU-side tests.
+"""
+
+import dataclasses
+
+from .material import IntegrationStats
+
+
+def shard_range(n_global, rank, world):
+    """Contiguous range [start, stop) of Gauss points owned by ``rank`` (cell-major dof order,
+    ``quadrature_map.py:255-260``); remainders go to the first ranks."""
+    base, rem = divmod(int(n_global), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_start(n_per_rank, rank):
+    """Global index of the first point of ``rank`` under weak scaling (fixed points per GPU)."""
+    return int(n_per_rank) * int(rank)
+
+
+def allreduce_stats(stats, group=None, device=None):
+    """Reduce :class:`IntegrationStats` over the process group: counts are summed, iteration count
+    and residual are maximised; ``kernel_ms`` becomes the max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return stats
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
+    sums = torch.tensor([stats.n_points, stats.n_plastic, stats.n_fail], dtype=torch.float64, device=device)
+    maxs = torch.tensor([stats.max_iter, stats.max_residual, stats.kernel_ms], dtype=torch.float64, device=device)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(maxs, op=dist.ReduceOp.MAX, group=group)
+    s, m = sums.tolist(), maxs.tolist()
+    return dataclasses.replace(
+        stats, n_points=int(s[0]), n_plastic=int(s[1]), n_fail=int(s[2]), max_iter=int(m[0]), max_residual=m[1], kernel_ms=m[2]
+    )

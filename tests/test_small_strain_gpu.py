@@ -91,10 +91,11 @@ def test_elastic_bit_exact(jm, n):
     assert np.array_equal(Ct, np.broadcast_to(C, (n, 6, 6)))
 
 
-def test_ppt1_variant_matches(jm, monkeypatch):
-    """The scalar-access kernel variant (DXM_PPT=1) gives the same bits as the double2 one."""
+def test_ppt2_variant_matches(jm, monkeypatch):
+    """The double2 kernel variant (DXM_PPT=2, two points per thread) gives the same bits as the
+    default scalar-access one."""
     n = 10007
-    monkeypatch.setenv("DXM_PPT", "1")
+    monkeypatch.setenv("DXM_PPT", "2")
     m = make(jm, "voce", VOCE, n)
     run_history(m, VOCE, n, amp=1.25e-2, K=3)
 
