@@ -1,0 +1,80 @@
+"""The C-ABI library builds for sm_100a without a GPU, exports every symbol include/dxm.h declares,
+fails loudly without a device, and the product package never touches the oracle (CPU only)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "dxm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dxm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(jm):
+    from dolfinx_materials_b200 import _lib
+
+    lib = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/dxm.h but not exported"
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes signatures and header drifted apart"
+    assert b"sm_100a" in lib.dxm_version()
+
+
+def test_library_contains_sm100a_sass_only(jm):
+    from dolfinx_materials_b200 import _lib
+
+    out = subprocess.run(["cuobjdump", "-lelf", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback(jm):
+    """Without a CUDA device the product path raises (it never routes through the oracle)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = jm.CUDAMaterial(jm.ElasticBehavior(elasticity=jm.LinearElasticIsotropic(E=1.0, nu=0.2)))
+    with pytest.raises(RuntimeError):
+        m.set_data_manager(8)
+    with pytest.raises(RuntimeError):
+        m.integrate([[0.0] * 6] * 8)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "dolfinx_materials_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "/root/reference" not in src, f
+
+
+def test_protocol_surface_without_gpu(jm):
+    """Names, sizes and ordering the reference's QuadratureMap relies on (quadrature_map.py:84-137,
+    :338-348; jaxmat.py:166-193)."""
+    el = jm.LinearElasticIsotropic(E=70e3, nu=0.3)
+    m = jm.CUDAMaterial(jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=jm.VoceHardening(sig0=350.0, sigu=500.0, b=1e3)))
+    assert m.gradients == {"strain": 6} and m.fluxes == {"stress": 6}
+    assert list(m.internal_state_variables.items()) == [("p", 1), ("epsp", 6)]
+    assert m.tangent_blocks == {("stress", "strain"): (6, 6)}
+    assert m.gradient_names == ["strain"] and m.flux_names == ["stress"]
+    assert m.rotation_matrix is None and m.name == "vonMisesIsotropicHardening"
+    assert set(m.material_properties) == {"E", "nu", "sig0", "sigu", "b", "H"}
+    f = jm.CUDAMaterial(jm.FeFpJ2Plasticity(elasticity=el, yield_stress=jm.VoceHardening(sig0=500.0, sigu=750.0, b=1000.0)))
+    assert f.gradients == {"F": 9} and f.fluxes == {"PK1": 9}
+    assert list(f.internal_state_variables.items()) == [("p", 1), ("be_bar", 6)]
+    assert f.tangent_blocks == {("PK1", "F"): (9, 9)}
+    with pytest.raises(TypeError):
+        jm.CUDAMaterial(jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=lambda p: 1.0))
+    with pytest.raises(KeyError):
+        m.update_material_property("nope", 1.0)
