@@ -231,7 +231,7 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
     a.d_iter = h->d_iter;
     a.d_resid = h->d_resid;
     a.d_fail = h->d_fail;
-    return launch_fefp(a, h->diag, h->num_sms, h->stream, &g_launches);
+    return launch_fefp(a, h->diag, h->num_sms, h->stream, &g_launches, &g_err);
   }
   SmallStrainArgs a{};
   a.eps = s1;
@@ -940,9 +940,3 @@ int dxm_copy_peak(int device, int64_t bytes, double* gbs) {
 
 }  // extern "C"
 
-namespace dxm {
-int launch_fefp(const FeFpArgs&, bool, int, cudaStream_t, std::atomic<long long>*) {
-  g_err = "FeFp kernel not built yet";
-  return -1;
-}
-}  // namespace dxm

@@ -1,23 +1,34 @@
-// Finite-strain FeFp J2 plasticity kernel (placeholder until the kernel lands).
+// Finite-strain hot path: multiplicative (Fe.Fp) J2 plasticity, internal state be_bar (isochoric elastic
+// left Cauchy-Green, Mandel 6) + p.  Replaces the per-point arithmetic behind JAXMaterial.integrate for
+// jaxmat `FeFpJ2Plasticity` (dolfinx_materials/jaxmat.py:166-193, 208-234; workload
+// tests/test_FeFp_jax.py:6-33, demos/jax/finite_strain_elastoplasticity/finite_strain_elastoplasticity.py:158-181).
+// Operation order == oracle/fefp.py (see there for the derivation: the reference's 7-unknown local
+// system reduces exactly to a 2x2 Newton in (dp, t) with be = alpha D + t 1).
+//
+// Layout: SoA, one Gauss point per thread.  Per point the kernel reads 25 doubles (F 9, F_old 9, p 1,
+// be_bar 6) and writes 97 (PK1 9, p 1, be_bar 6, Ct 81): 976 B, coalesced streaming accesses.  The 9x9
+// tangent is assembled column by column in registers from closed-form pieces and stored entry by entry.
 #pragma once
 #include <atomic>
+#include <string>
+
 #include "dxm_canon.cuh"
 
 namespace dxm {
 
 struct FeFpArgs {
-  const double* F;
+  const double* F;  // s1 gradient buffer [9][ld]
   double* P;
   double* p;
   double* be;
-  double* ct;
+  double* ct;  // [81][ld]
   const double* F_old;
   const double* p_old;
   const double* be_old;
   int64_t ld, start, count;
   bool perpoint;
   double E, mu, kappa, sig0, H, dsu, b;
-  const double* pp[6];
+  const double* pp[6];  // per-point E, nu, sig0, H, sigu, b
   StatSlot* stats;
   uint8_t* d_flag;
   int32_t* d_iter;
@@ -25,7 +36,354 @@ struct FeFpArgs {
   uint8_t* d_fail;
 };
 
-int launch_fefp(const FeFpArgs& a, bool diag, int num_sms, cudaStream_t stream,
-                std::atomic<long long>* launches);
+constexpr int kFeNewtonCap = 25;
+constexpr double kFeNewtonRtol = 1e-12;
+constexpr double kRsqrt2 = 0.70710678118654752440;
+constexpr double kSqrt2 = 1.41421356237309504880;
+
+// position of tensor component (i,j) in the reference's 9-vector [11,22,33,12,21,13,31,23,32]
+// (dolfinx_materials/utils.py:173-186)
+__device__ __forceinline__ constexpr int idx9(int i, int j) {
+  return i == j ? i : (i == 0 && j == 1) ? 3 : (i == 1 && j == 0) ? 4 : (i == 0 && j == 2) ? 5
+                  : (i == 2 && j == 0) ? 6 : (i == 1 && j == 2) ? 7 : 8;
+}
+
+// cube root from exactly rounded operations only (twin of oracle.fefp.cbrt_c)
+__device__ __forceinline__ double cbrt_c(double x) {
+  if (!(x > 0.0)) return __longlong_as_double(0x7ff8000000000000LL);
+  int e;
+  const double m = frexp(x, &e);
+  const int q = (e >= 0) ? (e / 3) : -((-e + 2) / 3);
+  const int r = e - 3 * q;
+  const double xr = m * (double)(1 << r);
+  double y = 0.65 + 0.27 * xr;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) y = (2.0 * y + xr / (y * y)) / 3.0;
+  return y * __hiloint2double((q + 1023) << 20, 0);
+}
+
+__device__ __forceinline__ double dot3(double a0, double b0, double a1, double b1, double a2,
+                                       double b2) {
+  return (a0 * b0 + a1 * b1) + a2 * b2;
+}
+
+__device__ __forceinline__ double det3(const double (&A)[3][3]) {
+  const double t0 = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]);
+  const double t1 = A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]);
+  const double t2 = A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+  return (t0 - t1) + t2;
+}
+
+__device__ __forceinline__ void inv3(const double (&A)[3][3], double (&Ai)[3][3], double& det) {
+  double c[3][3];
+  c[0][0] = A[1][1] * A[2][2] - A[1][2] * A[2][1];
+  c[0][1] = A[0][2] * A[2][1] - A[0][1] * A[2][2];
+  c[0][2] = A[0][1] * A[1][2] - A[0][2] * A[1][1];
+  c[1][0] = A[1][2] * A[2][0] - A[1][0] * A[2][2];
+  c[1][1] = A[0][0] * A[2][2] - A[0][2] * A[2][0];
+  c[1][2] = A[0][2] * A[1][0] - A[0][0] * A[1][2];
+  c[2][0] = A[1][0] * A[2][1] - A[1][1] * A[2][0];
+  c[2][1] = A[0][1] * A[2][0] - A[0][0] * A[2][1];
+  c[2][2] = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+  det = (A[0][0] * c[0][0] + A[0][1] * c[1][0]) + A[0][2] * c[2][0];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Ai[i][j] = c[i][j] / det;
+}
+
+template <bool PERPOINT, bool DIAG>
+__global__ void __launch_bounds__(128)
+    dxm_fefp_kernel(const FeFpArgs a) {
+  const int64_t ld = a.ld;
+  const int64_t ntile = (a.count + blockDim.x - 1) / blockDim.x;
+  PointStats acc;
+
+  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int64_t loc = tile * blockDim.x + threadIdx.x;
+    if (loc >= a.count) continue;
+    const int64_t i0 = a.start + loc;
+
+    double A[3][3], Ao[3][3], Bo[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        A[i][j] = __ldcs(a.F + (int64_t)idx9(i, j) * ld + i0);
+        Ao[i][j] = __ldcs(a.F_old + (int64_t)idx9(i, j) * ld + i0);
+      }
+    {
+      double beo[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) beo[c] = __ldcs(a.be_old + (int64_t)c * ld + i0);
+      Bo[0][0] = beo[0];
+      Bo[1][1] = beo[1];
+      Bo[2][2] = beo[2];
+      Bo[0][1] = Bo[1][0] = beo[3] * kRsqrt2;
+      Bo[0][2] = Bo[2][0] = beo[4] * kRsqrt2;
+      Bo[1][2] = Bo[2][1] = beo[5] * kRsqrt2;
+    }
+    const double p_old = __ldcs(a.p_old + i0);
+
+    double mu, kappa, sig0, H, dsu, b;
+    if (PERPOINT) {
+      const double E = __ldcs(a.pp[0] + i0), nu = __ldcs(a.pp[1] + i0);
+      mu = E / 2.0 / (1.0 + nu);
+      kappa = E / (3.0 * (1.0 - 2.0 * nu));
+      sig0 = __ldcs(a.pp[2] + i0);
+      H = __ldcs(a.pp[3] + i0);
+      const double d = __ldcs(a.pp[4] + i0) - sig0;
+      dsu = isfinite(d) ? d : 0.0;
+      b = __ldcs(a.pp[5] + i0);
+    } else {
+      mu = a.mu;
+      kappa = a.kappa;
+      sig0 = a.sig0;
+      H = a.H;
+      dsu = a.dsu;
+      b = a.b;
+    }
+    const double threemu = 3.0 * mu;
+    const double bdsu = b * dsu;
+
+    // ---- trial state ----------------------------------------------------------------------------
+    double B[3][3], D[3][3];
+    {
+      double Aoi[3][3], deto, f[3][3], M[3][3];
+      inv3(Ao, Aoi, deto);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          f[i][j] = dot3(A[i][0], Aoi[0][j], A[i][1], Aoi[1][j], A[i][2], Aoi[2][j]);
+      const double Jf = det3(f);
+      const double cb = cbrt_c(Jf);
+      const double s23 = 1.0 / (cb * cb);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          M[i][j] = dot3(f[i][0], Bo[0][j], f[i][1], Bo[1][j], f[i][2], Bo[2][j]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i; j < 3; ++j) {
+          B[i][j] = s23 * dot3(M[i][0], f[j][0], M[i][1], f[j][1], M[i][2], f[j][2]);
+          B[j][i] = B[i][j];
+        }
+    }
+    const double t0 = ((B[0][0] + B[1][1]) + B[2][2]) / 3.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) D[i][j] = (i == j) ? (B[i][j] - t0) : B[i][j];
+    const double dd = ((D[0][0] * D[0][0] + D[1][1] * D[1][1]) + D[2][2] * D[2][2]) +
+                      2.0 * ((D[0][1] * D[0][1] + D[0][2] * D[0][2]) + D[1][2] * D[1][2]);
+    const double d3 = det3(D);
+    const double seq = mu * sqrt(1.5 * dd);
+
+    double ecur = exp_c(-(b * p_old));
+    const double sy0 = (sig0 + H * p_old) + dsu * (1.0 - ecur);
+    const double ftr = seq - sy0;
+    const bool flag = ftr > 0.0;
+
+    // ---- local 2x2 Newton in (dp, t) ----------------------------------------------------------------
+    const double c = threemu / seq;
+    double dp = 0.0, t = t0, resid = 0.0;
+    int n_iter = 0;
+    bool fail = false;
+    if (flag) {
+      const double tol1 = kFeNewtonRtol * seq;
+      for (int it = 0;; ++it) {
+        const double alpha = 1.0 - (c * t) * dp;
+        const double p = p_old + dp;
+        const double sy = (sig0 + H * p) + dsu * (1.0 - ecur);
+        const double r1 = (seq - (threemu * t) * dp) - sy;
+        const double a2 = alpha * alpha;
+        const double r2 = ((t * t) * t - (0.5 * a2) * (dd * t)) + ((a2 * alpha) * d3 - 1.0);
+        if (fabs(r1) <= tol1 && fabs(r2) <= kFeNewtonRtol) {
+          resid = fabs(r1);
+          break;
+        }
+        if (it == kFeNewtonCap) {
+          resid = fabs(r1);
+          fail = true;
+          break;
+        }
+        const double dsy = H + bdsu * ecur;
+        const double g = 3.0 * (a2 * d3) - (alpha * dd) * t;
+        const double J11 = -(threemu * t) - dsy;
+        const double J12 = -(threemu * dp);
+        const double ct = c * t;
+        const double cdp = c * dp;
+        const double J21 = -(g * ct);
+        const double J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp;
+        const double det = J11 * J22 - J12 * J21;
+        const double dp_new = dp + (J12 * r2 - r1 * J22) / det;
+        const double t_new = t + (J21 * r1 - J11 * r2) / det;
+        dp = dp_new;
+        t = t_new;
+        ecur = exp_c(-(b * (p_old + dp)));
+        ++n_iter;
+      }
+    }
+    const double alpha = flag ? (1.0 - (c * t) * dp) : 1.0;
+    const double p_new = p_old + dp;
+
+    // ---- new state -----------------------------------------------------------------------------------
+    double be[6];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) be[i] = flag ? (alpha * D[i][i] + t) : B[i][i];
+    be[3] = (alpha * D[0][1]) * kSqrt2;
+    be[4] = (alpha * D[0][2]) * kSqrt2;
+    be[5] = (alpha * D[1][2]) * kSqrt2;
+
+    // ---- stress ----------------------------------------------------------------------------------------
+    double Ai[3][3], Jd, tau[3][3], P[3][3];
+    inv3(A, Ai, Jd);
+    const double muA = mu * alpha;
+    const double pvol = (0.5 * kappa) * (Jd * Jd - 1.0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) tau[i][j] = (i == j) ? (muA * D[i][j] + pvol) : (muA * D[i][j]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        P[i][j] = dot3(tau[i][0], Ai[j][0], tau[i][1], Ai[j][1], tau[i][2], Ai[j][2]);
+
+    double chk = (seq + fabs(Jd)) + p_new;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) chk = chk + fabs(be[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) chk = chk + fabs(P[i][j]);
+    if (!isfinite(chk)) fail = true;
+
+    // state and stress stores (the tangent follows)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) __stcs(a.P + (int64_t)idx9(i, j) * ld + i0, P[i][j]);
+    __stcs(a.p + i0, p_new);
+#pragma unroll
+    for (int c6 = 0; c6 < 6; ++c6) __stcs(a.be + (int64_t)c6 * ld + i0, be[c6]);
+
+    acc.n_plastic += flag ? 1u : 0u;
+    acc.n_fail += fail ? 1u : 0u;
+    acc.max_iter = n_iter > (int)acc.max_iter ? (unsigned)n_iter : acc.max_iter;
+    acc.max_resid = resid > acc.max_resid ? resid : acc.max_resid;
+    if (resid != resid) acc.max_resid = resid;
+    if (DIAG) {
+      a.d_flag[i0] = flag ? 1 : 0;
+      a.d_iter[i0] = n_iter;
+      a.d_resid[i0] = resid;
+      a.d_fail[i0] = fail ? 1 : 0;
+    }
+
+    // ---- local-solve sensitivities: d(alpha) = al1 (D:dD) + al2 (D^2:dD) --------------------------------
+    double al1 = 0.0, al2 = 0.0;
+    if (flag) {
+      const double sq1 = (1.5 * (mu * mu)) / seq;
+      const double a2 = alpha * alpha;
+      const double dsy = H + bdsu * ecur;
+      const double g = 3.0 * (a2 * d3) - (alpha * dd) * t;
+      const double ct = c * t;
+      const double cdp = c * dp;
+      const double J11 = -(threemu * t) - dsy;
+      const double J12 = -(threemu * dp);
+      const double J21 = -(g * ct);
+      const double J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp;
+      const double det = J11 * J22 - J12 * J21;
+      const double oma = (1.0 - alpha) / seq;
+      const double b11 = sq1;
+      const double b21 = (g * oma) * sq1 - a2 * t;
+      const double b22 = a2 * alpha;
+      const double p1 = -((b11 * J22 - J12 * b21) / det);
+      const double t1 = -((J11 * b21 - J21 * b11) / det);
+      const double p2 = (J12 * b22) / det;
+      const double t2 = -((J11 * b22) / det);
+      al1 = (oma * sq1 - ct * p1) - cdp * t1;
+      al2 = -(ct * p2) - cdp * t2;
+    }
+
+    // ---- tangent, column (k,l) = d/dF_kl, row (i,j) = PK1_ij ----------------------------------------------
+    double DA[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        DA[i][j] = dot3(D[i][0], Ai[j][0], D[i][1], Ai[j][1], D[i][2], Ai[j][2]);
+    const double kJ2 = kappa * (Jd * Jd);
+    const double twothird_dd = (2.0 / 3.0) * dd;
+    const double twod3 = 2.0 * d3;
+    const double twothird_muA = (2.0 / 3.0) * muA;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      double w[3], v[3], u[3], z[3], y[3], h[3], my[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) w[i] = Ai[l][i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) v[i] = dot3(B[i][0], w[0], B[i][1], w[1], B[i][2], w[2]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) u[i] = dot3(D[i][0], v[0], D[i][1], v[1], D[i][2], v[2]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) z[i] = dot3(D[i][0], u[0], D[i][1], u[1], D[i][2], u[2]);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) y[j] = dot3(Ai[j][0], v[0], Ai[j][1], v[1], Ai[j][2], v[2]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double tw = dot3(tau[i][0], w[0], tau[i][1], w[1], tau[i][2], w[2]);
+        h[i] = muA * v[i] - tw;
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) my[j] = muA * y[j];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double a1 = 2.0 * u[k] - twothird_dd * w[k];
+        const double a2p = (2.0 * z[k] - twothird_dd * v[k]) - twod3 * w[k];
+        const double cD = mu * (al1 * a1 + al2 * a2p) - twothird_muA * w[k];
+        const double cI = kJ2 * w[k] - twothird_muA * v[k];
+        const int col = idx9(k, l);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            double val = (cD * DA[i][j] + cI * Ai[j][i]) + h[i] * Ai[j][k];
+            if (i == k) val = val + my[j];
+            __stcs(a.ct + (int64_t)(idx9(i, j) * 9 + col) * ld + i0, val);
+          }
+      }
+    }
+  }
+  block_reduce_stats(acc, a.stats);
+}
+
+inline int launch_fefp(const FeFpArgs& a, bool diag, int num_sms, cudaStream_t stream,
+                       std::atomic<long long>* launches, std::string* err) {
+  const int block = 128;
+  const int64_t ntile = (a.count + block - 1) / block;
+  const void* k = a.perpoint ? (diag ? (const void*)dxm_fefp_kernel<true, true>
+                                     : (const void*)dxm_fefp_kernel<true, false>)
+                             : (diag ? (const void*)dxm_fefp_kernel<false, true>
+                                     : (const void*)dxm_fefp_kernel<false, false>);
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, block, 0);
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)per_sm * num_sms;
+  if (grid > ntile) grid = ntile;
+  if (grid < 1) grid = 1;
+  void* args[] = {(void*)&a};
+  cudaError_t e = cudaLaunchKernel(k, dim3((unsigned)grid), dim3(block), args, 0, stream);
+  launches->fetch_add(1);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    *err = std::string("dxm_fefp_kernel launch: ") + cudaGetErrorString(e);
+    return -1;
+  }
+  return 0;
+}
 
 }  // namespace dxm

@@ -36,4 +36,4 @@ hand-written :func:`oracle.canon.exp_c`.  The CUDA kernels are compiled with
 (flags, local iteration counts, stress, state and tangent).
 """
 
-from . import canon, small_strain, synth  # noqa: F401
+from . import canon, fefp, small_strain, synth  # noqa: F401
