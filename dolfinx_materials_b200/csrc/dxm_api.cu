@@ -127,6 +127,7 @@ int launch_aos_to_soa(dxm_handle* h, cudaStream_t st, const double* src, int64_t
                       double* dst, int64_t d0, int64_t count, int D) {
   if (count <= 0) return 0;
   const size_t smem = (size_t)kTile * (D | 1) * sizeof(double);
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(aos_to_soa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntile = (count + kTile - 1) / kTile;
   const int grid = (int)std::min<int64_t>(ntile, (int64_t)h->num_sms * 8);
   aos_to_soa_kernel<<<grid, 256, smem, st>>>(src, rs, c0, dst, h->ld, d0, count, D);
@@ -138,6 +139,7 @@ int launch_soa_to_aos(dxm_handle* h, cudaStream_t st, const double* src, int64_t
                       int64_t rs, int c0, int64_t count, int D) {
   if (count <= 0) return 0;
   const size_t smem = (size_t)kTile * (D | 1) * sizeof(double);
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(soa_to_aos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntile = (count + kTile - 1) / kTile;
   const int grid = (int)std::min<int64_t>(ntile, (int64_t)h->num_sms * 4);
   soa_to_aos_kernel<<<grid, 256, smem, st>>>(src, h->ld, s0, dst, rs, c0, count, D);
