@@ -57,6 +57,7 @@ SIGNATURES = {
     "dxm_launch_count": (ctypes.c_int64, []),
     "dxm_fp64_peak": (ctypes.c_int, [ctypes.c_int, c_double_p]),
     "dxm_copy_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, c_double_p]),
+    "dxm_stream_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, c_double_p]),
     "dxm_last_error": (ctypes.c_char_p, []),
     "dxm_version": (ctypes.c_char_p, []),
 }

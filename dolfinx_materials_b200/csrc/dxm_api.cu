@@ -940,5 +940,48 @@ int dxm_copy_peak(int device, int64_t bytes, double* gbs) {
   return 0;
 }
 
+
+int dxm_stream_peak(int device, int64_t n, int nread, int nwrite, double* gbs) {
+  if (!gbs || n < 1) return fail("dxm_stream_peak: bad argument");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  CK(cudaGetDeviceProperties(&prop, device));
+  const int64_t ld = (n + 63) & ~int64_t(63);
+  double *s = nullptr, *d = nullptr;
+  CK(cudaMalloc(&s, sizeof(double) * ld * nread));
+  CK(cudaMalloc(&d, sizeof(double) * ld * nwrite));
+  CK(cudaMemset(s, 0, sizeof(double) * ld * nread));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  const int grid = prop.multiProcessorCount * 2;
+  double best = 0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CK(cudaEventRecord(a));
+    if (nread == 25 && nwrite == 49)
+      stream_mix_kernel<25, 49><<<grid, 256>>>(s, d, ld, n);
+    else if (nread == 25 && nwrite == 97)
+      stream_mix_kernel<25, 97><<<grid, 256>>>(s, d, ld, n);
+    else if (nread == 37 && nwrite == 37)
+      stream_mix_kernel<37, 37><<<grid, 256>>>(s, d, ld, n);
+    else if (nread == 1 && nwrite == 1)
+      stream_mix_kernel<1, 1><<<grid, 256>>>(s, d, ld, n);
+    else
+      return fail("dxm_stream_peak: supported mixes are 25/49, 25/97, 37/37, 1/1");
+    LAUNCH_CHECK();
+    CK(cudaEventRecord(b));
+    CK(cudaEventSynchronize(b));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    best = std::max(best, 8.0 * (nread + nwrite) * n / (ms * 1e-3) / 1e9);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(s);
+  cudaFree(d);
+  *gbs = best;
+  return 0;
+}
+
 }  // extern "C"
 

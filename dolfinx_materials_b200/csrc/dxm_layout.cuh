@@ -123,4 +123,24 @@ __global__ void copy_kernel(const double2* __restrict__ src, double2* __restrict
     __stcs(dst + i, __ldcs(src + i));
 }
 
+// pure-traffic twin of the constitutive kernels: NR coalesced read streams, NW coalesced write
+// streams, one point per thread, no arithmetic to speak of -- the practical HBM ceiling for that mix
+template <int NR, int NW>
+__global__ void __launch_bounds__(256, 2)
+    stream_mix_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t ld, int64_t n) {
+  const int64_t ntile = (n + blockDim.x - 1) / blockDim.x;
+  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int64_t i = tile * blockDim.x + threadIdx.x;
+    if (i >= n) continue;
+    double v[NR];
+#pragma unroll
+    for (int c = 0; c < NR; ++c) v[c] = __ldcs(src + (int64_t)c * ld + i);
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < NR; ++c) s += v[c];
+#pragma unroll
+    for (int c = 0; c < NW; ++c) __stcs(dst + (int64_t)c * ld + i, s + (double)c);
+  }
+}
+
 }  // namespace dxm

@@ -35,11 +35,17 @@ def allreduce_stats(stats, group=None, device=None):
         return stats
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
-    sums = torch.tensor([stats.n_points, stats.n_plastic, stats.n_fail], dtype=torch.float64, device=device)
-    maxs = torch.tensor([stats.max_iter, stats.max_residual, stats.kernel_ms], dtype=torch.float64, device=device)
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(maxs, op=dist.ReduceOp.MAX, group=group)
-    s, m = sums.tolist(), maxs.tolist()
+    # one collective: gather the 6 numbers of every rank, combine locally (SUM counts, MAX the rest)
+    world = dist.get_world_size(group)
+    mine = torch.tensor(
+        [stats.n_points, stats.n_plastic, stats.n_fail, stats.max_iter, stats.max_residual, stats.kernel_ms],
+        dtype=torch.float64, device=device,
+    )
+    allv = torch.empty(world * 6, dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(allv, mine, group=group)
+    allv = allv.view(world, 6).cpu()
+    s = allv[:, :3].sum(dim=0).tolist()
+    m = allv[:, 3:].max(dim=0).values.tolist()
     return dataclasses.replace(
         stats, n_points=int(s[0]), n_plastic=int(s[1]), n_fail=int(s[2]), max_iter=int(m[0]), max_residual=m[1], kernel_ms=m[2]
     )

@@ -118,6 +118,9 @@ int dxm_host_free(void* ptr);
 int64_t dxm_launch_count(void);                       /* kernels launched by this library so far */
 int dxm_fp64_peak(int device, double* tflops);        /* register-resident DFMA microbenchmark   */
 int dxm_copy_peak(int device, int64_t bytes, double* gbs); /* device copy bandwidth (read+write)  */
+/* pure-traffic twin of the update kernels: nread coalesced read streams + nwrite write streams over n
+ * points (supported mixes 25/49 = J2, 25/97 = FeFp, 37/37, 1/1): the practical HBM ceiling for that mix */
+int dxm_stream_peak(int device, int64_t n, int nread, int nwrite, double* gbs);
 
 const char* dxm_last_error(void);
 const char* dxm_version(void);

@@ -198,3 +198,33 @@ def test_resident_path_and_dlpack(jm):
     m.integrate_resident()
     ref2 = ss.integrate(eps * 0.5, ss.zero_state(n), VOCE)
     assert np.array_equal(m.device_view("stress").cpu().numpy().T, ref2["stress"])
+
+
+def test_cfg1_uniaxial_tension_limit(jm):
+    """cfg1 (tests/uniaxial_tension.py + tests/mfront/test_elastoplasticity.py:16-36): plane-strain uniaxial
+    tension, E=70e3, nu=0.3, H=1e-6, sig0=250, 50 steps to 2 %.  The 1-element FE solve is replaced by its
+    fixed point (eyy such that sigma_yy = 0, found with the oracle); the GPU then replays the strain path on
+    n in {1, 4, 16} points (the test's meshes) and must reach 2/sqrt(3) [sig0, 0, sig0/2] at rtol 1e-2."""
+    from scipy.optimize import brentq
+
+    props = dict(E=70e3, nu=0.3, sig0=250.0, H=1e-6)
+    st1 = ss.zero_state(1)
+    path = []
+    for exx in np.linspace(0, 2e-2, 51)[1:]:
+        def syy(eyy):
+            return ss.integrate(np.array([[exx, eyy, 0, 0, 0, 0.0]]), st1, props)["stress"][0, 1]
+
+        eyy = brentq(syy, -exx, exx, xtol=1e-16, rtol=1e-15)
+        path.append([exx, eyy, 0, 0, 0, 0.0])
+        st1 = ss.advance(ss.integrate(np.array([path[-1]]), st1, props))
+    for n in (1, 4, 16):
+        m = make(jm, "linear", props, n)
+        st = ss.zero_state(n)
+        for e in path:
+            eps = np.tile(e, (n, 1))
+            flux, isv, Ct = m.integrate(eps)
+            ref = ss.integrate(eps, st, props)
+            assert np.array_equal(flux, ref["stress"]) and np.array_equal(Ct, ref["Ct"])
+            m.data_manager.update()
+            st = ss.advance(ref)
+        assert np.allclose(flux[:, :3], 2 / np.sqrt(3) * np.array([250.0, 0, 125.0]), rtol=1e-2, atol=1e-8)
