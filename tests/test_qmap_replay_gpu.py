@@ -23,6 +23,10 @@ def test_newton_like_load_stepping_full_mesh(jm):
     n = ncell * nqp
     qmap = QuadratureMapReplay(ncell, nqp, voce_material(jm))
     qmap.register_gradient("strain", np.zeros((n, 6)))
+    # first update at u = 0, as the demos do before the solve (finite_strain_elastoplasticity.py:185):
+    # initialize_state() captures the gradients evaluated at that moment into s0 (quadrature_map.py:281-295)
+    qmap.update()
+    assert np.count_nonzero(_get_vals(qmap.fluxes["stress"])) == 0
     st = ss.zero_state(n)
     for step in range(1, 4):
         # three "Newton iterations": perturbed gradients, always integrating from the same s0
@@ -75,6 +79,8 @@ def test_fefp_map_with_initial_state_update(jm):
     # the demo initialises be_bar explicitly (finite_strain_elastoplasticity.py:181); without it
     # initialize_state() would push the zero-initialised Function into s0
     qmap.update_initial_state("be_bar", np.array([1, 1, 1, 0, 0, 0.0]))
+    qmap.update()  # "enforce compilation" call of the demo at F = I (finite_strain_elastoplasticity.py:185)
+    assert np.abs(_get_vals(qmap.fluxes["PK1"])).max() == 0
     st = fefp.virgin_state(n)
     for step in range(1, 4):
         F = synth.defgrad(n, 2, 3e-2, step, 3)
