@@ -113,12 +113,29 @@ double* field_ptr(dxm_handle* h, int gen, const Field* f, bool for_read) {
   return h->gen[g] + (int64_t)f->row * h->ld;
 }
 
+// Grid sizing.  Measured on B200 (profiles/r01_layout_experiment.txt, r01_grid_sweep.json): for these
+// streaming kernels a persistent grid (resident CTAs x tile-stride loop) caps at ~5.65 TB/s because all
+// CTAs walk the 74 SoA streams in lock-step; handing the hardware block scheduler many small CTAs
+// (a few 256-point tiles each) desynchronises them and reaches ~6.5 TB/s.  One tile per CTA is slower
+// again (per-CTA statistics epilogue).  Default: kTilesPerCta tiles per CTA.
+// DXM_TPB=<t> overrides the tiles per CTA, DXM_GRID=<k> forces k CTAs per SM (persistent style).
+constexpr int kTilesPerCta = 4;
 int grid_for(const void* kernel, int block, size_t smem, int num_sms, int64_t ntile) {
-  int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
-  if (per_sm < 1) per_sm = 1;
-  int64_t g = (int64_t)per_sm * num_sms;
+  (void)kernel;
+  (void)block;
+  (void)smem;
+  static const int mult = [] {
+    const char* e = std::getenv("DXM_GRID");
+    return e ? std::atoi(e) : 0;
+  }();
+  static const int tpb = [] {
+    const char* e = std::getenv("DXM_TPB");
+    const int v = e ? std::atoi(e) : kTilesPerCta;
+    return v > 0 ? v : kTilesPerCta;
+  }();
+  int64_t g = mult > 0 ? (int64_t)mult * num_sms : (ntile + tpb - 1) / tpb;
   if (g > ntile) g = ntile;
+  if (g > 0x7fffffff) g = 0x7fffffff;
   if (g < 1) g = 1;
   return (int)g;
 }

@@ -10,6 +10,7 @@
 // tangent is assembled column by column in registers from closed-form pieces and stored entry by entry.
 #pragma once
 #include <atomic>
+#include <cstdlib>
 #include <string>
 
 #include "dxm_canon.cuh"
@@ -369,11 +370,19 @@ inline int launch_fefp(const FeFpArgs& a, bool diag, int num_sms, cudaStream_t s
                                      : (const void*)dxm_fefp_kernel<true, false>)
                              : (diag ? (const void*)dxm_fefp_kernel<false, true>
                                      : (const void*)dxm_fefp_kernel<false, false>);
-  int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, block, 0);
-  if (per_sm < 1) per_sm = 1;
-  int64_t grid = (int64_t)per_sm * num_sms;
+  // one CTA per tile (see grid_for in dxm_api.cu); DXM_GRID=<k> forces k CTAs per SM
+  static const int mult = [] {
+    const char* e = std::getenv("DXM_GRID");
+    return e ? std::atoi(e) : 0;
+  }();
+  static const int tpb = [] {
+    const char* e = std::getenv("DXM_TPB");
+    const int v = e ? std::atoi(e) : 4;
+    return v > 0 ? v : 4;
+  }();
+  int64_t grid = mult > 0 ? (int64_t)mult * num_sms : (ntile + tpb - 1) / tpb;
   if (grid > ntile) grid = ntile;
+  if (grid > 0x7fffffff) grid = 0x7fffffff;
   if (grid < 1) grid = 1;
   void* args[] = {(void*)&a};
   cudaError_t e = cudaLaunchKernel(k, dim3((unsigned)grid), dim3(block), args, 0, stream);
