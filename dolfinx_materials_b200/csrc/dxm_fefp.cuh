@@ -49,18 +49,20 @@ __device__ __forceinline__ constexpr int idx9(int i, int j) {
                   : (i == 2 && j == 0) ? 6 : (i == 1 && j == 2) ? 7 : 8;
 }
 
-// cube root from exactly rounded operations only (twin of oracle.fefp.cbrt_c)
-__device__ __forceinline__ double cbrt_c(double x) {
+constexpr double kThird = 1.0 / 3.0;
+
+// x^(-1/3), division free, from exactly rounded operations only (twin of oracle.fefp.rcbrt_c)
+__device__ __forceinline__ double rcbrt_c(double x) {
   if (!(x > 0.0)) return __longlong_as_double(0x7ff8000000000000LL);
   int e;
   const double m = frexp(x, &e);
   const int q = (e >= 0) ? (e / 3) : -((-e + 2) / 3);
   const int r = e - 3 * q;
   const double xr = m * (double)(1 << r);
-  double y = 0.65 + 0.27 * xr;
+  double y = 1.2 - 0.15 * xr;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) y = (2.0 * y + xr / (y * y)) / 3.0;
-  return y * __hiloint2double((q + 1023) << 20, 0);
+  for (int i = 0; i < 6; ++i) y = (y * (4.0 - xr * ((y * y) * y))) * kThird;
+  return y * __hiloint2double((1023 - q) << 20, 0);
 }
 
 __device__ __forceinline__ double dot3(double a0, double b0, double a1, double b1, double a2,
@@ -87,14 +89,15 @@ __device__ __forceinline__ void inv3(const double (&A)[3][3], double (&Ai)[3][3]
   c[2][1] = A[0][1] * A[2][0] - A[0][0] * A[2][1];
   c[2][2] = A[0][0] * A[1][1] - A[0][1] * A[1][0];
   det = (A[0][0] * c[0][0] + A[0][1] * c[1][0]) + A[0][2] * c[2][0];
+  const double rdet = 1.0 / det;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) Ai[i][j] = c[i][j] / det;
+    for (int j = 0; j < 3; ++j) Ai[i][j] = c[i][j] * rdet;
 }
 
-template <bool PERPOINT, bool DIAG>
-__global__ void __launch_bounds__(128)
+template <bool PERPOINT, bool DIAG, int MINB>
+__global__ void __launch_bounds__(128, MINB)
     dxm_fefp_kernel(const FeFpArgs a) {
   const int64_t ld = a.ld;
   const int64_t ntile = (a.count + blockDim.x - 1) / blockDim.x;
@@ -158,8 +161,8 @@ __global__ void __launch_bounds__(128)
         for (int j = 0; j < 3; ++j)
           f[i][j] = dot3(A[i][0], Aoi[0][j], A[i][1], Aoi[1][j], A[i][2], Aoi[2][j]);
       const double Jf = det3(f);
-      const double cb = cbrt_c(Jf);
-      const double s23 = 1.0 / (cb * cb);
+      const double rc = rcbrt_c(Jf);
+      const double s23 = rc * rc;
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(128)
           B[j][i] = B[i][j];
         }
     }
-    const double t0 = ((B[0][0] + B[1][1]) + B[2][2]) / 3.0;
+    const double t0 = ((B[0][0] + B[1][1]) + B[2][2]) * kThird;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -182,6 +185,7 @@ __global__ void __launch_bounds__(128)
                       2.0 * ((D[0][1] * D[0][1] + D[0][2] * D[0][2]) + D[1][2] * D[1][2]);
     const double d3 = det3(D);
     const double seq = mu * sqrt(1.5 * dd);
+    const double rseq = 1.0 / seq;
 
     double ecur = exp_c(-(b * p_old));
     const double sy0 = (sig0 + H * p_old) + dsu * (1.0 - ecur);
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(128)
     const bool flag = ftr > 0.0;
 
     // ---- local 2x2 Newton in (dp, t) ----------------------------------------------------------------
-    const double c = threemu / seq;
+    const double c = threemu * rseq;
     double dp = 0.0, t = t0, resid = 0.0;
     int n_iter = 0;
     bool fail = false;
@@ -219,9 +223,9 @@ __global__ void __launch_bounds__(128)
         const double cdp = c * dp;
         const double J21 = -(g * ct);
         const double J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp;
-        const double det = J11 * J22 - J12 * J21;
-        const double dp_new = dp + (J12 * r2 - r1 * J22) / det;
-        const double t_new = t + (J21 * r1 - J11 * r2) / det;
+        const double rdet = 1.0 / (J11 * J22 - J12 * J21);
+        const double dp_new = dp + (J12 * r2 - r1 * J22) * rdet;
+        const double t_new = t + (J21 * r1 - J11 * r2) * rdet;
         dp = dp_new;
         t = t_new;
         ecur = exp_c(-(b * (p_old + dp)));
@@ -239,20 +243,20 @@ __global__ void __launch_bounds__(128)
     be[4] = (alpha * D[0][2]) * kSqrt2;
     be[5] = (alpha * D[1][2]) * kSqrt2;
 
-    // ---- stress ----------------------------------------------------------------------------------------
-    double Ai[3][3], Jd, tau[3][3], P[3][3];
+    // ---- stress: tau = mu alpha D + pvol 1,  PK1 = tau F^-T = mu alpha (D F^-T) + pvol F^-T --------------
+    double Ai[3][3], Jd, DA[3][3], P[3][3];
     inv3(A, Ai, Jd);
     const double muA = mu * alpha;
     const double pvol = (0.5 * kappa) * (Jd * Jd - 1.0);
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int j = 0; j < 3; ++j) tau[i][j] = (i == j) ? (muA * D[i][j] + pvol) : (muA * D[i][j]);
+      for (int j = 0; j < 3; ++j)
+        DA[i][j] = dot3(D[i][0], Ai[j][0], D[i][1], Ai[j][1], D[i][2], Ai[j][2]);
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
-        P[i][j] = dot3(tau[i][0], Ai[j][0], tau[i][1], Ai[j][1], tau[i][2], Ai[j][2]);
+      for (int j = 0; j < 3; ++j) P[i][j] = muA * DA[i][j] + pvol * Ai[j][i];
 
     double chk = (seq + fabs(Jd)) + p_new;
 #pragma unroll
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(128)
     // ---- local-solve sensitivities: d(alpha) = al1 (D:dD) + al2 (D^2:dD) --------------------------------
     double al1 = 0.0, al2 = 0.0;
     if (flag) {
-      const double sq1 = (1.5 * (mu * mu)) / seq;
+      const double sq1 = (1.5 * (mu * mu)) * rseq;
       const double a2 = alpha * alpha;
       const double dsy = H + bdsu * ecur;
       const double g = 3.0 * (a2 * d3) - (alpha * dd) * t;
@@ -297,62 +301,61 @@ __global__ void __launch_bounds__(128)
       const double J12 = -(threemu * dp);
       const double J21 = -(g * ct);
       const double J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp;
-      const double det = J11 * J22 - J12 * J21;
-      const double oma = (1.0 - alpha) / seq;
-      const double b11 = sq1;
+      const double rdet = 1.0 / (J11 * J22 - J12 * J21);
+      const double oma = (1.0 - alpha) * rseq;
       const double b21 = (g * oma) * sq1 - a2 * t;
       const double b22 = a2 * alpha;
-      const double p1 = -((b11 * J22 - J12 * b21) / det);
-      const double t1 = -((J11 * b21 - J21 * b11) / det);
-      const double p2 = (J12 * b22) / det;
-      const double t2 = -((J11 * b22) / det);
+      const double p1 = -((sq1 * J22 - J12 * b21) * rdet);
+      const double t1 = -((J11 * b21 - J21 * sq1) * rdet);
+      const double p2 = (J12 * b22) * rdet;
+      const double t2 = -((J11 * b22) * rdet);
       al1 = (oma * sq1 - ct * p1) - cdp * t1;
       al2 = -(ct * p2) - cdp * t2;
     }
 
-    // ---- tangent, column (k,l) = d/dF_kl, row (i,j) = PK1_ij ----------------------------------------------
-    double DA[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-        DA[i][j] = dot3(D[i][0], Ai[j][0], D[i][1], Ai[j][1], D[i][2], Ai[j][2]);
+    // ---- tangent, column (k,l) = d/dF_kl, row (i,j) = PK1_ij; w = row l of F^-1, v = B w = D w + t0 w:
+    //      dP_ij = cD (D F^-T)_ij + cI F^-T_ij + delta_ik mu alpha (F^-1 v)_j + hs w_i F^-1_jk
     const double kJ2 = kappa * (Jd * Jd);
-    const double twothird_dd = (2.0 / 3.0) * dd;
+    const double c23dd = (2.0 / 3.0) * dd;
     const double twod3 = 2.0 * d3;
-    const double twothird_muA = (2.0 / 3.0) * muA;
+    const double c23muA = (2.0 / 3.0) * muA;
+    const double hs = muA * t0 - pvol;
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
-      double w[3], v[3], u[3], z[3], y[3], h[3], my[3];
+      double w[3], v[3], u[3], z[3], my[3], hw[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) w[i] = Ai[l][i];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) v[i] = dot3(B[i][0], w[0], B[i][1], w[1], B[i][2], w[2]);
+      for (int i = 0; i < 3; ++i) v[i] = dot3(D[i][0], w[0], D[i][1], w[1], D[i][2], w[2]) + t0 * w[i];
+      if (flag) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i) u[i] = dot3(D[i][0], v[0], D[i][1], v[1], D[i][2], v[2]);
+        for (int i = 0; i < 3; ++i) u[i] = dot3(D[i][0], v[0], D[i][1], v[1], D[i][2], v[2]);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) z[i] = dot3(D[i][0], u[0], D[i][1], u[1], D[i][2], u[2]);
+        for (int i = 0; i < 3; ++i) z[i] = dot3(D[i][0], u[0], D[i][1], u[1], D[i][2], u[2]);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) y[j] = dot3(Ai[j][0], v[0], Ai[j][1], v[1], Ai[j][2], v[2]);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const double tw = dot3(tau[i][0], w[0], tau[i][1], w[1], tau[i][2], w[2]);
-        h[i] = muA * v[i] - tw;
+        for (int i = 0; i < 3; ++i) u[i] = z[i] = 0.0;
       }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) my[j] = muA * y[j];
+      for (int j = 0; j < 3; ++j) my[j] = muA * dot3(Ai[j][0], v[0], Ai[j][1], v[1], Ai[j][2], v[2]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) hw[i] = hs * w[i];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const double a1 = 2.0 * u[k] - twothird_dd * w[k];
-        const double a2p = (2.0 * z[k] - twothird_dd * v[k]) - twod3 * w[k];
-        const double cD = mu * (al1 * a1 + al2 * a2p) - twothird_muA * w[k];
-        const double cI = kJ2 * w[k] - twothird_muA * v[k];
+        double cd0 = 0.0;
+        if (flag) {
+          const double a1 = 2.0 * u[k] - c23dd * w[k];
+          const double a2p = (2.0 * z[k] - c23dd * v[k]) - twod3 * w[k];
+          cd0 = mu * (al1 * a1 + al2 * a2p);
+        }
+        const double cD = cd0 - c23muA * w[k];
+        const double cI = kJ2 * w[k] - c23muA * v[k];
         const int col = idx9(k, l);
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
-            double val = (cD * DA[i][j] + cI * Ai[j][i]) + h[i] * Ai[j][k];
+            double val = (cD * DA[i][j] + cI * Ai[j][i]) + hw[i] * Ai[j][k];
             if (i == k) val = val + my[j];
             __stcs(a.ct + (int64_t)(idx9(i, j) * 9 + col) * ld + i0, val);
           }
@@ -362,23 +365,35 @@ __global__ void __launch_bounds__(128)
   block_reduce_stats(acc, a.stats);
 }
 
+template <int MINB>
+inline const void* fefp_kernel_ptr(bool perpoint, bool diag) {
+  return perpoint ? (diag ? (const void*)dxm_fefp_kernel<true, true, MINB>
+                          : (const void*)dxm_fefp_kernel<true, false, MINB>)
+                  : (diag ? (const void*)dxm_fefp_kernel<false, true, MINB>
+                          : (const void*)dxm_fefp_kernel<false, false, MINB>);
+}
+
 inline int launch_fefp(const FeFpArgs& a, bool diag, int num_sms, cudaStream_t stream,
                        std::atomic<long long>* launches, std::string* err) {
   const int block = 128;
   const int64_t ntile = (a.count + block - 1) / block;
-  const void* k = a.perpoint ? (diag ? (const void*)dxm_fefp_kernel<true, true>
-                                     : (const void*)dxm_fefp_kernel<true, false>)
-                             : (diag ? (const void*)dxm_fefp_kernel<false, true>
-                                     : (const void*)dxm_fefp_kernel<false, false>);
-  // one CTA per tile (see grid_for in dxm_api.cu); DXM_GRID=<k> forces k CTAs per SM
+  // DXM_FEFP_MINB: resident CTAs per SM the register allocation targets (3: <=168 regs, 4: <=128, 5: <=96)
+  static const int minb = [] {
+    const char* e = std::getenv("DXM_FEFP_MINB");
+    return e ? std::atoi(e) : 4;
+  }();
+  const void* k = minb == 4 ? fefp_kernel_ptr<4>(a.perpoint, diag)
+                  : minb == 5 ? fefp_kernel_ptr<5>(a.perpoint, diag)
+                              : fefp_kernel_ptr<3>(a.perpoint, diag);
+  // a few tiles per CTA (see grid_for in dxm_api.cu); DXM_GRID=<k> forces k CTAs per SM
   static const int mult = [] {
     const char* e = std::getenv("DXM_GRID");
     return e ? std::atoi(e) : 0;
   }();
   static const int tpb = [] {
     const char* e = std::getenv("DXM_TPB");
-    const int v = e ? std::atoi(e) : 4;
-    return v > 0 ? v : 4;
+    const int v = e ? std::atoi(e) : 2;
+    return v > 0 ? v : 2;
   }();
   int64_t grid = mult > 0 ? (int64_t)mult * num_sms : (ntile + tpb - 1) / tpb;
   if (grid > ntile) grid = ntile;

@@ -47,9 +47,13 @@ def _col(a, n):
     return a.reshape(n)
 
 
-def cbrt_c(x):
-    """Cube root of x > 0 from exactly rounded operations only: frexp range reduction to [0.5, 4),
-    linear initial guess, 5 Newton steps, exact rescaling (NaN for x <= 0)."""
+THIRD = 1.0 / 3.0
+
+
+def rcbrt_c(x):
+    """x^(-1/3) for x > 0 from exactly rounded operations only, division free: frexp range reduction
+    to [0.5, 4), linear initial guess, 6 Newton steps y <- y (4 - x y^3) / 3, exact rescaling
+    (NaN for x <= 0).  Accurate to 2 ulp."""
     x = np.asarray(x, dtype=np.float64)
     ok = x > 0.0
     xs = np.where(ok, x, 1.0)
@@ -57,10 +61,10 @@ def cbrt_c(x):
     q = np.floor_divide(e, 3)
     r = e - 3 * q
     xr = np.ldexp(m, r)
-    y = 0.65 + 0.27 * xr
-    for _ in range(5):
-        y = (2.0 * y + xr / (y * y)) / 3.0
-    y = np.ldexp(y, q)
+    y = 1.2 - 0.15 * xr
+    for _ in range(6):
+        y = (y * (4.0 - xr * ((y * y) * y))) * THIRD
+    y = np.ldexp(y, -q)
     return np.where(ok, y, np.nan)
 
 
@@ -87,7 +91,8 @@ def _inv3(A):
     c[2][1] = A[0][1] * A[2][0] - A[0][0] * A[2][1]
     c[2][2] = A[0][0] * A[1][1] - A[0][1] * A[1][0]
     det = (A[0][0] * c[0][0] + A[0][1] * c[1][0]) + A[0][2] * c[2][0]
-    return [[c[i][j] / det for j in range(3)] for i in range(3)], det
+    rdet = 1.0 / det
+    return [[c[i][j] * rdet for j in range(3)] for i in range(3)], det
 
 
 def _dot3(a0, b0, a1, b1, a2, b2):
@@ -131,21 +136,22 @@ def integrate(F, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
         Aoi, _ = _inv3(Ao)
         f = [[_dot3(A[i][0], Aoi[0][j], A[i][1], Aoi[1][j], A[i][2], Aoi[2][j]) for j in range(3)] for i in range(3)]
         Jf = _det3(f)
-        cb = cbrt_c(Jf)
-        s23 = 1.0 / (cb * cb)
+        rc = rcbrt_c(Jf)
+        s23 = rc * rc
         M = [[_dot3(f[i][0], Bo[0][j], f[i][1], Bo[1][j], f[i][2], Bo[2][j]) for j in range(3)] for i in range(3)]
         B = [[None] * 3 for _ in range(3)]
         for i in range(3):
             for j in range(i, 3):
                 B[i][j] = s23 * _dot3(M[i][0], f[j][0], M[i][1], f[j][1], M[i][2], f[j][2])
                 B[j][i] = B[i][j]
-        t0 = ((B[0][0] + B[1][1]) + B[2][2]) / 3.0
+        t0 = ((B[0][0] + B[1][1]) + B[2][2]) * THIRD
         D = [[B[i][j] - t0 if i == j else B[i][j] for j in range(3)] for i in range(3)]
         dd = ((D[0][0] * D[0][0] + D[1][1] * D[1][1]) + D[2][2] * D[2][2]) + 2.0 * (
             (D[0][1] * D[0][1] + D[0][2] * D[0][2]) + D[1][2] * D[1][2]
         )
         d3 = _det3(D)
         seq = mu * np.sqrt(1.5 * dd)
+        rseq = 1.0 / seq
 
         e0 = exp_c(-(b * p_old))
         sy0 = (sig0 + H * p_old) + dsu * (1.0 - e0)
@@ -153,7 +159,7 @@ def integrate(F, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
         flag = ftr > 0.0
 
         # ---- local 2x2 Newton --------------------------------------------------------------------
-        c = threemu / seq
+        c = threemu * rseq
         dp = np.zeros(n)
         t = t0.copy()
         ecur = e0.copy()
@@ -186,9 +192,9 @@ def integrate(F, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
             cdp = c * dp
             J21 = -(g * ct)
             J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp
-            det = J11 * J22 - J12 * J21
-            dp_new = dp + (J12 * r2 - r1 * J22) / det
-            t_new = t + (J21 * r1 - J11 * r2) / det
+            rdet = 1.0 / (J11 * J22 - J12 * J21)
+            dp_new = dp + (J12 * r2 - r1 * J22) * rdet
+            t_new = t + (J21 * r1 - J11 * r2) * rdet
             dp = np.where(active, dp_new, dp)
             t = np.where(active, t_new, t)
             e_new = exp_c(-(b * (p_old + dp)))
@@ -208,15 +214,15 @@ def integrate(F, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
         be[4] = (alpha * D[0][2]) * SQRT2
         be[5] = (alpha * D[1][2]) * SQRT2
 
-        # ---- stress ---------------------------------------------------------------------------------
+        # ---- stress: tau = mu alpha D + pvol 1, PK1 = tau F^-T = mu alpha (D F^-T) + pvol F^-T ----------
         Ai, Jd = _inv3(A)
         muA = mu * alpha
         pvol = (0.5 * kappa) * (Jd * Jd - 1.0)
-        tau = [[muA * D[i][j] + pvol if i == j else muA * D[i][j] for j in range(3)] for i in range(3)]
-        P = [[_dot3(tau[i][0], Ai[j][0], tau[i][1], Ai[j][1], tau[i][2], Ai[j][2]) for j in range(3)] for i in range(3)]
+        DA = [[_dot3(D[i][0], Ai[j][0], D[i][1], Ai[j][1], D[i][2], Ai[j][2]) for j in range(3)] for i in range(3)]
+        P = [[muA * DA[i][j] + pvol * Ai[j][i] for j in range(3)] for i in range(3)]
 
         # ---- local-solve sensitivities: d(alpha) = al1 * (D:dD) + al2 * (D^2:dD) --------------------------
-        sq1 = (1.5 * (mu * mu)) / seq
+        sq1 = (1.5 * (mu * mu)) * rseq
         a2 = alpha * alpha
         dsy = H + bdsu * ecur
         g = 3.0 * (a2 * d3) - (alpha * dd) * t
@@ -226,43 +232,41 @@ def integrate(F, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
         J12 = -(threemu * dp)
         J21 = -(g * ct)
         J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp
-        det = J11 * J22 - J12 * J21
-        oma = (1.0 - alpha) / seq
-        b11 = sq1
+        rdet = 1.0 / (J11 * J22 - J12 * J21)
+        oma = (1.0 - alpha) * rseq
         b21 = (g * oma) * sq1 - a2 * t
         b22 = a2 * alpha
-        p1 = -((b11 * J22 - J12 * b21) / det)
-        t1 = -((J11 * b21 - J21 * b11) / det)
-        p2 = (J12 * b22) / det
-        t2 = -((J11 * b22) / det)
+        p1 = -((sq1 * J22 - J12 * b21) * rdet)
+        t1 = -((J11 * b21 - J21 * sq1) * rdet)
+        p2 = (J12 * b22) * rdet
+        t2 = -((J11 * b22) * rdet)
         al1 = np.where(flag, (oma * sq1 - ct * p1) - cdp * t1, 0.0)
         al2 = np.where(flag, -(ct * p2) - cdp * t2, 0.0)
 
-        # ---- tangent, column (k, l) = d/dF_kl ----------------------------------------------------------
-        DA = [[_dot3(D[i][0], Ai[j][0], D[i][1], Ai[j][1], D[i][2], Ai[j][2]) for j in range(3)] for i in range(3)]
+        # ---- tangent, column (k, l) = d/dF_kl:  with w = row l of F^-1, v = B w = D w + t0 w -------------
+        #   dP_ij = cD (D F^-T)_ij + cI F^-T_ij + delta_ik mu alpha (F^-1 v)_j + hs w_i F^-1_jk
         kJ2 = kappa * (Jd * Jd)
-        twothird_dd = (2.0 / 3.0) * dd
+        c23dd = (2.0 / 3.0) * dd
         twod3 = 2.0 * d3
-        twothird_muA = (2.0 / 3.0) * muA
+        c23muA = (2.0 / 3.0) * muA
+        hs = muA * t0 - pvol
         Ct = np.zeros((n, 9, 9))
         for l in range(3):
             w = [Ai[l][0], Ai[l][1], Ai[l][2]]
-            v = [_dot3(B[i][0], w[0], B[i][1], w[1], B[i][2], w[2]) for i in range(3)]
+            v = [_dot3(D[i][0], w[0], D[i][1], w[1], D[i][2], w[2]) + t0 * w[i] for i in range(3)]
             u = [_dot3(D[i][0], v[0], D[i][1], v[1], D[i][2], v[2]) for i in range(3)]
             z = [_dot3(D[i][0], u[0], D[i][1], u[1], D[i][2], u[2]) for i in range(3)]
-            y = [_dot3(Ai[j][0], v[0], Ai[j][1], v[1], Ai[j][2], v[2]) for j in range(3)]
-            tw = [_dot3(tau[i][0], w[0], tau[i][1], w[1], tau[i][2], w[2]) for i in range(3)]
-            h = [muA * v[i] - tw[i] for i in range(3)]
-            my = [muA * y[j] for j in range(3)]
+            my = [muA * _dot3(Ai[j][0], v[0], Ai[j][1], v[1], Ai[j][2], v[2]) for j in range(3)]
+            hw = [hs * w[i] for i in range(3)]
             for k in range(3):
-                a1 = 2.0 * u[k] - twothird_dd * w[k]
-                a2p = (2.0 * z[k] - twothird_dd * v[k]) - twod3 * w[k]
-                cD = mu * (al1 * a1 + al2 * a2p) - twothird_muA * w[k]
-                cI = kJ2 * w[k] - twothird_muA * v[k]
+                a1 = 2.0 * u[k] - c23dd * w[k]
+                a2p = (2.0 * z[k] - c23dd * v[k]) - twod3 * w[k]
+                cD = np.where(flag, mu * (al1 * a1 + al2 * a2p), 0.0) - c23muA * w[k]
+                cI = kJ2 * w[k] - c23muA * v[k]
                 col = IDX9[k][l]
                 for i in range(3):
                     for j in range(3):
-                        val = (cD * DA[i][j] + cI * Ai[j][i]) + h[i] * Ai[j][k]
+                        val = (cD * DA[i][j] + cI * Ai[j][i]) + hw[i] * Ai[j][k]
                         if i == k:
                             val = val + my[j]
                         Ct[:, IDX9[i][j], col] = val
