@@ -252,6 +252,19 @@ def workload_config(args, world):
     }
 
 
+def load_traffic(n):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum at a stated n), scaled to
+    this run's n when the capture was taken at another size; None when no capture is recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)["dxm_small_strain_kernel"]
+        per_gp = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["n"]
+        return per_gp * n, f"ncu capture at n={t['n']:.0f} ({t['source']}): {per_gp:.1f} B/point"
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -400,6 +413,7 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = load_peaks()
         achieved = BYTES_PER_GP * n / (kms * 1e-3) / 1e9
+        traffic, traffic_src = load_traffic(n)
         line = {
             "metric": METRIC,
             "value": value,
@@ -420,7 +434,8 @@ def run_ours(args):
                 "peak": peak,
                 "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": None,
+                "traffic": traffic,
+                "traffic_source": traffic_src,
                 "kernel": "dxm_small_strain_kernel<HARD_GENERAL,uniform,PPT=1>",
                 "kernel_ms": kms,
                 "algorithmic_bytes_per_launch": BYTES_PER_GP * n,

@@ -1,0 +1,127 @@
+"""BASELINE.json's full sizes on one B200: cfg2 (J2+Voce, 1e8 points) and cfg3 (FeFp, 1e7 points), device
+resident.  The oracle cannot run 1e8 points in seconds, so the check is (i) bit-exact comparison with the
+oracle on slices at the beginning, the middle and the very end of the batch (exercises 64-bit indexing: the
+tangent alone is 28.8 GB) and (ii) size-independent properties evaluated on the device over ALL points:
+yield consistency on the active set, f <= 0 elsewhere, monotone p, symmetric tangent, elastic tangent == C,
+statistics consistent with per-point flags."""
+import numpy as np
+import pytest
+
+from oracle import fefp, synth
+from oracle import small_strain as ss
+
+pytestmark = pytest.mark.gpu
+VOCE = dict(E=70e3, nu=0.3, sig0=350.0, sigu=500.0, b=1e3)
+FEFP = dict(E=70e3, nu=0.3, sig0=500.0, sigu=750.0, b=1000.0)
+AMP, K = 1.25e-2, 4
+
+
+def test_cfg2_j2_voce_1e8_points(jm):
+    import torch
+
+    n = 100_000_000
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70e9:
+        pytest.skip("needs ~62 GB of device memory")
+    m = jm.CUDAMaterial(jm.vonMisesIsotropicHardening(
+        elasticity=jm.LinearElasticIsotropic(E=VOCE["E"], nu=VOCE["nu"]),
+        yield_stress=jm.VoceHardening(sig0=VOCE["sig0"], sigu=VOCE["sigu"], b=VOCE["b"])))
+    m.set_data_manager(n)
+    m.enable_diagnostics()
+    for k in range(1, K):
+        m.synth_gradients(0, AMP, k, K)
+        m.integrate_resident()
+        m.data_manager.update()
+    m.synth_gradients(0, AMP, K, K)
+    stats = m.integrate_resident()
+    assert stats.n_fail == 0 and stats.max_iter <= 6 and 0.5 < stats.n_plastic / n < 0.8
+
+    # (i) slices vs oracle, bit for bit
+    sig, p, ct = m.device_view("stress"), m.device_view("p"), m.device_view("Ct")
+    w = 50_000
+    for start in (0, n // 2 - 17, n - w):
+        st = ss.zero_state(w)
+        for k in range(1, K):
+            st = ss.advance(ss.integrate(synth.strain(w, 0, AMP, k, K, start=start), st, VOCE))
+        ref = ss.integrate(synth.strain(w, 0, AMP, K, K, start=start), st, VOCE)
+        sl = slice(start, start + w)
+        assert np.array_equal(sig[:, sl].cpu().numpy().T, ref["stress"])
+        assert np.array_equal(p[0, sl].cpu().numpy(), ref["p"])
+        assert np.array_equal(ct[:, sl].cpu().numpy().T.reshape(w, 6, 6), ref["Ct"])
+
+    # (ii) properties over all points, evaluated on the device in chunks
+    flag, n_iter, resid, fail = m.diagnostics()
+    assert int(flag.sum()) == stats.n_plastic and int(n_iter.max()) == stats.max_iter and fail.sum() == 0
+    flag_d = torch.from_numpy(flag).cuda().bool()
+    p0 = m.device_view("p", gen=0)
+    lam, mu = 70e3 * 0.3 / 1.3 / 0.4, 70e3 / 2 / 1.3
+    C = torch.zeros(36, dtype=torch.float64, device="cuda")
+    for j in range(6):
+        for i in range(6):
+            C[j * 6 + i] = (lam if (i < 3 and j < 3) else 0.0) + (2 * mu if i == j else 0.0)
+    chunk = 10_000_000
+    worst_f, worst_el = 0.0, -1e300
+    for s0 in range(0, n, chunk):
+        sl = slice(s0, s0 + chunk)
+        sg = sig[:, sl]
+        pm = sg[:3].mean(dim=0)
+        dev = sg.clone()
+        dev[:3] -= pm
+        seq = torch.sqrt(1.5 * (dev * dev).sum(dim=0))
+        sy = 350.0 + 150.0 * (1 - torch.exp(-1e3 * p[0, sl]))
+        f = seq - sy
+        fl = flag_d[sl]
+        worst_f = max(worst_f, f[fl].abs().max().item())
+        worst_el = max(worst_el, f[~fl].max().item())
+        assert (p[0, sl] >= p0[0, sl]).all()
+        c = ct[:, sl]
+        for j in range(6):
+            for i in range(j + 1, 6):
+                assert torch.equal(c[j * 6 + i], c[i * 6 + j])
+        assert torch.equal(c[:, ~fl], C[:, None].expand(-1, int((~fl).sum())))
+    assert worst_f < 1e-9 * 350.0 and worst_el <= 1e-9 * 350.0
+
+
+def test_cfg3_fefp_1e7_points(jm):
+    import torch
+
+    n = 10_000_000
+    m = jm.CUDAMaterial(jm.FeFpJ2Plasticity(
+        elasticity=jm.LinearElasticIsotropic(E=FEFP["E"], nu=FEFP["nu"]),
+        yield_stress=jm.VoceHardening(sig0=FEFP["sig0"], sigu=FEFP["sigu"], b=FEFP["b"])))
+    m.set_data_manager(n)
+    m.enable_diagnostics()
+    for k in range(1, K):
+        m.synth_gradients(0, 3e-2, k, K)
+        m.integrate_resident()
+        m.data_manager.update()
+    m.synth_gradients(0, 3e-2, K, K)
+    stats = m.integrate_resident()
+    assert stats.n_fail == 0 and 0.5 < stats.n_plastic / n < 0.95
+    P, p, be, ct, F = (m.device_view(k) for k in ("PK1", "p", "be_bar", "Ct", "F"))
+    w = 20_000
+    for start in (0, n - w):
+        st = fefp.virgin_state(w)
+        for k in range(1, K):
+            st = fefp.advance(fefp.integrate(synth.defgrad(w, 0, 3e-2, k, K, start=start), st, FEFP))
+        ref = fefp.integrate(synth.defgrad(w, 0, 3e-2, K, K, start=start), st, FEFP)
+        sl = slice(start, start + w)
+        assert np.array_equal(P[:, sl].cpu().numpy().T, ref["PK1"])
+        assert np.array_equal(be[:, sl].cpu().numpy().T, ref["be_bar"])
+        assert np.array_equal(ct[:, sl].cpu().numpy().T.reshape(w, 9, 9), ref["Ct"])
+    # det(be_bar) = 1 and yield consistency of the Kirchhoff stress over all points
+    r = 2 ** -0.5
+    b = be
+    det = (b[0] * (b[1] * b[2] - (b[5] * r) ** 2) - (b[3] * r) * ((b[3] * r) * b[2] - (b[5] * r) * (b[4] * r))
+           + (b[4] * r) * ((b[3] * r) * (b[5] * r) - b[1] * (b[4] * r)))
+    assert (det - 1).abs().max().item() < 5e-12
+    I9 = fefp.IDX9
+    tau = [[sum(P[I9[i][k]] * F[I9[j][k]] for k in range(3)) for j in range(3)] for i in range(3)]
+    tr = (tau[0][0] + tau[1][1] + tau[2][2]) / 3
+    ss2 = sum(((tau[i][j] - (tr if i == j else 0)) ** 2) for i in range(3) for j in range(3))
+    vm = torch.sqrt(1.5 * ss2)
+    sy = 500.0 + 250.0 * (1 - torch.exp(-1000.0 * p[0]))
+    flag = torch.from_numpy(m.diagnostics()[0]).cuda().bool()
+    assert (vm - sy)[flag].abs().max().item() < 1e-8 * 500
+    assert (vm - sy)[~flag].max().item() < 1e-8 * 500
+    assert (tau[0][1] - tau[1][0]).abs().max().item() < 1e-8
