@@ -891,6 +891,28 @@ int dxm_host_alloc(void** ptr, int64_t bytes) {
   return 0;
 }
 
+int dxm_host_register(void* ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return fail("dxm_host_register: bad argument");
+  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return 0;
+  }
+  CK(e);
+  return 0;
+}
+
+int dxm_host_unregister(void* ptr) {
+  if (!ptr) return 0;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e == cudaErrorHostMemoryNotRegistered) {
+    cudaGetLastError();
+    return 0;
+  }
+  CK(e);
+  return 0;
+}
+
 int dxm_host_free(void* ptr) {
   if (ptr) CK(cudaFreeHost(ptr));
   return 0;

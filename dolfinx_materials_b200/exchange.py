@@ -1,0 +1,141 @@
+"""GPU-aware replacement for the material-facing half of ``QuadratureMap.update`` / ``advance``
+(reference ``dolfinx_materials/quadrature_map.py:297-360``) -- SURVEY.md section 8(f) rank 1.
+
+What the reference does around every ``integrate`` call, on the host, per Newton iteration:
+gather ``_get_vals(gradient)[dofs, :]`` (a copy), ``np.concatenate``, three ``np.isnan`` scans over
+flux / isv / Ct, then fancy-index scatters ``fun.x.array[dofs] = arr`` for the flux, every internal state
+variable and the flattened tangent (``utils.py:136-143``).  Once the update itself runs at HBM speed these
+passes dominate.  ``QuadratureExchange`` keeps the same observable result (the same values end up in the same
+``x.array`` vectors) and removes them:
+
+* contiguous-range fast path: when the map covers all cells (``cells is None`` in the reference, the common
+  case) ``dofs`` is the identity, so the gradient ``x.array`` is handed to the library as is and the device
+  DMAs flux and tangent straight into the (page-locked) ``x.array`` of their Functions;
+* the NaN scans are replaced by the fail count reduced on the device;
+* internal state variables stay on the GPU during Newton iterations and are fetched once, in ``advance()``.
+
+Cell subsets fall back to one gather into / scatter out of page-locked staging arrays (same numpy
+indexing as the reference).  The class works on any objects exposing a flat float64 ``x.array`` (dolfinx
+``fem.Function``) or on plain ndarrays, so it runs without dolfinx.
+"""
+
+import warnings
+
+import numpy as np
+
+from . import PerformanceWarning
+from .material import PinnedArray, pin_array
+
+
+def _flat(fun):
+    """``fun.x.array`` for Function-like objects, the array itself otherwise."""
+    x = getattr(fun, "x", None)
+    arr = x.array if x is not None else getattr(fun, "array", fun)
+    if not isinstance(arr, np.ndarray) or arr.dtype != np.float64 or not arr.flags.c_contiguous:
+        raise TypeError("expected a C-contiguous float64 array (or an object with .x.array)")
+    return arr
+
+
+class QuadratureExchange:
+    def __init__(self, material, num_cells, num_qp, gradients, fluxes, internal_state_variables, jacobian_flatten,
+                 cells=None, pin=True):
+        self.material = material
+        self.num_qp = int(num_qp)
+        if len(material.gradients) != 1 or len(material.fluxes) != 1:
+            raise NotImplementedError("single-gradient / single-flux materials only (as the CUDA behaviours are)")
+        self.gname, self.gdim = next(iter(material.gradients.items()))
+        self.fname, self.fdim = next(iter(material.fluxes.items()))
+        self.grad = _flat(gradients[self.gname])
+        self.flux = _flat(fluxes[self.fname])
+        self.isv = {k: _flat(internal_state_variables[k]) for k in material.internal_state_variables}
+        self.jac = _flat(jacobian_flatten)
+        ntot = int(num_cells) * self.num_qp
+        self.identity = cells is None or (
+            len(cells) == num_cells and np.array_equal(np.asarray(cells), np.arange(num_cells))
+        )
+        if self.identity:
+            self.cells = np.arange(num_cells, dtype=np.int32)
+            self.dofs = None
+            self.n = ntot
+        else:
+            self.cells = np.asarray(cells, dtype=np.int32)
+            self.dofs = (np.repeat(self.num_qp * self.cells[:, None], self.num_qp, axis=1)
+                         + np.arange(self.num_qp)[None, :]).ravel()
+            self.n = len(self.dofs)
+        material.set_data_manager(self.n)
+        for name, prop in material.material_properties.items():
+            material.update_material_property(name, np.asarray(prop))
+        self._unpin = []
+        self._stage = None
+        if self.identity and pin:
+            for a in (self.grad, self.flux, self.jac, *self.isv.values()):
+                self._unpin.append(pin_array(a))
+        elif not self.identity:
+            nisv = sum(material.internal_state_variables.values())
+            self._stage = (PinnedArray((self.n, self.gdim)), PinnedArray((self.n, self.fdim)),
+                           PinnedArray((self.n, self.fdim * self.gdim)), PinnedArray((self.n, max(nisv, 1))))
+        self._initialized = False
+        self.last_stats = None
+
+    def close(self):
+        for u in self._unpin:
+            u()
+        self._unpin = []
+
+    # ---- quadrature_map.py:281-295 -------------------------------------------------------------------
+    def _take(self, flat, dim):
+        vals = flat.reshape(-1, max(1, dim))
+        return vals if self.identity else vals[self.dofs]
+
+    def initialize_state(self):
+        state = {self.gname: self._take(self.grad, self.gdim), self.fname: self._take(self.flux, self.fdim)}
+        for k, d in self.material.internal_state_variables.items():
+            state[k] = self._take(self.isv[k], d)
+        self.material.set_initial_state_dict(state)
+        self._initialized = True
+
+    def update_initial_state(self, field_name, value):
+        arrs = {self.gname: (self.grad, self.gdim), self.fname: (self.flux, self.fdim)}
+        arrs.update({k: (self.isv[k], d) for k, d in self.material.internal_state_variables.items()})
+        flat, dim = arrs[field_name]
+        vals = flat.reshape(-1, max(1, dim))
+        new = np.full((self.n, max(1, dim)), value, dtype=np.float64)
+        if self.identity:
+            vals[:] = new
+        else:
+            vals[self.dofs] = new
+        self.material.set_initial_state_dict({field_name: new})
+
+    # ---- quadrature_map.py:297-334 ---------------------------------------------------------------------
+    def update(self, dt=0):
+        """The gradient ``x.array`` must hold this iteration's evaluated gradients (what
+        ``QuadratureExpression.eval`` leaves there, ``quadrature_function.py:45-51``)."""
+        if not self._initialized:
+            self.initialize_state()
+        m = self.material
+        if self.identity:
+            stats = m.integrate_into(self.grad, self.flux, None, self.jac, dt)
+        else:
+            g, f, c, _ = self._stage
+            np.take(self.grad.reshape(-1, self.gdim), self.dofs, axis=0, out=g.array)
+            stats = m.integrate_into(g.array, f.array, None, c.array, dt)
+            self.flux.reshape(-1, self.fdim)[self.dofs] = f.array
+            self.jac.reshape(-1, self.fdim * self.gdim)[self.dofs] = c.array
+        self.last_stats = stats
+        if stats.n_fail:
+            warnings.warn(f"{stats.n_fail} Gauss point(s) failed their constitutive update", PerformanceWarning)
+        return stats
+
+    # ---- quadrature_map.py:350-360 -----------------------------------------------------------------------
+    def advance(self):
+        m = self.material
+        m.data_manager.update()
+        if self.identity:
+            m.read_state_into(self.fname, self.flux)
+            for k in m.internal_state_variables:
+                m.read_state_into(k, self.isv[k])
+        else:
+            final = m.get_final_state_dict()
+            self.flux.reshape(-1, self.fdim)[self.dofs] = final[self.fname]
+            for k, d in m.internal_state_variables.items():
+                self.isv[k].reshape(-1, max(1, d))[self.dofs] = final[k]

@@ -55,6 +55,17 @@ class _Pinned:
         self._fin = weakref.finalize(self, lib.dxm_host_free, ctypes.c_void_p(self.ptr))
 
 
+def pin_array(arr):
+    """Page-lock a caller-owned ndarray in place (``dxm_host_register``); returns a callable that
+    releases it.  Long-lived arrays only (registration costs ~0.2 ms / MB)."""
+    lib = _lib.load()
+    if not arr.flags.c_contiguous:
+        raise ValueError("only C-contiguous arrays can be page-locked")
+    addr = ctypes.c_void_p(arr.ctypes.data)
+    check(lib.dxm_host_register(addr, arr.nbytes), "dxm_host_register")
+    return lambda: lib.dxm_host_unregister(addr)
+
+
 PinnedArray = _Pinned  # public name: ``PinnedArray(shape).array`` is a page-locked ndarray view
 
 
@@ -281,6 +292,46 @@ class CUDAMaterial:
         )
         self._finish(rc, stats)
         return flux.array, isv.array, ct.array
+
+    def integrate_into(self, gradients, flux_out=None, isv_out=None, ct_out=None, dt=0):
+        """Same update as :meth:`integrate`, but results are written into caller-owned C-contiguous
+        float64 arrays (any of them may be ``None`` = not transferred).  With arrays page-locked by
+        :func:`pin_array` (e.g. the ``x.array`` of the dolfinx Quadrature Functions) the device DMAs
+        straight into them: no staging copy, no scatter.  Returns :class:`IntegrationStats`."""
+        self._require_handle()
+        lib = _lib.load()
+        ng = sum(self.gradients.values())
+        nf = sum(self.fluxes.values())
+        ni = sum(self.internal_state_variables.values())
+        g = np.asarray(gradients)
+        if g.dtype != np.float64 or not g.flags.c_contiguous or g.size != self._n * ng:
+            raise ValueError(f"gradients must be C-contiguous float64 with {self._n * ng} entries")
+
+        def ptr(a, size, name):
+            if a is None:
+                return None
+            if a.dtype != np.float64 or not a.flags.c_contiguous or a.size != size or not a.flags.writeable:
+                raise ValueError(f"{name} must be a writeable C-contiguous float64 array with {size} entries")
+            return a.ctypes.data_as(ctypes.c_void_p)
+
+        stats = Stats()
+        rc = lib.dxm_integrate(
+            self._h, g.ctypes.data_as(ctypes.c_void_p), MEM_HOST, float(dt),
+            ptr(flux_out, self._n * nf, "flux_out"), ptr(isv_out, self._n * ni, "isv_out"),
+            ptr(ct_out, self._n * nf * ng, "ct_out"), MEM_HOST, ctypes.byref(stats),
+        )
+        self._finish(rc, stats)
+        return self.last_stats
+
+    def read_state_into(self, key, out, gen=1):
+        """Fetch one state field (``(n, dim)`` AoS) into a caller-owned array (lazy D2H of internal
+        state: only ``advance()`` / ``project_on`` need it, ``quadrature_map.py:350-360``)."""
+        self._require_handle()
+        dim = self.variables[key]
+        if out.dtype != np.float64 or not out.flags.c_contiguous or out.size != self._n * dim:
+            raise ValueError(f"out must be C-contiguous float64 with {self._n * dim} entries")
+        check(_lib.load().dxm_get_state(self._h, gen, key.encode(), out.ctypes.data_as(ctypes.c_void_p), MEM_HOST),
+              "dxm_get_state")
 
     # ---- device-resident extensions ------------------------------------------------------------
     def integrate_resident(self, dt=0, wait=True):

@@ -113,6 +113,11 @@ int dxm_synth_gradients(dxm_handle* h, int recipe, uint64_t seed, double amp, in
 /* pinned host memory helpers (the Python wrapper allocates its output arrays with these) */
 int dxm_host_alloc(void** ptr, int64_t bytes);
 int dxm_host_free(void* ptr);
+/* page-lock / release a caller-owned host array in place (e.g. a dolfinx Function's x.array), so that
+ * dxm_integrate / dxm_get_state DMA straight into it -- the "contiguous-range fast path" that replaces the
+ * fancy-index gather/scatter of utils.py:98-143 when a QuadratureMap covers all cells */
+int dxm_host_register(void* ptr, int64_t bytes);
+int dxm_host_unregister(void* ptr);
 
 /* measurement support */
 int64_t dxm_launch_count(void);                       /* kernels launched by this library so far */
