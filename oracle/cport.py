@@ -1,0 +1,113 @@
+"""ctypes front-end of the plain-C oracle (``oracle/c/dxm_oracle.c``), same call signatures and return
+dictionaries as ``oracle.small_strain.integrate`` / ``oracle.fefp.integrate``.  TEST INFRASTRUCTURE ONLY."""
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "liboracle.so")
+_lib = None
+_NAMES = ("E", "nu", "sig0", "H", "sigu", "b")
+
+
+def load(build=True):
+    global _lib
+    if _lib is None:
+        src = os.path.join(HERE, "c", "dxm_oracle.c")
+        if build and (not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src)):
+            subprocess.run(["make", "-s", "-C", HERE], check=True)
+        _lib = ctypes.CDLL(LIB)
+    return _lib
+
+
+THREADS = 1  # row blocks are processed on this many Python threads (ctypes releases the GIL)
+
+
+def set_threads(n):
+    global THREADS
+    THREADS = max(1, int(n))
+
+
+def _run_blocks(n, call):
+    """call(lo, hi) over contiguous row blocks, in parallel when THREADS > 1"""
+    if THREADS == 1 or n < 4096:
+        call(0, n)
+        return
+    from concurrent.futures import ThreadPoolExecutor
+
+    edges = np.linspace(0, n, THREADS + 1).astype(np.int64)
+    with ThreadPoolExecutor(THREADS) as ex:
+        list(ex.map(lambda k: call(int(edges[k]), int(edges[k + 1])), range(THREADS)))
+
+
+def _props(props, n):
+    vals = dict(props)
+    vals.setdefault("H", 0.0)
+    vals.setdefault("sigu", vals["sig0"])
+    vals.setdefault("b", 0.0)
+    arrs, per = [], []
+    for k in _NAMES:
+        a = np.ascontiguousarray(np.asarray(vals[k], dtype=np.float64).ravel())
+        if a.size not in (1, n):
+            raise ValueError(f"property {k}: {a.size} values for {n} points")
+        arrs.append(a)
+        per.append(1 if a.size == n and n > 1 or (a.size == n and np.asarray(vals[k]).ndim > 0) else 0)
+    pers = (ctypes.c_int * 6)(*per)
+
+    def ptrs(lo):
+        return (ctypes.c_void_p * 6)(*[a.ctypes.data + (8 * lo if f else 0) for a, f in zip(arrs, per)])
+
+    return arrs, ptrs, pers
+
+
+def _c(a, lo=0):
+    return ctypes.c_void_p(a.ctypes.data + lo * a.strides[0])
+
+
+def small_strain(eps, state, props, newton_cap=25, rtol=1e-12):
+    lib = load()
+    eps = np.ascontiguousarray(eps, dtype=np.float64)
+    n = eps.shape[0]
+    e_old = np.ascontiguousarray(np.asarray(state["strain"], dtype=np.float64).reshape(n, 6))
+    s_old = np.ascontiguousarray(np.asarray(state["stress"], dtype=np.float64).reshape(n, 6))
+    p_old = np.ascontiguousarray(np.asarray(state["p"], dtype=np.float64).reshape(n))
+    ep_old = np.ascontiguousarray(np.asarray(state["epsp"], dtype=np.float64).reshape(n, 6))
+    keep, ptrs, pers = _props(props, n)
+    sig, p, epsp, Ct = np.empty((n, 6)), np.empty(n), np.empty((n, 6)), np.empty((n, 6, 6))
+    flag, fail = np.empty(n, np.uint8), np.empty(n, np.uint8)
+    n_iter, resid = np.empty(n, np.int32), np.empty(n)
+    def call(lo, hi):
+        lib.dxo_small_strain(ctypes.c_int64(hi - lo), _c(eps, lo), _c(e_old, lo), _c(s_old, lo), _c(p_old, lo),
+                             _c(ep_old, lo), ptrs(lo), pers, ctypes.c_int(newton_cap), ctypes.c_double(rtol),
+                             _c(sig, lo), _c(p, lo), _c(epsp, lo), _c(Ct, lo), _c(flag, lo), _c(n_iter, lo),
+                             _c(resid, lo), _c(fail, lo))
+
+    _run_blocks(n, call)
+    del keep
+    return {"strain": eps, "stress": sig, "p": p, "epsp": epsp, "Ct": Ct, "flag": flag, "n_iter": n_iter,
+            "resid": resid, "fail": fail}
+
+
+def fefp(F, state, props, newton_cap=25, rtol=1e-12):
+    lib = load()
+    F = np.ascontiguousarray(F, dtype=np.float64)
+    n = F.shape[0]
+    Fo = np.ascontiguousarray(np.asarray(state["F"], dtype=np.float64).reshape(n, 9))
+    p_old = np.ascontiguousarray(np.asarray(state["p"], dtype=np.float64).reshape(n))
+    beo = np.ascontiguousarray(np.asarray(state["be_bar"], dtype=np.float64).reshape(n, 6))
+    keep, ptrs, pers = _props(props, n)
+    P, p, be, Ct = np.empty((n, 9)), np.empty(n), np.empty((n, 6)), np.empty((n, 9, 9))
+    flag, fail = np.empty(n, np.uint8), np.empty(n, np.uint8)
+    n_iter, resid = np.empty(n, np.int32), np.empty(n)
+    def call(lo, hi):
+        lib.dxo_fefp(ctypes.c_int64(hi - lo), _c(F, lo), _c(Fo, lo), _c(p_old, lo), _c(beo, lo), ptrs(lo), pers,
+                     ctypes.c_int(newton_cap), ctypes.c_double(rtol), _c(P, lo), _c(p, lo), _c(be, lo), _c(Ct, lo),
+                     _c(flag, lo), _c(n_iter, lo), _c(resid, lo), _c(fail, lo))
+
+    _run_blocks(n, call)
+    del keep
+    return {"F": F, "PK1": P, "p": p, "be_bar": be, "Ct": Ct, "flag": flag, "n_iter": n_iter, "resid": resid,
+            "fail": fail}
