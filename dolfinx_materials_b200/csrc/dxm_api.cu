@@ -166,7 +166,12 @@ int launch_soa_to_aos(dxm_handle* h, cudaStream_t st, const double* src, int64_t
 
 int ensure_staging(dxm_handle* h) {
   if (h->chunk) return 0;
-  h->chunk = std::min<int64_t>(kChunk, (h->n + 1) & ~int64_t(1));
+  // ~8 pipeline stages for mid-size batches (H2D | update | D2H overlap), 32 Ki .. 512 Ki points per chunk
+  int64_t c = (h->n + 7) / 8;
+  c = std::max<int64_t>(c, 32768);
+  c = std::min<int64_t>(c, kChunk);
+  c = (c + 255) & ~int64_t(255);
+  h->chunk = std::min<int64_t>(c, (h->n + 1) & ~int64_t(1));
   if (h->chunk < 2) h->chunk = 2;
   const int64_t nout = h->nflux + h->nisv + h->nct;
   for (int s = 0; s < 2; ++s) {

@@ -100,3 +100,30 @@ def test_resident_synth_matches_oracle(jm):
     ref = fefp.integrate(F, fefp.virgin_state(n), PROPS)
     assert np.array_equal(material.device_view("PK1").cpu().numpy().T, ref["PK1"])
     assert np.array_equal(material.device_view("Ct").cpu().numpy().T.reshape(n, 9, 9), ref["Ct"])
+
+
+def test_per_point_properties(jm):
+    """Heterogeneous FeFp batch: per-Gauss-point E, nu, sig0, sigu, b, H (quadrature_map.py:160-172) incl. an
+    elastic class (sig0 = inf) -- exercises the PERPOINT instantiation of the kernel."""
+    n = 20011
+    cls = np.arange(n) % 3
+    props = {
+        "E": np.where(cls == 1, 90e3, 70e3), "nu": np.where(cls == 1, 0.25, 0.3),
+        "sig0": np.where(cls == 2, np.inf, 500.0), "sigu": np.where(cls == 2, np.inf, np.where(cls == 1, 600.0, 750.0)),
+        "b": np.where(cls == 1, 50.0, 1000.0), "H": np.where(cls == 0, 100.0, 0.0),
+    }
+    material = make(jm, n)
+    for k, v in props.items():
+        material.update_material_property(k, v)
+    st = fefp.virgin_state(n)
+    for k in range(1, 4):
+        F = synth.defgrad(n, 7, 4e-2, k, 3)
+        P, isv, Ct = material.integrate(F)
+        ref = fefp.integrate(F, st, props)
+        flag, n_iter, _, fail = material.diagnostics()
+        assert np.array_equal(flag, ref["flag"]) and np.array_equal(n_iter, ref["n_iter"]) and fail.sum() == 0
+        assert np.array_equal(P, ref["PK1"]) and np.array_equal(Ct, ref["Ct"])
+        assert np.array_equal(isv[:, 1:], ref["be_bar"])
+        material.data_manager.update()
+        st = fefp.advance(ref)
+    assert ref["flag"][cls == 2].sum() == 0 and ref["flag"][cls == 0].mean() > 0.3
