@@ -52,6 +52,13 @@ SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int64],
     ),
+    "dxm_mesh_create": (
+        ctypes.c_int,
+        [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+         ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)],
+    ),
+    "dxm_mesh_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "dxm_eval_gradient": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "dxm_host_alloc": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64]),
     "dxm_host_free": (ctypes.c_int, [ctypes.c_void_p]),
     "dxm_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),

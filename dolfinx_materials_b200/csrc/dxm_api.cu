@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/dxm.h"
+#include "dxm_fe_gradient.cuh"
 #include "dxm_fefp.cuh"
 #include "dxm_layout.cuh"
 #include "dxm_small_strain.cuh"
@@ -984,6 +985,109 @@ int dxm_copy_peak(int device, int64_t bytes, double* gbs) {
   return 0;
 }
 
+
+// ---- FE gradient evaluation ---------------------------------------------------------
+struct dxm_mesh {
+  int device = 0, tdim = 3, nd = 4, nqp = 1;
+  int64_t num_cells = 0, num_nodes = 0, num_dofs = 0;
+  double *coords = nullptr, *dphi = nullptr, *u = nullptr;
+  int32_t *geom_dofs = nullptr, *u_dofs = nullptr;
+};
+
+int dxm_mesh_destroy(dxm_mesh* m) {
+  if (!m) return 0;
+  cudaSetDevice(m->device);
+  cudaFree(m->coords);
+  cudaFree(m->dphi);
+  cudaFree(m->u);
+  cudaFree(m->geom_dofs);
+  cudaFree(m->u_dofs);
+  delete m;
+  return 0;
+}
+
+int dxm_mesh_create(int device, int tdim, int64_t num_cells, int64_t num_nodes, const double* coords,
+                    const int32_t* geom_dofmap, int ndofs_cell, const int32_t* u_dofmap, int64_t num_dofs,
+                    int nqp, const double* dphi, dxm_mesh** out) {
+  if (!out) return fail("dxm_mesh_create: out is NULL");
+  *out = nullptr;
+  if (tdim != 2 && tdim != 3) return fail("dxm_mesh_create: tdim must be 2 or 3");
+  if (num_cells <= 0 || num_nodes <= 0 || num_dofs <= 0 || ndofs_cell <= 0 || nqp <= 0 || !coords ||
+      !geom_dofmap || !u_dofmap || !dphi)
+    return fail("dxm_mesh_create: bad argument");
+  CK(cudaSetDevice(device));
+  dxm_mesh* m = new dxm_mesh();
+  m->device = device;
+  m->tdim = tdim;
+  m->nd = ndofs_cell;
+  m->nqp = nqp;
+  m->num_cells = num_cells;
+  m->num_nodes = num_nodes;
+  m->num_dofs = num_dofs;
+  auto up = [&](void** d, const void* h, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(d, bytes);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+  };
+  cudaError_t e = up((void**)&m->coords, coords, sizeof(double) * 3 * num_nodes);
+  if (e == cudaSuccess) e = up((void**)&m->geom_dofs, geom_dofmap, sizeof(int32_t) * (tdim + 1) * num_cells);
+  if (e == cudaSuccess) e = up((void**)&m->u_dofs, u_dofmap, sizeof(int32_t) * ndofs_cell * num_cells);
+  if (e == cudaSuccess) e = up((void**)&m->dphi, dphi, sizeof(double) * nqp * ndofs_cell * tdim);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->u, sizeof(double) * num_dofs * tdim);
+  if (e != cudaSuccess) {
+    dxm_mesh_destroy(m);
+    return fail(std::string("dxm_mesh_create: ") + cudaGetErrorString(e));
+  }
+  *out = m;
+  return 0;
+}
+
+int dxm_eval_gradient(dxm_mesh* m, dxm_handle* h, const double* u, int mem, int kind) {
+  if (!m || !h || !u) return fail("dxm_eval_gradient: NULL argument");
+  if (m->device != h->device) return fail("dxm_eval_gradient: mesh and material live on different devices");
+  if (kind != 0 && kind != 1) return fail("dxm_eval_gradient: kind must be 0 (strain) or 1 (F)");
+  if ((kind == 0 ? 6 : 9) != h->ngrad)
+    return fail("dxm_eval_gradient: gradient kind does not match the behaviour's gradient size");
+  if (m->num_cells * m->nqp != h->n)
+    return fail("dxm_eval_gradient: num_cells*nqp = " + std::to_string(m->num_cells * m->nqp) +
+                " but the material has " + std::to_string(h->n) + " Gauss points");
+  if (mem != DXM_MEM_HOST && mem != DXM_MEM_DEVICE) return fail("dxm_eval_gradient: bad mem kind");
+  if (set_device(h)) return -1;
+  CK(cudaMemcpyAsync(m->u, u, sizeof(double) * m->num_dofs * m->tdim,
+                     mem == DXM_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+  FeGradArgs a{};
+  a.coords = m->coords;
+  a.geom_dofs = m->geom_dofs;
+  a.u_dofs = m->u_dofs;
+  a.u = m->u;
+  a.dphi = m->dphi;
+  a.out = h->gen[1 - h->i0];  // s1's gradient block
+  a.ld = h->ld;
+  a.num_cells = m->num_cells;
+  a.nd = m->nd;
+  a.nqp = m->nqp;
+  a.kind = kind;
+  const int block = 128;
+  const int grid = (int)((m->num_cells + block - 1) / block);
+  if (m->tdim == 3) {
+    if (m->nd == 4)
+      fe_gradient_kernel<3, 4><<<grid, block, 0, h->stream>>>(a);
+    else if (m->nd == 10)
+      fe_gradient_kernel<3, 10><<<grid, block, 0, h->stream>>>(a);
+    else
+      fe_gradient_kernel<3, 0><<<grid, block, 0, h->stream>>>(a);
+  } else {
+    if (m->nd == 3)
+      fe_gradient_kernel<2, 3><<<grid, block, 0, h->stream>>>(a);
+    else if (m->nd == 6)
+      fe_gradient_kernel<2, 6><<<grid, block, 0, h->stream>>>(a);
+    else
+      fe_gradient_kernel<2, 0><<<grid, block, 0, h->stream>>>(a);
+  }
+  LAUNCH_CHECK();
+  if (mem == DXM_MEM_HOST) CK(cudaStreamSynchronize(h->stream));  // the caller's u is free again
+  return 0;
+}
 
 int dxm_stream_peak(int device, int64_t n, int nread, int nwrite, double* gbs) {
   if (!gbs || n < 1) return fail("dxm_stream_peak: bad argument");

@@ -110,6 +110,22 @@ int dxm_get_diagnostics(dxm_handle* h, uint8_t* flag, int32_t* n_iter, double* r
 int dxm_synth_gradients(dxm_handle* h, int recipe, uint64_t seed, double amp, int k, int K,
                         int64_t start);
 
+/* GPU gradient evaluation for affine simplex meshes -- replaces
+ * QuadratureExpression.eval (quadrature_function.py:45-51) + get_gradient_vals (quadrature_map.py:251-253) for the
+ * registered expressions of the hot-path demos: kind 0 = Mandel vector of sym(grad u) (utils.py:146-165),
+ * kind 1 = 9-vector of I + grad u (utils.py:168-190).  The mesh object holds device copies of
+ *   coords (num_nodes,3) [mesh.geometry.x], geom_dofmap (num_cells,tdim+1) [mesh.geometry.dofmap],
+ *   u_dofmap (num_cells,ndofs_cell) [V.dofmap.list], dphi (nqp,ndofs_cell,tdim) [basix tabulate, derivative 1].
+ * dxm_eval_gradient copies the blocked displacement vector u (num_dofs*tdim) and writes the gradients of all
+ * num_cells*nqp points straight into the material's gradient buffer; follow with
+ * dxm_integrate(h, NULL, DXM_MEM_RESIDENT, ...). */
+typedef struct dxm_mesh dxm_mesh;
+int dxm_mesh_create(int device, int tdim, int64_t num_cells, int64_t num_nodes, const double* coords,
+                    const int32_t* geom_dofmap, int ndofs_cell, const int32_t* u_dofmap, int64_t num_dofs,
+                    int nqp, const double* dphi, dxm_mesh** out);
+int dxm_mesh_destroy(dxm_mesh* m);
+int dxm_eval_gradient(dxm_mesh* m, dxm_handle* h, const double* u, int mem, int kind);
+
 /* pinned host memory helpers (the Python wrapper allocates its output arrays with these) */
 int dxm_host_alloc(void** ptr, int64_t bytes);
 int dxm_host_free(void* ptr);
