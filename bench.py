@@ -252,6 +252,20 @@ def workload_config(args, world):
     }
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads (and therefore its first-touch page-locked buffers) to the CPUs NVML
+    reports as local to its GPU: with 8 ranks on one box the e2e leg is bound by host-side D2H bandwidth,
+    and remote-NUMA pinned buffers halve it.  Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return True
+    except Exception:  # noqa: BLE001
+        return False
+
+
 def load_traffic(n):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
     (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum at a stated n), scaled to
@@ -290,6 +304,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     build.build_library()
