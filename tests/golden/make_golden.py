@@ -11,7 +11,8 @@ unused dolfinx import `dolfinx.common.Timer`, generic.py:2):
   * the same reference machinery (`Material.integrate`, per-point `_vmap` loop, `s1.set_item`,
     `data_manager.update()`) driving a per-point `constitutive_update` that calls the oracle for one
     point -> j2_voce_history.npz / j2_linear_history.npz : pins that the batched oracle + state carry
-    equals the reference's point-by-point protocol over a load history.  (The J2 arithmetic itself is
+    equals the reference's point-by-point protocol over a load history; fefp_history.npz likewise for the
+    finite-strain behaviour (gradient F, flux PK1, state p + be_bar).  (The J2 arithmetic itself is
     not in the reference tree -- it lives in un-vendored jaxmat -- so these vectors pin protocol and
     regression, not jaxmat parity; see oracle/__init__.py.)
 """
@@ -51,6 +52,7 @@ sys.path.insert(0, "/root/reference")
 from dolfinx_materials.generic import Material  # noqa: E402  (the reference)
 from dolfinx_materials.python_materials.elasticity import LinearElasticIsotropic  # noqa: E402
 
+from oracle import fefp  # noqa: E402
 from oracle import small_strain as ss  # noqa: E402
 from oracle import synth  # noqa: E402
 
@@ -121,10 +123,55 @@ def j2_history(name, props, n, amp, K, seed):
     np.savez(os.path.join(HERE, name), **out)
 
 
+class PointwiseFeFp(Material):
+    """FeFp as a per-point reference-style material: the reference's own integrate/_vmap/DataManager drive it."""
+
+    def __init__(self, props):
+        super().__init__()
+        self.props = props
+
+    @property
+    def gradients(self):
+        return {"F": 9}
+
+    @property
+    def fluxes(self):
+        return {"PK1": 9}
+
+    @property
+    def internal_state_variables(self):
+        return {"p": 1, "be_bar": 6}
+
+    def constitutive_update(self, F, state, dt):
+        st = {"F": state["F"].reshape(1, 9), "PK1": state["PK1"].reshape(1, 9), "p": state["p"].reshape(1),
+              "be_bar": state["be_bar"].reshape(1, 6)}
+        out = fefp.integrate(F.reshape(1, 9), st, self.props)
+        new = {"F": F, "PK1": out["PK1"][0], "p": out["p"], "be_bar": out["be_bar"][0]}
+        return out["Ct"][0], new
+
+
+def fefp_history(name, props, n, amp, K, seed):
+    mat = PointwiseFeFp(props)
+    mat.set_data_manager(n)
+    virgin = fefp.virgin_state(n)
+    mat.set_initial_state_dict({"F": virgin["F"], "be_bar": virgin["be_bar"]})
+    out = {"props_keys": np.array(sorted(props)), "props_vals": np.array([props[k] for k in sorted(props)])}
+    for k in range(1, K + 1):
+        F = synth.defgrad(n, seed, amp, k, K)
+        flux, isv, Ct = mat.integrate(F)
+        out[f"F{k}"] = F
+        out[f"flux{k}"] = np.array(flux)
+        out[f"isv{k}"] = np.array(isv)
+        out[f"Ct{k}"] = np.array(Ct)
+        mat.data_manager.update()
+    np.savez(os.path.join(HERE, name), **out)
+
+
 if __name__ == "__main__":
     elastic_reference()
     j2_history("j2_voce_history.npz", dict(E=70e3, nu=0.3, sig0=350.0, sigu=500.0, b=1e3), 96, 1.25e-2, 4, 0)
     j2_history("j2_linear_history.npz", dict(E=70e3, nu=0.3, sig0=250.0, H=5e3), 48, 1.25e-2, 3, 5)
+    fefp_history("fefp_history.npz", dict(E=70e3, nu=0.3, sig0=500.0, sigu=750.0, b=1000.0), 40, 4e-2, 3, 3)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

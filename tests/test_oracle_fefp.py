@@ -139,3 +139,24 @@ def test_inverted_element_is_flagged():
     F[1, 0] = -1.0  # det F < 0 relative to the identity reference
     out = fefp.integrate(F, fefp.virgin_state(3), PROPS)
     assert out["fail"].tolist() == [0, 1, 0]
+
+
+def test_history_matches_reference_protocol_run():
+    """tests/golden/fefp_history.npz: the reference's own Material.integrate / _vmap / DataManager drove a
+    per-point FeFp material over a 3-increment history (make_golden.py); the batched oracle with explicit
+    state carry must reproduce it exactly.  Pins protocol + regression, not jaxmat parity."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fefp_history.npz"))
+    props = dict(zip([str(k) for k in g["props_keys"]], [float(v) for v in g["props_vals"]]))
+    n = g["F1"].shape[0]
+    st = fefp.virgin_state(n)
+    k = 1
+    while f"F{k}" in g:
+        out = fefp.integrate(g[f"F{k}"], st, props)
+        assert np.array_equal(out["PK1"], g[f"flux{k}"])
+        assert np.array_equal(out["p"], g[f"isv{k}"][:, 0]) and np.array_equal(out["be_bar"], g[f"isv{k}"][:, 1:])
+        assert np.array_equal(out["Ct"], g[f"Ct{k}"])
+        st = fefp.advance(out)
+        k += 1
+    assert out["flag"].any()
