@@ -92,6 +92,7 @@ struct dxm_handle {
   int num_sms = 148;
   int ppt = 1;
   int minb = 2;
+  int vote = 1;
   std::atomic<int> refs{1};
 };
 
@@ -252,6 +253,7 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
     a.b = prop(h, 5);
     for (int i = 0; i < kNProp; ++i) a.pp[i] = h->pp ? h->pp + (int64_t)i * ld : nullptr;
     a.stats = h->d_stats;
+    a.vote = h->vote;
     a.d_flag = h->d_flag;
     a.d_iter = h->d_iter;
     a.d_resid = h->d_resid;
@@ -288,6 +290,7 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
     a.pb = h->pp + 5 * ld;
   }
   a.stats = h->d_stats;
+  a.vote = h->vote;
   a.d_flag = h->d_flag;
   a.d_iter = h->d_iter;
   a.d_resid = h->d_resid;
@@ -467,6 +470,8 @@ int dxm_create(int behaviour, int device, int64_t n, dxm_handle** out) {
   h->ppt = (env && std::atoi(env) == 2) ? 2 : 1;
   env = std::getenv("DXM_MINB");
   h->minb = env ? std::atoi(env) : 2;
+  env = std::getenv("DXM_VOTE");
+  h->vote = env ? std::atoi(env) : 1;
   if (behaviour == DXM_FEFP_VOCE) {
     h->ngrad = 9;
     h->nflux = 9;

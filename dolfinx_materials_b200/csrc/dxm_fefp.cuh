@@ -31,6 +31,7 @@ struct FeFpArgs {
   double E, mu, kappa, sig0, H, dsu, b;
   const double* pp[6];  // per-point E, nu, sig0, H, sigu, b
   StatSlot* stats;
+  int vote;
   uint8_t* d_flag;
   int32_t* d_iter;
   double* d_resid;
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(128, MINB)
 
   for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     const int64_t loc = tile * blockDim.x + threadIdx.x;
+    const unsigned warp_mask = __ballot_sync(0xffffffffu, loc < a.count);
     if (loc >= a.count) continue;
     const int64_t i0 = a.start + loc;
 
@@ -197,39 +199,43 @@ __global__ void __launch_bounds__(128, MINB)
     double dp = 0.0, t = t0, resid = 0.0;
     int n_iter = 0;
     bool fail = false;
-    if (flag) {
+    {
+      // 2x2 Newton, warp-synchronous with a warp-vote early exit (see dxm_small_strain.cuh)
+      bool active = flag;
       const double tol1 = kFeNewtonRtol * seq;
-      for (int it = 0;; ++it) {
-        const double alpha = 1.0 - (c * t) * dp;
-        const double p = p_old + dp;
-        const double sy = (sig0 + H * p) + dsu * (1.0 - ecur);
-        const double r1 = (seq - (threemu * t) * dp) - sy;
-        const double a2 = alpha * alpha;
-        const double r2 = ((t * t) * t - (0.5 * a2) * (dd * t)) + ((a2 * alpha) * d3 - 1.0);
-        if (fabs(r1) <= tol1 && fabs(r2) <= kFeNewtonRtol) {
-          resid = fabs(r1);
-          break;
+      for (int it = 0; a.vote ? __any_sync(warp_mask, active) : active; ++it) {
+        if (active) {
+          const double alpha = 1.0 - (c * t) * dp;
+          const double p = p_old + dp;
+          const double sy = (sig0 + H * p) + dsu * (1.0 - ecur);
+          const double r1 = (seq - (threemu * t) * dp) - sy;
+          const double a2 = alpha * alpha;
+          const double r2 = ((t * t) * t - (0.5 * a2) * (dd * t)) + ((a2 * alpha) * d3 - 1.0);
+          if (fabs(r1) <= tol1 && fabs(r2) <= kFeNewtonRtol) {
+            resid = fabs(r1);
+            active = false;
+          } else if (it == kFeNewtonCap) {
+            resid = fabs(r1);
+            fail = true;
+            active = false;
+          } else {
+            const double dsy = H + bdsu * ecur;
+            const double g = 3.0 * (a2 * d3) - (alpha * dd) * t;
+            const double J11 = -(threemu * t) - dsy;
+            const double J12 = -(threemu * dp);
+            const double ct = c * t;
+            const double cdp = c * dp;
+            const double J21 = -(g * ct);
+            const double J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp;
+            const double rdet = 1.0 / (J11 * J22 - J12 * J21);
+            const double dp_new = dp + (J12 * r2 - r1 * J22) * rdet;
+            const double t_new = t + (J21 * r1 - J11 * r2) * rdet;
+            dp = dp_new;
+            t = t_new;
+            ecur = exp_c(-(b * (p_old + dp)));
+            ++n_iter;
+          }
         }
-        if (it == kFeNewtonCap) {
-          resid = fabs(r1);
-          fail = true;
-          break;
-        }
-        const double dsy = H + bdsu * ecur;
-        const double g = 3.0 * (a2 * d3) - (alpha * dd) * t;
-        const double J11 = -(threemu * t) - dsy;
-        const double J12 = -(threemu * dp);
-        const double ct = c * t;
-        const double cdp = c * dp;
-        const double J21 = -(g * ct);
-        const double J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp;
-        const double rdet = 1.0 / (J11 * J22 - J12 * J21);
-        const double dp_new = dp + (J12 * r2 - r1 * J22) * rdet;
-        const double t_new = t + (J21 * r1 - J11 * r2) * rdet;
-        dp = dp_new;
-        t = t_new;
-        ecur = exp_c(-(b * (p_old + dp)));
-        ++n_iter;
       }
     }
     const double alpha = flag ? (1.0 - (c * t) * dp) : 1.0;

@@ -40,6 +40,7 @@ struct SmallStrainArgs {
   // per-point properties (PERPOINT == true), each [ld]
   const double *pE, *pnu, *psig0, *pH, *psigu, *pb;
   StatSlot* stats;
+  int vote;  // 1: warp-vote (__any_sync) Newton loop exit, 0: per-lane exit (A/B knob DXM_VOTE)
   // optional diagnostics (DIAG == true)
   uint8_t* d_flag;
   int32_t* d_iter;
@@ -58,7 +59,8 @@ __device__ __forceinline__ void j2_point(const PointProps& m, const double (&eps
                                          const double p_old, const double (&ep_old)[6],
                                          double (&sig)[6], double& p_new, double (&epsp)[6],
                                          double (&nrm)[6], double& A, double& B, double& gamma,
-                                         bool& flag, int& n_iter, double& resid, bool& fail) {
+                                         bool& flag, int& n_iter, double& resid, bool& fail,
+                                         const unsigned warp_mask, const bool vote) {
   const double twomu = 2.0 * m.mu;
   const double threemu = 3.0 * m.mu;
   double de[6], st[6], s[6];
@@ -99,28 +101,32 @@ __device__ __forceinline__ void j2_point(const PointProps& m, const double (&eps
     }
     const double f = seq - sy0;
     flag = f > 0.0;
-    if (flag) {
-      if (HARD == HARD_LINEAR || bdsu == 0.0) {
-        dp = f / (threemu + m.H);  // closed-form radial return (mfront :57-60)
-      } else {
-        const double tol = kNewtonRtol * seq;
-        for (int it = 0;; ++it) {
+    // closed-form radial return (mfront :57-60) for linear hardening / no saturation term
+    const bool closed = (HARD == HARD_LINEAR) || (bdsu == 0.0);
+    if (flag && closed) dp = f / (threemu + m.H);
+    if (HARD == HARD_GENERAL) {
+      // capped scalar Newton, warp-synchronous: every lane of the warp stays in the loop until the
+      // warp vote says no lane is still iterating (early exit as soon as the slowest lane converged)
+      bool active = flag && !closed;
+      const double tol = kNewtonRtol * seq;
+      for (int it = 0; vote ? __any_sync(warp_mask, active) : active; ++it) {
+        if (active) {
           const double p = p_old + dp;
           const double sy = (m.sig0 + m.H * p) + m.dsu * (1.0 - ecur);
           const double r = (seq - threemu * dp) - sy;
           if (fabs(r) <= tol) {
             resid = fabs(r);
-            break;
-          }
-          if (it == kNewtonCap) {
+            active = false;
+          } else if (it == kNewtonCap) {
             resid = fabs(r);
             fail = true;
-            break;
+            active = false;
+          } else {
+            const double dsy = m.H + bdsu * ecur;
+            dp = dp + r / (threemu + dsy);
+            ecur = exp_c(-(m.b * (p_old + dp)));
+            ++n_iter;
           }
-          const double dsy = m.H + bdsu * ecur;
-          dp = dp + r / (threemu + dsy);
-          ecur = exp_c(-(m.b * (p_old + dp)));
-          ++n_iter;
         }
       }
     }
@@ -170,6 +176,8 @@ __global__ void __launch_bounds__(256, MINB)
 
   for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     const int64_t loc = (tile * blockDim.x + threadIdx.x) * PPT;  // local index within launch
+    // lanes of this warp that own points in this tile (the vote mask of the local Newton loop)
+    const unsigned warp_mask = __ballot_sync(0xffffffffu, loc < a.count);
     if (loc >= a.count) continue;
     const int64_t i0 = a.start + loc;
 
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(256, MINB)
       int n_iter;
       double resid;
       j2_point<HARD>(m, e1, e0, s0, p_old[k], ep0, so, p_new[k], epo, nn, A[k], B[k], gamma[k],
-                     flag, n_iter, resid, fail);
+                     flag, n_iter, resid, fail, warp_mask, a.vote != 0);
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
         sig[c][k] = so[c];

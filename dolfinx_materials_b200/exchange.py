@@ -38,8 +38,9 @@ def _flat(fun):
 
 class QuadratureExchange:
     def __init__(self, material, num_cells, num_qp, gradients, fluxes, internal_state_variables, jacobian_flatten,
-                 cells=None, pin=True):
+                 cells=None, pin=True, strict=True):
         self.material = material
+        self.strict = strict
         self.num_qp = int(num_qp)
         if len(material.gradients) != 1 or len(material.fluxes) != 1:
             raise NotImplementedError("single-gradient / single-flux materials only (as the CUDA behaviours are)")
@@ -123,7 +124,12 @@ class QuadratureExchange:
             self.jac.reshape(-1, self.fdim * self.gdim)[self.dofs] = c.array
         self.last_stats = stats
         if stats.n_fail:
-            warnings.warn(f"{stats.n_fail} Gauss point(s) failed their constitutive update", PerformanceWarning)
+            # the reference asserts on NaN in flux / isv / Ct (quadrature_map.py:322-324); the device-side fail
+            # count covers those (non-finite results) plus local solves that hit their iteration cap
+            msg = f"{stats.n_fail} Gauss point(s) failed their constitutive update (max residual {stats.max_residual:.3e})"
+            if self.strict:
+                raise AssertionError(msg)
+            warnings.warn(msg, PerformanceWarning)
         return stats
 
     # ---- quadrature_map.py:350-360 -----------------------------------------------------------------------

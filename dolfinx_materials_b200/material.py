@@ -24,6 +24,15 @@ from . import PerformanceWarning, _lib
 from ._lib import MEM_DEVICE, MEM_HOST, MEM_RESIDENT, Stats, check
 
 
+try:  # same timer names as the reference when dolfinx is there (jaxmat.py:209-223, quadrature_map.py:320)
+    from dolfinx.common import Timer as _Timer
+except Exception:  # noqa: BLE001 - dolfinx is optional
+    import contextlib
+
+    def _Timer(name):
+        return contextlib.nullcontext()
+
+
 @dataclass
 class IntegrationStats:
     """Per-call statistics reduced on the device (fused replacement of the host NaN scans,
@@ -285,11 +294,12 @@ class CUDAMaterial:
             raise ValueError(f"gradients must have shape {(self._n, ng)}, got {g.shape}")
         flux, isv, ct = self._outputs()
         stats = Stats()
-        rc = lib.dxm_integrate(
-            self._h, g.ctypes.data_as(ctypes.c_void_p), MEM_HOST, float(dt),
-            ctypes.c_void_p(flux.ptr), ctypes.c_void_p(isv.ptr), ctypes.c_void_p(ct.ptr), MEM_HOST,
-            ctypes.byref(stats),
-        )
+        with _Timer("dxm: Constitutive update"):
+            rc = lib.dxm_integrate(
+                self._h, g.ctypes.data_as(ctypes.c_void_p), MEM_HOST, float(dt),
+                ctypes.c_void_p(flux.ptr), ctypes.c_void_p(isv.ptr), ctypes.c_void_p(ct.ptr), MEM_HOST,
+                ctypes.byref(stats),
+            )
         self._finish(rc, stats)
         return flux.array, isv.array, ct.array
 

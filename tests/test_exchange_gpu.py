@@ -83,3 +83,26 @@ def test_host_path_many_chunks_ragged(jm):
     mat.integrate_into(eps, f2, None, None)
     assert np.array_equal(f2, ref["stress"])
     unpin()
+
+
+def test_exchange_strict_failure_behaviour(jm):
+    """Non-finite gradients: strict mode raises AssertionError like the reference's NaN asserts
+    (quadrature_map.py:322-324); non-strict warns (mfront.py:269-272 convention)."""
+    from dolfinx_materials_b200.exchange import QuadratureExchange
+
+    ncell, nqp = 50, 1
+    for strict in (True, False):
+        mat = material(jm)
+        grad = synth.strain(ncell, 0, 1e-2, 1, 1).ravel()
+        grad[7] = np.nan
+        ex = QuadratureExchange(mat, ncell, nqp, {"strain": grad}, {"stress": np.zeros(ncell * 6)},
+                                {"p": np.zeros(ncell), "epsp": np.zeros(ncell * 6)}, np.zeros(ncell * 36), strict=strict)
+        ex.update_initial_state("strain", 0.0)
+        ex._initialized = True
+        if strict:
+            with pytest.raises(AssertionError):
+                ex.update()
+        else:
+            with pytest.warns(jm.PerformanceWarning):
+                assert ex.update().n_fail == 1
+        ex.close()
