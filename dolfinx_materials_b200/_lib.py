@@ -59,6 +59,17 @@ SIGNATURES = {
     ),
     "dxm_mesh_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "dxm_eval_gradient": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "dxm_mesh_set_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "dxm_element_forms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "dxm_system_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "dxm_system_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "dxm_system_set_bc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "dxm_system_set_lifting": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "dxm_assemble": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "dxm_system_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "dxm_system_nnz": (ctypes.c_int64, [ctypes.c_void_p]),
+    "dxm_system_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.POINTER(ctypes.c_int), c_double_p]),
     "dxm_host_alloc": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64]),
     "dxm_host_free": (ctypes.c_int, [ctypes.c_void_p]),
     "dxm_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),

@@ -337,7 +337,7 @@ class CUDAMaterial:
         """Fetch one state field (``(n, dim)`` AoS) into a caller-owned array (lazy D2H of internal
         state: only ``advance()`` / ``project_on`` need it, ``quadrature_map.py:350-360``)."""
         self._require_handle()
-        dim = self.variables[key]
+        dim = self.variables[key] if key != "Ct" else sum(a * b for a, b in self.tangent_blocks.values())
         if out.dtype != np.float64 or not out.flags.c_contiguous or out.size != self._n * dim:
             raise ValueError(f"out must be C-contiguous float64 with {self._n * dim} entries")
         check(_lib.load().dxm_get_state(self._h, gen, key.encode(), out.ctypes.data_as(ctypes.c_void_p), MEM_HOST),

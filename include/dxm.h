@@ -126,6 +126,43 @@ int dxm_mesh_create(int device, int tdim, int64_t num_cells, int64_t num_nodes, 
 int dxm_mesh_destroy(dxm_mesh* m);
 int dxm_eval_gradient(dxm_mesh* m, dxm_handle* h, const double* u, int mem, int kind);
 
+/* Fused flux / tangent -> element residual / stiffness contraction -- replaces, for the same
+ * affine-simplex / blocked-Lagrange setting as dxm_eval_gradient, the FFCx cell kernels DOLFINx runs over the
+ * Quadrature Functions that QuadratureMap.update fills (quadrature_map.py:331-334):
+ *   residual  Res = dot(flux, dgrad(v)) * qmap.dx          (assemble_vector, solvers.py:80-81)
+ *   tangent   Jac = qmap.derivative(Res, u, du)            (quadrature_map.py:132-158, layout :94-104)
+ * reading flux and Ct of the last dxm_integrate where they lie in HBM.  weights: reference-cell quadrature weights
+ * (basix.make_quadrature, quadrature_map.py:239-243).
+ * dxm_element_forms writes the element vectors fe (num_cells, nd*tdim) and matrices ke (num_cells, nd*tdim, nd*tdim)
+ * (row/col = a*tdim + r, the blocked local dof order; what MatSetValuesLocal / VecSetValuesLocal take); either
+ * pointer may be NULL; mem = DXM_MEM_HOST | DXM_MEM_DEVICE. */
+int dxm_mesh_set_weights(dxm_mesh* m, const double* weights);
+int dxm_element_forms(dxm_mesh* m, dxm_handle* h, int kind, double* fe, double* ke, int mem);
+
+/* Device-resident assembled system: CSR pattern of the blocked space (rowptr int64 [nrows+1], colidx int32 sorted
+ * within each row -- DOLFINx create_matrix / PETSc MatGetRowIJ), value array, right-hand side, optional Dirichlet
+ * marker (uint8 per global dof: constrained rows and columns receive no contribution, the diagonal is set to 1,
+ * the rhs entry to 0 -- the assemble_matrix(A, a, bcs) / set_bc convention for a Newton correction).
+ * dxm_assemble zeroes and fills values and/or rhs from the last dxm_integrate with fp64 atomics: the tangent
+ * (36 | 81 doubles per point) never leaves the device, only the assembled system does (dxm_system_get). */
+typedef struct dxm_system dxm_system;
+int dxm_system_create(int device, int64_t nrows, const int64_t* rowptr, const int32_t* colidx, dxm_system** out);
+int dxm_system_destroy(dxm_system* s);
+int dxm_system_set_bc(dxm_system* s, const uint8_t* marker); /* host array of nrows entries, NULL clears */
+/* prescribed solution values x_bc on the constrained dofs (host array of nrows entries, read where marker != 0;
+ * NULL: homogeneous).  dxm_assemble then moves the constrained columns to the right-hand side,
+ * rhs -= A[:, bc] x_bc, and sets rhs[bc] = x_bc (DOLFINx apply_lifting + set_bc, solvers.py:84-96) */
+int dxm_system_set_lifting(dxm_system* s, const double* values);
+int dxm_assemble(dxm_mesh* m, dxm_handle* h, int kind, dxm_system* s, int want_vector, int want_matrix);
+int dxm_system_get(dxm_system* s, double* values, double* rhs, int mem); /* either may be NULL */
+int64_t dxm_system_nnz(const dxm_system* s);
+/* Device-resident Krylov solve A x = rhs of the assembled system (BiCGStab, block x block Jacobi preconditioner,
+ * x0 = 0, stop at |r| <= rtol |rhs|); returns 0 converged, 1 maxit reached, < 0 error.  NOT part of the drop-in
+ * path -- the reference hands the system to PETSc (solvers.py:182-196); it exists so that the config-5 Newton loop
+ * can run in a DOLFINx/PETSc-free environment (scripts/newton_bar.py). */
+int dxm_system_solve(dxm_system* s, int block, double rtol, int maxit, double* x, int mem, int* iters,
+                     double* relres);
+
 /* pinned host memory helpers (the Python wrapper allocates its output arrays with these) */
 int dxm_host_alloc(void** ptr, int64_t bytes);
 int dxm_host_free(void* ptr);
