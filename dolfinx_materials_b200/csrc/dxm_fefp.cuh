@@ -97,9 +97,76 @@ __device__ __forceinline__ void inv3(const double (&A)[3][3], double (&Ai)[3][3]
     for (int j = 0; j < 3; ++j) Ai[i][j] = c[i][j] * rdet;
 }
 
-template <bool PERPOINT, bool DIAG, int MINB>
+struct FeFpLocalProps {
+  double threemu, sig0, H, dsu, bdsu, b;
+};
+
+// local 2x2 Newton in (dp, t); lanes outside `mask` must not call.  Inputs are six scalars per point, which is
+// what makes the block-level compaction below cheap.
+__device__ __forceinline__ void fefp_newton(const FeFpLocalProps& m, const double seq, const double dd,
+                                            const double d3, const double p_old, double& ecur, double& dp,
+                                            double& t, int& n_iter, double& resid, bool& fail, bool active,
+                                            const unsigned mask, const bool vote) {
+  const double c = m.threemu * (1.0 / seq);
+  const double tol1 = kFeNewtonRtol * seq;
+  for (int it = 0; vote ? __any_sync(mask, active) : active; ++it) {
+    if (active) {
+      const double alpha = 1.0 - (c * t) * dp;
+      const double p = p_old + dp;
+      const double sy = (m.sig0 + m.H * p) + m.dsu * (1.0 - ecur);
+      const double r1 = (seq - (m.threemu * t) * dp) - sy;
+      const double a2 = alpha * alpha;
+      const double r2 = ((t * t) * t - (0.5 * a2) * (dd * t)) + ((a2 * alpha) * d3 - 1.0);
+      if (fabs(r1) <= tol1 && fabs(r2) <= kFeNewtonRtol) {
+        resid = fabs(r1);
+        active = false;
+      } else if (it == kFeNewtonCap) {
+        resid = fabs(r1);
+        fail = true;
+        active = false;
+      } else {
+        const double dsy = m.H + m.bdsu * ecur;
+        const double g = 3.0 * (a2 * d3) - (alpha * dd) * t;
+        const double J11 = -(m.threemu * t) - dsy;
+        const double J12 = -(m.threemu * dp);
+        const double ct = c * t;
+        const double cdp = c * dp;
+        const double J21 = -(g * ct);
+        const double J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp;
+        const double rdet = 1.0 / (J11 * J22 - J12 * J21);
+        const double dp_new = dp + (J12 * r2 - r1 * J22) * rdet;
+        const double t_new = t + (J21 * r1 - J11 * r2) * rdet;
+        dp = dp_new;
+        t = t_new;
+        ecur = exp_c(-(m.b * (p_old + dp)));
+        ++n_iter;
+      }
+    }
+  }
+}
+
+// block-level compaction of the plastic points' local solves (see CompactSmem in dxm_small_strain.cuh)
+struct FeFpCompactSmem {
+  double a[6][128];  // in: seq, dd, d3, t0, p_old, ecur   out: dp, t, ecur, resid
+  int meta[128];
+  int warp_count[4];
+};
+template <bool C>
+struct FeFpCompactStore {
+  FeFpCompactSmem s;
+  __device__ __forceinline__ FeFpCompactSmem* get() { return &s; }
+};
+template <>
+struct FeFpCompactStore<false> {
+  __device__ __forceinline__ FeFpCompactSmem* get() { return nullptr; }
+};
+
+template <bool PERPOINT, bool DIAG, int MINB, bool COMPACT = false>
 __global__ void __launch_bounds__(128, MINB)
     dxm_fefp_kernel(const FeFpArgs a) {
+  static_assert(!COMPACT || !PERPOINT, "compaction: uniform properties only");
+  __shared__ FeFpCompactStore<COMPACT> cs_storage;
+  FeFpCompactSmem* cs = cs_storage.get();
   const int64_t ld = a.ld;
   const int64_t ntile = (a.count + blockDim.x - 1) / blockDim.x;
   PointStats acc;
@@ -107,8 +174,10 @@ __global__ void __launch_bounds__(128, MINB)
   for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     const int64_t loc = tile * blockDim.x + threadIdx.x;
     const unsigned warp_mask = __ballot_sync(0xffffffffu, loc < a.count);
-    if (loc >= a.count) continue;
-    const int64_t i0 = a.start + loc;
+    const bool live = loc < a.count;
+    if (!COMPACT && !live) continue;
+    // COMPACT: every thread of the CTA takes part in the block-level exchange; dead lanes shadow point 0
+    const int64_t i0 = a.start + (live ? loc : 0);
 
     double A[3][3], Ao[3][3], Bo[3][3];
 #pragma unroll
@@ -200,42 +269,66 @@ __global__ void __launch_bounds__(128, MINB)
     int n_iter = 0;
     bool fail = false;
     {
-      // 2x2 Newton, warp-synchronous with a warp-vote early exit (see dxm_small_strain.cuh)
-      bool active = flag;
-      const double tol1 = kFeNewtonRtol * seq;
-      for (int it = 0; a.vote ? __any_sync(warp_mask, active) : active; ++it) {
-        if (active) {
-          const double alpha = 1.0 - (c * t) * dp;
-          const double p = p_old + dp;
-          const double sy = (sig0 + H * p) + dsu * (1.0 - ecur);
-          const double r1 = (seq - (threemu * t) * dp) - sy;
-          const double a2 = alpha * alpha;
-          const double r2 = ((t * t) * t - (0.5 * a2) * (dd * t)) + ((a2 * alpha) * d3 - 1.0);
-          if (fabs(r1) <= tol1 && fabs(r2) <= kFeNewtonRtol) {
-            resid = fabs(r1);
-            active = false;
-          } else if (it == kFeNewtonCap) {
-            resid = fabs(r1);
-            fail = true;
-            active = false;
-          } else {
-            const double dsy = H + bdsu * ecur;
-            const double g = 3.0 * (a2 * d3) - (alpha * dd) * t;
-            const double J11 = -(threemu * t) - dsy;
-            const double J12 = -(threemu * dp);
-            const double ct = c * t;
-            const double cdp = c * dp;
-            const double J21 = -(g * ct);
-            const double J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp;
-            const double rdet = 1.0 / (J11 * J22 - J12 * J21);
-            const double dp_new = dp + (J12 * r2 - r1 * J22) * rdet;
-            const double t_new = t + (J21 * r1 - J11 * r2) * rdet;
-            dp = dp_new;
-            t = t_new;
-            ecur = exp_c(-(b * (p_old + dp)));
-            ++n_iter;
-          }
+      FeFpLocalProps lp;
+      lp.threemu = threemu;
+      lp.sig0 = sig0;
+      lp.H = H;
+      lp.dsu = dsu;
+      lp.bdsu = bdsu;
+      lp.b = b;
+      const bool active = live && flag;
+      if (!COMPACT) {
+        // warp-synchronous with a warp-vote early exit (see dxm_small_strain.cuh)
+        fefp_newton(lp, seq, dd, d3, p_old, ecur, dp, t, n_iter, resid, fail, active, warp_mask, a.vote != 0);
+      } else {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        const unsigned bal = __ballot_sync(0xffffffffu, active);
+        if (lane == 0) cs->warp_count[w] = __popc(bal);
+        __syncthreads();
+        int base = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cnt = cs->warp_count[i];
+          base += i < w ? cnt : 0;
+          total += cnt;
         }
+        const int slot = base + __popc(bal & ((1u << lane) - 1u));
+        if (active) {
+          cs->a[0][slot] = seq;
+          cs->a[1][slot] = dd;
+          cs->a[2][slot] = d3;
+          cs->a[3][slot] = t0;
+          cs->a[4][slot] = p_old;
+          cs->a[5][slot] = ecur;
+        }
+        __syncthreads();
+        const bool solver = (int)threadIdx.x < total;
+        const unsigned smask = __ballot_sync(0xffffffffu, solver);
+        if (solver) {
+          const int k = threadIdx.x;
+          const double sq = cs->a[0][k], dd_s = cs->a[1][k], d3_s = cs->a[2][k], po = cs->a[4][k];
+          double ts = cs->a[3][k], ec = cs->a[5][k], d = 0.0, rs = 0.0;
+          int ni = 0;
+          bool fl = false;
+          fefp_newton(lp, sq, dd_s, d3_s, po, ec, d, ts, ni, rs, fl, true, smask, a.vote != 0);
+          cs->a[0][k] = d;
+          cs->a[1][k] = ts;
+          cs->a[2][k] = ec;
+          cs->a[3][k] = rs;
+          cs->meta[k] = ni | (fl ? 1 << 16 : 0);
+        }
+        __syncthreads();
+        if (active) {
+          dp = cs->a[0][slot];
+          t = cs->a[1][slot];
+          ecur = cs->a[2][slot];
+          resid = cs->a[3][slot];
+          const int mt = cs->meta[slot];
+          n_iter = mt & 0xffff;
+          fail = (mt >> 16) != 0;
+        }
+        __syncthreads();  // slots are reused by the next tile
+        if (!live) continue;
       }
     }
     const double alpha = flag ? (1.0 - (c * t) * dp) : 1.0;
@@ -372,14 +465,16 @@ __global__ void __launch_bounds__(128, MINB)
 }
 
 template <int MINB>
-inline const void* fefp_kernel_ptr(bool perpoint, bool diag) {
+inline const void* fefp_kernel_ptr(bool perpoint, bool diag, bool compact = false) {
+  if (compact && !perpoint && MINB == 4)
+    return diag ? (const void*)dxm_fefp_kernel<false, true, 4, true> : (const void*)dxm_fefp_kernel<false, false, 4, true>;
   return perpoint ? (diag ? (const void*)dxm_fefp_kernel<true, true, MINB>
                           : (const void*)dxm_fefp_kernel<true, false, MINB>)
                   : (diag ? (const void*)dxm_fefp_kernel<false, true, MINB>
                           : (const void*)dxm_fefp_kernel<false, false, MINB>);
 }
 
-inline int launch_fefp(const FeFpArgs& a, bool diag, int num_sms, cudaStream_t stream,
+inline int launch_fefp(const FeFpArgs& a, bool diag, bool compact, int num_sms, cudaStream_t stream,
                        std::atomic<long long>* launches, std::string* err) {
   const int block = 128;
   const int64_t ntile = (a.count + block - 1) / block;
@@ -388,7 +483,7 @@ inline int launch_fefp(const FeFpArgs& a, bool diag, int num_sms, cudaStream_t s
     const char* e = std::getenv("DXM_FEFP_MINB");
     return e ? std::atoi(e) : 4;
   }();
-  const void* k = minb == 4 ? fefp_kernel_ptr<4>(a.perpoint, diag)
+  const void* k = minb == 4 ? fefp_kernel_ptr<4>(a.perpoint, diag, compact)
                   : minb == 5 ? fefp_kernel_ptr<5>(a.perpoint, diag)
                               : fefp_kernel_ptr<3>(a.perpoint, diag);
   // a few tiles per CTA (see grid_for in dxm_api.cu); DXM_GRID=<k> forces k CTAs per SM

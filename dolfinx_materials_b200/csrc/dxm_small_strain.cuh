@@ -52,15 +52,66 @@ struct PointProps {
   double lam, mu, sig0, H, dsu, b;
 };
 
+// ---- block-level compaction of the local Newton solves ("warp compaction of plastic points") -------------------
+// The Voce Newton depends on three scalars per point (seq, p_old, exp(-b p_old)).  With COMPACT the plastic
+// points of a 256-point tile publish them to consecutive shared-memory slots (ballot + popc prefix inside the
+// warp, warp totals across the CTA), threads 0..n_plastic-1 each solve one slot, and the owners read dp back:
+// only ceil(n_plastic/32) warps execute the loop instead of every warp that holds at least one plastic lane.
+// Same arithmetic per point -> bit-identical results.  Uniform properties only.
+struct CompactSmem {
+  double a[3][256];      // in: seq, p_old, ecur   out: dp, ecur, resid
+  int meta[256];         // out: n_iter | fail << 16
+  int warp_count[8];
+};
+
+template <bool C>
+struct CompactStore {
+  CompactSmem s;
+  __device__ __forceinline__ CompactSmem* get() { return &s; }
+};
+template <>
+struct CompactStore<false> {
+  __device__ __forceinline__ CompactSmem* get() { return nullptr; }
+};
+
+// capped scalar Newton on r(dp) = seq - 3 mu dp - sigY(p_old + dp); lanes outside `mask` must not call
+__device__ __forceinline__ void voce_newton(const PointProps& m, const double threemu, const double bdsu,
+                                            const double seq, const double p_old, double& ecur, double& dp,
+                                            int& n_iter, double& resid, bool& fail, bool active,
+                                            const unsigned mask, const bool vote) {
+  const double tol = kNewtonRtol * seq;
+  for (int it = 0; vote ? __any_sync(mask, active) : active; ++it) {
+    if (active) {
+      const double p = p_old + dp;
+      const double sy = (m.sig0 + m.H * p) + m.dsu * (1.0 - ecur);
+      const double r = (seq - threemu * dp) - sy;
+      if (fabs(r) <= tol) {
+        resid = fabs(r);
+        active = false;
+      } else if (it == kNewtonCap) {
+        resid = fabs(r);
+        fail = true;
+        active = false;
+      } else {
+        const double dsy = m.H + bdsu * ecur;
+        dp = dp + r / (threemu + dsy);
+        ecur = exp_c(-(m.b * (p_old + dp)));
+        ++n_iter;
+      }
+    }
+  }
+}
+
 // One Gauss point.  Returns results through references; everything stays in registers.
-template <int HARD>
+template <int HARD, bool COMPACT>
 __device__ __forceinline__ void j2_point(const PointProps& m, const double (&eps)[6],
                                          const double (&e_old)[6], const double (&s_old)[6],
                                          const double p_old, const double (&ep_old)[6],
                                          double (&sig)[6], double& p_new, double (&epsp)[6],
                                          double (&nrm)[6], double& A, double& B, double& gamma,
                                          bool& flag, int& n_iter, double& resid, bool& fail,
-                                         const unsigned warp_mask, const bool vote) {
+                                         const unsigned warp_mask, const bool vote, const bool live,
+                                         CompactSmem* cs) {
   const double twomu = 2.0 * m.mu;
   const double threemu = 3.0 * m.mu;
   double de[6], st[6], s[6];
@@ -107,27 +158,51 @@ __device__ __forceinline__ void j2_point(const PointProps& m, const double (&eps
     if (HARD == HARD_GENERAL) {
       // capped scalar Newton, warp-synchronous: every lane of the warp stays in the loop until the
       // warp vote says no lane is still iterating (early exit as soon as the slowest lane converged)
-      bool active = flag && !closed;
-      const double tol = kNewtonRtol * seq;
-      for (int it = 0; vote ? __any_sync(warp_mask, active) : active; ++it) {
-        if (active) {
-          const double p = p_old + dp;
-          const double sy = (m.sig0 + m.H * p) + m.dsu * (1.0 - ecur);
-          const double r = (seq - threemu * dp) - sy;
-          if (fabs(r) <= tol) {
-            resid = fabs(r);
-            active = false;
-          } else if (it == kNewtonCap) {
-            resid = fabs(r);
-            fail = true;
-            active = false;
-          } else {
-            const double dsy = m.H + bdsu * ecur;
-            dp = dp + r / (threemu + dsy);
-            ecur = exp_c(-(m.b * (p_old + dp)));
-            ++n_iter;
-          }
+      const bool active = live && flag && !closed;
+      if (!COMPACT) {
+        voce_newton(m, threemu, bdsu, seq, p_old, ecur, dp, n_iter, resid, fail, active, warp_mask, vote);
+      } else {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        const unsigned bal = __ballot_sync(0xffffffffu, active);
+        if (lane == 0) cs->warp_count[w] = __popc(bal);
+        __syncthreads();
+        int base = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = cs->warp_count[i];
+          base += i < w ? c : 0;
+          total += c;
         }
+        const int slot = base + __popc(bal & ((1u << lane) - 1u));
+        if (active) {
+          cs->a[0][slot] = seq;
+          cs->a[1][slot] = p_old;
+          cs->a[2][slot] = ecur;
+        }
+        __syncthreads();
+        const bool solver = (int)threadIdx.x < total;
+        const unsigned smask = __ballot_sync(0xffffffffu, solver);
+        if (solver) {
+          const double sq = cs->a[0][threadIdx.x], po = cs->a[1][threadIdx.x];
+          double ec = cs->a[2][threadIdx.x], d = 0.0, rs = 0.0;
+          int ni = 0;
+          bool fl = false;
+          voce_newton(m, threemu, bdsu, sq, po, ec, d, ni, rs, fl, true, smask, vote);
+          cs->a[0][threadIdx.x] = d;
+          cs->a[2][threadIdx.x] = ec;
+          cs->a[1][threadIdx.x] = rs;
+          cs->meta[threadIdx.x] = ni | (fl ? 1 << 16 : 0);
+        }
+        __syncthreads();
+        if (active) {
+          dp = cs->a[0][slot];
+          ecur = cs->a[2][slot];
+          resid = cs->a[1][slot];
+          const int mt = cs->meta[slot];
+          n_iter = mt & 0xffff;
+          fail = (mt >> 16) != 0;
+        }
+        __syncthreads();  // slots are reused by the next tile
       }
     }
     if (HARD == HARD_GENERAL) Hp = m.H + bdsu * ecur;
@@ -167,9 +242,12 @@ __device__ __forceinline__ void j2_point(const PointProps& m, const double (&eps
   if (!isfinite(chk)) fail = true;
 }
 
-template <int HARD, bool PERPOINT, int PPT, bool DIAG, int MINB>
+template <int HARD, bool PERPOINT, int PPT, bool DIAG, int MINB, bool COMPACT = false>
 __global__ void __launch_bounds__(256, MINB)
     dxm_small_strain_kernel(const SmallStrainArgs a) {
+  static_assert(!COMPACT || (HARD == HARD_GENERAL && !PERPOINT && PPT == 1), "compaction: uniform Voce, PPT = 1");
+  __shared__ CompactStore<COMPACT> cs_storage;
+  CompactSmem* cs = cs_storage.get();
   const int64_t ld = a.ld;
   const int64_t ntile = (a.count + (int64_t)blockDim.x * PPT - 1) / ((int64_t)blockDim.x * PPT);
   PointStats acc;
@@ -178,8 +256,10 @@ __global__ void __launch_bounds__(256, MINB)
     const int64_t loc = (tile * blockDim.x + threadIdx.x) * PPT;  // local index within launch
     // lanes of this warp that own points in this tile (the vote mask of the local Newton loop)
     const unsigned warp_mask = __ballot_sync(0xffffffffu, loc < a.count);
-    if (loc >= a.count) continue;
-    const int64_t i0 = a.start + loc;
+    const bool live = loc < a.count;
+    if (!COMPACT && !live) continue;
+    // COMPACT: every thread of the CTA takes part in the block-level exchange; dead lanes shadow point 0
+    const int64_t i0 = a.start + (live ? loc : 0);
 
     double eps[6][PPT], e_old[6][PPT], s_old[6][PPT], ep_old[6][PPT], p_old[PPT];
 #pragma unroll
@@ -233,15 +313,15 @@ __global__ void __launch_bounds__(256, MINB)
       bool flag, fail;
       int n_iter;
       double resid;
-      j2_point<HARD>(m, e1, e0, s0, p_old[k], ep0, so, p_new[k], epo, nn, A[k], B[k], gamma[k],
-                     flag, n_iter, resid, fail, warp_mask, a.vote != 0);
+      j2_point<HARD, COMPACT>(m, e1, e0, s0, p_old[k], ep0, so, p_new[k], epo, nn, A[k], B[k], gamma[k],
+                              flag, n_iter, resid, fail, warp_mask, a.vote != 0, live, cs);
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
         sig[c][k] = so[c];
         epsp[c][k] = epo[c];
         nrm[c][k] = nn[c];
       }
-      const bool valid = (loc + k) < a.count;
+      const bool valid = live && (loc + k) < a.count;
       if (valid) {
         acc.n_plastic += flag ? 1u : 0u;
         acc.n_fail += fail ? 1u : 0u;
@@ -258,6 +338,7 @@ __global__ void __launch_bounds__(256, MINB)
     }
 
     // ---- stores: state then the 36 tangent entries (row-major j*6+i, symmetric) ---------------
+    if (COMPACT && !live) continue;
 #pragma unroll
     for (int c = 0; c < 6; ++c) stv<PPT>(a.sig + c * ld + i0, sig[c]);
     stv<PPT>(a.p + i0, p_new);
