@@ -25,7 +25,10 @@ PARITY STATUS
   not installable here, and the reference's only test on that path
   (``tests/test_FeFp_jax.py``) asserts nothing.  The restatement follows the published
   algorithm and is checked by self-consistency (finite-difference
-  tangents, yield consistency, det(be_bar)=1).
+  tangents, yield consistency, det(be_bar)=1) and against an independent complex-arithmetic
+  statement of jaxmat's Fischer-Burmeister residual systems whose solution is differentiated
+  exactly by the complex-step method -- the definition of the reference's jacfwd tangent
+  (``tests/test_oracle_exact_derivative.py``: stress to 1e-11, tangent to 1e-10).
 
 Canonical arithmetic
 --------------------
