@@ -1019,6 +1019,7 @@ struct dxm_mesh {
   double *coords = nullptr, *dphi = nullptr, *u = nullptr, *weights = nullptr;
   int32_t *geom_dofs = nullptr, *u_dofs = nullptr;
   double *d_fe = nullptr, *d_ke = nullptr;  // element-form staging for host outputs (lazy)
+  unsigned long long uid = 0;               // identity for caches keyed on a mesh (addresses get reused)
 };
 
 int dxm_mesh_destroy(dxm_mesh* m) {
@@ -1046,7 +1047,9 @@ int dxm_mesh_create(int device, int tdim, int64_t num_cells, int64_t num_nodes, 
       !geom_dofmap || !u_dofmap || !dphi)
     return fail("dxm_mesh_create: bad argument");
   CK(cudaSetDevice(device));
+  static std::atomic<unsigned long long> next_uid{1};
   dxm_mesh* m = new dxm_mesh();
+  m->uid = next_uid.fetch_add(1);
   m->device = device;
   m->tdim = tdim;
   m->nd = ndofs_cell;
@@ -1131,6 +1134,10 @@ struct dxm_system {
   bool lift_on = false;    // false: homogeneous
   unsigned long long* missing = nullptr;
   double* work = nullptr;  // Krylov workspace: 9 vectors + block inverses + scalar slots (lazy)
+  // per-cell block offsets into the pattern, built at the first assembly with a given mesh (node-blocked patterns)
+  int32_t* off = nullptr;
+  unsigned long long off_mesh = 0;  // uid of the mesh the table was built for
+  bool off_valid = false;
 };
 
 int dxm_mesh_set_weights(dxm_mesh* m, const double* weights) {
@@ -1243,6 +1250,7 @@ int dxm_system_destroy(dxm_system* s) {
   cudaFree(s->missing);
   cudaFree(s->lift);
   cudaFree(s->work);
+  cudaFree(s->off);
   delete s;
   return 0;
 }
@@ -1324,6 +1332,27 @@ int dxm_assemble(dxm_mesh* m, dxm_handle* h, int kind, dxm_system* s, int want_v
   a.bc = s->bc;
   a.lift = (s->bc && s->lift_on && want_vector && want_matrix) ? s->lift : nullptr;
   a.missing = s->missing;
+  if (want_matrix && s->off_mesh != m->uid) {
+    // first assembly of this mesh into this pattern: locate every (cell, node a, node b) block once
+    cudaFree(s->off);
+    s->off = nullptr;
+    s->off_valid = false;
+    s->off_mesh = m->uid;
+    const int64_t cnt = m->num_cells * m->nd * m->nd;
+    if (cudaMalloc((void**)&s->off, sizeof(int32_t) * cnt) == cudaSuccess) {
+      CK(cudaMemsetAsync(s->missing, 0, sizeof(unsigned long long), h->stream));
+      fe_offsets_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(m->u_dofs, m->num_cells, m->nd, m->tdim,
+                                                                            s->rowptr, s->colidx, s->off, s->missing);
+      LAUNCH_CHECK();
+      unsigned long long bad = 0;
+      CK(cudaMemcpyAsync(&bad, s->missing, sizeof(bad), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      s->off_valid = bad == 0;  // otherwise: not node-blocked or entries missing -> per-entry search path reports
+    } else {
+      cudaGetLastError();  // no room for the table: keep searching
+    }
+  }
+  a.off = (want_matrix && s->off_valid) ? s->off : nullptr;
   if (want_vector) CK(cudaMemsetAsync(s->rhs, 0, sizeof(double) * s->nrows, h->stream));
   if (want_matrix) CK(cudaMemsetAsync(s->vals, 0, sizeof(double) * s->nnz, h->stream));
   CK(cudaMemsetAsync(s->missing, 0, sizeof(unsigned long long), h->stream));

@@ -44,6 +44,7 @@ struct FeFormArgs {
   const uint8_t* bc;  // optional Dirichlet marker per global dof
   const double* lift;  // optional prescribed solution values on the constrained dofs: b -= A[:, bc] lift[bc]
   unsigned long long* missing;  // count of (row, col) pairs not found in the pattern
+  const int32_t* off;  // optional (num_cells, nd, nd): offset of node b's column block inside node a's rows
 };
 
 constexpr int kFeMaxNd = 20;  // generic path: up to P3 tetrahedra
@@ -287,13 +288,17 @@ __global__ void __launch_bounds__(256) fe_forms_kernel(const FeFormArgs a, const
     for (int b = 0; b < NDC; ++b) {
       if (ND == 0 && b >= nd) break;
       const int32_t cbase = ud[b] * TDIM;
-      int64_t pos = csr_find(a.colidx, lo, hi, cbase);
+      // node-blocked patterns: the offset of (node a, node b) inside the row was found once (fe_offsets_kernel)
+      int64_t pos = a.off ? (a.off[((c0 + lc) * nd + an) * nd + b] >= 0 ? lo + a.off[((c0 + lc) * nd + an) * nd + b] : -1)
+                          : csr_find(a.colidx, lo, hi, cbase);
 #pragma unroll
       for (int s = 0; s < TDIM; ++s) {
         const int32_t gcol = cbase + s;
         if (s > 0) {
+          if (a.off)
+            pos = pos >= 0 ? pos + 1 : -1;
           // blocked pattern: the columns of one node are consecutive; fall back to a search otherwise
-          if (pos >= 0 && pos + 1 < hi && a.colidx[pos + 1] == gcol)
+          else if (pos >= 0 && pos + 1 < hi && a.colidx[pos + 1] == gcol)
             pos = pos + 1;
           else
             pos = csr_find(a.colidx, lo, hi, gcol);
@@ -313,6 +318,31 @@ __global__ void __launch_bounds__(256) fe_forms_kernel(const FeFormArgs a, const
     if (a.lift && lifted != 0.0) atomicAdd(a.b + grow, -lifted);
     if (miss) atomicAdd(a.missing, (unsigned long long)miss);
   }
+}
+
+// One-off per (mesh, pattern): offset of node b's column block inside the rows of node a, for every cell.  Valid
+// only for node-blocked patterns (the TDIM rows of a node share one column structure made of whole TDIM-blocks,
+// which is what DOLFINx builds for a blocked space); `bad` counts violations -> the caller keeps the search path.
+__global__ void fe_offsets_kernel(const int32_t* u_dofs, int64_t num_cells, int nd, int tdim, const int64_t* rowptr,
+                                  const int32_t* colidx, int32_t* off, unsigned long long* bad) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= num_cells * nd * nd) return;
+  const int64_t c = i / (nd * nd);
+  const int an = (int)((i / nd) % nd), b = (int)(i % nd);
+  const int32_t* ud = u_dofs + c * nd;
+  const int64_t row0 = (int64_t)ud[an] * tdim;
+  const int32_t col0 = ud[b] * tdim;
+  const int64_t lo = rowptr[row0], hi = rowptr[row0 + 1];
+  const int64_t pos = csr_find(colidx, lo, hi, col0);
+  bool ok = pos >= 0 && pos + tdim <= hi;
+  if (ok)
+    for (int r = 0; r < tdim && ok; ++r) {
+      const int64_t lr = rowptr[row0 + r];
+      ok = rowptr[row0 + r + 1] - lr == hi - lo;
+      for (int s = 0; s < tdim && ok; ++s) ok = colidx[lr + (pos - lo) + s] == col0 + s;
+    }
+  off[i] = ok ? (int32_t)(pos - lo) : -1;
+  if (!ok) atomicAdd(bad, 1ull);
 }
 
 // unit diagonal on constrained rows (assemble_matrix(..., bcs) convention); rhs = prescribed value (set_bc)

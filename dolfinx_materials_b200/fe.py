@@ -115,6 +115,7 @@ class AssembledSystem:
         self._h = h
         self._fin = weakref.finalize(self, lib.dxm_system_destroy, h)
         self.nnz = int(lib.dxm_system_nnz(h))
+        self._pin_vals = self._pin_rhs = None
         if bc is not None:
             self.set_bc(bc)
 
@@ -137,9 +138,16 @@ class AssembledSystem:
         check(_lib.load().dxm_assemble(ev._h, ev.material._h, ev.kind, self._h, int(vector), int(matrix)), "dxm_assemble")
 
     def get(self, values=True, rhs=True):
-        """-> (CSR values (nnz,), rhs (nrows,)) host copies (``A.setValuesCSR(rowptr, colidx, values)``)."""
-        v = np.empty(self.nnz) if values else None
-        b = np.empty(self.nrows) if rhs else None
+        """-> (CSR values (nnz,), rhs (nrows,)) on the host (``A.setValuesCSR(rowptr, colidx, values)``).  The arrays
+        are page-locked buffers owned by this object and overwritten by the next ``get`` (copy to keep)."""
+        from .material import PinnedArray
+
+        if values and self._pin_vals is None:
+            self._pin_vals = PinnedArray((self.nnz,))
+        if rhs and self._pin_rhs is None:
+            self._pin_rhs = PinnedArray((self.nrows,))
+        v = self._pin_vals.array if values else None
+        b = self._pin_rhs.array if rhs else None
         check(_lib.load().dxm_system_get(self._h, _ptr(v), _ptr(b), MEM_HOST), "dxm_system_get")
         return v, b
 

@@ -60,7 +60,7 @@ def test_tet_element_forms_and_assembly(jm, order, finite):
         # global assembly, no constraints
         system.set_bc(None)
         system.assemble()
-        vals, b = system.get()
+        vals, b = (x.copy() for x in system.get())
         b_ref, A_ref = ff.assemble(ud, fe_ref, ke_ref, len(nodes), 3)
         scale = np.abs(ke_ref).max()
         import scipy.sparse as sp
@@ -72,7 +72,7 @@ def test_tet_element_forms_and_assembly(jm, order, finite):
         bc = np.repeat(nodes[:, 0] < 1e-9 + 0.03 * 1.0, 3)
         system.set_bc(bc)
         system.assemble()
-        vals, b = system.get()
+        vals, b = (x.copy() for x in system.get())
         b_ref, A_ref = ff.assemble(ud, fe_ref, ke_ref, len(nodes), 3, bc=bc)
         A = sp.csr_matrix((vals, colidx, rowptr), shape=A_ref.shape)
         assert bc.any() and abs(A - A_ref).max() <= 1e-12 * scale
@@ -81,7 +81,7 @@ def test_tet_element_forms_and_assembly(jm, order, finite):
         lift = np.where(bc, np.sin(np.arange(bc.size) * 0.37) * 1e-3, 0.0)
         system.set_lifting(lift)
         system.assemble()
-        vals2, b = system.get()
+        vals2, b = (x.copy() for x in system.get())
         b_ref, _ = ff.assemble(ud, fe_ref, ke_ref, len(nodes), 3, bc=bc, lift=lift)
         assert np.array_equal(vals2, vals) or np.allclose(vals2, vals, rtol=0, atol=1e-12 * scale)
         assert np.array_equal(b[bc], lift[bc]) and np.allclose(b, b_ref, rtol=0, atol=1e-12 * np.abs(b_ref).max())
