@@ -20,8 +20,10 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-Xcompiler",
     "-fPIC",
-    "-shared",
 ]
+
+# translation units of the library (kernels live in the .cuh files they include)
+UNITS = ["dxm_api.cu", "dxm_fe_api.cu", "dxm_peaks.cu"]
 
 
 def _nvcc():
@@ -47,14 +49,28 @@ def build_library(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     LIB.parent.mkdir(parents=True, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "dxm_api.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
+    objdir = ROOT / "lib" / "obj"
+    objdir.mkdir(exist_ok=True)
+    nvcc = _nvcc()
+    procs = []
+    for unit in UNITS:  # compiled concurrently, one nvcc per translation unit
+        cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", str(objdir / (unit[:-3] + ".o")), str(CSRC / unit)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    log = ""
+    for cmd, pr in procs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out + err)
+        log += err
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB),
+           *[str(objdir / (u[:-3] + ".o")) for u in UNITS]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print(log)
     return LIB
 
 

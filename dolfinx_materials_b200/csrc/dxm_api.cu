@@ -1,104 +1,22 @@
 // libdxm_cuda.so -- C ABI (include/dxm.h) over the sm_100a constitutive-update kernels.
 // Host side only: handle / buffer management, the chunked host<->device pipeline, statistics.
-#include <cuda_runtime.h>
-
-#include <atomic>
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "../../include/dxm.h"
-#include "dxm_fe_forms.cuh"
-#include "dxm_fe_gradient.cuh"
+// (FE-side entry points: dxm_fe_api.cu; measurement support: dxm_peaks.cu.)
+#include "dxm_internal.cuh"
 #include "dxm_fefp.cuh"
-#include "dxm_krylov.cuh"
 #include "dxm_layout.cuh"
 #include "dxm_small_strain.cuh"
 
 using namespace dxm;
 
-namespace {
-
+namespace dxm_detail {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+}  // namespace dxm_detail
 
-int fail(const std::string& msg) {
-  g_err = msg;
-  return -1;
-}
-
-#define CK(call)                                                                              \
-  do {                                                                                        \
-    cudaError_t e_ = (call);                                                                  \
-    if (e_ != cudaSuccess) {                                                                  \
-      return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
-                  std::to_string(__LINE__) + ")");                                            \
-    }                                                                                         \
-  } while (0)
-
-#define LAUNCH_CHECK()            \
-  do {                            \
-    g_launches.fetch_add(1);      \
-    CK(cudaGetLastError());       \
-  } while (0)
-
+namespace {
 constexpr int64_t kChunk = 1 << 19;  // points per pipeline chunk on the host path
-constexpr int kNProp = 6;
 const char* kPropNames[kNProp] = {"E", "nu", "sig0", "H", "sigu", "b"};
-
-struct Field {
-  const char* name;
-  int row;  // first SoA row inside a generation block
-  int dim;
-};
-
 }  // namespace
-
-struct dxm_handle {
-  int behaviour = 0, device = 0;
-  int64_t n = 0, ld = 0;
-  int ngrad = 0, nflux = 0, nisv = 0, nrows = 0, nct = 0;
-  std::vector<Field> fields;
-  double* gen[2] = {nullptr, nullptr};  // device SoA blocks [nrows][ld]
-  int i0 = 0;                           // gen[i0] is s0, gen[1-i0] is s1
-  bool s1_valid = false;                // false => s1 reads alias s0 (after update/revert)
-  double* ct = nullptr;                 // [nct][ld]
-  // properties
-  double uni[kNProp] = {0, 0, 0, 0, 0, 0};
-  bool set[kNProp] = {false, false, false, false, false, false};
-  bool perpoint = false;
-  double* pp = nullptr;  // [kNProp][ld]
-  // statistics
-  StatSlot* d_stats = nullptr;
-  StatSlot* h_stats = nullptr;  // pinned
-  dxm_stats last{};
-  bool stats_pending = false;
-  // streams / events
-  cudaStream_t stream = nullptr, own_stream = nullptr, s_in = nullptr, s_out = nullptr;
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr},
-              ev_packed[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
-  std::vector<cudaEvent_t> ev_k;  // kernel timing event pairs
-  int n_ev_used = 0;
-  // staging (device AoS), allocated lazily
-  int64_t chunk = 0;
-  double* d_in[2] = {nullptr, nullptr};
-  double* d_out[2] = {nullptr, nullptr};
-  // diagnostics
-  bool diag = false;
-  uint8_t *d_flag = nullptr, *d_fail = nullptr;
-  int32_t* d_iter = nullptr;
-  double* d_resid = nullptr;
-  int num_sms = 148;
-  int ppt = 1;
-  int minb = 2;
-  int vote = 1;
-  int compact = -1;  // DXM_COMPACT: 0 never, 1 always, unset = auto (FeFp only, by the last plastic fraction)
-  int64_t prev_plastic = 0, prev_points = 0;
-  std::atomic<int> refs{1};
-};
 
 namespace {
 
@@ -106,11 +24,6 @@ const Field* find_field(const dxm_handle* h, const char* name) {
   for (const Field& f : h->fields)
     if (std::strcmp(f.name, name) == 0) return &f;
   return nullptr;
-}
-
-int set_device(const dxm_handle* h) {
-  CK(cudaSetDevice(h->device));
-  return 0;
 }
 
 double* field_ptr(dxm_handle* h, int gen, const Field* f, bool for_read) {
@@ -950,564 +863,4 @@ int dxm_host_free(void* ptr) {
   return 0;
 }
 
-int dxm_fp64_peak(int device, double* tflops) {
-  if (!tflops) return fail("dxm_fp64_peak: NULL argument");
-  CK(cudaSetDevice(device));
-  cudaDeviceProp prop{};
-  CK(cudaGetDeviceProperties(&prop, device));
-  double* d = nullptr;
-  CK(cudaMalloc(&d, 8));
-  cudaEvent_t a, b;
-  CK(cudaEventCreate(&a));
-  CK(cudaEventCreate(&b));
-  const int iters = 1 << 15, block = 256, grid = prop.multiProcessorCount * 8;
-  double best = 0;
-  for (int rep = 0; rep < 5; ++rep) {
-    CK(cudaEventRecord(a));
-    fp64_fma_kernel<<<grid, block>>>(d, iters, 1.0);
-    LAUNCH_CHECK();
-    CK(cudaEventRecord(b));
-    CK(cudaEventSynchronize(b));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, a, b));
-    const double fl = 2.0 * 8.0 * iters * (double)block * grid;
-    best = std::max(best, fl / (ms * 1e-3) / 1e12);
-  }
-  cudaEventDestroy(a);
-  cudaEventDestroy(b);
-  cudaFree(d);
-  *tflops = best;
-  return 0;
-}
-
-int dxm_copy_peak(int device, int64_t bytes, double* gbs) {
-  if (!gbs || bytes < 16) return fail("dxm_copy_peak: bad argument");
-  CK(cudaSetDevice(device));
-  cudaDeviceProp prop{};
-  CK(cudaGetDeviceProperties(&prop, device));
-  double2 *s = nullptr, *d = nullptr;
-  CK(cudaMalloc(&s, bytes));
-  CK(cudaMalloc(&d, bytes));
-  CK(cudaMemset(s, 0, bytes));
-  cudaEvent_t a, b;
-  CK(cudaEventCreate(&a));
-  CK(cudaEventCreate(&b));
-  double best = 0;
-  for (int rep = 0; rep < 6; ++rep) {
-    CK(cudaEventRecord(a));
-    copy_kernel<<<prop.multiProcessorCount * 16, 256>>>(s, d, bytes / 16);
-    LAUNCH_CHECK();
-    CK(cudaEventRecord(b));
-    CK(cudaEventSynchronize(b));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, a, b));
-    best = std::max(best, 2.0 * bytes / (ms * 1e-3) / 1e9);
-  }
-  cudaEventDestroy(a);
-  cudaEventDestroy(b);
-  cudaFree(s);
-  cudaFree(d);
-  *gbs = best;
-  return 0;
-}
-
-
-// ---- FE gradient evaluation ---------------------------------------------------------
-struct dxm_mesh {
-  int device = 0, tdim = 3, nd = 4, nqp = 1;
-  int64_t num_cells = 0, num_nodes = 0, num_dofs = 0;
-  double *coords = nullptr, *dphi = nullptr, *u = nullptr, *weights = nullptr;
-  int32_t *geom_dofs = nullptr, *u_dofs = nullptr;
-  double *d_fe = nullptr, *d_ke = nullptr;  // element-form staging for host outputs (lazy)
-  unsigned long long uid = 0;               // identity for caches keyed on a mesh (addresses get reused)
-};
-
-int dxm_mesh_destroy(dxm_mesh* m) {
-  if (!m) return 0;
-  cudaSetDevice(m->device);
-  cudaFree(m->coords);
-  cudaFree(m->dphi);
-  cudaFree(m->u);
-  cudaFree(m->geom_dofs);
-  cudaFree(m->u_dofs);
-  cudaFree(m->weights);
-  cudaFree(m->d_fe);
-  cudaFree(m->d_ke);
-  delete m;
-  return 0;
-}
-
-int dxm_mesh_create(int device, int tdim, int64_t num_cells, int64_t num_nodes, const double* coords,
-                    const int32_t* geom_dofmap, int ndofs_cell, const int32_t* u_dofmap, int64_t num_dofs,
-                    int nqp, const double* dphi, dxm_mesh** out) {
-  if (!out) return fail("dxm_mesh_create: out is NULL");
-  *out = nullptr;
-  if (tdim != 2 && tdim != 3) return fail("dxm_mesh_create: tdim must be 2 or 3");
-  if (num_cells <= 0 || num_nodes <= 0 || num_dofs <= 0 || ndofs_cell <= 0 || nqp <= 0 || !coords ||
-      !geom_dofmap || !u_dofmap || !dphi)
-    return fail("dxm_mesh_create: bad argument");
-  CK(cudaSetDevice(device));
-  static std::atomic<unsigned long long> next_uid{1};
-  dxm_mesh* m = new dxm_mesh();
-  m->uid = next_uid.fetch_add(1);
-  m->device = device;
-  m->tdim = tdim;
-  m->nd = ndofs_cell;
-  m->nqp = nqp;
-  m->num_cells = num_cells;
-  m->num_nodes = num_nodes;
-  m->num_dofs = num_dofs;
-  auto up = [&](void** d, const void* h, size_t bytes) -> cudaError_t {
-    cudaError_t e = cudaMalloc(d, bytes);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
-  };
-  cudaError_t e = up((void**)&m->coords, coords, sizeof(double) * 3 * num_nodes);
-  if (e == cudaSuccess) e = up((void**)&m->geom_dofs, geom_dofmap, sizeof(int32_t) * (tdim + 1) * num_cells);
-  if (e == cudaSuccess) e = up((void**)&m->u_dofs, u_dofmap, sizeof(int32_t) * ndofs_cell * num_cells);
-  if (e == cudaSuccess) e = up((void**)&m->dphi, dphi, sizeof(double) * nqp * ndofs_cell * tdim);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&m->u, sizeof(double) * num_dofs * tdim);
-  if (e != cudaSuccess) {
-    dxm_mesh_destroy(m);
-    return fail(std::string("dxm_mesh_create: ") + cudaGetErrorString(e));
-  }
-  *out = m;
-  return 0;
-}
-
-int dxm_eval_gradient(dxm_mesh* m, dxm_handle* h, const double* u, int mem, int kind) {
-  if (!m || !h || !u) return fail("dxm_eval_gradient: NULL argument");
-  if (m->device != h->device) return fail("dxm_eval_gradient: mesh and material live on different devices");
-  if (kind != 0 && kind != 1) return fail("dxm_eval_gradient: kind must be 0 (strain) or 1 (F)");
-  if ((kind == 0 ? 6 : 9) != h->ngrad)
-    return fail("dxm_eval_gradient: gradient kind does not match the behaviour's gradient size");
-  if (m->num_cells * m->nqp != h->n)
-    return fail("dxm_eval_gradient: num_cells*nqp = " + std::to_string(m->num_cells * m->nqp) +
-                " but the material has " + std::to_string(h->n) + " Gauss points");
-  if (mem != DXM_MEM_HOST && mem != DXM_MEM_DEVICE) return fail("dxm_eval_gradient: bad mem kind");
-  if (set_device(h)) return -1;
-  CK(cudaMemcpyAsync(m->u, u, sizeof(double) * m->num_dofs * m->tdim,
-                     mem == DXM_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
-  FeGradArgs a{};
-  a.coords = m->coords;
-  a.geom_dofs = m->geom_dofs;
-  a.u_dofs = m->u_dofs;
-  a.u = m->u;
-  a.dphi = m->dphi;
-  a.out = h->gen[1 - h->i0];  // s1's gradient block
-  a.ld = h->ld;
-  a.num_cells = m->num_cells;
-  a.nd = m->nd;
-  a.nqp = m->nqp;
-  a.kind = kind;
-  const int block = 128;
-  const int grid = (int)((m->num_cells + block - 1) / block);
-  if (m->tdim == 3) {
-    if (m->nd == 4)
-      fe_gradient_kernel<3, 4><<<grid, block, 0, h->stream>>>(a);
-    else if (m->nd == 10)
-      fe_gradient_kernel<3, 10><<<grid, block, 0, h->stream>>>(a);
-    else
-      fe_gradient_kernel<3, 0><<<grid, block, 0, h->stream>>>(a);
-  } else {
-    if (m->nd == 3)
-      fe_gradient_kernel<2, 3><<<grid, block, 0, h->stream>>>(a);
-    else if (m->nd == 6)
-      fe_gradient_kernel<2, 6><<<grid, block, 0, h->stream>>>(a);
-    else
-      fe_gradient_kernel<2, 0><<<grid, block, 0, h->stream>>>(a);
-  }
-  LAUNCH_CHECK();
-  if (mem == DXM_MEM_HOST) CK(cudaStreamSynchronize(h->stream));  // the caller's u is free again
-  return 0;
-}
-
-// ---- fused flux / tangent -> element forms and global assembly -----------------------
-struct dxm_system {
-  int device = 0;
-  int64_t nrows = 0, nnz = 0;
-  int64_t* rowptr = nullptr;
-  int32_t* colidx = nullptr;
-  double *vals = nullptr, *rhs = nullptr;
-  uint8_t* bc = nullptr;
-  double* lift = nullptr;  // prescribed solution values on the constrained dofs
-  bool lift_on = false;    // false: homogeneous
-  unsigned long long* missing = nullptr;
-  double* work = nullptr;  // Krylov workspace: 9 vectors + block inverses + scalar slots (lazy)
-  // per-cell block offsets into the pattern, built at the first assembly with a given mesh (node-blocked patterns)
-  int32_t* off = nullptr;
-  unsigned long long off_mesh = 0;  // uid of the mesh the table was built for
-  bool off_valid = false;
-};
-
-int dxm_mesh_set_weights(dxm_mesh* m, const double* weights) {
-  if (!m || !weights) return fail("dxm_mesh_set_weights: NULL argument");
-  CK(cudaSetDevice(m->device));
-  if (!m->weights) CK(cudaMalloc((void**)&m->weights, sizeof(double) * m->nqp));
-  CK(cudaMemcpy(m->weights, weights, sizeof(double) * m->nqp, cudaMemcpyHostToDevice));
-  return 0;
-}
-
-extern "C++" {
-namespace {
-
-int check_forms(const char* who, dxm_mesh* m, dxm_handle* h, int kind) {
-  if (!m || !h) return fail(std::string(who) + ": NULL argument");
-  if (m->device != h->device) return fail(std::string(who) + ": mesh and material live on different devices");
-  if (kind != 0 && kind != 1) return fail(std::string(who) + ": kind must be 0 (strain/stress) or 1 (F/PK1)");
-  if ((kind == 0 ? 6 : 9) != h->ngrad)
-    return fail(std::string(who) + ": kind does not match the behaviour's gradient size");
-  if (m->num_cells * m->nqp != h->n)
-    return fail(std::string(who) + ": num_cells*nqp = " + std::to_string(m->num_cells * m->nqp) +
-                " but the material has " + std::to_string(h->n) + " Gauss points");
-  if (!m->weights) return fail(std::string(who) + ": quadrature weights not set (dxm_mesh_set_weights)");
-  if (m->nd > kFeMaxNd) return fail(std::string(who) + ": at most " + std::to_string(kFeMaxNd) + " dofs per cell");
-  if (!h->s1_valid && h->last.n_points == 0)
-    return fail(std::string(who) + ": no constitutive update has been run on this material yet");
-  return 0;
-}
-
-template <int MODE>
-int launch_fe_forms(dxm_mesh* m, dxm_handle* h, FeFormArgs& a) {
-  const FeFormSmem L = fe_form_smem(m->tdim, m->nd, m->nqp, a.kind, MODE, a.want_mat != 0);
-  const void* k;
-  if (m->tdim == 3)
-    k = m->nd == 4    ? (const void*)fe_forms_kernel<3, 4, MODE>
-        : m->nd == 10 ? (const void*)fe_forms_kernel<3, 10, MODE>
-                      : (const void*)fe_forms_kernel<3, 0, MODE>;
-  else
-    k = m->nd == 3   ? (const void*)fe_forms_kernel<2, 3, MODE>
-        : m->nd == 6 ? (const void*)fe_forms_kernel<2, 6, MODE>
-                     : (const void*)fe_forms_kernel<2, 0, MODE>;
-  if (L.bytes > 227 * 1024) return fail("fe_forms: element too large for the shared-memory staging");
-  if (L.bytes > 48 * 1024)
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
-  const int64_t grid = (m->num_cells + L.cpb - 1) / L.cpb;
-  if (grid > 0x7fffffff) return fail("fe_forms: too many cells for one launch");
-  void* args[] = {(void*)&a, (void*)&L};
-  CK(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(256), args, L.bytes, h->stream));
-  LAUNCH_CHECK();
-  return 0;
-}
-
-void fill_form_args(dxm_mesh* m, dxm_handle* h, int kind, FeFormArgs& a) {
-  // flux and tangent of the last update: s1 while it is valid, else the generation it became at update()
-  const int g = h->s1_valid ? 1 - h->i0 : h->i0;
-  a.coords = m->coords;
-  a.geom_dofs = m->geom_dofs;
-  a.u_dofs = m->u_dofs;
-  a.dphi = m->dphi;
-  a.weights = m->weights;
-  a.flux = h->gen[g] + (int64_t)h->ngrad * h->ld;
-  a.ct = h->ct;
-  a.ld = h->ld;
-  a.num_cells = m->num_cells;
-  a.nd = m->nd;
-  a.nqp = m->nqp;
-  a.kind = kind;
-}
-
-}  // namespace
-}  // extern "C++"
-
-int dxm_element_forms(dxm_mesh* m, dxm_handle* h, int kind, double* fe, double* ke, int mem) {
-  if (check_forms("dxm_element_forms", m, h, kind)) return -1;
-  if (mem != DXM_MEM_HOST && mem != DXM_MEM_DEVICE) return fail("dxm_element_forms: bad mem kind");
-  if (!fe && !ke) return 0;
-  if (set_device(h)) return -1;
-  const int64_t ndof = (int64_t)m->nd * m->tdim;
-  const size_t fe_bytes = sizeof(double) * m->num_cells * ndof, ke_bytes = fe_bytes * ndof;
-  FeFormArgs a{};
-  fill_form_args(m, h, kind, a);
-  a.want_vec = fe != nullptr;
-  a.want_mat = ke != nullptr;
-  if (mem == DXM_MEM_DEVICE) {
-    a.fe = fe;
-    a.ke = ke;
-  } else {
-    if (fe && !m->d_fe) CK(cudaMalloc((void**)&m->d_fe, fe_bytes));
-    if (ke && !m->d_ke) CK(cudaMalloc((void**)&m->d_ke, ke_bytes));
-    a.fe = m->d_fe;
-    a.ke = m->d_ke;
-  }
-  if (launch_fe_forms<MODE_ELEMENT>(m, h, a)) return -1;
-  if (mem == DXM_MEM_HOST) {
-    if (fe) CK(cudaMemcpyAsync(fe, m->d_fe, fe_bytes, cudaMemcpyDeviceToHost, h->stream));
-    if (ke) CK(cudaMemcpyAsync(ke, m->d_ke, ke_bytes, cudaMemcpyDeviceToHost, h->stream));
-  }
-  CK(cudaStreamSynchronize(h->stream));
-  return 0;
-}
-
-int dxm_system_destroy(dxm_system* s) {
-  if (!s) return 0;
-  cudaSetDevice(s->device);
-  cudaFree(s->rowptr);
-  cudaFree(s->colidx);
-  cudaFree(s->vals);
-  cudaFree(s->rhs);
-  cudaFree(s->bc);
-  cudaFree(s->missing);
-  cudaFree(s->lift);
-  cudaFree(s->work);
-  cudaFree(s->off);
-  delete s;
-  return 0;
-}
-
-int dxm_system_create(int device, int64_t nrows, const int64_t* rowptr, const int32_t* colidx, dxm_system** out) {
-  if (!out) return fail("dxm_system_create: out is NULL");
-  *out = nullptr;
-  if (nrows <= 0 || !rowptr || !colidx) return fail("dxm_system_create: bad argument");
-  if (rowptr[0] != 0 || rowptr[nrows] <= 0) return fail("dxm_system_create: rowptr must start at 0 and be non-empty");
-  CK(cudaSetDevice(device));
-  dxm_system* s = new dxm_system();
-  s->device = device;
-  s->nrows = nrows;
-  s->nnz = rowptr[nrows];
-  cudaError_t e = cudaMalloc((void**)&s->rowptr, sizeof(int64_t) * (nrows + 1));
-  if (e == cudaSuccess) e = cudaMemcpy(s->rowptr, rowptr, sizeof(int64_t) * (nrows + 1), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->colidx, sizeof(int32_t) * s->nnz);
-  if (e == cudaSuccess) e = cudaMemcpy(s->colidx, colidx, sizeof(int32_t) * s->nnz, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->vals, sizeof(double) * s->nnz);
-  if (e == cudaSuccess) e = cudaMemset(s->vals, 0, sizeof(double) * s->nnz);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->rhs, sizeof(double) * nrows);
-  if (e == cudaSuccess) e = cudaMemset(s->rhs, 0, sizeof(double) * nrows);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->missing, sizeof(unsigned long long));
-  if (e != cudaSuccess) {
-    dxm_system_destroy(s);
-    return fail(std::string("dxm_system_create: ") + cudaGetErrorString(e));
-  }
-  *out = s;
-  return 0;
-}
-
-int64_t dxm_system_nnz(const dxm_system* s) { return s ? s->nnz : -1; }
-
-int dxm_system_set_bc(dxm_system* s, const uint8_t* marker) {
-  if (!s) return fail("dxm_system_set_bc: NULL system");
-  CK(cudaSetDevice(s->device));
-  if (!marker) {
-    cudaFree(s->bc);
-    s->bc = nullptr;
-    return 0;
-  }
-  if (!s->bc) CK(cudaMalloc((void**)&s->bc, s->nrows));
-  CK(cudaMemcpy(s->bc, marker, s->nrows, cudaMemcpyHostToDevice));
-  return 0;
-}
-
-int dxm_system_set_lifting(dxm_system* s, const double* values) {
-  if (!s) return fail("dxm_system_set_lifting: NULL system");
-  CK(cudaSetDevice(s->device));
-  if (!values) {
-    s->lift_on = false;
-    return 0;
-  }
-  if (!s->lift) CK(cudaMalloc((void**)&s->lift, sizeof(double) * s->nrows));
-  CK(cudaMemcpy(s->lift, values, sizeof(double) * s->nrows, cudaMemcpyHostToDevice));
-  s->lift_on = true;
-  return 0;
-}
-
-int dxm_assemble(dxm_mesh* m, dxm_handle* h, int kind, dxm_system* s, int want_vector, int want_matrix) {
-  if (check_forms("dxm_assemble", m, h, kind)) return -1;
-  if (!s) return fail("dxm_assemble: NULL system");
-  if (s->device != h->device) return fail("dxm_assemble: system and material live on different devices");
-  if (s->nrows != m->num_dofs * m->tdim)
-    return fail("dxm_assemble: the system has " + std::to_string(s->nrows) + " rows but the space has " +
-                std::to_string(m->num_dofs * m->tdim) + " dofs");
-  if (!want_vector && !want_matrix) return 0;
-  if (s->lift_on && s->bc && want_vector && !want_matrix)
-    return fail("dxm_assemble: lifting the constrained columns needs the matrix pass (want_matrix)");
-  if (set_device(h)) return -1;
-  FeFormArgs a{};
-  fill_form_args(m, h, kind, a);
-  a.want_vec = want_vector != 0;
-  a.want_mat = want_matrix != 0;
-  a.b = s->rhs;
-  a.rowptr = s->rowptr;
-  a.colidx = s->colidx;
-  a.vals = s->vals;
-  a.bc = s->bc;
-  a.lift = (s->bc && s->lift_on && want_vector && want_matrix) ? s->lift : nullptr;
-  a.missing = s->missing;
-  if (want_matrix && s->off_mesh != m->uid) {
-    // first assembly of this mesh into this pattern: locate every (cell, node a, node b) block once
-    cudaFree(s->off);
-    s->off = nullptr;
-    s->off_valid = false;
-    s->off_mesh = m->uid;
-    const int64_t cnt = m->num_cells * m->nd * m->nd;
-    if (cudaMalloc((void**)&s->off, sizeof(int32_t) * cnt) == cudaSuccess) {
-      CK(cudaMemsetAsync(s->missing, 0, sizeof(unsigned long long), h->stream));
-      fe_offsets_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(m->u_dofs, m->num_cells, m->nd, m->tdim,
-                                                                            s->rowptr, s->colidx, s->off, s->missing);
-      LAUNCH_CHECK();
-      unsigned long long bad = 0;
-      CK(cudaMemcpyAsync(&bad, s->missing, sizeof(bad), cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-      s->off_valid = bad == 0;  // otherwise: not node-blocked or entries missing -> per-entry search path reports
-    } else {
-      cudaGetLastError();  // no room for the table: keep searching
-    }
-  }
-  a.off = (want_matrix && s->off_valid) ? s->off : nullptr;
-  if (want_vector) CK(cudaMemsetAsync(s->rhs, 0, sizeof(double) * s->nrows, h->stream));
-  if (want_matrix) CK(cudaMemsetAsync(s->vals, 0, sizeof(double) * s->nnz, h->stream));
-  CK(cudaMemsetAsync(s->missing, 0, sizeof(unsigned long long), h->stream));
-  if (launch_fe_forms<MODE_GLOBAL>(m, h, a)) return -1;
-  if (s->bc) {
-    fe_bc_diag_kernel<<<(unsigned)((s->nrows + 255) / 256), 256, 0, h->stream>>>(
-        s->bc, s->rowptr, s->colidx, want_matrix ? s->vals : nullptr, s->nrows, a.lift,
-        want_vector ? s->rhs : nullptr);
-    LAUNCH_CHECK();
-  }
-  unsigned long long miss = 0;
-  CK(cudaMemcpyAsync(&miss, s->missing, sizeof(miss), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  if (miss)
-    return fail("dxm_assemble: " + std::to_string(miss) + " element entries have no slot in the CSR pattern");
-  return 0;
-}
-
-int dxm_system_get(dxm_system* s, double* values, double* rhs, int mem) {
-  if (!s) return fail("dxm_system_get: NULL system");
-  if (mem != DXM_MEM_HOST && mem != DXM_MEM_DEVICE) return fail("dxm_system_get: bad mem kind");
-  CK(cudaSetDevice(s->device));
-  const cudaMemcpyKind kd = mem == DXM_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-  if (values) CK(cudaMemcpy(values, s->vals, sizeof(double) * s->nnz, kd));
-  if (rhs) CK(cudaMemcpy(rhs, s->rhs, sizeof(double) * s->nrows, kd));
-  return 0;
-}
-
-int dxm_system_solve(dxm_system* s, int block, double rtol, int maxit, double* x, int mem, int* iters,
-                     double* relres) {
-  if (!s || !x) return fail("dxm_system_solve: NULL argument");
-  if (block < 1 || block > 3 || s->nrows % block) return fail("dxm_system_solve: block must be 1, 2 or 3 and divide nrows");
-  if (mem != DXM_MEM_HOST && mem != DXM_MEM_DEVICE) return fail("dxm_system_solve: bad mem kind");
-  if (maxit < 1) return fail("dxm_system_solve: maxit must be positive");
-  CK(cudaSetDevice(s->device));
-  const int64_t n = s->nrows;
-  const int64_t npad = (n + 31) & ~int64_t(31);
-  if (!s->work) CK(cudaMalloc((void**)&s->work, sizeof(double) * (npad * 9 + n * 3 + 2 * KS_N + 4)));
-  KrylovVecs k{};
-  double* w = s->work;
-  k.x = w;
-  k.r = w + npad;
-  k.rhat = w + 2 * npad;
-  k.p = w + 3 * npad;
-  k.v = w + 4 * npad;
-  k.s = w + 5 * npad;
-  k.t = w + 6 * npad;
-  k.y = w + 7 * npad;
-  k.z = w + 8 * npad;
-  double* minv = w + 9 * npad;
-  k.minv = minv;
-  k.slots = minv + n * 3;
-  k.scal = k.slots + 2 * KS_N;
-  k.n = n;
-  k.bs = block;
-  cudaStream_t st = nullptr;  // legacy default stream: ordered after the assembly's stream synchronisation
-  const unsigned gv = (unsigned)((n + 255) / 256);
-  block_jacobi_kernel<<<(unsigned)((n / block + 255) / 256), 256, 0, st>>>(s->rowptr, s->colidx, s->vals, n / block,
-                                                                          block, minv);
-  LAUNCH_CHECK();
-  CK(cudaMemsetAsync(k.slots, 0, sizeof(double) * 2 * KS_N, st));
-  const double one[4] = {1.0, 1.0, 1.0, 0.0};
-  CK(cudaMemcpyAsync(k.scal, one, sizeof(one), cudaMemcpyHostToDevice, st));
-  bicg_init_kernel<<<gv, 256, 0, st>>>(k, s->rhs);
-  LAUNCH_CHECK();
-  double bb = 0.0;
-  CK(cudaMemcpy(&bb, k.slots + KS_RR, sizeof(double), cudaMemcpyDeviceToHost));
-  int it = 0;
-  double rel = 0.0;
-  if (bb > 0.0 && std::isfinite(bb)) {
-    const double avg = (double)s->nnz / (double)n;
-    const int G = avg < 24 ? 4 : avg < 48 ? 8 : avg < 96 ? 16 : 32;
-    const unsigned gs = (unsigned)((n * G + 255) / 256);
-    auto spmv = [&](const double* in, double* out, const double* d1, double* s1, const double* d2, double* s2) {
-      switch (G) {
-        case 4: spmv_dot_kernel<4><<<gs, 256, 0, st>>>(s->rowptr, s->colidx, s->vals, in, out, n, d1, s1, d2, s2); break;
-        case 8: spmv_dot_kernel<8><<<gs, 256, 0, st>>>(s->rowptr, s->colidx, s->vals, in, out, n, d1, s1, d2, s2); break;
-        case 16: spmv_dot_kernel<16><<<gs, 256, 0, st>>>(s->rowptr, s->colidx, s->vals, in, out, n, d1, s1, d2, s2); break;
-        default: spmv_dot_kernel<32><<<gs, 256, 0, st>>>(s->rowptr, s->colidx, s->vals, in, out, n, d1, s1, d2, s2); break;
-      }
-      g_launches.fetch_add(1);
-    };
-    const int check_every = 8;
-    rel = 1.0;
-    while (it < maxit) {
-      const int bank = it & 1;
-      double* S = k.slots + bank * KS_N;
-      bicg_p_kernel<<<gv, 256, 0, st>>>(k, bank);
-      bicg_prec_kernel<<<gv, 256, 0, st>>>(k, k.p, k.y);
-      spmv(k.y, k.v, k.rhat, S + KS_RV, nullptr, nullptr);
-      bicg_s_kernel<<<gv, 256, 0, st>>>(k, bank);
-      bicg_prec_kernel<<<gv, 256, 0, st>>>(k, k.s, k.z);
-      spmv(k.z, k.t, k.s, S + KS_TS, nullptr, S + KS_TT);
-      bicg_x_kernel<<<gv, 256, 0, st>>>(k, bank);
-      bicg_scal_kernel<<<1, 1, 0, st>>>(k, bank);
-      g_launches.fetch_add(6);
-      ++it;
-      if (it % check_every == 0 || it == maxit) {
-        double rr = 0.0;
-        CK(cudaMemcpy(&rr, k.slots + (1 - bank) * KS_N + KS_RR, sizeof(double), cudaMemcpyDeviceToHost));
-        rel = std::sqrt(rr / bb);
-        if (!std::isfinite(rel)) break;
-        if (rel <= rtol) break;
-      }
-    }
-    CK(cudaGetLastError());
-  }
-  CK(cudaMemcpy(x, k.x, sizeof(double) * n, mem == DXM_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice));
-  if (iters) *iters = it;
-  if (relres) *relres = rel;
-  if (!std::isfinite(rel)) return fail("dxm_system_solve: BiCGStab broke down (non-finite residual)");
-  return rel <= rtol ? 0 : 1;
-}
-
-int dxm_stream_peak(int device, int64_t n, int nread, int nwrite, double* gbs) {
-  if (!gbs || n < 1) return fail("dxm_stream_peak: bad argument");
-  CK(cudaSetDevice(device));
-  cudaDeviceProp prop{};
-  CK(cudaGetDeviceProperties(&prop, device));
-  const int64_t ld = (n + 63) & ~int64_t(63);
-  double *s = nullptr, *d = nullptr;
-  CK(cudaMalloc(&s, sizeof(double) * ld * nread));
-  CK(cudaMalloc(&d, sizeof(double) * ld * nwrite));
-  CK(cudaMemset(s, 0, sizeof(double) * ld * nread));
-  cudaEvent_t a, b;
-  CK(cudaEventCreate(&a));
-  CK(cudaEventCreate(&b));
-  const int grid = prop.multiProcessorCount * 2;
-  double best = 0;
-  for (int rep = 0; rep < 6; ++rep) {
-    CK(cudaEventRecord(a));
-    if (nread == 25 && nwrite == 49)
-      stream_mix_kernel<25, 49><<<grid, 256>>>(s, d, ld, n);
-    else if (nread == 25 && nwrite == 97)
-      stream_mix_kernel<25, 97><<<grid, 256>>>(s, d, ld, n);
-    else if (nread == 37 && nwrite == 37)
-      stream_mix_kernel<37, 37><<<grid, 256>>>(s, d, ld, n);
-    else if (nread == 1 && nwrite == 1)
-      stream_mix_kernel<1, 1><<<grid, 256>>>(s, d, ld, n);
-    else
-      return fail("dxm_stream_peak: supported mixes are 25/49, 25/97, 37/37, 1/1");
-    LAUNCH_CHECK();
-    CK(cudaEventRecord(b));
-    CK(cudaEventSynchronize(b));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, a, b));
-    best = std::max(best, 8.0 * (nread + nwrite) * n / (ms * 1e-3) / 1e9);
-  }
-  cudaEventDestroy(a);
-  cudaEventDestroy(b);
-  cudaFree(s);
-  cudaFree(d);
-  *gbs = best;
-  return 0;
-}
-
 }  // extern "C"
-

@@ -1,0 +1,98 @@
+// Shared internals of libdxm_cuda.so's translation units (not part of the ABI): error plumbing, launch accounting
+// and the material handle.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dxm.h"
+#include "dxm_canon.cuh"
+
+namespace dxm_detail {
+extern thread_local std::string g_err;        // text behind dxm_last_error(), per calling thread
+extern std::atomic<long long> g_launches;     // kernels launched by the library (dxm_launch_count)
+inline int fail(const std::string& msg) {
+  g_err = msg;
+  return -1;
+}
+}  // namespace dxm_detail
+using dxm_detail::fail;
+using dxm_detail::g_err;
+using dxm_detail::g_launches;
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                  std::to_string(__LINE__) + ")");                                            \
+    }                                                                                         \
+  } while (0)
+
+#define LAUNCH_CHECK()            \
+  do {                            \
+    g_launches.fetch_add(1);      \
+    CK(cudaGetLastError());       \
+  } while (0)
+
+constexpr int kNProp = 6;
+
+struct Field {
+  const char* name;
+  int row;  // first SoA row inside a generation block
+  int dim;
+};
+
+struct dxm_handle {
+  int behaviour = 0, device = 0;
+  int64_t n = 0, ld = 0;
+  int ngrad = 0, nflux = 0, nisv = 0, nrows = 0, nct = 0;
+  std::vector<Field> fields;
+  double* gen[2] = {nullptr, nullptr};  // device SoA blocks [nrows][ld]
+  int i0 = 0;                           // gen[i0] is s0, gen[1-i0] is s1
+  bool s1_valid = false;                // false => s1 reads alias s0 (after update/revert)
+  double* ct = nullptr;                 // [nct][ld]
+  // properties
+  double uni[kNProp] = {0, 0, 0, 0, 0, 0};
+  bool set[kNProp] = {false, false, false, false, false, false};
+  bool perpoint = false;
+  double* pp = nullptr;  // [kNProp][ld]
+  // statistics
+  dxm::StatSlot* d_stats = nullptr;
+  dxm::StatSlot* h_stats = nullptr;  // pinned
+  dxm_stats last{};
+  bool stats_pending = false;
+  // streams / events
+  cudaStream_t stream = nullptr, own_stream = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr},
+              ev_packed[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> ev_k;  // kernel timing event pairs
+  int n_ev_used = 0;
+  // staging (device AoS), allocated lazily
+  int64_t chunk = 0;
+  double* d_in[2] = {nullptr, nullptr};
+  double* d_out[2] = {nullptr, nullptr};
+  // diagnostics
+  bool diag = false;
+  uint8_t *d_flag = nullptr, *d_fail = nullptr;
+  int32_t* d_iter = nullptr;
+  double* d_resid = nullptr;
+  int num_sms = 148;
+  int ppt = 1;
+  int minb = 2;
+  int vote = 1;
+  int compact = -1;  // DXM_COMPACT: 0 never, 1 always, unset = auto (FeFp only, by the last plastic fraction)
+  int64_t prev_plastic = 0, prev_points = 0;
+  std::atomic<int> refs{1};
+};
+
+inline int set_device(const dxm_handle* h) {
+  CK(cudaSetDevice(h->device));
+  return 0;
+}

@@ -98,49 +98,4 @@ __global__ void synth_kernel(double* __restrict__ dst, int64_t ld, int64_t count
   }
 }
 
-// ---- measurement kernels ---------------------------------------------------------------------
-__global__ void fp64_fma_kernel(double* out, int iters, double seed) {
-  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
-         a6 = a0 + 6, a7 = a0 + 7;
-  const double m = 0.999999, c = 1e-9;
-  for (int i = 0; i < iters; ++i) {
-    a0 = __fma_rn(a0, m, c);
-    a1 = __fma_rn(a1, m, c);
-    a2 = __fma_rn(a2, m, c);
-    a3 = __fma_rn(a3, m, c);
-    a4 = __fma_rn(a4, m, c);
-    a5 = __fma_rn(a5, m, c);
-    a6 = __fma_rn(a6, m, c);
-    a7 = __fma_rn(a7, m, c);
-  }
-  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-  if (s == 123.456) out[0] = s;
-}
-
-__global__ void copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, int64_t n2) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2;
-       i += (int64_t)gridDim.x * blockDim.x)
-    __stcs(dst + i, __ldcs(src + i));
-}
-
-// pure-traffic twin of the constitutive kernels: NR coalesced read streams, NW coalesced write
-// streams, one point per thread, no arithmetic to speak of -- the practical HBM ceiling for that mix
-template <int NR, int NW>
-__global__ void __launch_bounds__(256, 2)
-    stream_mix_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t ld, int64_t n) {
-  const int64_t ntile = (n + blockDim.x - 1) / blockDim.x;
-  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
-    const int64_t i = tile * blockDim.x + threadIdx.x;
-    if (i >= n) continue;
-    double v[NR];
-#pragma unroll
-    for (int c = 0; c < NR; ++c) v[c] = __ldcs(src + (int64_t)c * ld + i);
-    double s = 0.0;
-#pragma unroll
-    for (int c = 0; c < NR; ++c) s += v[c];
-#pragma unroll
-    for (int c = 0; c < NW; ++c) __stcs(dst + (int64_t)c * ld + i, s + (double)c);
-  }
-}
-
 }  // namespace dxm
