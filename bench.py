@@ -16,8 +16,11 @@ all-reduce of the failure / active-set counts and residual maximum.
 `value`  : device-resident throughput (inputs and outputs stay in HBM, SoA).
 `e2e`    : same metric through the reference-facing call `CUDAMaterial.integrate(host gradients)` ->
            host (flux, isv, Ct): pinned host buffers, H2D + D2H inside the timed region.
-`roofline`: algorithmic bytes (592 B / Gauss point) / average kernel time measured with CUDA events
-           on the launching stream inside the timed region, against MEASURED_PEAKS.json hbm_gbs.
+`roofline`: algorithmic bytes (592 B / Gauss point: the full 36-entry tangent of the reference boundary) /
+           average kernel time measured with CUDA events on the launching stream inside the timed region, against
+           MEASURED_PEAKS.json hbm_gbs.  The kernel stores each unique entry of the symmetric tangent once
+           (472 B / point of DRAM traffic, `traffic`), so `frac` can exceed 1; `moved_frac` is the fraction of the
+           HBM peak the bytes actually moved account for.
 `cpu_baseline`: the numpy oracle timed on the box's host cores on a bounded sample of the same workload.
 """
 
@@ -36,7 +39,8 @@ sys.path.insert(0, ROOT)
 
 PROPS = dict(E=70e3, nu=0.3, sig0=350.0, sigu=500.0, b=1e3)
 AMP, KINC, SEED = 1.25e-2, 4, 0
-BYTES_PER_GP = 592  # 25 doubles read + 49 written
+BYTES_PER_GP = 592  # algorithmic: 25 doubles read + 49 written
+BYTES_MOVED_PER_GP = 472  # what the kernel moves: the symmetric tangent is stored once (21 of its 36 entries)
 METRIC = "GP updates/s (fp64 J2 return map + Ct)"
 UNIT = "GP/s"
 
@@ -246,7 +250,7 @@ def workload_config(args, world):
         "global_points": int(args.n) * world,
         "properties": PROPS,
         "history": f"counter-based recipe seed {SEED}, amp {AMP}, increment {KINC}/{KINC} after {KINC - 1} state updates",
-        "l2": "inputs >> L2 (59.2 GB touched per step per GPU), no flush needed",
+        "l2": "inputs >> L2 (47.2 GB touched per step per GPU), no flush needed",
         "parallelism": f"points sharded over {world} GPU(s), no data-path collective; NCCL all-reduce of 4 statistics per step",
         "e2e_points_per_gpu": int(args.e2e_n),
     }
@@ -454,6 +458,9 @@ def run_ours(args):
                 "kernel": "dxm_small_strain_kernel<HARD_GENERAL,uniform,PPT=1>",
                 "kernel_ms": kms,
                 "algorithmic_bytes_per_launch": BYTES_PER_GP * n,
+                "moved_bytes_per_launch": BYTES_MOVED_PER_GP * n,
+                "moved_gbs": BYTES_MOVED_PER_GP * n / (kms * 1e-3) / 1e9,
+                "moved_frac": BYTES_MOVED_PER_GP * n / (kms * 1e-3) / 1e9 / peak,
                 "peak_source": peak_src,
             },
             "cpu_baseline": cpu,

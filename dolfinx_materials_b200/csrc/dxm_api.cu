@@ -72,13 +72,13 @@ int launch_aos_to_soa(dxm_handle* h, cudaStream_t st, const double* src, int64_t
 }
 
 int launch_soa_to_aos(dxm_handle* h, cudaStream_t st, const double* src, int64_t s0, double* dst,
-                      int64_t rs, int c0, int64_t count, int D) {
+                      int64_t rs, int c0, int64_t count, int D, int sym6 = 0) {
   if (count <= 0) return 0;
   const size_t smem = (size_t)kTile * (D | 1) * sizeof(double);
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(soa_to_aos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntile = (count + kTile - 1) / kTile;
   const int grid = (int)std::min<int64_t>(ntile, (int64_t)h->num_sms * 4);
-  soa_to_aos_kernel<<<grid, 256, smem, st>>>(src, h->ld, s0, dst, rs, c0, count, D);
+  soa_to_aos_kernel<<<grid, 256, smem, st>>>(src, h->ld, s0, dst, rs, c0, count, D, sym6);
   LAUNCH_CHECK();
   return 0;
 }
@@ -115,13 +115,11 @@ template <int HARD, bool PERPOINT>
 int dispatch_small_strain2(dxm_handle* h, const SmallStrainArgs& a) {
   // tuning knob (DXM_MINB: resident blocks per SM the register allocation targets) for the
   // production kernel only; see profiles/ for the sweep that picked the defaults
-  if (HARD == HARD_GENERAL && !PERPOINT && !h->diag && h->minb != 2) {
+  if (HARD == HARD_GENERAL && !PERPOINT && !h->diag && (h->minb == 1 || h->minb == 4)) {
     if (h->ppt == 2) {
       if (h->minb == 1) return launch_small_strain<HARD_GENERAL, false, 2, false, 1>(h, a);
-      if (h->minb == 3) return launch_small_strain<HARD_GENERAL, false, 2, false, 3>(h, a);
     } else {
       if (h->minb == 1) return launch_small_strain<HARD_GENERAL, false, 1, false, 1>(h, a);
-      if (h->minb == 3) return launch_small_strain<HARD_GENERAL, false, 1, false, 3>(h, a);
       if (h->minb == 4) return launch_small_strain<HARD_GENERAL, false, 1, false, 4>(h, a);
     }
   }
@@ -134,8 +132,16 @@ int dispatch_small_strain2(dxm_handle* h, const SmallStrainArgs& a) {
     return h->diag ? launch_small_strain<HARD, PERPOINT, 2, true>(h, a)
                    : launch_small_strain<HARD, PERPOINT, 2, false>(h, a);
   }
-  return h->diag ? launch_small_strain<HARD, PERPOINT, 1, true>(h, a)
-                 : launch_small_strain<HARD, PERPOINT, 1, false>(h, a);
+  // Resident CTAs per SM the register allocation targets.  With the packed tangent the uniform Voce / elastic
+  // kernels fit 3 CTAs (80 registers, <= 16 B of spills): 13.7 vs 12.1 G points/s at 2 CTAs for every batch size
+  // from 1e6 to 1e8 (profiles/r01e_sweep_minb_vs_n.json); the linear-hardening and per-point-property variants
+  // spill 40-64 B at 80 registers and stay at 2 (cfg1 11.5 vs 10.6, cfg4 12.6 vs 12.0 G points/s).
+  const int minb = h->minb > 0 ? h->minb : ((!PERPOINT && HARD != HARD_LINEAR) ? 3 : 2);
+  if (minb == 2)
+    return h->diag ? launch_small_strain<HARD, PERPOINT, 1, true, 2>(h, a)
+                   : launch_small_strain<HARD, PERPOINT, 1, false, 2>(h, a);
+  return h->diag ? launch_small_strain<HARD, PERPOINT, 1, true, 3>(h, a)
+                 : launch_small_strain<HARD, PERPOINT, 1, false, 3>(h, a);
 }
 
 double prop(const dxm_handle* h, int i) {
@@ -401,7 +407,7 @@ int dxm_create(int behaviour, int device, int64_t n, dxm_handle** out) {
   // scalar 8-byte accesses measured faster than double2 on B200 (profiles/r01_variant_sweep.json)
   h->ppt = (env && std::atoi(env) == 2) ? 2 : 1;
   env = std::getenv("DXM_MINB");
-  h->minb = env ? std::atoi(env) : 2;
+  h->minb = env ? std::atoi(env) : 0;  // 0 = per-variant default (dispatch_small_strain2)
   env = std::getenv("DXM_VOTE");
   h->vote = env ? std::atoi(env) : 1;
   env = std::getenv("DXM_COMPACT");
@@ -419,6 +425,8 @@ int dxm_create(int behaviour, int device, int64_t n, dxm_handle** out) {
   }
   h->nrows = h->ngrad + h->nflux + h->nisv;
   h->nct = h->nflux * h->ngrad;
+  // the small-strain tangent is symmetric: the kernels store its 21 unique entries once (sym6_packed)
+  h->nct_store = behaviour == DXM_FEFP_VOCE ? h->nct : kSym6Rows;
   auto bail = [&](int) {
     std::string keep = g_err;
     free_handle(h);
@@ -438,8 +446,8 @@ int dxm_create(int behaviour, int device, int64_t n, dxm_handle** out) {
     CKH(cudaMalloc(&h->gen[g], gen_bytes));
     CKH(cudaMemset(h->gen[g], 0, gen_bytes));
   }
-  CKH(cudaMalloc(&h->ct, sizeof(double) * h->nct * h->ld));
-  CKH(cudaMemset(h->ct, 0, sizeof(double) * h->nct * h->ld));
+  CKH(cudaMalloc(&h->ct, sizeof(double) * h->nct_store * h->ld));
+  CKH(cudaMemset(h->ct, 0, sizeof(double) * h->nct_store * h->ld));
   CKH(cudaMalloc(&h->d_stats, sizeof(StatSlot) * kStatSlots));
   CKH(cudaMemset(h->d_stats, 0, sizeof(StatSlot) * kStatSlots));
   CKH(cudaMallocHost(&h->h_stats, sizeof(StatSlot) * kStatSlots));
@@ -583,10 +591,11 @@ int dxm_get_state(dxm_handle* h, int gen, const char* field, double* out, int me
   if (gen != 0 && gen != 1) return fail("dxm_get_state: gen must be 0 or 1");
   if (set_device(h)) return -1;
   const double* src;
-  int dim;
+  int dim, sym6 = 0;
   if (std::strcmp(field, "Ct") == 0) {
     src = h->ct;
     dim = h->nct;
+    sym6 = h->nct_store != h->nct;
   } else {
     const Field* f = find_field(h, field);
     if (!f) return fail(std::string("dxm_get_state: unknown field '") + field + "'");
@@ -595,7 +604,7 @@ int dxm_get_state(dxm_handle* h, int gen, const char* field, double* out, int me
   }
   if (mem == DXM_MEM_RESIDENT) return fail("dxm_get_state: RESIDENT is not a destination");
   if (mem == DXM_MEM_DEVICE) {
-    if (launch_soa_to_aos(h, h->stream, src, 0, out, dim, 0, h->n, dim)) return -1;
+    if (launch_soa_to_aos(h, h->stream, src, 0, out, dim, 0, h->n, dim, sym6)) return -1;
     CK(cudaStreamSynchronize(h->stream));
     return 0;
   }
@@ -603,7 +612,7 @@ int dxm_get_state(dxm_handle* h, int gen, const char* field, double* out, int me
   const int64_t rows_per = (h->chunk * (h->nflux + h->nisv + h->nct)) / dim;
   for (int64_t s = 0; s < h->n; s += rows_per) {
     const int64_t m = std::min(rows_per, h->n - s);
-    if (launch_soa_to_aos(h, h->stream, src, s, h->d_out[0], dim, 0, m, dim)) return -1;
+    if (launch_soa_to_aos(h, h->stream, src, s, h->d_out[0], dim, 0, m, dim, sym6)) return -1;
     CK(cudaMemcpyAsync(out + s * dim, h->d_out[0], sizeof(double) * m * dim, cudaMemcpyDeviceToHost,
                        h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -629,7 +638,8 @@ int dxm_export_dlpack(dxm_handle* h, int gen, const char* field, void** out) {
   if (!out) return fail("dxm_export_dlpack: out is NULL");
   double* p = nullptr;
   if (dxm_device_ptr(h, gen, field, &p)) return -1;
-  const int dim = dxm_field_dim(h, field);
+  // the resident tangent of the small-strain behaviours is packed: 21 rows (include/dxm.h)
+  const int dim = std::strcmp(field, "Ct") == 0 ? h->nct_store : dxm_field_dim(h, field);
   DlCtx* ctx = new DlCtx{h, {dim, h->n}, {h->ld, 1}};
   DxmDLManagedTensor* t = new DxmDLManagedTensor();
   t->dl_tensor.data = p;
@@ -685,7 +695,7 @@ int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double*
         if (isv && launch_soa_to_aos(h, h->stream, s1 + (int64_t)isv_row * ld, 0, isv, h->nisv, 0,
                                      n, h->nisv))
           return -1;
-        if (ct && launch_soa_to_aos(h, h->stream, h->ct, 0, ct, h->nct, 0, n, h->nct)) return -1;
+        if (ct && launch_soa_to_aos(h, h->stream, h->ct, 0, ct, h->nct, 0, n, h->nct, h->nct_store != h->nct)) return -1;
       } else if (out_mem == DXM_MEM_HOST) {
         h->stats_pending = true;
         if (finish_stats(h)) return -1;
@@ -741,7 +751,7 @@ int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double*
         if (isv && launch_soa_to_aos(h, h->stream, s1 + (int64_t)isv_row * ld, s, o + CH * nf, ni, 0,
                                      m, ni))
           return -1;
-        if (ct && launch_soa_to_aos(h, h->stream, h->ct, s, o + CH * (nf + ni), nc, 0, m, nc))
+        if (ct && launch_soa_to_aos(h, h->stream, h->ct, s, o + CH * (nf + ni), nc, 0, m, nc, h->nct_store != nc))
           return -1;
         CK(cudaEventRecord(h->ev_packed[b], h->stream));
         CK(cudaStreamWaitEvent(h->s_out, h->ev_packed[b], 0));

@@ -41,6 +41,15 @@ __device__ __forceinline__ double exp_c(double x) {
   return y;
 }
 
+// Resident layout of a symmetric 6x6 tangent: the 21 entries (j <= i) of the upper triangle, row-major
+// (the order the small-strain kernel forms them in).  sym6_packed(c) maps a full row-major index c = j*6+i to it.
+constexpr int kSym6Rows = 21;
+__host__ __device__ __forceinline__ constexpr int sym6_packed(int c) {
+  const int a = c / 6, b = c % 6;
+  const int j = a < b ? a : b, i = a < b ? b : a;
+  return j * 6 - (j * (j - 1)) / 2 + (i - j);
+}
+
 // streaming (evict-first) vector loads / stores of PPT consecutive points
 template <int PPT>
 __device__ __forceinline__ void ldv(const double* __restrict__ p, double (&v)[PPT]);

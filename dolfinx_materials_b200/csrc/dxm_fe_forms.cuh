@@ -29,7 +29,7 @@ struct FeFormArgs {
   const double* dphi;        // (nqp, nd, TDIM)
   const double* weights;     // (nqp)
   const double* flux;        // SoA [6|9][ld]
-  const double* ct;          // SoA [36|81][ld]
+  const double* ct;          // SoA [21 (packed symmetric, sym6_packed) | 81][ld]
   int64_t ld, num_cells;
   int nd, nqp, kind;
   int want_vec, want_mat;
@@ -122,7 +122,7 @@ inline FeFormSmem fe_form_smem(int tdim, int nd, int nqp, int kind, int mode, bo
   s.cpb = 256 / s.ndof;
   if (s.cpb < 1) s.cpb = 1;
   s.np = s.cpb * nqp;
-  const int nflux = kind == 0 ? 6 : 9, nct = kind == 0 ? 36 : 81;
+  const int nflux = kind == 0 ? 6 : 9, nct = kind == 0 ? kSym6Rows : 81;
   size_t o = 0;
   s.off_vol = o;
   o += sizeof(double) * s.np;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) fe_forms_kernel(const FeFormArgs a, const
   const int nd = ND > 0 ? ND : a.nd;
   const int ndof = nd * TDIM;
   const int cpb = L.cpb, nqp = a.nqp, np = L.np;
-  const int nflux = a.kind == 0 ? 6 : 9, nct = a.kind == 0 ? 36 : 81;
+  const int nflux = a.kind == 0 ? 6 : 9, nct = a.kind == 0 ? kSym6Rows : 81;
   const int64_t c0 = (int64_t)blockIdx.x * cpb;
   const int ncell = (int)min((int64_t)cpb, a.num_cells - c0);
   const int npv = ncell * nqp;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) fe_forms_kernel(const FeFormArgs a, const
             if (a.kind == 1) {
               A = s_ct[(idx9_c(r, j) * 9 + idx9_c(s, l)) * np + pt];
             } else {
-              A = s_ct[(idx6_c(r, j) * 6 + idx6_c(s, l)) * np + pt];
+              A = s_ct[sym6_packed(idx6_c(r, j) * 6 + idx6_c(s, l)) * np + pt];
               const int noff = (r != j ? 1 : 0) + (s != l ? 1 : 0);
               if (noff == 1) A = A * kR2;
               if (noff == 2) A = A * 0.5;

@@ -53,11 +53,12 @@ struct dxm_handle {
   int behaviour = 0, device = 0;
   int64_t n = 0, ld = 0;
   int ngrad = 0, nflux = 0, nisv = 0, nrows = 0, nct = 0;
+  int nct_store = 0;  // resident tangent rows: nct, or 21 for the packed symmetric 6x6 of the small-strain behaviours
   std::vector<Field> fields;
   double* gen[2] = {nullptr, nullptr};  // device SoA blocks [nrows][ld]
   int i0 = 0;                           // gen[i0] is s0, gen[1-i0] is s1
   bool s1_valid = false;                // false => s1 reads alias s0 (after update/revert)
-  double* ct = nullptr;                 // [nct][ld]
+  double* ct = nullptr;                 // [nct_store][ld]
   // properties
   double uni[kNProp] = {0, 0, 0, 0, 0, 0};
   bool set[kNProp] = {false, false, false, false, false, false};
@@ -85,7 +86,7 @@ struct dxm_handle {
   double* d_resid = nullptr;
   int num_sms = 148;
   int ppt = 1;
-  int minb = 2;
+  int minb = 0;
   int vote = 1;
   int compact = -1;  // DXM_COMPACT: 0 never, 1 always, unset = auto (FeFp only, by the last plastic fraction)
   int64_t prev_plastic = 0, prev_points = 0;

@@ -38,29 +38,33 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// SoA src[c*ld + s0 + i], c<D  ->  AoS rows [0,count) with row stride `rs`, column offset `c0`
+// SoA src[c*ld + s0 + i], c<D  ->  AoS rows [0,count) with row stride `rs`, column offset `c0`.
+// sym6 != 0: the source holds the 21 packed rows of a symmetric 6x6 tangent, expanded to D = 36 columns on the way out
 __global__ void __launch_bounds__(256)
     soa_to_aos_kernel(const double* __restrict__ src, int64_t ld, int64_t s0,
-                      double* __restrict__ dst, int64_t rs, int c0, int64_t count, int D) {
+                      double* __restrict__ dst, int64_t rs, int c0, int64_t count, int D, int sym6) {
   extern __shared__ double sm[];
   const int stride = D | 1;
+  const int Ds = sym6 ? kSym6Rows : D;
   const int64_t ntile = (count + kTile - 1) / kTile;
   for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     const int64_t base = tile * kTile;
     const int m = (int)((count - base) < kTile ? (count - base) : kTile);
-    for (int idx = threadIdx.x; idx < kTile * D; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < kTile * Ds; idx += blockDim.x) {
       const int c = idx / kTile, p = idx % kTile;
       if (p < m) sm[p * stride + c] = __ldcs(src + (int64_t)c * ld + s0 + base + p);
     }
     __syncthreads();
     if (rs == D) {
       double* d = dst + base * rs;
-      for (int idx = threadIdx.x; idx < m * D; idx += blockDim.x)
-        __stcs(d + idx, sm[(idx / D) * stride + (idx % D)]);
+      for (int idx = threadIdx.x; idx < m * D; idx += blockDim.x) {
+        const int c = idx % D;
+        __stcs(d + idx, sm[(idx / D) * stride + (sym6 ? sym6_packed(c) : c)]);
+      }
     } else {
       for (int idx = threadIdx.x; idx < m * D; idx += blockDim.x) {
         const int p = idx / D, c = idx % D;
-        __stcs(dst + (base + p) * rs + c0 + c, sm[p * stride + c]);
+        __stcs(dst + (base + p) * rs + c0 + c, sm[p * stride + (sym6 ? sym6_packed(c) : c)]);
       }
     }
     __syncthreads();

@@ -136,6 +136,8 @@ int dxm_stream_peak(int device, int64_t n, int nread, int nwrite, double* gbs) {
     CK(cudaEventRecord(a));
     if (nread == 25 && nwrite == 49)
       stream_mix_kernel<25, 49><<<grid, 256>>>(s, d, ld, n);
+    else if (nread == 25 && nwrite == 34)
+      stream_mix_kernel<25, 34><<<grid, 256>>>(s, d, ld, n);
     else if (nread == 25 && nwrite == 97)
       stream_mix_kernel<25, 97><<<grid, 256>>>(s, d, ld, n);
     else if (nread == 37 && nwrite == 37)
@@ -143,7 +145,7 @@ int dxm_stream_peak(int device, int64_t n, int nread, int nwrite, double* gbs) {
     else if (nread == 1 && nwrite == 1)
       stream_mix_kernel<1, 1><<<grid, 256>>>(s, d, ld, n);
     else
-      return fail("dxm_stream_peak: supported mixes are 25/49, 25/97, 37/37, 1/1");
+      return fail("dxm_stream_peak: supported mixes are 25/49, 25/34, 25/97, 37/37, 1/1");
     LAUNCH_CHECK();
     CK(cudaEventRecord(b));
     CK(cudaEventSynchronize(b));

@@ -7,8 +7,9 @@
 //
 // Layout: SoA, one Gauss point per thread-lane, PPT consecutive points per thread (PPT=2 -> 16-byte
 // double2 accesses).  Per point the kernel reads 25 doubles (eps 6, eps_old 6, sig_old 6, p_old 1,
-// epsp_old 6) and writes 49 (sig 6, p 1, epsp 6, Ct 36): 592 B, all coalesced streaming accesses.
-// The tangent is never materialised: Ct = A 1x1 + B I - gamma n x n is formed entry by entry at
+// epsp_old 6) and writes 34 (sig 6, p 1, epsp 6, and the 21 unique entries of the symmetric Ct): 472 B of
+// traffic for 592 algorithmic bytes (the full 36-entry tangent of the reference boundary), all coalesced streaming.
+// The tangent is never held in registers: Ct = A 1x1 + B I - gamma n x n is formed entry by entry at
 // store time from 3 scalars and the flow direction.
 #pragma once
 #include "dxm_canon.cuh"
@@ -360,8 +361,8 @@ __global__ void __launch_bounds__(256, MINB)
             base = 0.0;
           v[k] = base - gamma[k] * (nrm[i][k] * nrm[j][k]);
         }
-        stv<PPT>(a.ct + (int64_t)(j * 6 + i) * ld + i0, v);
-        if (i != j) stv<PPT>(a.ct + (int64_t)(i * 6 + j) * ld + i0, v);
+        // symmetric: each unique entry is written once, packed (sym6_packed); the boundary transposes mirror it
+        stv<PPT>(a.ct + (int64_t)sym6_packed(j * 6 + i) * ld + i0, v);
       }
     }
   }

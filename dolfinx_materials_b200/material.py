@@ -33,6 +33,15 @@ except Exception:  # noqa: BLE001 - dolfinx is optional
         return contextlib.nullcontext()
 
 
+def _sym6_packed(c):
+    j, i = sorted(divmod(c, 6))
+    return j * 6 - (j * (j - 1)) // 2 + (i - j)
+
+
+# row of the packed resident tangent that holds entry c = j*6+i of the row-major symmetric 6x6 (include/dxm.h)
+SYM6_PACKED = np.array([_sym6_packed(c) for c in range(36)])
+
+
 @dataclass
 class IntegrationStats:
     """Per-call statistics reduced on the device (fused replacement of the host NaN scans,
@@ -367,7 +376,8 @@ class CUDAMaterial:
 
     def device_view(self, field, gen=1):
         """Zero-copy ``torch`` view (shape ``(dim, n)``, SoA) of a device-resident field via DLPack.
-        Views of generation buffers are invalidated by ``data_manager.update()``."""
+        Views of generation buffers are invalidated by ``data_manager.update()``.  ``"Ct"`` of a small-strain
+        behaviour has 21 rows (packed symmetric storage, see ``device_tangent``)."""
         self._require_handle()
         import torch
 
@@ -379,6 +389,19 @@ class CUDAMaterial:
         new.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
         capsule = new(mt, b"dltensor", None)
         return torch.from_dlpack(capsule)
+
+    def device_tangent(self, points=None):
+        """The resident tangent as a full ``(nflux*ngrad, n)`` torch tensor.  The small-strain behaviours store
+        their symmetric 6x6 tangent packed (21 rows, ``SYM6_PACKED``); this expands it on the device (a copy).
+        ``points``: optional slice of Gauss points."""
+        import torch
+
+        ct = self.device_view("Ct")
+        if points is not None:
+            ct = ct[:, points]
+        if ct.shape[0] == 21:
+            return ct[torch.as_tensor(SYM6_PACKED, device=ct.device)]
+        return ct
 
     def gradient_buffer(self):
         """Where a device-resident caller writes this step's gradients (SoA, shape ``(dim, n)``)."""

@@ -17,7 +17,10 @@
  *    the caller owns every array it passes, borrowed for the duration of the call.
  *  - host/“AoS” arrays are C-contiguous (n, dim) float64 exactly as QuadratureMap builds and consumes
  *    them (quadrature_map.py:313, :331-334; utils.py:136-143).  Device-resident fields are SoA:
- *    component c of point i at  base[c * ld + i],  ld = dxm_ld(h).
+ *    component c of point i at  base[c * ld + i],  ld = dxm_ld(h).  The resident tangent of the small-strain
+ *    behaviours is symmetric and stored packed: 21 rows, entry (j, i), j <= i, of the row-major 6x6 at row
+ *    j*6 - j(j-1)/2 + (i-j); every host / device-AoS output is the full (n, 36) array (mirrored on the way out).
+ *    The finite-strain tangent is stored in full (81 rows).
  *  - tensor conventions: symmetric tensors are Mandel 6-vectors [11,22,33,r2*12,r2*13,r2*23]
  *    (utils.py:146-165), non-symmetric ones [11,22,33,12,21,13,31,23,32] (utils.py:168-190);
  *    the tangent is row-major d flux_j / d grad_i at j*ngrad+i (quadrature_map.py:94-104).
@@ -177,7 +180,7 @@ int64_t dxm_launch_count(void);                       /* kernels launched by thi
 int dxm_fp64_peak(int device, double* tflops);        /* register-resident DFMA microbenchmark   */
 int dxm_copy_peak(int device, int64_t bytes, double* gbs); /* device copy bandwidth (read+write)  */
 /* pure-traffic twin of the update kernels: nread coalesced read streams + nwrite write streams over n
- * points (supported mixes 25/49 = J2, 25/97 = FeFp, 37/37, 1/1): the practical HBM ceiling for that mix */
+ * points (supported mixes 25/49 = J2 with a full tangent, 25/34 = J2 with the packed tangent, 25/97 = FeFp, 37/37, 1/1): the practical HBM ceiling for that mix */
 int dxm_stream_peak(int device, int64_t n, int nread, int nwrite, double* gbs);
 
 const char* dxm_last_error(void);

@@ -54,7 +54,7 @@ t_d2h = timeit(lambda: (mat.read_state_into("Ct", ct_pin.array), mat.read_state_
 # oracle (numpy) on a subset of cells, extrapolated
 sub = min(nc, 4096)
 flux = np.ascontiguousarray(mat.device_view("PK1").cpu().numpy().T)[: sub * nqp]
-ct = np.ascontiguousarray(mat.device_view("Ct").cpu().numpy().T)[: sub * nqp]
+ct = np.ascontiguousarray(mat.device_tangent().cpu().numpy().T)[: sub * nqp]
 t0 = time.perf_counter(); fe_ref, ke_ref = ff.element_forms(coords, gd[:sub], ud[:sub], dphi, w, flux, ct, 1, 3); t_or = time.perf_counter() - t0
 assert np.array_equal(ke_pin.array[:sub], ke_ref) and np.array_equal(fe_pin.array[:sub], fe_ref)
 ct_bytes = n * 81 * 8

@@ -24,7 +24,7 @@ def make_material(jm, finite):
 
 def device_outputs(mat, fname):
     flux = np.ascontiguousarray(mat.device_view(fname).cpu().numpy().T)
-    ct = np.ascontiguousarray(mat.device_view("Ct").cpu().numpy().T)
+    ct = np.ascontiguousarray(mat.device_tangent().cpu().numpy().T)
     return flux, ct
 
 

@@ -190,7 +190,7 @@ def test_resident_path_and_dlpack(jm):
     ref = ss.integrate(eps, ss.zero_state(n), VOCE)
     assert stats.n_plastic == int(ref["flag"].sum())
     assert np.array_equal(m.device_view("stress").cpu().numpy().T, ref["stress"])
-    assert np.array_equal(m.device_view("Ct").cpu().numpy().T.reshape(n, 6, 6), ref["Ct"])
+    assert np.array_equal(m.device_tangent().cpu().numpy().T.reshape(n, 6, 6), ref["Ct"])
     # write gradients from torch, integrate, compare with the host path
     gb = m.gradient_buffer()
     gb.copy_(torch.from_numpy(np.ascontiguousarray(eps.T * 0.5)).cuda())
