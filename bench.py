@@ -310,6 +310,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     bind_to_gpu_numa_node(local)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL's own banner ("NCCL version ...") goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     build.build_library()
     lib = _lib.load()

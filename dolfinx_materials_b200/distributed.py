@@ -49,3 +49,43 @@ def allreduce_stats(stats, group=None, device=None):
     return dataclasses.replace(
         stats, n_points=int(s[0]), n_plastic=int(s[1]), n_fail=int(s[2]), max_iter=int(m[0]), max_residual=m[1], kernel_ms=m[2]
     )
+
+
+def gpu_numa_node(device):
+    """NUMA node of the PCIe root the GPU hangs off (``/sys/bus/pci/devices/<bus id>/numa_node``), or None."""
+    import torch
+
+    try:
+        prop = torch.cuda.get_device_properties(device)
+        bus = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def bind_to_gpu_numa_node(device):
+    """Pin this process to the CPUs of the NUMA node next to its GPU, so that the page-locked host buffers it
+    allocates afterwards (first touch) sit behind the same PCIe root complex as the GPU.  With one process per GPU
+    on a two-socket box this keeps the host<->device DMA of ``integrate`` off the inter-socket link.
+    Returns ``(node, ncpus)`` or ``None`` when the topology cannot be read (nothing is changed then)."""
+    import os
+
+    node = gpu_numa_node(device)
+    if node is None or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node, len(allowed)
+    except Exception:  # noqa: BLE001
+        return None
