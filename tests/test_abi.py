@@ -78,3 +78,13 @@ def test_protocol_surface_without_gpu(jm):
         jm.CUDAMaterial(jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=lambda p: 1.0))
     with pytest.raises(KeyError):
         m.update_material_property("nope", 1.0)
+
+
+def test_packed_tangent_index_map():
+    """SYM6_PACKED (host mirror of sym6_packed in csrc/dxm_canon.cuh): the 21 rows of the resident small-strain
+    tangent, upper triangle row-major, shared by (j, i) and (i, j)."""
+    from dolfinx_materials_b200.material import SYM6_PACKED
+
+    m = SYM6_PACKED.reshape(6, 6)
+    assert np.array_equal(m, m.T) and sorted(set(m.ravel())) == list(range(21))
+    assert [m[j, i] for j in range(6) for i in range(j, 6)] == list(range(21))
