@@ -7,7 +7,11 @@ first use raises ``RuntimeError``.
 import ctypes
 import pathlib
 
-LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / "libdxm_cuda.so"
+import os
+
+# DXM_FMAD=1: the contracted (fused multiply-add) build, see build.py
+LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / (
+    "libdxm_cuda_fmad.so" if os.environ.get("DXM_FMAD", "0") not in ("", "0") else "libdxm_cuda.so")
 
 MEM_HOST, MEM_DEVICE, MEM_RESIDENT = 0, 1, 2
 
