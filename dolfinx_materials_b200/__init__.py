@@ -22,6 +22,7 @@ from .behaviors import (  # noqa: E402
     FeFpJ2Plasticity,
     LinearElasticIsotropic,
     LinearHardening,
+    TabulatedHardening,
     VoceHardening,
     vonMisesIsotropicHardening,
 )
@@ -33,6 +34,7 @@ __all__ = [
     "PerformanceWarning",
     "LinearElasticIsotropic",
     "LinearHardening",
+    "TabulatedHardening",
     "VoceHardening",
     "ElasticBehavior",
     "vonMisesIsotropicHardening",

@@ -37,6 +37,7 @@ SIGNATURES = {
     "dxm_ld": (ctypes.c_int64, [ctypes.c_void_p]),
     "dxm_npoints": (ctypes.c_int64, [ctypes.c_void_p]),
     "dxm_set_property": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    "dxm_set_hardening_table": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "dxm_field_dim": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
     "dxm_set_state": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int]),
     "dxm_get_state": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int]),

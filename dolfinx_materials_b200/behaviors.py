@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 from typing import Any
 
 # behaviour ids of include/dxm.h
-DXM_ELASTIC, DXM_J2_LINEAR, DXM_J2_VOCE, DXM_FEFP_VOCE = 0, 1, 2, 3
+DXM_ELASTIC, DXM_J2_LINEAR, DXM_J2_VOCE, DXM_FEFP_VOCE, DXM_J2_TABLE = 0, 1, 2, 3, 4
 
 
 @dataclass
@@ -42,14 +42,34 @@ class VoceHardening:
     H: Any = 0.0
 
 
+@dataclass
+class TabulatedHardening:
+    """Piecewise-linear isotropic hardening through ``(p[k], sig[k])`` (``p[0] = 0``, increasing, at most 64 points),
+    continued with the last slope.  ``vonMisesIsotropicHardening`` accepts an arbitrary ``yield_stress`` callable in
+    jaxmat (old demo ``demos/jax/elastoplasticity/_plane_stress_elastoplasticity.py:38-44``); a Python callable cannot be
+    compiled into the CUDA kernels, so ``from_callable`` samples it (denser near ``p = 0`` where hardening curves bend)."""
+
+    p: Any
+    sig: Any
+
+    @classmethod
+    def from_callable(cls, yield_stress, p_max, n=64):
+        import numpy as np
+
+        p = np.concatenate([[0.0], np.geomspace(p_max * 1e-5, p_max, n - 1)])
+        return cls(p=p, sig=np.array([float(yield_stress(x)) for x in p]))
+
+
 def _hardening_props(h):
+    if isinstance(h, TabulatedHardening):
+        return {}
     if isinstance(h, LinearHardening):
         return {"sig0": h.sig0, "H": h.H}
     if isinstance(h, VoceHardening):
         return {"sig0": h.sig0, "sigu": h.sigu, "b": h.b, "H": h.H}
     raise TypeError(
-        "yield_stress must be a LinearHardening or VoceHardening descriptor; arbitrary Python "
-        "callables cannot be compiled into the CUDA kernels"
+        "yield_stress must be a LinearHardening, VoceHardening or TabulatedHardening descriptor; arbitrary Python "
+        "callables cannot be compiled into the CUDA kernels (sample them with TabulatedHardening.from_callable)"
     )
 
 
@@ -75,7 +95,10 @@ class vonMisesIsotropicHardening(_Behavior):
     yield_stress: Any = None
 
     def __post_init__(self):
-        self.kind = DXM_J2_LINEAR if isinstance(self.yield_stress, LinearHardening) else DXM_J2_VOCE
+        if isinstance(self.yield_stress, TabulatedHardening):
+            self.kind = DXM_J2_TABLE
+        else:
+            self.kind = DXM_J2_LINEAR if isinstance(self.yield_stress, LinearHardening) else DXM_J2_VOCE
 
     def properties(self):
         return {**super().properties(), **_hardening_props(self.yield_stress)}

@@ -225,12 +225,22 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
     a.psigu = h->pp + 4 * ld;
     a.pb = h->pp + 5 * ld;
   }
+  a.table = h->table;
+  a.ntab = h->ntab;
   a.stats = h->d_stats;
   a.vote = h->vote;
   a.d_flag = h->d_flag;
   a.d_iter = h->d_iter;
   a.d_resid = h->d_resid;
   a.d_fail = h->d_fail;
+  if (h->behaviour == DXM_J2_TABLE) {
+    // 2 CTAs/SM: the segment walk keeps a few more values live than the closed forms
+    if (h->perpoint)
+      return h->diag ? launch_small_strain<HARD_TABLE, true, 1, true, 2>(h, a)
+                     : launch_small_strain<HARD_TABLE, true, 1, false, 2>(h, a);
+    return h->diag ? launch_small_strain<HARD_TABLE, false, 1, true, 2>(h, a)
+                   : launch_small_strain<HARD_TABLE, false, 1, false, 2>(h, a);
+  }
   if (h->perpoint) {
     switch (h->behaviour) {
       case DXM_ELASTIC: return dispatch_small_strain2<HARD_NONE, true>(h, a);
@@ -347,6 +357,7 @@ void free_handle(dxm_handle* h) {
   for (int g = 0; g < 2; ++g) cudaFree(h->gen[g]);
   cudaFree(h->ct);
   cudaFree(h->pp);
+  cudaFree(h->table);
   cudaFree(h->d_stats);
   cudaFreeHost(h->h_stats);
   for (int s = 0; s < 2; ++s) {
@@ -384,7 +395,7 @@ int dxm_create(int behaviour, int device, int64_t n, dxm_handle** out) {
   if (!out) return fail("dxm_create: out is NULL");
   *out = nullptr;
   if (n <= 0) return fail("dxm_create: n must be positive");
-  if (behaviour < DXM_ELASTIC || behaviour > DXM_FEFP_VOCE)
+  if (behaviour < DXM_ELASTIC || behaviour > DXM_J2_TABLE)
     return fail("dxm_create: unknown behaviour " + std::to_string(behaviour));
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
@@ -556,6 +567,29 @@ int dxm_set_property(dxm_handle* h, const char* name, const double* v, int64_t c
   return 0;
 }
 
+int dxm_set_hardening_table(dxm_handle* h, const double* p, const double* sig, int count) {
+  if (!h || !p || !sig) return fail("dxm_set_hardening_table: NULL argument");
+  if (h->behaviour != DXM_J2_TABLE) return fail("dxm_set_hardening_table: the handle is not a DXM_J2_TABLE behaviour");
+  if (count < 2 || count > kMaxTable)
+    return fail("dxm_set_hardening_table: between 2 and " + std::to_string(kMaxTable) + " points");
+  if (p[0] != 0.0) return fail("dxm_set_hardening_table: p[0] must be 0");
+  std::vector<double> t(3 * (size_t)count);
+  for (int k = 0; k < count; ++k) {
+    if (k > 0 && !(p[k] > p[k - 1])) return fail("dxm_set_hardening_table: p must increase strictly");
+    if (!std::isfinite(p[k]) || !std::isfinite(sig[k])) return fail("dxm_set_hardening_table: non-finite entry");
+    t[k] = p[k];
+    t[count + k] = sig[k];
+  }
+  for (int k = 0; k + 1 < count; ++k) t[2 * count + k] = (sig[k + 1] - sig[k]) / (p[k + 1] - p[k]);
+  t[3 * count - 1] = t[3 * count - 2];
+  if (set_device(h)) return -1;
+  CK(cudaStreamSynchronize(h->stream));
+  if (!h->table) CK(cudaMalloc(&h->table, sizeof(double) * 3 * kMaxTable));
+  CK(cudaMemcpy(h->table, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice));
+  h->ntab = count;
+  return 0;
+}
+
 int dxm_set_state(dxm_handle* h, int gen, const char* field, const double* v, int mem) {
   if (!h || !field || !v) return fail("dxm_set_state: NULL argument");
   if (gen != 0 && gen != 1) return fail("dxm_set_state: gen must be 0 or 1");
@@ -669,8 +703,11 @@ int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double*
   if (!h) return fail("dxm_integrate: NULL handle");
   if (set_device(h)) return -1;
   if (!h->set[0] || !h->set[1]) return fail("dxm_integrate: properties E and nu must be set");
-  if (h->behaviour != DXM_ELASTIC && !h->set[2])
+  if (h->behaviour == DXM_J2_TABLE) {
+    if (!h->table) return fail("dxm_integrate: hardening table not set (dxm_set_hardening_table)");
+  } else if (h->behaviour != DXM_ELASTIC && !h->set[2]) {
     return fail("dxm_integrate: property sig0 must be set");
+  }
   if (mem != DXM_MEM_RESIDENT && !grad) return fail("dxm_integrate: grad is NULL");
   if (finish_stats(h)) return -1;  // drain a previous asynchronous call
   CK(cudaMemsetAsync(h->d_stats, 0, sizeof(StatSlot) * kStatSlots, h->stream));

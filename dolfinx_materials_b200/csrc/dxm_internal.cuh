@@ -64,6 +64,8 @@ struct dxm_handle {
   bool set[kNProp] = {false, false, false, false, false, false};
   bool perpoint = false;
   double* pp = nullptr;  // [kNProp][ld]
+  double* table = nullptr;  // DXM_J2_TABLE: device [3][ntab] = p_k, sig_k, slope_k
+  int ntab = 0;
   // statistics
   dxm::StatSlot* d_stats = nullptr;
   dxm::StatSlot* h_stats = nullptr;  // pinned

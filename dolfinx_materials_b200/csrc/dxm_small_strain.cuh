@@ -19,7 +19,8 @@ namespace dxm {
 constexpr int kNewtonCap = 25;
 constexpr double kNewtonRtol = 1e-12;
 
-enum Hardening { HARD_NONE = 0, HARD_LINEAR = 1, HARD_GENERAL = 2 };
+enum Hardening { HARD_NONE = 0, HARD_LINEAR = 1, HARD_GENERAL = 2, HARD_TABLE = 3 };
+constexpr int kMaxTable = 64;  // points of a piecewise-linear hardening table
 
 struct SmallStrainArgs {
   // s1 (written) -- eps is read from s1.strain (the gradient buffer)
@@ -40,6 +41,9 @@ struct SmallStrainArgs {
   double lam, mu, sig0, H, dsu, b;
   // per-point properties (PERPOINT == true), each [ld]
   const double *pE, *pnu, *psig0, *pH, *psigu, *pb;
+  // HARD_TABLE: piecewise-linear sigma_Y through (tp[k], ts[k]) with segment slopes tH[k] (last repeated), [3][ntab]
+  const double* table;
+  int ntab;
   StatSlot* stats;
   int vote;  // 1: warp-vote (__any_sync) Newton loop exit, 0: per-lane exit (A/B knob DXM_VOTE)
   // optional diagnostics (DIAG == true)
@@ -51,6 +55,8 @@ struct SmallStrainArgs {
 
 struct PointProps {
   double lam, mu, sig0, H, dsu, b;
+  const double *tp, *ts, *tH;  // HARD_TABLE (shared memory)
+  int ntab;
 };
 
 // ---- block-level compaction of the local Newton solves ("warp compaction of plastic points") -------------------
@@ -145,7 +151,12 @@ __device__ __forceinline__ void j2_point(const PointProps& m, const double (&eps
     const double bdsu = m.b * m.dsu;
     double ecur = 1.0;
     double sy0;
-    if (HARD == HARD_GENERAL) {
+    int seg = 0;
+    if (HARD == HARD_TABLE) {
+      for (int k = 0; k + 1 < m.ntab; ++k)
+        if (p_old >= m.tp[k + 1]) seg = k + 1;
+      sy0 = m.ts[seg] + m.tH[seg] * (p_old - m.tp[seg]);
+    } else if (HARD == HARD_GENERAL) {
       ecur = exp_c(-(m.b * p_old));
       sy0 = (m.sig0 + m.H * p_old) + m.dsu * (1.0 - ecur);
     } else {
@@ -154,8 +165,25 @@ __device__ __forceinline__ void j2_point(const PointProps& m, const double (&eps
     const double f = seq - sy0;
     flag = f > 0.0;
     // closed-form radial return (mfront :57-60) for linear hardening / no saturation term
-    const bool closed = (HARD == HARD_LINEAR) || (bdsu == 0.0);
-    if (flag && closed) dp = f / (threemu + m.H);
+    const bool closed = (HARD == HARD_LINEAR) || (HARD == HARD_TABLE) || (bdsu == 0.0);
+    if (HARD == HARD_TABLE) {
+      // exact walk over the segments of the piecewise-linear curve: closed form per segment, move on while the
+      // solution leaves the segment (n_iter counts crossings)
+      if (live && flag) {
+        for (;;) {
+          dp = (seq - (m.ts[seg] + m.tH[seg] * (p_old - m.tp[seg]))) / (threemu + m.tH[seg]);
+          if (seg + 1 < m.ntab && p_old + dp > m.tp[seg + 1]) {
+            ++seg;
+            ++n_iter;
+          } else {
+            break;
+          }
+        }
+      }
+      Hp = m.tH[seg];
+    } else if (flag && closed) {
+      dp = f / (threemu + m.H);
+    }
     if (HARD == HARD_GENERAL) {
       // capped scalar Newton, warp-synchronous: every lane of the warp stays in the loop until the
       // warp vote says no lane is still iterating (early exit as soon as the slowest lane converged)
@@ -247,8 +275,14 @@ template <int HARD, bool PERPOINT, int PPT, bool DIAG, int MINB, bool COMPACT = 
 __global__ void __launch_bounds__(256, MINB)
     dxm_small_strain_kernel(const SmallStrainArgs a) {
   static_assert(!COMPACT || (HARD == HARD_GENERAL && !PERPOINT && PPT == 1), "compaction: uniform Voce, PPT = 1");
+  static_assert(HARD != HARD_TABLE || PPT == 1, "tabulated hardening: PPT = 1");
   __shared__ CompactStore<COMPACT> cs_storage;
   CompactSmem* cs = cs_storage.get();
+  __shared__ double s_table[HARD == HARD_TABLE ? 3 * kMaxTable : 1];
+  if (HARD == HARD_TABLE) {
+    for (int i = threadIdx.x; i < 3 * a.ntab; i += blockDim.x) s_table[i] = a.table[i];
+    __syncthreads();
+  }
   const int64_t ld = a.ld;
   const int64_t ntile = (a.count + (int64_t)blockDim.x * PPT - 1) / ((int64_t)blockDim.x * PPT);
   PointStats acc;
@@ -303,6 +337,10 @@ __global__ void __launch_bounds__(256, MINB)
         m.dsu = a.dsu;
         m.b = a.b;
       }
+      m.tp = s_table;
+      m.ts = s_table + a.ntab;
+      m.tH = s_table + 2 * a.ntab;
+      m.ntab = a.ntab;
       double e1[6], e0[6], s0[6], ep0[6], so[6], epo[6], nn[6];
 #pragma unroll
       for (int c = 0; c < 6; ++c) {

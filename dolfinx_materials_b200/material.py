@@ -236,6 +236,14 @@ class CUDAMaterial:
         self.data_manager = DeviceDataManager(self, ngauss)
         for key, value in self.material_properties.items():
             self._push_property(key, value)
+        table = getattr(self.behavior, "yield_stress", None)
+        if hasattr(table, "p") and hasattr(table, "sig"):  # TabulatedHardening
+            tp = np.ascontiguousarray(table.p, dtype=np.float64).ravel()
+            ts = np.ascontiguousarray(table.sig, dtype=np.float64).ravel()
+            if tp.size != ts.size:
+                raise ValueError("TabulatedHardening: p and sig must have the same length")
+            check(lib.dxm_set_hardening_table(self._h, tp.ctypes.data_as(ctypes.c_void_p), ts.ctypes.data_as(ctypes.c_void_p),
+                                              int(tp.size)), "dxm_set_hardening_table")
 
     def _require_handle(self):
         if self._h is None:

@@ -42,7 +42,8 @@ enum {
   DXM_ELASTIC = 0,   /* LinearElasticIsotropic: E, nu                                              */
   DXM_J2_LINEAR = 1, /* J2 + linear isotropic hardening, closed form: E, nu, sig0, H                */
   DXM_J2_VOCE = 2,   /* J2 + sig0 + H p + (sigu-sig0)(1-exp(-b p)), scalar Newton: E,nu,sig0,sigu,b,H */
-  DXM_FEFP_VOCE = 3  /* finite-strain FeFp J2 plasticity, same hardening law                        */
+  DXM_FEFP_VOCE = 3, /* finite-strain FeFp J2 plasticity, same hardening law                        */
+  DXM_J2_TABLE = 4   /* J2 + piecewise-linear isotropic hardening table (dxm_set_hardening_table): E, nu  */
 };
 
 /* where a caller-supplied array lives */
@@ -72,6 +73,13 @@ int64_t dxm_npoints(const dxm_handle* h);
  * (generic.py:119-120, called from quadrature_map.py:160-172 with a 0-d or per-point array).
  * count is 1 (uniform) or n (per Gauss point). names: "E","nu","sig0","H","sigu","b". */
 int dxm_set_property(dxm_handle* h, const char* name, const double* v, int64_t count, int mem);
+
+/* Piecewise-linear isotropic hardening sigma_Y(p) through the points (p[k], sig[k]), k < count (2 <= count <= 64,
+ * p[0] = 0, p strictly increasing), continued with the last slope -- the device-side stand-in for the arbitrary
+ * `yield_stress` callable jaxmat's vonMisesIsotropicHardening accepts (a Python callable cannot cross a C ABI; the
+ * host wrapper samples it).  DXM_J2_TABLE only.  The return map walks the segments and is exact (no local Newton);
+ * the per-point iteration count reports the number of segment crossings. */
+int dxm_set_hardening_table(dxm_handle* h, const double* p, const double* sig, int count);
 
 /* state -- replaces set_initial_state_dict / get_initial_state_dict / get_final_state_dict
  * (generic.py:194-201; MaterialStateManager.set_item / __getitem__, generic.py:260-292).

@@ -43,7 +43,10 @@ def integrate(eps, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
     eps   : (n, 6) Mandel strains (C-contiguous float64, as ``quadrature_map.py:313`` builds them)
     state : dict with ``strain`` (n,6), ``stress`` (n,6), ``p`` (n,) or (n,1), ``epsp`` (n,6)  (= s0)
     props : dict with ``E, nu, sig0`` and optionally ``H, sigu, b`` -- scalars or per-point (n,) arrays.
-            Pure elasticity: ``sig0 = inf``.
+            Pure elasticity: ``sig0 = inf``.  Alternatively ``table = (p_k, sig_k)``: piecewise-linear isotropic
+            hardening through the points ``(p_k, sig_k)`` (``p_0 = 0``, increasing), continued with the last slope --
+            the device-side stand-in for an arbitrary ``yield_stress`` callable of ``vonMisesIsotropicHardening``;
+            the return map walks the segments and is exact (no Newton), ``n_iter`` counts segment crossings.
     Returns a dict: ``strain, stress, p, epsp`` (= s1), ``Ct`` (n,6,6), ``flag`` (n,) uint8 active set,
     ``n_iter`` (n,) int32 local Newton iterations, ``resid`` (n,) final |r|, ``fail`` (n,) uint8.
     """
@@ -56,6 +59,10 @@ def integrate(eps, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
 
     E = _col(props["E"], n)
     nu = _col(props["nu"], n)
+    table = props.get("table")
+    if table is not None:
+        tp, ts, tH = table_slopes(*table)
+        props = dict(props, sig0=ts[0])
     sig0 = _col(props["sig0"], n)
     H = _col(props.get("H", 0.0), n)
     sigu = _col(props.get("sigu", props["sig0"]), n)
@@ -84,6 +91,12 @@ def integrate(eps, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
 
         e0 = exp_c(-(b * p_old))
         sy0 = (sig0 + H * p_old) + dsu * (1.0 - e0)
+        if table is not None:
+            K = len(tp)
+            seg = np.zeros(n, dtype=np.int64)
+            for k in range(K - 1):
+                seg = np.where(p_old >= tp[k + 1], k + 1, seg)
+            sy0 = ts[seg] + tH[seg] * (p_old - tp[seg])
         f = seq - sy0
         flag = f > 0.0
 
@@ -98,6 +111,22 @@ def integrate(eps, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
         # closed form (mfront :57-60)
         cf = flag & closed
         dp = np.where(cf, f / (threemu + H), dp)
+
+        if table is not None:
+            # exact walk over the segments of the piecewise-linear hardening curve
+            closed = np.ones(n, dtype=bool)
+            walking = flag.copy()
+            for _ in range(K):
+                cand = (seq - (ts[seg] + tH[seg] * (p_old - tp[seg]))) / (threemu + tH[seg])
+                dp = np.where(walking, cand, dp)
+                nxt = np.minimum(seg + 1, K - 1)
+                cross = walking & (seg < K - 1) & (p_old + dp > tp[nxt])
+                seg = np.where(cross, seg + 1, seg)
+                n_iter = n_iter + cross.astype(np.int32)
+                walking = cross
+                if not walking.any():
+                    break
+            H = tH[seg]
 
         # Newton on the natural residual
         active = flag & ~closed
@@ -169,6 +198,18 @@ def integrate(eps, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
         "resid": resid,
         "fail": fail.astype(np.uint8),
     }
+
+
+def table_slopes(p, sig):
+    """(p_k, sig_k, H_k) of a piecewise-linear hardening table; H_k = slope of segment k, the last one repeated."""
+    tp = np.ascontiguousarray(p, dtype=np.float64)
+    ts = np.ascontiguousarray(sig, dtype=np.float64)
+    if tp.ndim != 1 or tp.size != ts.size or tp.size < 2 or tp[0] != 0.0 or np.any(np.diff(tp) <= 0):
+        raise ValueError("hardening table: p must start at 0 and increase strictly, with one stress per point")
+    tH = np.empty_like(tp)
+    tH[:-1] = (ts[1:] - ts[:-1]) / (tp[1:] - tp[:-1])
+    tH[-1] = tH[-2]
+    return tp, ts, tH
 
 
 def zero_state(n):
