@@ -24,6 +24,12 @@ the 9-vector entries themselves; for kind 0 the Mandel factors are undone: ``S_r
 (``utils.py:146-165``).  Local dof ``(a, r)`` has index ``a * tdim + r`` (blocked space), point ordering is the
 reference's ``num_qp * cell + q`` (``quadrature_map.py:255-260``).
 
+PARITY STATUS: **unpinned against DOLFINx** -- dolfinx / ffcx / basix are not installable in the build container, so no
+reference-executed golden vectors exist for this row.  The restatement is checked instead against an independent
+dense B-matrix / einsum formulation, the patch test, linearity for an elastic material (fe == ke u_e) and a
+finite-difference tangent through the FeFp update (``tests/test_oracle_fe_forms.py``), and end to end by the Newton
+loop of ``tests/test_newton_bar_gpu.py`` (quadratic convergence only happens with a consistent residual / tangent pair).
+
 Operation order is canonical (explicit loops, no einsum) and shared with ``fe_forms_kernel``; element vectors and
 matrices therefore agree bit for bit.  Global assembly sums element contributions (order-dependent on the GPU:
 atomics), compared with a tolerance.

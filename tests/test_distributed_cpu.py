@@ -52,3 +52,15 @@ def test_shard_range_covers_everything():
             assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
             sizes = [b - a for a, b in r]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_numa_binding_is_best_effort_without_a_gpu():
+    """No CUDA device / no exposed topology: the helpers report None and leave the affinity mask alone."""
+    import os
+
+    from dolfinx_materials_b200.distributed import bind_to_gpu_numa_node, gpu_numa_node
+
+    before = os.sched_getaffinity(0)
+    assert gpu_numa_node(0) is None
+    assert bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
