@@ -72,6 +72,9 @@ SIGNATURES = {
     "dxm_system_set_lifting": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "dxm_assemble": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "dxm_system_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "dxm_system_defer_constraints": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "dxm_system_apply_constraints": (ctypes.c_int, [ctypes.c_void_p]),
+    "dxm_system_device_ptrs": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]),
     "dxm_system_nnz": (ctypes.c_int64, [ctypes.c_void_p]),
     "dxm_system_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                         ctypes.POINTER(ctypes.c_int), c_double_p]),

@@ -129,6 +129,8 @@ struct dxm_system {
   uint8_t* bc = nullptr;
   double* lift = nullptr;  // prescribed solution values on the constrained dofs
   bool lift_on = false;    // false: homogeneous
+  bool last_lift_on = false, last_vec = false, last_mat = false;  // what the last dxm_assemble produced
+  bool defer_bc = false;   // true: dxm_assemble leaves the constrained rows to dxm_system_apply_constraints
   unsigned long long* missing = nullptr;
   double* work = nullptr;  // Krylov workspace: 9 vectors + block inverses + scalar slots (lazy)
   // per-cell block offsets into the pattern, built at the first assembly with a given mesh (node-blocked patterns)
@@ -354,7 +356,10 @@ int dxm_assemble(dxm_mesh* m, dxm_handle* h, int kind, dxm_system* s, int want_v
   if (want_matrix) CK(cudaMemsetAsync(s->vals, 0, sizeof(double) * s->nnz, h->stream));
   CK(cudaMemsetAsync(s->missing, 0, sizeof(unsigned long long), h->stream));
   if (launch_fe_forms<MODE_GLOBAL>(m, h, a)) return -1;
-  if (s->bc) {
+  s->last_lift_on = a.lift != nullptr;
+  s->last_vec = want_vector != 0;
+  s->last_mat = want_matrix != 0;
+  if (s->bc && !s->defer_bc) {
     fe_bc_diag_kernel<<<(unsigned)((s->nrows + 255) / 256), 256, 0, h->stream>>>(
         s->bc, s->rowptr, s->colidx, want_matrix ? s->vals : nullptr, s->nrows, a.lift,
         want_vector ? s->rhs : nullptr);
@@ -365,6 +370,32 @@ int dxm_assemble(dxm_mesh* m, dxm_handle* h, int kind, dxm_system* s, int want_v
   CK(cudaStreamSynchronize(h->stream));
   if (miss)
     return fail("dxm_assemble: " + std::to_string(miss) + " element entries have no slot in the CSR pattern");
+  return 0;
+}
+
+int dxm_system_defer_constraints(dxm_system* s, int on) {
+  if (!s) return fail("dxm_system_defer_constraints: NULL system");
+  s->defer_bc = on != 0;
+  return 0;
+}
+
+int dxm_system_apply_constraints(dxm_system* s) {
+  if (!s) return fail("dxm_system_apply_constraints: NULL system");
+  if (!s->bc) return 0;
+  CK(cudaSetDevice(s->device));
+  fe_bc_diag_kernel<<<(unsigned)((s->nrows + 255) / 256), 256>>>(s->bc, s->rowptr, s->colidx,
+                                                               s->last_mat ? s->vals : nullptr, s->nrows,
+                                                               s->last_lift_on ? s->lift : nullptr,
+                                                               s->last_vec ? s->rhs : nullptr);
+  LAUNCH_CHECK();
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int dxm_system_device_ptrs(dxm_system* s, double** values, double** rhs) {
+  if (!s) return fail("dxm_system_device_ptrs: NULL system");
+  if (values) *values = s->vals;
+  if (rhs) *rhs = s->rhs;
   return 0;
 }
 

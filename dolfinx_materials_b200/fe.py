@@ -27,7 +27,7 @@ KIND_STRAIN, KIND_DEFGRAD = 0, 1
 
 
 class GradientEvaluator:
-    def __init__(self, material, coords, geom_dofmap, u_dofmap, dphi, tdim=3):
+    def __init__(self, material, coords, geom_dofmap, u_dofmap, dphi, tdim=3, num_dofs=None):
         lib = _lib.load()
         material._require_handle()
         self.material = material
@@ -43,7 +43,10 @@ class GradientEvaluator:
         if dphi.shape[1:] != (ud.shape[1], self.tdim) or gd.shape[0] != ud.shape[0]:
             raise ValueError("dphi must be (nqp, ndofs_cell, tdim) and the dofmaps must cover the same cells")
         self.num_cells, self.nqp, self.ndofs_cell = ud.shape[0], dphi.shape[0], ud.shape[1]
-        self.num_dofs = int(ud.max()) + 1
+        # num_dofs: size of the (global) space when this evaluator holds only a block of its cells (one rank's share)
+        self.num_dofs = int(ud.max()) + 1 if num_dofs is None else int(num_dofs)
+        if self.num_dofs <= int(ud.max()):
+            raise ValueError("num_dofs is smaller than the largest dof index of the dofmap")
         self.kind = KIND_DEFGRAD if material.behavior.finite_strain else KIND_STRAIN
         h = ctypes.c_void_p()
         check(
@@ -136,6 +139,44 @@ class AssembledSystem:
     def assemble(self, vector=True, matrix=True):
         ev = self.forms.ev
         check(_lib.load().dxm_assemble(ev._h, ev.material._h, ev.kind, self._h, int(vector), int(matrix)), "dxm_assemble")
+
+    # ---- rank-sharded assembly (one process per GPU, each with a contiguous block of cells) -----------------
+    def device_arrays(self):
+        """Zero-copy ``torch`` views of the CSR value array (nnz,) and the right-hand side (nrows,) on the device."""
+        import torch
+
+        pv, pr = ctypes.c_void_p(), ctypes.c_void_p()
+        check(_lib.load().dxm_system_device_ptrs(self._h, ctypes.byref(pv), ctypes.byref(pr)), "dxm_system_device_ptrs")
+
+        class _Cai:  # __cuda_array_interface__ carrier
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+        dev = torch.device("cuda", self.forms.ev.material.device)
+        return (torch.as_tensor(_Cai(pv.value, self.nnz), device=dev), torch.as_tensor(_Cai(pr.value, self.nrows), device=dev))
+
+    def assemble_sharded(self, group=None, vector=True, matrix=True):
+        """Assemble this rank's cells, sum values / rhs over the process group (NCCL all-reduce over NVLink -- the
+        one real exchange step of the FE side, what PETSc's assembly does for the reference), then apply the
+        constraints once.  Every rank ends up with the full system."""
+        import torch.distributed as dist
+
+        lib = _lib.load()
+        check(lib.dxm_system_defer_constraints(self._h, 1), "dxm_system_defer_constraints")
+        try:
+            self.assemble(vector=vector, matrix=matrix)
+        finally:
+            check(lib.dxm_system_defer_constraints(self._h, 0), "dxm_system_defer_constraints")
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            vals, rhs = self.device_arrays()
+            if matrix:
+                dist.all_reduce(vals, group=group)
+            if vector:
+                dist.all_reduce(rhs, group=group)
+            import torch
+
+            torch.cuda.synchronize()
+        check(lib.dxm_system_apply_constraints(self._h), "dxm_system_apply_constraints")
 
     def get(self, values=True, rhs=True):
         """-> (CSR values (nnz,), rhs (nrows,)) on the host (``A.setValuesCSR(rowptr, colidx, values)``).  The arrays

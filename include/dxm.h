@@ -166,6 +166,13 @@ int dxm_system_set_bc(dxm_system* s, const uint8_t* marker); /* host array of nr
 int dxm_system_set_lifting(dxm_system* s, const double* values);
 int dxm_assemble(dxm_mesh* m, dxm_handle* h, int kind, dxm_system* s, int want_vector, int want_matrix);
 int dxm_system_get(dxm_system* s, double* values, double* rhs, int mem); /* either may be NULL */
+/* Rank-sharded assembly (one process per GPU, each holding a contiguous block of cells): every rank
+ * assembles its cells into a system of the full pattern with the constrained rows deferred, the value / rhs arrays
+ * (device pointers below) are summed across ranks (NCCL all-reduce -- what PETSc's MatAssembly / ghost update do for
+ * the reference, solvers.py:84-96), then dxm_system_apply_constraints sets the unit diagonal and rhs[bc] once. */
+int dxm_system_defer_constraints(dxm_system* s, int on);
+int dxm_system_apply_constraints(dxm_system* s);
+int dxm_system_device_ptrs(dxm_system* s, double** values, double** rhs);
 int64_t dxm_system_nnz(const dxm_system* s);
 /* Device-resident Krylov solve A x = rhs of the assembled system (BiCGStab, block x block Jacobi preconditioner,
  * x0 = 0, stop at |r| <= rtol |rhs|); returns 0 converged, 1 maxit reached, < 0 error.  NOT part of the drop-in

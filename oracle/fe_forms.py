@@ -169,12 +169,13 @@ def sparsity(u_dofmap, num_dofs, tdim):
     return P.indptr.astype(np.int64), P.indices.astype(np.int32)
 
 
-def assemble(u_dofmap, fe, ke, num_dofs, tdim, bc=None, lift=None):
+def assemble(u_dofmap, fe, ke, num_dofs, tdim, bc=None, lift=None, constrain=True):
     """Global residual vector and CSR tangent from the element forms.  ``bc``: optional bool marker per global
     dof -- constrained rows/columns receive no contribution and a unit diagonal (what
     ``assemble_matrix(A, a, bcs)`` + ``set_bc`` leave for a Newton correction with homogeneous increments).
     ``lift``: prescribed solution values on the constrained dofs -- ``b -= A[:, bc] lift[bc]`` on the free rows
-    and ``b[bc] = lift[bc]`` (``apply_lifting`` + ``set_bc``, ``solvers.py:84-96``)."""
+    and ``b[bc] = lift[bc]`` (``apply_lifting`` + ``set_bc``, ``solvers.py:84-96``).  ``constrain=False`` leaves the
+    constrained rows empty (a rank's partial contribution, to be summed across ranks before ``apply_constraints``)."""
     import scipy.sparse as sp
 
     gdofs = global_dofs(u_dofmap, tdim)
@@ -192,11 +193,23 @@ def assemble(u_dofmap, fe, ke, num_dofs, tdim, bc=None, lift=None):
             lift = np.asarray(lift, dtype=np.float64)
             moved = np.where(free[rows] & ~free[cols], ke.ravel() * lift[cols], 0.0)
             np.subtract.at(b, rows, moved)
-            b[~free] = lift[~free]
+            if constrain:
+                b[~free] = lift[~free]
         vals = np.where(free[rows] & free[cols], ke.ravel(), 0.0)
         A = sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
         A.sum_duplicates()
-        if bc is not None:
+        if bc is not None and constrain:
             A = A + sp.diags(np.where(free, 0.0, 1.0), format="csr")
         A.sort_indices()
     return b, A
+
+
+def apply_constraints(A, b, bc, lift=None):
+    """Unit diagonal and prescribed rhs on the constrained dofs of a summed (rank-sharded) system."""
+    import scipy.sparse as sp
+
+    free = ~np.asarray(bc, dtype=bool)
+    A = A + sp.diags(np.where(free, 0.0, 1.0), format="csr")
+    b = b.copy()
+    b[~free] = 0.0 if lift is None else np.asarray(lift)[~free]
+    return A, b

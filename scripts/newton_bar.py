@@ -9,6 +9,13 @@ with a structured Kuhn mesh instead of gmsh and BiCGStab + block-Jacobi instead 
 PETSc, gmsh and MPI are not available in this image, so this is a surrogate of the reference's driver, not a run of it.
 
     python scripts/newton_bar.py [nx ny nz] [--steps S] [--strain E] [--json out.json]
+    torchrun --nproc-per-node N scripts/newton_bar.py ...        # N ranks, one GPU each
+
+With N ranks the cells are split into N contiguous blocks: each rank evaluates gradients, runs the
+constitutive update and assembles for its own cells only -- no exchange, as in the reference where every MPI rank owns
+a mesh partition -- then the assembled values / right-hand side are summed over the ranks with one NCCL all-reduce
+(the FE side's only exchange step, what PETSc's assembly does for the reference).  The Krylov stand-in is not
+distributed: rank 0 solves and broadcasts the correction.
 """
 import argparse
 import json
@@ -114,19 +121,30 @@ def boundary_conditions(nodes, L):
 
 def run_gpu(nx, ny, nz, steps=3, strain=0.01, L=10.0, W=1.0, newton_rtol=1e-8, newton_atol=1e-8, ksp_rtol=1e-8,
             ksp_maxit=50000, max_newton=20, verbose=True, props=None):
+    import torch
+    import torch.distributed as dist
+
     import dolfinx_materials_b200 as jm
+    from dolfinx_materials_b200.distributed import allreduce_stats, shard_range
     from dolfinx_materials_b200.fe import AssembledSystem, ElementForms, GradientEvaluator
+
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    device = torch.cuda.current_device()
+    verbose = verbose and rank == 0
 
     props = props or dict(E=70e3, nu=0.3, sig0=500.0, sigu=750.0, b=1000.0)
     t0 = time.perf_counter()
     coords, gd, ud, nodes = bar_mesh(nx, ny, nz, L, W)
     dphi = p2_tet_dphi(QP_DEG2)
-    nc, nqp = len(gd), 4
+    nc_global, nqp = len(gd), 4
+    c0, c1 = shard_range(nc_global, rank, world)  # this rank's contiguous block of cells
+    nc = c1 - c0
     mat = jm.CUDAMaterial(jm.FeFpJ2Plasticity(
         elasticity=jm.LinearElasticIsotropic(E=props["E"], nu=props["nu"]),
-        yield_stress=jm.VoceHardening(sig0=props["sig0"], sigu=props["sigu"], b=props["b"])))
+        yield_stress=jm.VoceHardening(sig0=props["sig0"], sigu=props["sigu"], b=props["b"])), device=device)
     mat.set_data_manager(nc * nqp)
-    ge = GradientEvaluator(mat, coords, gd, ud, dphi, tdim=3)
+    ge = GradientEvaluator(mat, coords, gd[c0:c1], ud[c0:c1], dphi, tdim=3, num_dofs=len(nodes))
     forms = ElementForms(ge, W_DEG2)
     rowptr, colidx = sparsity(ud, len(nodes))
     bc, top_dofs = boundary_conditions(nodes, L)
@@ -147,22 +165,33 @@ def run_gpu(nx, ny, nz, steps=3, strain=0.01, L=10.0, W=1.0, newton_rtol=1e-8, n
             t = time.perf_counter(); ge.eval(u); timers["gradients"] += time.perf_counter() - t
             t = time.perf_counter(); st = mat.integrate_resident(); timers["update"] += time.perf_counter() - t
             kernel_ms += st.kernel_ms
+            st = allreduce_stats(st)
             if st.n_fail:
                 raise RuntimeError(f"{st.n_fail} local solves failed")
             t = time.perf_counter()
             system.set_lifting(lift if it == 0 else None)
-            system.assemble()
+            system.assemble_sharded()  # local cells, then one NCCL all-reduce of values / rhs when world > 1
             timers["assemble"] += time.perf_counter() - t
             t = time.perf_counter(); _, rhs = system.get(values=False); timers["rhs_d2h"] += time.perf_counter() - t
             rn = float(np.linalg.norm(rhs))
             r0 = rn if r0 is None else r0
             if verbose:
-                print(f"step {k} newton {it}: |R| = {rn:.6e}  plastic {st.n_plastic / (nc * nqp):.3f}", flush=True)
+                print(f"step {k} newton {it}: |R| = {rn:.6e}  plastic {st.n_plastic / (nc_global * nqp):.3f}", flush=True)
             if it > 0 and (rn <= newton_atol or rn <= newton_rtol * r0):
                 break
             if it == max_newton:
                 raise RuntimeError("Newton did not converge")
-            t = time.perf_counter(); du, kit, rel, ok = system.solve(rtol=ksp_rtol, maxit=ksp_maxit); timers["solve"] += time.perf_counter() - t
+            t = time.perf_counter()
+            if rank == 0:
+                du, kit, rel, ok = system.solve(rtol=ksp_rtol, maxit=ksp_maxit)
+            if world > 1:  # the stand-in solver is not distributed: rank 0 solves, everyone gets the same correction
+                meta = torch.tensor([kit, rel, float(ok)] if rank == 0 else [0.0, 0.0, 0.0], dtype=torch.float64, device="cuda")
+                dut = torch.from_numpy(du).cuda() if rank == 0 else torch.empty(u.size, dtype=torch.float64, device="cuda")
+                dist.broadcast(meta, 0)
+                dist.broadcast(dut, 0)
+                du = dut.cpu().numpy()
+                kit, rel, ok = int(meta[0].item()), meta[1].item(), bool(meta[2].item())
+            timers["solve"] += time.perf_counter() - t
             if not ok:
                 raise RuntimeError(f"Krylov solve stalled at {rel:.3e} after {kit} iterations")
             history.append(dict(step=k, newton=it, residual=rn, krylov_iterations=kit, krylov_relres=rel))
@@ -170,13 +199,21 @@ def run_gpu(nx, ny, nz, steps=3, strain=0.01, L=10.0, W=1.0, newton_rtol=1e-8, n
         mat.data_manager.update()
     t_total = time.perf_counter() - t_loop
     n_updates = len(history) + steps
-    info = dict(cells=nc, points=nc * nqp, dofs=u.size, nnz=int(system.nnz), steps=steps, strain=strain,
+    if world > 1:  # per-stage times: slowest rank
+        tt = torch.tensor([timers[k] for k in sorted(timers)] + [kernel_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        for k, v in zip(sorted(timers), tt.tolist()):
+            timers[k] = v
+        kernel_ms = tt[-1].item()
+    nc = nc_global
+    info = dict(ranks=world, cells=nc, points=nc * nqp, dofs=u.size, nnz=int(system.nnz), steps=steps, strain=strain,
                 newton_iterations=len(history), constitutive_updates=n_updates, setup_s=t_setup, loop_s=t_total,
                 timers_s=timers, update_kernel_ms_total=kernel_ms,
                 constitutive_share=timers["update"] / t_total,
                 update_gps=nc * nqp * n_updates / max(timers["update"], 1e-12),
                 krylov_iterations_total=int(sum(h["krylov_iterations"] for h in history)),
-                plastic_fraction=st.n_plastic / (nc * nqp))
+                plastic_fraction=st.n_plastic / (nc * nqp),
+                u_l2=float(np.linalg.norm(u)), u_probe=[float(x) for x in u[:: max(1, u.size // 7)][:7]])
     return u, mat, info, history
 
 
@@ -189,7 +226,21 @@ if __name__ == "__main__":
     ap.add_argument("--ksp-rtol", type=float, default=1e-8)
     a = ap.parse_args()
     nx, ny, nz = (a.n + [8, 8])[:3]
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     u, mat, info, hist = run_gpu(nx, ny, nz, steps=a.steps, strain=a.strain, ksp_rtol=a.ksp_rtol)
+    if world > 1:
+        rank0 = dist.get_rank() == 0
+        dist.barrier()
+        dist.destroy_process_group()
+        if not rank0:
+            sys.exit(0)
     print(json.dumps(info, indent=1))
     if a.json:
         os.makedirs(os.path.dirname(a.json) or ".", exist_ok=True)

@@ -64,3 +64,59 @@ def test_numa_binding_is_best_effort_without_a_gpu():
     assert gpu_numa_node(0) is None
     assert bind_to_gpu_numa_node(0) is None
     assert os.sched_getaffinity(0) == before
+
+
+def _asm_worker(rank, world, port, q):
+    """Rank-sharded assembly, host logic: each rank assembles its contiguous block of cells with the constrained rows
+    deferred, values / rhs are summed over the group, constraints are applied once (what
+    AssembledSystem.assemble_sharded does with the CUDA kernels + NCCL)."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from dolfinx_materials_b200.distributed import shard_range
+    from oracle import fe_forms as ff
+    from oracle import fe_gradient as fg
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    coords, gd, ud, nodes = fg.box_tets(3, 2, 2, 2)
+    dphi, w = fg.tet_dphi(fg.TET_QP_DEG2, 2), np.full(4, 1.0 / 24.0)
+    nc = len(gd)
+    rng = np.random.default_rng(11)  # same data on every rank
+    flux = rng.standard_normal((nc * 4, 9))
+    ct = rng.standard_normal((nc * 4, 81))
+    n = 3 * len(nodes)
+    bc = np.repeat(nodes[:, 0] < 0.05, 3)
+    lift = np.where(bc, 1e-3 * np.cos(np.arange(n)), 0.0)
+    c0, c1 = shard_range(nc, rank, world)
+    fe, ke = ff.element_forms(coords, gd[c0:c1], ud[c0:c1], dphi, w, flux[4 * c0:4 * c1], ct[4 * c0:4 * c1], 1, 3)
+    b, A = ff.assemble(ud[c0:c1], fe, ke, len(nodes), 3, bc=bc, lift=lift, constrain=False)
+    dense = torch.from_numpy(A.toarray())
+    bt = torch.from_numpy(b)
+    dist.all_reduce(dense)
+    dist.all_reduce(bt)
+    import scipy.sparse as sp
+
+    A2, b2 = ff.apply_constraints(sp.csr_matrix(dense.numpy()), bt.numpy(), bc, lift)
+    fe_all, ke_all = ff.element_forms(coords, gd, ud, dphi, w, flux, ct, 1, 3)
+    b_ref, A_ref = ff.assemble(ud, fe_all, ke_all, len(nodes), 3, bc=bc, lift=lift)
+    scale = np.abs(ke_all).max()
+    q.put((rank, c0, c1, float(abs(A2 - A_ref).max() / scale), float(np.abs(b2 - b_ref).max() / np.abs(b_ref).max())))
+    dist.destroy_process_group()
+
+
+def test_rank_sharded_assembly_world2():
+    world, port = 2, 29613
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_asm_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == 72
+    for _, _, _, ea, eb in res:
+        assert ea < 1e-13 and eb < 1e-13
