@@ -37,7 +37,7 @@ def _nvcc():
 
 
 def sources():
-    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "dxm.h"]
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.hpp")) + [ROOT.parent / "include" / "dxm.h"]
 
 
 def needs_build():

@@ -3,6 +3,7 @@
 // (FE-side entry points: dxm_fe_api.cu; measurement support: dxm_peaks.cu.)
 #include "dxm_internal.cuh"
 #include "dxm_fefp.cuh"
+#include "dxm_host_mirror.hpp"
 #include "dxm_layout.cuh"
 #include "dxm_small_strain.cuh"
 
@@ -16,6 +17,7 @@ std::atomic<long long> g_launches{0};
 namespace {
 constexpr int64_t kChunk = 1 << 19;  // points per pipeline chunk on the host path
 const char* kPropNames[kNProp] = {"E", "nu", "sig0", "H", "sigu", "b"};
+constexpr bool kHostMirrorDefault = false;  // A/B on the B200 box: profiles/ (DXM_HOST_MIRROR overrides)
 }  // namespace
 
 namespace {
@@ -96,6 +98,22 @@ int ensure_staging(dxm_handle* h) {
   for (int s = 0; s < 2; ++s) {
     CK(cudaMalloc(&h->d_in[s], sizeof(double) * h->chunk * h->ngrad));
     CK(cudaMalloc(&h->d_out[s], sizeof(double) * h->chunk * nout));
+  }
+  return 0;
+}
+
+// DXM_HOST_MIRROR=0|1: send the symmetric tangent over PCIe packed (21 of 36 entries) and mirror it into the
+// caller's (n, 36) array with host threads (dxm_host_mirror.hpp) instead of expanding it on the device first.
+bool host_mirror_enabled() {
+  const char* e = std::getenv("DXM_HOST_MIRROR");
+  return e ? std::atoi(e) != 0 : kHostMirrorDefault;
+}
+
+int ensure_mirror_ring(dxm_handle* h) {
+  if (h->h_ctp[0]) return 0;
+  for (int s = 0; s < dxm_handle::kRing; ++s) {
+    CK(cudaMallocHost(&h->h_ctp[s], sizeof(double) * h->chunk * h->nct_store));
+    CK(cudaEventCreateWithFlags(&h->ev_ct[s], cudaEventDisableTiming));
   }
   return 0;
 }
@@ -367,6 +385,10 @@ void free_handle(dxm_handle* h) {
     if (h->ev_in_free[s]) cudaEventDestroy(h->ev_in_free[s]);
     if (h->ev_packed[s]) cudaEventDestroy(h->ev_packed[s]);
     if (h->ev_out_free[s]) cudaEventDestroy(h->ev_out_free[s]);
+  }
+  for (int s = 0; s < dxm_handle::kRing; ++s) {
+    if (h->h_ctp[s]) cudaFreeHost(h->h_ctp[s]);
+    if (h->ev_ct[s]) cudaEventDestroy(h->ev_ct[s]);
   }
   for (cudaEvent_t e : h->ev_k) cudaEventDestroy(e);
   cudaFree(h->d_flag);
@@ -761,8 +783,25 @@ int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double*
       return fail("dxm_integrate: host gradients require host outputs");
     if (ensure_staging(h)) return -1;
     // 3-stage pipeline over chunks: H2D (s_in) | transpose + update + pack (stream) | D2H (s_out)
+    // (+ a 4th stage on the host when the packed tangent is mirrored there, dxm_host_mirror.hpp)
     const int64_t CH = h->chunk;
-    const int nf = h->nflux, ni = h->nisv, nc = h->nct;
+    const int nf = h->nflux, ni = h->nisv, nc = h->nct, ncs = h->nct_store;
+    const bool mirror = ct && ncs != nc && host_mirror_enabled();
+    if (mirror && ensure_mirror_ring(h)) return -1;
+    struct Pending {
+      int slot;
+      int64_t s, m;
+    };
+    Pending pend[dxm_handle::kRing];
+    int npend = 0;
+    auto drain_one = [&]() -> int {  // oldest in-flight packed chunk -> the caller's (n, 36) rows
+      const Pending p = pend[0];
+      for (int i = 1; i < npend; ++i) pend[i - 1] = pend[i];
+      --npend;
+      CK(cudaEventSynchronize(h->ev_ct[p.slot]));
+      dxm_host::mirror_sym6(h->h_ctp[p.slot], ct + p.s * nc, p.m, 0);
+      return 0;
+    };
     // make the copy streams wait for whatever precedes on the compute stream
     CK(cudaEventRecord(h->ev_in_free[0], h->stream));
     CK(cudaEventRecord(h->ev_in_free[1], h->stream));
@@ -788,7 +827,8 @@ int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double*
         if (isv && launch_soa_to_aos(h, h->stream, s1 + (int64_t)isv_row * ld, s, o + CH * nf, ni, 0,
                                      m, ni))
           return -1;
-        if (ct && launch_soa_to_aos(h, h->stream, h->ct, s, o + CH * (nf + ni), nc, 0, m, nc, h->nct_store != nc))
+        if (ct && (mirror ? launch_soa_to_aos(h, h->stream, h->ct, s, o + CH * (nf + ni), ncs, 0, m, ncs, 0)
+                          : launch_soa_to_aos(h, h->stream, h->ct, s, o + CH * (nf + ni), nc, 0, m, nc, ncs != nc)))
           return -1;
         CK(cudaEventRecord(h->ev_packed[b], h->stream));
         CK(cudaStreamWaitEvent(h->s_out, h->ev_packed[b], 0));
@@ -798,12 +838,25 @@ int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double*
         if (isv)
           CK(cudaMemcpyAsync(isv + s * ni, o + CH * nf, sizeof(double) * m * ni,
                              cudaMemcpyDeviceToHost, h->s_out));
-        if (ct)
+        if (mirror) {
+          // ring slot c % kRing was last used by chunk c - kRing, drained below before chunk c - 1 was left
+          const int slot = (int)(c % dxm_handle::kRing);
+          CK(cudaMemcpyAsync(h->h_ctp[slot], o + CH * (nf + ni), sizeof(double) * m * ncs,
+                             cudaMemcpyDeviceToHost, h->s_out));
+          CK(cudaEventRecord(h->ev_ct[slot], h->s_out));
+          pend[npend++] = Pending{slot, s, m};
+        } else if (ct) {
           CK(cudaMemcpyAsync(ct + s * nc, o + CH * (nf + ni), sizeof(double) * m * nc,
                              cudaMemcpyDeviceToHost, h->s_out));
+        }
         CK(cudaEventRecord(h->ev_out_free[b], h->s_out));
+        // keep kRing - 1 chunks queued on the device while the host mirrors the oldest one
+        while (npend > dxm_handle::kRing - 1)
+          if (drain_one()) return -1;
       }
     }
+    while (npend > 0)
+      if (drain_one()) return -1;
     h->s1_valid = true;
     CK(cudaStreamSynchronize(h->s_out));
     CK(cudaStreamSynchronize(h->stream));
@@ -874,6 +927,12 @@ int dxm_synth_gradients(dxm_handle* h, int recipe, uint64_t seed, double amp, in
   synth_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(h->gen[1 - h->i0], h->ld, h->n, h->ngrad,
                                                        recipe, seed, amp, kfrac, start);
   LAUNCH_CHECK();
+  return 0;
+}
+
+int dxm_host_mirror_sym6(const double* packed, double* full, int64_t n, int threads) {
+  if (n < 0 || (n > 0 && (!packed || !full))) return fail("dxm_host_mirror_sym6: bad argument");
+  dxm_host::mirror_sym6(packed, full, n, threads);
   return 0;
 }
 

@@ -81,6 +81,10 @@ struct dxm_handle {
   int64_t chunk = 0;
   double* d_in[2] = {nullptr, nullptr};
   double* d_out[2] = {nullptr, nullptr};
+  // host mirror of the packed tangent (dxm_host_mirror.hpp): page-locked ring of packed (chunk, 21) blocks
+  static constexpr int kRing = 3;
+  double* h_ctp[kRing] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_ct[kRing] = {nullptr, nullptr, nullptr};
   // diagnostics
   bool diag = false;
   uint8_t *d_flag = nullptr, *d_fail = nullptr;

@@ -190,6 +190,13 @@ int dxm_host_free(void* ptr);
 int dxm_host_register(void* ptr, int64_t bytes);
 int dxm_host_unregister(void* ptr);
 
+/* Host half of the packed-tangent hand-off: expands packed (n, 21) rows of the symmetric 6x6 tangent (row map in the
+ * conventions above) into the reference's row-major (n, 36) array (quadrature_map.py:334) on `threads` host threads
+ * (<= 0: library default, DXM_HOST_THREADS).  Pure data movement, bit for bit.  dxm_integrate(..., DXM_MEM_HOST, ...)
+ * uses it internally when DXM_HOST_MIRROR=1: the device then sends 21 instead of 36 doubles per point over PCIe and
+ * the mirror runs on the host while the next chunk is in flight. */
+int dxm_host_mirror_sym6(const double* packed, double* full, int64_t n, int threads);
+
 /* measurement support */
 int64_t dxm_launch_count(void);                       /* kernels launched by this library so far */
 int dxm_fp64_peak(int device, double* tflops);        /* register-resident DFMA microbenchmark   */

@@ -89,3 +89,27 @@ def test_packed_tangent_index_map():
     m = SYM6_PACKED.reshape(6, 6)
     assert np.array_equal(m, m.T) and sorted(set(m.ravel())) == list(range(21))
     assert [m[j, i] for j in range(6) for i in range(j, 6)] == list(range(21))
+
+
+@pytest.mark.parametrize("n,threads", [(0, 1), (1, 1), (7, 0), (5000, 1), (40001, 0), (40001, 3)])
+def test_host_mirror_of_the_packed_tangent(jm, n, threads):
+    """dxm_host_mirror_sym6 (host half of the packed-tangent hand-off, no GPU involved): (n, 21) -> (n, 36), every
+    value copied bit for bit, on aligned (streaming stores) and unaligned destinations, 1 thread and the pool."""
+    from dolfinx_materials_b200 import _lib
+    from dolfinx_materials_b200.material import SYM6_PACKED
+
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    packed = rng.standard_normal((n, 21))
+    if n:
+        packed[0, :3] = [np.nan, -0.0, np.inf]
+    want = packed[:, SYM6_PACKED]
+    for offset in (0, 1):  # offset 1 double: 8-byte aligned only -> plain-store path
+        buf = np.full(n * 36 + 2 + offset, -7.0)
+        base = (-buf.ctypes.data // 8) % 2  # make `full` 16-byte aligned, then shift by `offset`
+        full = buf[base + offset: base + offset + n * 36]
+        assert (full.ctypes.data % 16 == 0) == (offset == 0) or n == 0
+        rc = lib.dxm_host_mirror_sym6(packed.ctypes.data_as(ctypes.c_void_p), full.ctypes.data_as(ctypes.c_void_p), n, threads)
+        assert rc == 0
+        assert full.reshape(n, 36).tobytes() == want.tobytes()
+        assert buf[base + offset + n * 36] == -7.0 and (base + offset == 0 or buf[base + offset - 1] == -7.0)
