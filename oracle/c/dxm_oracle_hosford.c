@@ -1,0 +1,325 @@
+/*
+ * dxm_oracle_hosford.c -- plain-C oracle of the small-strain Hosford plasticity update.  TEST INFRASTRUCTURE ONLY
+ * (see oracle/__init__.py); never linked into the product.
+ *
+ * Restates the behaviour of demos/multimaterials/IsotropicPlasticHosfordFlowLinear.mfront:1-27 (MFront `Implicit` DSL,
+ * StandardElastoViscoPlasticity brick: Hooke stress potential, "Plastic" flow with the Hosford criterion {a: 10} and
+ * linear isotropic hardening R0 + H p, theta = 1), the matrix phase of demos/multimaterials/multimaterials.py:245-254:
+ *
+ *     sigma_eq = ( 1/2 (|s1-s2|^a + |s2-s3|^a + |s3-s1|^a) )^(1/a)            principal stresses s_k
+ *     eel + dp n(sigma) = eel_old + deps ,  n = d sigma_eq / d sigma          (backward Euler, associated flow)
+ *     sigma_eq(sigma) - R0 - H (p_old + dp) = 0 ,  sigma = C : eel
+ *
+ * MFront's generated code is not in the tree and TFEL/MGIS are absent, so parity with MFront is UNPINNED; the
+ * restatement is checked against an independent solve of the 7-unknown system above (numpy eigh + scipy) and finite
+ * differences (tests/test_oracle_hosford.py).  State layout follows the other small-strain behaviours of this build
+ * (strain, stress, p, epsp; eel = strain - epsp); the exponent a is an even integer (2 = von Mises, 6/8 the usual
+ * bcc/fcc fits, 10 the demo), which makes every power a product chain and the tangent's spectral terms exact.
+ *
+ * Algorithm (operation order == csrc/dxm_hosford.cuh, compiled with -ffp-contract=off / -fmad=false):
+ *   trial stress as in the J2 update; cheap rejection sigma_eq <= max|s_i - s_j| <= 2/sqrt(3) seq_Mises;
+ *   cyclic Jacobi eigen-decomposition of the trial deviator (+, -, *, /, sqrt only); isotropy keeps the principal
+ *   axes, so the return map is a 4-unknown Newton (3 principal deviatoric stresses + dp) started from the radially
+ *   scaled trial state with a simple-decrease backtracking line search; the consistent tangent
+ *   Xi - (Xi n)(Xi n)^T / (n Xi n + H), Xi = (C^-1 + dp dn/dsigma)^-1, is assembled from its spectral form: a 3x3
+ *   normal block 2 mu A^-1 + lam 1 1^T - ..., and three shear moduli 2 mu / (1 + 2 mu dp theta_ij) with
+ *   theta_ij = (n_i - n_j)/(s_i - s_j) written as an exact divided difference (no 0/0 at repeated eigenvalues).
+ */
+#include <math.h>
+#include <stdint.h>
+
+#define RSQRT2 0.7071067811865476
+#define SQRT2 1.4142135623730951
+#define LS_MAX 10
+#define JACOBI_SWEEPS 8
+
+/* (x*x)^k, k >= 1, as a product chain */
+static double ipow2(double x, int k) {
+  const double x2 = x * x;
+  double y = x2;
+  for (int i = 1; i < k; ++i) y = y * x2;
+  return y;
+}
+
+/* q^(1/a), q in (0.5, 1]: Newton from above on y^a = q (monotone decreasing until rounding stops it) */
+static double aroot(double q, int a) {
+  const double ad = (double)a, am1 = ad - 1.0;
+  double y = 1.0;
+  for (int it = 0; it < 30; ++it) {
+    const double ym = (a > 2) ? ipow2(y, (a - 2) / 2) * y : y; /* y^(a-1) */
+    const double yn = (am1 * y + q / ym) / ad;
+    if (!(yn < y)) break;
+    y = yn;
+  }
+  return y;
+}
+
+/* Hosford equivalent stress of principal values l, its gradient n and h_k = (d_k/phi)^(a-2), u_k = d_k/phi */
+static void hosford_eval(const double l[3], int a, double* phi, double n[3], double h[3], double u[3]) {
+  const double d0 = l[0] - l[1], d1 = l[1] - l[2], d2 = l[2] - l[0];
+  const double m = fmax(fmax(fabs(d0), fabs(d1)), fabs(d2));
+  const double r0 = d0 / m, r1 = d1 / m, r2 = d2 / m;
+  const double q = 0.5 * ((ipow2(r0, a / 2) + ipow2(r1, a / 2)) + ipow2(r2, a / 2));
+  const double y = aroot(q, a);
+  *phi = m * y;
+  u[0] = r0 / y;
+  u[1] = r1 / y;
+  u[2] = r2 / y;
+  for (int k = 0; k < 3; ++k) h[k] = (a > 2) ? ipow2(u[k], (a - 2) / 2) : 1.0;
+  const double g0 = h[0] * u[0], g1 = h[1] * u[1], g2 = h[2] * u[2];
+  n[0] = 0.5 * (g0 - g2);
+  n[1] = 0.5 * (g1 - g0);
+  n[2] = 0.5 * (g2 - g1);
+}
+
+/* sum_{k=0}^{a-2} x^k y^(a-2-k)  ( = (x^(a-1) - y^(a-1)) / (x - y), exact also at x == y ) */
+static double divdiff(double x, double y, int a) {
+  double t = 1.0, xp = 1.0;
+  for (int j = 1; j <= a - 2; ++j) {
+    xp = xp * x;
+    t = y * t + xp;
+  }
+  return t;
+}
+
+/* one Jacobi rotation annihilating a_pq; r is the third index: arp = a_rp, arq = a_rq; Q columns p, q */
+static void jrot(double* app, double* aqq, double* apq, double* arp, double* arq, double Q[3][3], int p, int q) {
+  if (*apq == 0.0) return;
+  const double g = 100.0 * fabs(*apq);
+  if ((fabs(*app) + g == fabs(*app)) && (fabs(*aqq) + g == fabs(*aqq))) {
+    *apq = 0.0;
+    return;
+  }
+  const double theta = ((*aqq - *app) * 0.5) / *apq;
+  double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+  if (theta < 0.0) t = -t;
+  const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+  *app = *app - t * *apq;
+  *aqq = *aqq + t * *apq;
+  *apq = 0.0;
+  const double xp = *arp, xq = *arq;
+  *arp = c * xp - sn * xq;
+  *arq = sn * xp + c * xq;
+  for (int k = 0; k < 3; ++k) {
+    const double vp = Q[k][p], vq = Q[k][q];
+    Q[k][p] = c * vp - sn * vq;
+    Q[k][q] = sn * vp + c * vq;
+  }
+}
+
+/* symmetric 3x3 from a Mandel deviator: eigenvalues l, eigenvectors in the columns of Q */
+static void jacobi3(const double s[6], double l[3], double Q[3][3]) {
+  double a00 = s[0], a11 = s[1], a22 = s[2], a01 = s[3] * RSQRT2, a02 = s[4] * RSQRT2, a12 = s[5] * RSQRT2;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Q[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < JACOBI_SWEEPS; ++sweep) {
+    if ((fabs(a01) + fabs(a02)) + fabs(a12) == 0.0) break;
+    jrot(&a00, &a11, &a01, &a02, &a12, Q, 0, 1);
+    jrot(&a00, &a22, &a02, &a01, &a12, Q, 0, 2);
+    jrot(&a11, &a22, &a12, &a01, &a02, Q, 1, 2);
+  }
+  l[0] = a00;
+  l[1] = a11;
+  l[2] = a22;
+}
+
+typedef struct {
+  double rs[3], r4, phi, n[3], h[3], u[3], m2;
+} hres_t;
+
+static void hosford_residual(const double x[3], double dp, const double l[3], double twomu, double sy0, double H, int a,
+                             hres_t* o) {
+  hosford_eval(x, a, &o->phi, o->n, o->h, o->u);
+  const double c = twomu * dp;
+  for (int k = 0; k < 3; ++k) o->rs[k] = (x[k] - l[k]) + c * o->n[k];
+  o->r4 = o->phi - (sy0 + H * dp);
+  o->m2 = ((o->rs[0] * o->rs[0] + o->rs[1] * o->rs[1]) + o->rs[2] * o->rs[2]) + o->r4 * o->r4;
+}
+
+/* A = I + c k1 (M/2 - n n^T) (symmetric), its adjugate C and 1/det */
+static void hosford_system(const hres_t* r, double c, double k1, double Cf[6], double* idet) {
+  const double ck = c * k1;
+  const double A00 = 1.0 + ck * (0.5 * (r->h[0] + r->h[2]) - r->n[0] * r->n[0]);
+  const double A11 = 1.0 + ck * (0.5 * (r->h[0] + r->h[1]) - r->n[1] * r->n[1]);
+  const double A22 = 1.0 + ck * (0.5 * (r->h[1] + r->h[2]) - r->n[2] * r->n[2]);
+  const double A01 = ck * (-0.5 * r->h[0] - r->n[0] * r->n[1]);
+  const double A02 = ck * (-0.5 * r->h[2] - r->n[0] * r->n[2]);
+  const double A12 = ck * (-0.5 * r->h[1] - r->n[1] * r->n[2]);
+  Cf[0] = A11 * A22 - A12 * A12; /* C00 */
+  Cf[1] = A02 * A12 - A01 * A22; /* C01 */
+  Cf[2] = A01 * A12 - A02 * A11; /* C02 */
+  Cf[3] = A00 * A22 - A02 * A02; /* C11 */
+  Cf[4] = A01 * A02 - A00 * A12; /* C12 */
+  Cf[5] = A00 * A11 - A01 * A01; /* C22 */
+  const double det = (A00 * Cf[0] + A01 * Cf[1]) + A02 * Cf[2];
+  *idet = 1.0 / det;
+}
+
+static void sym3_apply(const double Cf[6], double idet, const double v[3], double o[3]) {
+  o[0] = ((Cf[0] * v[0] + Cf[1] * v[1]) + Cf[2] * v[2]) * idet;
+  o[1] = ((Cf[1] * v[0] + Cf[3] * v[1]) + Cf[4] * v[2]) * idet;
+  o[2] = ((Cf[2] * v[0] + Cf[4] * v[1]) + Cf[5] * v[2]) * idet;
+}
+
+/* props: E, nu, sig0 (R0), H scalars or per point (pp/per as in dxm_oracle.c, entries 0..3); a even integer >= 2 */
+void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double* s_old, const double* p_old_a,
+                 const double* ep_old, const double* const* pp, const int* per, int a, int newton_cap, double rtol,
+                 double* sig_o, double* p_o, double* epsp_o, double* ct_o, uint8_t* flag_o, int32_t* iter_o,
+                 double* resid_o, uint8_t* fail_o) {
+  for (int64_t pt = 0; pt < n; ++pt) {
+    const double E = per[0] ? pp[0][pt] : pp[0][0], nu = per[1] ? pp[1][pt] : pp[1][0];
+    const double sig0 = per[2] ? pp[2][pt] : pp[2][0], H = per[3] ? pp[3][pt] : pp[3][0];
+    const double lam = E * nu / (1 + nu) / (1 - 2 * nu);
+    const double mu = E / 2 / (1 + nu);
+    const double twomu = 2.0 * mu, threemu = 3.0 * mu;
+    const double p_old = p_old_a[pt];
+    double de[6], st[6], s[6];
+    for (int i = 0; i < 6; ++i) de[i] = eps[pt * 6 + i] - e_old[pt * 6 + i];
+    const double tr = (de[0] + de[1]) + de[2];
+    const double ltr = lam * tr;
+    for (int i = 0; i < 3; ++i) st[i] = s_old[pt * 6 + i] + (ltr + twomu * de[i]);
+    for (int i = 3; i < 6; ++i) st[i] = s_old[pt * 6 + i] + twomu * de[i];
+    const double pm = ((st[0] + st[1]) + st[2]) / 3.0;
+    for (int i = 0; i < 3; ++i) s[i] = st[i] - pm;
+    for (int i = 3; i < 6; ++i) s[i] = st[i];
+    double ss = s[0] * s[0] + s[1] * s[1];
+    for (int i = 2; i < 6; ++i) ss = ss + s[i] * s[i];
+    const double seq = sqrt(1.5 * ss);
+    const double sy0 = sig0 + H * p_old;
+
+    int flag = 0, n_iter = 0, fail = 0;
+    double dp = 0.0, resid = 0.0;
+    double l[3], Q[3][3];
+    hres_t cur;
+    if (1.1548 * seq > sy0) { /* sigma_eq <= max |s_i - s_j| <= 2/sqrt(3) seq: otherwise surely elastic */
+      jacobi3(s, l, Q);
+      hosford_eval(l, a, &cur.phi, cur.n, cur.h, cur.u);
+      const double f = cur.phi - sy0;
+      flag = f > 0.0;
+      if (flag) {
+        /* start on the yield surface along the trial direction, dp from the J2-like estimate */
+        dp = f / (threemu + H);
+        const double sc = (sy0 + H * dp) / cur.phi;
+        double x[3] = {l[0] * sc, l[1] * sc, l[2] * sc};
+        hosford_residual(x, dp, l, twomu, sy0, H, a, &cur);
+        const double tol = rtol * seq;
+        for (int it = 0;; ++it) {
+          const double res = fmax(fmax(fabs(cur.rs[0]), fabs(cur.rs[1])), fmax(fabs(cur.rs[2]), fabs(cur.r4)));
+          if (res <= tol) { resid = res; break; }
+          if (it == newton_cap || !(res == res)) { resid = res; fail = 1; break; }
+          double Cf[6], idet, y[3], z[3];
+          hosford_system(&cur, twomu * dp, ((double)a - 1.0) / cur.phi, Cf, &idet);
+          sym3_apply(Cf, idet, cur.rs, y);
+          sym3_apply(Cf, idet, cur.n, z);
+          const double ny = (cur.n[0] * y[0] + cur.n[1] * y[1]) + cur.n[2] * y[2];
+          const double nz = (cur.n[0] * z[0] + cur.n[1] * z[1]) + cur.n[2] * z[2];
+          const double ddp = (cur.r4 - ny) / (twomu * nz + H);
+          const double tz = twomu * ddp;
+          const double dx[3] = {-(y[0] + tz * z[0]), -(y[1] + tz * z[1]), -(y[2] + tz * z[2])};
+          double t = 1.0;
+          hres_t nxt;
+          double xn[3], dpn;
+          for (int ls = 0;; ++ls) {
+            for (int k = 0; k < 3; ++k) xn[k] = x[k] + t * dx[k];
+            dpn = dp + t * ddp;
+            hosford_residual(xn, dpn, l, twomu, sy0, H, a, &nxt);
+            if (nxt.m2 < cur.m2 || ls == LS_MAX) break;
+            t = 0.5 * t;
+          }
+          for (int k = 0; k < 3; ++k) x[k] = xn[k];
+          dp = dpn;
+          cur = nxt;
+          ++n_iter;
+        }
+      }
+    }
+
+    /* flow direction in the global Mandel basis, state update */
+    double mN[3][6], nrm[6];
+    if (flag) {
+      for (int k = 0; k < 3; ++k) {
+        mN[k][0] = Q[0][k] * Q[0][k];
+        mN[k][1] = Q[1][k] * Q[1][k];
+        mN[k][2] = Q[2][k] * Q[2][k];
+        mN[k][3] = SQRT2 * (Q[0][k] * Q[1][k]);
+        mN[k][4] = SQRT2 * (Q[0][k] * Q[2][k]);
+        mN[k][5] = SQRT2 * (Q[1][k] * Q[2][k]);
+      }
+      for (int i = 0; i < 6; ++i) nrm[i] = (cur.n[0] * mN[0][i] + cur.n[1] * mN[1][i]) + cur.n[2] * mN[2][i];
+    } else {
+      for (int i = 0; i < 6; ++i) nrm[i] = 0.0;
+      dp = 0.0;
+    }
+    double epsp[6];
+    for (int i = 0; i < 6; ++i) {
+      const double depsp = dp * nrm[i];
+      sig_o[pt * 6 + i] = st[i] - twomu * depsp;
+      epsp[i] = ep_old[pt * 6 + i] + depsp;
+      epsp_o[pt * 6 + i] = epsp[i];
+    }
+    const double p_new = p_old + dp;
+    p_o[pt] = p_new;
+
+    /* consistent tangent */
+    double* ct = ct_o + pt * 36;
+    if (!flag) {
+      const double AB = lam + twomu;
+      for (int j = 0; j < 6; ++j)
+        for (int i = 0; i < 6; ++i) ct[j * 6 + i] = (i == j) ? ((i < 3) ? AB : twomu) : ((i < 3 && j < 3) ? lam : 0.0);
+    } else {
+      double Cf[6], idet, z[3];
+      const double c = twomu * dp, iphi = 1.0 / cur.phi;
+      hosford_system(&cur, c, ((double)a - 1.0) / cur.phi, Cf, &idet);
+      sym3_apply(Cf, idet, cur.n, z);
+      const double nz = (cur.n[0] * z[0] + cur.n[1] * z[1]) + cur.n[2] * z[2];
+      const double w = (twomu * twomu) / (twomu * nz + H); /* (2 mu z)(2 mu z)^T / (2 mu n.z + H) */
+      const double ti = twomu * idet;
+      /* normal block An (symmetric): 2 mu A^-1 + lam - w z z^T */
+      double An[3][3];
+      An[0][0] = (ti * Cf[0] + lam) - w * (z[0] * z[0]);
+      An[0][1] = (ti * Cf[1] + lam) - w * (z[0] * z[1]);
+      An[0][2] = (ti * Cf[2] + lam) - w * (z[0] * z[2]);
+      An[1][1] = (ti * Cf[3] + lam) - w * (z[1] * z[1]);
+      An[1][2] = (ti * Cf[4] + lam) - w * (z[1] * z[2]);
+      An[2][2] = (ti * Cf[5] + lam) - w * (z[2] * z[2]);
+      An[1][0] = An[0][1];
+      An[2][0] = An[0][2];
+      An[2][1] = An[1][2];
+      /* shear moduli of the pairs (0,1), (1,2), (2,0): theta = (h_k + DD/2) / phi */
+      const double th01 = (cur.h[0] + 0.5 * divdiff(-cur.u[2], cur.u[1], a)) * iphi;
+      const double th12 = (cur.h[1] + 0.5 * divdiff(-cur.u[0], cur.u[2], a)) * iphi;
+      const double th20 = (cur.h[2] + 0.5 * divdiff(-cur.u[1], cur.u[0], a)) * iphi;
+      const double G[3] = {twomu / (1.0 + c * th01), twomu / (1.0 + c * th12), twomu / (1.0 + c * th20)};
+      /* unit Mandel vectors of sym(e_i e_j), pairs in the same order */
+      static const int PI[3] = {0, 1, 2}, PJ[3] = {1, 2, 0};
+      double mS[3][6];
+      for (int p = 0; p < 3; ++p) {
+        const int i = PI[p], j = PJ[p];
+        mS[p][0] = SQRT2 * (Q[0][i] * Q[0][j]);
+        mS[p][1] = SQRT2 * (Q[1][i] * Q[1][j]);
+        mS[p][2] = SQRT2 * (Q[2][i] * Q[2][j]);
+        mS[p][3] = Q[0][i] * Q[1][j] + Q[1][i] * Q[0][j];
+        mS[p][4] = Q[0][i] * Q[2][j] + Q[2][i] * Q[0][j];
+        mS[p][5] = Q[1][i] * Q[2][j] + Q[2][i] * Q[1][j];
+      }
+      double wN[3][6]; /* wN_i = sum_j An_ij mN_j */
+      for (int i = 0; i < 3; ++i)
+        for (int cc = 0; cc < 6; ++cc) wN[i][cc] = (An[i][0] * mN[0][cc] + An[i][1] * mN[1][cc]) + An[i][2] * mN[2][cc];
+      for (int j = 0; j < 6; ++j)
+        for (int i = j; i < 6; ++i) {
+          const double vn = (mN[0][j] * wN[0][i] + mN[1][j] * wN[1][i]) + mN[2][j] * wN[2][i];
+          const double vs = (G[0] * (mS[0][j] * mS[0][i]) + G[1] * (mS[1][j] * mS[1][i])) + G[2] * (mS[2][j] * mS[2][i]);
+          const double v = vn + vs;
+          ct[j * 6 + i] = v;
+          ct[i * 6 + j] = v;
+        }
+    }
+    double chk = (seq + fabs(pm)) + p_new;
+    for (int i = 0; i < 6; ++i) chk = chk + fabs(epsp[i]);
+    if (!isfinite(chk)) fail = 1;
+    flag_o[pt] = (uint8_t)flag;
+    iter_o[pt] = n_iter;
+    resid_o[pt] = resid;
+    fail_o[pt] = (uint8_t)fail;
+  }
+}

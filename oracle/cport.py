@@ -16,8 +16,8 @@ _NAMES = ("E", "nu", "sig0", "H", "sigu", "b")
 def load(build=True):
     global _lib
     if _lib is None:
-        src = os.path.join(HERE, "c", "dxm_oracle.c")
-        if build and (not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src)):
+        srcs = [os.path.join(HERE, "c", f) for f in ("dxm_oracle.c", "dxm_oracle_hosford.c")]
+        if build and (not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(s) for s in srcs)):
             subprocess.run(["make", "-s", "-C", HERE], check=True)
         _lib = ctypes.CDLL(LIB)
     return _lib
@@ -111,3 +111,33 @@ def fefp(F, state, props, newton_cap=25, rtol=1e-12):
     del keep
     return {"F": F, "PK1": P, "p": p, "be_bar": be, "Ct": Ct, "flag": flag, "n_iter": n_iter, "resid": resid,
             "fail": fail}
+
+
+def hosford(eps, state, props, newton_cap=25, rtol=1e-12):
+    """Small-strain Hosford plasticity (``oracle/c/dxm_oracle_hosford.c``); props: E, nu, sig0, H (scalars or per
+    point) and the even integer exponent ``a``."""
+    lib = load()
+    eps = np.ascontiguousarray(eps, dtype=np.float64)
+    n = eps.shape[0]
+    e_old = np.ascontiguousarray(np.asarray(state["strain"], dtype=np.float64).reshape(n, 6))
+    s_old = np.ascontiguousarray(np.asarray(state["stress"], dtype=np.float64).reshape(n, 6))
+    p_old = np.ascontiguousarray(np.asarray(state["p"], dtype=np.float64).reshape(n))
+    ep_old = np.ascontiguousarray(np.asarray(state["epsp"], dtype=np.float64).reshape(n, 6))
+    a = int(props["a"])
+    if a < 2 or a % 2 or a > 64 or a != props["a"]:
+        raise ValueError("Hosford exponent: an even integer in [2, 64]")
+    keep, ptrs, pers = _props({k: v for k, v in props.items() if k != "a"}, n)
+    sig, p, epsp, Ct = np.empty((n, 6)), np.empty(n), np.empty((n, 6)), np.empty((n, 6, 6))
+    flag, fail = np.empty(n, np.uint8), np.empty(n, np.uint8)
+    n_iter, resid = np.empty(n, np.int32), np.empty(n)
+
+    def call(lo, hi):
+        lib.dxo_hosford(ctypes.c_int64(hi - lo), _c(eps, lo), _c(e_old, lo), _c(s_old, lo), _c(p_old, lo),
+                        _c(ep_old, lo), ptrs(lo), pers, ctypes.c_int(a), ctypes.c_int(newton_cap), ctypes.c_double(rtol),
+                        _c(sig, lo), _c(p, lo), _c(epsp, lo), _c(Ct, lo), _c(flag, lo), _c(n_iter, lo),
+                        _c(resid, lo), _c(fail, lo))
+
+    _run_blocks(n, call)
+    del keep
+    return {"strain": eps, "stress": sig, "p": p, "epsp": epsp, "Ct": Ct, "flag": flag, "n_iter": n_iter,
+            "resid": resid, "fail": fail}
