@@ -20,6 +20,8 @@ class PerformanceWarning(UserWarning):
 from .behaviors import (  # noqa: E402
     ElasticBehavior,
     FeFpJ2Plasticity,
+    GeneralIsotropicHardening,
+    Hosford,
     LinearElasticIsotropic,
     LinearHardening,
     TabulatedHardening,
@@ -39,4 +41,6 @@ __all__ = [
     "ElasticBehavior",
     "vonMisesIsotropicHardening",
     "FeFpJ2Plasticity",
+    "GeneralIsotropicHardening",
+    "Hosford",
 ]

@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 from typing import Any
 
 # behaviour ids of include/dxm.h
-DXM_ELASTIC, DXM_J2_LINEAR, DXM_J2_VOCE, DXM_FEFP_VOCE, DXM_J2_TABLE = 0, 1, 2, 3, 4
+DXM_ELASTIC, DXM_J2_LINEAR, DXM_J2_VOCE, DXM_FEFP_VOCE, DXM_J2_TABLE, DXM_HOSFORD_LINEAR = 0, 1, 2, 3, 4, 5
 
 
 @dataclass
@@ -102,6 +102,39 @@ class vonMisesIsotropicHardening(_Behavior):
 
     def properties(self):
         return {**super().properties(), **_hardening_props(self.yield_stress)}
+
+
+@dataclass
+class Hosford:
+    """Hosford equivalent stress ``(1/2 (|s1-s2|^a + |s2-s3|^a + |s3-s1|^a))^(1/a)`` with an even integer exponent
+    (``a = 2``: von Mises; ``criterion : "Hosford" {a: 10}`` in
+    ``demos/multimaterials/IsotropicPlasticHosfordFlowLinear.mfront:21``)."""
+
+    a: int = 10
+
+
+@dataclass
+class GeneralIsotropicHardening(_Behavior):
+    """Small-strain associated plasticity with a non-quadratic isotropic criterion and linear isotropic hardening
+    ``R0 + H p`` -- the MFront behaviour of the matrix phase of ``demos/multimaterials/multimaterials.py:245-254``
+    (``young_modulus, poisson_ratio, R0, hardening_slope`` = ``E, nu, sig0, H`` here); the class name follows the
+    jaxmat behaviour the old demo mentions (``_plane_stress_elastoplasticity.py:17,45``)."""
+
+    yield_stress: Any = None
+    equivalent_stress: Any = field(default_factory=Hosford)
+
+    def __post_init__(self):
+        if not isinstance(self.yield_stress, LinearHardening):
+            raise TypeError("GeneralIsotropicHardening: yield_stress must be a LinearHardening descriptor")
+        if not isinstance(self.equivalent_stress, Hosford):
+            raise TypeError("GeneralIsotropicHardening: equivalent_stress must be a Hosford descriptor")
+        a = self.equivalent_stress.a
+        if int(a) != a or a < 2 or a > 64 or int(a) % 2:
+            raise ValueError("Hosford exponent: an even integer in [2, 64]")
+        self.kind = DXM_HOSFORD_LINEAR
+
+    def properties(self):
+        return {**super().properties(), **_hardening_props(self.yield_stress), "a": int(self.equivalent_stress.a)}
 
 
 @dataclass

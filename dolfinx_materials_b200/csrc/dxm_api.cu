@@ -4,6 +4,7 @@
 #include "dxm_internal.cuh"
 #include "dxm_fefp.cuh"
 #include "dxm_host_mirror.hpp"
+#include "dxm_hosford.cuh"
 #include "dxm_layout.cuh"
 #include "dxm_small_strain.cuh"
 
@@ -251,6 +252,21 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
   a.d_iter = h->d_iter;
   a.d_resid = h->d_resid;
   a.d_fail = h->d_fail;
+  if (h->behaviour == DXM_HOSFORD_LINEAR) {
+    a.hos_a = h->hos_a;
+    const int block = 128;
+    const int64_t ntile = (count + block - 1) / block;
+    const int grid = grid_for(nullptr, block, 0, h->num_sms, ntile);
+    if (h->perpoint) {
+      if (h->diag) dxm_hosford_kernel<true, true><<<grid, block, 0, h->stream>>>(a);
+      else dxm_hosford_kernel<true, false><<<grid, block, 0, h->stream>>>(a);
+    } else {
+      if (h->diag) dxm_hosford_kernel<false, true><<<grid, block, 0, h->stream>>>(a);
+      else dxm_hosford_kernel<false, false><<<grid, block, 0, h->stream>>>(a);
+    }
+    LAUNCH_CHECK();
+    return 0;
+  }
   if (h->behaviour == DXM_J2_TABLE) {
     // 2 CTAs/SM: the segment walk keeps a few more values live than the closed forms
     if (h->perpoint)
@@ -417,7 +433,7 @@ int dxm_create(int behaviour, int device, int64_t n, dxm_handle** out) {
   if (!out) return fail("dxm_create: out is NULL");
   *out = nullptr;
   if (n <= 0) return fail("dxm_create: n must be positive");
-  if (behaviour < DXM_ELASTIC || behaviour > DXM_J2_TABLE)
+  if (behaviour < DXM_ELASTIC || behaviour > DXM_HOSFORD_LINEAR)
     return fail("dxm_create: unknown behaviour " + std::to_string(behaviour));
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
@@ -537,6 +553,22 @@ int dxm_field_dim(const dxm_handle* h, const char* field) {
 
 int dxm_set_property(dxm_handle* h, const char* name, const double* v, int64_t count, int mem) {
   if (!h || !name || !v) return fail("dxm_set_property: NULL argument");
+  if (std::strcmp(name, "a") == 0) {
+    if (h->behaviour != DXM_HOSFORD_LINEAR) return fail("dxm_set_property: 'a' is a property of DXM_HOSFORD_LINEAR only");
+    if (count != 1) return fail("dxm_set_property: the Hosford exponent 'a' is uniform (count must be 1)");
+    double val;
+    if (mem == DXM_MEM_HOST) {
+      val = v[0];
+    } else {
+      if (set_device(h)) return -1;
+      CK(cudaMemcpy(&val, v, sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    const int ai = (int)val;
+    if ((double)ai != val || ai < 2 || ai > 64 || (ai & 1))
+      return fail("dxm_set_property: the Hosford exponent 'a' must be an even integer in [2, 64]");
+    h->hos_a = ai;
+    return 0;
+  }
   int idx = -1;
   for (int i = 0; i < kNProp; ++i)
     if (std::strcmp(name, kPropNames[i]) == 0) idx = i;

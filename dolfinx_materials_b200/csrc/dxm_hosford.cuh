@@ -1,0 +1,406 @@
+// Small-strain plasticity with the Hosford criterion and linear isotropic hardening -- the behaviour of the matrix
+// phase of the reference's multi-material demo (demos/multimaterials/IsotropicPlasticHosfordFlowLinear.mfront:1-27,
+// used at demos/multimaterials/multimaterials.py:245-254 through MFront/MGIS), behind the same handle / state layout
+// (strain, stress, p, epsp) as the J2 behaviours.
+//
+//   sigma_eq = (1/2 (|s1-s2|^a + |s2-s3|^a + |s3-s1|^a))^(1/a),  a even integer (2 = von Mises, 10 in the demo)
+//   backward Euler, associated flow:  sigma = sigma_tr - 2 mu dp n(sigma),  sigma_eq(sigma) = R0 + H (p_old + dp)
+//
+// One Gauss point per thread.  Isotropy keeps the principal axes of the trial stress, so per point:
+//   * cheap rejection: sigma_eq <= max|s_i - s_j| <= 2/sqrt(3) seq_Mises  -> clearly elastic points skip the rest;
+//   * cyclic Jacobi eigen-decomposition of the trial deviator in registers (+ - * / sqrt only);
+//   * 4-unknown Newton (3 principal deviatoric stresses + dp) from the radially scaled trial state, with a
+//     simple-decrease backtracking line search (plain Newton overshoots at the rounded corners of the surface);
+//     3x3 solves by the symmetric adjugate;
+//   * consistent tangent from its spectral form: normal block 2 mu A^-1 + lam 1 1^T - w z z^T and three shear moduli
+//     2 mu / (1 + 2 mu dp theta_ij), theta_ij = (n_i - n_j)/(s_i - s_j) as an exact divided difference (even a), rotated
+//     back with the eigenvectors and stored packed (21 unique entries) like the J2 tangent.
+// All powers are product chains; operation order == oracle/c/dxm_oracle_hosford.c (bit-identical with -fmad=false).
+// The point routine is __host__ __device__ so that a CPU test can run the very same code against the oracle
+// (tests/hosford_host_check.cu) -- the product only ever calls it from the kernel below.
+#pragma once
+#include "dxm_canon.cuh"
+#include "dxm_small_strain.cuh"
+
+namespace dxm {
+
+#define DXM_HD __host__ __device__ __forceinline__
+
+constexpr double kHosRSqrt2 = 0.7071067811865476;
+constexpr double kHosSqrt2 = 1.4142135623730951;
+constexpr int kHosfordLsMax = 10;
+constexpr int kJacobiSweeps = 8;
+
+// (x*x)^k, k >= 1
+DXM_HD double hos_ipow2(double x, int k) {
+  const double x2 = x * x;
+  double y = x2;
+  for (int i = 1; i < k; ++i) y = y * x2;
+  return y;
+}
+
+// q^(1/a), q in (0.5, 1]: Newton from above on y^a = q
+DXM_HD double hos_aroot(double q, int a) {
+  const double ad = (double)a, am1 = ad - 1.0;
+  double y = 1.0;
+  for (int it = 0; it < 30; ++it) {
+    const double ym = (a > 2) ? hos_ipow2(y, (a - 2) / 2) * y : y;
+    const double yn = (am1 * y + q / ym) / ad;
+    if (!(yn < y)) break;
+    y = yn;
+  }
+  return y;
+}
+
+struct HosEval {
+  double phi, n[3], h[3], u[3];
+};
+
+DXM_HD void hos_eval(const double (&l)[3], int a, HosEval& e) {
+  const double d0 = l[0] - l[1], d1 = l[1] - l[2], d2 = l[2] - l[0];
+  const double m = fmax(fmax(fabs(d0), fabs(d1)), fabs(d2));
+  const double r0 = d0 / m, r1 = d1 / m, r2 = d2 / m;
+  const double q = 0.5 * ((hos_ipow2(r0, a / 2) + hos_ipow2(r1, a / 2)) + hos_ipow2(r2, a / 2));
+  const double y = hos_aroot(q, a);
+  e.phi = m * y;
+  e.u[0] = r0 / y;
+  e.u[1] = r1 / y;
+  e.u[2] = r2 / y;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) e.h[k] = (a > 2) ? hos_ipow2(e.u[k], (a - 2) / 2) : 1.0;
+  const double g0 = e.h[0] * e.u[0], g1 = e.h[1] * e.u[1], g2 = e.h[2] * e.u[2];
+  e.n[0] = 0.5 * (g0 - g2);
+  e.n[1] = 0.5 * (g1 - g0);
+  e.n[2] = 0.5 * (g2 - g1);
+}
+
+// sum_{k=0}^{a-2} x^k y^(a-2-k)
+DXM_HD double hos_divdiff(double x, double y, int a) {
+  double t = 1.0, xp = 1.0;
+  for (int j = 1; j <= a - 2; ++j) {
+    xp = xp * x;
+    t = y * t + xp;
+  }
+  return t;
+}
+
+// Jacobi rotation annihilating a_pq (P < Q compile-time, so the eigenvector matrix stays in registers)
+template <int P, int Q>
+DXM_HD void hos_jrot(double& app, double& aqq, double& apq, double& arp, double& arq, double (&V)[3][3]) {
+  if (apq == 0.0) return;
+  const double g = 100.0 * fabs(apq);
+  if ((fabs(app) + g == fabs(app)) && (fabs(aqq) + g == fabs(aqq))) {
+    apq = 0.0;
+    return;
+  }
+  const double theta = ((aqq - app) * 0.5) / apq;
+  double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+  if (theta < 0.0) t = -t;
+  const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+  app = app - t * apq;
+  aqq = aqq + t * apq;
+  apq = 0.0;
+  const double xp = arp, xq = arq;
+  arp = c * xp - sn * xq;
+  arq = sn * xp + c * xq;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double vp = V[k][P], vq = V[k][Q];
+    V[k][P] = c * vp - sn * vq;
+    V[k][Q] = sn * vp + c * vq;
+  }
+}
+
+DXM_HD void hos_jacobi3(const double (&s)[6], double (&l)[3], double (&V)[3][3]) {
+  double a00 = s[0], a11 = s[1], a22 = s[2], a01 = s[3] * kHosRSqrt2, a02 = s[4] * kHosRSqrt2, a12 = s[5] * kHosRSqrt2;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < kJacobiSweeps; ++sweep) {
+    if ((fabs(a01) + fabs(a02)) + fabs(a12) == 0.0) break;
+    hos_jrot<0, 1>(a00, a11, a01, a02, a12, V);
+    hos_jrot<0, 2>(a00, a22, a02, a01, a12, V);
+    hos_jrot<1, 2>(a11, a22, a12, a01, a02, V);
+  }
+  l[0] = a00;
+  l[1] = a11;
+  l[2] = a22;
+}
+
+struct HosRes {
+  HosEval e;
+  double rs[3], r4, m2;
+};
+
+DXM_HD void hos_residual(const double (&x)[3], double dp, const double (&l)[3], double twomu, double sy0, double H,
+                         int a, HosRes& o) {
+  hos_eval(x, a, o.e);
+  const double c = twomu * dp;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) o.rs[k] = (x[k] - l[k]) + c * o.e.n[k];
+  o.r4 = o.e.phi - (sy0 + H * dp);
+  o.m2 = ((o.rs[0] * o.rs[0] + o.rs[1] * o.rs[1]) + o.rs[2] * o.rs[2]) + o.r4 * o.r4;
+}
+
+// A = I + c k1 (M/2 - n n^T): adjugate (6 unique cofactors) and 1/det
+DXM_HD void hos_system(const HosEval& r, double c, double k1, double (&Cf)[6], double& idet) {
+  const double ck = c * k1;
+  const double A00 = 1.0 + ck * (0.5 * (r.h[0] + r.h[2]) - r.n[0] * r.n[0]);
+  const double A11 = 1.0 + ck * (0.5 * (r.h[0] + r.h[1]) - r.n[1] * r.n[1]);
+  const double A22 = 1.0 + ck * (0.5 * (r.h[1] + r.h[2]) - r.n[2] * r.n[2]);
+  const double A01 = ck * (-0.5 * r.h[0] - r.n[0] * r.n[1]);
+  const double A02 = ck * (-0.5 * r.h[2] - r.n[0] * r.n[2]);
+  const double A12 = ck * (-0.5 * r.h[1] - r.n[1] * r.n[2]);
+  Cf[0] = A11 * A22 - A12 * A12;
+  Cf[1] = A02 * A12 - A01 * A22;
+  Cf[2] = A01 * A12 - A02 * A11;
+  Cf[3] = A00 * A22 - A02 * A02;
+  Cf[4] = A01 * A02 - A00 * A12;
+  Cf[5] = A00 * A11 - A01 * A01;
+  const double det = (A00 * Cf[0] + A01 * Cf[1]) + A02 * Cf[2];
+  idet = 1.0 / det;
+}
+
+DXM_HD void hos_apply(const double (&Cf)[6], double idet, const double (&v)[3], double (&o)[3]) {
+  o[0] = ((Cf[0] * v[0] + Cf[1] * v[1]) + Cf[2] * v[2]) * idet;
+  o[1] = ((Cf[1] * v[0] + Cf[3] * v[1]) + Cf[4] * v[2]) * idet;
+  o[2] = ((Cf[2] * v[0] + Cf[4] * v[1]) + Cf[5] * v[2]) * idet;
+}
+
+// unit Mandel vector of sym(e_I e_J) (I != J) or of e_I e_I, from the eigenvector matrix
+template <int I, int J>
+DXM_HD void hos_mandel_pair(const double (&V)[3][3], double (&m)[6]) {
+  if (I == J) {
+    m[0] = V[0][I] * V[0][I];
+    m[1] = V[1][I] * V[1][I];
+    m[2] = V[2][I] * V[2][I];
+    m[3] = kHosSqrt2 * (V[0][I] * V[1][I]);
+    m[4] = kHosSqrt2 * (V[0][I] * V[2][I]);
+    m[5] = kHosSqrt2 * (V[1][I] * V[2][I]);
+  } else {
+    m[0] = kHosSqrt2 * (V[0][I] * V[0][J]);
+    m[1] = kHosSqrt2 * (V[1][I] * V[1][J]);
+    m[2] = kHosSqrt2 * (V[2][I] * V[2][J]);
+    m[3] = V[0][I] * V[1][J] + V[1][I] * V[0][J];
+    m[4] = V[0][I] * V[2][J] + V[2][I] * V[0][J];
+    m[5] = V[1][I] * V[2][J] + V[2][I] * V[1][J];
+  }
+}
+
+// One Gauss point.  ct21: the 21 unique tangent entries (j <= i, row-major upper triangle = sym6_packed order).
+DXM_HD void hosford_point(const double lam, const double mu, const double sig0, const double H, const int a,
+                          const double (&eps)[6], const double (&e_old)[6], const double (&s_old)[6],
+                          const double p_old, const double (&ep_old)[6], double (&sig)[6], double& p_new,
+                          double (&epsp)[6], double (&ct21)[21], bool& flag, int& n_iter, double& resid,
+                          bool& fail) {
+  const double twomu = 2.0 * mu;
+  const double threemu = 3.0 * mu;
+  double de[6], st[6], s[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) de[i] = eps[i] - e_old[i];
+  const double tr = (de[0] + de[1]) + de[2];
+  const double ltr = lam * tr;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) st[i] = s_old[i] + (ltr + twomu * de[i]);
+#pragma unroll
+  for (int i = 3; i < 6; ++i) st[i] = s_old[i] + twomu * de[i];
+  const double pm = ((st[0] + st[1]) + st[2]) / 3.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) s[i] = st[i] - pm;
+#pragma unroll
+  for (int i = 3; i < 6; ++i) s[i] = st[i];
+  double ss = s[0] * s[0] + s[1] * s[1];
+#pragma unroll
+  for (int i = 2; i < 6; ++i) ss = ss + s[i] * s[i];
+  const double seq = sqrt(1.5 * ss);
+  const double sy0 = sig0 + H * p_old;
+
+  flag = false;
+  n_iter = 0;
+  fail = false;
+  resid = 0.0;
+  double dp = 0.0;
+  double l[3], V[3][3];
+  HosRes cur;
+  if (1.1548 * seq > sy0) {  // sigma_eq <= max|s_i - s_j| <= 2/sqrt(3) seq_Mises: otherwise surely elastic
+    hos_jacobi3(s, l, V);
+    hos_eval(l, a, cur.e);
+    const double f = cur.e.phi - sy0;
+    flag = f > 0.0;
+    if (flag) {
+      dp = f / (threemu + H);
+      const double sc = (sy0 + H * dp) / cur.e.phi;
+      double x[3] = {l[0] * sc, l[1] * sc, l[2] * sc};
+      hos_residual(x, dp, l, twomu, sy0, H, a, cur);
+      const double tol = kNewtonRtol * seq;
+      for (int it = 0;; ++it) {
+        const double res = fmax(fmax(fabs(cur.rs[0]), fabs(cur.rs[1])), fmax(fabs(cur.rs[2]), fabs(cur.r4)));
+        if (res <= tol) {
+          resid = res;
+          break;
+        }
+        if (it == kNewtonCap || !(res == res)) {
+          resid = res;
+          fail = true;
+          break;
+        }
+        double Cf[6], idet, y[3], z[3];
+        hos_system(cur.e, twomu * dp, ((double)a - 1.0) / cur.e.phi, Cf, idet);
+        hos_apply(Cf, idet, cur.rs, y);
+        hos_apply(Cf, idet, cur.e.n, z);
+        const double ny = (cur.e.n[0] * y[0] + cur.e.n[1] * y[1]) + cur.e.n[2] * y[2];
+        const double nz = (cur.e.n[0] * z[0] + cur.e.n[1] * z[1]) + cur.e.n[2] * z[2];
+        const double ddp = (cur.r4 - ny) / (twomu * nz + H);
+        const double tz = twomu * ddp;
+        const double dx[3] = {-(y[0] + tz * z[0]), -(y[1] + tz * z[1]), -(y[2] + tz * z[2])};
+        double t = 1.0;
+        HosRes nxt;
+        double xn[3], dpn;
+        for (int ls = 0;; ++ls) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) xn[k] = x[k] + t * dx[k];
+          dpn = dp + t * ddp;
+          hos_residual(xn, dpn, l, twomu, sy0, H, a, nxt);
+          if (nxt.m2 < cur.m2 || ls == kHosfordLsMax) break;
+          t = 0.5 * t;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) x[k] = xn[k];
+        dp = dpn;
+        cur = nxt;
+        ++n_iter;
+      }
+    }
+  }
+
+  double mN0[6], mN1[6], mN2[6], nrm[6];
+  if (flag) {
+    hos_mandel_pair<0, 0>(V, mN0);
+    hos_mandel_pair<1, 1>(V, mN1);
+    hos_mandel_pair<2, 2>(V, mN2);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) nrm[i] = (cur.e.n[0] * mN0[i] + cur.e.n[1] * mN1[i]) + cur.e.n[2] * mN2[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) nrm[i] = 0.0;
+    dp = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const double depsp = dp * nrm[i];
+    sig[i] = st[i] - twomu * depsp;
+    epsp[i] = ep_old[i] + depsp;
+  }
+  p_new = p_old + dp;
+
+  if (!flag) {
+    const double AB = lam + twomu;
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+      for (int i = j; i < 6; ++i)
+        ct21[sym6_packed(j * 6 + i)] = (i == j) ? ((i < 3) ? AB : twomu) : ((i < 3 && j < 3) ? lam : 0.0);
+  } else {
+    double Cf[6], idet, z[3];
+    const double c = twomu * dp, iphi = 1.0 / cur.e.phi;
+    hos_system(cur.e, c, ((double)a - 1.0) / cur.e.phi, Cf, idet);
+    hos_apply(Cf, idet, cur.e.n, z);
+    const double nz = (cur.e.n[0] * z[0] + cur.e.n[1] * z[1]) + cur.e.n[2] * z[2];
+    const double w = (twomu * twomu) / (twomu * nz + H);
+    const double ti = twomu * idet;
+    const double An00 = (ti * Cf[0] + lam) - w * (z[0] * z[0]);
+    const double An01 = (ti * Cf[1] + lam) - w * (z[0] * z[1]);
+    const double An02 = (ti * Cf[2] + lam) - w * (z[0] * z[2]);
+    const double An11 = (ti * Cf[3] + lam) - w * (z[1] * z[1]);
+    const double An12 = (ti * Cf[4] + lam) - w * (z[1] * z[2]);
+    const double An22 = (ti * Cf[5] + lam) - w * (z[2] * z[2]);
+    const double th01 = (cur.e.h[0] + 0.5 * hos_divdiff(-cur.e.u[2], cur.e.u[1], a)) * iphi;
+    const double th12 = (cur.e.h[1] + 0.5 * hos_divdiff(-cur.e.u[0], cur.e.u[2], a)) * iphi;
+    const double th20 = (cur.e.h[2] + 0.5 * hos_divdiff(-cur.e.u[1], cur.e.u[0], a)) * iphi;
+    const double G0 = twomu / (1.0 + c * th01), G1 = twomu / (1.0 + c * th12), G2 = twomu / (1.0 + c * th20);
+    double mS0[6], mS1[6], mS2[6];
+    hos_mandel_pair<0, 1>(V, mS0);
+    hos_mandel_pair<1, 2>(V, mS1);
+    hos_mandel_pair<2, 0>(V, mS2);
+    double wN0[6], wN1[6], wN2[6];
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) {
+      wN0[cc] = (An00 * mN0[cc] + An01 * mN1[cc]) + An02 * mN2[cc];
+      wN1[cc] = (An01 * mN0[cc] + An11 * mN1[cc]) + An12 * mN2[cc];
+      wN2[cc] = (An02 * mN0[cc] + An12 * mN1[cc]) + An22 * mN2[cc];
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+      for (int i = j; i < 6; ++i) {
+        const double vn = (mN0[j] * wN0[i] + mN1[j] * wN1[i]) + mN2[j] * wN2[i];
+        const double vs = (G0 * (mS0[j] * mS0[i]) + G1 * (mS1[j] * mS1[i])) + G2 * (mS2[j] * mS2[i]);
+        ct21[sym6_packed(j * 6 + i)] = vn + vs;
+      }
+  }
+  double chk = (seq + fabs(pm)) + p_new;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) chk = chk + fabs(epsp[i]);
+  if (!isfinite(chk)) fail = true;
+}
+
+#ifdef __CUDACC__
+// SmallStrainArgs is shared with the J2 kernels (same SoA state layout); a.dsu / a.b are unused, a.hos_a = exponent.
+template <bool PERPOINT, bool DIAG>
+__global__ void __launch_bounds__(128, 3) dxm_hosford_kernel(const SmallStrainArgs a) {
+  const int64_t ld = a.ld;
+  const int64_t ntile = (a.count + blockDim.x - 1) / blockDim.x;
+  PointStats acc;
+  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int64_t loc = tile * blockDim.x + threadIdx.x;
+    if (loc >= a.count) continue;
+    const int64_t i0 = a.start + loc;
+    double eps[6], e_old[6], s_old[6], ep_old[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) eps[c] = __ldcs(a.eps + c * ld + i0);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) e_old[c] = __ldcs(a.eps_old + c * ld + i0);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s_old[c] = __ldcs(a.sig_old + c * ld + i0);
+    const double p_old = __ldcs(a.p_old + i0);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ep_old[c] = __ldcs(a.epsp_old + c * ld + i0);
+    double lam = a.lam, mu = a.mu, sig0 = a.sig0, H = a.H;
+    if (PERPOINT) {
+      const double E = __ldcs(a.pE + i0), nu = __ldcs(a.pnu + i0);
+      lam = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu);
+      mu = E / 2.0 / (1.0 + nu);
+      sig0 = __ldcs(a.psig0 + i0);
+      H = __ldcs(a.pH + i0);
+    }
+    double sig[6], epsp[6], ct21[21], p_new, resid;
+    bool flag, fail;
+    int n_iter;
+    hosford_point(lam, mu, sig0, H, a.hos_a, eps, e_old, s_old, p_old, ep_old, sig, p_new, epsp, ct21, flag, n_iter,
+                  resid, fail);
+    acc.n_plastic += flag ? 1u : 0u;
+    acc.n_fail += fail ? 1u : 0u;
+    acc.max_iter = n_iter > (int)acc.max_iter ? (unsigned)n_iter : acc.max_iter;
+    acc.max_resid = resid > acc.max_resid ? resid : acc.max_resid;
+    if (resid != resid) acc.max_resid = resid;
+    if (DIAG) {
+      a.d_flag[i0] = flag ? 1 : 0;
+      a.d_iter[i0] = n_iter;
+      a.d_resid[i0] = resid;
+      a.d_fail[i0] = fail ? 1 : 0;
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) __stcs(a.sig + c * ld + i0, sig[c]);
+    __stcs(a.p + i0, p_new);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) __stcs(a.epsp + c * ld + i0, epsp[c]);
+#pragma unroll
+    for (int r = 0; r < 21; ++r) __stcs(a.ct + (int64_t)r * ld + i0, ct21[r]);
+  }
+  block_reduce_stats(acc, a.stats);
+}
+#endif  // __CUDACC__
+
+#undef DXM_HD
+}  // namespace dxm

@@ -44,6 +44,7 @@ struct SmallStrainArgs {
   // HARD_TABLE: piecewise-linear sigma_Y through (tp[k], ts[k]) with segment slopes tH[k] (last repeated), [3][ntab]
   const double* table;
   int ntab;
+  int hos_a;  // DXM_HOSFORD_LINEAR: exponent of the Hosford criterion (even integer)
   StatSlot* stats;
   int vote;  // 1: warp-vote (__any_sync) Newton loop exit, 0: per-lane exit (A/B knob DXM_VOTE)
   // optional diagnostics (DIAG == true)

@@ -208,9 +208,9 @@ class CUDAMaterial:
         passes them (``quadrature_map.py:160-172``)."""
         if key not in self.material_properties:
             raise KeyError(f"'{key}' is not a property of {self.name}: {list(self.material_properties)}")
-        self.material_properties[key] = value
         if self._h is not None:
-            self._push_property(key, value)
+            self._push_property(key, value)  # raises on a rejected value: the stored property stays as it was
+        self.material_properties[key] = value
 
     def _push_property(self, key, value):
         lib = _lib.load()

@@ -43,7 +43,10 @@ enum {
   DXM_J2_LINEAR = 1, /* J2 + linear isotropic hardening, closed form: E, nu, sig0, H                */
   DXM_J2_VOCE = 2,   /* J2 + sig0 + H p + (sigu-sig0)(1-exp(-b p)), scalar Newton: E,nu,sig0,sigu,b,H */
   DXM_FEFP_VOCE = 3, /* finite-strain FeFp J2 plasticity, same hardening law                        */
-  DXM_J2_TABLE = 4   /* J2 + piecewise-linear isotropic hardening table (dxm_set_hardening_table): E, nu  */
+  DXM_J2_TABLE = 4,  /* J2 + piecewise-linear isotropic hardening table (dxm_set_hardening_table): E, nu  */
+  DXM_HOSFORD_LINEAR = 5 /* Hosford criterion (even integer exponent a) + linear isotropic hardening: E, nu, sig0 (R0),
+                          * H, a -- demos/multimaterials/IsotropicPlasticHosfordFlowLinear.mfront (a = 10), the
+                          * matrix phase of demos/multimaterials/multimaterials.py:245-254                         */
 };
 
 /* where a caller-supplied array lives */
@@ -71,7 +74,8 @@ int64_t dxm_npoints(const dxm_handle* h);
 
 /* material properties -- replaces Material.update_material_property(name, values)
  * (generic.py:119-120, called from quadrature_map.py:160-172 with a 0-d or per-point array).
- * count is 1 (uniform) or n (per Gauss point). names: "E","nu","sig0","H","sigu","b". */
+ * count is 1 (uniform) or n (per Gauss point). names: "E","nu","sig0","H","sigu","b"; DXM_HOSFORD_LINEAR also takes
+ * "a" (uniform only: an even integer in [2, 64], default 10). */
 int dxm_set_property(dxm_handle* h, const char* name, const double* v, int64_t count, int mem);
 
 /* Piecewise-linear isotropic hardening sigma_Y(p) through the points (p[k], sig[k]), k < count (2 <= count <= 64,

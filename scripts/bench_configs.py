@@ -67,5 +67,34 @@ for _ in range(6):
     a = ma.integrate_resident(); b = mb.integrate_resident(); tot.append(a.kernel_ms + b.kernel_ms)
 ms = sorted(tot[2:])[2]
 out.append(dict(cfg="cfg4 two handles back-to-back (matrix J2-linear + inclusions Voce)", n=n, ms=ms, gps=n / ms * 1e3, gbs=592 * n / ms / 1e6))
+del ma, mb
+
+# cfg4 with the demo's own matrix law: Hosford (a = 10) + linear hardening in the matrix handle (70 % of the points,
+# IsotropicPlasticHosfordFlowLinear.mfront), J2 + Voce in the inclusions handle -- two handles back to back
+mh = jm.CUDAMaterial(jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.LinearHardening(sig0=200.0, H=10.0),
+                                                  equivalent_stress=jm.Hosford(a=10)))
+mb = jm.CUDAMaterial(jm.vonMisesIsotropicHardening(elasticity=jm.LinearElasticIsotropic(E=90e3, nu=0.25),
+                                                   yield_stress=jm.VoceHardening(sig0=200.0, sigu=300.0, b=10.0)))
+mh.set_data_manager(na); mb.set_data_manager(nb)
+for mm, st in ((mh, 0), (mb, na)):
+    for k in range(1, 4):
+        mm.synth_gradients(0, 1.25e-2, k, 4, start=st); mm.integrate_resident(); mm.data_manager.update()
+    mm.synth_gradients(0, 1.25e-2, 4, 4, start=st)
+tot, th = [], []
+for _ in range(6):
+    a = mh.integrate_resident(); b = mb.integrate_resident(); tot.append(a.kernel_ms + b.kernel_ms); th.append(a.kernel_ms)
+ms = sorted(tot[2:])[2]; msh = sorted(th[2:])[2]
+out.append(dict(cfg="cfg4 faithful: matrix Hosford(a=10)+linear handle, inclusions J2+Voce handle, back to back", n=n, ms=ms,
+                gps=n / ms * 1e3, hosford_n=na, hosford_ms=msh, hosford_gps=na / msh * 1e3, hosford_gbs_moved=472 * na / msh / 1e6,
+                hosford_plastic=a.n_plastic / na, hosford_max_iter=a.max_iter, hosford_fail=a.n_fail))
+del mh, mb
+# Hosford kernel alone over the plastic fraction (amplitude sweep), n = 1e7
+mh = jm.CUDAMaterial(jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.LinearHardening(sig0=200.0, H=10.0)))
+mh.set_data_manager(n)
+for amp in (2e-3, 4e-3, 8e-3, 1.25e-2, 5e-2):
+    mh.data_manager.revert(); mh.synth_gradients(0, amp, 1, 1)
+    ms, s = timeit(mh)
+    out.append(dict(cfg=f"Hosford a=10 alone, virgin state, amp {amp}", n=n, ms=ms, gps=n / ms * 1e3, gbs_moved=472 * n / ms / 1e6,
+                    plastic=s.n_plastic / n, max_iter=s.max_iter, fail=s.n_fail))
 print(json.dumps(out, indent=1))
 os.makedirs("gpurun_out", exist_ok=True); json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)

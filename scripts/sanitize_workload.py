@@ -1,5 +1,5 @@
 """Small workload that touches every kernel of the library, for compute-sanitizer (memcheck / racecheck / initcheck):
-host-pipeline J2 (packed tangent, compaction on and off), FeFp (compacted), per-point properties, gradient evaluation,
+host-pipeline J2 (packed tangent, compaction on and off; DXM_HOST_MIRROR=0/1 from the environment), Hosford, FeFp (compacted), per-point properties, gradient evaluation,
 element forms, assembly with constraints + lifting, Krylov solve."""
 import os, sys
 import numpy as np
@@ -14,6 +14,7 @@ el = jm.LinearElasticIsotropic(E=70e3, nu=0.3)
 n = 3001
 for beh in (jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=jm.VoceHardening(sig0=350.0, sigu=500.0, b=1e3)),
             jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=jm.LinearHardening(sig0=250.0, H=5e3)),
+            jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.LinearHardening(sig0=200.0, H=10.0)),
             jm.ElasticBehavior(elasticity=el)):
     m = jm.CUDAMaterial(beh); m.set_data_manager(n)
     for k in range(1, 4):

@@ -1,0 +1,34 @@
+// CPU-side check of the CUDA kernel's per-point routine (tests/test_hosford_host.py): dxm::hosford_point is
+// __host__ __device__, so the very code the kernel runs per Gauss point is executed here on the host, point by point,
+// and compared bit for bit with the oracle -- without a GPU.  Test scaffolding only: nothing in the product calls this.
+#include "../dolfinx_materials_b200/csrc/dxm_hosford.cuh"
+
+extern "C" void hosford_host(int64_t n, const double* eps, const double* e_old, const double* s_old, const double* p_old,
+                             const double* ep_old, double E, double nu, double sig0, double H, int a, double* sig,
+                             double* p, double* epsp, double* ct, uint8_t* flag, int32_t* n_iter, double* resid,
+                             uint8_t* fail) {
+  const double lam = E * nu / (1 + nu) / (1 - 2 * nu);
+  const double mu = E / 2 / (1 + nu);
+  for (int64_t i = 0; i < n; ++i) {
+    double e1[6], e0[6], s0[6], ep0[6], so[6], epo[6], ct21[21], pn, rs;
+    bool fl, fa;
+    int it;
+    for (int c = 0; c < 6; ++c) {
+      e1[c] = eps[i * 6 + c];
+      e0[c] = e_old[i * 6 + c];
+      s0[c] = s_old[i * 6 + c];
+      ep0[c] = ep_old[i * 6 + c];
+    }
+    dxm::hosford_point(lam, mu, sig0, H, a, e1, e0, s0, p_old[i], ep0, so, pn, epo, ct21, fl, it, rs, fa);
+    for (int c = 0; c < 6; ++c) {
+      sig[i * 6 + c] = so[c];
+      epsp[i * 6 + c] = epo[c];
+    }
+    p[i] = pn;
+    for (int c = 0; c < 36; ++c) ct[i * 36 + c] = ct21[dxm::sym6_packed(c)];
+    flag[i] = fl;
+    n_iter[i] = it;
+    resid[i] = rs;
+    fail[i] = fa;
+  }
+}

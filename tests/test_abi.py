@@ -75,6 +75,13 @@ def test_protocol_surface_without_gpu(jm):
     assert f.gradients == {"F": 9} and f.fluxes == {"PK1": 9}
     assert list(f.internal_state_variables.items()) == [("p", 1), ("be_bar", 6)]
     assert f.tangent_blocks == {("PK1", "F"): (9, 9)}
+    g = jm.CUDAMaterial(jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.LinearHardening(sig0=200.0, H=10.0)))
+    assert g.gradients == {"strain": 6} and g.fluxes == {"stress": 6} and g.tangent_blocks == {("stress", "strain"): (6, 6)}
+    assert g.material_properties == {"E": 70e3, "nu": 0.3, "sig0": 200.0, "H": 10.0, "a": 10}  # the demo's exponent
+    with pytest.raises(ValueError):
+        jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.LinearHardening(sig0=1.0), equivalent_stress=jm.Hosford(a=7))
+    with pytest.raises(TypeError):
+        jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.VoceHardening(sig0=1.0, sigu=2.0, b=1.0))
     with pytest.raises(TypeError):
         jm.CUDAMaterial(jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=lambda p: 1.0))
     with pytest.raises(KeyError):

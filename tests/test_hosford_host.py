@@ -1,0 +1,78 @@
+"""The Hosford kernel's per-point routine (``csrc/dxm_hosford.cuh``: ``hosford_point``, ``__host__ __device__``)
+executed on the CPU and compared bit for bit with the oracle -- the same code path the GPU runs per Gauss point,
+checked where no GPU is available.  (The GPU parity tests proper are in ``tests/test_hosford_gpu.py``.)"""
+
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import hosford as ho
+from oracle import small_strain as ss
+from oracle import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hosford_host_check.cu")
+LIB = os.path.join(HERE, "_build", "libhosford_host_check.so")
+
+
+@pytest.fixture(scope="module")
+def host():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    deps = [SRC] + [os.path.join(HERE, "..", "dolfinx_materials_b200", "csrc", f)
+                    for f in ("dxm_hosford.cuh", "dxm_small_strain.cuh", "dxm_canon.cuh")]
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-fmad=false",
+                        "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-o", LIB, SRC], check=True)
+    return ctypes.CDLL(LIB)
+
+
+def run(lib, eps, st, props):
+    n = eps.shape[0]
+    c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    eps = np.ascontiguousarray(eps)
+    e_old, s_old = np.ascontiguousarray(st["strain"]), np.ascontiguousarray(st["stress"])
+    p_old, ep_old = np.ascontiguousarray(st["p"]).reshape(n), np.ascontiguousarray(st["epsp"])
+    sig, p, epsp, ct = np.empty((n, 6)), np.empty(n), np.empty((n, 6)), np.empty((n, 6, 6))
+    flag, fail, it, rs = np.empty(n, np.uint8), np.empty(n, np.uint8), np.empty(n, np.int32), np.empty(n)
+    lib.hosford_host(ctypes.c_int64(n), c(eps), c(e_old), c(s_old), c(p_old), c(ep_old), ctypes.c_double(props["E"]),
+                     ctypes.c_double(props["nu"]), ctypes.c_double(props["sig0"]), ctypes.c_double(props["H"]),
+                     ctypes.c_int(props["a"]), c(sig), c(p), c(epsp), c(ct), c(flag), c(it), c(rs), c(fail))
+    return {"strain": eps, "stress": sig, "p": p, "epsp": epsp, "Ct": ct, "flag": flag, "n_iter": it, "resid": rs,
+            "fail": fail}
+
+
+@pytest.mark.parametrize("a", [2, 6, 10, 20])
+def test_kernel_point_routine_equals_oracle_bit_for_bit(host, a):
+    props = dict(E=70e3, nu=0.3, sig0=200.0, H=10.0, a=a)
+    n = 20000
+    st = ss.zero_state(n)
+    for k in range(1, 4):
+        eps = synth.strain(n, a, 1.25e-2, k, 3)
+        ref = ho.integrate(eps, st, props)
+        got = run(host, eps, st, props)
+        for key in ("flag", "n_iter", "fail", "stress", "p", "epsp", "Ct", "resid"):
+            assert np.array_equal(got[key], ref[key]), (key, k)
+        st = ss.advance(ref)
+    assert 0.3 < ref["flag"].mean() < 0.95 and ref["fail"].sum() == 0
+
+
+def test_kernel_point_routine_degenerate_and_extreme_inputs(host):
+    props = dict(E=70e3, nu=0.3, sig0=200.0, H=1e-6, a=10)
+    rows = [[0, 0, 0, 0, 0, 0], [8e-3, -3e-3, -3e-3, 0, 0, 0], [1e-2, 1e-2, 1e-2, 0, 0, 0], [0, 0, 0, 2e-2, 0, 0],
+            [0.3, -0.1, 0.05, 0.2, -0.3, 0.1], [np.nan, 0, 0, 0, 0, 0], [1e-3, 1e-3, -2e-3, 0, 0, 0]]
+    eps = np.array(rows, dtype=float)
+    st = ss.zero_state(len(rows))
+    ref = ho.integrate(eps, st, props)
+    got = run(host, eps, st, props)
+    for key in ("flag", "n_iter", "fail"):
+        assert np.array_equal(got[key], ref[key]), key
+    for key in ("stress", "p", "epsp", "Ct", "resid"):
+        assert got[key].tobytes() == ref[key].tobytes(), key  # bitwise, NaN included
+    assert ref["fail"][5] == 1 and ref["fail"].sum() == 1
