@@ -254,6 +254,40 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
   a.d_fail = h->d_fail;
   if (h->behaviour == DXM_HOSFORD_LINEAR) {
     a.hos_a = h->hos_a;
+    // Split launch (stream + queue the candidates | persistent local solves over the queue) for batches large enough
+    // to pay a second launch; the fused kernel below that and as the A/B reference (DXM_HOS_SPLIT=0|1).
+    const char* e = std::getenv("DXM_HOS_SPLIT");
+    const bool split = e ? std::atoi(e) != 0 : count >= 32768;
+    if (split) {
+      if (!h->hos_queue) {
+        CK(cudaMalloc(&h->hos_queue, sizeof(unsigned) * h->ld));
+        CK(cudaMalloc(&h->hos_count, sizeof(unsigned)));
+      }
+      a.hos_queue = h->hos_queue;
+      a.hos_count = h->hos_count;
+      CK(cudaMemsetAsync(h->hos_count, 0, sizeof(unsigned), h->stream));
+      const int64_t ntile = (count + 255) / 256;
+      const int grid = grid_for(nullptr, 256, 0, h->num_sms, ntile);
+      e = std::getenv("DXM_HOS_MINB");
+      const int minb = e ? std::atoi(e) : 3;
+#define DXM_HOS_SPLIT_LAUNCH(PP, DG)                                                                  \
+  do {                                                                                                \
+    dxm_hosford_light_kernel<PP, DG><<<grid, 256, 0, h->stream>>>(a);                                 \
+    LAUNCH_CHECK();                                                                                   \
+    if (minb == 4) dxm_hosford_heavy_kernel<PP, DG, 4><<<h->num_sms * 4, 128, 0, h->stream>>>(a);     \
+    else dxm_hosford_heavy_kernel<PP, DG, 3><<<h->num_sms * 3, 128, 0, h->stream>>>(a);               \
+    LAUNCH_CHECK();                                                                                   \
+  } while (0)
+      if (h->perpoint) {
+        if (h->diag) DXM_HOS_SPLIT_LAUNCH(true, true);
+        else DXM_HOS_SPLIT_LAUNCH(true, false);
+      } else {
+        if (h->diag) DXM_HOS_SPLIT_LAUNCH(false, true);
+        else DXM_HOS_SPLIT_LAUNCH(false, false);
+      }
+#undef DXM_HOS_SPLIT_LAUNCH
+      return 0;
+    }
     const int block = 128;
     const int64_t ntile = (count + block - 1) / block;
     const int grid = grid_for(nullptr, block, 0, h->num_sms, ntile);
@@ -392,6 +426,8 @@ void free_handle(dxm_handle* h) {
   cudaFree(h->ct);
   cudaFree(h->pp);
   cudaFree(h->table);
+  cudaFree(h->hos_queue);
+  cudaFree(h->hos_count);
   cudaFree(h->d_stats);
   cudaFreeHost(h->h_stats);
   for (int s = 0; s < 2; ++s) {

@@ -8,7 +8,8 @@
 //
 // One Gauss point per thread.  Isotropy keeps the principal axes of the trial stress, so per point:
 //   * cheap rejection: sigma_eq <= max|s_i - s_j| <= 2/sqrt(3) seq_Mises  -> clearly elastic points skip the rest;
-//   * cyclic Jacobi eigen-decomposition of the trial deviator in registers (+ - * / sqrt only);
+//   * cyclic Jacobi eigen-decomposition of the trial deviator in registers (+ - * / sqrt only); the equivalent stress
+//     costs two divisions per evaluation (the a-th root is a division-free Newton on q^(-1/a));
 //   * 4-unknown Newton (3 principal deviatoric stresses + dp) from the radially scaled trial state, with a
 //     simple-decrease backtracking line search (plain Newton overshoots at the rounded corners of the surface);
 //     3x3 solves by the symmetric adjugate;
@@ -17,7 +18,15 @@
 //     back with the eigenvectors and stored packed (21 unique entries) like the J2 tangent.
 // All powers are product chains; operation order == oracle/c/dxm_oracle_hosford.c (bit-identical with -fmad=false).
 // The point routine is __host__ __device__ so that a CPU test can run the very same code against the oracle
-// (tests/hosford_host_check.cu) -- the product only ever calls it from the kernel below.
+// (tests/hosford_host_check.cu) -- the product only ever calls it from the kernels below.
+//
+// Launch structure (profiles/r01f_hosford_v1_ncu_*: the fused one-kernel version is latency-bound -- 168 registers,
+// 12 warps per SM, 22 of 32 lanes active, and a warp with ONE candidate lane pays the whole local solve):
+//   dxm_hosford_light_kernel  streams every point like the J2 kernel (256 threads, high occupancy), finishes the
+//                             clearly elastic ones and appends the others' indices to a device queue
+//                             (warp-aggregated atomics keep neighbours together);
+//   dxm_hosford_heavy_kernel  persistent grid over the queue: every lane of every warp holds a candidate point.
+// The fused kernel remains for small batches (one launch) and as the A/B reference (DXM_HOS_SPLIT=0|1).
 #pragma once
 #include "dxm_canon.cuh"
 #include "dxm_small_strain.cuh"
@@ -39,33 +48,33 @@ DXM_HD double hos_ipow2(double x, int k) {
   return y;
 }
 
-// q^(1/a), q in (0.5, 1]: Newton from above on y^a = q
-DXM_HD double hos_aroot(double q, int a) {
-  const double ad = (double)a, am1 = ad - 1.0;
-  double y = 1.0;
+// q^(-1/a), q in (0.5, 1]: division-free Newton from below on w^-a = q
+DXM_HD double hos_arootinv(double q, int a, double inv_a) {
+  double w = 1.0;
   for (int it = 0; it < 30; ++it) {
-    const double ym = (a > 2) ? hos_ipow2(y, (a - 2) / 2) * y : y;
-    const double yn = (am1 * y + q / ym) / ad;
-    if (!(yn < y)) break;
-    y = yn;
+    const double wn = w * (1.0 + (1.0 - q * hos_ipow2(w, a / 2)) * inv_a);
+    if (!(wn > w)) break;
+    w = wn;
   }
-  return y;
+  return w;
 }
 
 struct HosEval {
-  double phi, n[3], h[3], u[3];
+  double phi, iphi, n[3], h[3], u[3];
 };
 
-DXM_HD void hos_eval(const double (&l)[3], int a, HosEval& e) {
+DXM_HD void hos_eval(const double (&l)[3], int a, double inv_a, HosEval& e) {
   const double d0 = l[0] - l[1], d1 = l[1] - l[2], d2 = l[2] - l[0];
   const double m = fmax(fmax(fabs(d0), fabs(d1)), fabs(d2));
-  const double r0 = d0 / m, r1 = d1 / m, r2 = d2 / m;
+  const double im = 1.0 / m;
+  const double r0 = d0 * im, r1 = d1 * im, r2 = d2 * im;
   const double q = 0.5 * ((hos_ipow2(r0, a / 2) + hos_ipow2(r1, a / 2)) + hos_ipow2(r2, a / 2));
-  const double y = hos_aroot(q, a);
-  e.phi = m * y;
-  e.u[0] = r0 / y;
-  e.u[1] = r1 / y;
-  e.u[2] = r2 / y;
+  const double w = hos_arootinv(q, a, inv_a);
+  e.phi = m / w;
+  e.iphi = w * im;
+  e.u[0] = r0 * w;
+  e.u[1] = r1 * w;
+  e.u[2] = r2 * w;
 #pragma unroll
   for (int k = 0; k < 3; ++k) e.h[k] = (a > 2) ? hos_ipow2(e.u[k], (a - 2) / 2) : 1.0;
   const double g0 = e.h[0] * e.u[0], g1 = e.h[1] * e.u[1], g2 = e.h[2] * e.u[2];
@@ -93,9 +102,9 @@ DXM_HD void hos_jrot(double& app, double& aqq, double& apq, double& arp, double&
     apq = 0.0;
     return;
   }
-  const double theta = ((aqq - app) * 0.5) / apq;
-  double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
-  if (theta < 0.0) t = -t;
+  const double delta = (aqq - app) * 0.5;
+  double t = apq / (fabs(delta) + sqrt(delta * delta + apq * apq));
+  if (delta < 0.0) t = -t;
   const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
   app = app - t * apq;
   aqq = aqq + t * apq;
@@ -134,8 +143,8 @@ struct HosRes {
 };
 
 DXM_HD void hos_residual(const double (&x)[3], double dp, const double (&l)[3], double twomu, double sy0, double H,
-                         int a, HosRes& o) {
-  hos_eval(x, a, o.e);
+                         int a, double inv_a, HosRes& o) {
+  hos_eval(x, a, inv_a, o.e);
   const double c = twomu * dp;
 #pragma unroll
   for (int k = 0; k < 3; ++k) o.rs[k] = (x[k] - l[k]) + c * o.e.n[k];
@@ -189,7 +198,10 @@ DXM_HD void hos_mandel_pair(const double (&V)[3][3], double (&m)[6]) {
 }
 
 // One Gauss point.  ct21: the 21 unique tangent entries (j <= i, row-major upper triangle = sym6_packed order).
-DXM_HD void hosford_point(const double lam, const double mu, const double sig0, const double H, const int a,
+// LIGHT == true: only the clearly elastic points are finished; for a candidate (the cheap rejection did not fire) the
+// routine returns true without touching the outputs and the caller hands the point to the full routine.
+template <bool LIGHT>
+DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, const double H, const int a,
                           const double (&eps)[6], const double (&e_old)[6], const double (&s_old)[6],
                           const double p_old, const double (&ep_old)[6], double (&sig)[6], double& p_new,
                           double (&epsp)[6], double (&ct21)[21], bool& flag, int& n_iter, double& resid,
@@ -221,61 +233,82 @@ DXM_HD void hosford_point(const double lam, const double mu, const double sig0, 
   fail = false;
   resid = 0.0;
   double dp = 0.0;
-  double l[3], V[3][3];
+  double V[3][3];
   HosRes cur;
-  if (1.1548 * seq > sy0) {  // sigma_eq <= max|s_i - s_j| <= 2/sqrt(3) seq_Mises: otherwise surely elastic
+  // sigma_eq <= max|s_i - s_j| <= 2/sqrt(3) seq_Mises: below that bound the point is surely elastic
+  const bool candidate = 1.1548 * seq > sy0;
+  if (LIGHT && candidate) return true;
+  if (!LIGHT && candidate) {
+    const double am1 = (double)a - 1.0, inv_a = 1.0 / (double)a;
+    const double tol = kNewtonRtol * seq;
+    double l[3], x[3] = {0.0, 0.0, 0.0}, xe[3], dx[3] = {0.0, 0.0, 0.0}, dpe = 0.0, ddp = 0.0, t = 1.0;
+    int ls = 0, stage = 0;
     hos_jacobi3(s, l, V);
-    hos_eval(l, a, cur.e);
-    const double f = cur.e.phi - sy0;
-    flag = f > 0.0;
-    if (flag) {
-      dp = f / (threemu + H);
-      const double sc = (sy0 + H * dp) / cur.e.phi;
-      double x[3] = {l[0] * sc, l[1] * sc, l[2] * sc};
-      hos_residual(x, dp, l, twomu, sy0, H, a, cur);
-      const double tol = kNewtonRtol * seq;
-      for (int it = 0;; ++it) {
-        const double res = fmax(fmax(fabs(cur.rs[0]), fabs(cur.rs[1])), fmax(fabs(cur.rs[2]), fabs(cur.r4)));
-        if (res <= tol) {
-          resid = res;
-          break;
-        }
-        if (it == kNewtonCap || !(res == res)) {
-          resid = res;
-          fail = true;
-          break;
-        }
-        double Cf[6], idet, y[3], z[3];
-        hos_system(cur.e, twomu * dp, ((double)a - 1.0) / cur.e.phi, Cf, idet);
-        hos_apply(Cf, idet, cur.rs, y);
-        hos_apply(Cf, idet, cur.e.n, z);
-        const double ny = (cur.e.n[0] * y[0] + cur.e.n[1] * y[1]) + cur.e.n[2] * y[2];
-        const double nz = (cur.e.n[0] * z[0] + cur.e.n[1] * z[1]) + cur.e.n[2] * z[2];
-        const double ddp = (cur.r4 - ny) / (twomu * nz + H);
-        const double tz = twomu * ddp;
-        const double dx[3] = {-(y[0] + tz * z[0]), -(y[1] + tz * z[1]), -(y[2] + tz * z[2])};
-        double t = 1.0;
-        HosRes nxt;
-        double xn[3], dpn;
-        for (int ls = 0;; ++ls) {
 #pragma unroll
-          for (int k = 0; k < 3; ++k) xn[k] = x[k] + t * dx[k];
-          dpn = dp + t * ddp;
-          hos_residual(xn, dpn, l, twomu, sy0, H, a, nxt);
-          if (nxt.m2 < cur.m2 || ls == kHosfordLsMax) break;
+    for (int k = 0; k < 3; ++k) xe[k] = l[k];
+    // One evaluation site for the three uses of the residual (trial state, start point, line-search candidates):
+    // stage 0 = yield check at the trial state, 1 = start point, 2 = line-search candidate of a Newton step.
+    for (;;) {
+      HosRes nxt;
+      hos_residual(xe, dpe, l, twomu, sy0, H, a, inv_a, nxt);
+      if (stage == 0) {
+        const double f = nxt.e.phi - sy0;
+        flag = f > 0.0;
+        if (!flag) break;
+        // start on the yield surface along the trial direction, dp from the J2-like estimate
+        dpe = f / (threemu + H);
+        const double sc = (sy0 + H * dpe) / nxt.e.phi;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) xe[k] = l[k] * sc;
+        stage = 1;
+        continue;
+      }
+      if (stage == 2) {
+        if (!(nxt.m2 < cur.m2 || ls == kHosfordLsMax)) {  // no decrease: halve the step
           t = 0.5 * t;
-        }
+          ++ls;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) x[k] = xn[k];
-        dp = dpn;
-        cur = nxt;
+          for (int k = 0; k < 3; ++k) xe[k] = x[k] + t * dx[k];
+          dpe = dp + t * ddp;
+          continue;
+        }
         ++n_iter;
       }
+      stage = 2;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) x[k] = xe[k];
+      dp = dpe;
+      cur = nxt;
+      const double res = fmax(fmax(fabs(cur.rs[0]), fabs(cur.rs[1])), fmax(fabs(cur.rs[2]), fabs(cur.r4)));
+      if (res <= tol) {
+        resid = res;
+        break;
+      }
+      if (n_iter == kNewtonCap || !(res == res)) {
+        resid = res;
+        fail = true;
+        break;
+      }
+      double Cf[6], idet, y[3], z[3];
+      hos_system(cur.e, twomu * dp, am1 * cur.e.iphi, Cf, idet);
+      hos_apply(Cf, idet, cur.rs, y);
+      hos_apply(Cf, idet, cur.e.n, z);
+      const double ny = (cur.e.n[0] * y[0] + cur.e.n[1] * y[1]) + cur.e.n[2] * y[2];
+      const double nz = (cur.e.n[0] * z[0] + cur.e.n[1] * z[1]) + cur.e.n[2] * z[2];
+      ddp = (cur.r4 - ny) / (twomu * nz + H);
+      const double tz = twomu * ddp;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) dx[k] = -(y[k] + tz * z[k]);
+      t = 1.0;
+      ls = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) xe[k] = x[k] + t * dx[k];
+      dpe = dp + t * ddp;
     }
   }
 
   double mN0[6], mN1[6], mN2[6], nrm[6];
-  if (flag) {
+  if (!LIGHT && flag) {
     hos_mandel_pair<0, 0>(V, mN0);
     hos_mandel_pair<1, 1>(V, mN1);
     hos_mandel_pair<2, 2>(V, mN2);
@@ -294,7 +327,7 @@ DXM_HD void hosford_point(const double lam, const double mu, const double sig0, 
   }
   p_new = p_old + dp;
 
-  if (!flag) {
+  if (LIGHT || !flag) {
     const double AB = lam + twomu;
 #pragma unroll
     for (int j = 0; j < 6; ++j)
@@ -303,8 +336,8 @@ DXM_HD void hosford_point(const double lam, const double mu, const double sig0, 
         ct21[sym6_packed(j * 6 + i)] = (i == j) ? ((i < 3) ? AB : twomu) : ((i < 3 && j < 3) ? lam : 0.0);
   } else {
     double Cf[6], idet, z[3];
-    const double c = twomu * dp, iphi = 1.0 / cur.e.phi;
-    hos_system(cur.e, c, ((double)a - 1.0) / cur.e.phi, Cf, idet);
+    const double c = twomu * dp, iphi = cur.e.iphi;
+    hos_system(cur.e, c, ((double)a - 1.0) * cur.e.iphi, Cf, idet);
     hos_apply(Cf, idet, cur.e.n, z);
     const double nz = (cur.e.n[0] * z[0] + cur.e.n[1] * z[1]) + cur.e.n[2] * z[2];
     const double w = (twomu * twomu) / (twomu * nz + H);
@@ -343,60 +376,135 @@ DXM_HD void hosford_point(const double lam, const double mu, const double sig0, 
 #pragma unroll
   for (int i = 0; i < 6; ++i) chk = chk + fabs(epsp[i]);
   if (!isfinite(chk)) fail = true;
+  return false;
 }
 
 #ifdef __CUDACC__
-// SmallStrainArgs is shared with the J2 kernels (same SoA state layout); a.dsu / a.b are unused, a.hos_a = exponent.
+// SmallStrainArgs is shared with the J2 kernels (same SoA state layout); a.dsu / a.b are unused, a.hos_a = exponent,
+// a.hos_queue / a.hos_count = the candidate queue of the split launch.
+struct HosPointIO {
+  double eps[6], e_old[6], s_old[6], ep_old[6], p_old, lam, mu, sig0, H;
+};
+
+template <bool PERPOINT>
+__device__ __forceinline__ void hos_load(const SmallStrainArgs& a, int64_t i0, HosPointIO& io) {
+  const int64_t ld = a.ld;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) io.eps[c] = __ldcs(a.eps + c * ld + i0);
+#pragma unroll
+  for (int c = 0; c < 6; ++c) io.e_old[c] = __ldcs(a.eps_old + c * ld + i0);
+#pragma unroll
+  for (int c = 0; c < 6; ++c) io.s_old[c] = __ldcs(a.sig_old + c * ld + i0);
+  io.p_old = __ldcs(a.p_old + i0);
+#pragma unroll
+  for (int c = 0; c < 6; ++c) io.ep_old[c] = __ldcs(a.epsp_old + c * ld + i0);
+  io.lam = a.lam;
+  io.mu = a.mu;
+  io.sig0 = a.sig0;
+  io.H = a.H;
+  if (PERPOINT) {
+    const double E = __ldcs(a.pE + i0), nu = __ldcs(a.pnu + i0);
+    io.lam = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu);
+    io.mu = E / 2.0 / (1.0 + nu);
+    io.sig0 = __ldcs(a.psig0 + i0);
+    io.H = __ldcs(a.pH + i0);
+  }
+}
+
+template <bool DIAG>
+__device__ __forceinline__ void hos_finish(const SmallStrainArgs& a, int64_t i0, const double (&sig)[6], double p_new,
+                                           const double (&epsp)[6], const double (&ct21)[21], bool flag, int n_iter,
+                                           double resid, bool fail, PointStats& acc) {
+  const int64_t ld = a.ld;
+  acc.n_plastic += flag ? 1u : 0u;
+  acc.n_fail += fail ? 1u : 0u;
+  acc.max_iter = n_iter > (int)acc.max_iter ? (unsigned)n_iter : acc.max_iter;
+  acc.max_resid = resid > acc.max_resid ? resid : acc.max_resid;
+  if (resid != resid) acc.max_resid = resid;
+  if (DIAG) {
+    a.d_flag[i0] = flag ? 1 : 0;
+    a.d_iter[i0] = n_iter;
+    a.d_resid[i0] = resid;
+    a.d_fail[i0] = fail ? 1 : 0;
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) __stcs(a.sig + c * ld + i0, sig[c]);
+  __stcs(a.p + i0, p_new);
+#pragma unroll
+  for (int c = 0; c < 6; ++c) __stcs(a.epsp + c * ld + i0, epsp[c]);
+#pragma unroll
+  for (int r = 0; r < 21; ++r) __stcs(a.ct + (int64_t)r * ld + i0, ct21[r]);
+}
+
+// fused: every thread runs the full routine on its own point (small batches, A/B reference)
 template <bool PERPOINT, bool DIAG>
 __global__ void __launch_bounds__(128, 3) dxm_hosford_kernel(const SmallStrainArgs a) {
-  const int64_t ld = a.ld;
   const int64_t ntile = (a.count + blockDim.x - 1) / blockDim.x;
   PointStats acc;
   for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     const int64_t loc = tile * blockDim.x + threadIdx.x;
     if (loc >= a.count) continue;
     const int64_t i0 = a.start + loc;
-    double eps[6], e_old[6], s_old[6], ep_old[6];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) eps[c] = __ldcs(a.eps + c * ld + i0);
-#pragma unroll
-    for (int c = 0; c < 6; ++c) e_old[c] = __ldcs(a.eps_old + c * ld + i0);
-#pragma unroll
-    for (int c = 0; c < 6; ++c) s_old[c] = __ldcs(a.sig_old + c * ld + i0);
-    const double p_old = __ldcs(a.p_old + i0);
-#pragma unroll
-    for (int c = 0; c < 6; ++c) ep_old[c] = __ldcs(a.epsp_old + c * ld + i0);
-    double lam = a.lam, mu = a.mu, sig0 = a.sig0, H = a.H;
-    if (PERPOINT) {
-      const double E = __ldcs(a.pE + i0), nu = __ldcs(a.pnu + i0);
-      lam = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu);
-      mu = E / 2.0 / (1.0 + nu);
-      sig0 = __ldcs(a.psig0 + i0);
-      H = __ldcs(a.pH + i0);
-    }
+    HosPointIO io;
+    hos_load<PERPOINT>(a, i0, io);
     double sig[6], epsp[6], ct21[21], p_new, resid;
     bool flag, fail;
     int n_iter;
-    hosford_point(lam, mu, sig0, H, a.hos_a, eps, e_old, s_old, p_old, ep_old, sig, p_new, epsp, ct21, flag, n_iter,
-                  resid, fail);
-    acc.n_plastic += flag ? 1u : 0u;
-    acc.n_fail += fail ? 1u : 0u;
-    acc.max_iter = n_iter > (int)acc.max_iter ? (unsigned)n_iter : acc.max_iter;
-    acc.max_resid = resid > acc.max_resid ? resid : acc.max_resid;
-    if (resid != resid) acc.max_resid = resid;
-    if (DIAG) {
-      a.d_flag[i0] = flag ? 1 : 0;
-      a.d_iter[i0] = n_iter;
-      a.d_resid[i0] = resid;
-      a.d_fail[i0] = fail ? 1 : 0;
+    hosford_point<false>(io.lam, io.mu, io.sig0, io.H, a.hos_a, io.eps, io.e_old, io.s_old, io.p_old, io.ep_old, sig,
+                         p_new, epsp, ct21, flag, n_iter, resid, fail);
+    hos_finish<DIAG>(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
+  }
+  block_reduce_stats(acc, a.stats);
+}
+
+// split, pass 1: stream all points, finish the clearly elastic ones, queue the candidates
+template <bool PERPOINT, bool DIAG>
+__global__ void __launch_bounds__(256, 3) dxm_hosford_light_kernel(const SmallStrainArgs a) {
+  const int64_t ntile = (a.count + blockDim.x - 1) / blockDim.x;
+  PointStats acc;
+  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int64_t loc = tile * blockDim.x + threadIdx.x;
+    const bool live = loc < a.count;
+    bool heavy = false;
+    if (live) {
+      const int64_t i0 = a.start + loc;
+      HosPointIO io;
+      hos_load<PERPOINT>(a, i0, io);
+      double sig[6], epsp[6], ct21[21], p_new, resid;
+      bool flag, fail;
+      int n_iter;
+      heavy = hosford_point<true>(io.lam, io.mu, io.sig0, io.H, a.hos_a, io.eps, io.e_old, io.s_old, io.p_old,
+                                  io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
+      if (!heavy) hos_finish<DIAG>(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
     }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) __stcs(a.sig + c * ld + i0, sig[c]);
-    __stcs(a.p + i0, p_new);
-#pragma unroll
-    for (int c = 0; c < 6; ++c) __stcs(a.epsp + c * ld + i0, epsp[c]);
-#pragma unroll
-    for (int r = 0; r < 21; ++r) __stcs(a.ct + (int64_t)r * ld + i0, ct21[r]);
+    // warp-aggregated append: one atomic per warp, lanes keep their order (neighbours stay neighbours in the queue)
+    const unsigned bal = __ballot_sync(0xffffffffu, heavy);
+    if (bal) {
+      const int lane = threadIdx.x & 31;
+      unsigned base = 0;
+      if (lane == __ffs(bal) - 1) base = atomicAdd(a.hos_count, (unsigned)__popc(bal));
+      base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+      if (heavy) a.hos_queue[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned)loc;
+    }
+  }
+  block_reduce_stats(acc, a.stats);
+}
+
+// split, pass 2: persistent grid over the queue, every lane holds a candidate point
+template <bool PERPOINT, bool DIAG, int MINB>
+__global__ void __launch_bounds__(128, MINB) dxm_hosford_heavy_kernel(const SmallStrainArgs a) {
+  const unsigned total = *a.hos_count;
+  PointStats acc;
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+    const int64_t i0 = a.start + (int64_t)a.hos_queue[q];
+    HosPointIO io;
+    hos_load<PERPOINT>(a, i0, io);
+    double sig[6], epsp[6], ct21[21], p_new, resid;
+    bool flag, fail;
+    int n_iter;
+    hosford_point<false>(io.lam, io.mu, io.sig0, io.H, a.hos_a, io.eps, io.e_old, io.s_old, io.p_old, io.ep_old, sig,
+                         p_new, epsp, ct21, flag, n_iter, resid, fail);
+    hos_finish<DIAG>(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
   }
   block_reduce_stats(acc, a.stats);
 }

@@ -45,6 +45,8 @@ struct SmallStrainArgs {
   const double* table;
   int ntab;
   int hos_a;  // DXM_HOSFORD_LINEAR: exponent of the Hosford criterion (even integer)
+  unsigned* hos_queue;  // split launch: local indices of the candidate points, [count]
+  unsigned* hos_count;  // ... and how many there are
   StatSlot* stats;
   int vote;  // 1: warp-vote (__any_sync) Newton loop exit, 0: per-lane exit (A/B knob DXM_VOTE)
   // optional diagnostics (DIAG == true)

@@ -18,7 +18,8 @@
  *
  * Algorithm (operation order == csrc/dxm_hosford.cuh, compiled with -ffp-contract=off / -fmad=false):
  *   trial stress as in the J2 update; cheap rejection sigma_eq <= max|s_i - s_j| <= 2/sqrt(3) seq_Mises;
- *   cyclic Jacobi eigen-decomposition of the trial deviator (+, -, *, /, sqrt only); isotropy keeps the principal
+ *   cyclic Jacobi eigen-decomposition of the trial deviator (+, -, *, /, sqrt only; the equivalent stress costs two
+ *   divisions per evaluation: the a-th root is a division-free Newton on q^(-1/a)); isotropy keeps the principal
  *   axes, so the return map is a 4-unknown Newton (3 principal deviatoric stresses + dp) started from the radially
  *   scaled trial state with a simple-decrease backtracking line search; the consistent tangent
  *   Xi - (Xi n)(Xi n)^T / (n Xi n + H), Xi = (C^-1 + dp dn/dsigma)^-1, is assembled from its spectral form: a 3x3
@@ -41,30 +42,33 @@ static double ipow2(double x, int k) {
   return y;
 }
 
-/* q^(1/a), q in (0.5, 1]: Newton from above on y^a = q (monotone decreasing until rounding stops it) */
-static double aroot(double q, int a) {
-  const double ad = (double)a, am1 = ad - 1.0;
-  double y = 1.0;
+/* q^(-1/a), q in (0.5, 1]: division-free Newton from below on w^-a = q, w <- w (1 + (1 - q w^a)/a) (monotone
+ * increasing until rounding stops it) */
+static double arootinv(double q, int a, double inv_a) {
+  double w = 1.0;
   for (int it = 0; it < 30; ++it) {
-    const double ym = (a > 2) ? ipow2(y, (a - 2) / 2) * y : y; /* y^(a-1) */
-    const double yn = (am1 * y + q / ym) / ad;
-    if (!(yn < y)) break;
-    y = yn;
+    const double wn = w * (1.0 + (1.0 - q * ipow2(w, a / 2)) * inv_a);
+    if (!(wn > w)) break;
+    w = wn;
   }
-  return y;
+  return w;
 }
 
-/* Hosford equivalent stress of principal values l, its gradient n and h_k = (d_k/phi)^(a-2), u_k = d_k/phi */
-static void hosford_eval(const double l[3], int a, double* phi, double n[3], double h[3], double u[3]) {
+/* Hosford equivalent stress of principal values l, 1/phi, its gradient n, h_k = (d_k/phi)^(a-2), u_k = d_k/phi.
+ * Two divisions: 1/max|d| and phi = max|d| / w. */
+static void hosford_eval(const double l[3], int a, double inv_a, double* phi, double* iphi, double n[3], double h[3],
+                         double u[3]) {
   const double d0 = l[0] - l[1], d1 = l[1] - l[2], d2 = l[2] - l[0];
   const double m = fmax(fmax(fabs(d0), fabs(d1)), fabs(d2));
-  const double r0 = d0 / m, r1 = d1 / m, r2 = d2 / m;
+  const double im = 1.0 / m;
+  const double r0 = d0 * im, r1 = d1 * im, r2 = d2 * im;
   const double q = 0.5 * ((ipow2(r0, a / 2) + ipow2(r1, a / 2)) + ipow2(r2, a / 2));
-  const double y = aroot(q, a);
-  *phi = m * y;
-  u[0] = r0 / y;
-  u[1] = r1 / y;
-  u[2] = r2 / y;
+  const double w = arootinv(q, a, inv_a);
+  *phi = m / w;
+  *iphi = w * im;
+  u[0] = r0 * w;
+  u[1] = r1 * w;
+  u[2] = r2 * w;
   for (int k = 0; k < 3; ++k) h[k] = (a > 2) ? ipow2(u[k], (a - 2) / 2) : 1.0;
   const double g0 = h[0] * u[0], g1 = h[1] * u[1], g2 = h[2] * u[2];
   n[0] = 0.5 * (g0 - g2);
@@ -90,9 +94,10 @@ static void jrot(double* app, double* aqq, double* apq, double* arp, double* arq
     *apq = 0.0;
     return;
   }
-  const double theta = ((*aqq - *app) * 0.5) / *apq;
-  double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
-  if (theta < 0.0) t = -t;
+  /* t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = delta / a_pq, written with one division */
+  const double delta = (*aqq - *app) * 0.5;
+  double t = *apq / (fabs(delta) + sqrt(delta * delta + *apq * *apq));
+  if (delta < 0.0) t = -t;
   const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
   *app = *app - t * *apq;
   *aqq = *aqq + t * *apq;
@@ -124,12 +129,12 @@ static void jacobi3(const double s[6], double l[3], double Q[3][3]) {
 }
 
 typedef struct {
-  double rs[3], r4, phi, n[3], h[3], u[3], m2;
+  double rs[3], r4, phi, iphi, n[3], h[3], u[3], m2;
 } hres_t;
 
 static void hosford_residual(const double x[3], double dp, const double l[3], double twomu, double sy0, double H, int a,
-                             hres_t* o) {
-  hosford_eval(x, a, &o->phi, o->n, o->h, o->u);
+                             double inv_a, hres_t* o) {
+  hosford_eval(x, a, inv_a, &o->phi, &o->iphi, o->n, o->h, o->u);
   const double c = twomu * dp;
   for (int k = 0; k < 3; ++k) o->rs[k] = (x[k] - l[k]) + c * o->n[k];
   o->r4 = o->phi - (sy0 + H * dp);
@@ -186,6 +191,7 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
     for (int i = 2; i < 6; ++i) ss = ss + s[i] * s[i];
     const double seq = sqrt(1.5 * ss);
     const double sy0 = sig0 + H * p_old;
+    const double am1 = (double)a - 1.0, inv_a = 1.0 / (double)a;
 
     int flag = 0, n_iter = 0, fail = 0;
     double dp = 0.0, resid = 0.0;
@@ -193,7 +199,7 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
     hres_t cur;
     if (1.1548 * seq > sy0) { /* sigma_eq <= max |s_i - s_j| <= 2/sqrt(3) seq: otherwise surely elastic */
       jacobi3(s, l, Q);
-      hosford_eval(l, a, &cur.phi, cur.n, cur.h, cur.u);
+      hosford_eval(l, a, inv_a, &cur.phi, &cur.iphi, cur.n, cur.h, cur.u);
       const double f = cur.phi - sy0;
       flag = f > 0.0;
       if (flag) {
@@ -201,14 +207,14 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
         dp = f / (threemu + H);
         const double sc = (sy0 + H * dp) / cur.phi;
         double x[3] = {l[0] * sc, l[1] * sc, l[2] * sc};
-        hosford_residual(x, dp, l, twomu, sy0, H, a, &cur);
+        hosford_residual(x, dp, l, twomu, sy0, H, a, inv_a, &cur);
         const double tol = rtol * seq;
         for (int it = 0;; ++it) {
           const double res = fmax(fmax(fabs(cur.rs[0]), fabs(cur.rs[1])), fmax(fabs(cur.rs[2]), fabs(cur.r4)));
           if (res <= tol) { resid = res; break; }
           if (it == newton_cap || !(res == res)) { resid = res; fail = 1; break; }
           double Cf[6], idet, y[3], z[3];
-          hosford_system(&cur, twomu * dp, ((double)a - 1.0) / cur.phi, Cf, &idet);
+          hosford_system(&cur, twomu * dp, am1 * cur.iphi, Cf, &idet);
           sym3_apply(Cf, idet, cur.rs, y);
           sym3_apply(Cf, idet, cur.n, z);
           const double ny = (cur.n[0] * y[0] + cur.n[1] * y[1]) + cur.n[2] * y[2];
@@ -222,7 +228,7 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
           for (int ls = 0;; ++ls) {
             for (int k = 0; k < 3; ++k) xn[k] = x[k] + t * dx[k];
             dpn = dp + t * ddp;
-            hosford_residual(xn, dpn, l, twomu, sy0, H, a, &nxt);
+            hosford_residual(xn, dpn, l, twomu, sy0, H, a, inv_a, &nxt);
             if (nxt.m2 < cur.m2 || ls == LS_MAX) break;
             t = 0.5 * t;
           }
@@ -268,8 +274,8 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
         for (int i = 0; i < 6; ++i) ct[j * 6 + i] = (i == j) ? ((i < 3) ? AB : twomu) : ((i < 3 && j < 3) ? lam : 0.0);
     } else {
       double Cf[6], idet, z[3];
-      const double c = twomu * dp, iphi = 1.0 / cur.phi;
-      hosford_system(&cur, c, ((double)a - 1.0) / cur.phi, Cf, &idet);
+      const double c = twomu * dp, iphi = cur.iphi;
+      hosford_system(&cur, c, am1 * cur.iphi, Cf, &idet);
       sym3_apply(Cf, idet, cur.n, z);
       const double nz = (cur.n[0] * z[0] + cur.n[1] * z[1]) + cur.n[2] * z[2];
       const double w = (twomu * twomu) / (twomu * nz + H); /* (2 mu z)(2 mu z)^T / (2 mu n.z + H) */

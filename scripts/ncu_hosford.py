@@ -1,4 +1,4 @@
-"""Workload for the ncu capture of dxm_hosford_kernel: 4e6 points, the demo's parameters (a = 10), second increment of
+"""Workload for the ncu capture of the Hosford kernels (split launch: light + heavy; DXM_HOS_SPLIT=0: fused): 4e6 points, the demo's parameters (a = 10), second increment of
 a two-increment history (about half the points plastic)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -6,7 +6,7 @@
 extern "C" void hosford_host(int64_t n, const double* eps, const double* e_old, const double* s_old, const double* p_old,
                              const double* ep_old, double E, double nu, double sig0, double H, int a, double* sig,
                              double* p, double* epsp, double* ct, uint8_t* flag, int32_t* n_iter, double* resid,
-                             uint8_t* fail) {
+                             uint8_t* fail, int split, int64_t* n_candidates) {
   const double lam = E * nu / (1 + nu) / (1 - 2 * nu);
   const double mu = E / 2 / (1 + nu);
   for (int64_t i = 0; i < n; ++i) {
@@ -19,7 +19,14 @@ extern "C" void hosford_host(int64_t n, const double* eps, const double* e_old, 
       s0[c] = s_old[i * 6 + c];
       ep0[c] = ep_old[i * 6 + c];
     }
-    dxm::hosford_point(lam, mu, sig0, H, a, e1, e0, s0, p_old[i], ep0, so, pn, epo, ct21, fl, it, rs, fa);
+    // split != 0 replays the two-kernel launch: the light pass finishes the clearly elastic points and reports the
+    // candidates, which the full routine then recomputes from scratch (dxm_hosford_light_kernel / _heavy_kernel)
+    bool heavy = true;
+    if (split) heavy = dxm::hosford_point<true>(lam, mu, sig0, H, a, e1, e0, s0, p_old[i], ep0, so, pn, epo, ct21, fl, it, rs, fa);
+    if (heavy) {
+      if (split) ++*n_candidates;
+      dxm::hosford_point<false>(lam, mu, sig0, H, a, e1, e0, s0, p_old[i], ep0, so, pn, epo, ct21, fl, it, rs, fa);
+    }
     for (int c = 0; c < 6; ++c) {
       sig[i * 6 + c] = so[c];
       epsp[i * 6 + c] = epo[c];

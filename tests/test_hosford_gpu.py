@@ -42,6 +42,23 @@ def check(m, out, ref):
     assert s.max_iter == int(ref["n_iter"].max()) and s.max_residual == ref["resid"].max()
 
 
+@pytest.mark.parametrize("split", ["0", "1"])
+@pytest.mark.parametrize("n", [129, 50_003])
+def test_fused_and_split_launches_agree_with_the_oracle(jm, monkeypatch, split, n):
+    """DXM_HOS_SPLIT: one fused kernel vs light pass + queue + persistent local solves -- same bits either way."""
+    monkeypatch.setenv("DXM_HOS_SPLIT", split)
+    m = make(jm, DEMO, n)
+    st = ss.zero_state(n)
+    for k, amp in ((1, 2e-3), (2, 6e-3), (3, 1.25e-2)):  # few, some, most points plastic
+        eps = synth.strain(n, 4, amp, 1, 1)
+        out = m.integrate(eps)
+        ref = ho.integrate(eps, st, DEMO)
+        check(m, out, ref)
+        m.data_manager.update()
+        st = ss.advance(ref)
+    assert m.last_stats.n_plastic > 0.5 * n
+
+
 @pytest.mark.parametrize("a", [2, 6, 10, 20])
 @pytest.mark.parametrize("n", [1, 129, 50_003])
 def test_history_bit_exact(jm, a, n):

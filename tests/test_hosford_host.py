@@ -33,7 +33,7 @@ def host():
     return ctypes.CDLL(LIB)
 
 
-def run(lib, eps, st, props):
+def run(lib, eps, st, props, split=0):
     n = eps.shape[0]
     c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
     eps = np.ascontiguousarray(eps)
@@ -41,10 +41,12 @@ def run(lib, eps, st, props):
     p_old, ep_old = np.ascontiguousarray(st["p"]).reshape(n), np.ascontiguousarray(st["epsp"])
     sig, p, epsp, ct = np.empty((n, 6)), np.empty(n), np.empty((n, 6)), np.empty((n, 6, 6))
     flag, fail, it, rs = np.empty(n, np.uint8), np.empty(n, np.uint8), np.empty(n, np.int32), np.empty(n)
+    ncand = ctypes.c_int64(0)
     lib.hosford_host(ctypes.c_int64(n), c(eps), c(e_old), c(s_old), c(p_old), c(ep_old), ctypes.c_double(props["E"]),
                      ctypes.c_double(props["nu"]), ctypes.c_double(props["sig0"]), ctypes.c_double(props["H"]),
-                     ctypes.c_int(props["a"]), c(sig), c(p), c(epsp), c(ct), c(flag), c(it), c(rs), c(fail))
-    return {"strain": eps, "stress": sig, "p": p, "epsp": epsp, "Ct": ct, "flag": flag, "n_iter": it, "resid": rs,
+                     ctypes.c_int(props["a"]), c(sig), c(p), c(epsp), c(ct), c(flag), c(it), c(rs), c(fail),
+                     ctypes.c_int(split), ctypes.byref(ncand))
+    return {"candidates": ncand.value, "strain": eps, "stress": sig, "p": p, "epsp": epsp, "Ct": ct, "flag": flag, "n_iter": it, "resid": rs,
             "fail": fail}
 
 
@@ -56,9 +58,12 @@ def test_kernel_point_routine_equals_oracle_bit_for_bit(host, a):
     for k in range(1, 4):
         eps = synth.strain(n, a, 1.25e-2, k, 3)
         ref = ho.integrate(eps, st, props)
-        got = run(host, eps, st, props)
-        for key in ("flag", "n_iter", "fail", "stress", "p", "epsp", "Ct", "resid"):
-            assert np.array_equal(got[key], ref[key]), (key, k)
+        for split in (0, 1):
+            got = run(host, eps, st, props, split)
+            for key in ("flag", "n_iter", "fail", "stress", "p", "epsp", "Ct", "resid"):
+                assert np.array_equal(got[key], ref[key]), (key, k, split)
+        # the light pass hands over every plastic point and only a thin shell of elastic ones near the surface
+        assert ref["flag"].sum() <= got["candidates"] <= ref["flag"].sum() + 0.35 * n
         st = ss.advance(ref)
     assert 0.3 < ref["flag"].mean() < 0.95 and ref["fail"].sum() == 0
 
@@ -70,9 +75,10 @@ def test_kernel_point_routine_degenerate_and_extreme_inputs(host):
     eps = np.array(rows, dtype=float)
     st = ss.zero_state(len(rows))
     ref = ho.integrate(eps, st, props)
-    got = run(host, eps, st, props)
-    for key in ("flag", "n_iter", "fail"):
-        assert np.array_equal(got[key], ref[key]), key
-    for key in ("stress", "p", "epsp", "Ct", "resid"):
-        assert got[key].tobytes() == ref[key].tobytes(), key  # bitwise, NaN included
+    for split in (0, 1):
+        got = run(host, eps, st, props, split)
+        for key in ("flag", "n_iter", "fail"):
+            assert np.array_equal(got[key], ref[key]), key
+        for key in ("stress", "p", "epsp", "Ct", "resid"):
+            assert got[key].tobytes() == ref[key].tobytes(), key  # bitwise, NaN included
     assert ref["fail"][5] == 1 and ref["fail"].sum() == 1
