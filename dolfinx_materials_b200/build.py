@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 ]
 
 # translation units of the library (kernels live in the .cuh files they include)
-UNITS = ["dxm_api.cu", "dxm_fe_api.cu", "dxm_peaks.cu"]
+UNITS = ["dxm_api.cu", "dxm_hosford_api.cu", "dxm_fe_api.cu", "dxm_peaks.cu"]
 
 
 def _nvcc():

@@ -18,6 +18,8 @@ std::atomic<long long> g_launches{0};
 namespace {
 constexpr int64_t kChunk = 1 << 19;  // points per pipeline chunk on the host path
 const char* kPropNames[kNProp] = {"E", "nu", "sig0", "H", "sigu", "b"};
+constexpr double kHosSplitMaxPlastic = 0.6;  // Hosford: fused kernel above this plastic fraction (previous call)
+constexpr int kHosHeavyMinB = 3;             // Hosford local-solve kernel: resident CTAs per SM (A/B: DXM_HOS_MINB)
 constexpr bool kHostMirrorDefault = false;  // A/B on the B200 box: profiles/ (DXM_HOST_MIRROR overrides)
 }  // namespace
 
@@ -254,52 +256,29 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
   a.d_fail = h->d_fail;
   if (h->behaviour == DXM_HOSFORD_LINEAR) {
     a.hos_a = h->hos_a;
-    // Split launch (stream + queue the candidates | persistent local solves over the queue) for batches large enough
-    // to pay a second launch; the fused kernel below that and as the A/B reference (DXM_HOS_SPLIT=0|1).
+    a.hos_bound = hosford_bound(h->hos_a);
+    // Split launch (stream everything + queue the candidates | persistent local solves over the queue) or one fused
+    // kernel.  The split wins while a good part of the batch is elastic (its light pass runs at HBM speed and the
+    // local solves are packed into full warps); when most points are plastic the extra pass costs more than the
+    // packing gains (profiles/r01g_configs.json), and small batches do not pay a second launch: auto mode keys on
+    // the batch size and on the plastic fraction of the previous call.  DXM_HOS_SPLIT=0|1 forces either.
     const char* e = std::getenv("DXM_HOS_SPLIT");
-    const bool split = e ? std::atoi(e) != 0 : count >= 32768;
-    if (split) {
-      if (!h->hos_queue) {
-        CK(cudaMalloc(&h->hos_queue, sizeof(unsigned) * h->ld));
-        CK(cudaMalloc(&h->hos_count, sizeof(unsigned)));
-      }
-      a.hos_queue = h->hos_queue;
-      a.hos_count = h->hos_count;
-      CK(cudaMemsetAsync(h->hos_count, 0, sizeof(unsigned), h->stream));
-      const int64_t ntile = (count + 255) / 256;
-      const int grid = grid_for(nullptr, 256, 0, h->num_sms, ntile);
-      e = std::getenv("DXM_HOS_MINB");
-      const int minb = e ? std::atoi(e) : 3;
-#define DXM_HOS_SPLIT_LAUNCH(PP, DG)                                                                  \
-  do {                                                                                                \
-    dxm_hosford_light_kernel<PP, DG><<<grid, 256, 0, h->stream>>>(a);                                 \
-    LAUNCH_CHECK();                                                                                   \
-    if (minb == 4) dxm_hosford_heavy_kernel<PP, DG, 4><<<h->num_sms * 4, 128, 0, h->stream>>>(a);     \
-    else dxm_hosford_heavy_kernel<PP, DG, 3><<<h->num_sms * 3, 128, 0, h->stream>>>(a);               \
-    LAUNCH_CHECK();                                                                                   \
-  } while (0)
-      if (h->perpoint) {
-        if (h->diag) DXM_HOS_SPLIT_LAUNCH(true, true);
-        else DXM_HOS_SPLIT_LAUNCH(true, false);
-      } else {
-        if (h->diag) DXM_HOS_SPLIT_LAUNCH(false, true);
-        else DXM_HOS_SPLIT_LAUNCH(false, false);
-      }
-#undef DXM_HOS_SPLIT_LAUNCH
-      return 0;
+    bool split = count >= 32768;
+    if (split && h->prev_points > 0) split = (double)h->prev_plastic < kHosSplitMaxPlastic * (double)h->prev_points;
+    if (e) split = std::atoi(e) != 0;
+    if (split && !h->hos_queue) {
+      CK(cudaMalloc(&h->hos_queue, sizeof(unsigned) * h->ld));
+      CK(cudaMalloc(&h->hos_count, sizeof(unsigned)));
     }
-    const int block = 128;
-    const int64_t ntile = (count + block - 1) / block;
-    const int grid = grid_for(nullptr, block, 0, h->num_sms, ntile);
-    if (h->perpoint) {
-      if (h->diag) dxm_hosford_kernel<true, true><<<grid, block, 0, h->stream>>>(a);
-      else dxm_hosford_kernel<true, false><<<grid, block, 0, h->stream>>>(a);
-    } else {
-      if (h->diag) dxm_hosford_kernel<false, true><<<grid, block, 0, h->stream>>>(a);
-      else dxm_hosford_kernel<false, false><<<grid, block, 0, h->stream>>>(a);
-    }
-    LAUNCH_CHECK();
-    return 0;
+    if (split) CK(cudaMemsetAsync(h->hos_count, 0, sizeof(unsigned), h->stream));
+    a.hos_queue = h->hos_queue;
+    a.hos_count = h->hos_count;
+    e = std::getenv("DXM_HOS_MINB");
+    HosLaunch cfg{h->num_sms, h->stream, split, e ? std::atoi(e) : kHosHeavyMinB, kTilesPerCta};
+    int launches = 0;
+    const int rc = launch_hosford(a, cfg, &launches);
+    g_launches.fetch_add(launches);
+    return rc;
   }
   if (h->behaviour == DXM_J2_TABLE) {
     // 2 CTAs/SM: the segment walk keeps a few more values live than the closed forms

@@ -44,6 +44,7 @@ constexpr int kJacobiSweeps = 8;
 DXM_HD double hos_ipow2(double x, int k) {
   const double x2 = x * x;
   double y = x2;
+#pragma unroll
   for (int i = 1; i < k; ++i) y = y * x2;
   return y;
 }
@@ -86,6 +87,7 @@ DXM_HD void hos_eval(const double (&l)[3], int a, double inv_a, HosEval& e) {
 // sum_{k=0}^{a-2} x^k y^(a-2-k)
 DXM_HD double hos_divdiff(double x, double y, int a) {
   double t = 1.0, xp = 1.0;
+#pragma unroll
   for (int j = 1; j <= a - 2; ++j) {
     xp = xp * x;
     t = y * t + xp;
@@ -200,12 +202,16 @@ DXM_HD void hos_mandel_pair(const double (&V)[3][3], double (&m)[6]) {
 // One Gauss point.  ct21: the 21 unique tangent entries (j <= i, row-major upper triangle = sym6_packed order).
 // LIGHT == true: only the clearly elastic points are finished; for a candidate (the cheap rejection did not fire) the
 // routine returns true without touching the outputs and the caller hands the point to the full routine.
-template <bool LIGHT>
-DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, const double H, const int a,
-                          const double (&eps)[6], const double (&e_old)[6], const double (&s_old)[6],
+// AT > 0: the exponent as a compile-time constant (the power chains unroll into straight DMUL sequences; with a
+// run-time exponent 35 % of the executed instructions were loop bookkeeping, profiles/r01g_hosford_v2_*); AT == 0: a_rt.
+// bound: (2^(a-1)+1)^(1/a)/sqrt(3) (1 + 1e-9) >= sigma_eq / seq_Mises for every stress state (maximum at pure shear).
+template <bool LIGHT, int AT>
+DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, const double H, const int a_rt,
+                          const double bound, const double (&eps)[6], const double (&e_old)[6], const double (&s_old)[6],
                           const double p_old, const double (&ep_old)[6], double (&sig)[6], double& p_new,
                           double (&epsp)[6], double (&ct21)[21], bool& flag, int& n_iter, double& resid,
                           bool& fail) {
+  const int a = AT > 0 ? AT : a_rt;
   const double twomu = 2.0 * mu;
   const double threemu = 3.0 * mu;
   double de[6], st[6], s[6];
@@ -235,8 +241,8 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
   double dp = 0.0;
   double V[3][3];
   HosRes cur;
-  // sigma_eq <= max|s_i - s_j| <= 2/sqrt(3) seq_Mises: below that bound the point is surely elastic
-  const bool candidate = 1.1548 * seq > sy0;
+  // sigma_eq <= bound * seq_Mises: below that the point is surely elastic
+  const bool candidate = bound * seq > sy0;
   if (LIGHT && candidate) return true;
   if (!LIGHT && candidate) {
     const double am1 = (double)a - 1.0, inv_a = 1.0 / (double)a;
@@ -248,23 +254,24 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
     for (int k = 0; k < 3; ++k) xe[k] = l[k];
     // One evaluation site for the three uses of the residual (trial state, start point, line-search candidates):
     // stage 0 = yield check at the trial state, 1 = start point, 2 = line-search candidate of a Newton step.
+    double m_prev = 0.0;
     for (;;) {
-      HosRes nxt;
-      hos_residual(xe, dpe, l, twomu, sy0, H, a, inv_a, nxt);
+      // evaluated in place: once the step (dx, ddp) is formed only the merit value of the previous iterate is needed
+      hos_residual(xe, dpe, l, twomu, sy0, H, a, inv_a, cur);
       if (stage == 0) {
-        const double f = nxt.e.phi - sy0;
+        const double f = cur.e.phi - sy0;
         flag = f > 0.0;
         if (!flag) break;
         // start on the yield surface along the trial direction, dp from the J2-like estimate
         dpe = f / (threemu + H);
-        const double sc = (sy0 + H * dpe) / nxt.e.phi;
+        const double sc = (sy0 + H * dpe) / cur.e.phi;
 #pragma unroll
         for (int k = 0; k < 3; ++k) xe[k] = l[k] * sc;
         stage = 1;
         continue;
       }
       if (stage == 2) {
-        if (!(nxt.m2 < cur.m2 || ls == kHosfordLsMax)) {  // no decrease: halve the step
+        if (!(cur.m2 < m_prev || ls == kHosfordLsMax)) {  // no decrease: halve the step
           t = 0.5 * t;
           ++ls;
 #pragma unroll
@@ -278,7 +285,7 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
 #pragma unroll
       for (int k = 0; k < 3; ++k) x[k] = xe[k];
       dp = dpe;
-      cur = nxt;
+      m_prev = cur.m2;
       const double res = fmax(fmax(fabs(cur.rs[0]), fabs(cur.rs[1])), fmax(fabs(cur.rs[2]), fabs(cur.r4)));
       if (res <= tol) {
         resid = res;
@@ -379,14 +386,15 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
   return false;
 }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) && defined(DXM_HOSFORD_KERNELS)  // kernels: instantiated in dxm_hosford_api.cu only
 // SmallStrainArgs is shared with the J2 kernels (same SoA state layout); a.dsu / a.b are unused, a.hos_a = exponent,
-// a.hos_queue / a.hos_count = the candidate queue of the split launch.
+// a.hos_bound = candidate bound, a.hos_queue / a.hos_count = the candidate queue of the split launch.  Per-point
+// properties (a.pE != nullptr) and diagnostics (a.d_flag != nullptr) are run-time switches here: the kernels are
+// templated on the exponent only.
 struct HosPointIO {
   double eps[6], e_old[6], s_old[6], ep_old[6], p_old, lam, mu, sig0, H;
 };
 
-template <bool PERPOINT>
 __device__ __forceinline__ void hos_load(const SmallStrainArgs& a, int64_t i0, HosPointIO& io) {
   const int64_t ld = a.ld;
 #pragma unroll
@@ -402,7 +410,7 @@ __device__ __forceinline__ void hos_load(const SmallStrainArgs& a, int64_t i0, H
   io.mu = a.mu;
   io.sig0 = a.sig0;
   io.H = a.H;
-  if (PERPOINT) {
+  if (a.pE) {
     const double E = __ldcs(a.pE + i0), nu = __ldcs(a.pnu + i0);
     io.lam = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu);
     io.mu = E / 2.0 / (1.0 + nu);
@@ -411,7 +419,6 @@ __device__ __forceinline__ void hos_load(const SmallStrainArgs& a, int64_t i0, H
   }
 }
 
-template <bool DIAG>
 __device__ __forceinline__ void hos_finish(const SmallStrainArgs& a, int64_t i0, const double (&sig)[6], double p_new,
                                            const double (&epsp)[6], const double (&ct21)[21], bool flag, int n_iter,
                                            double resid, bool fail, PointStats& acc) {
@@ -421,7 +428,7 @@ __device__ __forceinline__ void hos_finish(const SmallStrainArgs& a, int64_t i0,
   acc.max_iter = n_iter > (int)acc.max_iter ? (unsigned)n_iter : acc.max_iter;
   acc.max_resid = resid > acc.max_resid ? resid : acc.max_resid;
   if (resid != resid) acc.max_resid = resid;
-  if (DIAG) {
+  if (a.d_flag) {
     a.d_flag[i0] = flag ? 1 : 0;
     a.d_iter[i0] = n_iter;
     a.d_resid[i0] = resid;
@@ -436,8 +443,8 @@ __device__ __forceinline__ void hos_finish(const SmallStrainArgs& a, int64_t i0,
   for (int r = 0; r < 21; ++r) __stcs(a.ct + (int64_t)r * ld + i0, ct21[r]);
 }
 
-// fused: every thread runs the full routine on its own point (small batches, A/B reference)
-template <bool PERPOINT, bool DIAG>
+// fused: every thread runs the full routine on its own point (small batches, mostly-plastic batches, A/B reference)
+template <int AT>
 __global__ void __launch_bounds__(128, 3) dxm_hosford_kernel(const SmallStrainArgs a) {
   const int64_t ntile = (a.count + blockDim.x - 1) / blockDim.x;
   PointStats acc;
@@ -446,19 +453,18 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_kernel(const SmallStrainAr
     if (loc >= a.count) continue;
     const int64_t i0 = a.start + loc;
     HosPointIO io;
-    hos_load<PERPOINT>(a, i0, io);
+    hos_load(a, i0, io);
     double sig[6], epsp[6], ct21[21], p_new, resid;
     bool flag, fail;
     int n_iter;
-    hosford_point<false>(io.lam, io.mu, io.sig0, io.H, a.hos_a, io.eps, io.e_old, io.s_old, io.p_old, io.ep_old, sig,
-                         p_new, epsp, ct21, flag, n_iter, resid, fail);
-    hos_finish<DIAG>(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
+    hosford_point<false, AT>(io.lam, io.mu, io.sig0, io.H, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old, io.p_old,
+                             io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
+    hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
   }
   block_reduce_stats(acc, a.stats);
 }
 
 // split, pass 1: stream all points, finish the clearly elastic ones, queue the candidates
-template <bool PERPOINT, bool DIAG>
 __global__ void __launch_bounds__(256, 3) dxm_hosford_light_kernel(const SmallStrainArgs a) {
   const int64_t ntile = (a.count + blockDim.x - 1) / blockDim.x;
   PointStats acc;
@@ -469,13 +475,13 @@ __global__ void __launch_bounds__(256, 3) dxm_hosford_light_kernel(const SmallSt
     if (live) {
       const int64_t i0 = a.start + loc;
       HosPointIO io;
-      hos_load<PERPOINT>(a, i0, io);
+      hos_load(a, i0, io);
       double sig[6], epsp[6], ct21[21], p_new, resid;
       bool flag, fail;
       int n_iter;
-      heavy = hosford_point<true>(io.lam, io.mu, io.sig0, io.H, a.hos_a, io.eps, io.e_old, io.s_old, io.p_old,
-                                  io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
-      if (!heavy) hos_finish<DIAG>(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
+      heavy = hosford_point<true, 0>(io.lam, io.mu, io.sig0, io.H, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old,
+                                     io.p_old, io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
+      if (!heavy) hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
     }
     // warp-aggregated append: one atomic per warp, lanes keep their order (neighbours stay neighbours in the queue)
     const unsigned bal = __ballot_sync(0xffffffffu, heavy);
@@ -491,23 +497,37 @@ __global__ void __launch_bounds__(256, 3) dxm_hosford_light_kernel(const SmallSt
 }
 
 // split, pass 2: persistent grid over the queue, every lane holds a candidate point
-template <bool PERPOINT, bool DIAG, int MINB>
+template <int AT, int MINB>
 __global__ void __launch_bounds__(128, MINB) dxm_hosford_heavy_kernel(const SmallStrainArgs a) {
   const unsigned total = *a.hos_count;
   PointStats acc;
   for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
     const int64_t i0 = a.start + (int64_t)a.hos_queue[q];
     HosPointIO io;
-    hos_load<PERPOINT>(a, i0, io);
+    hos_load(a, i0, io);
     double sig[6], epsp[6], ct21[21], p_new, resid;
     bool flag, fail;
     int n_iter;
-    hosford_point<false>(io.lam, io.mu, io.sig0, io.H, a.hos_a, io.eps, io.e_old, io.s_old, io.p_old, io.ep_old, sig,
-                         p_new, epsp, ct21, flag, n_iter, resid, fail);
-    hos_finish<DIAG>(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
+    hosford_point<false, AT>(io.lam, io.mu, io.sig0, io.H, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old, io.p_old,
+                             io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
+    hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
   }
   block_reduce_stats(acc, a.stats);
 }
+
+#endif  // kernels
+
+#ifdef __CUDACC__
+// host side of the Hosford launches (dxm_hosford_api.cu)
+struct HosLaunch {
+  int num_sms;
+  cudaStream_t stream;
+  bool split;  // light + queue + heavy instead of the fused kernel
+  int minb;    // heavy kernel: resident CTAs per SM the register allocation targets (3 | 4)
+  int tiles_per_cta;
+};
+int launch_hosford(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches);
+double hosford_bound(int a);
 #endif  // __CUDACC__
 
 #undef DXM_HD

@@ -1,0 +1,54 @@
+// Launch side of the Hosford behaviour (its own translation unit: the local-solve kernels are large and are
+// instantiated once per supported compile-time exponent).
+#define DXM_HOSFORD_KERNELS
+#include "dxm_internal.cuh"
+#include "dxm_hosford.cuh"
+
+namespace dxm {
+
+// sup over all stress states of sigma_eq(Hosford, a) / seq(von Mises) = (2^(a-1) + 1)^(1/a) / sqrt(3), reached in
+// pure shear (1 for a = 2 and a = 4, -> 2/sqrt(3) = Tresca as a -> inf); tests/test_oracle_hosford.py scans it.
+double hosford_bound(int a) {
+  return std::pow(std::pow(2.0, (double)(a - 1)) + 1.0, 1.0 / (double)a) / std::sqrt(3.0) * (1.0 + 1e-9);
+}
+
+namespace {
+template <int AT>
+int launch_at(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches) {
+  if (cfg.split) {
+    const int64_t ntile = (a.count + 255) / 256;
+    int64_t grid = (ntile + cfg.tiles_per_cta - 1) / cfg.tiles_per_cta;
+    if (grid < 1) grid = 1;
+    dxm_hosford_light_kernel<<<(unsigned)grid, 256, 0, cfg.stream>>>(a);
+    ++*launches;
+    CK(cudaGetLastError());
+    if (cfg.minb == 4)
+      dxm_hosford_heavy_kernel<AT, 4><<<cfg.num_sms * 4, 128, 0, cfg.stream>>>(a);
+    else
+      dxm_hosford_heavy_kernel<AT, 3><<<cfg.num_sms * 3, 128, 0, cfg.stream>>>(a);
+    ++*launches;
+    CK(cudaGetLastError());
+    return 0;
+  }
+  const int64_t ntile = (a.count + 127) / 128;
+  int64_t grid = (ntile + cfg.tiles_per_cta - 1) / cfg.tiles_per_cta;
+  if (grid < 1) grid = 1;
+  dxm_hosford_kernel<AT><<<(unsigned)grid, 128, 0, cfg.stream>>>(a);
+  ++*launches;
+  CK(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+// exponents with an unrolled instantiation: 6 and 8 (the usual bcc / fcc fits) and 10 (the reference demo); any other
+// even exponent runs the generic loops -- same operation order, same bits
+int launch_hosford(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches) {
+  switch (a.hos_a) {
+    case 6: return launch_at<6>(a, cfg, launches);
+    case 8: return launch_at<8>(a, cfg, launches);
+    case 10: return launch_at<10>(a, cfg, launches);
+    default: return launch_at<0>(a, cfg, launches);
+  }
+}
+
+}  // namespace dxm

@@ -45,6 +45,7 @@ struct SmallStrainArgs {
   const double* table;
   int ntab;
   int hos_a;  // DXM_HOSFORD_LINEAR: exponent of the Hosford criterion (even integer)
+  double hos_bound;  // ... and sup sigma_eq / seq_Mises (1 + 1e-9): points below it are finished without a local solve
   unsigned* hos_queue;  // split launch: local indices of the candidate points, [count]
   unsigned* hos_count;  // ... and how many there are
   StatSlot* stats;

@@ -17,7 +17,7 @@
  * bcc/fcc fits, 10 the demo), which makes every power a product chain and the tangent's spectral terms exact.
  *
  * Algorithm (operation order == csrc/dxm_hosford.cuh, compiled with -ffp-contract=off / -fmad=false):
- *   trial stress as in the J2 update; cheap rejection sigma_eq <= max|s_i - s_j| <= 2/sqrt(3) seq_Mises;
+ *   trial stress as in the J2 update; cheap rejection sigma_eq <= (2^(a-1)+1)^(1/a)/sqrt(3) seq_Mises (pure shear);
  *   cyclic Jacobi eigen-decomposition of the trial deviator (+, -, *, /, sqrt only; the equivalent stress costs two
  *   divisions per evaluation: the a-th root is a division-free Newton on q^(-1/a)); isotropy keeps the principal
  *   axes, so the return map is a 4-unknown Newton (3 principal deviatoric stresses + dp) started from the radially
@@ -169,6 +169,7 @@ static void sym3_apply(const double Cf[6], double idet, const double v[3], doubl
 /* props: E, nu, sig0 (R0), H scalars or per point (pp/per as in dxm_oracle.c, entries 0..3); a even integer >= 2 */
 void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double* s_old, const double* p_old_a,
                  const double* ep_old, const double* const* pp, const int* per, int a, int newton_cap, double rtol,
+                 double bound,
                  double* sig_o, double* p_o, double* epsp_o, double* ct_o, uint8_t* flag_o, int32_t* iter_o,
                  double* resid_o, uint8_t* fail_o) {
   for (int64_t pt = 0; pt < n; ++pt) {
@@ -197,7 +198,7 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
     double dp = 0.0, resid = 0.0;
     double l[3], Q[3][3];
     hres_t cur;
-    if (1.1548 * seq > sy0) { /* sigma_eq <= max |s_i - s_j| <= 2/sqrt(3) seq: otherwise surely elastic */
+    if (bound * seq > sy0) { /* sigma_eq <= bound * seq (bound >= (2^(a-1)+1)^(1/a)/sqrt(3)): otherwise surely elastic */
       jacobi3(s, l, Q);
       hosford_eval(l, a, inv_a, &cur.phi, &cur.iphi, cur.n, cur.h, cur.u);
       const double f = cur.phi - sy0;

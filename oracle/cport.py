@@ -126,7 +126,9 @@ def hosford(eps, state, props, newton_cap=25, rtol=1e-12):
     a = int(props["a"])
     if a < 2 or a % 2 or a > 64 or a != props["a"]:
         raise ValueError("Hosford exponent: an even integer in [2, 64]")
-    keep, ptrs, pers = _props({k: v for k, v in props.items() if k != "a"}, n)
+    # sup sigma_eq / seq_Mises (pure shear), with a safety margin: points below it skip the eigen-decomposition
+    bound = float(props.get("bound", (2.0 ** (a - 1) + 1.0) ** (1.0 / a) / np.sqrt(3.0) * (1.0 + 1e-9)))
+    keep, ptrs, pers = _props({k: v for k, v in props.items() if k not in ("a", "bound")}, n)
     sig, p, epsp, Ct = np.empty((n, 6)), np.empty(n), np.empty((n, 6)), np.empty((n, 6, 6))
     flag, fail = np.empty(n, np.uint8), np.empty(n, np.uint8)
     n_iter, resid = np.empty(n, np.int32), np.empty(n)
@@ -134,7 +136,7 @@ def hosford(eps, state, props, newton_cap=25, rtol=1e-12):
     def call(lo, hi):
         lib.dxo_hosford(ctypes.c_int64(hi - lo), _c(eps, lo), _c(e_old, lo), _c(s_old, lo), _c(p_old, lo),
                         _c(ep_old, lo), ptrs(lo), pers, ctypes.c_int(a), ctypes.c_int(newton_cap), ctypes.c_double(rtol),
-                        _c(sig, lo), _c(p, lo), _c(epsp, lo), _c(Ct, lo), _c(flag, lo), _c(n_iter, lo),
+                        ctypes.c_double(bound), _c(sig, lo), _c(p, lo), _c(epsp, lo), _c(Ct, lo), _c(flag, lo), _c(n_iter, lo),
                         _c(resid, lo), _c(fail, lo))
 
     _run_blocks(n, call)

@@ -3,10 +3,35 @@
 // and compared bit for bit with the oracle -- without a GPU.  Test scaffolding only: nothing in the product calls this.
 #include "../dolfinx_materials_b200/csrc/dxm_hosford.cuh"
 
+namespace {
+template <int AT>
+void run(int64_t n, const double* eps, const double* e_old, const double* s_old, const double* p_old,
+         const double* ep_old, double E, double nu, double sig0, double H, int a, double bound, double* sig, double* p,
+         double* epsp, double* ct, uint8_t* flag, int32_t* n_iter, double* resid, uint8_t* fail, int split,
+         int64_t* n_candidates);
+}
+
+// same dispatch as launch_hosford (dxm_hosford_api.cu): unrolled instantiations for a = 6, 8, 10, generic loops else
 extern "C" void hosford_host(int64_t n, const double* eps, const double* e_old, const double* s_old, const double* p_old,
-                             const double* ep_old, double E, double nu, double sig0, double H, int a, double* sig,
-                             double* p, double* epsp, double* ct, uint8_t* flag, int32_t* n_iter, double* resid,
-                             uint8_t* fail, int split, int64_t* n_candidates) {
+                             const double* ep_old, double E, double nu, double sig0, double H, int a, double bound,
+                             double* sig, double* p, double* epsp, double* ct, uint8_t* flag, int32_t* n_iter,
+                             double* resid, uint8_t* fail, int split, int64_t* n_candidates, int force_generic) {
+#define DXM_ARGS n, eps, e_old, s_old, p_old, ep_old, E, nu, sig0, H, a, bound, sig, p, epsp, ct, flag, n_iter, resid, fail, split, n_candidates
+  if (force_generic) return run<0>(DXM_ARGS);
+  switch (a) {
+    case 6: return run<6>(DXM_ARGS);
+    case 8: return run<8>(DXM_ARGS);
+    case 10: return run<10>(DXM_ARGS);
+    default: return run<0>(DXM_ARGS);
+  }
+}
+
+namespace {
+template <int AT>
+void run(int64_t n, const double* eps, const double* e_old, const double* s_old, const double* p_old,
+         const double* ep_old, double E, double nu, double sig0, double H, int a, double bound, double* sig, double* p,
+         double* epsp, double* ct, uint8_t* flag, int32_t* n_iter, double* resid, uint8_t* fail, int split,
+         int64_t* n_candidates) {
   const double lam = E * nu / (1 + nu) / (1 - 2 * nu);
   const double mu = E / 2 / (1 + nu);
   for (int64_t i = 0; i < n; ++i) {
@@ -22,10 +47,10 @@ extern "C" void hosford_host(int64_t n, const double* eps, const double* e_old, 
     // split != 0 replays the two-kernel launch: the light pass finishes the clearly elastic points and reports the
     // candidates, which the full routine then recomputes from scratch (dxm_hosford_light_kernel / _heavy_kernel)
     bool heavy = true;
-    if (split) heavy = dxm::hosford_point<true>(lam, mu, sig0, H, a, e1, e0, s0, p_old[i], ep0, so, pn, epo, ct21, fl, it, rs, fa);
+    if (split) heavy = dxm::hosford_point<true, 0>(lam, mu, sig0, H, a, bound, e1, e0, s0, p_old[i], ep0, so, pn, epo, ct21, fl, it, rs, fa);
     if (heavy) {
       if (split) ++*n_candidates;
-      dxm::hosford_point<false>(lam, mu, sig0, H, a, e1, e0, s0, p_old[i], ep0, so, pn, epo, ct21, fl, it, rs, fa);
+      dxm::hosford_point<false, AT>(lam, mu, sig0, H, a, bound, e1, e0, s0, p_old[i], ep0, so, pn, epo, ct21, fl, it, rs, fa);
     }
     for (int c = 0; c < 6; ++c) {
       sig[i * 6 + c] = so[c];
@@ -39,3 +64,4 @@ extern "C" void hosford_host(int64_t n, const double* eps, const double* e_old, 
     fail[i] = fa;
   }
 }
+}  // namespace

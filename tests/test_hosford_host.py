@@ -33,7 +33,7 @@ def host():
     return ctypes.CDLL(LIB)
 
 
-def run(lib, eps, st, props, split=0):
+def run(lib, eps, st, props, split=0, generic=0):
     n = eps.shape[0]
     c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
     eps = np.ascontiguousarray(eps)
@@ -42,15 +42,17 @@ def run(lib, eps, st, props, split=0):
     sig, p, epsp, ct = np.empty((n, 6)), np.empty(n), np.empty((n, 6)), np.empty((n, 6, 6))
     flag, fail, it, rs = np.empty(n, np.uint8), np.empty(n, np.uint8), np.empty(n, np.int32), np.empty(n)
     ncand = ctypes.c_int64(0)
+    a = props["a"]
+    bound = (2.0 ** (a - 1) + 1.0) ** (1.0 / a) / np.sqrt(3.0) * (1.0 + 1e-9)  # hosford_bound(), dxm_hosford_api.cu
     lib.hosford_host(ctypes.c_int64(n), c(eps), c(e_old), c(s_old), c(p_old), c(ep_old), ctypes.c_double(props["E"]),
                      ctypes.c_double(props["nu"]), ctypes.c_double(props["sig0"]), ctypes.c_double(props["H"]),
-                     ctypes.c_int(props["a"]), c(sig), c(p), c(epsp), c(ct), c(flag), c(it), c(rs), c(fail),
-                     ctypes.c_int(split), ctypes.byref(ncand))
+                     ctypes.c_int(props["a"]), ctypes.c_double(bound), c(sig), c(p), c(epsp), c(ct), c(flag), c(it), c(rs),
+                     c(fail), ctypes.c_int(split), ctypes.byref(ncand), ctypes.c_int(generic))
     return {"candidates": ncand.value, "strain": eps, "stress": sig, "p": p, "epsp": epsp, "Ct": ct, "flag": flag, "n_iter": it, "resid": rs,
             "fail": fail}
 
 
-@pytest.mark.parametrize("a", [2, 6, 10, 20])
+@pytest.mark.parametrize("a", [2, 4, 6, 8, 10, 20])
 def test_kernel_point_routine_equals_oracle_bit_for_bit(host, a):
     props = dict(E=70e3, nu=0.3, sig0=200.0, H=10.0, a=a)
     n = 20000
@@ -58,12 +60,12 @@ def test_kernel_point_routine_equals_oracle_bit_for_bit(host, a):
     for k in range(1, 4):
         eps = synth.strain(n, a, 1.25e-2, k, 3)
         ref = ho.integrate(eps, st, props)
-        for split in (0, 1):
-            got = run(host, eps, st, props, split)
+        for split, generic in ((0, 0), (1, 0), (1, 1)):  # unrolled-exponent and generic instantiations
+            got = run(host, eps, st, props, split, generic)
             for key in ("flag", "n_iter", "fail", "stress", "p", "epsp", "Ct", "resid"):
-                assert np.array_equal(got[key], ref[key]), (key, k, split)
+                assert np.array_equal(got[key], ref[key]), (key, k, split, generic)
         # the light pass hands over every plastic point and only a thin shell of elastic ones near the surface
-        assert ref["flag"].sum() <= got["candidates"] <= ref["flag"].sum() + 0.35 * n
+        assert ref["flag"].sum() <= got["candidates"] <= ref["flag"].sum() + 0.2 * n
         st = ss.advance(ref)
     assert 0.3 < ref["flag"].mean() < 0.95 and ref["fail"].sum() == 0
 

@@ -161,3 +161,22 @@ def test_per_point_properties_match_uniform_runs():
             sel = (E == e) & (s0 == s)
             uni = ho.integrate(eps[sel], ss.zero_state(int(sel.sum())), dict(E=e, nu=0.3, sig0=s, H=10.0, a=10))
             assert np.array_equal(uni["stress"], mixed["stress"][sel]) and np.array_equal(uni["Ct"], mixed["Ct"][sel])
+
+
+@pytest.mark.parametrize("a", [2, 4, 6, 8, 10, 20, 64])
+def test_candidate_bound_is_the_pure_shear_ratio(a):
+    """sup sigma_eq / seq_Mises over all stress states = (2^(a-1)+1)^(1/a)/sqrt(3) (pure shear): the kernels finish points
+    below bound * seq_Mises <= sigma_Y without an eigen-decomposition, so the bound must never be exceeded."""
+    th = np.linspace(0.0, 2 * np.pi, 20001)
+    s = np.stack([2.0 / 3.0 * np.cos(th - 2 * np.pi * k / 3) for k in range(3)], axis=1)  # unit von Mises stress
+    v = np.concatenate([s, np.zeros_like(s)], axis=1)
+    ratio = np.array([ho.sigma_eq(x, a) for x in v])
+    bound = (2.0 ** (a - 1) + 1.0) ** (1.0 / a) / np.sqrt(3.0)
+    assert ratio.max() <= bound * (1 + 1e-12) and ratio.max() >= bound * (1 - 1e-6)
+    # a deliberately useless bound (everything is a candidate) gives the same bits as the default one
+    n = 3000
+    eps = synth.strain(n, 3, 8e-3, 1, 1)
+    tight = ho.integrate(eps, ss.zero_state(n), dict(DEMO, a=a))
+    loose = ho.integrate(eps, ss.zero_state(n), dict(DEMO, a=a, bound=1e30))
+    for key in ("stress", "p", "epsp", "Ct", "flag", "n_iter", "resid", "fail"):
+        assert np.array_equal(tight[key], loose[key]), key
