@@ -18,8 +18,7 @@ std::atomic<long long> g_launches{0};
 namespace {
 constexpr int64_t kChunk = 1 << 19;  // points per pipeline chunk on the host path
 const char* kPropNames[kNProp] = {"E", "nu", "sig0", "H", "sigu", "b"};
-constexpr double kHosSplitMaxPlastic = 0.6;  // Hosford: fused kernel above this plastic fraction (previous call)
-constexpr int kHosHeavyMinB = 3;             // Hosford local-solve kernel: resident CTAs per SM (A/B: DXM_HOS_MINB)
+constexpr double kHosSplitMaxPlastic = 0.45;  // Hosford: fused kernel above this plastic fraction (previous call)
 constexpr bool kHostMirrorDefault = false;  // A/B on the B200 box: profiles/ (DXM_HOST_MIRROR overrides)
 }  // namespace
 
@@ -260,7 +259,7 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
     // Split launch (stream everything + queue the candidates | persistent local solves over the queue) or one fused
     // kernel.  The split wins while a good part of the batch is elastic (its light pass runs at HBM speed and the
     // local solves are packed into full warps); when most points are plastic the extra pass costs more than the
-    // packing gains (profiles/r01g_configs.json), and small batches do not pay a second launch: auto mode keys on
+    // packing gains (crossover at 40-50 % plastic, profiles/r01g_configs.json), and small batches do not pay a second launch: auto mode keys on
     // the batch size and on the plastic fraction of the previous call.  DXM_HOS_SPLIT=0|1 forces either.
     const char* e = std::getenv("DXM_HOS_SPLIT");
     bool split = count >= 32768;
@@ -273,8 +272,7 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
     if (split) CK(cudaMemsetAsync(h->hos_count, 0, sizeof(unsigned), h->stream));
     a.hos_queue = h->hos_queue;
     a.hos_count = h->hos_count;
-    e = std::getenv("DXM_HOS_MINB");
-    HosLaunch cfg{h->num_sms, h->stream, split, e ? std::atoi(e) : kHosHeavyMinB, kTilesPerCta};
+    HosLaunch cfg{h->num_sms, h->stream, split, kTilesPerCta};
     int launches = 0;
     const int rc = launch_hosford(a, cfg, &launches);
     g_launches.fetch_add(launches);

@@ -523,7 +523,6 @@ struct HosLaunch {
   int num_sms;
   cudaStream_t stream;
   bool split;  // light + queue + heavy instead of the fused kernel
-  int minb;    // heavy kernel: resident CTAs per SM the register allocation targets (3 | 4)
   int tiles_per_cta;
 };
 int launch_hosford(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches);

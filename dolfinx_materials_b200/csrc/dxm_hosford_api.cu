@@ -22,10 +22,8 @@ int launch_at(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches) {
     dxm_hosford_light_kernel<<<(unsigned)grid, 256, 0, cfg.stream>>>(a);
     ++*launches;
     CK(cudaGetLastError());
-    if (cfg.minb == 4)
-      dxm_hosford_heavy_kernel<AT, 4><<<cfg.num_sms * 4, 128, 0, cfg.stream>>>(a);
-    else
-      dxm_hosford_heavy_kernel<AT, 3><<<cfg.num_sms * 3, 128, 0, cfg.stream>>>(a);
+    // 3 resident CTAs per SM (168 registers); 4 (128 registers, 3x the spills) measured 0-20 % slower (profiles/r01g_configs.json)
+    dxm_hosford_heavy_kernel<AT, 3><<<cfg.num_sms * 3, 128, 0, cfg.stream>>>(a);
     ++*launches;
     CK(cudaGetLastError());
     return 0;

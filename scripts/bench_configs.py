@@ -89,16 +89,16 @@ out.append(dict(cfg="cfg4 faithful: matrix Hosford(a=10)+linear handle, inclusio
                 hosford_plastic=a.n_plastic / na, hosford_max_iter=a.max_iter, hosford_fail=a.n_fail))
 del mh, mb
 # Hosford kernel alone over the plastic fraction (amplitude sweep), n = 1e7: fused kernel vs split launch (light pass +
-# candidate queue + persistent local solves), the latter at 3 and 4 resident CTAs per SM (168 / 128 registers)
+# candidate queue + persistent local solves), (r01g also ran the local-solve kernel at 4 resident CTAs per SM / 128 registers: 0-20 % slower)
 mh = jm.CUDAMaterial(jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.LinearHardening(sig0=200.0, H=10.0)))
 mh.set_data_manager(n)
-for split, minb in (("0", "3"), ("1", "3"), ("1", "4")):
-    os.environ["DXM_HOS_SPLIT"] = split; os.environ["DXM_HOS_MINB"] = minb
+for split, minb in (("0", "3"), ("1", "3")):
+    os.environ["DXM_HOS_SPLIT"] = split
     for amp in (2e-3, 4e-3, 8e-3, 1.25e-2, 5e-2):
         mh.data_manager.revert(); mh.synth_gradients(0, amp, 1, 1)
         ms, s = timeit(mh)
         out.append(dict(cfg=f"Hosford a=10 alone, virgin state, amp {amp}", split=int(split), minb=int(minb), n=n, ms=ms, gps=n / ms * 1e3,
                         gbs_moved=472 * n / ms / 1e6, plastic=s.n_plastic / n, max_iter=s.max_iter, fail=s.n_fail))
-del os.environ["DXM_HOS_SPLIT"], os.environ["DXM_HOS_MINB"]
+del os.environ["DXM_HOS_SPLIT"]
 print(json.dumps(out, indent=1))
 os.makedirs("gpurun_out", exist_ok=True); json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
