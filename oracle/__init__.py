@@ -30,6 +30,11 @@ PARITY STATUS
   exactly by the complex-step method -- the definition of the reference's jacfwd tangent
   (``tests/test_oracle_exact_derivative.py``: stress to 1e-11, tangent to 1e-10).
 
+* Hosford (``oracle/hosford.py``, plain C): **parity unpinned** against MFront (TFEL/MGIS absent, generated code not
+  in the tree); restates ``demos/multimaterials/IsotropicPlasticHosfordFlowLinear.mfront`` and is checked against an
+  independent statement of the implicit system, finite-difference tangents, a = 2 == the J2 oracle and the
+  criterion's known yield points (``tests/test_oracle_hosford.py``).
+
 Canonical arithmetic
 --------------------
 Every function is written component-wise with an explicit operation order and uses only

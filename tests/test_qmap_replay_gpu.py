@@ -93,3 +93,49 @@ def test_fefp_map_with_initial_state_update(jm):
         st = fefp.advance(ref)
         assert np.array_equal(_get_vals(qmap.internal_state_variables["be_bar"]), st["be_bar"])
     assert ref["flag"].mean() > 0.2
+
+
+def test_multimaterial_hosford_matrix_and_voce_inclusions(jm):
+    """The reference's multi-material set-up (demos/multimaterials/multimaterials.py:245-273): the matrix cells carry the
+    Hosford (a = 10) + linear hardening law that the demo takes from MFront, the inclusion cells J2 + Voce, each
+    through its own map on a cell subset; load stepping with advance().  Stresses and tangents of both maps equal the
+    oracles on their own points, and add up to a field with disjoint supports."""
+    from oracle import hosford as ho
+
+    ncell, nqp = 400, 1  # P1 triangles, one point per cell (multimaterials.py:264)
+    matrix_props = dict(E=70e3, nu=0.3, sig0=200.0, H=10.0, a=10)  # multimaterials.py:245-254
+    incl_props = dict(E=90e3, nu=0.25, sig0=200.0, sigu=300.0, b=10.0)  # multimaterials.py:256-261
+    cells = np.arange(ncell)
+    incl = cells[(cells // 20) % 3 == 1]  # blocks of inclusion cells
+    matrix = np.setdiff1d(cells, incl)
+    m1 = jm.CUDAMaterial(jm.GeneralIsotropicHardening(
+        elasticity=jm.LinearElasticIsotropic(E=matrix_props["E"], nu=matrix_props["nu"]),
+        yield_stress=jm.LinearHardening(sig0=matrix_props["sig0"], H=matrix_props["H"]),
+        equivalent_stress=jm.Hosford(a=10)))
+    m2 = jm.CUDAMaterial(jm.vonMisesIsotropicHardening(
+        elasticity=jm.LinearElasticIsotropic(E=incl_props["E"], nu=incl_props["nu"]),
+        yield_stress=jm.VoceHardening(sig0=incl_props["sig0"], sigu=incl_props["sigu"], b=incl_props["b"])))
+    q1 = QuadratureMapReplay(ncell, nqp, m1, cells=matrix)
+    q2 = QuadratureMapReplay(ncell, nqp, m2, cells=incl)
+    zero = np.zeros((ncell * nqp, 6))
+    for q in (q1, q2):
+        q.register_gradient("strain", zero)
+        q.update()
+    st1, st2 = ss.zero_state(len(matrix)), ss.zero_state(len(incl))
+    for step in range(1, 4):
+        eps = synth.strain(ncell * nqp, 8, 1.25e-2, step, 3)
+        for q in (q1, q2):
+            q.set_gradient_values("strain", eps)
+            q.update()
+        r1 = ho.integrate(eps[matrix], st1, matrix_props)
+        r2 = ss.integrate(eps[incl], st2, incl_props)
+        s1, s2 = _get_vals(q1.fluxes["stress"]), _get_vals(q2.fluxes["stress"])
+        assert np.array_equal(s1[matrix], r1["stress"]) and np.array_equal(s2[incl], r2["stress"])
+        assert np.count_nonzero(s1[incl]) == 0 and np.count_nonzero(s2[matrix]) == 0
+        assert np.array_equal(q1.jacobian_flatten.array.reshape(-1, 36)[matrix], r1["Ct"].reshape(-1, 36))
+        assert np.array_equal(q2.jacobian_flatten.array.reshape(-1, 36)[incl], r2["Ct"].reshape(-1, 36))
+        for q in (q1, q2):
+            q.advance()
+        st1, st2 = ss.advance(r1), ss.advance(r2)
+        assert np.array_equal(_get_vals(q1.internal_state_variables["p"])[matrix, 0], st1["p"])
+    assert r1["flag"].mean() > 0.3 and r2["flag"].mean() > 0.3
