@@ -21,7 +21,8 @@ all-reduce of the failure / active-set counts and residual maximum.
            MEASURED_PEAKS.json hbm_gbs.  The kernel stores each unique entry of the symmetric tangent once
            (472 B / point of DRAM traffic, `traffic`), so `frac` can exceed 1; `moved_frac` is the fraction of the
            HBM peak the bytes actually moved account for.
-`cpu_baseline`: the numpy oracle timed on the box's host cores on a bounded sample of the same workload.
+`cpu_baseline`: the numpy oracle timed on the box's host cores on a bounded sample of the same workload
+           (`c_port`: the plain-C oracle on the same cores, for scale).
 """
 
 import argparse
@@ -137,6 +138,31 @@ class CpuArm:
             p.join(timeout=10)
 
 
+def c_port_rate(cores, points_per_core=400_000, passes=3):
+    """The plain-C restatement of the same update (oracle/c, gcc -O2 -ffp-contract=off, bit-identical to the numpy
+    oracle) on `cores` threads: one pass at increment KINC from the state after KINC - 1 increments.  Reported next
+    to the numpy figure because a compiled CPU path (the reference's JAX-CPU back-end is one) sits between the two."""
+    from oracle import cport
+    from oracle import small_strain as ss
+    from oracle import synth
+
+    n = points_per_core * cores
+    cport.set_threads(cores)
+    st = ss.zero_state(n)
+    for k in range(1, KINC):
+        st = ss.advance(cport.small_strain(synth.strain(n, SEED, AMP, k, KINC), st, PROPS))
+    eps = synth.strain(n, SEED, AMP, KINC, KINC)
+    best = None
+    for _ in range(passes):
+        t0 = time.perf_counter()
+        out = cport.small_strain(eps, st, PROPS)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": n / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n} points of the same workload, plain-C oracle on {cores} threads, best of {passes} passes at increment {KINC}/{KINC}",
+            "sample_plastic_fraction": float(out["flag"].mean())}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -158,6 +184,10 @@ def run_reference(args):
         t += w
         pts += p
     arm.close()
+    try:
+        c_port = c_port_rate(cores)
+    except Exception as e:  # noqa: BLE001 - the C figure is an extra, the numpy arm is the line's value
+        c_port = {"unavailable": str(e)[:200]}
     value = pts / t
     sample = f"{pts // args.steps} points/step ({cores} procs x {cpc} chunks x {arm.chunk}), numpy oracle, increment {KINC}/{KINC} from the state after {KINC - 1} increments"
     line = {
@@ -175,7 +205,7 @@ def run_reference(args):
         "dtype": "f64",
         "data": "synthetic",
         "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "c_port": c_port},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference CPU path = numpy port of the reference algorithm (oracle/); the reference's own jaxmat/JAX back-end is not installable offline (DESIGN.md)",
@@ -430,6 +460,10 @@ def run_ours(args):
             "sample": f"first {pts} points of the same workload ({cores} procs x {cpc} chunks x {arm.chunk}), numpy oracle, one pass at increment {KINC}/{KINC}",
             "sample_plastic_fraction": sum(r[0] for r in res) / pts,
         }
+        try:
+            cpu["c_port"] = c_port_rate(cores)
+        except Exception as e:  # noqa: BLE001
+            cpu["c_port"] = {"unavailable": str(e)[:200]}
 
     if rank == 0:
         peak, peak_src = load_peaks()

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import dolfinx_materials_b200 as jm
 from dolfinx_materials_b200 import build
-from oracle import fefp, small_strain as ss, synth
+from oracle import fefp, hosford as ho, small_strain as ss, synth
 build.build_library()
 el = jm.LinearElasticIsotropic(E=70e3, nu=0.3)
 out = dict(fmad=os.environ.get("DXM_FMAD", "0"))
@@ -28,4 +28,18 @@ for k in range(1, 5):
     flag, n_iter, _, _ = fm.diagnostics(); fm.data_manager.update(); fst = fefp.advance(ref)
 out["fefp"] = dict(PK1=rel(P, ref["PK1"]), Ct=rel(Ct, ref["Ct"]), p=rel(isv[:, 0], ref["p"]),
                    flag_mismatch=int((flag != ref["flag"]).sum()), iter_mismatch=int((n_iter != ref["n_iter"]).sum()))
+# Hosford (a = 10): the local Newton's line search compares merit values, so a handful of iteration counts may move
+H = dict(E=70e3, nu=0.3, sig0=200.0, H=10.0, a=10)
+hm = jm.CUDAMaterial(jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.LinearHardening(sig0=200.0, H=10.0)))
+hm.set_data_manager(n); hm.enable_diagnostics(); hst = ss.zero_state(n)
+for k in range(1, 5):
+    eps = synth.strain(n, 0, 1.25e-2, k, 4); flux, isv, Ct = hm.integrate(eps); ref = ho.integrate(eps, hst, H)
+    flag, n_iter, _, _ = hm.diagnostics(); hm.data_manager.update(); hst = ss.advance(ref)
+out["hosford"] = dict(stress=rel(flux, ref["stress"]), Ct=rel(Ct, ref["Ct"]), p=rel(isv[:, 0], ref["p"]),
+                      flag_mismatch=int((flag != ref["flag"]).sum()), iter_mismatch=int((n_iter != ref["n_iter"]).sum()))
+n2 = 4_000_000
+hb = jm.CUDAMaterial(hm.behavior); hb.set_data_manager(n2); hb.synth_gradients(0, 1.25e-2, 1, 1)
+os.environ["DXM_HOS_SPLIT"] = "0"
+ts = sorted(hb.integrate_resident().kernel_ms for _ in range(7))
+out["hosford_fused_ms_4e6"] = ts[3]; out["hosford_plastic"] = hb.last_stats.n_plastic / n2
 print(json.dumps(out))
