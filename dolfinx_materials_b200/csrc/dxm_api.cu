@@ -18,7 +18,7 @@ std::atomic<long long> g_launches{0};
 namespace {
 constexpr int64_t kChunk = 1 << 19;  // points per pipeline chunk on the host path
 const char* kPropNames[kNProp] = {"E", "nu", "sig0", "H", "sigu", "b"};
-constexpr double kHosSplitMaxPlastic = 0.45;  // Hosford: fused kernel above this plastic fraction (previous call)
+constexpr double kHosSplitMaxPlastic = 0.55;  // Hosford: fused kernel above this plastic fraction (previous call)
 constexpr bool kHostMirrorDefault = false;  // A/B on the B200 box: profiles/ (DXM_HOST_MIRROR overrides)
 }  // namespace
 
@@ -256,23 +256,16 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
   if (h->behaviour == DXM_HOSFORD_LINEAR) {
     a.hos_a = h->hos_a;
     a.hos_bound = hosford_bound(h->hos_a);
-    // Split launch (stream everything + queue the candidates | persistent local solves over the queue) or one fused
-    // kernel.  The split wins while a good part of the batch is elastic (its light pass runs at HBM speed and the
-    // local solves are packed into full warps); when most points are plastic the extra pass costs more than the
-    // packing gains (crossover at 40-50 % plastic, profiles/r01g_configs.json), and small batches do not pay a second launch: auto mode keys on
-    // the batch size and on the plastic fraction of the previous call.  DXM_HOS_SPLIT=0|1 forces either.
+    // Tiled kernel (stream a tile, pack the candidates into full warps) or the fused one.  Tiling wins while a good
+    // part of the batch is elastic (6.6 vs 4.6 G points/s at 3 % plastic); when most points are plastic its extra
+    // pass costs more than the packing gains (crossover at 50-60 % plastic, profiles/r01h_configs.json), and small
+    // batches are latency-bound either way: auto mode keys on the batch size and on the plastic fraction of the
+    // previous call.  DXM_HOS_SPLIT=0|1 forces fused | tiled.
     const char* e = std::getenv("DXM_HOS_SPLIT");
-    bool split = count >= 32768;
-    if (split && h->prev_points > 0) split = (double)h->prev_plastic < kHosSplitMaxPlastic * (double)h->prev_points;
-    if (e) split = std::atoi(e) != 0;
-    if (split && !h->hos_queue) {
-      CK(cudaMalloc(&h->hos_queue, sizeof(unsigned) * h->ld));
-      CK(cudaMalloc(&h->hos_count, sizeof(unsigned)));
-    }
-    if (split) CK(cudaMemsetAsync(h->hos_count, 0, sizeof(unsigned), h->stream));
-    a.hos_queue = h->hos_queue;
-    a.hos_count = h->hos_count;
-    HosLaunch cfg{h->num_sms, h->stream, split, kTilesPerCta};
+    bool tiled = count >= 32768;
+    if (tiled && h->prev_points > 0) tiled = (double)h->prev_plastic < kHosSplitMaxPlastic * (double)h->prev_points;
+    if (e) tiled = std::atoi(e) != 0;
+    HosLaunch cfg{h->num_sms, h->stream, tiled, kTilesPerCta};
     int launches = 0;
     const int rc = launch_hosford(a, cfg, &launches);
     g_launches.fetch_add(launches);
@@ -403,8 +396,6 @@ void free_handle(dxm_handle* h) {
   cudaFree(h->ct);
   cudaFree(h->pp);
   cudaFree(h->table);
-  cudaFree(h->hos_queue);
-  cudaFree(h->hos_count);
   cudaFree(h->d_stats);
   cudaFreeHost(h->h_stats);
   for (int s = 0; s < 2; ++s) {

@@ -20,13 +20,12 @@
 // The point routine is __host__ __device__ so that a CPU test can run the very same code against the oracle
 // (tests/hosford_host_check.cu) -- the product only ever calls it from the kernels below.
 //
-// Launch structure (profiles/r01f_hosford_v1_ncu_*: the fused one-kernel version is latency-bound -- 168 registers,
-// 12 warps per SM, 22 of 32 lanes active, and a warp with ONE candidate lane pays the whole local solve):
-//   dxm_hosford_light_kernel  streams every point like the J2 kernel (256 threads, high occupancy), finishes the
-//                             clearly elastic ones and appends the others' indices to a device queue
-//                             (warp-aggregated atomics keep neighbours together);
-//   dxm_hosford_heavy_kernel  persistent grid over the queue: every lane of every warp holds a candidate point.
-// The fused kernel remains for small batches (one launch) and as the A/B reference (DXM_HOS_SPLIT=0|1).
+// Launch structure (profiles/r01f_hosford_v1_ncu_*: a warp with ONE candidate lane pays the whole local solve):
+//   dxm_hosford_kernel        fused: every thread runs the full routine on its own point -- small batches and batches
+//                             where most points are plastic;
+//   dxm_hosford_tiled_kernel  each CTA streams a 1024-point tile, finishes the clearly elastic points and packs the
+//                             candidates into full warps through a shared-memory queue -- wins below ~55 % plastic.
+// Auto mode by batch size and the previous call's plastic fraction (DXM_HOS_SPLIT=0|1 forces fused | tiled).
 #pragma once
 #include "dxm_canon.cuh"
 #include "dxm_small_strain.cuh"
@@ -388,34 +387,39 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
 
 #if defined(__CUDACC__) && defined(DXM_HOSFORD_KERNELS)  // kernels: instantiated in dxm_hosford_api.cu only
 // SmallStrainArgs is shared with the J2 kernels (same SoA state layout); a.dsu / a.b are unused, a.hos_a = exponent,
-// a.hos_bound = candidate bound, a.hos_queue / a.hos_count = the candidate queue of the split launch.  Per-point
+// a.hos_bound = candidate bound.  Per-point
 // properties (a.pE != nullptr) and diagnostics (a.d_flag != nullptr) are run-time switches here: the kernels are
 // templated on the exponent only.
 struct HosPointIO {
   double eps[6], e_old[6], s_old[6], ep_old[6], p_old, lam, mu, sig0, H;
 };
 
+// STREAM: evict-first loads (last use of the inputs); phase A of the tiled kernel keeps them cacheable for phase B
+template <bool STREAM>
+__device__ __forceinline__ double hos_ld(const double* p) { return STREAM ? __ldcs(p) : __ldg(p); }
+
+template <bool STREAM>
 __device__ __forceinline__ void hos_load(const SmallStrainArgs& a, int64_t i0, HosPointIO& io) {
   const int64_t ld = a.ld;
 #pragma unroll
-  for (int c = 0; c < 6; ++c) io.eps[c] = __ldcs(a.eps + c * ld + i0);
+  for (int c = 0; c < 6; ++c) io.eps[c] = hos_ld<STREAM>(a.eps + c * ld + i0);
 #pragma unroll
-  for (int c = 0; c < 6; ++c) io.e_old[c] = __ldcs(a.eps_old + c * ld + i0);
+  for (int c = 0; c < 6; ++c) io.e_old[c] = hos_ld<STREAM>(a.eps_old + c * ld + i0);
 #pragma unroll
-  for (int c = 0; c < 6; ++c) io.s_old[c] = __ldcs(a.sig_old + c * ld + i0);
-  io.p_old = __ldcs(a.p_old + i0);
+  for (int c = 0; c < 6; ++c) io.s_old[c] = hos_ld<STREAM>(a.sig_old + c * ld + i0);
+  io.p_old = hos_ld<STREAM>(a.p_old + i0);
 #pragma unroll
-  for (int c = 0; c < 6; ++c) io.ep_old[c] = __ldcs(a.epsp_old + c * ld + i0);
+  for (int c = 0; c < 6; ++c) io.ep_old[c] = hos_ld<STREAM>(a.epsp_old + c * ld + i0);
   io.lam = a.lam;
   io.mu = a.mu;
   io.sig0 = a.sig0;
   io.H = a.H;
   if (a.pE) {
-    const double E = __ldcs(a.pE + i0), nu = __ldcs(a.pnu + i0);
+    const double E = hos_ld<STREAM>(a.pE + i0), nu = hos_ld<STREAM>(a.pnu + i0);
     io.lam = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu);
     io.mu = E / 2.0 / (1.0 + nu);
-    io.sig0 = __ldcs(a.psig0 + i0);
-    io.H = __ldcs(a.pH + i0);
+    io.sig0 = hos_ld<STREAM>(a.psig0 + i0);
+    io.H = hos_ld<STREAM>(a.pH + i0);
   }
 }
 
@@ -453,7 +457,7 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_kernel(const SmallStrainAr
     if (loc >= a.count) continue;
     const int64_t i0 = a.start + loc;
     HosPointIO io;
-    hos_load(a, i0, io);
+    hos_load<true>(a, i0, io);
     double sig[6], epsp[6], ct21[21], p_new, resid;
     bool flag, fail;
     int n_iter;
@@ -464,57 +468,61 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_kernel(const SmallStrainAr
   block_reduce_stats(acc, a.stats);
 }
 
-// split, pass 1: stream all points, finish the clearly elastic ones, queue the candidates
-__global__ void __launch_bounds__(256, 3) dxm_hosford_light_kernel(const SmallStrainArgs a) {
-  const int64_t ntile = (a.count + blockDim.x - 1) / blockDim.x;
+// tiled: one CTA owns a tile of kHosTile consecutive points.  Phase A streams the tile (clearly elastic points are
+// finished, candidates go to a shared-memory queue with one warp-aggregated atomic per warp, order kept); phase B
+// packs the candidates into full warps for the local solves.  The candidates' stores land next to the neighbours'
+// stores issued moments earlier by the same CTA -- a device-wide queue + second kernel (r01g) lost exactly that
+// locality when few points are candidates (scattered 8-byte accesses) and was slower in every regime.
+constexpr int kHosTile = 1024;
+template <int AT>
+__global__ void __launch_bounds__(128, 3) dxm_hosford_tiled_kernel(const SmallStrainArgs a) {
+  __shared__ unsigned s_queue[kHosTile];
+  __shared__ unsigned s_count;
+  const int64_t ntile = (a.count + kHosTile - 1) / kHosTile;
   PointStats acc;
   for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
-    const int64_t loc = tile * blockDim.x + threadIdx.x;
-    const bool live = loc < a.count;
-    bool heavy = false;
-    if (live) {
-      const int64_t i0 = a.start + loc;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    for (int sub = 0; sub < kHosTile / 128; ++sub) {
+      const int64_t loc = tile * kHosTile + sub * 128 + threadIdx.x;
+      bool heavy = false;
+      if (loc < a.count) {
+        const int64_t i0 = a.start + loc;
+        HosPointIO io;
+        hos_load<false>(a, i0, io);
+        double sig[6], epsp[6], ct21[21], p_new, resid;
+        bool flag, fail;
+        int n_iter;
+        heavy = hosford_point<true, 0>(io.lam, io.mu, io.sig0, io.H, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old,
+                                       io.p_old, io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
+        if (!heavy) hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, heavy);
+      if (bal) {
+        const int lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == __ffs(bal) - 1) base = atomicAdd(&s_count, (unsigned)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+        if (heavy) s_queue[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned)(loc - tile * kHosTile);
+      }
+    }
+    __syncthreads();
+    const unsigned total = s_count;
+    for (unsigned q = threadIdx.x; q < total; q += blockDim.x) {
+      const int64_t i0 = a.start + tile * kHosTile + (int64_t)s_queue[q];
       HosPointIO io;
-      hos_load(a, i0, io);
+      hos_load<true>(a, i0, io);
       double sig[6], epsp[6], ct21[21], p_new, resid;
       bool flag, fail;
       int n_iter;
-      heavy = hosford_point<true, 0>(io.lam, io.mu, io.sig0, io.H, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old,
-                                     io.p_old, io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
-      if (!heavy) hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
+      hosford_point<false, AT>(io.lam, io.mu, io.sig0, io.H, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old, io.p_old,
+                               io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
+      hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
     }
-    // warp-aggregated append: one atomic per warp, lanes keep their order (neighbours stay neighbours in the queue)
-    const unsigned bal = __ballot_sync(0xffffffffu, heavy);
-    if (bal) {
-      const int lane = threadIdx.x & 31;
-      unsigned base = 0;
-      if (lane == __ffs(bal) - 1) base = atomicAdd(a.hos_count, (unsigned)__popc(bal));
-      base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-      if (heavy) a.hos_queue[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned)loc;
-    }
+    __syncthreads();  // the queue is reused by the next tile
   }
   block_reduce_stats(acc, a.stats);
 }
-
-// split, pass 2: persistent grid over the queue, every lane holds a candidate point
-template <int AT, int MINB>
-__global__ void __launch_bounds__(128, MINB) dxm_hosford_heavy_kernel(const SmallStrainArgs a) {
-  const unsigned total = *a.hos_count;
-  PointStats acc;
-  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
-    const int64_t i0 = a.start + (int64_t)a.hos_queue[q];
-    HosPointIO io;
-    hos_load(a, i0, io);
-    double sig[6], epsp[6], ct21[21], p_new, resid;
-    bool flag, fail;
-    int n_iter;
-    hosford_point<false, AT>(io.lam, io.mu, io.sig0, io.H, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old, io.p_old,
-                             io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
-    hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
-  }
-  block_reduce_stats(acc, a.stats);
-}
-
 #endif  // kernels
 
 #ifdef __CUDACC__
@@ -522,7 +530,7 @@ __global__ void __launch_bounds__(128, MINB) dxm_hosford_heavy_kernel(const Smal
 struct HosLaunch {
   int num_sms;
   cudaStream_t stream;
-  bool split;  // light + queue + heavy instead of the fused kernel
+  bool tiled;  // tiled kernel (stream + CTA-local candidate queue + packed local solves) instead of the fused one
   int tiles_per_cta;
 };
 int launch_hosford(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches);

@@ -15,15 +15,9 @@ double hosford_bound(int a) {
 namespace {
 template <int AT>
 int launch_at(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches) {
-  if (cfg.split) {
-    const int64_t ntile = (a.count + 255) / 256;
-    int64_t grid = (ntile + cfg.tiles_per_cta - 1) / cfg.tiles_per_cta;
-    if (grid < 1) grid = 1;
-    dxm_hosford_light_kernel<<<(unsigned)grid, 256, 0, cfg.stream>>>(a);
-    ++*launches;
-    CK(cudaGetLastError());
-    // 3 resident CTAs per SM (168 registers); 4 (128 registers, 3x the spills) measured 0-20 % slower (profiles/r01g_configs.json)
-    dxm_hosford_heavy_kernel<AT, 3><<<cfg.num_sms * 3, 128, 0, cfg.stream>>>(a);
+  if (cfg.tiled) {
+    const int64_t ntile = (a.count + kHosTile - 1) / kHosTile;
+    dxm_hosford_tiled_kernel<AT><<<(unsigned)(ntile < 1 ? 1 : ntile), 128, 0, cfg.stream>>>(a);
     ++*launches;
     CK(cudaGetLastError());
     return 0;

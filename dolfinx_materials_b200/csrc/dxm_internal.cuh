@@ -67,7 +67,6 @@ struct dxm_handle {
   double* table = nullptr;  // DXM_J2_TABLE: device [3][ntab] = p_k, sig_k, slope_k
   int ntab = 0;
   int hos_a = 10;  // DXM_HOSFORD_LINEAR: exponent (the demo's value by default)
-  unsigned *hos_queue = nullptr, *hos_count = nullptr;  // candidate queue of the split Hosford launch ([ld], [1])
   // statistics
   dxm::StatSlot* d_stats = nullptr;
   dxm::StatSlot* h_stats = nullptr;  // pinned

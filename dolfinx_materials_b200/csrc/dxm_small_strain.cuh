@@ -46,8 +46,6 @@ struct SmallStrainArgs {
   int ntab;
   int hos_a;  // DXM_HOSFORD_LINEAR: exponent of the Hosford criterion (even integer)
   double hos_bound;  // ... and sup sigma_eq / seq_Mises (1 + 1e-9): points below it are finished without a local solve
-  unsigned* hos_queue;  // split launch: local indices of the candidate points, [count]
-  unsigned* hos_count;  // ... and how many there are
   StatSlot* stats;
   int vote;  // 1: warp-vote (__any_sync) Newton loop exit, 0: per-lane exit (A/B knob DXM_VOTE)
   // optional diagnostics (DIAG == true)

@@ -88,8 +88,8 @@ out.append(dict(cfg="cfg4 faithful: matrix Hosford(a=10)+linear handle, inclusio
                 gps=n / ms * 1e3, hosford_n=na, hosford_ms=msh, hosford_gps=na / msh * 1e3, hosford_gbs_moved=472 * na / msh / 1e6,
                 hosford_plastic=a.n_plastic / na, hosford_max_iter=a.max_iter, hosford_fail=a.n_fail))
 del mh, mb
-# Hosford kernel alone over the plastic fraction (amplitude sweep), n = 1e7: fused kernel vs split launch (light pass +
-# candidate queue + persistent local solves), (r01g also ran the local-solve kernel at 4 resident CTAs per SM / 128 registers: 0-20 % slower)
+# Hosford kernel alone over the plastic fraction (amplitude sweep), n = 1e7: fused kernel vs tiled kernel (stream a 1024-point
+# tile + CTA-local candidate queue + packed local solves; r01g/r01h also ran a device-wide queue + second kernel: slower), (r01g also ran the local-solve kernel at 4 resident CTAs per SM / 128 registers: 0-20 % slower)
 mh = jm.CUDAMaterial(jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.LinearHardening(sig0=200.0, H=10.0)))
 mh.set_data_manager(n)
 for split, minb in (("0", "3"), ("1", "3")):

@@ -18,7 +18,7 @@ for beh in (jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=jm.VoceHar
             jm.ElasticBehavior(elasticity=el)):
     m = jm.CUDAMaterial(beh); m.set_data_manager(n)
     for k in range(1, 4):
-        os.environ["DXM_HOS_SPLIT"] = str(k % 2)  # Hosford: fused kernel and split (light + queue + heavy) launches
+        os.environ["DXM_HOS_SPLIT"] = str(k % 2)  # Hosford: fused and tiled kernels
         flux, isv, ct = m.integrate(synth.strain(n, 0, 1.25e-2, k, 3)); m.data_manager.update()
     m.update_material_property("E", np.linspace(60e3, 80e3, n)); m.integrate(synth.strain(n, 0, 1.3e-2, 3, 3))
     m.device_tangent(); m.get_final_state_dict()

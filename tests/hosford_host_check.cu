@@ -44,8 +44,8 @@ void run(int64_t n, const double* eps, const double* e_old, const double* s_old,
       s0[c] = s_old[i * 6 + c];
       ep0[c] = ep_old[i * 6 + c];
     }
-    // split != 0 replays the two-kernel launch: the light pass finishes the clearly elastic points and reports the
-    // candidates, which the full routine then recomputes from scratch (dxm_hosford_light_kernel / _heavy_kernel)
+    // split != 0 replays the tiled kernel: phase A finishes the clearly elastic points and reports the candidates,
+    // which the full routine then recomputes from scratch (dxm_hosford_tiled_kernel)
     bool heavy = true;
     if (split) heavy = dxm::hosford_point<true, 0>(lam, mu, sig0, H, a, bound, e1, e0, s0, p_old[i], ep0, so, pn, epo, ct21, fl, it, rs, fa);
     if (heavy) {

@@ -45,7 +45,8 @@ def check(m, out, ref):
 @pytest.mark.parametrize("split", ["0", "1"])
 @pytest.mark.parametrize("n", [129, 50_003])
 def test_fused_and_split_launches_agree_with_the_oracle(jm, monkeypatch, split, n):
-    """DXM_HOS_SPLIT: one fused kernel vs light pass + queue + persistent local solves -- same bits either way."""
+    """DXM_HOS_SPLIT: fused kernel (0) vs tiled kernel (1: stream a tile, CTA-local candidate queue, packed local
+    solves) -- same bits either way."""
     monkeypatch.setenv("DXM_HOS_SPLIT", split)
     m = make(jm, DEMO, n)
     st = ss.zero_state(n)

@@ -84,3 +84,26 @@ def test_kernel_point_routine_degenerate_and_extreme_inputs(host):
         for key in ("stress", "p", "epsp", "Ct", "resid"):
             assert got[key].tobytes() == ref[key].tobytes(), key  # bitwise, NaN included
     assert ref["fail"][5] == 1 and ref["fail"].sum() == 1
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_kernel_point_routine_random_states_and_properties(host, seed):
+    """Arbitrary admissible previous states (pre-stress, accumulated plastic strain) and properties, non-proportional
+    increments, unloading: kernel routine == oracle bit for bit, fused and split."""
+    rng = np.random.default_rng(seed)
+    n = 4000
+    for a in (6, 8, 10, 12):
+        props = dict(E=float(rng.uniform(50e3, 210e3)), nu=float(rng.uniform(0.05, 0.45)),
+                     sig0=float(rng.uniform(100.0, 400.0)), H=float(rng.choice([0.0, 10.0, 2e3])), a=a)
+        st = ss.zero_state(n)
+        # build a non-trivial state with two oracle steps in unrelated directions, then test a third one (some
+        # points reload, some unload, some stay elastic)
+        for k in range(2):
+            st = ss.advance(ho.integrate(synth.strain(n, 10 * seed + k, 8e-3, 1, 1), st, props))
+        eps = st["strain"] + rng.standard_normal((n, 6)) * rng.uniform(0, 2e-3, (n, 1))
+        ref = ho.integrate(eps, st, props)
+        assert ref["fail"].sum() == 0 and 0.02 < ref["flag"].mean() < 0.98
+        for split in (0, 1):
+            got = run(host, eps, st, props, split)
+            for key in ("flag", "n_iter", "fail", "stress", "p", "epsp", "Ct", "resid"):
+                assert np.array_equal(got[key], ref[key]), (key, a, split)
