@@ -123,3 +123,84 @@ def test_cfg3_fefp_1e7_points(jm):
     assert (vm - sy)[flag].abs().max().item() < 1e-8 * 500
     assert (vm - sy)[~flag].max().item() < 1e-8 * 500
     assert (tau[0][1] - tau[1][0]).abs().max().item() < 1e-8
+
+
+def test_cfg4_multimaterial_hosford_matrix_1e7_points(jm):
+    """cfg4 at full size with the demo's own two laws (multimaterials.py:245-261): a 7e6-point matrix handle with the
+    Hosford (a = 10) + linear hardening law and a 3e6-point inclusions handle with J2 + Voce, loaded through the same
+    4-increment history.  Slices of both against their oracles bit for bit; over ALL Hosford points, on the device:
+    sigma_eq(sigma) = R0 + H p on the active set (eigenvalues by torch), f <= 0 elsewhere, p monotone, plastic strain
+    traceless, elastic tangent == C, statistics == per-point flags."""
+    import torch
+
+    from oracle import hosford as ho
+
+    n = 10_000_000
+    na, nb = 7_000_000, 3_000_000
+    HOS = dict(E=70e3, nu=0.3, sig0=200.0, H=10.0, a=10)
+    INC = dict(E=90e3, nu=0.25, sig0=200.0, sigu=300.0, b=10.0)
+    mh = jm.CUDAMaterial(jm.GeneralIsotropicHardening(
+        elasticity=jm.LinearElasticIsotropic(E=HOS["E"], nu=HOS["nu"]),
+        yield_stress=jm.LinearHardening(sig0=HOS["sig0"], H=HOS["H"]), equivalent_stress=jm.Hosford(a=10)))
+    mi = jm.CUDAMaterial(jm.vonMisesIsotropicHardening(
+        elasticity=jm.LinearElasticIsotropic(E=INC["E"], nu=INC["nu"]),
+        yield_stress=jm.VoceHardening(sig0=INC["sig0"], sigu=INC["sigu"], b=INC["b"])))
+    mh.set_data_manager(na)
+    mi.set_data_manager(nb)
+    mh.enable_diagnostics()
+    for m, start in ((mh, 0), (mi, na)):
+        for k in range(1, K):
+            m.synth_gradients(0, AMP, k, K, start=start)
+            m.integrate_resident()
+            m.data_manager.update()
+        m.synth_gradients(0, AMP, K, K, start=start)
+    sh = mh.integrate_resident()
+    si = mi.integrate_resident()
+    assert sh.n_fail == 0 and si.n_fail == 0 and sh.max_iter <= 8
+    assert 0.6 < sh.n_plastic / na < 0.95 and 0.5 < si.n_plastic / nb < 0.95
+
+    w = 20_000
+    for m, props, integ, base, starts in ((mh, HOS, ho.integrate, 0, (0, na // 2 + 3, na - w)),
+                                          (mi, INC, ss.integrate, na, (0, nb - w))):
+        for start in starts:
+            st = ss.zero_state(w)
+            for k in range(1, K):
+                st = ss.advance(integ(synth.strain(w, 0, AMP, k, K, start=base + start), st, props))
+            ref = integ(synth.strain(w, 0, AMP, K, K, start=base + start), st, props)
+            sl = slice(start, start + w)
+            assert np.array_equal(m.device_view("stress")[:, sl].cpu().numpy().T, ref["stress"])
+            assert np.array_equal(m.device_view("p")[0, sl].cpu().numpy(), ref["p"])
+            assert np.array_equal(m.device_view("epsp")[:, sl].cpu().numpy().T, ref["epsp"])
+            assert np.array_equal(m.device_tangent(sl).cpu().numpy().T.reshape(w, 6, 6), ref["Ct"])
+
+    flag, n_iter, resid, fail = mh.diagnostics()
+    assert int(flag.sum()) == sh.n_plastic and int(n_iter.max()) == sh.max_iter and fail.sum() == 0
+    assert resid.max() == sh.max_residual
+    flag_d = torch.from_numpy(flag).cuda().bool()
+    sig, p, p0, epsp = mh.device_view("stress"), mh.device_view("p"), mh.device_view("p", gen=0), mh.device_view("epsp")
+    lam, mu = 70e3 * 0.3 / 1.3 / 0.4, 70e3 / 2 / 1.3
+    C = torch.zeros(36, dtype=torch.float64, device="cuda")
+    for j in range(6):
+        for i in range(6):
+            C[j * 6 + i] = (lam if (i < 3 and j < 3) else 0.0) + (2 * mu if i == j else 0.0)
+    r = 2 ** -0.5
+    worst_f, worst_el = 0.0, -1e300
+    chunk = 1_000_000
+    for s0 in range(0, na, chunk):
+        sl = slice(s0, s0 + chunk)
+        s = sig[:, sl]
+        T = torch.stack([torch.stack([s[0], s[3] * r, s[4] * r]), torch.stack([s[3] * r, s[1], s[5] * r]),
+                         torch.stack([s[4] * r, s[5] * r, s[2]])]).permute(2, 0, 1).contiguous()
+        ev = torch.linalg.eigvalsh(T)
+        d = torch.stack([ev[:, 0] - ev[:, 1], ev[:, 1] - ev[:, 2], ev[:, 2] - ev[:, 0]]).abs()
+        dm = d.max(dim=0).values.clamp_min(1e-300)
+        phi = dm * (0.5 * ((d / dm) ** 10).sum(dim=0)) ** 0.1
+        f = phi - (200.0 + 10.0 * p[0, sl])
+        fl = flag_d[sl]
+        worst_f = max(worst_f, f[fl].abs().max().item())
+        worst_el = max(worst_el, f[~fl].max().item())
+        assert (p[0, sl] >= p0[0, sl]).all()
+        assert epsp[:3, sl].sum(dim=0).abs().max().item() < 1e-14
+        c = mh.device_tangent(sl)
+        assert torch.equal(c[:, ~fl], C[:, None].expand(-1, int((~fl).sum())))
+    assert worst_f < 1e-9 * 200.0 and worst_el <= 1e-9 * 200.0
