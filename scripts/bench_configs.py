@@ -100,5 +100,32 @@ for split, minb in (("0", "3"), ("1", "3")):
         out.append(dict(cfg=f"Hosford a=10 alone, virgin state, amp {amp}", split=int(split), minb=int(minb), n=n, ms=ms, gps=n / ms * 1e3,
                         gbs_moved=472 * n / ms / 1e6, plastic=s.n_plastic / n, max_iter=s.max_iter, fail=s.n_fail))
 del os.environ["DXM_HOS_SPLIT"]
+del mh
+
+# the same batch with the plastic points contiguous (sorted by strain amplitude, i.e. as a mesh with a
+# localised plastic zone presents them) vs interleaved at random (the synthetic default) -- the difference is what lane
+# divergence costs each kernel.  One increment from the virgin state, so that permuting the gradients permutes nothing else.
+import torch
+n2 = 10_000_000
+for name, beh, amp in (("J2+Voce", jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=jm.VoceHardening(sig0=350.0, sigu=500.0, b=1e3)), 6e-3),
+                       ("Hosford a=10 (auto fused/tiled)", jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.LinearHardening(sig0=200.0, H=10.0)), 4e-3),
+                       ("FeFp+Voce", jm.FeFpJ2Plasticity(elasticity=el, yield_stress=jm.VoceHardening(sig0=500.0, sigu=750.0, b=1000.0)), 1.2e-2)):
+    mm = jm.CUDAMaterial(beh); mm.set_data_manager(n2)
+    mm.synth_gradients(0, amp, 1, 1)
+    g = mm.gradient_buffer()
+    dev = g.clone()
+    if dev.shape[0] == 9: dev[:3] -= 1.0
+    perm = torch.argsort((dev * dev).sum(dim=0))
+    del dev
+    res = {}
+    for order in ("shuffled", "sorted"):
+        if order == "sorted":
+            g.copy_(g[:, perm].clone()); torch.cuda.synchronize()
+        mm.integrate_resident()  # auto modes key on the previous call's plastic fraction
+        ms, s = timeit(mm)
+        res[order] = ms
+    out.append(dict(cfg=f"divergence exposure: {name}, n=1e7, one increment from the virgin state", shuffled_ms=res["shuffled"],
+                    sorted_ms=res["sorted"], plastic=s.n_plastic / n2, sorted_speedup=res["shuffled"] / res["sorted"]))
+    del mm, g, perm
 print(json.dumps(out, indent=1))
 os.makedirs("gpurun_out", exist_ok=True); json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
