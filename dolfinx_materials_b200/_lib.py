@@ -83,6 +83,8 @@ SIGNATURES = {
     "dxm_host_register": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
     "dxm_host_unregister": (ctypes.c_int, [ctypes.c_void_p]),
     "dxm_host_mirror_sym6": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    "dxm_host_gather_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int]),
+    "dxm_host_scatter_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int]),
     "dxm_launch_count": (ctypes.c_int64, []),
     "dxm_fp64_peak": (ctypes.c_int, [ctypes.c_int, c_double_p]),
     "dxm_copy_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, c_double_p]),

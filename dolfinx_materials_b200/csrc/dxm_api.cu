@@ -972,6 +972,18 @@ int dxm_host_mirror_sym6(const double* packed, double* full, int64_t n, int thre
   return 0;
 }
 
+int dxm_host_gather_rows(const double* src, const int64_t* rows, int64_t n, int64_t row_len, double* dst, int threads) {
+  if (n < 0 || row_len < 0 || (n > 0 && row_len > 0 && (!src || !rows || !dst))) return fail("dxm_host_gather_rows: bad argument");
+  dxm_host::gather_rows(src, rows, n, row_len, dst, threads);
+  return 0;
+}
+
+int dxm_host_scatter_rows(double* dst, const int64_t* rows, int64_t n, int64_t row_len, const double* src, int threads) {
+  if (n < 0 || row_len < 0 || (n > 0 && row_len > 0 && (!src || !rows || !dst))) return fail("dxm_host_scatter_rows: bad argument");
+  dxm_host::scatter_rows(dst, rows, n, row_len, src, threads);
+  return 0;
+}
+
 int dxm_host_alloc(void** ptr, int64_t bytes) {
   if (!ptr || bytes < 0) return fail("dxm_host_alloc: bad argument");
   CK(cudaMallocHost(ptr, (size_t)(bytes ? bytes : 1)));

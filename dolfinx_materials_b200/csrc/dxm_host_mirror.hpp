@@ -13,6 +13,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -152,6 +153,36 @@ inline void mirror_sym6(const double* packed, double* full, int64_t n, int threa
     const int64_t per = ((n + nparts - 1) / nparts + 7) & ~int64_t(7);
     const int64_t r0 = std::min<int64_t>(n, per * part), r1 = std::min<int64_t>(n, r0 + per);
     if (r1 > r0) mirror_rows(packed, full, r0, r1);
+  });
+}
+
+// Row gather / scatter by index on the pool: dst[r, :] = src[rows[r], :] and dst[rows[r], :] = src[r, :] with rows of
+// `row_len` doubles.  These are the two host passes a QuadratureMap over a cell SUBSET cannot avoid (the Function
+// arrays span the whole mesh, quadrature_map.py:251-260, utils.py:136-143); numpy's fancy indexing runs them at
+// 1-2 GB/s on one core, which is 10x slower than the PCIe copy they sit next to.
+inline void gather_rows(const double* src, const int64_t* rows, int64_t n, int64_t row_len, double* dst, int threads) {
+  if (n <= 0 || row_len <= 0) return;
+  auto body = [&](int64_t r0, int64_t r1) {
+    for (int64_t r = r0; r < r1; ++r) std::memcpy(dst + r * row_len, src + rows[r] * row_len, sizeof(double) * row_len);
+  };
+  if (threads == 1 || n * row_len < 65536) return body(0, n);
+  pool().run([&](int part, int nparts) {
+    const int64_t per = (n + nparts - 1) / nparts;
+    const int64_t r0 = std::min<int64_t>(n, per * part), r1 = std::min<int64_t>(n, r0 + per);
+    if (r1 > r0) body(r0, r1);
+  });
+}
+
+inline void scatter_rows(double* dst, const int64_t* rows, int64_t n, int64_t row_len, const double* src, int threads) {
+  if (n <= 0 || row_len <= 0) return;
+  auto body = [&](int64_t r0, int64_t r1) {
+    for (int64_t r = r0; r < r1; ++r) std::memcpy(dst + rows[r] * row_len, src + r * row_len, sizeof(double) * row_len);
+  };
+  if (threads == 1 || n * row_len < 65536) return body(0, n);
+  pool().run([&](int part, int nparts) {  // distinct rows -> disjoint destinations, no synchronisation needed
+    const int64_t per = (n + nparts - 1) / nparts;
+    const int64_t r0 = std::min<int64_t>(n, per * part), r1 = std::min<int64_t>(n, r0 + per);
+    if (r1 > r0) body(r0, r1);
   });
 }
 

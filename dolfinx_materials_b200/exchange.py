@@ -14,17 +14,32 @@ passes dominate.  ``QuadratureExchange`` keeps the same observable result (the s
 * the NaN scans are replaced by the fail count reduced on the device;
 * internal state variables stay on the GPU during Newton iterations and are fetched once, in ``advance()``.
 
-Cell subsets fall back to one gather into / scatter out of page-locked staging arrays (same numpy
-indexing as the reference).  The class works on any objects exposing a flat float64 ``x.array`` (dolfinx
+Cell subsets (one map per material region, ``demos/multimaterials/multimaterials.py:265-273``) cannot avoid one
+gather into / scatter out of page-locked staging arrays -- the Function arrays span the whole mesh -- but they run
+cell-block-wise on the library's host thread pool (``dxm_host_gather_rows`` / ``dxm_host_scatter_rows``) instead
+of numpy fancy indexing.  The class works on any objects exposing a flat float64 ``x.array`` (dolfinx
 ``fem.Function``) or on plain ndarrays, so it runs without dolfinx.
 """
 
+import ctypes
 import warnings
 
 import numpy as np
 
-from . import PerformanceWarning
+from . import PerformanceWarning, _lib
 from .material import PinnedArray, pin_array
+
+
+def _gather_cells(src_flat, cells64, block, dst):
+    """dst[c, :] = src[cells[c], :] with rows of ``block`` doubles (all points of a cell), on the host pool."""
+    _lib.check(_lib.load().dxm_host_gather_rows(src_flat.ctypes.data_as(ctypes.c_void_p), cells64.ctypes.data_as(ctypes.c_void_p),
+                                                len(cells64), block, dst.ctypes.data_as(ctypes.c_void_p), 0), "dxm_host_gather_rows")
+
+
+def _scatter_cells(dst_flat, cells64, block, src):
+    """dst[cells[c], :] = src[c, :] (``_update_vals`` with ``cells``, ``utils.py:136-143``), on the host pool."""
+    _lib.check(_lib.load().dxm_host_scatter_rows(dst_flat.ctypes.data_as(ctypes.c_void_p), cells64.ctypes.data_as(ctypes.c_void_p),
+                                                 len(cells64), block, src.ctypes.data_as(ctypes.c_void_p), 0), "dxm_host_scatter_rows")
 
 
 def _flat(fun):
@@ -60,6 +75,9 @@ class QuadratureExchange:
             self.n = ntot
         else:
             self.cells = np.asarray(cells, dtype=np.int32)
+            if len(np.unique(self.cells)) != len(self.cells) or self.cells.min() < 0 or self.cells.max() >= num_cells:
+                raise ValueError("cells must be distinct indices in [0, num_cells)")
+            self.cells64 = np.ascontiguousarray(self.cells, dtype=np.int64)
             self.dofs = (np.repeat(self.num_qp * self.cells[:, None], self.num_qp, axis=1)
                          + np.arange(self.num_qp)[None, :]).ravel()
             self.n = len(self.dofs)
@@ -118,10 +136,11 @@ class QuadratureExchange:
             stats = m.integrate_into(self.grad, self.flux, None, self.jac, dt)
         else:
             g, f, c, _ = self._stage
-            np.take(self.grad.reshape(-1, self.gdim), self.dofs, axis=0, out=g.array)
+            q = self.num_qp
+            _gather_cells(self.grad, self.cells64, q * self.gdim, g.array)
             stats = m.integrate_into(g.array, f.array, None, c.array, dt)
-            self.flux.reshape(-1, self.fdim)[self.dofs] = f.array
-            self.jac.reshape(-1, self.fdim * self.gdim)[self.dofs] = c.array
+            _scatter_cells(self.flux, self.cells64, q * self.fdim, f.array)
+            _scatter_cells(self.jac, self.cells64, q * self.fdim * self.gdim, c.array)
         self.last_stats = stats
         if stats.n_fail:
             # the reference asserts on NaN in flux / isv / Ct (quadrature_map.py:322-324); the device-side fail
@@ -142,6 +161,6 @@ class QuadratureExchange:
                 m.read_state_into(k, self.isv[k])
         else:
             final = m.get_final_state_dict()
-            self.flux.reshape(-1, self.fdim)[self.dofs] = final[self.fname]
+            _scatter_cells(self.flux, self.cells64, self.num_qp * self.fdim, np.ascontiguousarray(final[self.fname]))
             for k, d in m.internal_state_variables.items():
-                self.isv[k].reshape(-1, max(1, d))[self.dofs] = final[k]
+                _scatter_cells(self.isv[k], self.cells64, self.num_qp * max(1, d), np.ascontiguousarray(final[k]))

@@ -201,6 +201,14 @@ int dxm_host_unregister(void* ptr);
  * the mirror runs on the host while the next chunk is in flight. */
 int dxm_host_mirror_sym6(const double* packed, double* full, int64_t n, int threads);
 
+/* Host-side row gather / scatter by index on the library's thread pool (pure data movement, no device involved):
+ *   gather : dst[r, :] = src[rows[r], :]        scatter : dst[rows[r], :] = src[r, :]        rows of row_len doubles
+ * -- the two passes a QuadratureMap built on a cell SUBSET needs around integrate(), because the Function arrays
+ * span the whole mesh: _get_vals(gradient)[dofs, :] (quadrature_map.py:251-253) and fun.x.array[dofs] = arr
+ * (utils.py:136-143).  rows must be distinct for scatter (they are: one entry per cell). threads <= 0: pool default. */
+int dxm_host_gather_rows(const double* src, const int64_t* rows, int64_t n, int64_t row_len, double* dst, int threads);
+int dxm_host_scatter_rows(double* dst, const int64_t* rows, int64_t n, int64_t row_len, const double* src, int threads);
+
 /* measurement support */
 int64_t dxm_launch_count(void);                       /* kernels launched by this library so far */
 int dxm_fp64_peak(int device, double* tflops);        /* register-resident DFMA microbenchmark   */

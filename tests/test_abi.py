@@ -120,3 +120,25 @@ def test_host_mirror_of_the_packed_tangent(jm, n, threads):
         assert rc == 0
         assert full.reshape(n, 36).tobytes() == want.tobytes()
         assert buf[base + offset + n * 36] == -7.0 and (base + offset == 0 or buf[base + offset - 1] == -7.0)
+
+
+@pytest.mark.parametrize("n,row_len,threads", [(0, 5, 1), (1, 1, 1), (1000, 24, 1), (30000, 36, 0), (30000, 7, 3)])
+def test_host_row_gather_and_scatter(jm, n, row_len, threads):
+    """dxm_host_gather_rows / dxm_host_scatter_rows == numpy fancy indexing (the subset passes of QuadratureMap)."""
+    from dolfinx_materials_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(n + row_len)
+    total = 3 * n + 5
+    rows = np.sort(rng.choice(total, size=n, replace=False)).astype(np.int64)
+    src = rng.standard_normal((total, row_len))
+    dst = np.full((n, row_len), np.nan)
+    c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    assert lib.dxm_host_gather_rows(c(src), c(rows), n, row_len, c(dst), threads) == 0
+    assert np.array_equal(dst, src[rows])
+    big = np.zeros((total, row_len))
+    vals = rng.standard_normal((n, row_len))
+    assert lib.dxm_host_scatter_rows(c(big), c(rows), n, row_len, c(vals), threads) == 0
+    want = np.zeros((total, row_len))
+    want[rows] = vals
+    assert np.array_equal(big, want)
