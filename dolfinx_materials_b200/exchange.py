@@ -160,7 +160,12 @@ class QuadratureExchange:
             for k in m.internal_state_variables:
                 m.read_state_into(k, self.isv[k])
         else:
-            final = m.get_final_state_dict()
-            _scatter_cells(self.flux, self.cells64, self.num_qp * self.fdim, np.ascontiguousarray(final[self.fname]))
+            # only what the Functions hold (flux + internal state), through the page-locked staging arrays
+            _, f, _, w = self._stage
+            m.read_state_into(self.fname, f.array)
+            _scatter_cells(self.flux, self.cells64, self.num_qp * self.fdim, f.array)
             for k, d in m.internal_state_variables.items():
-                _scatter_cells(self.isv[k], self.cells64, self.num_qp * max(1, d), np.ascontiguousarray(final[k]))
+                d = max(1, d)
+                buf = w.array.reshape(-1)[: self.n * d].reshape(self.n, d)
+                m.read_state_into(k, buf)
+                _scatter_cells(self.isv[k], self.cells64, self.num_qp * d, buf)
