@@ -828,7 +828,7 @@ int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double*
       int slot;
       int64_t s, m;
     };
-    Pending pend[dxm_handle::kRing];
+    Pending pend[dxm_handle::kRing] = {};
     int npend = 0;
     auto drain_one = [&]() -> int {  // oldest in-flight packed chunk -> the caller's (n, 36) rows
       const Pending p = pend[0];
