@@ -115,17 +115,18 @@ class Hosford:
 
 @dataclass
 class GeneralIsotropicHardening(_Behavior):
-    """Small-strain associated plasticity with a non-quadratic isotropic criterion and linear isotropic hardening
-    ``R0 + H p`` -- the MFront behaviour of the matrix phase of ``demos/multimaterials/multimaterials.py:245-254``
-    (``young_modulus, poisson_ratio, R0, hardening_slope`` = ``E, nu, sig0, H`` here); the class name follows the
-    jaxmat behaviour the old demo mentions (``_plane_stress_elastoplasticity.py:17,45``)."""
+    """Small-strain associated plasticity with a non-quadratic isotropic criterion and isotropic hardening.  With
+    ``LinearHardening`` (``R0 + H p``) it is the MFront behaviour of the matrix phase of
+    ``demos/multimaterials/multimaterials.py:245-254`` (``young_modulus, poisson_ratio, R0, hardening_slope`` =
+    ``E, nu, sig0, H`` here); with ``VoceHardening`` it is the jaxmat behaviour of that name as the old demo calls it,
+    ``GeneralIsotropicHardening(elastic_model, yield_stress, ...)`` (``_plane_stress_elastoplasticity.py:17,45``)."""
 
     yield_stress: Any = None
     equivalent_stress: Any = field(default_factory=Hosford)
 
     def __post_init__(self):
-        if not isinstance(self.yield_stress, LinearHardening):
-            raise TypeError("GeneralIsotropicHardening: yield_stress must be a LinearHardening descriptor")
+        if not isinstance(self.yield_stress, (LinearHardening, VoceHardening)):
+            raise TypeError("GeneralIsotropicHardening: yield_stress must be a LinearHardening or VoceHardening descriptor")
         if not isinstance(self.equivalent_stress, Hosford):
             raise TypeError("GeneralIsotropicHardening: equivalent_stress must be a Hosford descriptor")
         a = self.equivalent_stress.a

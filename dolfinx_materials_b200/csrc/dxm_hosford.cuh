@@ -1,10 +1,12 @@
-// Small-strain plasticity with the Hosford criterion and linear isotropic hardening -- the behaviour of the matrix
-// phase of the reference's multi-material demo (demos/multimaterials/IsotropicPlasticHosfordFlowLinear.mfront:1-27,
-// used at demos/multimaterials/multimaterials.py:245-254 through MFront/MGIS), behind the same handle / state layout
+// Small-strain plasticity with the Hosford criterion and isotropic hardening -- linear hardening is the behaviour of the
+// matrix phase of the reference's multi-material demo (demos/multimaterials/IsotropicPlasticHosfordFlowLinear.mfront:1-27,
+// used at demos/multimaterials/multimaterials.py:245-254 through MFront/MGIS); with the general law of the J2 kernels
+// (sig0 + H p + (sigu - sig0)(1 - exp(-b p))) it is jaxmat's GeneralIsotropicHardening(elastic, yield_stress, ...)
+// (demos/jax/elastoplasticity/_plane_stress_elastoplasticity.py:17,45) -- behind the same handle / state layout
 // (strain, stress, p, epsp) as the J2 behaviours.
 //
 //   sigma_eq = (1/2 (|s1-s2|^a + |s2-s3|^a + |s3-s1|^a))^(1/a),  a even integer (2 = von Mises, 10 in the demo)
-//   backward Euler, associated flow:  sigma = sigma_tr - 2 mu dp n(sigma),  sigma_eq(sigma) = R0 + H (p_old + dp)
+//   backward Euler, associated flow:  sigma = sigma_tr - 2 mu dp n(sigma),  sigma_eq(sigma) = sigma_Y(p_old + dp)
 //
 // One Gauss point per thread.  Isotropy keeps the principal axes of the trial stress, so per point:
 //   * cheap rejection: sigma_eq <= max|s_i - s_j| <= 2/sqrt(3) seq_Mises  -> clearly elastic points skip the rest;
@@ -38,6 +40,47 @@ constexpr double kHosRSqrt2 = 0.7071067811865476;
 constexpr double kHosSqrt2 = 1.4142135623730951;
 constexpr int kHosfordLsMax = 10;
 constexpr int kJacobiSweeps = 8;
+
+// exp_c of dxm_canon.cuh written for host and device (same operations; ldexp is exact where it is used)
+DXM_HD double hos_exp(double x) {
+#ifdef __CUDA_ARCH__
+  return exp_c(x);
+#else
+  if (x != x) return x;
+  if (x < -kExpClamp) return 0.0;
+  if (x > kExpClamp) return INFINITY;
+  const double k = rint(x * kLog2e);
+  const double r = (x - k * kLn2Hi) - k * kLn2Lo;
+  double y = 1.0 / 6227020800.0;
+  y = y * r + 1.0 / 479001600.0;
+  y = y * r + 1.0 / 39916800.0;
+  y = y * r + 1.0 / 3628800.0;
+  y = y * r + 1.0 / 362880.0;
+  y = y * r + 1.0 / 40320.0;
+  y = y * r + 1.0 / 5040.0;
+  y = y * r + 1.0 / 720.0;
+  y = y * r + 1.0 / 120.0;
+  y = y * r + 1.0 / 24.0;
+  y = y * r + 1.0 / 6.0;
+  y = y * r + 0.5;
+  y = y * r + 1.0;
+  y = y * r + 1.0;
+  return ldexp(y, (int)k);
+#endif
+}
+
+// isotropic hardening sigma_Y(p) = sig0 + H p + dsu (1 - exp(-b p)) and its slope at p = p_old + dp (the law of the J2
+// behaviours: linear for dsu = 0, Voce for H = 0)
+struct HosHard {
+  double sig0, H, dsu, b, bdsu, p_old;
+};
+
+DXM_HD void hos_hard(const HosHard& hd, double dp, double& sy, double& dsy) {
+  const double p = hd.p_old + dp;
+  const double e = (hd.bdsu != 0.0) ? hos_exp(-(hd.b * p)) : 1.0;
+  sy = (hd.sig0 + hd.H * p) + hd.dsu * (1.0 - e);
+  dsy = hd.H + hd.bdsu * e;
+}
 
 // (x*x)^k, k >= 1
 DXM_HD double hos_ipow2(double x, int k) {
@@ -140,16 +183,18 @@ DXM_HD void hos_jacobi3(const double (&s)[6], double (&l)[3], double (&V)[3][3])
 
 struct HosRes {
   HosEval e;
-  double rs[3], r4, m2;
+  double rs[3], r4, m2, dsy;
 };
 
-DXM_HD void hos_residual(const double (&x)[3], double dp, const double (&l)[3], double twomu, double sy0, double H,
+DXM_HD void hos_residual(const double (&x)[3], double dp, const double (&l)[3], double twomu, const HosHard& hd,
                          int a, double inv_a, HosRes& o) {
   hos_eval(x, a, inv_a, o.e);
   const double c = twomu * dp;
 #pragma unroll
   for (int k = 0; k < 3; ++k) o.rs[k] = (x[k] - l[k]) + c * o.e.n[k];
-  o.r4 = o.e.phi - (sy0 + H * dp);
+  double sy;
+  hos_hard(hd, dp, sy, o.dsy);
+  o.r4 = o.e.phi - sy;
   o.m2 = ((o.rs[0] * o.rs[0] + o.rs[1] * o.rs[1]) + o.rs[2] * o.rs[2]) + o.r4 * o.r4;
 }
 
@@ -205,8 +250,8 @@ DXM_HD void hos_mandel_pair(const double (&V)[3][3], double (&m)[6]) {
 // run-time exponent 35 % of the executed instructions were loop bookkeeping, profiles/r01g_hosford_v2_*); AT == 0: a_rt.
 // bound: (2^(a-1)+1)^(1/a)/sqrt(3) (1 + 1e-9) >= sigma_eq / seq_Mises for every stress state (maximum at pure shear).
 template <bool LIGHT, int AT>
-DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, const double H, const int a_rt,
-                          const double bound, const double (&eps)[6], const double (&e_old)[6], const double (&s_old)[6],
+DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, const double H, const double dsu,
+                          const double b, const int a_rt, const double bound, const double (&eps)[6], const double (&e_old)[6], const double (&s_old)[6],
                           const double p_old, const double (&ep_old)[6], double (&sig)[6], double& p_new,
                           double (&epsp)[6], double (&ct21)[21], bool& flag, int& n_iter, double& resid,
                           bool& fail) {
@@ -231,7 +276,9 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
 #pragma unroll
   for (int i = 2; i < 6; ++i) ss = ss + s[i] * s[i];
   const double seq = sqrt(1.5 * ss);
-  const double sy0 = sig0 + H * p_old;
+  const HosHard hd{sig0, H, dsu, b, b * dsu, p_old};
+  double sy0, dsy0;
+  hos_hard(hd, 0.0, sy0, dsy0);
 
   flag = false;
   n_iter = 0;
@@ -256,14 +303,16 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
     double m_prev = 0.0;
     for (;;) {
       // evaluated in place: once the step (dx, ddp) is formed only the merit value of the previous iterate is needed
-      hos_residual(xe, dpe, l, twomu, sy0, H, a, inv_a, cur);
+      hos_residual(xe, dpe, l, twomu, hd, a, inv_a, cur);
       if (stage == 0) {
         const double f = cur.e.phi - sy0;
         flag = f > 0.0;
         if (!flag) break;
         // start on the yield surface along the trial direction, dp from the J2-like estimate
-        dpe = f / (threemu + H);
-        const double sc = (sy0 + H * dpe) / cur.e.phi;
+        dpe = f / (threemu + dsy0);
+        double sy1, dsy1;
+        hos_hard(hd, dpe, sy1, dsy1);
+        const double sc = sy1 / cur.e.phi;
 #pragma unroll
         for (int k = 0; k < 3; ++k) xe[k] = l[k] * sc;
         stage = 1;
@@ -301,7 +350,7 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
       hos_apply(Cf, idet, cur.e.n, z);
       const double ny = (cur.e.n[0] * y[0] + cur.e.n[1] * y[1]) + cur.e.n[2] * y[2];
       const double nz = (cur.e.n[0] * z[0] + cur.e.n[1] * z[1]) + cur.e.n[2] * z[2];
-      ddp = (cur.r4 - ny) / (twomu * nz + H);
+      ddp = (cur.r4 - ny) / (twomu * nz + cur.dsy);
       const double tz = twomu * ddp;
 #pragma unroll
       for (int k = 0; k < 3; ++k) dx[k] = -(y[k] + tz * z[k]);
@@ -346,7 +395,7 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
     hos_system(cur.e, c, ((double)a - 1.0) * cur.e.iphi, Cf, idet);
     hos_apply(Cf, idet, cur.e.n, z);
     const double nz = (cur.e.n[0] * z[0] + cur.e.n[1] * z[1]) + cur.e.n[2] * z[2];
-    const double w = (twomu * twomu) / (twomu * nz + H);
+    const double w = (twomu * twomu) / (twomu * nz + cur.dsy);
     const double ti = twomu * idet;
     const double An00 = (ti * Cf[0] + lam) - w * (z[0] * z[0]);
     const double An01 = (ti * Cf[1] + lam) - w * (z[0] * z[1]);
@@ -386,12 +435,12 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
 }
 
 #if defined(__CUDACC__) && defined(DXM_HOSFORD_KERNELS)  // kernels: instantiated in dxm_hosford_api.cu only
-// SmallStrainArgs is shared with the J2 kernels (same SoA state layout); a.dsu / a.b are unused, a.hos_a = exponent,
+// SmallStrainArgs is shared with the J2 kernels (same SoA state layout and hardening law); a.hos_a = exponent,
 // a.hos_bound = candidate bound.  Per-point
 // properties (a.pE != nullptr) and diagnostics (a.d_flag != nullptr) are run-time switches here: the kernels are
 // templated on the exponent only.
 struct HosPointIO {
-  double eps[6], e_old[6], s_old[6], ep_old[6], p_old, lam, mu, sig0, H;
+  double eps[6], e_old[6], s_old[6], ep_old[6], p_old, lam, mu, sig0, H, dsu, b;
 };
 
 // STREAM: evict-first loads (last use of the inputs); phase A of the tiled kernel keeps them cacheable for phase B
@@ -414,12 +463,17 @@ __device__ __forceinline__ void hos_load(const SmallStrainArgs& a, int64_t i0, H
   io.mu = a.mu;
   io.sig0 = a.sig0;
   io.H = a.H;
+  io.dsu = a.dsu;
+  io.b = a.b;
   if (a.pE) {
     const double E = hos_ld<STREAM>(a.pE + i0), nu = hos_ld<STREAM>(a.pnu + i0);
     io.lam = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu);
     io.mu = E / 2.0 / (1.0 + nu);
     io.sig0 = hos_ld<STREAM>(a.psig0 + i0);
     io.H = hos_ld<STREAM>(a.pH + i0);
+    const double d = hos_ld<STREAM>(a.psigu + i0) - io.sig0;
+    io.dsu = isfinite(d) ? d : 0.0;
+    io.b = hos_ld<STREAM>(a.pb + i0);
   }
 }
 
@@ -461,7 +515,7 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_kernel(const SmallStrainAr
     double sig[6], epsp[6], ct21[21], p_new, resid;
     bool flag, fail;
     int n_iter;
-    hosford_point<false, AT>(io.lam, io.mu, io.sig0, io.H, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old, io.p_old,
+    hosford_point<false, AT>(io.lam, io.mu, io.sig0, io.H, io.dsu, io.b, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old, io.p_old,
                              io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
     hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
   }
@@ -493,7 +547,7 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_tiled_kernel(const SmallSt
         double sig[6], epsp[6], ct21[21], p_new, resid;
         bool flag, fail;
         int n_iter;
-        heavy = hosford_point<true, 0>(io.lam, io.mu, io.sig0, io.H, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old,
+        heavy = hosford_point<true, 0>(io.lam, io.mu, io.sig0, io.H, io.dsu, io.b, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old,
                                        io.p_old, io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
         if (!heavy) hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
       }
@@ -515,7 +569,7 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_tiled_kernel(const SmallSt
       double sig[6], epsp[6], ct21[21], p_new, resid;
       bool flag, fail;
       int n_iter;
-      hosford_point<false, AT>(io.lam, io.mu, io.sig0, io.H, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old, io.p_old,
+      hosford_point<false, AT>(io.lam, io.mu, io.sig0, io.H, io.dsu, io.b, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old, io.p_old,
                                io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
       hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
     }

@@ -44,9 +44,10 @@ enum {
   DXM_J2_VOCE = 2,   /* J2 + sig0 + H p + (sigu-sig0)(1-exp(-b p)), scalar Newton: E,nu,sig0,sigu,b,H */
   DXM_FEFP_VOCE = 3, /* finite-strain FeFp J2 plasticity, same hardening law                        */
   DXM_J2_TABLE = 4,  /* J2 + piecewise-linear isotropic hardening table (dxm_set_hardening_table): E, nu  */
-  DXM_HOSFORD_LINEAR = 5 /* Hosford criterion (even integer exponent a) + linear isotropic hardening: E, nu, sig0 (R0),
-                          * H, a -- demos/multimaterials/IsotropicPlasticHosfordFlowLinear.mfront (a = 10), the
-                          * matrix phase of demos/multimaterials/multimaterials.py:245-254                         */
+  DXM_HOSFORD_LINEAR = 5 /* Hosford criterion (even integer exponent a) + isotropic hardening sig0 + H p
+                          * [+ (sigu-sig0)(1-exp(-b p))]: E, nu, sig0 (R0), H, a [, sigu, b] -- with linear hardening
+                          * demos/multimaterials/IsotropicPlasticHosfordFlowLinear.mfront (a = 10), the matrix phase of
+                          * demos/multimaterials/multimaterials.py:245-254                                          */
 };
 
 /* where a caller-supplied array lives */

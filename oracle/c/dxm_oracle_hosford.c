@@ -4,7 +4,9 @@
  *
  * Restates the behaviour of demos/multimaterials/IsotropicPlasticHosfordFlowLinear.mfront:1-27 (MFront `Implicit` DSL,
  * StandardElastoViscoPlasticity brick: Hooke stress potential, "Plastic" flow with the Hosford criterion {a: 10} and
- * linear isotropic hardening R0 + H p, theta = 1), the matrix phase of demos/multimaterials/multimaterials.py:245-254:
+ * linear isotropic hardening R0 + H p, theta = 1), the matrix phase of demos/multimaterials/multimaterials.py:245-254
+ * (generalised to the hardening law of the J2 behaviours, sig0 + H p + (sigu - sig0)(1 - exp(-b p)), i.e. jaxmat's
+ * GeneralIsotropicHardening(elastic_model, yield_stress, ...) of demos/jax/elastoplasticity/_plane_stress_elastoplasticity.py:45):
  *
  *     sigma_eq = ( 1/2 (|s1-s2|^a + |s2-s3|^a + |s3-s1|^a) )^(1/a)            principal stresses s_k
  *     eel + dp n(sigma) = eel_old + deps ,  n = d sigma_eq / d sigma          (backward Euler, associated flow)
@@ -33,6 +35,44 @@
 #define SQRT2 1.4142135623730951
 #define LS_MAX 10
 #define JACOBI_SWEEPS 8
+
+/* same canonical exp as oracle/c/dxm_oracle.c (Cody-Waite, degree-13 Horner, exact scaling) */
+static double exp_c(double x) {
+  const double LOG2E = 1.4426950408889634, LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+  if (x != x) return x;
+  if (x < -700.0) return 0.0;
+  if (x > 700.0) return INFINITY;
+  const double k = rint(x * LOG2E);
+  const double r = (x - k * LN2_HI) - k * LN2_LO;
+  double y = 1.0 / 6227020800.0;
+  y = y * r + 1.0 / 479001600.0;
+  y = y * r + 1.0 / 39916800.0;
+  y = y * r + 1.0 / 3628800.0;
+  y = y * r + 1.0 / 362880.0;
+  y = y * r + 1.0 / 40320.0;
+  y = y * r + 1.0 / 5040.0;
+  y = y * r + 1.0 / 720.0;
+  y = y * r + 1.0 / 120.0;
+  y = y * r + 1.0 / 24.0;
+  y = y * r + 1.0 / 6.0;
+  y = y * r + 0.5;
+  y = y * r + 1.0;
+  y = y * r + 1.0;
+  return ldexp(y, (int)k);
+}
+
+/* isotropic hardening sigma_Y(p) = sig0 + H p + dsu (1 - exp(-b p)) (the law of the J2 behaviours: linear for
+ * dsu = 0, Voce for H = 0) and its slope, at p = p_old + dp */
+typedef struct {
+  double sig0, H, dsu, b, bdsu, p_old;
+} hard_t;
+
+static void hard_eval(const hard_t* hd, double dp, double* sy, double* dsy) {
+  const double p = hd->p_old + dp;
+  const double e = (hd->bdsu != 0.0) ? exp_c(-(hd->b * p)) : 1.0;
+  *sy = (hd->sig0 + hd->H * p) + hd->dsu * (1.0 - e);
+  *dsy = hd->H + hd->bdsu * e;
+}
 
 /* (x*x)^k, k >= 1, as a product chain */
 static double ipow2(double x, int k) {
@@ -129,15 +169,17 @@ static void jacobi3(const double s[6], double l[3], double Q[3][3]) {
 }
 
 typedef struct {
-  double rs[3], r4, phi, iphi, n[3], h[3], u[3], m2;
+  double rs[3], r4, phi, iphi, n[3], h[3], u[3], m2, dsy;
 } hres_t;
 
-static void hosford_residual(const double x[3], double dp, const double l[3], double twomu, double sy0, double H, int a,
+static void hosford_residual(const double x[3], double dp, const double l[3], double twomu, const hard_t* hd, int a,
                              double inv_a, hres_t* o) {
   hosford_eval(x, a, inv_a, &o->phi, &o->iphi, o->n, o->h, o->u);
   const double c = twomu * dp;
   for (int k = 0; k < 3; ++k) o->rs[k] = (x[k] - l[k]) + c * o->n[k];
-  o->r4 = o->phi - (sy0 + H * dp);
+  double sy;
+  hard_eval(hd, dp, &sy, &o->dsy);
+  o->r4 = o->phi - sy;
   o->m2 = ((o->rs[0] * o->rs[0] + o->rs[1] * o->rs[1]) + o->rs[2] * o->rs[2]) + o->r4 * o->r4;
 }
 
@@ -166,7 +208,7 @@ static void sym3_apply(const double Cf[6], double idet, const double v[3], doubl
   o[2] = ((Cf[2] * v[0] + Cf[4] * v[1]) + Cf[5] * v[2]) * idet;
 }
 
-/* props: E, nu, sig0 (R0), H scalars or per point (pp/per as in dxm_oracle.c, entries 0..3); a even integer >= 2 */
+/* props: E, nu, sig0 (R0), H, sigu, b scalars or per point (pp/per as in dxm_oracle.c); a even integer >= 2 */
 void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double* s_old, const double* p_old_a,
                  const double* ep_old, const double* const* pp, const int* per, int a, int newton_cap, double rtol,
                  double bound,
@@ -175,6 +217,9 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
   for (int64_t pt = 0; pt < n; ++pt) {
     const double E = per[0] ? pp[0][pt] : pp[0][0], nu = per[1] ? pp[1][pt] : pp[1][0];
     const double sig0 = per[2] ? pp[2][pt] : pp[2][0], H = per[3] ? pp[3][pt] : pp[3][0];
+    const double sigu = per[4] ? pp[4][pt] : pp[4][0], bb = per[5] ? pp[5][pt] : pp[5][0];
+    double dsu = sigu - sig0;
+    if (!isfinite(dsu)) dsu = 0.0;
     const double lam = E * nu / (1 + nu) / (1 - 2 * nu);
     const double mu = E / 2 / (1 + nu);
     const double twomu = 2.0 * mu, threemu = 3.0 * mu;
@@ -191,7 +236,9 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
     double ss = s[0] * s[0] + s[1] * s[1];
     for (int i = 2; i < 6; ++i) ss = ss + s[i] * s[i];
     const double seq = sqrt(1.5 * ss);
-    const double sy0 = sig0 + H * p_old;
+    const hard_t hd = {sig0, H, dsu, bb, bb * dsu, p_old};
+    double sy0, dsy0;
+    hard_eval(&hd, 0.0, &sy0, &dsy0);
     const double am1 = (double)a - 1.0, inv_a = 1.0 / (double)a;
 
     int flag = 0, n_iter = 0, fail = 0;
@@ -205,10 +252,12 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
       flag = f > 0.0;
       if (flag) {
         /* start on the yield surface along the trial direction, dp from the J2-like estimate */
-        dp = f / (threemu + H);
-        const double sc = (sy0 + H * dp) / cur.phi;
+        dp = f / (threemu + dsy0);
+        double sy1, dsy1;
+        hard_eval(&hd, dp, &sy1, &dsy1);
+        const double sc = sy1 / cur.phi;
         double x[3] = {l[0] * sc, l[1] * sc, l[2] * sc};
-        hosford_residual(x, dp, l, twomu, sy0, H, a, inv_a, &cur);
+        hosford_residual(x, dp, l, twomu, &hd, a, inv_a, &cur);
         const double tol = rtol * seq;
         for (int it = 0;; ++it) {
           const double res = fmax(fmax(fabs(cur.rs[0]), fabs(cur.rs[1])), fmax(fabs(cur.rs[2]), fabs(cur.r4)));
@@ -220,7 +269,7 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
           sym3_apply(Cf, idet, cur.n, z);
           const double ny = (cur.n[0] * y[0] + cur.n[1] * y[1]) + cur.n[2] * y[2];
           const double nz = (cur.n[0] * z[0] + cur.n[1] * z[1]) + cur.n[2] * z[2];
-          const double ddp = (cur.r4 - ny) / (twomu * nz + H);
+          const double ddp = (cur.r4 - ny) / (twomu * nz + cur.dsy);
           const double tz = twomu * ddp;
           const double dx[3] = {-(y[0] + tz * z[0]), -(y[1] + tz * z[1]), -(y[2] + tz * z[2])};
           double t = 1.0;
@@ -229,7 +278,7 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
           for (int ls = 0;; ++ls) {
             for (int k = 0; k < 3; ++k) xn[k] = x[k] + t * dx[k];
             dpn = dp + t * ddp;
-            hosford_residual(xn, dpn, l, twomu, sy0, H, a, inv_a, &nxt);
+            hosford_residual(xn, dpn, l, twomu, &hd, a, inv_a, &nxt);
             if (nxt.m2 < cur.m2 || ls == LS_MAX) break;
             t = 0.5 * t;
           }
@@ -279,7 +328,7 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
       hosford_system(&cur, c, am1 * cur.iphi, Cf, &idet);
       sym3_apply(Cf, idet, cur.n, z);
       const double nz = (cur.n[0] * z[0] + cur.n[1] * z[1]) + cur.n[2] * z[2];
-      const double w = (twomu * twomu) / (twomu * nz + H); /* (2 mu z)(2 mu z)^T / (2 mu n.z + H) */
+      const double w = (twomu * twomu) / (twomu * nz + cur.dsy); /* (2 mu z)(2 mu z)^T / (2 mu n.z + sigma_Y'(p)) */
       const double ti = twomu * idet;
       /* normal block An (symmetric): 2 mu A^-1 + lam - w z z^T */
       double An[3][3];

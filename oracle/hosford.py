@@ -17,7 +17,8 @@ from .small_strain import advance, zero_state  # noqa: F401  (same state layout:
 
 
 def integrate(eps, state, props, newton_cap=25, rtol=1e-12):
-    """props: ``E, nu, sig0`` (R0), ``H`` (scalars or per-point arrays) and the even integer exponent ``a``.
+    """props: ``E, nu, sig0`` (R0), ``H`` and optionally ``sigu, b`` (Voce term) -- scalars or per-point arrays -- and the
+    even integer exponent ``a``.
     Returns the same dictionary as ``oracle.small_strain.integrate``."""
     return cport.hosford(eps, state, dict(props, H=props.get("H", 0.0)), newton_cap, rtol)
 
@@ -53,4 +54,10 @@ def implicit_residual(sig, dp, sig_tr, p_old, props):
     C : n = 2 mu n) and the yield condition; returns (6-vector, scalar)."""
     mu = props["E"] / 2 / (1 + props["nu"])
     n = flow_direction(sig, props["a"])
-    return sig - sig_tr + 2 * mu * dp * n, sigma_eq(sig, props["a"]) - (props["sig0"] + props.get("H", 0.0) * (p_old + dp))
+    return sig - sig_tr + 2 * mu * dp * n, sigma_eq(sig, props["a"]) - yield_stress(p_old + dp, props)
+
+
+def yield_stress(p, props):
+    """sig0 + H p + (sigu - sig0)(1 - exp(-b p)) -- linear for sigu = sig0, Voce for H = 0 (tests/test_FeFp_jax.py:14-15)."""
+    sig0 = props["sig0"]
+    return sig0 + props.get("H", 0.0) * p + (props.get("sigu", sig0) - sig0) * (1.0 - np.exp(-props.get("b", 0.0) * p))

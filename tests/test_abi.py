@@ -80,8 +80,10 @@ def test_protocol_surface_without_gpu(jm):
     assert g.material_properties == {"E": 70e3, "nu": 0.3, "sig0": 200.0, "H": 10.0, "a": 10}  # the demo's exponent
     with pytest.raises(ValueError):
         jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.LinearHardening(sig0=1.0), equivalent_stress=jm.Hosford(a=7))
+    gv = jm.CUDAMaterial(jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.VoceHardening(sig0=1.0, sigu=2.0, b=1.0)))
+    assert set(gv.material_properties) == {"E", "nu", "sig0", "sigu", "b", "H", "a"}
     with pytest.raises(TypeError):
-        jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.VoceHardening(sig0=1.0, sigu=2.0, b=1.0))
+        jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.TabulatedHardening(p=[0.0, 1.0], sig=[1.0, 2.0]))
     with pytest.raises(TypeError):
         jm.CUDAMaterial(jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=lambda p: 1.0))
     with pytest.raises(KeyError):

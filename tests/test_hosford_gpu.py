@@ -17,9 +17,11 @@ DEMO = dict(E=70e3, nu=0.3, sig0=200.0, H=10.0, a=10)  # multimaterials.py:245-2
 
 
 def make(jm, props, n, diag=True):
+    hard = (jm.VoceHardening(sig0=props["sig0"], sigu=props["sigu"], b=props["b"], H=props.get("H", 0.0)) if "sigu" in props
+            else jm.LinearHardening(sig0=props["sig0"], H=props["H"]))
     beh = jm.GeneralIsotropicHardening(
         elasticity=jm.LinearElasticIsotropic(E=props["E"], nu=props["nu"]),
-        yield_stress=jm.LinearHardening(sig0=props["sig0"], H=props["H"]),
+        yield_stress=hard,
         equivalent_stress=jm.Hosford(a=props["a"]),
     )
     m = jm.CUDAMaterial(beh)
@@ -158,3 +160,38 @@ def test_nan_gradient_is_reported_as_a_failed_point(jm):
     assert any("failed" in str(x.message) for x in w)
     ok = np.arange(n) != 7
     assert np.array_equal(out[0][ok], ref["stress"][ok]) and np.array_equal(out[2][ok], ref["Ct"][ok])
+
+
+@pytest.mark.parametrize("split", ["0", "1"])
+@pytest.mark.parametrize("a", [2, 10])
+def test_voce_hardening_behind_the_hosford_criterion(jm, monkeypatch, split, a):
+    """jaxmat's GeneralIsotropicHardening(elastic, Voce yield stress, ...) with the Hosford norm: bit-exact vs the
+    oracle; per-point saturation stress; a = 2 agrees with the J2 + Voce kernel to rounding."""
+    monkeypatch.setenv("DXM_HOS_SPLIT", split)
+    props = dict(E=70e3, nu=0.3, sig0=350.0, sigu=500.0, b=1e3, H=25.0, a=a)
+    n = 40_001
+    m = make(jm, props, n)
+    sigu = np.where(np.arange(n) % 2 == 0, 500.0, 430.0)
+    m.update_material_property("sigu", sigu)
+    st = ss.zero_state(n)
+    for k in range(1, 4):
+        eps = synth.strain(n, 6, 1.25e-2, k, 3)
+        out = m.integrate(eps)
+        ref = ho.integrate(eps, st, dict(props, sigu=sigu))
+        check(m, out, ref)
+        m.data_manager.update()
+        st = ss.advance(ref)
+    assert 0.3 < ref["flag"].mean() < 0.95 and ref["n_iter"].max() <= 8
+    if a == 2:
+        j = jm.CUDAMaterial(jm.vonMisesIsotropicHardening(
+            elasticity=jm.LinearElasticIsotropic(E=props["E"], nu=props["nu"]),
+            yield_stress=jm.VoceHardening(sig0=350.0, sigu=500.0, b=1e3, H=25.0)))
+        j.set_data_manager(n)
+        j.update_material_property("sigu", sigu)
+        h2 = make(jm, props, n, diag=False)
+        h2.update_material_property("sigu", sigu)
+        eps = synth.strain(n, 6, 1.25e-2, 1, 1)
+        fj, _, cj = j.integrate(eps)
+        fh, _, ch = h2.integrate(eps)
+        np.testing.assert_allclose(fh, fj, rtol=1e-11, atol=1e-9)
+        np.testing.assert_allclose(ch, cj, rtol=1e-8, atol=1e-7 * props["E"])

@@ -45,7 +45,8 @@ def run(lib, eps, st, props, split=0, generic=0):
     a = props["a"]
     bound = (2.0 ** (a - 1) + 1.0) ** (1.0 / a) / np.sqrt(3.0) * (1.0 + 1e-9)  # hosford_bound(), dxm_hosford_api.cu
     lib.hosford_host(ctypes.c_int64(n), c(eps), c(e_old), c(s_old), c(p_old), c(ep_old), ctypes.c_double(props["E"]),
-                     ctypes.c_double(props["nu"]), ctypes.c_double(props["sig0"]), ctypes.c_double(props["H"]),
+                     ctypes.c_double(props["nu"]), ctypes.c_double(props["sig0"]), ctypes.c_double(props.get("H", 0.0)),
+                     ctypes.c_double(props.get("sigu", props["sig0"])), ctypes.c_double(props.get("b", 0.0)),
                      ctypes.c_int(props["a"]), ctypes.c_double(bound), c(sig), c(p), c(epsp), c(ct), c(flag), c(it), c(rs),
                      c(fail), ctypes.c_int(split), ctypes.byref(ncand), ctypes.c_int(generic))
     return {"candidates": ncand.value, "strain": eps, "stress": sig, "p": p, "epsp": epsp, "Ct": ct, "flag": flag, "n_iter": it, "resid": rs,
@@ -107,3 +108,20 @@ def test_kernel_point_routine_random_states_and_properties(host, seed):
             got = run(host, eps, st, props, split)
             for key in ("flag", "n_iter", "fail", "stress", "p", "epsp", "Ct", "resid"):
                 assert np.array_equal(got[key], ref[key]), (key, a, split)
+
+
+@pytest.mark.parametrize("a", [2, 6, 10, 14])
+def test_kernel_point_routine_voce_hardening(host, a):
+    """General hardening law (Voce term + linear term) behind the Hosford criterion: kernel routine == oracle."""
+    props = dict(E=70e3, nu=0.3, sig0=350.0, sigu=500.0, b=1e3, H=25.0, a=a)
+    n = 20000
+    st = ss.zero_state(n)
+    for k in range(1, 4):
+        eps = synth.strain(n, a, 1.25e-2, k, 3)
+        ref = ho.integrate(eps, st, props)
+        for split in (0, 1):
+            got = run(host, eps, st, props, split)
+            for key in ("flag", "n_iter", "fail", "stress", "p", "epsp", "Ct", "resid"):
+                assert np.array_equal(got[key], ref[key]), (key, k, split)
+        st = ss.advance(ref)
+    assert 0.3 < ref["flag"].mean() < 0.95 and ref["fail"].sum() == 0

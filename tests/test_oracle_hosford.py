@@ -54,7 +54,7 @@ def test_solution_satisfies_the_independent_implicit_system(a):
         sig_tr = st["stress"] + (out["strain"] - st["strain"]) @ C
         for i in range(n):
             phi = ho.sigma_eq(out["stress"][i], a)
-            sy = props["sig0"] + props["H"] * out["p"][i]
+            sy = ho.yield_stress(out["p"][i], props)
             if out["flag"][i]:
                 seen += 1
                 r6, r1 = ho.implicit_residual(out["stress"][i], out["p"][i] - st["p"][i], sig_tr[i], st["p"][i], props)
@@ -180,3 +180,49 @@ def test_candidate_bound_is_the_pure_shear_ratio(a):
     loose = ho.integrate(eps, ss.zero_state(n), dict(DEMO, a=a, bound=1e30))
     for key in ("stress", "p", "epsp", "Ct", "flag", "n_iter", "resid", "fail"):
         assert np.array_equal(tight[key], loose[key]), key
+
+
+VOCE = dict(E=70e3, nu=0.3, sig0=350.0, sigu=500.0, b=1e3, H=0.0)  # plane_elastoplasticity.py:60-69
+
+
+def test_voce_hardening_exponent_two_is_the_j2_voce_oracle():
+    """GeneralIsotropicHardening(elastic, Voce yield stress, Hosford a = 2) == vonMisesIsotropicHardening(elastic, Voce)."""
+    n = 3000
+    st_h, st_j = ss.zero_state(n), ss.zero_state(n)
+    for k in range(1, 5):
+        eps = synth.strain(n, 1, 1.25e-2, k, 4)
+        h = ho.integrate(eps, st_h, dict(VOCE, a=2))
+        j = ss.integrate(eps, st_j, VOCE)
+        assert np.array_equal(h["flag"], j["flag"])
+        np.testing.assert_allclose(h["stress"], j["stress"], rtol=1e-11, atol=1e-9)
+        np.testing.assert_allclose(h["p"], j["p"], rtol=1e-9, atol=1e-16)
+        np.testing.assert_allclose(h["Ct"], j["Ct"], rtol=1e-8, atol=1e-7 * VOCE["E"])
+        st_h, st_j = ss.advance(h), ss.advance(j)
+    assert h["flag"].mean() > 0.5
+
+
+@pytest.mark.parametrize("a", [6, 10])
+def test_voce_hardening_solution_and_tangent(a):
+    props = dict(VOCE, a=a, H=25.0)
+    n = 40
+    (st, out) = history(props, n, 1.0e-2, 3, seed=a)[-1]
+    assert out["fail"].sum() == 0 and out["flag"].sum() > 10
+    lam = props["E"] * props["nu"] / (1 + props["nu"]) / (1 - 2 * props["nu"])
+    mu = props["E"] / 2 / (1 + props["nu"])
+    C = 2 * mu * np.eye(6)
+    C[:3, :3] += lam
+    sig_tr = st["stress"] + (out["strain"] - st["strain"]) @ C
+    for i in np.flatnonzero(out["flag"]):
+        r6, r1 = ho.implicit_residual(out["stress"][i], out["p"][i] - st["p"][i], sig_tr[i], st["p"][i], props)
+        assert np.abs(r6).max() < 2e-6 * props["sig0"] and abs(r1) < 1e-9 * props["sig0"]
+    eps, h = out["strain"], 1e-8
+    J = np.zeros((n, 6, 6))
+    for i in range(6):
+        d = np.zeros(6)
+        d[i] = h
+        plus, minus = ho.integrate(eps + d, st, props), ho.integrate(eps - d, st, props)
+        J[:, :, i] = (plus["stress"] - minus["stress"]) / (2 * h)
+        J[(plus["flag"] != out["flag"]) | (minus["flag"] != out["flag"]), :, i] = np.nan
+    good = ~np.isnan(J).any(axis=(1, 2))
+    assert out["flag"][good].sum() > 5
+    assert (np.abs(out["Ct"][good] - J[good]).max(axis=(1, 2)) / props["E"]).max() < 2e-6
