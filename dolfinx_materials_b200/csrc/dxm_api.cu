@@ -265,7 +265,8 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
     bool tiled = count >= 32768;
     if (tiled && h->prev_points > 0) tiled = (double)h->prev_plastic < kHosSplitMaxPlastic * (double)h->prev_points;
     if (e) tiled = std::atoi(e) != 0;
-    HosLaunch cfg{h->num_sms, h->stream, tiled, kTilesPerCta};
+    // sigu is only ever set for a hardening law with a saturation term (VoceHardening); otherwise it follows sig0
+    HosLaunch cfg{h->num_sms, h->stream, h->set[4], tiled, kTilesPerCta};
     int launches = 0;
     const int rc = launch_hosford(a, cfg, &launches);
     g_launches.fetch_add(launches);

@@ -249,9 +249,11 @@ DXM_HD void hos_mandel_pair(const double (&V)[3][3], double (&m)[6]) {
 // AT > 0: the exponent as a compile-time constant (the power chains unroll into straight DMUL sequences; with a
 // run-time exponent 35 % of the executed instructions were loop bookkeeping, profiles/r01g_hosford_v2_*); AT == 0: a_rt.
 // bound: (2^(a-1)+1)^(1/a)/sqrt(3) (1 + 1e-9) >= sigma_eq / seq_Mises for every stress state (maximum at pure shear).
-template <bool LIGHT, int AT>
-DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, const double H, const double dsu,
-                          const double b, const int a_rt, const double bound, const double (&eps)[6], const double (&e_old)[6], const double (&s_old)[6],
+// VOCE == false: the saturation term is absent at compile time (dsu = b = 0: same bits as the general law with
+// dsu = 0, without its registers -- carrying it at run time cost the linear-hardening case 14-30 %, profiles/r01l).
+template <bool LIGHT, int AT, bool VOCE>
+DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, const double H, const double dsu_rt,
+                          const double b_rt, const int a_rt, const double bound, const double (&eps)[6], const double (&e_old)[6], const double (&s_old)[6],
                           const double p_old, const double (&ep_old)[6], double (&sig)[6], double& p_new,
                           double (&epsp)[6], double (&ct21)[21], bool& flag, int& n_iter, double& resid,
                           bool& fail) {
@@ -276,7 +278,8 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
 #pragma unroll
   for (int i = 2; i < 6; ++i) ss = ss + s[i] * s[i];
   const double seq = sqrt(1.5 * ss);
-  const HosHard hd{sig0, H, dsu, b, b * dsu, p_old};
+  const double dsu = VOCE ? dsu_rt : 0.0, b = VOCE ? b_rt : 0.0;
+  const HosHard hd{sig0, H, dsu, b, VOCE ? b * dsu : 0.0, p_old};
   double sy0, dsy0;
   hos_hard(hd, 0.0, sy0, dsy0);
 
@@ -447,7 +450,7 @@ struct HosPointIO {
 template <bool STREAM>
 __device__ __forceinline__ double hos_ld(const double* p) { return STREAM ? __ldcs(p) : __ldg(p); }
 
-template <bool STREAM>
+template <bool STREAM, bool VOCE>
 __device__ __forceinline__ void hos_load(const SmallStrainArgs& a, int64_t i0, HosPointIO& io) {
   const int64_t ld = a.ld;
 #pragma unroll
@@ -471,9 +474,11 @@ __device__ __forceinline__ void hos_load(const SmallStrainArgs& a, int64_t i0, H
     io.mu = E / 2.0 / (1.0 + nu);
     io.sig0 = hos_ld<STREAM>(a.psig0 + i0);
     io.H = hos_ld<STREAM>(a.pH + i0);
-    const double d = hos_ld<STREAM>(a.psigu + i0) - io.sig0;
-    io.dsu = isfinite(d) ? d : 0.0;
-    io.b = hos_ld<STREAM>(a.pb + i0);
+    if (VOCE) {
+      const double d = hos_ld<STREAM>(a.psigu + i0) - io.sig0;
+      io.dsu = isfinite(d) ? d : 0.0;
+      io.b = hos_ld<STREAM>(a.pb + i0);
+    }
   }
 }
 
@@ -502,7 +507,7 @@ __device__ __forceinline__ void hos_finish(const SmallStrainArgs& a, int64_t i0,
 }
 
 // fused: every thread runs the full routine on its own point (small batches, mostly-plastic batches, A/B reference)
-template <int AT>
+template <int AT, bool VOCE>
 __global__ void __launch_bounds__(128, 3) dxm_hosford_kernel(const SmallStrainArgs a) {
   const int64_t ntile = (a.count + blockDim.x - 1) / blockDim.x;
   PointStats acc;
@@ -511,11 +516,11 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_kernel(const SmallStrainAr
     if (loc >= a.count) continue;
     const int64_t i0 = a.start + loc;
     HosPointIO io;
-    hos_load<true>(a, i0, io);
+    hos_load<true, VOCE>(a, i0, io);
     double sig[6], epsp[6], ct21[21], p_new, resid;
     bool flag, fail;
     int n_iter;
-    hosford_point<false, AT>(io.lam, io.mu, io.sig0, io.H, io.dsu, io.b, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old, io.p_old,
+    hosford_point<false, AT, VOCE>(io.lam, io.mu, io.sig0, io.H, io.dsu, io.b, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old, io.p_old,
                              io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
     hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
   }
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_kernel(const SmallStrainAr
 // stores issued moments earlier by the same CTA -- a device-wide queue + second kernel (r01g) lost exactly that
 // locality when few points are candidates (scattered 8-byte accesses) and was slower in every regime.
 constexpr int kHosTile = 1024;
-template <int AT>
+template <int AT, bool VOCE>
 __global__ void __launch_bounds__(128, 3) dxm_hosford_tiled_kernel(const SmallStrainArgs a) {
   __shared__ unsigned s_queue[kHosTile];
   __shared__ unsigned s_count;
@@ -543,11 +548,11 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_tiled_kernel(const SmallSt
       if (loc < a.count) {
         const int64_t i0 = a.start + loc;
         HosPointIO io;
-        hos_load<false>(a, i0, io);
+        hos_load<false, VOCE>(a, i0, io);
         double sig[6], epsp[6], ct21[21], p_new, resid;
         bool flag, fail;
         int n_iter;
-        heavy = hosford_point<true, 0>(io.lam, io.mu, io.sig0, io.H, io.dsu, io.b, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old,
+        heavy = hosford_point<true, 0, VOCE>(io.lam, io.mu, io.sig0, io.H, io.dsu, io.b, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old,
                                        io.p_old, io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
         if (!heavy) hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
       }
@@ -565,11 +570,11 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_tiled_kernel(const SmallSt
     for (unsigned q = threadIdx.x; q < total; q += blockDim.x) {
       const int64_t i0 = a.start + tile * kHosTile + (int64_t)s_queue[q];
       HosPointIO io;
-      hos_load<true>(a, i0, io);
+      hos_load<true, VOCE>(a, i0, io);
       double sig[6], epsp[6], ct21[21], p_new, resid;
       bool flag, fail;
       int n_iter;
-      hosford_point<false, AT>(io.lam, io.mu, io.sig0, io.H, io.dsu, io.b, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old, io.p_old,
+      hosford_point<false, AT, VOCE>(io.lam, io.mu, io.sig0, io.H, io.dsu, io.b, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old, io.p_old,
                                io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
       hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
     }
@@ -584,6 +589,7 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_tiled_kernel(const SmallSt
 struct HosLaunch {
   int num_sms;
   cudaStream_t stream;
+  bool voce;   // the hardening law has a saturation term (sigu was set): general-law instantiation
   bool tiled;  // tiled kernel (stream + CTA-local candidate queue + packed local solves) instead of the fused one
   int tiles_per_cta;
 };

@@ -13,11 +13,11 @@ double hosford_bound(int a) {
 }
 
 namespace {
-template <int AT>
+template <int AT, bool VOCE>
 int launch_at(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches) {
   if (cfg.tiled) {
     const int64_t ntile = (a.count + kHosTile - 1) / kHosTile;
-    dxm_hosford_tiled_kernel<AT><<<(unsigned)(ntile < 1 ? 1 : ntile), 128, 0, cfg.stream>>>(a);
+    dxm_hosford_tiled_kernel<AT, VOCE><<<(unsigned)(ntile < 1 ? 1 : ntile), 128, 0, cfg.stream>>>(a);
     ++*launches;
     CK(cudaGetLastError());
     return 0;
@@ -25,7 +25,7 @@ int launch_at(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches) {
   const int64_t ntile = (a.count + 127) / 128;
   int64_t grid = (ntile + cfg.tiles_per_cta - 1) / cfg.tiles_per_cta;
   if (grid < 1) grid = 1;
-  dxm_hosford_kernel<AT><<<(unsigned)grid, 128, 0, cfg.stream>>>(a);
+  dxm_hosford_kernel<AT, VOCE><<<(unsigned)grid, 128, 0, cfg.stream>>>(a);
   ++*launches;
   CK(cudaGetLastError());
   return 0;
@@ -35,11 +35,19 @@ int launch_at(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches) {
 // exponents with an unrolled instantiation: 6 and 8 (the usual bcc / fcc fits) and 10 (the reference demo); any other
 // even exponent runs the generic loops -- same operation order, same bits
 int launch_hosford(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches) {
+  if (cfg.voce) {
+    switch (a.hos_a) {
+      case 6: return launch_at<6, true>(a, cfg, launches);
+      case 8: return launch_at<8, true>(a, cfg, launches);
+      case 10: return launch_at<10, true>(a, cfg, launches);
+      default: return launch_at<0, true>(a, cfg, launches);
+    }
+  }
   switch (a.hos_a) {
-    case 6: return launch_at<6>(a, cfg, launches);
-    case 8: return launch_at<8>(a, cfg, launches);
-    case 10: return launch_at<10>(a, cfg, launches);
-    default: return launch_at<0>(a, cfg, launches);
+    case 6: return launch_at<6, false>(a, cfg, launches);
+    case 8: return launch_at<8, false>(a, cfg, launches);
+    case 10: return launch_at<10, false>(a, cfg, launches);
+    default: return launch_at<0, false>(a, cfg, launches);
   }
 }
 

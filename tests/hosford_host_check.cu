@@ -6,7 +6,7 @@
 #include "../dolfinx_materials_b200/csrc/dxm_hosford.cuh"
 
 namespace {
-template <int AT>
+template <int AT, bool VOCE>
 void run(int64_t n, const double* eps, const double* e_old, const double* s_old, const double* p_old,
          const double* ep_old, double E, double nu, double sig0, double H, double sigu, double b, int a, double bound, double* sig, double* p,
          double* epsp, double* ct, uint8_t* flag, int32_t* n_iter, double* resid, uint8_t* fail, int split,
@@ -19,17 +19,27 @@ extern "C" void hosford_host(int64_t n, const double* eps, const double* e_old, 
                              double* sig, double* p, double* epsp, double* ct, uint8_t* flag, int32_t* n_iter,
                              double* resid, uint8_t* fail, int split, int64_t* n_candidates, int force_generic) {
 #define DXM_ARGS n, eps, e_old, s_old, p_old, ep_old, E, nu, sig0, H, sigu, b, a, bound, sig, p, epsp, ct, flag, n_iter, resid, fail, split, n_candidates
-  if (force_generic) return run<0>(DXM_ARGS);
+  const bool voce = sigu != sig0;  // the product keys on "sigu was set" (dxm_api.cu); equivalent for this harness
+  if (voce) {
+    if (force_generic) return run<0, true>(DXM_ARGS);
+    switch (a) {
+      case 6: return run<6, true>(DXM_ARGS);
+      case 8: return run<8, true>(DXM_ARGS);
+      case 10: return run<10, true>(DXM_ARGS);
+      default: return run<0, true>(DXM_ARGS);
+    }
+  }
+  if (force_generic) return run<0, false>(DXM_ARGS);
   switch (a) {
-    case 6: return run<6>(DXM_ARGS);
-    case 8: return run<8>(DXM_ARGS);
-    case 10: return run<10>(DXM_ARGS);
-    default: return run<0>(DXM_ARGS);
+    case 6: return run<6, false>(DXM_ARGS);
+    case 8: return run<8, false>(DXM_ARGS);
+    case 10: return run<10, false>(DXM_ARGS);
+    default: return run<0, false>(DXM_ARGS);
   }
 }
 
 namespace {
-template <int AT>
+template <int AT, bool VOCE>
 void run(int64_t n, const double* eps, const double* e_old, const double* s_old, const double* p_old,
          const double* ep_old, double E, double nu, double sig0, double H, double sigu, double b, int a, double bound, double* sig, double* p,
          double* epsp, double* ct, uint8_t* flag, int32_t* n_iter, double* resid, uint8_t* fail, int split,
@@ -51,10 +61,10 @@ void run(int64_t n, const double* eps, const double* e_old, const double* s_old,
     // split != 0 replays the tiled kernel: phase A finishes the clearly elastic points and reports the candidates,
     // which the full routine then recomputes from scratch (dxm_hosford_tiled_kernel)
     bool heavy = true;
-    if (split) heavy = dxm::hosford_point<true, 0>(lam, mu, sig0, H, dsu, b, a, bound, e1, e0, s0, p_old[i], ep0, so, pn, epo, ct21, fl, it, rs, fa);
+    if (split) heavy = dxm::hosford_point<true, 0, VOCE>(lam, mu, sig0, H, dsu, b, a, bound, e1, e0, s0, p_old[i], ep0, so, pn, epo, ct21, fl, it, rs, fa);
     if (heavy) {
       if (split) ++*n_candidates;
-      dxm::hosford_point<false, AT>(lam, mu, sig0, H, dsu, b, a, bound, e1, e0, s0, p_old[i], ep0, so, pn, epo, ct21, fl, it, rs, fa);
+      dxm::hosford_point<false, AT, VOCE>(lam, mu, sig0, H, dsu, b, a, bound, e1, e0, s0, p_old[i], ep0, so, pn, epo, ct21, fl, it, rs, fa);
     }
     for (int c = 0; c < 6; ++c) {
       sig[i * 6 + c] = so[c];
