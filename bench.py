@@ -339,8 +339,17 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     bind_to_gpu_numa_node(local)
+    # stdout carries exactly ONE JSON line: everything else that writes to file descriptor 1 -- NCCL prints its
+    # "NCCL version ..." banner there from C, whatever NCCL_DEBUG_FILE says -- is sent to stderr for the whole run;
+    # the result line goes to a private duplicate of the original stdout (emit()).
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(out_fd, (json.dumps(obj) + "\n").encode())
+
     if world > 1:
-        # keep stdout to the one JSON line: NCCL's own banner ("NCCL version ...") goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     build.build_library()
@@ -506,7 +515,7 @@ def run_ours(args):
             "stats": {"plastic_fraction": s.n_plastic / (n * world), "n_fail": s.n_fail, "max_iter": s.max_iter,
                       "max_residual": s.max_residual},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
