@@ -48,6 +48,11 @@ SIGNATURES = {
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
          ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(Stats)],
     ),
+    "dxm_integrate_range": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(Stats)],
+    ),
     "dxm_last_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Stats)]),
     "dxm_update": (ctypes.c_int, [ctypes.c_void_p]),
     "dxm_revert": (ctypes.c_int, [ctypes.c_void_p]),

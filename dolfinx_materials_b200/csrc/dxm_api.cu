@@ -757,8 +757,9 @@ int dxm_last_stats(dxm_handle* h, dxm_stats* stats) {
   return 0;
 }
 
-int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double* flux, double* isv,
-                  double* ct, int out_mem, dxm_stats* stats) {
+// points [start, start + count) of the handle; the host arrays hold `count` rows (dxm_integrate: the whole handle)
+static int integrate_impl(dxm_handle* h, int64_t start, int64_t count, const double* grad, int mem, double dt,
+                          double* flux, double* isv, double* ct, int out_mem, dxm_stats* stats) {
   if (!h) return fail("dxm_integrate: NULL handle");
   if (set_device(h)) return -1;
   if (!h->set[0] || !h->set[1]) return fail("dxm_integrate: properties E and nu must be set");
@@ -768,20 +769,25 @@ int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double*
     return fail("dxm_integrate: property sig0 must be set");
   }
   if (mem != DXM_MEM_RESIDENT && !grad) return fail("dxm_integrate: grad is NULL");
+  if (start < 0 || count <= 0 || start + count > h->n || (start & 1))
+    return fail("dxm_integrate_range: need 0 <= start (even), count > 0, start + count <= n");
+  const bool whole = start == 0 && count == h->n;
+  if (!whole && mem != DXM_MEM_HOST && !(mem == DXM_MEM_RESIDENT && !flux && !isv && !ct))
+    return fail("dxm_integrate_range: partial ranges take host arrays, or resident gradients without outputs");
   if (finish_stats(h)) return -1;  // drain a previous asynchronous call
   CK(cudaMemsetAsync(h->d_stats, 0, sizeof(StatSlot) * kStatSlots, h->stream));
   h->n_ev_used = 0;
   h->last = dxm_stats{};
-  h->last.n_points = h->n;
+  h->last.n_points = count;
   double* s1 = h->gen[1 - h->i0];
-  const int64_t ld = h->ld, n = h->n;
+  const int64_t ld = h->ld, n = count;
   const int isv_row = h->ngrad + h->nflux;
   const bool any_out = flux || isv || ct;
 
   if (mem == DXM_MEM_RESIDENT || mem == DXM_MEM_DEVICE) {
     if (mem == DXM_MEM_DEVICE)
       if (launch_aos_to_soa(h, h->stream, grad, h->ngrad, 0, s1, 0, n, h->ngrad)) return -1;
-    if (timed_update(h, 0, n, dt)) return -1;
+    if (timed_update(h, start, n, dt)) return -1;
     h->s1_valid = true;
     if (any_out) {
       if (out_mem == DXM_MEM_DEVICE) {
@@ -853,19 +859,19 @@ int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double*
                          cudaMemcpyHostToDevice, h->s_in));
       CK(cudaEventRecord(h->ev_in[b], h->s_in));
       CK(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
-      if (launch_aos_to_soa(h, h->stream, h->d_in[b], h->ngrad, 0, s1, s, m, h->ngrad)) return -1;
+      if (launch_aos_to_soa(h, h->stream, h->d_in[b], h->ngrad, 0, s1, start + s, m, h->ngrad)) return -1;
       CK(cudaEventRecord(h->ev_in_free[b], h->stream));
-      if (timed_update(h, s, m, dt)) return -1;
+      if (timed_update(h, start + s, m, dt)) return -1;
       if (any_out) {
         CK(cudaStreamWaitEvent(h->stream, h->ev_out_free[b], 0));
         double* o = h->d_out[b];
-        if (flux && launch_soa_to_aos(h, h->stream, s1 + (int64_t)h->ngrad * ld, s, o, nf, 0, m, nf))
+        if (flux && launch_soa_to_aos(h, h->stream, s1 + (int64_t)h->ngrad * ld, start + s, o, nf, 0, m, nf))
           return -1;
-        if (isv && launch_soa_to_aos(h, h->stream, s1 + (int64_t)isv_row * ld, s, o + CH * nf, ni, 0,
+        if (isv && launch_soa_to_aos(h, h->stream, s1 + (int64_t)isv_row * ld, start + s, o + CH * nf, ni, 0,
                                      m, ni))
           return -1;
-        if (ct && (mirror ? launch_soa_to_aos(h, h->stream, h->ct, s, o + CH * (nf + ni), ncs, 0, m, ncs, 0)
-                          : launch_soa_to_aos(h, h->stream, h->ct, s, o + CH * (nf + ni), nc, 0, m, nc, ncs != nc)))
+        if (ct && (mirror ? launch_soa_to_aos(h, h->stream, h->ct, start + s, o + CH * (nf + ni), ncs, 0, m, ncs, 0)
+                          : launch_soa_to_aos(h, h->stream, h->ct, start + s, o + CH * (nf + ni), nc, 0, m, nc, ncs != nc)))
           return -1;
         CK(cudaEventRecord(h->ev_packed[b], h->stream));
         CK(cudaStreamWaitEvent(h->s_out, h->ev_packed[b], 0));
@@ -905,6 +911,16 @@ int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double*
   if (finish_stats(h)) return -1;
   *stats = h->last;
   return (int)std::min<int64_t>(h->last.n_fail, 0x7fffffff);
+}
+
+int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double* flux, double* isv,
+                  double* ct, int out_mem, dxm_stats* stats) {
+  return integrate_impl(h, 0, h ? h->n : 0, grad, mem, dt, flux, isv, ct, out_mem, stats);
+}
+
+int dxm_integrate_range(dxm_handle* h, int64_t start, int64_t count, const double* grad, int mem, double dt,
+                        double* flux, double* isv, double* ct, int out_mem, dxm_stats* stats) {
+  return integrate_impl(h, start, count, grad, mem, dt, flux, isv, ct, out_mem, stats);
 }
 
 int dxm_update(dxm_handle* h) {

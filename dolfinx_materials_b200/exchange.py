@@ -23,6 +23,7 @@ of numpy fancy indexing.  The class works on any objects exposing a flat float64
 
 import ctypes
 import warnings
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -52,6 +53,8 @@ def _flat(fun):
 
 
 class QuadratureExchange:
+    PIPELINE_POINTS = 1 << 19  # points per pipelined chunk of a cell-subset map (the library's own transfer chunk)
+
     def __init__(self, material, num_cells, num_qp, gradients, fluxes, internal_state_variables, jacobian_flatten,
                  cells=None, pin=True, strict=True):
         self.material = material
@@ -91,8 +94,17 @@ class QuadratureExchange:
                 self._unpin.append(pin_array(a))
         elif not self.identity:
             nisv = sum(material.internal_state_variables.values())
-            self._stage = (PinnedArray((self.n, self.gdim)), PinnedArray((self.n, self.fdim)),
-                           PinnedArray((self.n, self.fdim * self.gdim)), PinnedArray((self.n, max(nisv, 1))))
+            # large subsets: chunks of whole cells, double-buffered, so that the host gather / scatter of one chunk
+            # overlaps the transfers and the update of its neighbours (integrate_range_into)
+            per = max(2, (self.PIPELINE_POINTS // self.num_qp) & ~1)  # cells per chunk, even -> even point offsets
+            self._chunks = ([(c0, min(per, len(self.cells) - c0)) for c0 in range(0, len(self.cells), per)]
+                            if self.n >= 2 * self.PIPELINE_POINTS else None)
+            m = per * self.num_qp if self._chunks else self.n
+            nbuf = 2 if self._chunks else 1
+            self._stage = [(PinnedArray((m, self.gdim)), PinnedArray((m, self.fdim)),
+                            PinnedArray((m, self.fdim * self.gdim))) for _ in range(nbuf)]
+            self._stage_state = PinnedArray((self.n, max(nisv, self.fdim, 1)))
+            self._host = ThreadPoolExecutor(1) if self._chunks else None
         self._initialized = False
         self.last_stats = None
 
@@ -100,6 +112,9 @@ class QuadratureExchange:
         for u in self._unpin:
             u()
         self._unpin = []
+        if getattr(self, "_host", None) is not None:
+            self._host.shutdown()
+            self._host = None
 
     # ---- quadrature_map.py:281-295 -------------------------------------------------------------------
     def _take(self, flat, dim):
@@ -135,12 +150,7 @@ class QuadratureExchange:
         if self.identity:
             stats = m.integrate_into(self.grad, self.flux, None, self.jac, dt)
         else:
-            g, f, c, _ = self._stage
-            q = self.num_qp
-            _gather_cells(self.grad, self.cells64, q * self.gdim, g.array)
-            stats = m.integrate_into(g.array, f.array, None, c.array, dt)
-            _scatter_cells(self.flux, self.cells64, q * self.fdim, f.array)
-            _scatter_cells(self.jac, self.cells64, q * self.fdim * self.gdim, c.array)
+            stats = self._update_subset(dt)
         self.last_stats = stats
         if stats.n_fail:
             # the reference asserts on NaN in flux / isv / Ct (quadrature_map.py:322-324); the device-side fail
@@ -150,6 +160,57 @@ class QuadratureExchange:
                 raise AssertionError(msg)
             warnings.warn(msg, PerformanceWarning)
         return stats
+
+    def _update_subset(self, dt):
+        m, q = self.material, self.num_qp
+        gb, fb, cb = q * self.gdim, q * self.fdim, q * self.fdim * self.gdim
+        if not self._chunks:
+            g, f, c = self._stage[0]
+            _gather_cells(self.grad, self.cells64, gb, g.array)
+            stats = m.integrate_into(g.array, f.array, None, c.array, dt)
+            _scatter_cells(self.flux, self.cells64, fb, f.array)
+            _scatter_cells(self.jac, self.cells64, cb, c.array)
+            return stats
+
+        # pipelined: while the device works on chunk k (integrate_range_into releases the GIL), the helper thread
+        # scatters chunk k-1 and gathers chunk k+1 on the library's host pool
+        def gather(k):
+            c0, nc = self._chunks[k]
+            g = self._stage[k % 2][0].array
+            _gather_cells(self.grad, self.cells64[c0:c0 + nc], gb, g[: nc * q])
+
+        def scatter(k):
+            c0, nc = self._chunks[k]
+            _, f, c = self._stage[k % 2]
+            _scatter_cells(self.flux, self.cells64[c0:c0 + nc], fb, f.array[: nc * q])
+            _scatter_cells(self.jac, self.cells64[c0:c0 + nc], cb, c.array[: nc * q])
+
+        total = None
+        scattered = []
+        pending_gather = self._host.submit(gather, 0)
+        for k, (c0, nc) in enumerate(self._chunks):
+            pending_gather.result()
+            if k >= 2:
+                scattered[k - 2].result()  # the last reader of this chunk's output buffers
+            if k + 1 < len(self._chunks):
+                pending_gather = self._host.submit(gather, k + 1)  # its buffer was last read by integrate(k-1): done
+            g, f, c = self._stage[k % 2]
+            npt = nc * q
+            st = m.integrate_range_into(c0 * q, npt, g.array[:npt], f.array[:npt], None, c.array[:npt], dt)
+            scattered.append(self._host.submit(scatter, k))
+            if total is None:
+                total = st
+            else:
+                total.n_points += st.n_points
+                total.n_plastic += st.n_plastic
+                total.n_fail += st.n_fail
+                total.max_iter = max(total.max_iter, st.max_iter)
+                total.max_residual = max(total.max_residual, st.max_residual)
+                total.kernel_ms += st.kernel_ms
+        for fut in scattered[-2:]:
+            fut.result()
+        m.last_stats = total
+        return total
 
     # ---- quadrature_map.py:350-360 -----------------------------------------------------------------------
     def advance(self):
@@ -161,11 +222,9 @@ class QuadratureExchange:
                 m.read_state_into(k, self.isv[k])
         else:
             # only what the Functions hold (flux + internal state), through the page-locked staging arrays
-            _, f, _, w = self._stage
-            m.read_state_into(self.fname, f.array)
-            _scatter_cells(self.flux, self.cells64, self.num_qp * self.fdim, f.array)
-            for k, d in m.internal_state_variables.items():
+            w = self._stage_state
+            for k, d in [(self.fname, self.fdim), *m.internal_state_variables.items()]:
                 d = max(1, d)
                 buf = w.array.reshape(-1)[: self.n * d].reshape(self.n, d)
                 m.read_state_into(k, buf)
-                _scatter_cells(self.isv[k], self.cells64, self.num_qp * d, buf)
+                _scatter_cells(self.flux if k == self.fname else self.isv[k], self.cells64, self.num_qp * d, buf)

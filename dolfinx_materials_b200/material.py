@@ -350,6 +350,34 @@ class CUDAMaterial:
         self._finish(rc, stats)
         return self.last_stats
 
+    def integrate_range_into(self, start, count, gradients, flux_out=None, isv_out=None, ct_out=None, dt=0):
+        """:meth:`integrate_into` for the points ``[start, start + count)`` only (``start`` even); the arrays hold
+        ``count`` rows.  Lets a caller overlap its own host work (gather / scatter of a cell-subset map) with the
+        device; every range of a step must be integrated before ``data_manager.update()`` or reading ``s1``.
+        Returns the :class:`IntegrationStats` of the range (not stored in ``last_stats``)."""
+        self._require_handle()
+        lib = _lib.load()
+        ng = sum(self.gradients.values())
+        nf = sum(self.fluxes.values())
+        ni = sum(self.internal_state_variables.values())
+        count = int(count)
+
+        def ptr(a, size, name, writeable=True):
+            if a is None:
+                return None
+            if a.dtype != np.float64 or not a.flags.c_contiguous or a.size != size or (writeable and not a.flags.writeable):
+                raise ValueError(f"{name} must be a C-contiguous float64 array with {size} entries")
+            return a.ctypes.data_as(ctypes.c_void_p)
+
+        stats = Stats()
+        rc = lib.dxm_integrate_range(
+            self._h, int(start), count, ptr(np.asarray(gradients), count * ng, "gradients", False), MEM_HOST, float(dt),
+            ptr(flux_out, count * nf, "flux_out"), ptr(isv_out, count * ni, "isv_out"),
+            ptr(ct_out, count * nf * ng, "ct_out"), MEM_HOST, ctypes.byref(stats),
+        )
+        check(rc, "dxm_integrate_range")
+        return IntegrationStats.from_c(stats)
+
     def read_state_into(self, key, out, gen=1):
         """Fetch one state field (``(n, dim)`` AoS) into a caller-owned array (lazy D2H of internal
         state: only ``advance()`` / ``project_on`` need it, ``quadrature_map.py:350-360``)."""

@@ -108,6 +108,14 @@ int dxm_export_dlpack(dxm_handle* h, int gen, const char* field, void** out);
 int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double* flux, double* isv,
                   double* ct, int out_mem, dxm_stats* stats);
 
+/* The same update restricted to the points [start, start + count) of the handle (start even); grad / flux / isv / ct hold
+ * `count` rows.  For callers that overlap their own host work with the device (QuadratureExchange pipelines the
+ * gather / scatter of a cell-subset map against the transfers this way).  Takes host arrays, or resident gradients
+ * without outputs.  s1 is complete only once every range of the step has been integrated: do that before dxm_update or
+ * reading s1.  Statistics are those of the range. */
+int dxm_integrate_range(dxm_handle* h, int64_t start, int64_t count, const double* grad, int mem, double dt,
+                        double* flux, double* isv, double* ct, int out_mem, dxm_stats* stats);
+
 /* statistics of the last dxm_integrate (synchronises the handle's stream); use it after a call made
  * with stats == NULL, which returns without waiting for the device */
 int dxm_last_stats(dxm_handle* h, dxm_stats* stats);
