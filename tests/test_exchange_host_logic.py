@@ -1,0 +1,135 @@
+"""Host-side logic of QuadratureExchange without a GPU: the chunk bookkeeping, buffer rotation and helper-thread
+ordering of the pipelined cell-subset path, and the host-pool gather / scatter it uses, driven with a stand-in material
+(a test double that implements the few methods the exchange calls with plain numpy -- NOT a CPU fallback of the
+product: the product's materials need the CUDA library and a B200)."""
+import numpy as np
+import pytest
+
+from dolfinx_materials_b200.material import IntegrationStats
+
+
+class _DataManager:
+    def __init__(self, m):
+        self.m = m
+
+    def update(self):
+        self.m.s0 = {k: v.copy() for k, v in self.m.s1.items()}
+
+
+class StandInMaterial:
+    """flux = 2 * strain + p_old, Ct row = outer(strain, 1..6) flattened, p_new = p_old + |strain|_1."""
+
+    gradients = {"strain": 6}
+    fluxes = {"stress": 6}
+    internal_state_variables = {"p": 1, "epsp": 6}
+    material_properties = {"E": 1.0}
+
+    def __init__(self):
+        self.calls = []
+
+    def set_data_manager(self, n):
+        self.n = n
+        self.s0 = {"strain": np.zeros((n, 6)), "stress": np.zeros((n, 6)), "p": np.zeros((n, 1)), "epsp": np.zeros((n, 6))}
+        self.s1 = {k: v.copy() for k, v in self.s0.items()}
+        self.data_manager = _DataManager(self)
+
+    def update_material_property(self, name, value):
+        pass
+
+    def set_initial_state_dict(self, state):
+        for k, v in state.items():
+            self.s0[k] = np.array(v, dtype=float).reshape(self.n, -1)
+
+    def _compute(self, sl, g, flux, ct):
+        g = np.asarray(g).reshape(-1, 6)
+        p_old = self.s0["p"][sl]
+        self.s1["strain"][sl] = g
+        self.s1["stress"][sl] = 2.0 * g + p_old
+        self.s1["p"][sl] = p_old + np.abs(g).sum(axis=1, keepdims=True)
+        self.s1["epsp"][sl] = -g
+        if flux is not None:
+            flux.reshape(-1, 6)[:] = self.s1["stress"][sl]
+        if ct is not None:
+            ct.reshape(-1, 36)[:] = (g[:, :, None] * np.arange(1.0, 7.0)[None, None, :]).reshape(-1, 36)
+        return IntegrationStats(n_points=len(g), n_plastic=int((g[:, 0] > 0).sum()), max_iter=3, max_residual=float(np.abs(g).max()))
+
+    def integrate_into(self, g, flux_out=None, isv_out=None, ct_out=None, dt=0):
+        self.calls.append(("all", 0, self.n))
+        return self._compute(slice(0, self.n), g, flux_out, ct_out)
+
+    def integrate_range_into(self, start, count, g, flux_out=None, isv_out=None, ct_out=None, dt=0):
+        assert start % 2 == 0
+        self.calls.append(("range", start, count))
+        return self._compute(slice(start, start + count), g, flux_out, ct_out)
+
+    def read_state_into(self, key, out, gen=1):
+        out.reshape(self.n, -1)[:] = (self.s1 if gen == 1 else self.s0)[key]
+
+
+@pytest.fixture
+def no_pinning(monkeypatch):
+    """PinnedArray needs the CUDA runtime; the logic under test does not care where the staging arrays live."""
+    import dolfinx_materials_b200.exchange as ex
+
+    class Plain:
+        def __init__(self, shape):
+            self.array = np.zeros(shape)
+
+    monkeypatch.setattr(ex, "PinnedArray", Plain)
+    return ex
+
+
+@pytest.mark.parametrize("pipeline_points,expect_chunks", [(1 << 19, 0), (1500, 9), (100, 127)])
+def test_subset_exchange_bookkeeping(jm, no_pinning, monkeypatch, pipeline_points, expect_chunks):
+    ex = no_pinning
+    monkeypatch.setattr(ex.QuadratureExchange, "PIPELINE_POINTS", pipeline_points)
+    ncell, nqp = 5000, 4
+    ntot = ncell * nqp
+    rng = np.random.default_rng(0)
+    cells = np.sort(rng.choice(ncell, 3041, replace=False))  # odd count -> ragged last chunk
+    dofs = (nqp * cells[:, None] + np.arange(nqp)[None, :]).ravel()
+    mat = StandInMaterial()
+    grad = rng.standard_normal(ntot * 6)
+    flux, jac = np.full(ntot * 6, 7.0), np.full(ntot * 36, 7.0)
+    isv = {"p": np.zeros(ntot), "epsp": np.zeros(ntot * 6)}
+    x = ex.QuadratureExchange(mat, ncell, nqp, {"strain": grad}, {"stress": flux}, isv, jac, cells=cells, pin=False)
+    assert (len(x._chunks) if x._chunks else 0) == expect_chunks
+    for step in range(2):
+        grad[:] = rng.standard_normal(ntot * 6)
+        p_old = mat.s0["p"].copy()
+        mat.calls.clear()
+        stats = x.update()
+        g = grad.reshape(-1, 6)[dofs]
+        want_flux, want_jac = np.full((ntot, 6), 7.0), np.full((ntot, 36), 7.0)
+        if step:
+            want_flux, want_jac = prev_flux.copy(), prev_jac.copy()
+        want_flux[dofs] = 2.0 * g + p_old
+        want_jac[dofs] = (g[:, :, None] * np.arange(1.0, 7.0)[None, None, :]).reshape(-1, 36)
+        assert np.array_equal(flux.reshape(-1, 6), want_flux) and np.array_equal(jac.reshape(-1, 36), want_jac)
+        assert stats.n_points == len(dofs) and stats.n_plastic == int((g[:, 0] > 0).sum())
+        assert stats.max_residual == np.abs(g).max()
+        if expect_chunks:
+            # every point exactly once, in order, chunk starts even
+            assert [c[0] for c in mat.calls] == ["range"] * expect_chunks
+            assert sum(c[2] for c in mat.calls) == len(dofs) and mat.calls[0][1] == 0
+            assert all(a[1] + a[2] == b[1] for a, b in zip(mat.calls, mat.calls[1:]))
+        else:
+            assert mat.calls == [("all", 0, len(dofs))]
+        x.advance()
+        assert np.array_equal(isv["p"][dofs], (p_old + np.abs(g).sum(axis=1, keepdims=True)).ravel())
+        assert np.array_equal(isv["epsp"].reshape(-1, 6)[dofs], -g)
+        untouched = np.setdiff1d(np.arange(ntot), dofs)
+        assert np.all(isv["p"][untouched] == 0) and np.all(flux.reshape(-1, 6)[untouched] == 7.0)
+        prev_flux, prev_jac = flux.reshape(-1, 6).copy(), jac.reshape(-1, 36).copy()
+    x.close()
+
+
+def test_subset_cells_are_validated(jm, no_pinning):
+    ex = no_pinning
+    mat = StandInMaterial()
+    arrs = dict(gradients={"strain": np.zeros(60)}, fluxes={"stress": np.zeros(60)},
+                internal_state_variables={"p": np.zeros(10), "epsp": np.zeros(60)}, jacobian_flatten=np.zeros(360))
+    with pytest.raises(ValueError):
+        ex.QuadratureExchange(mat, 10, 1, cells=np.array([1, 1, 2]), pin=False, **arrs)
+    with pytest.raises(ValueError):
+        ex.QuadratureExchange(mat, 10, 1, cells=np.array([1, 12]), pin=False, **arrs)
