@@ -9,7 +9,6 @@ with NCCL (``torch.distributed``, backend "nccl") over NVLink; ``gloo`` works fo
 
 import dataclasses
 
-from .material import IntegrationStats
 
 
 def shard_range(n_global, rank, world):

@@ -21,7 +21,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import PerformanceWarning, _lib
-from ._lib import MEM_DEVICE, MEM_HOST, MEM_RESIDENT, Stats, check
+from ._lib import MEM_HOST, MEM_RESIDENT, Stats, check
 
 
 try:  # same timer names as the reference when dolfinx is there (jaxmat.py:209-223, quadrature_map.py:320)
