@@ -125,3 +125,39 @@ def test_kernel_point_routine_voce_hardening(host, a):
                 assert np.array_equal(got[key], ref[key]), (key, k, split)
         st = ss.advance(ref)
     assert 0.3 < ref["flag"].mean() < 0.95 and ref["fail"].sum() == 0
+
+
+def test_kernel_point_routine_fuzz_over_regimes(host):
+    """Properties over orders of magnitude, strain steps from 1e-3 to 300 x the yield strain, repeated eigenvalues,
+    nearly hydrostatic and nearly uniaxial states, exponents 2..64, with and without the Voce term, load reversal:
+    no failed local solve, at most a dozen Newton iterations, kernel routine == oracle bit for bit (NaN-safe compare)."""
+    rng = np.random.default_rng(123)
+    n = 1500
+    worst = 0
+    for trial in range(24):
+        a = int(rng.choice([2, 4, 6, 8, 10, 12, 16, 20, 32, 64]))
+        props = dict(E=float(10 ** rng.uniform(3, 6)), nu=float(rng.uniform(0.0, 0.495)), sig0=float(10 ** rng.uniform(0, 3)),
+                     H=float(rng.choice([0.0, 1e-6, 10.0, 1e4, 1e6])), a=a)
+        if rng.random() < 0.4:
+            props.update(sigu=props["sig0"] * float(rng.uniform(1.0, 3.0)), b=float(10 ** rng.uniform(0, 4)))
+        scale = props["sig0"] / props["E"] * 10 ** rng.uniform(-3, 2.5, size=(n, 1))
+        d = rng.standard_normal((n, 6))
+        if trial % 4 == 1:  # repeated eigenvalues
+            d[:, 3:] = 0
+            d[:, 1] = d[:, 2]
+        if trial % 4 == 2:  # nearly hydrostatic
+            d[:, :3] = d[:, :1] + 1e-9 * d[:, :3]
+            d[:, 3:] *= 1e-9
+        if trial % 4 == 3:  # nearly uniaxial strain
+            d[:, 1:] *= 1e-7
+        st = ss.zero_state(n)
+        for k in range(2):
+            eps = st["strain"] + scale * d * (1 if k == 0 else rng.uniform(-1, 1, size=(n, 1)))
+            ref = ho.integrate(eps, st, props)
+            got = run(host, eps, st, props, int(rng.integers(0, 2)))
+            for key in ("flag", "n_iter", "fail", "stress", "p", "epsp", "Ct", "resid"):
+                assert got[key].tobytes() == ref[key].tobytes(), (key, trial, props)
+            assert ref["fail"].sum() == 0 and np.isfinite(ref["Ct"]).all(), (trial, props)
+            worst = max(worst, int(ref["n_iter"].max()))
+            st = ss.advance(ref)
+    assert worst <= 14
