@@ -56,7 +56,10 @@ class QuadratureExchange:
     PIPELINE_POINTS = 1 << 19  # points per pipelined chunk of a cell-subset map (the library's own transfer chunk)
 
     def __init__(self, material, num_cells, num_qp, gradients, fluxes, internal_state_variables, jacobian_flatten,
-                 cells=None, pin=True, strict=True):
+                 cells=None, pin=True, strict=True, keep_data_manager=False):
+        """``keep_data_manager``: the material already has a data manager of the right size (the reference's
+        ``QuadratureMap.__init__`` created it, ``quadrature_map.py:231-233``) whose properties and initial state must
+        survive -- do not create a new one."""
         self.material = material
         self.strict = strict
         self.num_qp = int(num_qp)
@@ -84,9 +87,13 @@ class QuadratureExchange:
             self.dofs = (np.repeat(self.num_qp * self.cells[:, None], self.num_qp, axis=1)
                          + np.arange(self.num_qp)[None, :]).ravel()
             self.n = len(self.dofs)
-        material.set_data_manager(self.n)
-        for name, prop in material.material_properties.items():
-            material.update_material_property(name, np.asarray(prop))
+        if keep_data_manager:
+            if getattr(material, "_n", None) != self.n:
+                raise ValueError(f"keep_data_manager: the material's data manager holds {getattr(material, '_n', None)} points, the map {self.n}")
+        else:
+            material.set_data_manager(self.n)
+            for name, prop in material.material_properties.items():
+                material.update_material_property(name, np.asarray(prop))
         self._unpin = []
         self._stage = None
         if self.identity and pin:
@@ -141,9 +148,11 @@ class QuadratureExchange:
         self.material.set_initial_state_dict({field_name: new})
 
     # ---- quadrature_map.py:297-334 ---------------------------------------------------------------------
-    def update(self, dt=0):
+    def update(self, dt=0, fetch_internal_state=False):
         """The gradient ``x.array`` must hold this iteration's evaluated gradients (what
-        ``QuadratureExpression.eval`` leaves there, ``quadrature_function.py:45-51``)."""
+        ``QuadratureExpression.eval`` leaves there, ``quadrature_function.py:45-51``).  ``fetch_internal_state``: also
+        refresh the internal-state Functions now, as the reference does on every update (``quadrature_map.py:333``);
+        by default they are refreshed in ``advance()`` only."""
         if not self._initialized:
             self.initialize_state()
         m = self.material
@@ -152,6 +161,8 @@ class QuadratureExchange:
         else:
             stats = self._update_subset(dt)
         self.last_stats = stats
+        if fetch_internal_state:
+            self.fetch_state(flux=False)
         if stats.n_fail:
             # the reference asserts on NaN in flux / isv / Ct (quadrature_map.py:322-324); the device-side fail
             # count covers those (non-finite results) plus local solves that hit their iteration cap
@@ -212,19 +223,23 @@ class QuadratureExchange:
         m.last_stats = total
         return total
 
-    # ---- quadrature_map.py:350-360 -----------------------------------------------------------------------
-    def advance(self):
+    def fetch_state(self, flux=True, internal=True):
+        """Copy the material's current ``s1`` flux and / or internal state variables into their Functions."""
         m = self.material
-        m.data_manager.update()
+        fields = ([(self.fname, self.fdim)] if flux else []) + (list(m.internal_state_variables.items()) if internal else [])
         if self.identity:
-            m.read_state_into(self.fname, self.flux)
-            for k in m.internal_state_variables:
-                m.read_state_into(k, self.isv[k])
+            for k, _ in fields:
+                m.read_state_into(k, self.flux if k == self.fname else self.isv[k])
         else:
-            # only what the Functions hold (flux + internal state), through the page-locked staging arrays
+            # only what the Functions hold, through a page-locked staging array
             w = self._stage_state
-            for k, d in [(self.fname, self.fdim), *m.internal_state_variables.items()]:
+            for k, d in fields:
                 d = max(1, d)
                 buf = w.array.reshape(-1)[: self.n * d].reshape(self.n, d)
                 m.read_state_into(k, buf)
                 _scatter_cells(self.flux if k == self.fname else self.isv[k], self.cells64, self.num_qp * d, buf)
+
+    # ---- quadrature_map.py:350-360 -----------------------------------------------------------------------
+    def advance(self):
+        self.material.data_manager.update()
+        self.fetch_state()

@@ -5,65 +5,9 @@ product: the product's materials need the CUDA library and a B200)."""
 import numpy as np
 import pytest
 
-from dolfinx_materials_b200.material import IntegrationStats
 
 
-class _DataManager:
-    def __init__(self, m):
-        self.m = m
-
-    def update(self):
-        self.m.s0 = {k: v.copy() for k, v in self.m.s1.items()}
-
-
-class StandInMaterial:
-    """flux = 2 * strain + p_old, Ct row = outer(strain, 1..6) flattened, p_new = p_old + |strain|_1."""
-
-    gradients = {"strain": 6}
-    fluxes = {"stress": 6}
-    internal_state_variables = {"p": 1, "epsp": 6}
-    material_properties = {"E": 1.0}
-
-    def __init__(self):
-        self.calls = []
-
-    def set_data_manager(self, n):
-        self.n = n
-        self.s0 = {"strain": np.zeros((n, 6)), "stress": np.zeros((n, 6)), "p": np.zeros((n, 1)), "epsp": np.zeros((n, 6))}
-        self.s1 = {k: v.copy() for k, v in self.s0.items()}
-        self.data_manager = _DataManager(self)
-
-    def update_material_property(self, name, value):
-        pass
-
-    def set_initial_state_dict(self, state):
-        for k, v in state.items():
-            self.s0[k] = np.array(v, dtype=float).reshape(self.n, -1)
-
-    def _compute(self, sl, g, flux, ct):
-        g = np.asarray(g).reshape(-1, 6)
-        p_old = self.s0["p"][sl]
-        self.s1["strain"][sl] = g
-        self.s1["stress"][sl] = 2.0 * g + p_old
-        self.s1["p"][sl] = p_old + np.abs(g).sum(axis=1, keepdims=True)
-        self.s1["epsp"][sl] = -g
-        if flux is not None:
-            flux.reshape(-1, 6)[:] = self.s1["stress"][sl]
-        if ct is not None:
-            ct.reshape(-1, 36)[:] = (g[:, :, None] * np.arange(1.0, 7.0)[None, None, :]).reshape(-1, 36)
-        return IntegrationStats(n_points=len(g), n_plastic=int((g[:, 0] > 0).sum()), max_iter=3, max_residual=float(np.abs(g).max()))
-
-    def integrate_into(self, g, flux_out=None, isv_out=None, ct_out=None, dt=0):
-        self.calls.append(("all", 0, self.n))
-        return self._compute(slice(0, self.n), g, flux_out, ct_out)
-
-    def integrate_range_into(self, start, count, g, flux_out=None, isv_out=None, ct_out=None, dt=0):
-        assert start % 2 == 0
-        self.calls.append(("range", start, count))
-        return self._compute(slice(start, start + count), g, flux_out, ct_out)
-
-    def read_state_into(self, key, out, gen=1):
-        out.reshape(self.n, -1)[:] = (self.s1 if gen == 1 else self.s0)[key]
+from qmap_standin import StandInMaterial
 
 
 @pytest.fixture
