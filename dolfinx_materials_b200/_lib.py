@@ -33,6 +33,7 @@ class Stats(ctypes.Structure):
 SIGNATURES = {
     "dxm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p)]),
     "dxm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "dxm_device_count": (ctypes.c_int, []),
     "dxm_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "dxm_ld": (ctypes.c_int64, [ctypes.c_void_p]),
     "dxm_npoints": (ctypes.c_int64, [ctypes.c_void_p]),

@@ -434,6 +434,15 @@ const char* dxm_last_error(void) { return g_err.c_str(); }
 const char* dxm_version(void) { return "dxm-b200 0.1 (sm_100a, fp64, -fmad=false)"; }
 int64_t dxm_launch_count(void) { return g_launches.load(); }
 
+int dxm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
 int dxm_create(int behaviour, int device, int64_t n, dxm_handle** out) {
   if (!out) return fail("dxm_create: out is NULL");
   *out = nullptr;

@@ -11,6 +11,35 @@ import dataclasses
 
 
 
+_LOCAL_RANK_VARS = ("LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID",
+                    "PMI_LOCAL_RANK", "SLURM_LOCALID")
+
+
+def local_rank(environ=None):
+    """Rank of this process on its node, from the launcher's environment (torchrun, Open MPI, MVAPICH2, Intel MPI /
+    Hydra, Slurm); 0 when none of them is set.  The reference runs one dolfinx MPI rank per partition
+    (``quadrature_map.py:66-70``); with one rank per GPU this is the device to use."""
+    import os
+
+    env = os.environ if environ is None else environ
+    for var in _LOCAL_RANK_VARS:
+        val = env.get(var)
+        if val is not None and val.strip().lstrip("-").isdigit():
+            return int(val)
+    return 0
+
+
+def default_device(device_count=None, environ=None):
+    """``local_rank() % device_count`` (several ranks share a GPU when there are more ranks than GPUs, as the
+    reference's GPU demo allows: ``finite_strain_elastoplasticity.py:33``)."""
+    if device_count is None:
+        from . import _lib
+
+        device_count = _lib.load().dxm_device_count()
+    r = local_rank(environ)
+    return r % device_count if device_count and device_count > 0 else r
+
+
 def shard_range(n_global, rank, world):
     """Contiguous range [start, stop) of Gauss points owned by ``rank`` (cell-major dof order,
     ``quadrature_map.py:255-260``); remainders go to the first ranks."""

@@ -146,8 +146,14 @@ class CUDAMaterial:
     """Converts a behaviour descriptor into a dolfinx_materials-compatible material running on a
     B200 (the role ``JAXMaterial(behavior)`` plays in the reference, ``jaxmat.py:141-156``)."""
 
-    def __init__(self, behavior, device=0, warn_on_failure=True):
+    def __init__(self, behavior, device=None, warn_on_failure=True):
+        """``device``: CUDA device index; ``None`` = this process's local rank modulo the number of devices (one MPI
+        rank / torchrun worker per GPU), 0 for a single process."""
         self.behavior = behavior
+        if device is None:
+            from .distributed import default_device
+
+            device = default_device()
         self.device = int(device)
         self.warn_on_failure = warn_on_failure
         self.material_properties = dict(behavior.properties())

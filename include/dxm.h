@@ -69,6 +69,7 @@ typedef struct dxm_stats {
 /* life cycle -- replaces Material.set_data_manager(ngauss) (generic.py:172-174, jaxmat.py:195-197) */
 int dxm_create(int behaviour, int device, int64_t n, dxm_handle** out);
 int dxm_destroy(dxm_handle* h);
+int dxm_device_count(void); /* CUDA devices visible to this process (0 when there is none or no driver) */
 int dxm_set_stream(dxm_handle* h, void* cuda_stream); /* run on the caller's stream (default: own) */
 int64_t dxm_ld(const dxm_handle* h);                  /* SoA leading dimension (>= n)              */
 int64_t dxm_npoints(const dxm_handle* h);

@@ -120,3 +120,24 @@ def test_rank_sharded_assembly_world2():
     assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == 72
     for _, _, _, ea, eb in res:
         assert ea < 1e-13 and eb < 1e-13
+
+
+def test_local_rank_and_default_device_from_launcher_environment():
+    from dolfinx_materials_b200.distributed import default_device, local_rank
+
+    assert local_rank({}) == 0
+    assert local_rank({"OMPI_COMM_WORLD_LOCAL_RANK": "3"}) == 3
+    assert local_rank({"LOCAL_RANK": "5", "SLURM_LOCALID": "1"}) == 5  # torchrun wins over the scheduler
+    assert local_rank({"SLURM_LOCALID": "x"}) == 0
+    assert default_device(8, {"LOCAL_RANK": "11"}) == 3  # more ranks than GPUs: ranks share devices
+    assert default_device(0, {"LOCAL_RANK": "2"}) == 2  # no device visible: dxm_create will say so
+
+
+def test_device_count_without_a_gpu():
+    import torch
+
+    from dolfinx_materials_b200 import _lib, build
+
+    build.build_library()
+    n = _lib.load().dxm_device_count()
+    assert n == (torch.cuda.device_count() if torch.cuda.is_available() else 0)
