@@ -14,7 +14,8 @@ unused dolfinx import `dolfinx.common.Timer`, generic.py:2):
     equals the reference's point-by-point protocol over a load history; fefp_history.npz likewise for the
     finite-strain behaviour (gradient F, flux PK1, state p + be_bar).  (The J2 arithmetic itself is
     not in the reference tree -- it lives in un-vendored jaxmat -- so these vectors pin protocol and
-    regression, not jaxmat parity; see oracle/__init__.py.)
+    regression, not jaxmat parity; see oracle/__init__.py.)  hosford_history.npz: the same for the Hosford behaviour
+    (oracle/hosford.py; MFront parity unpinned).
 """
 import os
 import sys
@@ -53,6 +54,7 @@ from dolfinx_materials.generic import Material  # noqa: E402  (the reference)
 from dolfinx_materials.python_materials.elasticity import LinearElasticIsotropic  # noqa: E402
 
 from oracle import fefp  # noqa: E402
+from oracle import hosford as ho  # noqa: E402
 from oracle import small_strain as ss  # noqa: E402
 from oracle import synth  # noqa: E402
 
@@ -167,10 +169,38 @@ def fefp_history(name, props, n, amp, K, seed):
     np.savez(os.path.join(HERE, name), **out)
 
 
+class PointwiseHosford(PointwiseJ2):
+    """Hosford criterion + linear hardening, point by point through the reference's machinery (the behaviour the
+    multi-material demo takes from MFront, demos/multimaterials/multimaterials.py:245-254)."""
+
+    def constitutive_update(self, eps, state, dt):
+        st = {k: np.asarray(v, dtype=float).reshape(1, -1) for k, v in state.items()}
+        st["p"] = st["p"].reshape(1)
+        out = ho.integrate(eps.reshape(1, 6), st, self.props)
+        new = {"strain": eps, "stress": out["stress"][0], "p": out["p"], "epsp": out["epsp"][0]}
+        return out["Ct"][0], new
+
+
+def hosford_history(name, props, n, amp, K, seed):
+    mat = PointwiseHosford(props)
+    mat.set_data_manager(n)
+    out = {"props_keys": np.array(sorted(props)), "props_vals": np.array([float(props[k]) for k in sorted(props)])}
+    for k in range(1, K + 1):
+        eps = synth.strain(n, seed, amp, k, K)
+        flux, isv, Ct = mat.integrate(eps)
+        out[f"eps{k}"] = eps
+        out[f"flux{k}"] = np.array(flux)
+        out[f"isv{k}"] = np.array(isv)
+        out[f"Ct{k}"] = np.array(Ct)
+        mat.data_manager.update()
+    np.savez(os.path.join(HERE, name), **out)
+
+
 if __name__ == "__main__":
     elastic_reference()
     j2_history("j2_voce_history.npz", dict(E=70e3, nu=0.3, sig0=350.0, sigu=500.0, b=1e3), 96, 1.25e-2, 4, 0)
     j2_history("j2_linear_history.npz", dict(E=70e3, nu=0.3, sig0=250.0, H=5e3), 48, 1.25e-2, 3, 5)
+    hosford_history("hosford_history.npz", dict(E=70e3, nu=0.3, sig0=200.0, H=10.0, a=10), 48, 1.25e-2, 3, 7)
     fefp_history("fefp_history.npz", dict(E=70e3, nu=0.3, sig0=500.0, sigu=750.0, b=1000.0), 40, 4e-2, 3, 3)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -29,7 +29,7 @@ def test_elastic_vs_reference_run(jm):
     assert np.allclose(flux, g["flux_nu0"]) and np.allclose(flux[0, :3], 70e3 * np.array([1e-3, 0, 0]))
 
 
-@pytest.mark.parametrize("name", ["j2_voce_history.npz", "j2_linear_history.npz", "fefp_history.npz"])
+@pytest.mark.parametrize("name", ["j2_voce_history.npz", "j2_linear_history.npz", "fefp_history.npz", "hosford_history.npz"])
 def test_histories_vs_reference_protocol_run(jm, name):
     g = np.load(os.path.join(GOLD, name))
     p = dict(zip([str(k) for k in g["props_keys"]], [float(v) for v in g["props_vals"]]))
@@ -39,7 +39,12 @@ def test_histories_vs_reference_protocol_run(jm, name):
     else:
         hard = jm.LinearHardening(sig0=p["sig0"], H=p["H"])
     finite = name.startswith("fefp")
-    beh = jm.FeFpJ2Plasticity(elasticity=el, yield_stress=hard) if finite else jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=hard)
+    if finite:
+        beh = jm.FeFpJ2Plasticity(elasticity=el, yield_stress=hard)
+    elif name.startswith("hosford"):
+        beh = jm.GeneralIsotropicHardening(elasticity=el, yield_stress=hard, equivalent_stress=jm.Hosford(a=int(p["a"])))
+    else:
+        beh = jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=hard)
     key = "F" if finite else "eps"
     n = g[f"{key}1"].shape[0]
     m = jm.CUDAMaterial(beh)

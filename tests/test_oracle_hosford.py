@@ -226,3 +226,25 @@ def test_voce_hardening_solution_and_tangent(a):
     good = ~np.isnan(J).any(axis=(1, 2))
     assert out["flag"][good].sum() > 5
     assert (np.abs(out["Ct"][good] - J[good]).max(axis=(1, 2)) / props["E"]).max() < 2e-6
+
+
+def test_history_matches_reference_protocol_run():
+    """tests/golden/hosford_history.npz: the reference's own Material.integrate / _vmap / DataManager drove a per-point
+    Hosford material over a 3-increment history (tests/golden/make_golden.py); the batched oracle with explicit state
+    carry reproduces it bit for bit (pins protocol and regression; MFront parity itself is unpinned)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hosford_history.npz"))
+    props = dict(zip([str(k) for k in g["props_keys"]], [float(v) for v in g["props_vals"]]))
+    props["a"] = int(props["a"])
+    n = g["eps1"].shape[0]
+    st = ss.zero_state(n)
+    k = 1
+    while f"eps{k}" in g:
+        out = ho.integrate(g[f"eps{k}"], st, props)
+        assert np.array_equal(out["stress"], g[f"flux{k}"])
+        assert np.array_equal(out["p"], g[f"isv{k}"][:, 0]) and np.array_equal(out["epsp"], g[f"isv{k}"][:, 1:])
+        assert np.array_equal(out["Ct"], g[f"Ct{k}"])
+        st = ss.advance(out)
+        k += 1
+    assert k == 4 and out["flag"].any() and not out["flag"].all()
