@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cmath>
+
 namespace dxm {
 
 constexpr double kLog2e = 1.4426950408889634;
@@ -40,6 +42,61 @@ __device__ __forceinline__ double exp_c(double x) {
   if (x != x) y = x;
   return y;
 }
+
+#define DXM_HD __host__ __device__ __forceinline__
+
+// exp_c for code that is compiled for the host as well (the per-point routines the CPU tests execute against the
+// oracle, tests/*_host_check.cu): on the device it IS exp_c; on the host the same operations, with ldexp doing the
+// exact 2^k scaling.
+DXM_HD double exp_hd(double x) {
+#ifdef __CUDA_ARCH__
+  return exp_c(x);
+#else
+  if (x != x) return x;
+  if (x < -kExpClamp) return 0.0;
+  if (x > kExpClamp) return INFINITY;
+  const double k = rint(x * kLog2e);
+  const double r = (x - k * kLn2Hi) - k * kLn2Lo;
+  double y = 1.0 / 6227020800.0;
+  y = y * r + 1.0 / 479001600.0;
+  y = y * r + 1.0 / 39916800.0;
+  y = y * r + 1.0 / 3628800.0;
+  y = y * r + 1.0 / 362880.0;
+  y = y * r + 1.0 / 40320.0;
+  y = y * r + 1.0 / 5040.0;
+  y = y * r + 1.0 / 720.0;
+  y = y * r + 1.0 / 120.0;
+  y = y * r + 1.0 / 24.0;
+  y = y * r + 1.0 / 6.0;
+  y = y * r + 0.5;
+  y = y * r + 1.0;
+  y = y * r + 1.0;
+  return ldexp(y, (int)k);
+#endif
+}
+
+// streaming (evict-first) scalar access for code that also compiles for the host
+DXM_HD double ld_stream(const double* p) {
+#ifdef __CUDA_ARCH__
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
+DXM_HD void st_stream(double* p, double v) {
+#ifdef __CUDA_ARCH__
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+
+// warp vote of the local Newton loops; a host caller (CPU test harness) is a warp of one lane
+#ifdef __CUDA_ARCH__
+#define DXM_ANY_SYNC(mask, pred) __any_sync(mask, pred)
+#else
+#define DXM_ANY_SYNC(mask, pred) (pred)
+#endif
 
 // Resident layout of a symmetric 6x6 tangent: the 21 entries (j <= i) of the upper triangle, row-major
 // (the order the small-strain kernel forms them in).  sym6_packed(c) maps a full row-major index c = j*6+i to it.

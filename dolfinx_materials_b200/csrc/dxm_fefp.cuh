@@ -45,7 +45,7 @@ constexpr double kSqrt2 = 1.41421356237309504880;
 
 // position of tensor component (i,j) in the reference's 9-vector [11,22,33,12,21,13,31,23,32]
 // (dolfinx_materials/utils.py:173-186)
-__device__ __forceinline__ constexpr int idx9(int i, int j) {
+DXM_HD constexpr int idx9(int i, int j) {
   return i == j ? i : (i == 0 && j == 1) ? 3 : (i == 1 && j == 0) ? 4 : (i == 0 && j == 2) ? 5
                   : (i == 2 && j == 0) ? 6 : (i == 1 && j == 2) ? 7 : 8;
 }
@@ -53,8 +53,12 @@ __device__ __forceinline__ constexpr int idx9(int i, int j) {
 constexpr double kThird = 1.0 / 3.0;
 
 // x^(-1/3), division free, from exactly rounded operations only (twin of oracle.fefp.rcbrt_c)
-__device__ __forceinline__ double rcbrt_c(double x) {
+DXM_HD double rcbrt_c(double x) {
+#ifdef __CUDA_ARCH__
   if (!(x > 0.0)) return __longlong_as_double(0x7ff8000000000000LL);
+#else
+  if (!(x > 0.0)) return NAN;
+#endif
   int e;
   const double m = frexp(x, &e);
   const int q = (e >= 0) ? (e / 3) : -((-e + 2) / 3);
@@ -63,22 +67,26 @@ __device__ __forceinline__ double rcbrt_c(double x) {
   double y = 1.2 - 0.15 * xr;
 #pragma unroll
   for (int i = 0; i < 6; ++i) y = (y * (4.0 - xr * ((y * y) * y))) * kThird;
+#ifdef __CUDA_ARCH__
   return y * __hiloint2double((1023 - q) << 20, 0);
+#else
+  return ldexp(y, -q);  // exact: y in [0.7, 1.3], |q| <= 358
+#endif
 }
 
-__device__ __forceinline__ double dot3(double a0, double b0, double a1, double b1, double a2,
+DXM_HD double dot3(double a0, double b0, double a1, double b1, double a2,
                                        double b2) {
   return (a0 * b0 + a1 * b1) + a2 * b2;
 }
 
-__device__ __forceinline__ double det3(const double (&A)[3][3]) {
+DXM_HD double det3(const double (&A)[3][3]) {
   const double t0 = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]);
   const double t1 = A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]);
   const double t2 = A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
   return (t0 - t1) + t2;
 }
 
-__device__ __forceinline__ void inv3(const double (&A)[3][3], double (&Ai)[3][3], double& det) {
+DXM_HD void inv3(const double (&A)[3][3], double (&Ai)[3][3], double& det) {
   double c[3][3];
   c[0][0] = A[1][1] * A[2][2] - A[1][2] * A[2][1];
   c[0][1] = A[0][2] * A[2][1] - A[0][1] * A[2][2];
@@ -103,13 +111,13 @@ struct FeFpLocalProps {
 
 // local 2x2 Newton in (dp, t); lanes outside `mask` must not call.  Inputs are six scalars per point, which is
 // what makes the block-level compaction below cheap.
-__device__ __forceinline__ void fefp_newton(const FeFpLocalProps& m, const double seq, const double dd,
+DXM_HD void fefp_newton(const FeFpLocalProps& m, const double seq, const double dd,
                                             const double d3, const double p_old, double& ecur, double& dp,
                                             double& t, int& n_iter, double& resid, bool& fail, bool active,
                                             const unsigned mask, const bool vote) {
   const double c = m.threemu * (1.0 / seq);
   const double tol1 = kFeNewtonRtol * seq;
-  for (int it = 0; vote ? __any_sync(mask, active) : active; ++it) {
+  for (int it = 0; vote ? DXM_ANY_SYNC(mask, active) : active; ++it) {
     if (active) {
       const double alpha = 1.0 - (c * t) * dp;
       const double p = p_old + dp;
@@ -138,7 +146,7 @@ __device__ __forceinline__ void fefp_newton(const FeFpLocalProps& m, const doubl
         const double t_new = t + (J21 * r1 - J11 * r2) * rdet;
         dp = dp_new;
         t = t_new;
-        ecur = exp_c(-(m.b * (p_old + dp)));
+        ecur = exp_hd(-(m.b * (p_old + dp)));
         ++n_iter;
       }
     }
@@ -161,13 +169,305 @@ struct FeFpCompactStore<false> {
   __device__ __forceinline__ FeFpCompactSmem* get() { return nullptr; }
 };
 
+// One Gauss point at SoA position i0: loads, local solve, state / stress / tangent stores (the tangent entries are
+// stored as they are formed, so the 81 of them never sit in registers together).  __host__ __device__ (without
+// COMPACT) so that a CPU test can run the very code the kernel runs per point against the oracle
+// (tests/point_host_check.cu) -- the product only ever calls it from the kernel below.
+template <bool PERPOINT, bool DIAG, bool COMPACT>
+DXM_HD void fefp_point(const FeFpArgs& a, const int64_t i0, const bool live, const unsigned warp_mask,
+                       FeFpCompactSmem* cs, PointStats& acc) {
+  const int64_t ld = a.ld;
+  double A[3][3], Ao[3][3], Bo[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      A[i][j] = ld_stream(a.F + (int64_t)idx9(i, j) * ld + i0);
+      Ao[i][j] = ld_stream(a.F_old + (int64_t)idx9(i, j) * ld + i0);
+    }
+  {
+    double beo[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) beo[c] = ld_stream(a.be_old + (int64_t)c * ld + i0);
+    Bo[0][0] = beo[0];
+    Bo[1][1] = beo[1];
+    Bo[2][2] = beo[2];
+    Bo[0][1] = Bo[1][0] = beo[3] * kRsqrt2;
+    Bo[0][2] = Bo[2][0] = beo[4] * kRsqrt2;
+    Bo[1][2] = Bo[2][1] = beo[5] * kRsqrt2;
+  }
+  const double p_old = ld_stream(a.p_old + i0);
+
+  double mu, kappa, sig0, H, dsu, b;
+  if (PERPOINT) {
+    const double E = ld_stream(a.pp[0] + i0), nu = ld_stream(a.pp[1] + i0);
+    mu = E / 2.0 / (1.0 + nu);
+    kappa = E / (3.0 * (1.0 - 2.0 * nu));
+    sig0 = ld_stream(a.pp[2] + i0);
+    H = ld_stream(a.pp[3] + i0);
+    const double d = ld_stream(a.pp[4] + i0) - sig0;
+    dsu = isfinite(d) ? d : 0.0;
+    b = ld_stream(a.pp[5] + i0);
+  } else {
+    mu = a.mu;
+    kappa = a.kappa;
+    sig0 = a.sig0;
+    H = a.H;
+    dsu = a.dsu;
+    b = a.b;
+  }
+  const double threemu = 3.0 * mu;
+  const double bdsu = b * dsu;
+
+  // ---- trial state ----------------------------------------------------------------------------
+  double B[3][3], D[3][3];
+  {
+    double Aoi[3][3], deto, f[3][3], M[3][3];
+    inv3(Ao, Aoi, deto);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        f[i][j] = dot3(A[i][0], Aoi[0][j], A[i][1], Aoi[1][j], A[i][2], Aoi[2][j]);
+    const double Jf = det3(f);
+    const double rc = rcbrt_c(Jf);
+    const double s23 = rc * rc;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        M[i][j] = dot3(f[i][0], Bo[0][j], f[i][1], Bo[1][j], f[i][2], Bo[2][j]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = i; j < 3; ++j) {
+        B[i][j] = s23 * dot3(M[i][0], f[j][0], M[i][1], f[j][1], M[i][2], f[j][2]);
+        B[j][i] = B[i][j];
+      }
+  }
+  const double t0 = ((B[0][0] + B[1][1]) + B[2][2]) * kThird;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) D[i][j] = (i == j) ? (B[i][j] - t0) : B[i][j];
+  const double dd = ((D[0][0] * D[0][0] + D[1][1] * D[1][1]) + D[2][2] * D[2][2]) +
+                    2.0 * ((D[0][1] * D[0][1] + D[0][2] * D[0][2]) + D[1][2] * D[1][2]);
+  const double d3 = det3(D);
+  const double seq = mu * sqrt(1.5 * dd);
+  const double rseq = 1.0 / seq;
+
+  double ecur = exp_hd(-(b * p_old));
+  const double sy0 = (sig0 + H * p_old) + dsu * (1.0 - ecur);
+  const double ftr = seq - sy0;
+  const bool flag = ftr > 0.0;
+
+  // ---- local 2x2 Newton in (dp, t) ----------------------------------------------------------------
+  const double c = threemu * rseq;
+  double dp = 0.0, t = t0, resid = 0.0;
+  int n_iter = 0;
+  bool fail = false;
+  {
+    FeFpLocalProps lp;
+    lp.threemu = threemu;
+    lp.sig0 = sig0;
+    lp.H = H;
+    lp.dsu = dsu;
+    lp.bdsu = bdsu;
+    lp.b = b;
+    const bool active = live && flag;
+    if (!COMPACT) {
+      // warp-synchronous with a warp-vote early exit (see dxm_small_strain.cuh)
+      fefp_newton(lp, seq, dd, d3, p_old, ecur, dp, t, n_iter, resid, fail, active, warp_mask, a.vote != 0);
+    } else {
+#ifdef __CUDA_ARCH__
+      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+      const unsigned bal = __ballot_sync(0xffffffffu, active);
+      if (lane == 0) cs->warp_count[w] = __popc(bal);
+      __syncthreads();
+      int base = 0, total = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int cnt = cs->warp_count[i];
+        base += i < w ? cnt : 0;
+        total += cnt;
+      }
+      const int slot = base + __popc(bal & ((1u << lane) - 1u));
+      if (active) {
+        cs->a[0][slot] = seq;
+        cs->a[1][slot] = dd;
+        cs->a[2][slot] = d3;
+        cs->a[3][slot] = t0;
+        cs->a[4][slot] = p_old;
+        cs->a[5][slot] = ecur;
+      }
+      __syncthreads();
+      const bool solver = (int)threadIdx.x < total;
+      const unsigned smask = __ballot_sync(0xffffffffu, solver);
+      if (solver) {
+        const int k = threadIdx.x;
+        const double sq = cs->a[0][k], dd_s = cs->a[1][k], d3_s = cs->a[2][k], po = cs->a[4][k];
+        double ts = cs->a[3][k], ec = cs->a[5][k], d = 0.0, rs = 0.0;
+        int ni = 0;
+        bool fl = false;
+        fefp_newton(lp, sq, dd_s, d3_s, po, ec, d, ts, ni, rs, fl, true, smask, a.vote != 0);
+        cs->a[0][k] = d;
+        cs->a[1][k] = ts;
+        cs->a[2][k] = ec;
+        cs->a[3][k] = rs;
+        cs->meta[k] = ni | (fl ? 1 << 16 : 0);
+      }
+      __syncthreads();
+      if (active) {
+        dp = cs->a[0][slot];
+        t = cs->a[1][slot];
+        ecur = cs->a[2][slot];
+        resid = cs->a[3][slot];
+        const int mt = cs->meta[slot];
+        n_iter = mt & 0xffff;
+        fail = (mt >> 16) != 0;
+      }
+      __syncthreads();  // slots are reused by the next tile
+      if (!live) return;
+#endif
+    }
+  }
+  const double alpha = flag ? (1.0 - (c * t) * dp) : 1.0;
+  const double p_new = p_old + dp;
+
+  // ---- new state -----------------------------------------------------------------------------------
+  double be[6];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) be[i] = flag ? (alpha * D[i][i] + t) : B[i][i];
+  be[3] = (alpha * D[0][1]) * kSqrt2;
+  be[4] = (alpha * D[0][2]) * kSqrt2;
+  be[5] = (alpha * D[1][2]) * kSqrt2;
+
+  // ---- stress: tau = mu alpha D + pvol 1,  PK1 = tau F^-T = mu alpha (D F^-T) + pvol F^-T --------------
+  double Ai[3][3], Jd, DA[3][3], P[3][3];
+  inv3(A, Ai, Jd);
+  const double muA = mu * alpha;
+  const double pvol = (0.5 * kappa) * (Jd * Jd - 1.0);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      DA[i][j] = dot3(D[i][0], Ai[j][0], D[i][1], Ai[j][1], D[i][2], Ai[j][2]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) P[i][j] = muA * DA[i][j] + pvol * Ai[j][i];
+
+  double chk = (seq + fabs(Jd)) + p_new;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) chk = chk + fabs(be[i]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) chk = chk + fabs(P[i][j]);
+  if (!isfinite(chk)) fail = true;
+
+  // state and stress stores (the tangent follows)
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) st_stream(a.P + (int64_t)idx9(i, j) * ld + i0, P[i][j]);
+  st_stream(a.p + i0, p_new);
+#pragma unroll
+  for (int c6 = 0; c6 < 6; ++c6) st_stream(a.be + (int64_t)c6 * ld + i0, be[c6]);
+
+  acc.n_plastic += flag ? 1u : 0u;
+  acc.n_fail += fail ? 1u : 0u;
+  acc.max_iter = n_iter > (int)acc.max_iter ? (unsigned)n_iter : acc.max_iter;
+  acc.max_resid = resid > acc.max_resid ? resid : acc.max_resid;
+  if (resid != resid) acc.max_resid = resid;
+  if (DIAG) {
+    a.d_flag[i0] = flag ? 1 : 0;
+    a.d_iter[i0] = n_iter;
+    a.d_resid[i0] = resid;
+    a.d_fail[i0] = fail ? 1 : 0;
+  }
+
+  // ---- local-solve sensitivities: d(alpha) = al1 (D:dD) + al2 (D^2:dD) --------------------------------
+  double al1 = 0.0, al2 = 0.0;
+  if (flag) {
+    const double sq1 = (1.5 * (mu * mu)) * rseq;
+    const double a2 = alpha * alpha;
+    const double dsy = H + bdsu * ecur;
+    const double g = 3.0 * (a2 * d3) - (alpha * dd) * t;
+    const double ct = c * t;
+    const double cdp = c * dp;
+    const double J11 = -(threemu * t) - dsy;
+    const double J12 = -(threemu * dp);
+    const double J21 = -(g * ct);
+    const double J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp;
+    const double rdet = 1.0 / (J11 * J22 - J12 * J21);
+    const double oma = (1.0 - alpha) * rseq;
+    const double b21 = (g * oma) * sq1 - a2 * t;
+    const double b22 = a2 * alpha;
+    const double p1 = -((sq1 * J22 - J12 * b21) * rdet);
+    const double t1 = -((J11 * b21 - J21 * sq1) * rdet);
+    const double p2 = (J12 * b22) * rdet;
+    const double t2 = -((J11 * b22) * rdet);
+    al1 = (oma * sq1 - ct * p1) - cdp * t1;
+    al2 = -(ct * p2) - cdp * t2;
+  }
+
+  // ---- tangent, column (k,l) = d/dF_kl, row (i,j) = PK1_ij; w = row l of F^-1, v = B w = D w + t0 w:
+  //      dP_ij = cD (D F^-T)_ij + cI F^-T_ij + delta_ik mu alpha (F^-1 v)_j + hs w_i F^-1_jk
+  const double kJ2 = kappa * (Jd * Jd);
+  const double c23dd = (2.0 / 3.0) * dd;
+  const double twod3 = 2.0 * d3;
+  const double c23muA = (2.0 / 3.0) * muA;
+  const double hs = muA * t0 - pvol;
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    double w[3], v[3], u[3], z[3], my[3], hw[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w[i] = Ai[l][i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = dot3(D[i][0], w[0], D[i][1], w[1], D[i][2], w[2]) + t0 * w[i];
+    if (flag) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) u[i] = dot3(D[i][0], v[0], D[i][1], v[1], D[i][2], v[2]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) z[i] = dot3(D[i][0], u[0], D[i][1], u[1], D[i][2], u[2]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) u[i] = z[i] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) my[j] = muA * dot3(Ai[j][0], v[0], Ai[j][1], v[1], Ai[j][2], v[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) hw[i] = hs * w[i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double cd0 = 0.0;
+      if (flag) {
+        const double a1 = 2.0 * u[k] - c23dd * w[k];
+        const double a2p = (2.0 * z[k] - c23dd * v[k]) - twod3 * w[k];
+        cd0 = mu * (al1 * a1 + al2 * a2p);
+      }
+      const double cD = cd0 - c23muA * w[k];
+      const double cI = kJ2 * w[k] - c23muA * v[k];
+      const int col = idx9(k, l);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          double val = (cD * DA[i][j] + cI * Ai[j][i]) + hw[i] * Ai[j][k];
+          if (i == k) val = val + my[j];
+          st_stream(a.ct + (int64_t)(idx9(i, j) * 9 + col) * ld + i0, val);
+        }
+    }
+  }
+}
+
 template <bool PERPOINT, bool DIAG, int MINB, bool COMPACT = false>
 __global__ void __launch_bounds__(128, MINB)
     dxm_fefp_kernel(const FeFpArgs a) {
   static_assert(!COMPACT || !PERPOINT, "compaction: uniform properties only");
   __shared__ FeFpCompactStore<COMPACT> cs_storage;
   FeFpCompactSmem* cs = cs_storage.get();
-  const int64_t ld = a.ld;
   const int64_t ntile = (a.count + blockDim.x - 1) / blockDim.x;
   PointStats acc;
 
@@ -178,288 +478,7 @@ __global__ void __launch_bounds__(128, MINB)
     if (!COMPACT && !live) continue;
     // COMPACT: every thread of the CTA takes part in the block-level exchange; dead lanes shadow point 0
     const int64_t i0 = a.start + (live ? loc : 0);
-
-    double A[3][3], Ao[3][3], Bo[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        A[i][j] = __ldcs(a.F + (int64_t)idx9(i, j) * ld + i0);
-        Ao[i][j] = __ldcs(a.F_old + (int64_t)idx9(i, j) * ld + i0);
-      }
-    {
-      double beo[6];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) beo[c] = __ldcs(a.be_old + (int64_t)c * ld + i0);
-      Bo[0][0] = beo[0];
-      Bo[1][1] = beo[1];
-      Bo[2][2] = beo[2];
-      Bo[0][1] = Bo[1][0] = beo[3] * kRsqrt2;
-      Bo[0][2] = Bo[2][0] = beo[4] * kRsqrt2;
-      Bo[1][2] = Bo[2][1] = beo[5] * kRsqrt2;
-    }
-    const double p_old = __ldcs(a.p_old + i0);
-
-    double mu, kappa, sig0, H, dsu, b;
-    if (PERPOINT) {
-      const double E = __ldcs(a.pp[0] + i0), nu = __ldcs(a.pp[1] + i0);
-      mu = E / 2.0 / (1.0 + nu);
-      kappa = E / (3.0 * (1.0 - 2.0 * nu));
-      sig0 = __ldcs(a.pp[2] + i0);
-      H = __ldcs(a.pp[3] + i0);
-      const double d = __ldcs(a.pp[4] + i0) - sig0;
-      dsu = isfinite(d) ? d : 0.0;
-      b = __ldcs(a.pp[5] + i0);
-    } else {
-      mu = a.mu;
-      kappa = a.kappa;
-      sig0 = a.sig0;
-      H = a.H;
-      dsu = a.dsu;
-      b = a.b;
-    }
-    const double threemu = 3.0 * mu;
-    const double bdsu = b * dsu;
-
-    // ---- trial state ----------------------------------------------------------------------------
-    double B[3][3], D[3][3];
-    {
-      double Aoi[3][3], deto, f[3][3], M[3][3];
-      inv3(Ao, Aoi, deto);
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-          f[i][j] = dot3(A[i][0], Aoi[0][j], A[i][1], Aoi[1][j], A[i][2], Aoi[2][j]);
-      const double Jf = det3(f);
-      const double rc = rcbrt_c(Jf);
-      const double s23 = rc * rc;
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-          M[i][j] = dot3(f[i][0], Bo[0][j], f[i][1], Bo[1][j], f[i][2], Bo[2][j]);
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = i; j < 3; ++j) {
-          B[i][j] = s23 * dot3(M[i][0], f[j][0], M[i][1], f[j][1], M[i][2], f[j][2]);
-          B[j][i] = B[i][j];
-        }
-    }
-    const double t0 = ((B[0][0] + B[1][1]) + B[2][2]) * kThird;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) D[i][j] = (i == j) ? (B[i][j] - t0) : B[i][j];
-    const double dd = ((D[0][0] * D[0][0] + D[1][1] * D[1][1]) + D[2][2] * D[2][2]) +
-                      2.0 * ((D[0][1] * D[0][1] + D[0][2] * D[0][2]) + D[1][2] * D[1][2]);
-    const double d3 = det3(D);
-    const double seq = mu * sqrt(1.5 * dd);
-    const double rseq = 1.0 / seq;
-
-    double ecur = exp_c(-(b * p_old));
-    const double sy0 = (sig0 + H * p_old) + dsu * (1.0 - ecur);
-    const double ftr = seq - sy0;
-    const bool flag = ftr > 0.0;
-
-    // ---- local 2x2 Newton in (dp, t) ----------------------------------------------------------------
-    const double c = threemu * rseq;
-    double dp = 0.0, t = t0, resid = 0.0;
-    int n_iter = 0;
-    bool fail = false;
-    {
-      FeFpLocalProps lp;
-      lp.threemu = threemu;
-      lp.sig0 = sig0;
-      lp.H = H;
-      lp.dsu = dsu;
-      lp.bdsu = bdsu;
-      lp.b = b;
-      const bool active = live && flag;
-      if (!COMPACT) {
-        // warp-synchronous with a warp-vote early exit (see dxm_small_strain.cuh)
-        fefp_newton(lp, seq, dd, d3, p_old, ecur, dp, t, n_iter, resid, fail, active, warp_mask, a.vote != 0);
-      } else {
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-        const unsigned bal = __ballot_sync(0xffffffffu, active);
-        if (lane == 0) cs->warp_count[w] = __popc(bal);
-        __syncthreads();
-        int base = 0, total = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int cnt = cs->warp_count[i];
-          base += i < w ? cnt : 0;
-          total += cnt;
-        }
-        const int slot = base + __popc(bal & ((1u << lane) - 1u));
-        if (active) {
-          cs->a[0][slot] = seq;
-          cs->a[1][slot] = dd;
-          cs->a[2][slot] = d3;
-          cs->a[3][slot] = t0;
-          cs->a[4][slot] = p_old;
-          cs->a[5][slot] = ecur;
-        }
-        __syncthreads();
-        const bool solver = (int)threadIdx.x < total;
-        const unsigned smask = __ballot_sync(0xffffffffu, solver);
-        if (solver) {
-          const int k = threadIdx.x;
-          const double sq = cs->a[0][k], dd_s = cs->a[1][k], d3_s = cs->a[2][k], po = cs->a[4][k];
-          double ts = cs->a[3][k], ec = cs->a[5][k], d = 0.0, rs = 0.0;
-          int ni = 0;
-          bool fl = false;
-          fefp_newton(lp, sq, dd_s, d3_s, po, ec, d, ts, ni, rs, fl, true, smask, a.vote != 0);
-          cs->a[0][k] = d;
-          cs->a[1][k] = ts;
-          cs->a[2][k] = ec;
-          cs->a[3][k] = rs;
-          cs->meta[k] = ni | (fl ? 1 << 16 : 0);
-        }
-        __syncthreads();
-        if (active) {
-          dp = cs->a[0][slot];
-          t = cs->a[1][slot];
-          ecur = cs->a[2][slot];
-          resid = cs->a[3][slot];
-          const int mt = cs->meta[slot];
-          n_iter = mt & 0xffff;
-          fail = (mt >> 16) != 0;
-        }
-        __syncthreads();  // slots are reused by the next tile
-        if (!live) continue;
-      }
-    }
-    const double alpha = flag ? (1.0 - (c * t) * dp) : 1.0;
-    const double p_new = p_old + dp;
-
-    // ---- new state -----------------------------------------------------------------------------------
-    double be[6];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) be[i] = flag ? (alpha * D[i][i] + t) : B[i][i];
-    be[3] = (alpha * D[0][1]) * kSqrt2;
-    be[4] = (alpha * D[0][2]) * kSqrt2;
-    be[5] = (alpha * D[1][2]) * kSqrt2;
-
-    // ---- stress: tau = mu alpha D + pvol 1,  PK1 = tau F^-T = mu alpha (D F^-T) + pvol F^-T --------------
-    double Ai[3][3], Jd, DA[3][3], P[3][3];
-    inv3(A, Ai, Jd);
-    const double muA = mu * alpha;
-    const double pvol = (0.5 * kappa) * (Jd * Jd - 1.0);
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-        DA[i][j] = dot3(D[i][0], Ai[j][0], D[i][1], Ai[j][1], D[i][2], Ai[j][2]);
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) P[i][j] = muA * DA[i][j] + pvol * Ai[j][i];
-
-    double chk = (seq + fabs(Jd)) + p_new;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) chk = chk + fabs(be[i]);
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) chk = chk + fabs(P[i][j]);
-    if (!isfinite(chk)) fail = true;
-
-    // state and stress stores (the tangent follows)
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) __stcs(a.P + (int64_t)idx9(i, j) * ld + i0, P[i][j]);
-    __stcs(a.p + i0, p_new);
-#pragma unroll
-    for (int c6 = 0; c6 < 6; ++c6) __stcs(a.be + (int64_t)c6 * ld + i0, be[c6]);
-
-    acc.n_plastic += flag ? 1u : 0u;
-    acc.n_fail += fail ? 1u : 0u;
-    acc.max_iter = n_iter > (int)acc.max_iter ? (unsigned)n_iter : acc.max_iter;
-    acc.max_resid = resid > acc.max_resid ? resid : acc.max_resid;
-    if (resid != resid) acc.max_resid = resid;
-    if (DIAG) {
-      a.d_flag[i0] = flag ? 1 : 0;
-      a.d_iter[i0] = n_iter;
-      a.d_resid[i0] = resid;
-      a.d_fail[i0] = fail ? 1 : 0;
-    }
-
-    // ---- local-solve sensitivities: d(alpha) = al1 (D:dD) + al2 (D^2:dD) --------------------------------
-    double al1 = 0.0, al2 = 0.0;
-    if (flag) {
-      const double sq1 = (1.5 * (mu * mu)) * rseq;
-      const double a2 = alpha * alpha;
-      const double dsy = H + bdsu * ecur;
-      const double g = 3.0 * (a2 * d3) - (alpha * dd) * t;
-      const double ct = c * t;
-      const double cdp = c * dp;
-      const double J11 = -(threemu * t) - dsy;
-      const double J12 = -(threemu * dp);
-      const double J21 = -(g * ct);
-      const double J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp;
-      const double rdet = 1.0 / (J11 * J22 - J12 * J21);
-      const double oma = (1.0 - alpha) * rseq;
-      const double b21 = (g * oma) * sq1 - a2 * t;
-      const double b22 = a2 * alpha;
-      const double p1 = -((sq1 * J22 - J12 * b21) * rdet);
-      const double t1 = -((J11 * b21 - J21 * sq1) * rdet);
-      const double p2 = (J12 * b22) * rdet;
-      const double t2 = -((J11 * b22) * rdet);
-      al1 = (oma * sq1 - ct * p1) - cdp * t1;
-      al2 = -(ct * p2) - cdp * t2;
-    }
-
-    // ---- tangent, column (k,l) = d/dF_kl, row (i,j) = PK1_ij; w = row l of F^-1, v = B w = D w + t0 w:
-    //      dP_ij = cD (D F^-T)_ij + cI F^-T_ij + delta_ik mu alpha (F^-1 v)_j + hs w_i F^-1_jk
-    const double kJ2 = kappa * (Jd * Jd);
-    const double c23dd = (2.0 / 3.0) * dd;
-    const double twod3 = 2.0 * d3;
-    const double c23muA = (2.0 / 3.0) * muA;
-    const double hs = muA * t0 - pvol;
-#pragma unroll
-    for (int l = 0; l < 3; ++l) {
-      double w[3], v[3], u[3], z[3], my[3], hw[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) w[i] = Ai[l][i];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) v[i] = dot3(D[i][0], w[0], D[i][1], w[1], D[i][2], w[2]) + t0 * w[i];
-      if (flag) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) u[i] = dot3(D[i][0], v[0], D[i][1], v[1], D[i][2], v[2]);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) z[i] = dot3(D[i][0], u[0], D[i][1], u[1], D[i][2], u[2]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) u[i] = z[i] = 0.0;
-      }
-#pragma unroll
-      for (int j = 0; j < 3; ++j) my[j] = muA * dot3(Ai[j][0], v[0], Ai[j][1], v[1], Ai[j][2], v[2]);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) hw[i] = hs * w[i];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        double cd0 = 0.0;
-        if (flag) {
-          const double a1 = 2.0 * u[k] - c23dd * w[k];
-          const double a2p = (2.0 * z[k] - c23dd * v[k]) - twod3 * w[k];
-          cd0 = mu * (al1 * a1 + al2 * a2p);
-        }
-        const double cD = cd0 - c23muA * w[k];
-        const double cI = kJ2 * w[k] - c23muA * v[k];
-        const int col = idx9(k, l);
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            double val = (cD * DA[i][j] + cI * Ai[j][i]) + hw[i] * Ai[j][k];
-            if (i == k) val = val + my[j];
-            __stcs(a.ct + (int64_t)(idx9(i, j) * 9 + col) * ld + i0, val);
-          }
-      }
-    }
+    fefp_point<PERPOINT, DIAG, COMPACT>(a, i0, live, warp_mask, cs, acc);
   }
   block_reduce_stats(acc, a.stats);
 }

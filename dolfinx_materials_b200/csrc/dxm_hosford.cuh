@@ -34,40 +34,13 @@
 
 namespace dxm {
 
-#define DXM_HD __host__ __device__ __forceinline__
-
 constexpr double kHosRSqrt2 = 0.7071067811865476;
 constexpr double kHosSqrt2 = 1.4142135623730951;
 constexpr int kHosfordLsMax = 10;
 constexpr int kJacobiSweeps = 8;
 
-// exp_c of dxm_canon.cuh written for host and device (same operations; ldexp is exact where it is used)
-DXM_HD double hos_exp(double x) {
-#ifdef __CUDA_ARCH__
-  return exp_c(x);
-#else
-  if (x != x) return x;
-  if (x < -kExpClamp) return 0.0;
-  if (x > kExpClamp) return INFINITY;
-  const double k = rint(x * kLog2e);
-  const double r = (x - k * kLn2Hi) - k * kLn2Lo;
-  double y = 1.0 / 6227020800.0;
-  y = y * r + 1.0 / 479001600.0;
-  y = y * r + 1.0 / 39916800.0;
-  y = y * r + 1.0 / 3628800.0;
-  y = y * r + 1.0 / 362880.0;
-  y = y * r + 1.0 / 40320.0;
-  y = y * r + 1.0 / 5040.0;
-  y = y * r + 1.0 / 720.0;
-  y = y * r + 1.0 / 120.0;
-  y = y * r + 1.0 / 24.0;
-  y = y * r + 1.0 / 6.0;
-  y = y * r + 0.5;
-  y = y * r + 1.0;
-  y = y * r + 1.0;
-  return ldexp(y, (int)k);
-#endif
-}
+// exp_c written for host and device: exp_hd of dxm_canon.cuh
+DXM_HD double hos_exp(double x) { return exp_hd(x); }
 
 // isotropic hardening sigma_Y(p) = sig0 + H p + dsu (1 - exp(-b p)) and its slope at p = p_old + dp (the law of the J2
 // behaviours: linear for dsu = 0, Voce for H = 0)

@@ -84,12 +84,12 @@ struct CompactStore<false> {
 };
 
 // capped scalar Newton on r(dp) = seq - 3 mu dp - sigY(p_old + dp); lanes outside `mask` must not call
-__device__ __forceinline__ void voce_newton(const PointProps& m, const double threemu, const double bdsu,
+DXM_HD void voce_newton(const PointProps& m, const double threemu, const double bdsu,
                                             const double seq, const double p_old, double& ecur, double& dp,
                                             int& n_iter, double& resid, bool& fail, bool active,
                                             const unsigned mask, const bool vote) {
   const double tol = kNewtonRtol * seq;
-  for (int it = 0; vote ? __any_sync(mask, active) : active; ++it) {
+  for (int it = 0; vote ? DXM_ANY_SYNC(mask, active) : active; ++it) {
     if (active) {
       const double p = p_old + dp;
       const double sy = (m.sig0 + m.H * p) + m.dsu * (1.0 - ecur);
@@ -104,16 +104,18 @@ __device__ __forceinline__ void voce_newton(const PointProps& m, const double th
       } else {
         const double dsy = m.H + bdsu * ecur;
         dp = dp + r / (threemu + dsy);
-        ecur = exp_c(-(m.b * (p_old + dp)));
+        ecur = exp_hd(-(m.b * (p_old + dp)));
         ++n_iter;
       }
     }
   }
 }
 
-// One Gauss point.  Returns results through references; everything stays in registers.
+// One Gauss point.  Returns results through references; everything stays in registers.  __host__ __device__ (without
+// COMPACT) so that a CPU test can run the very code the kernel runs per point against the oracle
+// (tests/point_host_check.cu) -- the product only ever calls it from the kernel below.
 template <int HARD, bool COMPACT>
-__device__ __forceinline__ void j2_point(const PointProps& m, const double (&eps)[6],
+DXM_HD void j2_point(const PointProps& m, const double (&eps)[6],
                                          const double (&e_old)[6], const double (&s_old)[6],
                                          const double p_old, const double (&ep_old)[6],
                                          double (&sig)[6], double& p_new, double (&epsp)[6],
@@ -159,7 +161,7 @@ __device__ __forceinline__ void j2_point(const PointProps& m, const double (&eps
         if (p_old >= m.tp[k + 1]) seg = k + 1;
       sy0 = m.ts[seg] + m.tH[seg] * (p_old - m.tp[seg]);
     } else if (HARD == HARD_GENERAL) {
-      ecur = exp_c(-(m.b * p_old));
+      ecur = exp_hd(-(m.b * p_old));
       sy0 = (m.sig0 + m.H * p_old) + m.dsu * (1.0 - ecur);
     } else {
       sy0 = m.sig0 + m.H * p_old;
@@ -193,6 +195,7 @@ __device__ __forceinline__ void j2_point(const PointProps& m, const double (&eps
       if (!COMPACT) {
         voce_newton(m, threemu, bdsu, seq, p_old, ecur, dp, n_iter, resid, fail, active, warp_mask, vote);
       } else {
+#ifdef __CUDA_ARCH__
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
         const unsigned bal = __ballot_sync(0xffffffffu, active);
         if (lane == 0) cs->warp_count[w] = __popc(bal);
@@ -234,6 +237,7 @@ __device__ __forceinline__ void j2_point(const PointProps& m, const double (&eps
           fail = (mt >> 16) != 0;
         }
         __syncthreads();  // slots are reused by the next tile
+#endif
       }
     }
     if (HARD == HARD_GENERAL) Hp = m.H + bdsu * ecur;
@@ -271,6 +275,31 @@ __device__ __forceinline__ void j2_point(const PointProps& m, const double (&eps
 #pragma unroll
   for (int i = 0; i < 6; ++i) chk = chk + fabs(epsp[i]);
   if (!isfinite(chk)) fail = true;
+}
+
+// Lame constants and hardening parameters of one point from its (E, nu, sig0, H, sigu, b) row (per-point properties)
+DXM_HD void point_props(const double E, const double nu, const double sig0, const double H, const double sigu,
+                        const double b, PointProps& m) {
+  m.lam = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu);
+  m.mu = E / 2.0 / (1.0 + nu);
+  m.sig0 = sig0;
+  m.H = H;
+  const double d = sigu - sig0;
+  m.dsu = isfinite(d) ? d : 0.0;
+  m.b = b;
+}
+
+// entry (j, i), j <= i, of the symmetric tangent Ct = A 1x1 + B I - gamma n x n
+DXM_HD double j2_tangent_entry(const int i, const int j, const double A, const double B, const double gamma,
+                               const double ni, const double nj) {
+  double base;
+  if (i == j)
+    base = (i < 3) ? (A + B) : B;
+  else if (i < 3 && j < 3)
+    base = A;
+  else
+    base = 0.0;
+  return base - gamma * (ni * nj);
 }
 
 template <int HARD, bool PERPOINT, int PPT, bool DIAG, int MINB, bool COMPACT = false>
@@ -324,13 +353,7 @@ __global__ void __launch_bounds__(256, MINB)
     for (int k = 0; k < PPT; ++k) {
       PointProps m;
       if (PERPOINT) {
-        m.lam = vE[k] * vnu[k] / (1.0 + vnu[k]) / (1.0 - 2.0 * vnu[k]);
-        m.mu = vE[k] / 2.0 / (1.0 + vnu[k]);
-        m.sig0 = vs0[k];
-        m.H = vH[k];
-        const double d = vsu[k] - vs0[k];
-        m.dsu = isfinite(d) ? d : 0.0;
-        m.b = vb[k];
+        point_props(vE[k], vnu[k], vs0[k], vH[k], vsu[k], vb[k], m);
       } else {
         m.lam = a.lam;
         m.mu = a.mu;
@@ -391,16 +414,7 @@ __global__ void __launch_bounds__(256, MINB)
       for (int i = j; i < 6; ++i) {
         double v[PPT];
 #pragma unroll
-        for (int k = 0; k < PPT; ++k) {
-          double base;
-          if (i == j)
-            base = (i < 3) ? (A[k] + B[k]) : B[k];
-          else if (i < 3 && j < 3)
-            base = A[k];
-          else
-            base = 0.0;
-          v[k] = base - gamma[k] * (nrm[i][k] * nrm[j][k]);
-        }
+        for (int k = 0; k < PPT; ++k) v[k] = j2_tangent_entry(i, j, A[k], B[k], gamma[k], nrm[i][k], nrm[j][k]);
         // symmetric: each unique entry is written once, packed (sym6_packed); the boundary transposes mirror it
         stv<PPT>(a.ct + (int64_t)sym6_packed(j * 6 + i) * ld + i0, v);
       }
