@@ -49,18 +49,17 @@ struct FeFormArgs {
 
 constexpr int kFeMaxNd = 20;  // generic path: up to P3 tetrahedra
 
-__device__ __forceinline__ constexpr int idx9_c(int i, int j) {
+DXM_HD constexpr int idx9_c(int i, int j) {
   return i == j ? i : (i == 0 && j == 1) ? 3 : (i == 1 && j == 0) ? 4 : (i == 0 && j == 2) ? 5
                   : (i == 2 && j == 0) ? 6 : (i == 1 && j == 2) ? 7 : 8;
 }
-__device__ __forceinline__ constexpr int idx6_c(int i, int j) {
+DXM_HD constexpr int idx6_c(int i, int j) {
   return i == j ? i : (i + j == 1) ? 3 : (i + j == 2) ? 4 : 5;
 }
 
 // J^-1 and det J of an affine simplex, same operation order as fe_gradient_kernel / oracle.fe_forms.geometry
 template <int TDIM>
-__device__ __forceinline__ void cell_geometry(const double* coords, const int32_t* gd, double (&K)[TDIM][TDIM],
-                                              double& det) {
+DXM_HD void cell_geometry(const double* coords, const int32_t* gd, double (&K)[TDIM][TDIM], double& det) {
   double x0[TDIM], J[TDIM][TDIM];
   const double* p0 = coords + (int64_t)gd[0] * 3;
 #pragma unroll
@@ -138,6 +137,94 @@ inline FeFormSmem fe_form_smem(int tdim, int nd, int nqp, int kind, int mode, bo
   return s;
 }
 
+// vol_q = w_q |det J| and g[a][j] = sum_m dphi[q][a][m] K[m][j] of Gauss point q of `cell` (the kernel's staging step)
+template <int TDIM>
+DXM_HD void fe_form_point_geometry(const FeFormArgs& a, const int64_t cell, const int q, const int nd, double& vol,
+                                   double* g) {
+  double K[TDIM][TDIM], det;
+  cell_geometry<TDIM>(a.coords, a.geom_dofs + cell * (TDIM + 1), K, det);
+  vol = a.weights[q] * fabs(det);
+  const double* dq = a.dphi + (int64_t)q * nd * TDIM;
+  for (int n = 0; n < nd; ++n) {
+#pragma unroll
+    for (int j = 0; j < TDIM; ++j) {
+      double acc = dq[n * TDIM] * K[0][j];
+#pragma unroll
+      for (int m = 1; m < TDIM; ++m) acc = acc + dq[n * TDIM + m] * K[m][j];
+      g[n * TDIM + j] = acc;
+    }
+  }
+}
+
+// Row (a, r) of the element vector / matrix of local cell `lc` from the staged arrays: vol [np], g [np][nd][TDIM],
+// flux [nflux][np], ct [nct][np] (shared memory in the kernel).  __host__ __device__ like the point routines of the
+// constitutive kernels, so that a CPU test can run it against the oracle (tests/fe_host_check.cu).
+template <int TDIM, int ND>
+DXM_HD void fe_form_row(const int kind, const bool want_mat, const int nqp, const int nd, const int np, const int lc,
+                        const int an, const int r, const double* s_vol, const double* s_g, const double* s_flux,
+                        const double* s_ct, double& fe, double* acc) {
+  constexpr double kR2 = 0.70710678118654752440;
+  constexpr int NDC = ND > 0 ? ND : kFeMaxNd;
+  for (int q = 0; q < nqp; ++q) {
+    const int pt = lc * nqp + q;
+    const double vol = s_vol[pt];
+    const double* g = s_g + (int64_t)pt * nd * TDIM;
+    double ga[TDIM];
+#pragma unroll
+    for (int j = 0; j < TDIM; ++j) ga[j] = g[an * TDIM + j];
+    // residual row
+    {
+      double t = 0.0;
+#pragma unroll
+      for (int j = 0; j < TDIM; ++j) {
+        double S;
+        if (kind == 1) {
+          S = s_flux[idx9_c(r, j) * np + pt];
+        } else {
+          S = s_flux[idx6_c(r, j) * np + pt];
+          if (r != j) S = S * kR2;
+        }
+        t = j == 0 ? S * ga[0] : t + S * ga[j];
+      }
+      fe = q == 0 ? vol * t : fe + vol * t;
+    }
+    if (!want_mat) continue;
+    // W[s][l] = sum_j g[a][j] A(rj, sl)
+    double W[TDIM][TDIM];
+#pragma unroll
+    for (int s = 0; s < TDIM; ++s)
+#pragma unroll
+      for (int l = 0; l < TDIM; ++l) {
+        double w = 0.0;
+#pragma unroll
+        for (int j = 0; j < TDIM; ++j) {
+          double A;
+          if (kind == 1) {
+            A = s_ct[(idx9_c(r, j) * 9 + idx9_c(s, l)) * np + pt];
+          } else {
+            A = s_ct[sym6_packed(idx6_c(r, j) * 6 + idx6_c(s, l)) * np + pt];
+            const int noff = (r != j ? 1 : 0) + (s != l ? 1 : 0);
+            if (noff == 1) A = A * kR2;
+            if (noff == 2) A = A * 0.5;
+          }
+          w = j == 0 ? ga[0] * A : w + ga[j] * A;
+        }
+        W[s][l] = w;
+      }
+#pragma unroll
+    for (int b = 0; b < NDC; ++b) {
+      if (ND == 0 && b >= nd) break;
+#pragma unroll
+      for (int s = 0; s < TDIM; ++s) {
+        double t2 = W[s][0] * g[b * TDIM];
+#pragma unroll
+        for (int l = 1; l < TDIM; ++l) t2 = t2 + W[s][l] * g[b * TDIM + l];
+        acc[b * TDIM + s] = q == 0 ? vol * t2 : acc[b * TDIM + s] + vol * t2;
+      }
+    }
+  }
+}
+
 template <int TDIM, int ND, int MODE>
 __global__ void __launch_bounds__(256) fe_forms_kernel(const FeFormArgs a, const FeFormSmem L) {
   extern __shared__ double smem[];
@@ -154,25 +241,11 @@ __global__ void __launch_bounds__(256) fe_forms_kernel(const FeFormArgs a, const
   const int ncell = (int)min((int64_t)cpb, a.num_cells - c0);
   const int npv = ncell * nqp;
   const int64_t p0 = c0 * nqp;
-  constexpr double kR2 = 0.70710678118654752440;
 
   // ---- stage: geometry -> vol_q, g[q][a][j]; flux / tangent rows of this CTA's points -------------------
   for (int i = threadIdx.x; i < npv; i += blockDim.x) {
     const int lc = i / nqp, q = i - lc * nqp;
-    double K[TDIM][TDIM], det;
-    cell_geometry<TDIM>(a.coords, a.geom_dofs + (c0 + lc) * (TDIM + 1), K, det);
-    s_vol[i] = a.weights[q] * fabs(det);
-    const double* dq = a.dphi + (int64_t)q * nd * TDIM;
-    double* g = s_g + (int64_t)i * nd * TDIM;
-    for (int n = 0; n < nd; ++n) {
-#pragma unroll
-      for (int j = 0; j < TDIM; ++j) {
-        double acc = dq[n * TDIM] * K[0][j];
-#pragma unroll
-        for (int m = 1; m < TDIM; ++m) acc = acc + dq[n * TDIM + m] * K[m][j];
-        g[n * TDIM + j] = acc;
-      }
-    }
+    fe_form_point_geometry<TDIM>(a, c0 + lc, q, nd, s_vol[i], s_g + (int64_t)i * nd * TDIM);
   }
   for (int i = threadIdx.x; i < nflux * np; i += blockDim.x) {
     const int row = i / np, k = i - row * np;
@@ -193,66 +266,7 @@ __global__ void __launch_bounds__(256) fe_forms_kernel(const FeFormArgs a, const
   constexpr int NDC = ND > 0 ? ND : kFeMaxNd;
   double fe = 0.0;
   double acc[NDC * TDIM];
-  if (live) {
-    for (int q = 0; q < nqp; ++q) {
-      const int pt = lc * nqp + q;
-      const double vol = s_vol[pt];
-      const double* g = s_g + (int64_t)pt * nd * TDIM;
-      double ga[TDIM];
-#pragma unroll
-      for (int j = 0; j < TDIM; ++j) ga[j] = g[an * TDIM + j];
-      // residual row
-      {
-        double t = 0.0;
-#pragma unroll
-        for (int j = 0; j < TDIM; ++j) {
-          double S;
-          if (a.kind == 1) {
-            S = s_flux[idx9_c(r, j) * np + pt];
-          } else {
-            S = s_flux[idx6_c(r, j) * np + pt];
-            if (r != j) S = S * kR2;
-          }
-          t = j == 0 ? S * ga[0] : t + S * ga[j];
-        }
-        fe = q == 0 ? vol * t : fe + vol * t;
-      }
-      if (!a.want_mat) continue;
-      // W[s][l] = sum_j g[a][j] A(rj, sl)
-      double W[TDIM][TDIM];
-#pragma unroll
-      for (int s = 0; s < TDIM; ++s)
-#pragma unroll
-        for (int l = 0; l < TDIM; ++l) {
-          double w = 0.0;
-#pragma unroll
-          for (int j = 0; j < TDIM; ++j) {
-            double A;
-            if (a.kind == 1) {
-              A = s_ct[(idx9_c(r, j) * 9 + idx9_c(s, l)) * np + pt];
-            } else {
-              A = s_ct[sym6_packed(idx6_c(r, j) * 6 + idx6_c(s, l)) * np + pt];
-              const int noff = (r != j ? 1 : 0) + (s != l ? 1 : 0);
-              if (noff == 1) A = A * kR2;
-              if (noff == 2) A = A * 0.5;
-            }
-            w = j == 0 ? ga[0] * A : w + ga[j] * A;
-          }
-          W[s][l] = w;
-        }
-#pragma unroll
-      for (int b = 0; b < NDC; ++b) {
-        if (ND == 0 && b >= nd) break;
-#pragma unroll
-        for (int s = 0; s < TDIM; ++s) {
-          double t2 = W[s][0] * g[b * TDIM];
-#pragma unroll
-          for (int l = 1; l < TDIM; ++l) t2 = t2 + W[s][l] * g[b * TDIM + l];
-          acc[b * TDIM + s] = q == 0 ? vol * t2 : acc[b * TDIM + s] + vol * t2;
-        }
-      }
-    }
-  }
+  if (live) fe_form_row<TDIM, ND>(a.kind, a.want_mat != 0, nqp, nd, np, lc, an, r, s_vol, s_g, s_flux, s_ct, fe, acc);
 
   if (MODE == MODE_ELEMENT) {
     if (live && a.want_vec) a.fe[(c0 + lc) * ndof + row] = fe;

@@ -27,17 +27,12 @@ struct FeGradArgs {
 
 constexpr int kFeMaxTab = 4 * 10 * 3 * 4;  // doubles of tabulated gradients staged in shared memory
 
+// One cell: J^-1, nodal displacements, every quadrature point of the cell.  __host__ __device__ so that a CPU test can
+// run the very code the kernel runs per cell against the oracle (tests/fe_host_check.cu) -- the product only ever calls
+// it from the kernel below.  `dphi`: the tabulated gradients (shared memory in the kernel).
 template <int TDIM, int ND>
-__global__ void __launch_bounds__(128) fe_gradient_kernel(const FeGradArgs a) {
-  __shared__ double s_dphi[kFeMaxTab];
-  const int nd = ND > 0 ? ND : a.nd;
-  const int ntab = a.nqp * nd * TDIM;
-  for (int i = threadIdx.x; i < ntab && i < kFeMaxTab; i += blockDim.x) s_dphi[i] = a.dphi[i];
-  __syncthreads();
-  const double* dphi = ntab <= kFeMaxTab ? s_dphi : a.dphi;
+DXM_HD void fe_gradient_cell(const FeGradArgs& a, const double* dphi, const int nd, const int64_t c) {
   constexpr double kR2 = 0.70710678118654752440;
-  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c >= a.num_cells) return;
 
   // affine geometry: J[i][j] = x_{j+1}[i] - x_0[i]
   double x0[TDIM], J[TDIM][TDIM], K[TDIM][TDIM];
@@ -152,6 +147,19 @@ __global__ void __launch_bounds__(128) fe_gradient_kernel(const FeGradArgs a) {
       o[8 * a.ld] = G[2][1];
     }
   }
+}
+
+template <int TDIM, int ND>
+__global__ void __launch_bounds__(128) fe_gradient_kernel(const FeGradArgs a) {
+  __shared__ double s_dphi[kFeMaxTab];
+  const int nd = ND > 0 ? ND : a.nd;
+  const int ntab = a.nqp * nd * TDIM;
+  for (int i = threadIdx.x; i < ntab && i < kFeMaxTab; i += blockDim.x) s_dphi[i] = a.dphi[i];
+  __syncthreads();
+  const double* dphi = ntab <= kFeMaxTab ? s_dphi : a.dphi;
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= a.num_cells) return;
+  fe_gradient_cell<TDIM, ND>(a, dphi, nd, c);
 }
 
 }  // namespace dxm
