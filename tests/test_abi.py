@@ -85,7 +85,7 @@ def test_protocol_surface_without_gpu(jm):
     with pytest.raises(TypeError):
         jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.TabulatedHardening(p=[0.0, 1.0], sig=[1.0, 2.0]))
     with pytest.raises(TypeError):
-        jm.CUDAMaterial(jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=lambda p: 1.0))
+        jm.CUDAMaterial(jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=lambda p: 1.0 + p ** 0.3))  # not of the kernels' family
     with pytest.raises(KeyError):
         m.update_material_property("nope", 1.0)
 

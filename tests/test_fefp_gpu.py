@@ -56,6 +56,44 @@ def test_FeFp_plasticity(jm, Nbatch=10):
     assert np.array_equal(state["be_bar"], ref["be_bar"]) and np.array_equal(state["F"], F)
 
 
+def test_FeFp_plasticity_yield_stress_callable(jm, Nbatch=10):
+    """tests/test_FeFp_jax.py:6-33 line for line, including the ``yield_stress`` *function* it hands to
+    ``FeFpJ2Plasticity`` (numpy standing in for jax.numpy): the host side recognises the Voce law behind it."""
+    E = 70e3
+    nu = 0.3
+    sig0 = 500.0
+
+    b = 1000
+    sigu = 750.0
+
+    def yield_stress(p):
+        return sig0 + (sigu - sig0) * (1 - np.exp(-b * p))
+
+    elastic_model = jm.LinearElasticIsotropic(E=E, nu=nu)
+
+    behavior = jm.FeFpJ2Plasticity(elasticity=elastic_model, yield_stress=yield_stress)
+    material = jm.CUDAMaterial(behavior)
+    material.set_data_manager(Nbatch)
+    assert material.material_properties == {"E": E, "nu": nu, "sig0": 500.0, "sigu": 750.0, "b": 1000.0, "H": 0.0}
+
+    eps = 2e-2
+
+    Nsteps = 20
+    dt = 0
+    st = fefp.virgin_state(Nbatch)
+    for t in np.linspace(0, 1.0, Nsteps)[1:]:
+        F = np.zeros((Nbatch, 9))
+        F[:, 0] = 1 + eps * t
+        F[:, [1, 2]] = 1 - eps / 2 * t
+        P, isv, Ct = material.integrate(F, dt)
+        ref = fefp.integrate(F, st, PROPS)
+        assert np.array_equal(P, ref["PK1"]) and np.array_equal(Ct, ref["Ct"]) and np.array_equal(isv[:, 0], ref["p"])
+
+        material.data_manager.update()
+        st = fefp.advance(ref)
+    assert abs(isv[0, 0] - 1.076097e-2) < 5e-9 and abs(P[0, 0] - 473.1527) < 5e-5
+
+
 @pytest.mark.parametrize("n", [1, 33, 1000, 50021])
 def test_random_history_bit_exact(jm, n):
     material = make(jm, n)
