@@ -29,6 +29,13 @@ def test_library_exports_every_declared_symbol(jm):
     assert b"sm_100a" in lib.dxm_version()
 
 
+def test_integration_guide_names_every_entry_point():
+    """INTEGRATION.md section 3 maps each C entry point to the reference interface it replaces: none may be missing."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [s for s in header_symbols() if s not in doc]
+    assert not missing, f"INTEGRATION.md does not mention {missing}"
+
+
 def test_library_contains_sm100a_sass_only(jm):
     from dolfinx_materials_b200 import _lib
 
