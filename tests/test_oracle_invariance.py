@@ -142,3 +142,46 @@ def test_fefp_is_isotropic_under_change_of_reference_frame():
         assert np.allclose(rot["p"], ref["p"], rtol=1e-8, atol=1e-15)
         st, st_r = fefp.advance(ref), fefp.advance(rot)
     assert ref["flag"].mean() > 0.3
+
+
+def test_fefp_small_strain_limit_is_the_j2_voce_law():
+    """Two independently formulated restatements meet: for displacement gradients of order 1e-5 (and a yield stress scaled
+    down so that most points still yield) the multiplicative FeFp update reduces to the additive small-strain J2 + Voce
+    update to first order in |grad u| -- PK1 -> sigma, same cumulated plastic strain, dP/dF -> the small-strain tangent."""
+    n, K, amp = 1500, 3, 4e-5
+    props = dict(E=70e3, nu=0.3, sig0=0.5, sigu=0.75, b=2e5)
+    st9, st6 = fefp.virgin_state(n), ss.zero_state(n)
+    for k in range(1, K + 1):
+        F = synth.defgrad(n, 8, amp, k, K)
+        H = v9_to_tensor(F) - np.eye(3)
+        eps = tensor_to_mandel(0.5 * (H + np.swapaxes(H, -1, -2)))
+        fin = fefp.integrate(F, st9, props)
+        sml = ss.integrate(np.ascontiguousarray(eps), st6, props)
+        small = np.abs(H).max()  # ~1e-4: size of the neglected geometric terms
+        assert small < 2e-4 and fin["fail"].sum() == 0 and sml["fail"].sum() == 0
+        sig = mandel_to_tensor(sml["stress"])
+        P = v9_to_tensor(fin["PK1"])
+        assert np.abs(P - sig).max() <= 5 * small * np.abs(sig).max()  # measured: 1.7 |grad u|
+        both = (fin["flag"] == 1) & (sml["flag"] == 1)
+        assert (fin["flag"] != sml["flag"]).mean() < 0.01  # only points within O(|grad u|) of the yield surface may differ
+        assert np.allclose(fin["p"][both], sml["p"][both], rtol=50 * small, atol=1e-4 * sml["p"].max())
+        # dP_ij/dF_kl vs C_ijkl of the small-strain tangent (minor symmetries: Mandel factors undone)
+        C4 = np.empty((n, 3, 3, 3, 3))
+        for r_, (i, j) in enumerate(IDX9):
+            for c_, (kk, l) in enumerate(IDX9):
+                C4[:, i, j, kk, l] = fin["Ct"][:, r_, c_]
+        M6 = [(0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2)]
+        C4s = np.empty_like(C4)
+        for a_, (i, j) in enumerate(M6):
+            for b_, (kk, l) in enumerate(M6):
+                v = sml["Ct"][:, a_, b_] / ((R2 if i != j else 1.0) * (R2 if kk != l else 1.0))
+                for (ii, jj) in {(i, j), (j, i)}:
+                    for (k2, l2) in {(kk, l), (l, kk)}:
+                        C4s[:, ii, jj, k2, l2] = v
+        agree = fin["flag"] == sml["flag"]
+        err = np.abs(C4[agree] - C4s[agree]).reshape(agree.sum(), -1).max(axis=1)
+        # first order in |grad u| almost everywhere; points sitting within O(|grad u|) of the yield surface have an
+        # O(1) sensitivity of the plastic moduli to that perturbation
+        assert np.quantile(err, 0.98) <= 50 * small * np.abs(C4s).max()
+        st9, st6 = fefp.advance(fin), ss.advance(sml)
+    assert both.mean() > 0.3
