@@ -219,3 +219,35 @@ def test_fefp_point_routine_per_point_properties_and_bad_input(host):
         assert_same(run_fefp(host, F, st, props), ref, FEFP_KEYS, (k,))
         st = fefp.advance(ref)
     assert ref["fail"][5] == 1 and ref["fail"][6] == 1 and ref["fail"].sum() == 2
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_point_routines_differential_fuzz_over_extreme_regimes(host, seed):
+    """Strain amplitudes from 1e-14 to 30, moduli over 8 decades, Poisson ratios from -0.9 to 0.499, hardening rates
+    over 10 decades: whatever regime a point ends up in (elastic, converged, capped, non-finite) the kernel routines
+    and the oracle agree bit for bit -- flags, iteration counts, residuals, results."""
+    rng = np.random.default_rng(seed)
+    idx9 = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 0), (0, 2), (2, 0), (1, 2), (2, 1)]
+    regimes = set()
+    for _ in range(4):
+        n = 3000
+        props = dict(E=10 ** rng.uniform(0, 8), nu=rng.uniform(-0.9, 0.499), sig0=10 ** rng.uniform(-3, 5),
+                     b=10 ** rng.uniform(-3, 7), H=float(rng.choice([0.0, 10 ** rng.uniform(-6, 6)])))
+        props["sigu"] = props["sig0"] * rng.uniform(0.5, 3.0)
+        eps = rng.standard_normal((n, 6)) * 10.0 ** rng.uniform(-14, 1.5, (n, 1))
+        st = ss.zero_state(n)
+        with np.errstate(all="ignore"):
+            for k in (1, 2):
+                ref = ss.integrate(eps * k / 2, st, props)
+                assert_same(run_j2(host, eps * k / 2, st, props, HARD_GENERAL), ref, J2_KEYS, ("j2", props, k))
+                st = ss.advance(ref)
+            regimes |= {("j2", int(f), int(x)) for f, x in zip(ref["flag"], ref["fail"])}
+            G = rng.standard_normal((n, 3, 3)) * 10.0 ** rng.uniform(-12, -0.3, (n, 1, 1))
+            F = np.ascontiguousarray(np.stack([(np.eye(3) + G)[:, i, j] for (i, j) in idx9], axis=1))
+            st = fefp.virgin_state(n)
+            for Fk in (np.ascontiguousarray(0.5 * (st["F"] + F)), F):
+                ref = fefp.integrate(Fk, st, props)
+                assert_same(run_fefp(host, Fk, st, props), ref, FEFP_KEYS, ("fefp", props))
+                st = fefp.advance(ref)
+            regimes |= {("fefp", int(f), int(x)) for f, x in zip(ref["flag"], ref["fail"])}
+    assert {("j2", 0, 0), ("j2", 1, 0), ("fefp", 0, 0), ("fefp", 1, 0)} <= regimes
