@@ -1,6 +1,9 @@
-// Canonical fp64 building blocks.  The whole library is compiled with -fmad=false: every
-// expression below is a sequence of correctly rounded IEEE-754 operations in a fixed order, which
-// is what makes the kernels bit-comparable with the CPU oracle (oracle/canon.py).
+// Canonical fp64 building blocks.  The whole library is compiled with -fmad=false: the compiler never contracts
+// a product into an addition on its own.  Every expression below is a sequence of correctly rounded IEEE-754
+// operations in a fixed order -- + - * / sqrt rint and the EXPLICIT fused multiply-add fma_c / fms_c / fnma_c, placed by
+// hand at the same positions as in the CPU oracle (oracle/canon.py, oracle/c/dxm_canon.h) -- which is what makes the
+// kernels bit-comparable with the oracle while issuing one DFMA where the un-fused form needed DMUL + DADD.
+// -DDXM_UNFUSED turns the three helpers back into two roundings (the round-1 arithmetic; A/B builds only).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -14,26 +17,45 @@ constexpr double kLn2Hi = 6.93147180369123816490e-01;
 constexpr double kLn2Lo = 1.90821492927058770002e-10;
 constexpr double kExpClamp = 700.0;
 
-// exp(x): Cody-Waite reduction, degree-13 Horner (mul + add, never fused), exact 2^k scaling.
+#define DXM_HD __host__ __device__ __forceinline__
+
+// a*b + c, a*b - c, c - a*b with ONE rounding (DFMA on the device, fma() of <cmath> on the host)
+#ifdef DXM_UNFUSED
+DXM_HD double fma_c(double a, double b, double c) { return a * b + c; }
+DXM_HD double fms_c(double a, double b, double c) { return a * b - c; }
+DXM_HD double fnma_c(double a, double b, double c) { return c - a * b; }
+#else
+DXM_HD double fma_c(double a, double b, double c) { return fma(a, b, c); }
+DXM_HD double fms_c(double a, double b, double c) { return fma(a, b, -c); }
+DXM_HD double fnma_c(double a, double b, double c) { return fma(-a, b, c); }
+#endif
+
+// degree-13 Horner polynomial of exp on the reduced argument (13 fused steps)
+DXM_HD double exp_poly(double r) {
+  double y = 1.0 / 6227020800.0;
+  y = fma_c(y, r, 1.0 / 479001600.0);
+  y = fma_c(y, r, 1.0 / 39916800.0);
+  y = fma_c(y, r, 1.0 / 3628800.0);
+  y = fma_c(y, r, 1.0 / 362880.0);
+  y = fma_c(y, r, 1.0 / 40320.0);
+  y = fma_c(y, r, 1.0 / 5040.0);
+  y = fma_c(y, r, 1.0 / 720.0);
+  y = fma_c(y, r, 1.0 / 120.0);
+  y = fma_c(y, r, 1.0 / 24.0);
+  y = fma_c(y, r, 1.0 / 6.0);
+  y = fma_c(y, r, 0.5);
+  y = fma_c(y, r, 1.0);
+  y = fma_c(y, r, 1.0);
+  return y;
+}
+
+// exp(x): Cody-Waite reduction, degree-13 Horner (fused steps), exact 2^k scaling.
 __device__ __forceinline__ double exp_c(double x) {
   const bool inr = (x >= -kExpClamp) && (x <= kExpClamp);
   const double xs = inr ? x : 0.0;
   const double k = rint(xs * kLog2e);
-  const double r = (xs - k * kLn2Hi) - k * kLn2Lo;
-  double y = 1.0 / 6227020800.0;
-  y = y * r + 1.0 / 479001600.0;
-  y = y * r + 1.0 / 39916800.0;
-  y = y * r + 1.0 / 3628800.0;
-  y = y * r + 1.0 / 362880.0;
-  y = y * r + 1.0 / 40320.0;
-  y = y * r + 1.0 / 5040.0;
-  y = y * r + 1.0 / 720.0;
-  y = y * r + 1.0 / 120.0;
-  y = y * r + 1.0 / 24.0;
-  y = y * r + 1.0 / 6.0;
-  y = y * r + 0.5;
-  y = y * r + 1.0;
-  y = y * r + 1.0;
+  const double r = fnma_c(k, kLn2Lo, fnma_c(k, kLn2Hi, xs));
+  double y = exp_poly(r);
   // |k| <= 1010 and y in [0.7, 1.5]: 2^k is a normal double and the product is exact
   const int ki = (int)k;
   y = y * __hiloint2double((ki + 1023) << 20, 0);
@@ -42,8 +64,6 @@ __device__ __forceinline__ double exp_c(double x) {
   if (x != x) y = x;
   return y;
 }
-
-#define DXM_HD __host__ __device__ __forceinline__
 
 // exp_c for code that is compiled for the host as well (the per-point routines the CPU tests execute against the
 // oracle, tests/*_host_check.cu): on the device it IS exp_c; on the host the same operations, with ldexp doing the
@@ -56,22 +76,8 @@ DXM_HD double exp_hd(double x) {
   if (x < -kExpClamp) return 0.0;
   if (x > kExpClamp) return INFINITY;
   const double k = rint(x * kLog2e);
-  const double r = (x - k * kLn2Hi) - k * kLn2Lo;
-  double y = 1.0 / 6227020800.0;
-  y = y * r + 1.0 / 479001600.0;
-  y = y * r + 1.0 / 39916800.0;
-  y = y * r + 1.0 / 3628800.0;
-  y = y * r + 1.0 / 362880.0;
-  y = y * r + 1.0 / 40320.0;
-  y = y * r + 1.0 / 5040.0;
-  y = y * r + 1.0 / 720.0;
-  y = y * r + 1.0 / 120.0;
-  y = y * r + 1.0 / 24.0;
-  y = y * r + 1.0 / 6.0;
-  y = y * r + 0.5;
-  y = y * r + 1.0;
-  y = y * r + 1.0;
-  return ldexp(y, (int)k);
+  const double r = fnma_c(k, kLn2Lo, fnma_c(k, kLn2Hi, x));
+  return ldexp(exp_poly(r), (int)k);
 #endif
 }
 

@@ -64,9 +64,9 @@ DXM_HD double rcbrt_c(double x) {
   const int q = (e >= 0) ? (e / 3) : -((-e + 2) / 3);
   const int r = e - 3 * q;
   const double xr = m * (double)(1 << r);
-  double y = 1.2 - 0.15 * xr;
+  double y = fnma_c(0.15, xr, 1.2);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) y = (y * (4.0 - xr * ((y * y) * y))) * kThird;
+  for (int i = 0; i < 6; ++i) y = (y * fnma_c(xr, (y * y) * y, 4.0)) * kThird;
 #ifdef __CUDA_ARCH__
   return y * __hiloint2double((1023 - q) << 20, 0);
 #else
@@ -76,28 +76,28 @@ DXM_HD double rcbrt_c(double x) {
 
 DXM_HD double dot3(double a0, double b0, double a1, double b1, double a2,
                                        double b2) {
-  return (a0 * b0 + a1 * b1) + a2 * b2;
+  return fma_c(a2, b2, fma_c(a1, b1, a0 * b0));
 }
 
 DXM_HD double det3(const double (&A)[3][3]) {
-  const double t0 = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]);
-  const double t1 = A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]);
-  const double t2 = A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
-  return (t0 - t1) + t2;
+  const double m0 = fms_c(A[1][1], A[2][2], A[1][2] * A[2][1]);
+  const double m1 = fms_c(A[1][0], A[2][2], A[1][2] * A[2][0]);
+  const double m2 = fms_c(A[1][0], A[2][1], A[1][1] * A[2][0]);
+  return fma_c(A[0][2], m2, fnma_c(A[0][1], m1, A[0][0] * m0));
 }
 
 DXM_HD void inv3(const double (&A)[3][3], double (&Ai)[3][3], double& det) {
   double c[3][3];
-  c[0][0] = A[1][1] * A[2][2] - A[1][2] * A[2][1];
-  c[0][1] = A[0][2] * A[2][1] - A[0][1] * A[2][2];
-  c[0][2] = A[0][1] * A[1][2] - A[0][2] * A[1][1];
-  c[1][0] = A[1][2] * A[2][0] - A[1][0] * A[2][2];
-  c[1][1] = A[0][0] * A[2][2] - A[0][2] * A[2][0];
-  c[1][2] = A[0][2] * A[1][0] - A[0][0] * A[1][2];
-  c[2][0] = A[1][0] * A[2][1] - A[1][1] * A[2][0];
-  c[2][1] = A[0][1] * A[2][0] - A[0][0] * A[2][1];
-  c[2][2] = A[0][0] * A[1][1] - A[0][1] * A[1][0];
-  det = (A[0][0] * c[0][0] + A[0][1] * c[1][0]) + A[0][2] * c[2][0];
+  c[0][0] = fms_c(A[1][1], A[2][2], A[1][2] * A[2][1]);
+  c[0][1] = fms_c(A[0][2], A[2][1], A[0][1] * A[2][2]);
+  c[0][2] = fms_c(A[0][1], A[1][2], A[0][2] * A[1][1]);
+  c[1][0] = fms_c(A[1][2], A[2][0], A[1][0] * A[2][2]);
+  c[1][1] = fms_c(A[0][0], A[2][2], A[0][2] * A[2][0]);
+  c[1][2] = fms_c(A[0][2], A[1][0], A[0][0] * A[1][2]);
+  c[2][0] = fms_c(A[1][0], A[2][1], A[1][1] * A[2][0]);
+  c[2][1] = fms_c(A[0][1], A[2][0], A[0][0] * A[2][1]);
+  c[2][2] = fms_c(A[0][0], A[1][1], A[0][1] * A[1][0]);
+  det = fma_c(A[0][2], c[2][0], fma_c(A[0][1], c[1][0], A[0][0] * c[0][0]));
   const double rdet = 1.0 / det;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -119,12 +119,16 @@ DXM_HD void fefp_newton(const FeFpLocalProps& m, const double seq, const double 
   const double tol1 = kFeNewtonRtol * seq;
   for (int it = 0; vote ? DXM_ANY_SYNC(mask, active) : active; ++it) {
     if (active) {
-      const double alpha = 1.0 - (c * t) * dp;
+      const double ct = c * t;
+      const double tmt = m.threemu * t;
+      const double alpha = fnma_c(ct, dp, 1.0);
       const double p = p_old + dp;
-      const double sy = (m.sig0 + m.H * p) + m.dsu * (1.0 - ecur);
-      const double r1 = (seq - (m.threemu * t) * dp) - sy;
+      const double sy = fma_c(m.dsu, 1.0 - ecur, fma_c(m.H, p, m.sig0));
+      const double r1 = fnma_c(tmt, dp, seq) - sy;
       const double a2 = alpha * alpha;
-      const double r2 = ((t * t) * t - (0.5 * a2) * (dd * t)) + ((a2 * alpha) * d3 - 1.0);
+      const double ha2 = 0.5 * a2;
+      const double tt = t * t;
+      const double r2 = fnma_c(ha2, dd * t, tt * t) + fms_c(a2 * alpha, d3, 1.0);
       if (fabs(r1) <= tol1 && fabs(r2) <= kFeNewtonRtol) {
         resid = fabs(r1);
         active = false;
@@ -133,17 +137,16 @@ DXM_HD void fefp_newton(const FeFpLocalProps& m, const double seq, const double 
         fail = true;
         active = false;
       } else {
-        const double dsy = m.H + m.bdsu * ecur;
-        const double g = 3.0 * (a2 * d3) - (alpha * dd) * t;
-        const double J11 = -(m.threemu * t) - dsy;
+        const double dsy = fma_c(m.bdsu, ecur, m.H);
+        const double g = fnma_c(alpha * dd, t, 3.0 * (a2 * d3));
+        const double J11 = -tmt - dsy;
         const double J12 = -(m.threemu * dp);
-        const double ct = c * t;
         const double cdp = c * dp;
         const double J21 = -(g * ct);
-        const double J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp;
-        const double rdet = 1.0 / (J11 * J22 - J12 * J21);
-        const double dp_new = dp + (J12 * r2 - r1 * J22) * rdet;
-        const double t_new = t + (J21 * r1 - J11 * r2) * rdet;
+        const double J22 = fnma_c(g, cdp, fnma_c(ha2, dd, 3.0 * tt));
+        const double rdet = 1.0 / fms_c(J11, J22, J12 * J21);
+        const double dp_new = fma_c(fms_c(J12, r2, r1 * J22), rdet, dp);
+        const double t_new = fma_c(fms_c(J21, r1, J11 * r2), rdet, t);
         dp = dp_new;
         t = t_new;
         ecur = exp_hd(-(m.b * (p_old + dp)));
@@ -250,14 +253,14 @@ DXM_HD void fefp_point(const FeFpArgs& a, const int64_t i0, const bool live, con
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) D[i][j] = (i == j) ? (B[i][j] - t0) : B[i][j];
-  const double dd = ((D[0][0] * D[0][0] + D[1][1] * D[1][1]) + D[2][2] * D[2][2]) +
-                    2.0 * ((D[0][1] * D[0][1] + D[0][2] * D[0][2]) + D[1][2] * D[1][2]);
+  const double dd = fma_c(2.0, dot3(D[0][1], D[0][1], D[0][2], D[0][2], D[1][2], D[1][2]),
+                          dot3(D[0][0], D[0][0], D[1][1], D[1][1], D[2][2], D[2][2]));
   const double d3 = det3(D);
   const double seq = mu * sqrt(1.5 * dd);
   const double rseq = 1.0 / seq;
 
   double ecur = exp_hd(-(b * p_old));
-  const double sy0 = (sig0 + H * p_old) + dsu * (1.0 - ecur);
+  const double sy0 = fma_c(dsu, 1.0 - ecur, fma_c(H, p_old, sig0));
   const double ftr = seq - sy0;
   const bool flag = ftr > 0.0;
 
@@ -331,13 +334,13 @@ DXM_HD void fefp_point(const FeFpArgs& a, const int64_t i0, const bool live, con
 #endif
     }
   }
-  const double alpha = flag ? (1.0 - (c * t) * dp) : 1.0;
+  const double alpha = flag ? fnma_c(c * t, dp, 1.0) : 1.0;
   const double p_new = p_old + dp;
 
   // ---- new state -----------------------------------------------------------------------------------
   double be[6];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) be[i] = flag ? (alpha * D[i][i] + t) : B[i][i];
+  for (int i = 0; i < 3; ++i) be[i] = flag ? fma_c(alpha, D[i][i], t) : B[i][i];
   be[3] = (alpha * D[0][1]) * kSqrt2;
   be[4] = (alpha * D[0][2]) * kSqrt2;
   be[5] = (alpha * D[1][2]) * kSqrt2;
@@ -346,7 +349,7 @@ DXM_HD void fefp_point(const FeFpArgs& a, const int64_t i0, const bool live, con
   double Ai[3][3], Jd, DA[3][3], P[3][3];
   inv3(A, Ai, Jd);
   const double muA = mu * alpha;
-  const double pvol = (0.5 * kappa) * (Jd * Jd - 1.0);
+  const double pvol = (0.5 * kappa) * fms_c(Jd, Jd, 1.0);
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -355,7 +358,7 @@ DXM_HD void fefp_point(const FeFpArgs& a, const int64_t i0, const bool live, con
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) P[i][j] = muA * DA[i][j] + pvol * Ai[j][i];
+    for (int j = 0; j < 3; ++j) P[i][j] = fma_c(muA, DA[i][j], pvol * Ai[j][i]);
 
   double chk = (seq + fabs(Jd)) + p_new;
 #pragma unroll
@@ -392,24 +395,24 @@ DXM_HD void fefp_point(const FeFpArgs& a, const int64_t i0, const bool live, con
   if (flag) {
     const double sq1 = (1.5 * (mu * mu)) * rseq;
     const double a2 = alpha * alpha;
-    const double dsy = H + bdsu * ecur;
-    const double g = 3.0 * (a2 * d3) - (alpha * dd) * t;
+    const double dsy = fma_c(bdsu, ecur, H);
+    const double g = fnma_c(alpha * dd, t, 3.0 * (a2 * d3));
     const double ct = c * t;
     const double cdp = c * dp;
     const double J11 = -(threemu * t) - dsy;
     const double J12 = -(threemu * dp);
     const double J21 = -(g * ct);
-    const double J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp;
-    const double rdet = 1.0 / (J11 * J22 - J12 * J21);
+    const double J22 = fnma_c(g, cdp, fnma_c(0.5 * a2, dd, 3.0 * (t * t)));
+    const double rdet = 1.0 / fms_c(J11, J22, J12 * J21);
     const double oma = (1.0 - alpha) * rseq;
-    const double b21 = (g * oma) * sq1 - a2 * t;
+    const double b21 = fms_c(g * oma, sq1, a2 * t);
     const double b22 = a2 * alpha;
-    const double p1 = -((sq1 * J22 - J12 * b21) * rdet);
-    const double t1 = -((J11 * b21 - J21 * sq1) * rdet);
+    const double p1 = -(fms_c(sq1, J22, J12 * b21) * rdet);
+    const double t1 = -(fms_c(J11, b21, J21 * sq1) * rdet);
     const double p2 = (J12 * b22) * rdet;
     const double t2 = -((J11 * b22) * rdet);
-    al1 = (oma * sq1 - ct * p1) - cdp * t1;
-    al2 = -(ct * p2) - cdp * t2;
+    al1 = fnma_c(cdp, t1, fnma_c(ct, p1, oma * sq1));
+    al2 = fnma_c(cdp, t2, -(ct * p2));
   }
 
   // ---- tangent, column (k,l) = d/dF_kl, row (i,j) = PK1_ij; w = row l of F^-1, v = B w = D w + t0 w:
@@ -418,14 +421,14 @@ DXM_HD void fefp_point(const FeFpArgs& a, const int64_t i0, const bool live, con
   const double c23dd = (2.0 / 3.0) * dd;
   const double twod3 = 2.0 * d3;
   const double c23muA = (2.0 / 3.0) * muA;
-  const double hs = muA * t0 - pvol;
+  const double hs = fms_c(muA, t0, pvol);
 #pragma unroll
   for (int l = 0; l < 3; ++l) {
     double w[3], v[3], u[3], z[3], my[3], hw[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) w[i] = Ai[l][i];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) v[i] = dot3(D[i][0], w[0], D[i][1], w[1], D[i][2], w[2]) + t0 * w[i];
+    for (int i = 0; i < 3; ++i) v[i] = fma_c(t0, w[i], dot3(D[i][0], w[0], D[i][1], w[1], D[i][2], w[2]));
     if (flag) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) u[i] = dot3(D[i][0], v[0], D[i][1], v[1], D[i][2], v[2]);
@@ -443,18 +446,18 @@ DXM_HD void fefp_point(const FeFpArgs& a, const int64_t i0, const bool live, con
     for (int k = 0; k < 3; ++k) {
       double cd0 = 0.0;
       if (flag) {
-        const double a1 = 2.0 * u[k] - c23dd * w[k];
-        const double a2p = (2.0 * z[k] - c23dd * v[k]) - twod3 * w[k];
-        cd0 = mu * (al1 * a1 + al2 * a2p);
+        const double a1 = fnma_c(c23dd, w[k], 2.0 * u[k]);
+        const double a2p = fnma_c(twod3, w[k], fnma_c(c23dd, v[k], 2.0 * z[k]));
+        cd0 = mu * fma_c(al2, a2p, al1 * a1);
       }
-      const double cD = cd0 - c23muA * w[k];
-      const double cI = kJ2 * w[k] - c23muA * v[k];
+      const double cD = fnma_c(c23muA, w[k], cd0);
+      const double cI = fnma_c(c23muA, v[k], kJ2 * w[k]);
       const int col = idx9(k, l);
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          double val = (cD * DA[i][j] + cI * Ai[j][i]) + hw[i] * Ai[j][k];
+          double val = fma_c(hw[i], Ai[j][k], fma_c(cI, Ai[j][i], cD * DA[i][j]));
           if (i == k) val = val + my[j];
           st_stream(a.ct + (int64_t)(idx9(i, j) * 9 + col) * ld + i0, val);
         }

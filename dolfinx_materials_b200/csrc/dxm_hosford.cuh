@@ -51,8 +51,8 @@ struct HosHard {
 DXM_HD void hos_hard(const HosHard& hd, double dp, double& sy, double& dsy) {
   const double p = hd.p_old + dp;
   const double e = (hd.bdsu != 0.0) ? hos_exp(-(hd.b * p)) : 1.0;
-  sy = (hd.sig0 + hd.H * p) + hd.dsu * (1.0 - e);
-  dsy = hd.H + hd.bdsu * e;
+  sy = fma_c(hd.dsu, 1.0 - e, fma_c(hd.H, p, hd.sig0));
+  dsy = fma_c(hd.bdsu, e, hd.H);
 }
 
 // (x*x)^k, k >= 1
@@ -68,7 +68,7 @@ DXM_HD double hos_ipow2(double x, int k) {
 DXM_HD double hos_arootinv(double q, int a, double inv_a) {
   double w = 1.0;
   for (int it = 0; it < 30; ++it) {
-    const double wn = w * (1.0 + (1.0 - q * hos_ipow2(w, a / 2)) * inv_a);
+    const double wn = w * fma_c(fnma_c(q, hos_ipow2(w, a / 2), 1.0), inv_a, 1.0);
     if (!(wn > w)) break;
     w = wn;
   }
@@ -105,7 +105,7 @@ DXM_HD double hos_divdiff(double x, double y, int a) {
 #pragma unroll
   for (int j = 1; j <= a - 2; ++j) {
     xp = xp * x;
-    t = y * t + xp;
+    t = fma_c(y, t, xp);
   }
   return t;
 }
@@ -120,20 +120,20 @@ DXM_HD void hos_jrot(double& app, double& aqq, double& apq, double& arp, double&
     return;
   }
   const double delta = (aqq - app) * 0.5;
-  double t = apq / (fabs(delta) + sqrt(delta * delta + apq * apq));
+  double t = apq / (fabs(delta) + sqrt(fma_c(delta, delta, apq * apq)));
   if (delta < 0.0) t = -t;
-  const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
-  app = app - t * apq;
-  aqq = aqq + t * apq;
+  const double c = 1.0 / sqrt(fma_c(t, t, 1.0)), sn = t * c;
+  app = fnma_c(t, apq, app);
+  aqq = fma_c(t, apq, aqq);
   apq = 0.0;
   const double xp = arp, xq = arq;
-  arp = c * xp - sn * xq;
-  arq = sn * xp + c * xq;
+  arp = fms_c(c, xp, sn * xq);
+  arq = fma_c(sn, xp, c * xq);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const double vp = V[k][P], vq = V[k][Q];
-    V[k][P] = c * vp - sn * vq;
-    V[k][Q] = sn * vp + c * vq;
+    V[k][P] = fms_c(c, vp, sn * vq);
+    V[k][Q] = fma_c(sn, vp, c * vq);
   }
 }
 
@@ -164,36 +164,36 @@ DXM_HD void hos_residual(const double (&x)[3], double dp, const double (&l)[3], 
   hos_eval(x, a, inv_a, o.e);
   const double c = twomu * dp;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) o.rs[k] = (x[k] - l[k]) + c * o.e.n[k];
+  for (int k = 0; k < 3; ++k) o.rs[k] = fma_c(c, o.e.n[k], x[k] - l[k]);
   double sy;
   hos_hard(hd, dp, sy, o.dsy);
   o.r4 = o.e.phi - sy;
-  o.m2 = ((o.rs[0] * o.rs[0] + o.rs[1] * o.rs[1]) + o.rs[2] * o.rs[2]) + o.r4 * o.r4;
+  o.m2 = fma_c(o.r4, o.r4, fma_c(o.rs[2], o.rs[2], fma_c(o.rs[1], o.rs[1], o.rs[0] * o.rs[0])));
 }
 
 // A = I + c k1 (M/2 - n n^T): adjugate (6 unique cofactors) and 1/det
 DXM_HD void hos_system(const HosEval& r, double c, double k1, double (&Cf)[6], double& idet) {
   const double ck = c * k1;
-  const double A00 = 1.0 + ck * (0.5 * (r.h[0] + r.h[2]) - r.n[0] * r.n[0]);
-  const double A11 = 1.0 + ck * (0.5 * (r.h[0] + r.h[1]) - r.n[1] * r.n[1]);
-  const double A22 = 1.0 + ck * (0.5 * (r.h[1] + r.h[2]) - r.n[2] * r.n[2]);
-  const double A01 = ck * (-0.5 * r.h[0] - r.n[0] * r.n[1]);
-  const double A02 = ck * (-0.5 * r.h[2] - r.n[0] * r.n[2]);
-  const double A12 = ck * (-0.5 * r.h[1] - r.n[1] * r.n[2]);
-  Cf[0] = A11 * A22 - A12 * A12;
-  Cf[1] = A02 * A12 - A01 * A22;
-  Cf[2] = A01 * A12 - A02 * A11;
-  Cf[3] = A00 * A22 - A02 * A02;
-  Cf[4] = A01 * A02 - A00 * A12;
-  Cf[5] = A00 * A11 - A01 * A01;
-  const double det = (A00 * Cf[0] + A01 * Cf[1]) + A02 * Cf[2];
+  const double A00 = fma_c(ck, fnma_c(r.n[0], r.n[0], 0.5 * (r.h[0] + r.h[2])), 1.0);
+  const double A11 = fma_c(ck, fnma_c(r.n[1], r.n[1], 0.5 * (r.h[0] + r.h[1])), 1.0);
+  const double A22 = fma_c(ck, fnma_c(r.n[2], r.n[2], 0.5 * (r.h[1] + r.h[2])), 1.0);
+  const double A01 = ck * fnma_c(r.n[0], r.n[1], -0.5 * r.h[0]);
+  const double A02 = ck * fnma_c(r.n[0], r.n[2], -0.5 * r.h[2]);
+  const double A12 = ck * fnma_c(r.n[1], r.n[2], -0.5 * r.h[1]);
+  Cf[0] = fms_c(A11, A22, A12 * A12);
+  Cf[1] = fms_c(A02, A12, A01 * A22);
+  Cf[2] = fms_c(A01, A12, A02 * A11);
+  Cf[3] = fms_c(A00, A22, A02 * A02);
+  Cf[4] = fms_c(A01, A02, A00 * A12);
+  Cf[5] = fms_c(A00, A11, A01 * A01);
+  const double det = fma_c(A02, Cf[2], fma_c(A01, Cf[1], A00 * Cf[0]));
   idet = 1.0 / det;
 }
 
 DXM_HD void hos_apply(const double (&Cf)[6], double idet, const double (&v)[3], double (&o)[3]) {
-  o[0] = ((Cf[0] * v[0] + Cf[1] * v[1]) + Cf[2] * v[2]) * idet;
-  o[1] = ((Cf[1] * v[0] + Cf[3] * v[1]) + Cf[4] * v[2]) * idet;
-  o[2] = ((Cf[2] * v[0] + Cf[4] * v[1]) + Cf[5] * v[2]) * idet;
+  o[0] = fma_c(Cf[2], v[2], fma_c(Cf[1], v[1], Cf[0] * v[0])) * idet;
+  o[1] = fma_c(Cf[4], v[2], fma_c(Cf[3], v[1], Cf[1] * v[0])) * idet;
+  o[2] = fma_c(Cf[5], v[2], fma_c(Cf[4], v[1], Cf[2] * v[0])) * idet;
 }
 
 // unit Mandel vector of sym(e_I e_J) (I != J) or of e_I e_I, from the eigenvector matrix
@@ -210,9 +210,9 @@ DXM_HD void hos_mandel_pair(const double (&V)[3][3], double (&m)[6]) {
     m[0] = kHosSqrt2 * (V[0][I] * V[0][J]);
     m[1] = kHosSqrt2 * (V[1][I] * V[1][J]);
     m[2] = kHosSqrt2 * (V[2][I] * V[2][J]);
-    m[3] = V[0][I] * V[1][J] + V[1][I] * V[0][J];
-    m[4] = V[0][I] * V[2][J] + V[2][I] * V[0][J];
-    m[5] = V[1][I] * V[2][J] + V[2][I] * V[1][J];
+    m[3] = fma_c(V[0][I], V[1][J], V[1][I] * V[0][J]);
+    m[4] = fma_c(V[0][I], V[2][J], V[2][I] * V[0][J]);
+    m[5] = fma_c(V[1][I], V[2][J], V[2][I] * V[1][J]);
   }
 }
 
@@ -239,17 +239,17 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
   const double tr = (de[0] + de[1]) + de[2];
   const double ltr = lam * tr;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) st[i] = s_old[i] + (ltr + twomu * de[i]);
+  for (int i = 0; i < 3; ++i) st[i] = s_old[i] + fma_c(twomu, de[i], ltr);
 #pragma unroll
-  for (int i = 3; i < 6; ++i) st[i] = s_old[i] + twomu * de[i];
+  for (int i = 3; i < 6; ++i) st[i] = fma_c(twomu, de[i], s_old[i]);
   const double pm = ((st[0] + st[1]) + st[2]) / 3.0;
 #pragma unroll
   for (int i = 0; i < 3; ++i) s[i] = st[i] - pm;
 #pragma unroll
   for (int i = 3; i < 6; ++i) s[i] = st[i];
-  double ss = s[0] * s[0] + s[1] * s[1];
+  double ss = s[0] * s[0];
 #pragma unroll
-  for (int i = 2; i < 6; ++i) ss = ss + s[i] * s[i];
+  for (int i = 1; i < 6; ++i) ss = fma_c(s[i], s[i], ss);
   const double seq = sqrt(1.5 * ss);
   const double dsu = VOCE ? dsu_rt : 0.0, b = VOCE ? b_rt : 0.0;
   const HosHard hd{sig0, H, dsu, b, VOCE ? b * dsu : 0.0, p_old};
@@ -299,8 +299,8 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
           t = 0.5 * t;
           ++ls;
 #pragma unroll
-          for (int k = 0; k < 3; ++k) xe[k] = x[k] + t * dx[k];
-          dpe = dp + t * ddp;
+          for (int k = 0; k < 3; ++k) xe[k] = fma_c(t, dx[k], x[k]);
+          dpe = fma_c(t, ddp, dp);
           continue;
         }
         ++n_iter;
@@ -324,17 +324,17 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
       hos_system(cur.e, twomu * dp, am1 * cur.e.iphi, Cf, idet);
       hos_apply(Cf, idet, cur.rs, y);
       hos_apply(Cf, idet, cur.e.n, z);
-      const double ny = (cur.e.n[0] * y[0] + cur.e.n[1] * y[1]) + cur.e.n[2] * y[2];
-      const double nz = (cur.e.n[0] * z[0] + cur.e.n[1] * z[1]) + cur.e.n[2] * z[2];
-      ddp = (cur.r4 - ny) / (twomu * nz + cur.dsy);
+      const double ny = fma_c(cur.e.n[2], y[2], fma_c(cur.e.n[1], y[1], cur.e.n[0] * y[0]));
+      const double nz = fma_c(cur.e.n[2], z[2], fma_c(cur.e.n[1], z[1], cur.e.n[0] * z[0]));
+      ddp = (cur.r4 - ny) / fma_c(twomu, nz, cur.dsy);
       const double tz = twomu * ddp;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) dx[k] = -(y[k] + tz * z[k]);
+      for (int k = 0; k < 3; ++k) dx[k] = -fma_c(tz, z[k], y[k]);
       t = 1.0;
       ls = 0;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) xe[k] = x[k] + t * dx[k];
-      dpe = dp + t * ddp;
+      for (int k = 0; k < 3; ++k) xe[k] = fma_c(t, dx[k], x[k]);
+      dpe = fma_c(t, ddp, dp);
     }
   }
 
@@ -344,7 +344,7 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
     hos_mandel_pair<1, 1>(V, mN1);
     hos_mandel_pair<2, 2>(V, mN2);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) nrm[i] = (cur.e.n[0] * mN0[i] + cur.e.n[1] * mN1[i]) + cur.e.n[2] * mN2[i];
+    for (int i = 0; i < 6; ++i) nrm[i] = fma_c(cur.e.n[2], mN2[i], fma_c(cur.e.n[1], mN1[i], cur.e.n[0] * mN0[i]));
   } else {
 #pragma unroll
     for (int i = 0; i < 6; ++i) nrm[i] = 0.0;
@@ -353,7 +353,7 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     const double depsp = dp * nrm[i];
-    sig[i] = st[i] - twomu * depsp;
+    sig[i] = fnma_c(twomu, depsp, st[i]);
     epsp[i] = ep_old[i] + depsp;
   }
   p_new = p_old + dp;
@@ -370,19 +370,19 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
     const double c = twomu * dp, iphi = cur.e.iphi;
     hos_system(cur.e, c, ((double)a - 1.0) * cur.e.iphi, Cf, idet);
     hos_apply(Cf, idet, cur.e.n, z);
-    const double nz = (cur.e.n[0] * z[0] + cur.e.n[1] * z[1]) + cur.e.n[2] * z[2];
-    const double w = (twomu * twomu) / (twomu * nz + cur.dsy);
+    const double nz = fma_c(cur.e.n[2], z[2], fma_c(cur.e.n[1], z[1], cur.e.n[0] * z[0]));
+    const double w = (twomu * twomu) / fma_c(twomu, nz, cur.dsy);
     const double ti = twomu * idet;
-    const double An00 = (ti * Cf[0] + lam) - w * (z[0] * z[0]);
-    const double An01 = (ti * Cf[1] + lam) - w * (z[0] * z[1]);
-    const double An02 = (ti * Cf[2] + lam) - w * (z[0] * z[2]);
-    const double An11 = (ti * Cf[3] + lam) - w * (z[1] * z[1]);
-    const double An12 = (ti * Cf[4] + lam) - w * (z[1] * z[2]);
-    const double An22 = (ti * Cf[5] + lam) - w * (z[2] * z[2]);
-    const double th01 = (cur.e.h[0] + 0.5 * hos_divdiff(-cur.e.u[2], cur.e.u[1], a)) * iphi;
-    const double th12 = (cur.e.h[1] + 0.5 * hos_divdiff(-cur.e.u[0], cur.e.u[2], a)) * iphi;
-    const double th20 = (cur.e.h[2] + 0.5 * hos_divdiff(-cur.e.u[1], cur.e.u[0], a)) * iphi;
-    const double G0 = twomu / (1.0 + c * th01), G1 = twomu / (1.0 + c * th12), G2 = twomu / (1.0 + c * th20);
+    const double An00 = fnma_c(w, z[0] * z[0], fma_c(ti, Cf[0], lam));
+    const double An01 = fnma_c(w, z[0] * z[1], fma_c(ti, Cf[1], lam));
+    const double An02 = fnma_c(w, z[0] * z[2], fma_c(ti, Cf[2], lam));
+    const double An11 = fnma_c(w, z[1] * z[1], fma_c(ti, Cf[3], lam));
+    const double An12 = fnma_c(w, z[1] * z[2], fma_c(ti, Cf[4], lam));
+    const double An22 = fnma_c(w, z[2] * z[2], fma_c(ti, Cf[5], lam));
+    const double th01 = fma_c(0.5, hos_divdiff(-cur.e.u[2], cur.e.u[1], a), cur.e.h[0]) * iphi;
+    const double th12 = fma_c(0.5, hos_divdiff(-cur.e.u[0], cur.e.u[2], a), cur.e.h[1]) * iphi;
+    const double th20 = fma_c(0.5, hos_divdiff(-cur.e.u[1], cur.e.u[0], a), cur.e.h[2]) * iphi;
+    const double G0 = twomu / fma_c(c, th01, 1.0), G1 = twomu / fma_c(c, th12, 1.0), G2 = twomu / fma_c(c, th20, 1.0);
     double mS0[6], mS1[6], mS2[6];
     hos_mandel_pair<0, 1>(V, mS0);
     hos_mandel_pair<1, 2>(V, mS1);
@@ -390,16 +390,16 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
     double wN0[6], wN1[6], wN2[6];
 #pragma unroll
     for (int cc = 0; cc < 6; ++cc) {
-      wN0[cc] = (An00 * mN0[cc] + An01 * mN1[cc]) + An02 * mN2[cc];
-      wN1[cc] = (An01 * mN0[cc] + An11 * mN1[cc]) + An12 * mN2[cc];
-      wN2[cc] = (An02 * mN0[cc] + An12 * mN1[cc]) + An22 * mN2[cc];
+      wN0[cc] = fma_c(An02, mN2[cc], fma_c(An01, mN1[cc], An00 * mN0[cc]));
+      wN1[cc] = fma_c(An12, mN2[cc], fma_c(An11, mN1[cc], An01 * mN0[cc]));
+      wN2[cc] = fma_c(An22, mN2[cc], fma_c(An12, mN1[cc], An02 * mN0[cc]));
     }
 #pragma unroll
     for (int j = 0; j < 6; ++j)
 #pragma unroll
       for (int i = j; i < 6; ++i) {
-        const double vn = (mN0[j] * wN0[i] + mN1[j] * wN1[i]) + mN2[j] * wN2[i];
-        const double vs = (G0 * (mS0[j] * mS0[i]) + G1 * (mS1[j] * mS1[i])) + G2 * (mS2[j] * mS2[i]);
+        const double vn = fma_c(mN2[j], wN2[i], fma_c(mN1[j], wN1[i], mN0[j] * wN0[i]));
+        const double vs = fma_c(G2, mS2[j] * mS2[i], fma_c(G1, mS1[j] * mS1[i], G0 * (mS0[j] * mS0[i])));
         ct21[sym6_packed(j * 6 + i)] = vn + vs;
       }
   }

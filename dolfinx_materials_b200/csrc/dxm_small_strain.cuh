@@ -92,8 +92,8 @@ DXM_HD void voce_newton(const PointProps& m, const double threemu, const double 
   for (int it = 0; vote ? DXM_ANY_SYNC(mask, active) : active; ++it) {
     if (active) {
       const double p = p_old + dp;
-      const double sy = (m.sig0 + m.H * p) + m.dsu * (1.0 - ecur);
-      const double r = (seq - threemu * dp) - sy;
+      const double sy = fma_c(m.dsu, 1.0 - ecur, fma_c(m.H, p, m.sig0));
+      const double r = fnma_c(threemu, dp, seq) - sy;
       if (fabs(r) <= tol) {
         resid = fabs(r);
         active = false;
@@ -102,7 +102,7 @@ DXM_HD void voce_newton(const PointProps& m, const double threemu, const double 
         fail = true;
         active = false;
       } else {
-        const double dsy = m.H + bdsu * ecur;
+        const double dsy = fma_c(bdsu, ecur, m.H);
         dp = dp + r / (threemu + dsy);
         ecur = exp_hd(-(m.b * (p_old + dp)));
         ++n_iter;
@@ -131,17 +131,17 @@ DXM_HD void j2_point(const PointProps& m, const double (&eps)[6],
   const double tr = (de[0] + de[1]) + de[2];
   const double ltr = m.lam * tr;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) st[i] = s_old[i] + (ltr + twomu * de[i]);
+  for (int i = 0; i < 3; ++i) st[i] = s_old[i] + fma_c(twomu, de[i], ltr);
 #pragma unroll
-  for (int i = 3; i < 6; ++i) st[i] = s_old[i] + twomu * de[i];
+  for (int i = 3; i < 6; ++i) st[i] = fma_c(twomu, de[i], s_old[i]);
   const double pm = ((st[0] + st[1]) + st[2]) / 3.0;
 #pragma unroll
   for (int i = 0; i < 3; ++i) s[i] = st[i] - pm;
 #pragma unroll
   for (int i = 3; i < 6; ++i) s[i] = st[i];
-  double ss = s[0] * s[0] + s[1] * s[1];
+  double ss = s[0] * s[0];
 #pragma unroll
-  for (int i = 2; i < 6; ++i) ss = ss + s[i] * s[i];
+  for (int i = 1; i < 6; ++i) ss = fma_c(s[i], s[i], ss);
   const double seq = sqrt(1.5 * ss);
 
   double dp = 0.0;
@@ -159,12 +159,12 @@ DXM_HD void j2_point(const PointProps& m, const double (&eps)[6],
     if (HARD == HARD_TABLE) {
       for (int k = 0; k + 1 < m.ntab; ++k)
         if (p_old >= m.tp[k + 1]) seg = k + 1;
-      sy0 = m.ts[seg] + m.tH[seg] * (p_old - m.tp[seg]);
+      sy0 = fma_c(m.tH[seg], p_old - m.tp[seg], m.ts[seg]);
     } else if (HARD == HARD_GENERAL) {
       ecur = exp_hd(-(m.b * p_old));
-      sy0 = (m.sig0 + m.H * p_old) + m.dsu * (1.0 - ecur);
+      sy0 = fma_c(m.dsu, 1.0 - ecur, fma_c(m.H, p_old, m.sig0));
     } else {
-      sy0 = m.sig0 + m.H * p_old;
+      sy0 = fma_c(m.H, p_old, m.sig0);
     }
     const double f = seq - sy0;
     flag = f > 0.0;
@@ -175,7 +175,7 @@ DXM_HD void j2_point(const PointProps& m, const double (&eps)[6],
       // solution leaves the segment (n_iter counts crossings)
       if (live && flag) {
         for (;;) {
-          dp = (seq - (m.ts[seg] + m.tH[seg] * (p_old - m.tp[seg]))) / (threemu + m.tH[seg]);
+          dp = (seq - fma_c(m.tH[seg], p_old - m.tp[seg], m.ts[seg])) / (threemu + m.tH[seg]);
           if (seg + 1 < m.ntab && p_old + dp > m.tp[seg + 1]) {
             ++seg;
             ++n_iter;
@@ -240,7 +240,7 @@ DXM_HD void j2_point(const PointProps& m, const double (&eps)[6],
 #endif
       }
     }
-    if (HARD == HARD_GENERAL) Hp = m.H + bdsu * ecur;
+    if (HARD == HARD_GENERAL) Hp = fma_c(bdsu, ecur, m.H);
   }
 
   double q = 0.0;
@@ -257,7 +257,7 @@ DXM_HD void j2_point(const PointProps& m, const double (&eps)[6],
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     const double depsp = dp * nrm[i];
-    sig[i] = st[i] - twomu * depsp;
+    sig[i] = fnma_c(twomu, depsp, st[i]);
     epsp[i] = ep_old[i] + depsp;
   }
   p_new = p_old + dp;
@@ -268,8 +268,8 @@ DXM_HD void j2_point(const PointProps& m, const double (&eps)[6],
     const double cste = 1.0 / (threemu + Hp);
     gamma = fourmu2 * (cste - q);
   }
-  A = m.lam + 0.5 * beta;
-  B = twomu - 1.5 * beta;
+  A = fma_c(0.5, beta, m.lam);
+  B = fnma_c(1.5, beta, twomu);
 
   double chk = (seq + fabs(pm)) + p_new;
 #pragma unroll
@@ -299,7 +299,7 @@ DXM_HD double j2_tangent_entry(const int i, const int j, const double A, const d
     base = A;
   else
     base = 0.0;
-  return base - gamma * (ni * nj);
+  return fnma_c(gamma, ni * nj, base);
 }
 
 template <int HARD, bool PERPOINT, int PPT, bool DIAG, int MINB, bool COMPACT = false>

@@ -14,34 +14,9 @@
  *   -ffp-contract=off is essential: every operation is individually rounded, in the order written.
  * Arrays are C-contiguous (n, dim) float64 exactly as the reference's QuadratureMap hands them over.
  */
-#include <math.h>
-#include <stdint.h>
+#include "dxm_canon.h"
 
 #define NEWTON_CAP_DEFAULT 25
-
-static double exp_c(double x) {
-  const double LOG2E = 1.4426950408889634, LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
-  if (x != x) return x;
-  if (x < -700.0) return 0.0;
-  if (x > 700.0) return INFINITY;
-  const double k = rint(x * LOG2E);
-  const double r = (x - k * LN2_HI) - k * LN2_LO;
-  double y = 1.0 / 6227020800.0;
-  y = y * r + 1.0 / 479001600.0;
-  y = y * r + 1.0 / 39916800.0;
-  y = y * r + 1.0 / 3628800.0;
-  y = y * r + 1.0 / 362880.0;
-  y = y * r + 1.0 / 40320.0;
-  y = y * r + 1.0 / 5040.0;
-  y = y * r + 1.0 / 720.0;
-  y = y * r + 1.0 / 120.0;
-  y = y * r + 1.0 / 24.0;
-  y = y * r + 1.0 / 6.0;
-  y = y * r + 0.5;
-  y = y * r + 1.0;
-  y = y * r + 1.0;
-  return ldexp(y, (int)k);
-}
 
 static double rcbrt_c(double x) {
   if (!(x > 0.0)) return NAN;
@@ -50,8 +25,8 @@ static double rcbrt_c(double x) {
   const int q = (e >= 0) ? (e / 3) : -((-e + 2) / 3);
   const int r = e - 3 * q;
   const double xr = ldexp(m, r);
-  double y = 1.2 - 0.15 * xr;
-  for (int i = 0; i < 6; ++i) y = (y * (4.0 - xr * ((y * y) * y))) * (1.0 / 3.0);
+  double y = FNMA(0.15, xr, 1.2);
+  for (int i = 0; i < 6; ++i) y = (y * FNMA(xr, (y * y) * y, 4.0)) * (1.0 / 3.0);
   return ldexp(y, -q);
 }
 
@@ -88,16 +63,16 @@ void dxo_small_strain(int64_t n, const double* eps, const double* e_old, const d
     for (int i = 0; i < 6; ++i) de[i] = eps[pt * 6 + i] - e_old[pt * 6 + i];
     const double tr = (de[0] + de[1]) + de[2];
     const double ltr = lam * tr;
-    for (int i = 0; i < 3; ++i) st[i] = s_old[pt * 6 + i] + (ltr + twomu * de[i]);
-    for (int i = 3; i < 6; ++i) st[i] = s_old[pt * 6 + i] + twomu * de[i];
+    for (int i = 0; i < 3; ++i) st[i] = s_old[pt * 6 + i] + FMA(twomu, de[i], ltr);
+    for (int i = 3; i < 6; ++i) st[i] = FMA(twomu, de[i], s_old[pt * 6 + i]);
     const double pm = ((st[0] + st[1]) + st[2]) / 3.0;
     for (int i = 0; i < 3; ++i) s[i] = st[i] - pm;
     for (int i = 3; i < 6; ++i) s[i] = st[i];
-    double ss = s[0] * s[0] + s[1] * s[1];
-    for (int i = 2; i < 6; ++i) ss = ss + s[i] * s[i];
+    double ss = s[0] * s[0];
+    for (int i = 1; i < 6; ++i) ss = FMA(s[i], s[i], ss);
     const double seq = sqrt(1.5 * ss);
     double ecur = exp_c(-(m.b * p_old));
-    const double sy0 = (m.sig0 + m.H * p_old) + dsu * (1.0 - ecur);
+    const double sy0 = FMA(dsu, 1.0 - ecur, FMA(m.H, p_old, m.sig0));
     const double f = seq - sy0;
     const int flag = f > 0.0;
     double dp = 0.0, resid = 0.0;
@@ -109,18 +84,18 @@ void dxo_small_strain(int64_t n, const double* eps, const double* e_old, const d
         const double tol = rtol * seq;
         for (int it = 0;; ++it) {
           const double p = p_old + dp;
-          const double sy = (m.sig0 + m.H * p) + dsu * (1.0 - ecur);
-          const double r = (seq - threemu * dp) - sy;
+          const double sy = FMA(dsu, 1.0 - ecur, FMA(m.H, p, m.sig0));
+          const double r = FNMA(threemu, dp, seq) - sy;
           if (fabs(r) <= tol) { resid = fabs(r); break; }
           if (it == newton_cap) { resid = fabs(r); fail = 1; break; }
-          const double dsy = m.H + bdsu * ecur;
+          const double dsy = FMA(bdsu, ecur, m.H);
           dp = dp + r / (threemu + dsy);
           ecur = exp_c(-(m.b * (p_old + dp)));
           ++n_iter;
         }
       }
     }
-    const double Hp = m.H + bdsu * ecur;
+    const double Hp = FMA(bdsu, ecur, m.H);
     double nrm[6], q = 0.0, gamma = 0.0;
     if (flag) {
       for (int i = 0; i < 6; ++i) nrm[i] = (1.5 * s[i]) / seq;
@@ -132,7 +107,7 @@ void dxo_small_strain(int64_t n, const double* eps, const double* e_old, const d
     double epsp[6];
     for (int i = 0; i < 6; ++i) {
       const double depsp = dp * nrm[i];
-      sig_o[pt * 6 + i] = st[i] - twomu * depsp;
+      sig_o[pt * 6 + i] = FNMA(twomu, depsp, st[i]);
       epsp[i] = ep_old[pt * 6 + i] + depsp;
       epsp_o[pt * 6 + i] = epsp[i];
     }
@@ -144,11 +119,11 @@ void dxo_small_strain(int64_t n, const double* eps, const double* e_old, const d
       const double cste = 1.0 / (threemu + Hp);
       gamma = fourmu2 * (cste - q);
     }
-    const double A = lam + 0.5 * beta, B = twomu - 1.5 * beta, AB = A + B;
+    const double A = FMA(0.5, beta, lam), B = FNMA(1.5, beta, twomu), AB = A + B;
     for (int j = 0; j < 6; ++j)
       for (int i = 0; i < 6; ++i) {
         const double base = (i == j) ? ((i < 3) ? AB : B) : ((i < 3 && j < 3) ? A : 0.0);
-        ct_o[pt * 36 + j * 6 + i] = base - gamma * (nrm[i] * nrm[j]);
+        ct_o[pt * 36 + j * 6 + i] = FNMA(gamma, nrm[i] * nrm[j], base);
       }
     double chk = (seq + fabs(pm)) + p_new;
     for (int i = 0; i < 6; ++i) chk = chk + fabs(epsp[i]);
@@ -163,27 +138,25 @@ void dxo_small_strain(int64_t n, const double* eps, const double* e_old, const d
 /* ---- finite strain FeFp -- order of operations == oracle/fefp.py ------------------------------------ */
 static const int IDX9[3][3] = {{0, 3, 5}, {4, 1, 7}, {6, 8, 2}};
 
-static double dot3(double a0, double b0, double a1, double b1, double a2, double b2) { return (a0 * b0 + a1 * b1) + a2 * b2; }
-
 static double det3(double A[3][3]) {
-  const double t0 = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]);
-  const double t1 = A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]);
-  const double t2 = A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
-  return (t0 - t1) + t2;
+  const double m0 = FMS(A[1][1], A[2][2], A[1][2] * A[2][1]);
+  const double m1 = FMS(A[1][0], A[2][2], A[1][2] * A[2][0]);
+  const double m2 = FMS(A[1][0], A[2][1], A[1][1] * A[2][0]);
+  return FMA(A[0][2], m2, FNMA(A[0][1], m1, A[0][0] * m0));
 }
 
 static double inv3(double A[3][3], double Ai[3][3]) {
   double c[3][3];
-  c[0][0] = A[1][1] * A[2][2] - A[1][2] * A[2][1];
-  c[0][1] = A[0][2] * A[2][1] - A[0][1] * A[2][2];
-  c[0][2] = A[0][1] * A[1][2] - A[0][2] * A[1][1];
-  c[1][0] = A[1][2] * A[2][0] - A[1][0] * A[2][2];
-  c[1][1] = A[0][0] * A[2][2] - A[0][2] * A[2][0];
-  c[1][2] = A[0][2] * A[1][0] - A[0][0] * A[1][2];
-  c[2][0] = A[1][0] * A[2][1] - A[1][1] * A[2][0];
-  c[2][1] = A[0][1] * A[2][0] - A[0][0] * A[2][1];
-  c[2][2] = A[0][0] * A[1][1] - A[0][1] * A[1][0];
-  const double det = (A[0][0] * c[0][0] + A[0][1] * c[1][0]) + A[0][2] * c[2][0];
+  c[0][0] = FMS(A[1][1], A[2][2], A[1][2] * A[2][1]);
+  c[0][1] = FMS(A[0][2], A[2][1], A[0][1] * A[2][2]);
+  c[0][2] = FMS(A[0][1], A[1][2], A[0][2] * A[1][1]);
+  c[1][0] = FMS(A[1][2], A[2][0], A[1][0] * A[2][2]);
+  c[1][1] = FMS(A[0][0], A[2][2], A[0][2] * A[2][0]);
+  c[1][2] = FMS(A[0][2], A[1][0], A[0][0] * A[1][2]);
+  c[2][0] = FMS(A[1][0], A[2][1], A[1][1] * A[2][0]);
+  c[2][1] = FMS(A[0][1], A[2][0], A[0][0] * A[2][1]);
+  c[2][2] = FMS(A[0][0], A[1][1], A[0][1] * A[1][0]);
+  const double det = FMA(A[0][2], c[2][0], FMA(A[0][1], c[1][0], A[0][0] * c[0][0]));
   const double rdet = 1.0 / det;
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) Ai[i][j] = c[i][j] * rdet;
@@ -231,13 +204,13 @@ void dxo_fefp(int64_t n, const double* F, const double* F_old, const double* p_o
     const double t0 = ((B[0][0] + B[1][1]) + B[2][2]) * THIRD;
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) D[i][j] = (i == j) ? (B[i][j] - t0) : B[i][j];
-    const double dd = ((D[0][0] * D[0][0] + D[1][1] * D[1][1]) + D[2][2] * D[2][2]) +
-                      2.0 * ((D[0][1] * D[0][1] + D[0][2] * D[0][2]) + D[1][2] * D[1][2]);
+    const double dd = FMA(2.0, dot3(D[0][1], D[0][1], D[0][2], D[0][2], D[1][2], D[1][2]),
+                          dot3(D[0][0], D[0][0], D[1][1], D[1][1], D[2][2], D[2][2]));
     const double d3 = det3(D);
     const double seq = mu * sqrt(1.5 * dd);
     const double rseq = 1.0 / seq;
     double ecur = exp_c(-(m.b * p_old));
-    const double sy0 = (m.sig0 + m.H * p_old) + dsu * (1.0 - ecur);
+    const double sy0 = FMA(dsu, 1.0 - ecur, FMA(m.H, p_old, m.sig0));
     const int flag = (seq - sy0) > 0.0;
     const double c = threemu * rseq;
     double dp = 0.0, t = t0, resid = 0.0;
@@ -245,72 +218,76 @@ void dxo_fefp(int64_t n, const double* F, const double* F_old, const double* p_o
     if (flag) {
       const double tol1 = rtol * seq;
       for (int it = 0;; ++it) {
-        const double alpha = 1.0 - (c * t) * dp;
+        const double ct = c * t;
+        const double tmt = threemu * t;
+        const double alpha = FNMA(ct, dp, 1.0);
         const double p = p_old + dp;
-        const double sy = (m.sig0 + m.H * p) + dsu * (1.0 - ecur);
-        const double r1 = (seq - (threemu * t) * dp) - sy;
+        const double sy = FMA(dsu, 1.0 - ecur, FMA(m.H, p, m.sig0));
+        const double r1 = FNMA(tmt, dp, seq) - sy;
         const double a2 = alpha * alpha;
-        const double r2 = ((t * t) * t - (0.5 * a2) * (dd * t)) + ((a2 * alpha) * d3 - 1.0);
+        const double ha2 = 0.5 * a2;
+        const double tt = t * t;
+        const double r2 = FNMA(ha2, dd * t, tt * t) + FMS(a2 * alpha, d3, 1.0);
         if (fabs(r1) <= tol1 && fabs(r2) <= rtol) { resid = fabs(r1); break; }
         if (it == newton_cap) { resid = fabs(r1); fail = 1; break; }
-        const double dsy = m.H + bdsu * ecur;
-        const double g = 3.0 * (a2 * d3) - (alpha * dd) * t;
-        const double J11 = -(threemu * t) - dsy, J12 = -(threemu * dp);
-        const double ct = c * t, cdp = c * dp;
+        const double dsy = FMA(bdsu, ecur, m.H);
+        const double g = FNMA(alpha * dd, t, 3.0 * (a2 * d3));
+        const double J11 = -tmt - dsy, J12 = -(threemu * dp);
+        const double cdp = c * dp;
         const double J21 = -(g * ct);
-        const double J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp;
-        const double rdet = 1.0 / (J11 * J22 - J12 * J21);
-        const double dp_new = dp + (J12 * r2 - r1 * J22) * rdet;
-        const double t_new = t + (J21 * r1 - J11 * r2) * rdet;
+        const double J22 = FNMA(g, cdp, FNMA(ha2, dd, 3.0 * tt));
+        const double rdet = 1.0 / FMS(J11, J22, J12 * J21);
+        const double dp_new = FMA(FMS(J12, r2, r1 * J22), rdet, dp);
+        const double t_new = FMA(FMS(J21, r1, J11 * r2), rdet, t);
         dp = dp_new;
         t = t_new;
         ecur = exp_c(-(m.b * (p_old + dp)));
         ++n_iter;
       }
     }
-    const double alpha = flag ? (1.0 - (c * t) * dp) : 1.0;
+    const double alpha = flag ? FNMA(c * t, dp, 1.0) : 1.0;
     const double p_new = p_old + dp;
     double be[6];
-    for (int i = 0; i < 3; ++i) be[i] = flag ? (alpha * D[i][i] + t) : B[i][i];
+    for (int i = 0; i < 3; ++i) be[i] = flag ? FMA(alpha, D[i][i], t) : B[i][i];
     be[3] = (alpha * D[0][1]) * SQRT2;
     be[4] = (alpha * D[0][2]) * SQRT2;
     be[5] = (alpha * D[1][2]) * SQRT2;
     double Ai[3][3], DA[3][3], P[3][3];
     const double Jd = inv3(A, Ai);
     const double muA = mu * alpha;
-    const double pvol = (0.5 * kappa) * (Jd * Jd - 1.0);
+    const double pvol = (0.5 * kappa) * FMS(Jd, Jd, 1.0);
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) DA[i][j] = dot3(D[i][0], Ai[j][0], D[i][1], Ai[j][1], D[i][2], Ai[j][2]);
     for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) P[i][j] = muA * DA[i][j] + pvol * Ai[j][i];
+      for (int j = 0; j < 3; ++j) P[i][j] = FMA(muA, DA[i][j], pvol * Ai[j][i]);
     double al1 = 0.0, al2 = 0.0;
     if (flag) {
       const double sq1 = (1.5 * (mu * mu)) * rseq;
       const double a2 = alpha * alpha;
-      const double dsy = m.H + bdsu * ecur;
-      const double g = 3.0 * (a2 * d3) - (alpha * dd) * t;
+      const double dsy = FMA(bdsu, ecur, m.H);
+      const double g = FNMA(alpha * dd, t, 3.0 * (a2 * d3));
       const double ct = c * t, cdp = c * dp;
       const double J11 = -(threemu * t) - dsy, J12 = -(threemu * dp);
       const double J21 = -(g * ct);
-      const double J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp;
-      const double rdet = 1.0 / (J11 * J22 - J12 * J21);
+      const double J22 = FNMA(g, cdp, FNMA(0.5 * a2, dd, 3.0 * (t * t)));
+      const double rdet = 1.0 / FMS(J11, J22, J12 * J21);
       const double oma = (1.0 - alpha) * rseq;
-      const double b21 = (g * oma) * sq1 - a2 * t;
+      const double b21 = FMS(g * oma, sq1, a2 * t);
       const double b22 = a2 * alpha;
-      const double p1 = -((sq1 * J22 - J12 * b21) * rdet);
-      const double t1 = -((J11 * b21 - J21 * sq1) * rdet);
+      const double p1 = -(FMS(sq1, J22, J12 * b21) * rdet);
+      const double t1 = -(FMS(J11, b21, J21 * sq1) * rdet);
       const double p2 = (J12 * b22) * rdet;
       const double t2 = -((J11 * b22) * rdet);
-      al1 = (oma * sq1 - ct * p1) - cdp * t1;
-      al2 = -(ct * p2) - cdp * t2;
+      al1 = FNMA(cdp, t1, FNMA(ct, p1, oma * sq1));
+      al2 = FNMA(cdp, t2, -(ct * p2));
     }
     const double kJ2 = kappa * (Jd * Jd);
     const double c23dd = (2.0 / 3.0) * dd, twod3 = 2.0 * d3, c23muA = (2.0 / 3.0) * muA;
-    const double hs = muA * t0 - pvol;
+    const double hs = FMS(muA, t0, pvol);
     for (int l = 0; l < 3; ++l) {
       double w[3], v[3], u[3], z[3], my[3], hw[3];
       for (int i = 0; i < 3; ++i) w[i] = Ai[l][i];
-      for (int i = 0; i < 3; ++i) v[i] = dot3(D[i][0], w[0], D[i][1], w[1], D[i][2], w[2]) + t0 * w[i];
+      for (int i = 0; i < 3; ++i) v[i] = FMA(t0, w[i], dot3(D[i][0], w[0], D[i][1], w[1], D[i][2], w[2]));
       for (int i = 0; i < 3; ++i) u[i] = dot3(D[i][0], v[0], D[i][1], v[1], D[i][2], v[2]);
       for (int i = 0; i < 3; ++i) z[i] = dot3(D[i][0], u[0], D[i][1], u[1], D[i][2], u[2]);
       for (int j = 0; j < 3; ++j) my[j] = muA * dot3(Ai[j][0], v[0], Ai[j][1], v[1], Ai[j][2], v[2]);
@@ -318,16 +295,16 @@ void dxo_fefp(int64_t n, const double* F, const double* F_old, const double* p_o
       for (int k = 0; k < 3; ++k) {
         double cd0 = 0.0;
         if (flag) {
-          const double a1 = 2.0 * u[k] - c23dd * w[k];
-          const double a2p = (2.0 * z[k] - c23dd * v[k]) - twod3 * w[k];
-          cd0 = mu * (al1 * a1 + al2 * a2p);
+          const double a1 = FNMA(c23dd, w[k], 2.0 * u[k]);
+          const double a2p = FNMA(twod3, w[k], FNMA(c23dd, v[k], 2.0 * z[k]));
+          cd0 = mu * FMA(al2, a2p, al1 * a1);
         }
-        const double cD = cd0 - c23muA * w[k];
-        const double cI = kJ2 * w[k] - c23muA * v[k];
+        const double cD = FNMA(c23muA, w[k], cd0);
+        const double cI = FNMA(c23muA, v[k], kJ2 * w[k]);
         const int col = IDX9[k][l];
         for (int i = 0; i < 3; ++i)
           for (int j = 0; j < 3; ++j) {
-            double val = (cD * DA[i][j] + cI * Ai[j][i]) + hw[i] * Ai[j][k];
+            double val = FMA(hw[i], Ai[j][k], FMA(cI, Ai[j][i], cD * DA[i][j]));
             if (i == k) val = val + my[j];
             ct_o[pt * 81 + IDX9[i][j] * 9 + col] = val;
           }

@@ -28,38 +28,12 @@
  *   normal block 2 mu A^-1 + lam 1 1^T - ..., and three shear moduli 2 mu / (1 + 2 mu dp theta_ij) with
  *   theta_ij = (n_i - n_j)/(s_i - s_j) written as an exact divided difference (no 0/0 at repeated eigenvalues).
  */
-#include <math.h>
-#include <stdint.h>
+#include "dxm_canon.h"
 
 #define RSQRT2 0.7071067811865476
 #define SQRT2 1.4142135623730951
 #define LS_MAX 10
 #define JACOBI_SWEEPS 8
-
-/* same canonical exp as oracle/c/dxm_oracle.c (Cody-Waite, degree-13 Horner, exact scaling) */
-static double exp_c(double x) {
-  const double LOG2E = 1.4426950408889634, LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
-  if (x != x) return x;
-  if (x < -700.0) return 0.0;
-  if (x > 700.0) return INFINITY;
-  const double k = rint(x * LOG2E);
-  const double r = (x - k * LN2_HI) - k * LN2_LO;
-  double y = 1.0 / 6227020800.0;
-  y = y * r + 1.0 / 479001600.0;
-  y = y * r + 1.0 / 39916800.0;
-  y = y * r + 1.0 / 3628800.0;
-  y = y * r + 1.0 / 362880.0;
-  y = y * r + 1.0 / 40320.0;
-  y = y * r + 1.0 / 5040.0;
-  y = y * r + 1.0 / 720.0;
-  y = y * r + 1.0 / 120.0;
-  y = y * r + 1.0 / 24.0;
-  y = y * r + 1.0 / 6.0;
-  y = y * r + 0.5;
-  y = y * r + 1.0;
-  y = y * r + 1.0;
-  return ldexp(y, (int)k);
-}
 
 /* isotropic hardening sigma_Y(p) = sig0 + H p + dsu (1 - exp(-b p)) (the law of the J2 behaviours: linear for
  * dsu = 0, Voce for H = 0) and its slope, at p = p_old + dp */
@@ -70,8 +44,8 @@ typedef struct {
 static void hard_eval(const hard_t* hd, double dp, double* sy, double* dsy) {
   const double p = hd->p_old + dp;
   const double e = (hd->bdsu != 0.0) ? exp_c(-(hd->b * p)) : 1.0;
-  *sy = (hd->sig0 + hd->H * p) + hd->dsu * (1.0 - e);
-  *dsy = hd->H + hd->bdsu * e;
+  *sy = FMA(hd->dsu, 1.0 - e, FMA(hd->H, p, hd->sig0));
+  *dsy = FMA(hd->bdsu, e, hd->H);
 }
 
 /* (x*x)^k, k >= 1, as a product chain */
@@ -87,7 +61,7 @@ static double ipow2(double x, int k) {
 static double arootinv(double q, int a, double inv_a) {
   double w = 1.0;
   for (int it = 0; it < 30; ++it) {
-    const double wn = w * (1.0 + (1.0 - q * ipow2(w, a / 2)) * inv_a);
+    const double wn = w * FMA(FNMA(q, ipow2(w, a / 2), 1.0), inv_a, 1.0);
     if (!(wn > w)) break;
     w = wn;
   }
@@ -121,7 +95,7 @@ static double divdiff(double x, double y, int a) {
   double t = 1.0, xp = 1.0;
   for (int j = 1; j <= a - 2; ++j) {
     xp = xp * x;
-    t = y * t + xp;
+    t = FMA(y, t, xp);
   }
   return t;
 }
@@ -136,19 +110,19 @@ static void jrot(double* app, double* aqq, double* apq, double* arp, double* arq
   }
   /* t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = delta / a_pq, written with one division */
   const double delta = (*aqq - *app) * 0.5;
-  double t = *apq / (fabs(delta) + sqrt(delta * delta + *apq * *apq));
+  double t = *apq / (fabs(delta) + sqrt(FMA(delta, delta, *apq * *apq)));
   if (delta < 0.0) t = -t;
-  const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
-  *app = *app - t * *apq;
-  *aqq = *aqq + t * *apq;
+  const double c = 1.0 / sqrt(FMA(t, t, 1.0)), sn = t * c;
+  *app = FNMA(t, *apq, *app);
+  *aqq = FMA(t, *apq, *aqq);
   *apq = 0.0;
   const double xp = *arp, xq = *arq;
-  *arp = c * xp - sn * xq;
-  *arq = sn * xp + c * xq;
+  *arp = FMS(c, xp, sn * xq);
+  *arq = FMA(sn, xp, c * xq);
   for (int k = 0; k < 3; ++k) {
     const double vp = Q[k][p], vq = Q[k][q];
-    Q[k][p] = c * vp - sn * vq;
-    Q[k][q] = sn * vp + c * vq;
+    Q[k][p] = FMS(c, vp, sn * vq);
+    Q[k][q] = FMA(sn, vp, c * vq);
   }
 }
 
@@ -176,36 +150,36 @@ static void hosford_residual(const double x[3], double dp, const double l[3], do
                              double inv_a, hres_t* o) {
   hosford_eval(x, a, inv_a, &o->phi, &o->iphi, o->n, o->h, o->u);
   const double c = twomu * dp;
-  for (int k = 0; k < 3; ++k) o->rs[k] = (x[k] - l[k]) + c * o->n[k];
+  for (int k = 0; k < 3; ++k) o->rs[k] = FMA(c, o->n[k], x[k] - l[k]);
   double sy;
   hard_eval(hd, dp, &sy, &o->dsy);
   o->r4 = o->phi - sy;
-  o->m2 = ((o->rs[0] * o->rs[0] + o->rs[1] * o->rs[1]) + o->rs[2] * o->rs[2]) + o->r4 * o->r4;
+  o->m2 = FMA(o->r4, o->r4, FMA(o->rs[2], o->rs[2], FMA(o->rs[1], o->rs[1], o->rs[0] * o->rs[0])));
 }
 
 /* A = I + c k1 (M/2 - n n^T) (symmetric), its adjugate C and 1/det */
 static void hosford_system(const hres_t* r, double c, double k1, double Cf[6], double* idet) {
   const double ck = c * k1;
-  const double A00 = 1.0 + ck * (0.5 * (r->h[0] + r->h[2]) - r->n[0] * r->n[0]);
-  const double A11 = 1.0 + ck * (0.5 * (r->h[0] + r->h[1]) - r->n[1] * r->n[1]);
-  const double A22 = 1.0 + ck * (0.5 * (r->h[1] + r->h[2]) - r->n[2] * r->n[2]);
-  const double A01 = ck * (-0.5 * r->h[0] - r->n[0] * r->n[1]);
-  const double A02 = ck * (-0.5 * r->h[2] - r->n[0] * r->n[2]);
-  const double A12 = ck * (-0.5 * r->h[1] - r->n[1] * r->n[2]);
-  Cf[0] = A11 * A22 - A12 * A12; /* C00 */
-  Cf[1] = A02 * A12 - A01 * A22; /* C01 */
-  Cf[2] = A01 * A12 - A02 * A11; /* C02 */
-  Cf[3] = A00 * A22 - A02 * A02; /* C11 */
-  Cf[4] = A01 * A02 - A00 * A12; /* C12 */
-  Cf[5] = A00 * A11 - A01 * A01; /* C22 */
-  const double det = (A00 * Cf[0] + A01 * Cf[1]) + A02 * Cf[2];
+  const double A00 = FMA(ck, FNMA(r->n[0], r->n[0], 0.5 * (r->h[0] + r->h[2])), 1.0);
+  const double A11 = FMA(ck, FNMA(r->n[1], r->n[1], 0.5 * (r->h[0] + r->h[1])), 1.0);
+  const double A22 = FMA(ck, FNMA(r->n[2], r->n[2], 0.5 * (r->h[1] + r->h[2])), 1.0);
+  const double A01 = ck * FNMA(r->n[0], r->n[1], -0.5 * r->h[0]);
+  const double A02 = ck * FNMA(r->n[0], r->n[2], -0.5 * r->h[2]);
+  const double A12 = ck * FNMA(r->n[1], r->n[2], -0.5 * r->h[1]);
+  Cf[0] = FMS(A11, A22, A12 * A12); /* C00 */
+  Cf[1] = FMS(A02, A12, A01 * A22); /* C01 */
+  Cf[2] = FMS(A01, A12, A02 * A11); /* C02 */
+  Cf[3] = FMS(A00, A22, A02 * A02); /* C11 */
+  Cf[4] = FMS(A01, A02, A00 * A12); /* C12 */
+  Cf[5] = FMS(A00, A11, A01 * A01); /* C22 */
+  const double det = FMA(A02, Cf[2], FMA(A01, Cf[1], A00 * Cf[0]));
   *idet = 1.0 / det;
 }
 
 static void sym3_apply(const double Cf[6], double idet, const double v[3], double o[3]) {
-  o[0] = ((Cf[0] * v[0] + Cf[1] * v[1]) + Cf[2] * v[2]) * idet;
-  o[1] = ((Cf[1] * v[0] + Cf[3] * v[1]) + Cf[4] * v[2]) * idet;
-  o[2] = ((Cf[2] * v[0] + Cf[4] * v[1]) + Cf[5] * v[2]) * idet;
+  o[0] = FMA(Cf[2], v[2], FMA(Cf[1], v[1], Cf[0] * v[0])) * idet;
+  o[1] = FMA(Cf[4], v[2], FMA(Cf[3], v[1], Cf[1] * v[0])) * idet;
+  o[2] = FMA(Cf[5], v[2], FMA(Cf[4], v[1], Cf[2] * v[0])) * idet;
 }
 
 /* props: E, nu, sig0 (R0), H, sigu, b scalars or per point (pp/per as in dxm_oracle.c); a even integer >= 2 */
@@ -228,13 +202,13 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
     for (int i = 0; i < 6; ++i) de[i] = eps[pt * 6 + i] - e_old[pt * 6 + i];
     const double tr = (de[0] + de[1]) + de[2];
     const double ltr = lam * tr;
-    for (int i = 0; i < 3; ++i) st[i] = s_old[pt * 6 + i] + (ltr + twomu * de[i]);
-    for (int i = 3; i < 6; ++i) st[i] = s_old[pt * 6 + i] + twomu * de[i];
+    for (int i = 0; i < 3; ++i) st[i] = s_old[pt * 6 + i] + FMA(twomu, de[i], ltr);
+    for (int i = 3; i < 6; ++i) st[i] = FMA(twomu, de[i], s_old[pt * 6 + i]);
     const double pm = ((st[0] + st[1]) + st[2]) / 3.0;
     for (int i = 0; i < 3; ++i) s[i] = st[i] - pm;
     for (int i = 3; i < 6; ++i) s[i] = st[i];
-    double ss = s[0] * s[0] + s[1] * s[1];
-    for (int i = 2; i < 6; ++i) ss = ss + s[i] * s[i];
+    double ss = s[0] * s[0];
+    for (int i = 1; i < 6; ++i) ss = FMA(s[i], s[i], ss);
     const double seq = sqrt(1.5 * ss);
     const hard_t hd = {sig0, H, dsu, bb, bb * dsu, p_old};
     double sy0, dsy0;
@@ -267,17 +241,17 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
           hosford_system(&cur, twomu * dp, am1 * cur.iphi, Cf, &idet);
           sym3_apply(Cf, idet, cur.rs, y);
           sym3_apply(Cf, idet, cur.n, z);
-          const double ny = (cur.n[0] * y[0] + cur.n[1] * y[1]) + cur.n[2] * y[2];
-          const double nz = (cur.n[0] * z[0] + cur.n[1] * z[1]) + cur.n[2] * z[2];
-          const double ddp = (cur.r4 - ny) / (twomu * nz + cur.dsy);
+          const double ny = dot3(cur.n[0], y[0], cur.n[1], y[1], cur.n[2], y[2]);
+          const double nz = dot3(cur.n[0], z[0], cur.n[1], z[1], cur.n[2], z[2]);
+          const double ddp = (cur.r4 - ny) / FMA(twomu, nz, cur.dsy);
           const double tz = twomu * ddp;
-          const double dx[3] = {-(y[0] + tz * z[0]), -(y[1] + tz * z[1]), -(y[2] + tz * z[2])};
+          const double dx[3] = {-FMA(tz, z[0], y[0]), -FMA(tz, z[1], y[1]), -FMA(tz, z[2], y[2])};
           double t = 1.0;
           hres_t nxt;
           double xn[3], dpn;
           for (int ls = 0;; ++ls) {
-            for (int k = 0; k < 3; ++k) xn[k] = x[k] + t * dx[k];
-            dpn = dp + t * ddp;
+            for (int k = 0; k < 3; ++k) xn[k] = FMA(t, dx[k], x[k]);
+            dpn = FMA(t, ddp, dp);
             hosford_residual(xn, dpn, l, twomu, &hd, a, inv_a, &nxt);
             if (nxt.m2 < cur.m2 || ls == LS_MAX) break;
             t = 0.5 * t;
@@ -301,7 +275,7 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
         mN[k][4] = SQRT2 * (Q[0][k] * Q[2][k]);
         mN[k][5] = SQRT2 * (Q[1][k] * Q[2][k]);
       }
-      for (int i = 0; i < 6; ++i) nrm[i] = (cur.n[0] * mN[0][i] + cur.n[1] * mN[1][i]) + cur.n[2] * mN[2][i];
+      for (int i = 0; i < 6; ++i) nrm[i] = dot3(cur.n[0], mN[0][i], cur.n[1], mN[1][i], cur.n[2], mN[2][i]);
     } else {
       for (int i = 0; i < 6; ++i) nrm[i] = 0.0;
       dp = 0.0;
@@ -309,7 +283,7 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
     double epsp[6];
     for (int i = 0; i < 6; ++i) {
       const double depsp = dp * nrm[i];
-      sig_o[pt * 6 + i] = st[i] - twomu * depsp;
+      sig_o[pt * 6 + i] = FNMA(twomu, depsp, st[i]);
       epsp[i] = ep_old[pt * 6 + i] + depsp;
       epsp_o[pt * 6 + i] = epsp[i];
     }
@@ -327,25 +301,25 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
       const double c = twomu * dp, iphi = cur.iphi;
       hosford_system(&cur, c, am1 * cur.iphi, Cf, &idet);
       sym3_apply(Cf, idet, cur.n, z);
-      const double nz = (cur.n[0] * z[0] + cur.n[1] * z[1]) + cur.n[2] * z[2];
-      const double w = (twomu * twomu) / (twomu * nz + cur.dsy); /* (2 mu z)(2 mu z)^T / (2 mu n.z + sigma_Y'(p)) */
+      const double nz = dot3(cur.n[0], z[0], cur.n[1], z[1], cur.n[2], z[2]);
+      const double w = (twomu * twomu) / FMA(twomu, nz, cur.dsy); /* (2 mu z)(2 mu z)^T / (2 mu n.z + sigma_Y'(p)) */
       const double ti = twomu * idet;
       /* normal block An (symmetric): 2 mu A^-1 + lam - w z z^T */
       double An[3][3];
-      An[0][0] = (ti * Cf[0] + lam) - w * (z[0] * z[0]);
-      An[0][1] = (ti * Cf[1] + lam) - w * (z[0] * z[1]);
-      An[0][2] = (ti * Cf[2] + lam) - w * (z[0] * z[2]);
-      An[1][1] = (ti * Cf[3] + lam) - w * (z[1] * z[1]);
-      An[1][2] = (ti * Cf[4] + lam) - w * (z[1] * z[2]);
-      An[2][2] = (ti * Cf[5] + lam) - w * (z[2] * z[2]);
+      An[0][0] = FNMA(w, z[0] * z[0], FMA(ti, Cf[0], lam));
+      An[0][1] = FNMA(w, z[0] * z[1], FMA(ti, Cf[1], lam));
+      An[0][2] = FNMA(w, z[0] * z[2], FMA(ti, Cf[2], lam));
+      An[1][1] = FNMA(w, z[1] * z[1], FMA(ti, Cf[3], lam));
+      An[1][2] = FNMA(w, z[1] * z[2], FMA(ti, Cf[4], lam));
+      An[2][2] = FNMA(w, z[2] * z[2], FMA(ti, Cf[5], lam));
       An[1][0] = An[0][1];
       An[2][0] = An[0][2];
       An[2][1] = An[1][2];
       /* shear moduli of the pairs (0,1), (1,2), (2,0): theta = (h_k + DD/2) / phi */
-      const double th01 = (cur.h[0] + 0.5 * divdiff(-cur.u[2], cur.u[1], a)) * iphi;
-      const double th12 = (cur.h[1] + 0.5 * divdiff(-cur.u[0], cur.u[2], a)) * iphi;
-      const double th20 = (cur.h[2] + 0.5 * divdiff(-cur.u[1], cur.u[0], a)) * iphi;
-      const double G[3] = {twomu / (1.0 + c * th01), twomu / (1.0 + c * th12), twomu / (1.0 + c * th20)};
+      const double th01 = FMA(0.5, divdiff(-cur.u[2], cur.u[1], a), cur.h[0]) * iphi;
+      const double th12 = FMA(0.5, divdiff(-cur.u[0], cur.u[2], a), cur.h[1]) * iphi;
+      const double th20 = FMA(0.5, divdiff(-cur.u[1], cur.u[0], a), cur.h[2]) * iphi;
+      const double G[3] = {twomu / FMA(c, th01, 1.0), twomu / FMA(c, th12, 1.0), twomu / FMA(c, th20, 1.0)};
       /* unit Mandel vectors of sym(e_i e_j), pairs in the same order */
       static const int PI[3] = {0, 1, 2}, PJ[3] = {1, 2, 0};
       double mS[3][6];
@@ -354,17 +328,17 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
         mS[p][0] = SQRT2 * (Q[0][i] * Q[0][j]);
         mS[p][1] = SQRT2 * (Q[1][i] * Q[1][j]);
         mS[p][2] = SQRT2 * (Q[2][i] * Q[2][j]);
-        mS[p][3] = Q[0][i] * Q[1][j] + Q[1][i] * Q[0][j];
-        mS[p][4] = Q[0][i] * Q[2][j] + Q[2][i] * Q[0][j];
-        mS[p][5] = Q[1][i] * Q[2][j] + Q[2][i] * Q[1][j];
+        mS[p][3] = FMA(Q[0][i], Q[1][j], Q[1][i] * Q[0][j]);
+        mS[p][4] = FMA(Q[0][i], Q[2][j], Q[2][i] * Q[0][j]);
+        mS[p][5] = FMA(Q[1][i], Q[2][j], Q[2][i] * Q[1][j]);
       }
       double wN[3][6]; /* wN_i = sum_j An_ij mN_j */
       for (int i = 0; i < 3; ++i)
-        for (int cc = 0; cc < 6; ++cc) wN[i][cc] = (An[i][0] * mN[0][cc] + An[i][1] * mN[1][cc]) + An[i][2] * mN[2][cc];
+        for (int cc = 0; cc < 6; ++cc) wN[i][cc] = dot3(An[i][0], mN[0][cc], An[i][1], mN[1][cc], An[i][2], mN[2][cc]);
       for (int j = 0; j < 6; ++j)
         for (int i = j; i < 6; ++i) {
-          const double vn = (mN[0][j] * wN[0][i] + mN[1][j] * wN[1][i]) + mN[2][j] * wN[2][i];
-          const double vs = (G[0] * (mS[0][j] * mS[0][i]) + G[1] * (mS[1][j] * mS[1][i])) + G[2] * (mS[2][j] * mS[2][i]);
+          const double vn = dot3(mN[0][j], wN[0][i], mN[1][j], wN[1][i], mN[2][j], wN[2][i]);
+          const double vs = FMA(G[2], mS[2][j] * mS[2][i], FMA(G[1], mS[1][j] * mS[1][i], G[0] * (mS[0][j] * mS[0][i])));
           const double v = vn + vs;
           ct[j * 6 + i] = v;
           ct[i * 6 + j] = v;

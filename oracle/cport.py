@@ -9,18 +9,38 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_build", "liboracle.so")
+LIB_UNFUSED = os.path.join(HERE, "_build", "liboracle_unfused.so")  # every explicit fma split again (round-1 arithmetic)
 _lib = None
+_lib_unfused = None
 _NAMES = ("E", "nu", "sig0", "H", "sigu", "b")
 
 
-def load(build=True):
-    global _lib
+def _cpu_has_fma():
+    try:
+        with open("/proc/cpuinfo") as f:
+            return " fma " in f.read().replace("\n", " ")
+    except OSError:
+        return True
+
+
+def load(build=True, fused=None):
+    """The C oracle; ``fused=None`` follows ``oracle.canon.FUSED`` (False: the -DDXO_UNFUSED twin)."""
+    global _lib, _lib_unfused
     if _lib is None:
-        srcs = [os.path.join(HERE, "c", f) for f in ("dxm_oracle.c", "dxm_oracle_hosford.c")]
-        if build and (not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(s) for s in srcs)):
-            subprocess.run(["make", "-s", "-C", HERE], check=True)
+        srcs = [os.path.join(HERE, "c", f) for f in os.listdir(os.path.join(HERE, "c"))] + [os.path.join(HERE, "Makefile")]
+        stale = any(not os.path.exists(p) or os.path.getmtime(p) < max(os.path.getmtime(s) for s in srcs)
+                    for p in (LIB, LIB_UNFUSED))
+        if build and stale:
+            subprocess.run(["make", "-s", "-C", HERE] + ([] if _cpu_has_fma() else ["FMAFLAG="]), check=True)
+        elif not _cpu_has_fma():  # prebuilt with -mfma for a CPU without it: rebuild on libm's fma()
+            subprocess.run(["make", "-s", "-B", "-C", HERE, "FMAFLAG="], check=True)
         _lib = ctypes.CDLL(LIB)
-    return _lib
+        _lib_unfused = ctypes.CDLL(LIB_UNFUSED)
+    if fused is None:
+        from . import canon
+
+        fused = canon.FUSED
+    return _lib if fused else _lib_unfused
 
 
 THREADS = 1  # row blocks are processed on this many Python threads (ctypes releases the GIL)

@@ -29,7 +29,8 @@ Every expression is written component-wise in a fixed order (``oracle/canon.py``
 
 import numpy as np
 
-from .canon import exp_c
+from .canon import dot3 as _dot3
+from .canon import exp_c, fma, fms, fnma
 
 NEWTON_CAP = 25
 NEWTON_RTOL = 1e-12
@@ -61,9 +62,9 @@ def rcbrt_c(x):
     q = np.floor_divide(e, 3)
     r = e - 3 * q
     xr = np.ldexp(m, r)
-    y = 1.2 - 0.15 * xr
+    y = fnma(0.15, xr, 1.2)
     for _ in range(6):
-        y = (y * (4.0 - xr * ((y * y) * y))) * THIRD
+        y = (y * fnma(xr, (y * y) * y, 4.0)) * THIRD
     y = np.ldexp(y, -q)
     return np.where(ok, y, np.nan)
 
@@ -73,30 +74,26 @@ def _unpack9(v):
 
 
 def _det3(A):
-    t0 = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1])
-    t1 = A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0])
-    t2 = A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0])
-    return (t0 - t1) + t2
+    m0 = fms(A[1][1], A[2][2], A[1][2] * A[2][1])
+    m1 = fms(A[1][0], A[2][2], A[1][2] * A[2][0])
+    m2 = fms(A[1][0], A[2][1], A[1][1] * A[2][0])
+    return fma(A[0][2], m2, fnma(A[0][1], m1, A[0][0] * m0))
 
 
 def _inv3(A):
     c = [[None] * 3 for _ in range(3)]
-    c[0][0] = A[1][1] * A[2][2] - A[1][2] * A[2][1]
-    c[0][1] = A[0][2] * A[2][1] - A[0][1] * A[2][2]
-    c[0][2] = A[0][1] * A[1][2] - A[0][2] * A[1][1]
-    c[1][0] = A[1][2] * A[2][0] - A[1][0] * A[2][2]
-    c[1][1] = A[0][0] * A[2][2] - A[0][2] * A[2][0]
-    c[1][2] = A[0][2] * A[1][0] - A[0][0] * A[1][2]
-    c[2][0] = A[1][0] * A[2][1] - A[1][1] * A[2][0]
-    c[2][1] = A[0][1] * A[2][0] - A[0][0] * A[2][1]
-    c[2][2] = A[0][0] * A[1][1] - A[0][1] * A[1][0]
-    det = (A[0][0] * c[0][0] + A[0][1] * c[1][0]) + A[0][2] * c[2][0]
+    c[0][0] = fms(A[1][1], A[2][2], A[1][2] * A[2][1])
+    c[0][1] = fms(A[0][2], A[2][1], A[0][1] * A[2][2])
+    c[0][2] = fms(A[0][1], A[1][2], A[0][2] * A[1][1])
+    c[1][0] = fms(A[1][2], A[2][0], A[1][0] * A[2][2])
+    c[1][1] = fms(A[0][0], A[2][2], A[0][2] * A[2][0])
+    c[1][2] = fms(A[0][2], A[1][0], A[0][0] * A[1][2])
+    c[2][0] = fms(A[1][0], A[2][1], A[1][1] * A[2][0])
+    c[2][1] = fms(A[0][1], A[2][0], A[0][0] * A[2][1])
+    c[2][2] = fms(A[0][0], A[1][1], A[0][1] * A[1][0])
+    det = fma(A[0][2], c[2][0], fma(A[0][1], c[1][0], A[0][0] * c[0][0]))
     rdet = 1.0 / det
     return [[c[i][j] * rdet for j in range(3)] for i in range(3)], det
-
-
-def _dot3(a0, b0, a1, b1, a2, b2):
-    return (a0 * b0 + a1 * b1) + a2 * b2
 
 
 def integrate(F, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
@@ -146,15 +143,14 @@ def integrate(F, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
                 B[j][i] = B[i][j]
         t0 = ((B[0][0] + B[1][1]) + B[2][2]) * THIRD
         D = [[B[i][j] - t0 if i == j else B[i][j] for j in range(3)] for i in range(3)]
-        dd = ((D[0][0] * D[0][0] + D[1][1] * D[1][1]) + D[2][2] * D[2][2]) + 2.0 * (
-            (D[0][1] * D[0][1] + D[0][2] * D[0][2]) + D[1][2] * D[1][2]
-        )
+        dd = fma(2.0, _dot3(D[0][1], D[0][1], D[0][2], D[0][2], D[1][2], D[1][2]),
+                 _dot3(D[0][0], D[0][0], D[1][1], D[1][1], D[2][2], D[2][2]))
         d3 = _det3(D)
         seq = mu * np.sqrt(1.5 * dd)
         rseq = 1.0 / seq
 
         e0 = exp_c(-(b * p_old))
-        sy0 = (sig0 + H * p_old) + dsu * (1.0 - e0)
+        sy0 = fma(dsu, 1.0 - e0, fma(H, p_old, sig0))
         ftr = seq - sy0
         flag = ftr > 0.0
 
@@ -171,12 +167,16 @@ def integrate(F, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
         for it in range(newton_cap + 1):
             if not active.any():
                 break
-            alpha = 1.0 - (c * t) * dp
+            ct = c * t
+            tmt = threemu * t
+            alpha = fnma(ct, dp, 1.0)
             p = p_old + dp
-            sy = (sig0 + H * p) + dsu * (1.0 - ecur)
-            r1 = (seq - (threemu * t) * dp) - sy
+            sy = fma(dsu, 1.0 - ecur, fma(H, p, sig0))
+            r1 = fnma(tmt, dp, seq) - sy
             a2 = alpha * alpha
-            r2 = ((t * t) * t - (0.5 * a2) * (dd * t)) + ((a2 * alpha) * d3 - 1.0)
+            ha2 = 0.5 * a2
+            tt = t * t
+            r2 = fnma(ha2, dd * t, tt * t) + fms(a2 * alpha, d3, 1.0)
             conv = (np.abs(r1) <= tol1) & (np.abs(r2) <= rtol)
             resid = np.where(active & conv, np.abs(r1), resid)
             active = active & ~conv
@@ -184,17 +184,16 @@ def integrate(F, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
                 fail |= active
                 resid = np.where(active, np.abs(r1), resid)
                 break
-            dsy = H + bdsu * ecur
-            g = 3.0 * (a2 * d3) - (alpha * dd) * t
-            J11 = -(threemu * t) - dsy
+            dsy = fma(bdsu, ecur, H)
+            g = fnma(alpha * dd, t, 3.0 * (a2 * d3))
+            J11 = -tmt - dsy
             J12 = -(threemu * dp)
-            ct = c * t
             cdp = c * dp
             J21 = -(g * ct)
-            J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp
-            rdet = 1.0 / (J11 * J22 - J12 * J21)
-            dp_new = dp + (J12 * r2 - r1 * J22) * rdet
-            t_new = t + (J21 * r1 - J11 * r2) * rdet
+            J22 = fnma(g, cdp, fnma(ha2, dd, 3.0 * tt))
+            rdet = 1.0 / fms(J11, J22, J12 * J21)
+            dp_new = fma(fms(J12, r2, r1 * J22), rdet, dp)
+            t_new = fma(fms(J21, r1, J11 * r2), rdet, t)
             dp = np.where(active, dp_new, dp)
             t = np.where(active, t_new, t)
             e_new = exp_c(-(b * (p_old + dp)))
@@ -203,13 +202,13 @@ def integrate(F, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
 
         dp = np.where(flag, dp, 0.0)
         t = np.where(flag, t, t0)
-        alpha = np.where(flag, 1.0 - (c * t) * dp, 1.0)
+        alpha = np.where(flag, fnma(c * t, dp, 1.0), 1.0)
         p_new = p_old + dp
 
         # ---- new state -----------------------------------------------------------------------------
         be = [None] * 6
         for i in range(3):
-            be[i] = np.where(flag, alpha * D[i][i] + t, B[i][i])
+            be[i] = np.where(flag, fma(alpha, D[i][i], t), B[i][i])
         be[3] = (alpha * D[0][1]) * SQRT2
         be[4] = (alpha * D[0][2]) * SQRT2
         be[5] = (alpha * D[1][2]) * SQRT2
@@ -217,31 +216,31 @@ def integrate(F, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
         # ---- stress: tau = mu alpha D + pvol 1, PK1 = tau F^-T = mu alpha (D F^-T) + pvol F^-T ----------
         Ai, Jd = _inv3(A)
         muA = mu * alpha
-        pvol = (0.5 * kappa) * (Jd * Jd - 1.0)
+        pvol = (0.5 * kappa) * fms(Jd, Jd, 1.0)
         DA = [[_dot3(D[i][0], Ai[j][0], D[i][1], Ai[j][1], D[i][2], Ai[j][2]) for j in range(3)] for i in range(3)]
-        P = [[muA * DA[i][j] + pvol * Ai[j][i] for j in range(3)] for i in range(3)]
+        P = [[fma(muA, DA[i][j], pvol * Ai[j][i]) for j in range(3)] for i in range(3)]
 
         # ---- local-solve sensitivities: d(alpha) = al1 * (D:dD) + al2 * (D^2:dD) --------------------------
         sq1 = (1.5 * (mu * mu)) * rseq
         a2 = alpha * alpha
-        dsy = H + bdsu * ecur
-        g = 3.0 * (a2 * d3) - (alpha * dd) * t
+        dsy = fma(bdsu, ecur, H)
+        g = fnma(alpha * dd, t, 3.0 * (a2 * d3))
         ct = c * t
         cdp = c * dp
         J11 = -(threemu * t) - dsy
         J12 = -(threemu * dp)
         J21 = -(g * ct)
-        J22 = (3.0 * (t * t) - (0.5 * a2) * dd) - g * cdp
-        rdet = 1.0 / (J11 * J22 - J12 * J21)
+        J22 = fnma(g, cdp, fnma(0.5 * a2, dd, 3.0 * (t * t)))
+        rdet = 1.0 / fms(J11, J22, J12 * J21)
         oma = (1.0 - alpha) * rseq
-        b21 = (g * oma) * sq1 - a2 * t
+        b21 = fms(g * oma, sq1, a2 * t)
         b22 = a2 * alpha
-        p1 = -((sq1 * J22 - J12 * b21) * rdet)
-        t1 = -((J11 * b21 - J21 * sq1) * rdet)
+        p1 = -(fms(sq1, J22, J12 * b21) * rdet)
+        t1 = -(fms(J11, b21, J21 * sq1) * rdet)
         p2 = (J12 * b22) * rdet
         t2 = -((J11 * b22) * rdet)
-        al1 = np.where(flag, (oma * sq1 - ct * p1) - cdp * t1, 0.0)
-        al2 = np.where(flag, -(ct * p2) - cdp * t2, 0.0)
+        al1 = np.where(flag, fnma(cdp, t1, fnma(ct, p1, oma * sq1)), 0.0)
+        al2 = np.where(flag, fnma(cdp, t2, -(ct * p2)), 0.0)
 
         # ---- tangent, column (k, l) = d/dF_kl:  with w = row l of F^-1, v = B w = D w + t0 w -------------
         #   dP_ij = cD (D F^-T)_ij + cI F^-T_ij + delta_ik mu alpha (F^-1 v)_j + hs w_i F^-1_jk
@@ -249,24 +248,24 @@ def integrate(F, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
         c23dd = (2.0 / 3.0) * dd
         twod3 = 2.0 * d3
         c23muA = (2.0 / 3.0) * muA
-        hs = muA * t0 - pvol
+        hs = fms(muA, t0, pvol)
         Ct = np.zeros((n, 9, 9))
         for l in range(3):
             w = [Ai[l][0], Ai[l][1], Ai[l][2]]
-            v = [_dot3(D[i][0], w[0], D[i][1], w[1], D[i][2], w[2]) + t0 * w[i] for i in range(3)]
+            v = [fma(t0, w[i], _dot3(D[i][0], w[0], D[i][1], w[1], D[i][2], w[2])) for i in range(3)]
             u = [_dot3(D[i][0], v[0], D[i][1], v[1], D[i][2], v[2]) for i in range(3)]
             z = [_dot3(D[i][0], u[0], D[i][1], u[1], D[i][2], u[2]) for i in range(3)]
             my = [muA * _dot3(Ai[j][0], v[0], Ai[j][1], v[1], Ai[j][2], v[2]) for j in range(3)]
             hw = [hs * w[i] for i in range(3)]
             for k in range(3):
-                a1 = 2.0 * u[k] - c23dd * w[k]
-                a2p = (2.0 * z[k] - c23dd * v[k]) - twod3 * w[k]
-                cD = np.where(flag, mu * (al1 * a1 + al2 * a2p), 0.0) - c23muA * w[k]
-                cI = kJ2 * w[k] - c23muA * v[k]
+                a1 = fnma(c23dd, w[k], 2.0 * u[k])
+                a2p = fnma(twod3, w[k], fnma(c23dd, v[k], 2.0 * z[k]))
+                cD = fnma(c23muA, w[k], np.where(flag, mu * fma(al2, a2p, al1 * a1), 0.0))
+                cI = fnma(c23muA, v[k], kJ2 * w[k])
                 col = IDX9[k][l]
                 for i in range(3):
                     for j in range(3):
-                        val = (cD * DA[i][j] + cI * Ai[j][i]) + hw[i] * Ai[j][k]
+                        val = fma(hw[i], Ai[j][k], fma(cI, Ai[j][i], cD * DA[i][j]))
                         if i == k:
                             val = val + my[j]
                         Ct[:, IDX9[i][j], col] = val

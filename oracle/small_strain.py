@@ -24,7 +24,7 @@ Every expression below is written component-wise in a fixed operation order (see
 
 import numpy as np
 
-from .canon import exp_c, lame
+from .canon import exp_c, fma, fnma, lame
 
 NEWTON_CAP = 25
 NEWTON_RTOL = 1e-12
@@ -80,23 +80,23 @@ def integrate(eps, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
         de = [eps[:, i] - e_old[:, i] for i in range(6)]
         tr = (de[0] + de[1]) + de[2]
         ltr = lam * tr
-        st = [s_old[:, i] + (ltr + twomu * de[i]) for i in range(3)]
-        st += [s_old[:, i] + twomu * de[i] for i in range(3, 6)]
+        st = [s_old[:, i] + fma(twomu, de[i], ltr) for i in range(3)]
+        st += [fma(twomu, de[i], s_old[:, i]) for i in range(3, 6)]
         pm = ((st[0] + st[1]) + st[2]) / 3.0
         s = [st[i] - pm for i in range(3)] + [st[i] for i in range(3, 6)]
-        ss = s[0] * s[0] + s[1] * s[1]
-        for i in range(2, 6):
-            ss = ss + s[i] * s[i]
+        ss = s[0] * s[0]
+        for i in range(1, 6):
+            ss = fma(s[i], s[i], ss)
         seq = np.sqrt(1.5 * ss)
 
         e0 = exp_c(-(b * p_old))
-        sy0 = (sig0 + H * p_old) + dsu * (1.0 - e0)
+        sy0 = fma(dsu, 1.0 - e0, fma(H, p_old, sig0))
         if table is not None:
             K = len(tp)
             seg = np.zeros(n, dtype=np.int64)
             for k in range(K - 1):
                 seg = np.where(p_old >= tp[k + 1], k + 1, seg)
-            sy0 = ts[seg] + tH[seg] * (p_old - tp[seg])
+            sy0 = fma(tH[seg], p_old - tp[seg], ts[seg])
         f = seq - sy0
         flag = f > 0.0
 
@@ -117,7 +117,7 @@ def integrate(eps, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
             closed = np.ones(n, dtype=bool)
             walking = flag.copy()
             for _ in range(K):
-                cand = (seq - (ts[seg] + tH[seg] * (p_old - tp[seg]))) / (threemu + tH[seg])
+                cand = (seq - fma(tH[seg], p_old - tp[seg], ts[seg])) / (threemu + tH[seg])
                 dp = np.where(walking, cand, dp)
                 nxt = np.minimum(seg + 1, K - 1)
                 cross = walking & (seg < K - 1) & (p_old + dp > tp[nxt])
@@ -135,8 +135,8 @@ def integrate(eps, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
             if not active.any():
                 break
             p = p_old + dp
-            sy = (sig0 + H * p) + dsu * (1.0 - ecur)
-            r = (seq - threemu * dp) - sy
+            sy = fma(dsu, 1.0 - ecur, fma(H, p, sig0))
+            r = fnma(threemu, dp, seq) - sy
             conv = np.abs(r) <= tol
             done = active & conv
             resid = np.where(done, np.abs(r), resid)
@@ -145,7 +145,7 @@ def integrate(eps, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
                 fail |= active
                 resid = np.where(active, np.abs(r), resid)
                 break
-            dsy = H + bdsu * ecur
+            dsy = fma(bdsu, ecur, H)
             dp_new = dp + r / (threemu + dsy)
             dp = np.where(active, dp_new, dp)
             e_new = exp_c(-(b * (p_old + dp)))
@@ -153,11 +153,11 @@ def integrate(eps, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
             n_iter = n_iter + active.astype(np.int32)
 
         # ---- state update -----------------------------------------------------------------
-        Hp = H + bdsu * ecur  # sigma_Y'(p_new)
+        Hp = fma(bdsu, ecur, H)  # sigma_Y'(p_new)
         nrm = [np.where(flag, (1.5 * s[i]) / seq, 0.0) for i in range(6)]
         dp = np.where(flag, dp, 0.0)
         depsp = [dp * nrm[i] for i in range(6)]
-        sig = [st[i] - twomu * depsp[i] for i in range(6)]
+        sig = [fnma(twomu, depsp[i], st[i]) for i in range(6)]
         epsp = [ep_old[:, i] + depsp[i] for i in range(6)]
         p_new = p_old + dp
 
@@ -167,8 +167,8 @@ def integrate(eps, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
         fourmu2 = (4.0 * mu) * mu
         beta = fourmu2 * q
         gamma = np.where(flag, fourmu2 * (cste - q), 0.0)
-        A = lam + 0.5 * beta
-        B = twomu - 1.5 * beta
+        A = fma(0.5, beta, lam)
+        B = fnma(1.5, beta, twomu)
         AB = A + B
         Ct = np.zeros((n, 6, 6))
         for j in range(6):
@@ -179,7 +179,7 @@ def integrate(eps, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
                     base = A
                 else:
                     base = 0.0
-                Ct[:, j, i] = base - gamma * (nrm[i] * nrm[j])
+                Ct[:, j, i] = fnma(gamma, nrm[i] * nrm[j], base)
 
         # fused non-finite check (replaces the host NaN scans of quadrature_map.py:322-324)
         chk = (seq + np.abs(pm)) + p_new

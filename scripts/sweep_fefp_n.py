@@ -21,7 +21,7 @@ for n in [int(float(a)) for a in (sys.argv[1:] or ["1e7", "2e7", "4e7", "8e7"])]
     time.sleep(0.3)
     ts = []
     t0 = time.time()
-    while time.time() - t0 < 1.5:
+    while time.time() - t0 < float(os.environ.get("DXM_SUSTAIN_S", "3.0")):
         ts.append(m.integrate_resident().kernel_ms)
     smi.terminate()
     lines = [l.split(",") for l in smi.stdout.read().strip().splitlines() if "," in l]

@@ -4,8 +4,10 @@ import os
 
 import numpy as np
 import pytest
+from golden_check import close
 
 pytestmark = pytest.mark.gpu
+
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -52,9 +54,12 @@ def test_histories_vs_reference_protocol_run(jm, name):
     k = 1
     while f"{key}{k}" in g:
         flux, isv, Ct = m.integrate(g[f"{key}{k}"])
-        assert np.array_equal(flux, g[f"flux{k}"])
-        assert np.array_equal(isv, g[f"isv{k}"])
-        assert np.array_equal(Ct, g[f"Ct{k}"])
+        # the fixtures hold the round-1 (un-fused) arithmetic; the kernels' fused canonical arithmetic agrees with it
+        # to the north star's rtol 1e-10 (bit-identity with the fused oracle: the other GPU tests)
+        close(flux, g[f"flux{k}"], "flux")
+        for c0, c1 in ((0, 1), (1, isv.shape[1])):
+            close(isv[:, c0:c1], g[f"isv{k}"][:, c0:c1], "isv")
+        close(Ct, g[f"Ct{k}"], "Ct")
         m.data_manager.update()
         k += 1
     assert k > 3
