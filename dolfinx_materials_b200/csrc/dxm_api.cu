@@ -18,7 +18,7 @@ std::atomic<long long> g_launches{0};
 namespace {
 constexpr int64_t kChunk = 1 << 19;  // points per pipeline chunk on the host path
 const char* kPropNames[kNProp] = {"E", "nu", "sig0", "H", "sigu", "b"};
-constexpr double kHosSplitMaxPlastic = 0.55;  // Hosford: fused kernel above this plastic fraction (previous call)
+constexpr double kHosSplitMaxPlastic = 0.45;  // Hosford: fused kernel above this plastic fraction (previous call)
 constexpr bool kHostMirrorDefault = false;  // A/B on the B200 box: profiles/ (DXM_HOST_MIRROR overrides)
 }  // namespace
 
@@ -257,16 +257,19 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
     a.hos_a = h->hos_a;
     a.hos_bound = hosford_bound(h->hos_a);
     // Tiled kernel (stream a tile, pack the candidates into full warps) or the fused one.  Tiling wins while a good
-    // part of the batch is elastic (6.6 vs 4.6 G points/s at 3 % plastic); when most points are plastic its extra
-    // pass costs more than the packing gains (crossover at 50-60 % plastic, profiles/r01h_configs.json), and small
+    // part of the batch is elastic (6.5 vs 4.8 G points/s at 3 % plastic); when most points are plastic its extra
+    // pass costs more than the packing gains (crossover at 40-50 % plastic, profiles/r02c_hosford_ab_*.json), and small
     // batches are latency-bound either way: auto mode keys on the batch size and on the plastic fraction of the
-    // previous call.  DXM_HOS_SPLIT=0|1 forces fused | tiled.
+    // previous call.  DXM_HOS_SPLIT=0|1 forces fused | tiled.  (A warp-private queue -- every heavy pass a full warp, no
+    // block barrier -- was also measured in round 2: same times as the tiled kernel to 2-5 %; the local solves are bound
+    // by the latency of their dependent FP64 chains, not by idle lanes.  Not kept.)
     const char* e = std::getenv("DXM_HOS_SPLIT");
     bool tiled = count >= 32768;
     if (tiled && h->prev_points > 0) tiled = (double)h->prev_plastic < kHosSplitMaxPlastic * (double)h->prev_points;
     if (e) tiled = std::atoi(e) != 0;
+    const char* mb = std::getenv("DXM_HOS_MINB");  // A/B knob, read per call like DXM_HOS_SPLIT
     // sigu is only ever set for a hardening law with a saturation term (VoceHardening); otherwise it follows sig0
-    HosLaunch cfg{h->num_sms, h->stream, h->set[4], tiled, kTilesPerCta};
+    HosLaunch cfg{h->num_sms, h->stream, h->set[4], tiled, kTilesPerCta, mb ? std::atoi(mb) : 0};
     int launches = 0;
     const int rc = launch_hosford(a, cfg, &launches);
     g_launches.fetch_add(launches);

@@ -216,130 +216,149 @@ DXM_HD void hos_mandel_pair(const double (&V)[3][3], double (&m)[6]) {
   }
 }
 
-// One Gauss point.  ct21: the 21 unique tangent entries (j <= i, row-major upper triangle = sym6_packed order).
-// LIGHT == true: only the clearly elastic points are finished; for a candidate (the cheap rejection did not fire) the
-// routine returns true without touching the outputs and the caller hands the point to the full routine.
+// ---- one Gauss point, in four stages ---------------------------------------------------------------------------------
+// hos_trial -> hos_jacobi3 -> hos_newton -> hos_finish.  hosford_point() below runs them back to back (CPU harness,
+// phase A of the tiled kernel); the local-solve kernels run the same stages but keep only what the Newton loop needs in
+// registers across it: the eigenvectors wait in shared memory and the trial stress / old plastic strain are re-formed
+// from the (L2-resident) inputs afterwards -- same operations on the same values, hence the same bits, with 128 instead
+// of 168 registers per thread (profiles/r02c_hosford_*).
+//
 // AT > 0: the exponent as a compile-time constant (the power chains unroll into straight DMUL sequences; with a
 // run-time exponent 35 % of the executed instructions were loop bookkeeping, profiles/r01g_hosford_v2_*); AT == 0: a_rt.
 // bound: (2^(a-1)+1)^(1/a)/sqrt(3) (1 + 1e-9) >= sigma_eq / seq_Mises for every stress state (maximum at pure shear).
 // VOCE == false: the saturation term is absent at compile time (dsu = b = 0: same bits as the general law with
 // dsu = 0, without its registers -- carrying it at run time cost the linear-hardening case 14-30 %, profiles/r01l).
-template <bool LIGHT, int AT, bool VOCE>
-DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, const double H, const double dsu_rt,
-                          const double b_rt, const int a_rt, const double bound, const double (&eps)[6], const double (&e_old)[6], const double (&s_old)[6],
-                          const double p_old, const double (&ep_old)[6], double (&sig)[6], double& p_new,
-                          double (&epsp)[6], double (&ct21)[21], bool& flag, int& n_iter, double& resid,
-                          bool& fail) {
-  const int a = AT > 0 ? AT : a_rt;
+struct HosTrial {
+  double st[6], s[6], pm, seq;
+};
+
+// trial stress, its deviator and the von Mises equivalent (same expressions as the J2 update)
+DXM_HD void hos_trial(const double lam, const double mu, const double (&eps)[6], const double (&e_old)[6],
+                      const double (&s_old)[6], HosTrial& t) {
   const double twomu = 2.0 * mu;
-  const double threemu = 3.0 * mu;
-  double de[6], st[6], s[6];
+  double de[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) de[i] = eps[i] - e_old[i];
   const double tr = (de[0] + de[1]) + de[2];
   const double ltr = lam * tr;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) st[i] = s_old[i] + fma_c(twomu, de[i], ltr);
+  for (int i = 0; i < 3; ++i) t.st[i] = s_old[i] + fma_c(twomu, de[i], ltr);
 #pragma unroll
-  for (int i = 3; i < 6; ++i) st[i] = fma_c(twomu, de[i], s_old[i]);
-  const double pm = ((st[0] + st[1]) + st[2]) / 3.0;
+  for (int i = 3; i < 6; ++i) t.st[i] = fma_c(twomu, de[i], s_old[i]);
+  t.pm = ((t.st[0] + t.st[1]) + t.st[2]) / 3.0;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) s[i] = st[i] - pm;
+  for (int i = 0; i < 3; ++i) t.s[i] = t.st[i] - t.pm;
 #pragma unroll
-  for (int i = 3; i < 6; ++i) s[i] = st[i];
-  double ss = s[0] * s[0];
+  for (int i = 3; i < 6; ++i) t.s[i] = t.st[i];
+  double ss = t.s[0] * t.s[0];
 #pragma unroll
-  for (int i = 1; i < 6; ++i) ss = fma_c(s[i], s[i], ss);
-  const double seq = sqrt(1.5 * ss);
-  const double dsu = VOCE ? dsu_rt : 0.0, b = VOCE ? b_rt : 0.0;
-  const HosHard hd{sig0, H, dsu, b, VOCE ? b * dsu : 0.0, p_old};
-  double sy0, dsy0;
-  hos_hard(hd, 0.0, sy0, dsy0);
+  for (int i = 1; i < 6; ++i) ss = fma_c(t.s[i], t.s[i], ss);
+  t.seq = sqrt(1.5 * ss);
+}
 
-  flag = false;
-  n_iter = 0;
-  fail = false;
-  resid = 0.0;
+struct HosSol {
+  HosRes cur;  // residual / criterion data at the solution (the tangent needs e.n, e.h, e.u, e.iphi, dsy)
+  double dp, resid;
+  int n_iter;
+  bool flag, fail;
+};
+
+// 4-unknown Newton (3 principal deviatoric stresses + dp) in the principal axes of the trial deviator, eigenvalues l
+template <int AT>
+DXM_HD void hos_newton(const double (&l)[3], const double mu, const HosHard& hd, const double sy0, const double dsy0,
+                       const double seq, const int a_rt, HosSol& o) {
+  const int a = AT > 0 ? AT : a_rt;
+  const double twomu = 2.0 * mu;
+  const double threemu = 3.0 * mu;
+  const double am1 = (double)a - 1.0, inv_a = 1.0 / (double)a;
+  const double tol = kNewtonRtol * seq;
+  o.flag = false;
+  o.fail = false;
+  o.n_iter = 0;
+  o.resid = 0.0;
   double dp = 0.0;
-  double V[3][3];
-  HosRes cur;
-  // sigma_eq <= bound * seq_Mises: below that the point is surely elastic
-  const bool candidate = bound * seq > sy0;
-  if (LIGHT && candidate) return true;
-  if (!LIGHT && candidate) {
-    const double am1 = (double)a - 1.0, inv_a = 1.0 / (double)a;
-    const double tol = kNewtonRtol * seq;
-    double l[3], x[3] = {0.0, 0.0, 0.0}, xe[3], dx[3] = {0.0, 0.0, 0.0}, dpe = 0.0, ddp = 0.0, t = 1.0;
-    int ls = 0, stage = 0;
-    hos_jacobi3(s, l, V);
+  double x[3] = {0.0, 0.0, 0.0}, xe[3], dx[3] = {0.0, 0.0, 0.0}, dpe = 0.0, ddp = 0.0, t = 1.0;
+  int ls = 0, stage = 0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) xe[k] = l[k];
-    // One evaluation site for the three uses of the residual (trial state, start point, line-search candidates):
-    // stage 0 = yield check at the trial state, 1 = start point, 2 = line-search candidate of a Newton step.
-    double m_prev = 0.0;
-    for (;;) {
-      // evaluated in place: once the step (dx, ddp) is formed only the merit value of the previous iterate is needed
-      hos_residual(xe, dpe, l, twomu, hd, a, inv_a, cur);
-      if (stage == 0) {
-        const double f = cur.e.phi - sy0;
-        flag = f > 0.0;
-        if (!flag) break;
-        // start on the yield surface along the trial direction, dp from the J2-like estimate
-        dpe = f / (threemu + dsy0);
-        double sy1, dsy1;
-        hos_hard(hd, dpe, sy1, dsy1);
-        const double sc = sy1 / cur.e.phi;
+  for (int k = 0; k < 3; ++k) xe[k] = l[k];
+  // One evaluation site for the three uses of the residual (trial state, start point, line-search candidates):
+  // stage 0 = yield check at the trial state, 1 = start point, 2 = line-search candidate of a Newton step.
+  double m_prev = 0.0;
+  for (;;) {
+    // evaluated in place: once the step (dx, ddp) is formed only the merit value of the previous iterate is needed
+    hos_residual(xe, dpe, l, twomu, hd, a, inv_a, o.cur);
+    if (stage == 0) {
+      const double f = o.cur.e.phi - sy0;
+      o.flag = f > 0.0;
+      if (!o.flag) break;
+      // start on the yield surface along the trial direction, dp from the J2-like estimate
+      dpe = f / (threemu + dsy0);
+      double sy1, dsy1;
+      hos_hard(hd, dpe, sy1, dsy1);
+      const double sc = sy1 / o.cur.e.phi;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) xe[k] = l[k] * sc;
-        stage = 1;
+      for (int k = 0; k < 3; ++k) xe[k] = l[k] * sc;
+      stage = 1;
+      continue;
+    }
+    if (stage == 2) {
+      if (!(o.cur.m2 < m_prev || ls == kHosfordLsMax)) {  // no decrease: halve the step
+        t = 0.5 * t;
+        ++ls;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) xe[k] = fma_c(t, dx[k], x[k]);
+        dpe = fma_c(t, ddp, dp);
         continue;
       }
-      if (stage == 2) {
-        if (!(cur.m2 < m_prev || ls == kHosfordLsMax)) {  // no decrease: halve the step
-          t = 0.5 * t;
-          ++ls;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) xe[k] = fma_c(t, dx[k], x[k]);
-          dpe = fma_c(t, ddp, dp);
-          continue;
-        }
-        ++n_iter;
-      }
-      stage = 2;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) x[k] = xe[k];
-      dp = dpe;
-      m_prev = cur.m2;
-      const double res = fmax(fmax(fabs(cur.rs[0]), fabs(cur.rs[1])), fmax(fabs(cur.rs[2]), fabs(cur.r4)));
-      if (res <= tol) {
-        resid = res;
-        break;
-      }
-      if (n_iter == kNewtonCap || !(res == res)) {
-        resid = res;
-        fail = true;
-        break;
-      }
-      double Cf[6], idet, y[3], z[3];
-      hos_system(cur.e, twomu * dp, am1 * cur.e.iphi, Cf, idet);
-      hos_apply(Cf, idet, cur.rs, y);
-      hos_apply(Cf, idet, cur.e.n, z);
-      const double ny = fma_c(cur.e.n[2], y[2], fma_c(cur.e.n[1], y[1], cur.e.n[0] * y[0]));
-      const double nz = fma_c(cur.e.n[2], z[2], fma_c(cur.e.n[1], z[1], cur.e.n[0] * z[0]));
-      ddp = (cur.r4 - ny) / fma_c(twomu, nz, cur.dsy);
-      const double tz = twomu * ddp;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) dx[k] = -fma_c(tz, z[k], y[k]);
-      t = 1.0;
-      ls = 0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) xe[k] = fma_c(t, dx[k], x[k]);
-      dpe = fma_c(t, ddp, dp);
+      ++o.n_iter;
     }
+    stage = 2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) x[k] = xe[k];
+    dp = dpe;
+    m_prev = o.cur.m2;
+    const double res = fmax(fmax(fabs(o.cur.rs[0]), fabs(o.cur.rs[1])), fmax(fabs(o.cur.rs[2]), fabs(o.cur.r4)));
+    if (res <= tol) {
+      o.resid = res;
+      break;
+    }
+    if (o.n_iter == kNewtonCap || !(res == res)) {
+      o.resid = res;
+      o.fail = true;
+      break;
+    }
+    double Cf[6], idet, y[3], z[3];
+    hos_system(o.cur.e, twomu * dp, am1 * o.cur.e.iphi, Cf, idet);
+    hos_apply(Cf, idet, o.cur.rs, y);
+    hos_apply(Cf, idet, o.cur.e.n, z);
+    const double ny = fma_c(o.cur.e.n[2], y[2], fma_c(o.cur.e.n[1], y[1], o.cur.e.n[0] * y[0]));
+    const double nz = fma_c(o.cur.e.n[2], z[2], fma_c(o.cur.e.n[1], z[1], o.cur.e.n[0] * z[0]));
+    ddp = (o.cur.r4 - ny) / fma_c(twomu, nz, o.cur.dsy);
+    const double tz = twomu * ddp;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dx[k] = -fma_c(tz, z[k], y[k]);
+    t = 1.0;
+    ls = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) xe[k] = fma_c(t, dx[k], x[k]);
+    dpe = fma_c(t, ddp, dp);
   }
+  o.dp = dp;
+}
 
+// new state, stress and the 21 unique tangent entries (j <= i, row-major upper triangle = sym6_packed order) from the
+// trial state, the old plastic strain and -- plastic points only -- the local solution and the eigenvectors V
+template <int AT>
+DXM_HD void hos_finish(const double lam, const double mu, const HosTrial& tr, const double p_old,
+                       const double (&ep_old)[6], const bool plastic, const HosSol& so, const double (&V)[3][3],
+                       const int a_rt, double (&sig)[6], double& p_new, double (&epsp)[6], double (&ct21)[21],
+                       bool& fail) {
+  const int a = AT > 0 ? AT : a_rt;
+  const double twomu = 2.0 * mu;
+  const HosRes& cur = so.cur;
+  double dp = so.dp;
   double mN0[6], mN1[6], mN2[6], nrm[6];
-  if (!LIGHT && flag) {
+  if (plastic) {
     hos_mandel_pair<0, 0>(V, mN0);
     hos_mandel_pair<1, 1>(V, mN1);
     hos_mandel_pair<2, 2>(V, mN2);
@@ -353,12 +372,12 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     const double depsp = dp * nrm[i];
-    sig[i] = fnma_c(twomu, depsp, st[i]);
+    sig[i] = fnma_c(twomu, depsp, tr.st[i]);
     epsp[i] = ep_old[i] + depsp;
   }
   p_new = p_old + dp;
 
-  if (LIGHT || !flag) {
+  if (!plastic) {
     const double AB = lam + twomu;
 #pragma unroll
     for (int j = 0; j < 6; ++j)
@@ -403,10 +422,52 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
         ct21[sym6_packed(j * 6 + i)] = vn + vs;
       }
   }
-  double chk = (seq + fabs(pm)) + p_new;
+  double chk = (tr.seq + fabs(tr.pm)) + p_new;
 #pragma unroll
   for (int i = 0; i < 6; ++i) chk = chk + fabs(epsp[i]);
   if (!isfinite(chk)) fail = true;
+}
+
+DXM_HD HosHard hos_hardening(const double sig0, const double H, const double dsu_rt, const double b_rt,
+                             const double p_old, const bool voce) {
+  const double dsu = voce ? dsu_rt : 0.0, b = voce ? b_rt : 0.0;
+  return HosHard{sig0, H, dsu, b, voce ? b * dsu : 0.0, p_old};
+}
+
+// One Gauss point, the four stages back to back.  LIGHT == true: only the clearly elastic points are finished; for a
+// candidate (the cheap rejection did not fire) the routine returns true without touching the outputs and the caller
+// hands the point to the full routine.
+template <bool LIGHT, int AT, bool VOCE>
+DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, const double H, const double dsu_rt,
+                          const double b_rt, const int a_rt, const double bound, const double (&eps)[6], const double (&e_old)[6], const double (&s_old)[6],
+                          const double p_old, const double (&ep_old)[6], double (&sig)[6], double& p_new,
+                          double (&epsp)[6], double (&ct21)[21], bool& flag, int& n_iter, double& resid,
+                          bool& fail) {
+  HosTrial tr;
+  hos_trial(lam, mu, eps, e_old, s_old, tr);
+  const HosHard hd = hos_hardening(sig0, H, dsu_rt, b_rt, p_old, VOCE);
+  double sy0, dsy0;
+  hos_hard(hd, 0.0, sy0, dsy0);
+  // sigma_eq <= bound * seq_Mises: below that the point is surely elastic
+  const bool candidate = bound * tr.seq > sy0;
+  if (LIGHT && candidate) return true;
+  HosSol so;
+  so.flag = false;
+  so.fail = false;
+  so.n_iter = 0;
+  so.resid = 0.0;
+  so.dp = 0.0;
+  double V[3][3];
+  if (!LIGHT && candidate) {
+    double l[3];
+    hos_jacobi3(tr.s, l, V);
+    hos_newton<AT>(l, mu, hd, sy0, dsy0, tr.seq, a_rt, so);
+  }
+  flag = so.flag;
+  n_iter = so.n_iter;
+  resid = so.resid;
+  fail = so.fail;
+  hos_finish<AT>(lam, mu, tr, p_old, ep_old, !LIGHT && so.flag, so, V, a_rt, sig, p_new, epsp, ct21, fail);
   return false;
 }
 
@@ -419,12 +480,13 @@ struct HosPointIO {
   double eps[6], e_old[6], s_old[6], ep_old[6], p_old, lam, mu, sig0, H, dsu, b;
 };
 
-// STREAM: evict-first loads (last use of the inputs); phase A of the tiled kernel keeps them cacheable for phase B
+// STREAM: evict-first loads (last use of the inputs); the first pass over a point keeps them cacheable for the second
 template <bool STREAM>
 __device__ __forceinline__ double hos_ld(const double* p) { return STREAM ? __ldcs(p) : __ldg(p); }
 
-template <bool STREAM, bool VOCE>
-__device__ __forceinline__ void hos_load(const SmallStrainArgs& a, int64_t i0, HosPointIO& io) {
+// the three 6-vectors the trial stress is formed from
+template <bool STREAM>
+__device__ __forceinline__ void hos_load_trial(const SmallStrainArgs& a, int64_t i0, HosPointIO& io) {
   const int64_t ld = a.ld;
 #pragma unroll
   for (int c = 0; c < 6; ++c) io.eps[c] = hos_ld<STREAM>(a.eps + c * ld + i0);
@@ -432,9 +494,11 @@ __device__ __forceinline__ void hos_load(const SmallStrainArgs& a, int64_t i0, H
   for (int c = 0; c < 6; ++c) io.e_old[c] = hos_ld<STREAM>(a.eps_old + c * ld + i0);
 #pragma unroll
   for (int c = 0; c < 6; ++c) io.s_old[c] = hos_ld<STREAM>(a.sig_old + c * ld + i0);
+}
+
+template <bool STREAM, bool VOCE>
+__device__ __forceinline__ void hos_load_props(const SmallStrainArgs& a, int64_t i0, HosPointIO& io) {
   io.p_old = hos_ld<STREAM>(a.p_old + i0);
-#pragma unroll
-  for (int c = 0; c < 6; ++c) io.ep_old[c] = hos_ld<STREAM>(a.epsp_old + c * ld + i0);
   io.lam = a.lam;
   io.mu = a.mu;
   io.sig0 = a.sig0;
@@ -455,7 +519,15 @@ __device__ __forceinline__ void hos_load(const SmallStrainArgs& a, int64_t i0, H
   }
 }
 
-__device__ __forceinline__ void hos_finish(const SmallStrainArgs& a, int64_t i0, const double (&sig)[6], double p_new,
+template <bool STREAM, bool VOCE>
+__device__ __forceinline__ void hos_load(const SmallStrainArgs& a, int64_t i0, HosPointIO& io) {
+  hos_load_trial<STREAM>(a, i0, io);
+  hos_load_props<STREAM, VOCE>(a, i0, io);
+#pragma unroll
+  for (int c = 0; c < 6; ++c) io.ep_old[c] = hos_ld<STREAM>(a.epsp_old + c * a.ld + i0);
+}
+
+__device__ __forceinline__ void hos_finish_store(const SmallStrainArgs& a, int64_t i0, const double (&sig)[6], double p_new,
                                            const double (&epsp)[6], const double (&ct21)[21], bool flag, int n_iter,
                                            double resid, bool fail, PointStats& acc) {
   const int64_t ld = a.ld;
@@ -479,23 +551,70 @@ __device__ __forceinline__ void hos_finish(const SmallStrainArgs& a, int64_t i0,
   for (int r = 0; r < 21; ++r) __stcs(a.ct + (int64_t)r * ld + i0, ct21[r]);
 }
 
-// fused: every thread runs the full routine on its own point (small batches, mostly-plastic batches, A/B reference)
+constexpr int kHosBlock = 128;
+struct HosPark {
+  double V[9][kHosBlock];  // eigenvectors of the thread's point while its Newton loop runs
+};
+
+// Full update of the point at SoA position i0 by the calling thread, register-lean: across the Newton loop only the
+// eigenvalues, the loop state and the hardening constants stay in registers -- the eigenvectors wait in shared memory
+// and the trial stress is formed a second time from the inputs (cacheable first pass -> L2 hits) once the loop is over.
+// Same stages, same operations on the same values as hosford_point(): bit-identical results.
 template <int AT, bool VOCE>
-__global__ void __launch_bounds__(128, 3) dxm_hosford_kernel(const SmallStrainArgs a) {
+__device__ __forceinline__ void hos_solve_point(const SmallStrainArgs& a, const int64_t i0, HosPark& park, PointStats& acc) {
+  HosPointIO io;
+  hos_load_props<false, VOCE>(a, i0, io);
+  const HosHard hd = hos_hardening(io.sig0, io.H, io.dsu, io.b, io.p_old, VOCE);
+  double sy0, dsy0;
+  hos_hard(hd, 0.0, sy0, dsy0);
+  HosSol so;
+  so.flag = false;
+  so.fail = false;
+  so.n_iter = 0;
+  so.resid = 0.0;
+  so.dp = 0.0;
+  {
+    HosTrial tr;
+    hos_load_trial<false>(a, i0, io);
+    hos_trial(io.lam, io.mu, io.eps, io.e_old, io.s_old, tr);
+    if (a.hos_bound * tr.seq > sy0) {
+      double l[3], V[3][3];
+      hos_jacobi3(tr.s, l, V);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) park.V[r * 3 + c][threadIdx.x] = V[r][c];
+      hos_newton<AT>(l, io.mu, hd, sy0, dsy0, tr.seq, a.hos_a, so);
+    }
+  }
+  HosTrial tr;
+  hos_load_trial<true>(a, i0, io);
+  hos_trial(io.lam, io.mu, io.eps, io.e_old, io.s_old, tr);
+#pragma unroll
+  for (int c = 0; c < 6; ++c) io.ep_old[c] = __ldcs(a.epsp_old + c * a.ld + i0);
+  double V[3][3];
+  if (so.flag) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) V[r][c] = park.V[r * 3 + c][threadIdx.x];
+  }
+  double sig[6], epsp[6], ct21[21], p_new;
+  bool fail = so.fail;
+  hos_finish<AT>(io.lam, io.mu, tr, io.p_old, io.ep_old, so.flag, so, V, a.hos_a, sig, p_new, epsp, ct21, fail);
+  hos_finish_store(a, i0, sig, p_new, epsp, ct21, so.flag, so.n_iter, so.resid, fail, acc);
+}
+
+// fused: every thread runs the full routine on its own point (small batches, mostly-plastic batches, A/B reference)
+template <int AT, bool VOCE, int MINB>
+__global__ void __launch_bounds__(kHosBlock, MINB) dxm_hosford_kernel(const SmallStrainArgs a) {
+  __shared__ HosPark park;
   const int64_t ntile = (a.count + blockDim.x - 1) / blockDim.x;
   PointStats acc;
   for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     const int64_t loc = tile * blockDim.x + threadIdx.x;
     if (loc >= a.count) continue;
-    const int64_t i0 = a.start + loc;
-    HosPointIO io;
-    hos_load<true, VOCE>(a, i0, io);
-    double sig[6], epsp[6], ct21[21], p_new, resid;
-    bool flag, fail;
-    int n_iter;
-    hosford_point<false, AT, VOCE>(io.lam, io.mu, io.sig0, io.H, io.dsu, io.b, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old, io.p_old,
-                             io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
-    hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
+    hos_solve_point<AT, VOCE>(a, a.start + loc, park, acc);
   }
   block_reduce_stats(acc, a.stats);
 }
@@ -506,8 +625,9 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_kernel(const SmallStrainAr
 // stores issued moments earlier by the same CTA -- a device-wide queue + second kernel (r01g) lost exactly that
 // locality when few points are candidates (scattered 8-byte accesses) and was slower in every regime.
 constexpr int kHosTile = 1024;
-template <int AT, bool VOCE>
-__global__ void __launch_bounds__(128, 3) dxm_hosford_tiled_kernel(const SmallStrainArgs a) {
+template <int AT, bool VOCE, int MINB>
+__global__ void __launch_bounds__(kHosBlock, MINB) dxm_hosford_tiled_kernel(const SmallStrainArgs a) {
+  __shared__ HosPark park;
   __shared__ unsigned s_queue[kHosTile];
   __shared__ unsigned s_count;
   const int64_t ntile = (a.count + kHosTile - 1) / kHosTile;
@@ -515,8 +635,8 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_tiled_kernel(const SmallSt
   for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    for (int sub = 0; sub < kHosTile / 128; ++sub) {
-      const int64_t loc = tile * kHosTile + sub * 128 + threadIdx.x;
+    for (int sub = 0; sub < kHosTile / kHosBlock; ++sub) {
+      const int64_t loc = tile * kHosTile + sub * kHosBlock + threadIdx.x;
       bool heavy = false;
       if (loc < a.count) {
         const int64_t i0 = a.start + loc;
@@ -527,7 +647,7 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_tiled_kernel(const SmallSt
         int n_iter;
         heavy = hosford_point<true, 0, VOCE>(io.lam, io.mu, io.sig0, io.H, io.dsu, io.b, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old,
                                        io.p_old, io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
-        if (!heavy) hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
+        if (!heavy) hos_finish_store(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
       }
       const unsigned bal = __ballot_sync(0xffffffffu, heavy);
       if (bal) {
@@ -540,21 +660,13 @@ __global__ void __launch_bounds__(128, 3) dxm_hosford_tiled_kernel(const SmallSt
     }
     __syncthreads();
     const unsigned total = s_count;
-    for (unsigned q = threadIdx.x; q < total; q += blockDim.x) {
-      const int64_t i0 = a.start + tile * kHosTile + (int64_t)s_queue[q];
-      HosPointIO io;
-      hos_load<true, VOCE>(a, i0, io);
-      double sig[6], epsp[6], ct21[21], p_new, resid;
-      bool flag, fail;
-      int n_iter;
-      hosford_point<false, AT, VOCE>(io.lam, io.mu, io.sig0, io.H, io.dsu, io.b, a.hos_a, a.hos_bound, io.eps, io.e_old, io.s_old, io.p_old,
-                               io.ep_old, sig, p_new, epsp, ct21, flag, n_iter, resid, fail);
-      hos_finish(a, i0, sig, p_new, epsp, ct21, flag, n_iter, resid, fail, acc);
-    }
+    for (unsigned q = threadIdx.x; q < total; q += blockDim.x)
+      hos_solve_point<AT, VOCE>(a, a.start + tile * kHosTile + (int64_t)s_queue[q], park, acc);
     __syncthreads();  // the queue is reused by the next tile
   }
   block_reduce_stats(acc, a.stats);
 }
+
 #endif  // kernels
 
 #ifdef __CUDACC__
@@ -565,6 +677,7 @@ struct HosLaunch {
   bool voce;   // the hardening law has a saturation term (sigu was set): general-law instantiation
   bool tiled;  // tiled kernel (stream + CTA-local candidate queue + packed local solves) instead of the fused one
   int tiles_per_cta;
+  int minb;  // resident CTAs per SM the register allocation targets: 4 (128 registers) or 3 (168); 0 = per-kernel default
 };
 int launch_hosford(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches);
 double hosford_bound(int a);

@@ -13,22 +13,32 @@ double hosford_bound(int a) {
 }
 
 namespace {
-template <int AT, bool VOCE>
-int launch_at(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches) {
+template <int AT, bool VOCE, int MINB>
+int launch_at2(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches) {
   if (cfg.tiled) {
     const int64_t ntile = (a.count + kHosTile - 1) / kHosTile;
-    dxm_hosford_tiled_kernel<AT, VOCE><<<(unsigned)(ntile < 1 ? 1 : ntile), 128, 0, cfg.stream>>>(a);
+    dxm_hosford_tiled_kernel<AT, VOCE, MINB><<<(unsigned)(ntile < 1 ? 1 : ntile), kHosBlock, 0, cfg.stream>>>(a);
     ++*launches;
     CK(cudaGetLastError());
     return 0;
   }
-  const int64_t ntile = (a.count + 127) / 128;
+  const int64_t ntile = (a.count + kHosBlock - 1) / kHosBlock;
   int64_t grid = (ntile + cfg.tiles_per_cta - 1) / cfg.tiles_per_cta;
   if (grid < 1) grid = 1;
-  dxm_hosford_kernel<AT, VOCE><<<(unsigned)grid, 128, 0, cfg.stream>>>(a);
+  dxm_hosford_kernel<AT, VOCE, MINB><<<(unsigned)grid, kHosBlock, 0, cfg.stream>>>(a);
   ++*launches;
   CK(cudaGetLastError());
   return 0;
+}
+
+template <int AT, bool VOCE>
+int launch_at(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches) {
+  // Registers: the fused kernel gains 6 % at 4 resident CTAs per SM (128 registers) now that only the Newton loop's own
+  // state crosses the loop; the tiled kernel, whose streaming phase shares the allocation, loses 4-13 % there and stays
+  // at 3 CTAs (168 registers) -- profiles/r02c_hosford_ab_minb_fused_warpqueue.json.  DXM_HOS_MINB=3|4 forces either.
+  const int minb = cfg.minb ? cfg.minb : (cfg.tiled ? 3 : 4);
+  if (minb == 3) return launch_at2<AT, VOCE, 3>(a, cfg, launches);
+  return launch_at2<AT, VOCE, 4>(a, cfg, launches);
 }
 }  // namespace
 
