@@ -55,6 +55,13 @@ SIGNATURES = {
          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(Stats)],
     ),
     "dxm_last_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Stats)]),
+    "dxm_enable_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "dxm_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "dxm_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "dxm_comm_size": (ctypes.c_int, []),
+    "dxm_comm_rank": (ctypes.c_int, []),
+    "dxm_comm_destroy": (ctypes.c_int, []),
+    "dxm_use_global_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "dxm_update": (ctypes.c_int, [ctypes.c_void_p]),
     "dxm_revert": (ctypes.c_int, [ctypes.c_void_p]),
     "dxm_enable_diagnostics": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 ]
 
 # translation units of the library (kernels live in the .cuh files they include)
-UNITS = ["dxm_api.cu", "dxm_hosford_api.cu", "dxm_fe_api.cu", "dxm_peaks.cu"]
+UNITS = ["dxm_api.cu", "dxm_hosford_api.cu", "dxm_fe_api.cu", "dxm_peaks.cu", "dxm_comm.cu"]
 
 
 def _nvcc():
@@ -68,7 +68,7 @@ def build_library(force=False, verbose=False):
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out + err)
         log += err
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB),
-           *[str(objdir / (u[:-3] + ".o")) for u in UNITS]]
+           *[str(objdir / (u[:-3] + ".o")) for u in UNITS], "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

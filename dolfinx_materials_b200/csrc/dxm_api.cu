@@ -19,6 +19,7 @@ namespace {
 constexpr int64_t kChunk = 1 << 19;  // points per pipeline chunk on the host path
 const char* kPropNames[kNProp] = {"E", "nu", "sig0", "H", "sigu", "b"};
 constexpr double kHosSplitMaxPlastic = 0.45;  // Hosford: fused kernel above this plastic fraction (previous call)
+constexpr int64_t kAutoTimingPoints = 1 << 18;  // kernel_ms events by default only where two event records are noise
 constexpr bool kHostMirrorDefault = false;  // A/B on the B200 box: profiles/ (DXM_HOST_MIRROR overrides)
 }  // namespace
 
@@ -123,9 +124,13 @@ int ensure_mirror_ring(dxm_handle* h) {
 template <int HARD, bool PERPOINT, int PPT, bool DIAG, int MINB = 2, bool COMPACT = false>
 int launch_small_strain(dxm_handle* h, const SmallStrainArgs& a) {
   const void* k = (const void*)dxm_small_strain_kernel<HARD, PERPOINT, PPT, DIAG, MINB, COMPACT>;
-  const int block = 256;
+  // Small batches (cfg1's meshes, per-rank shards of a strongly scaled solve) are latency-bound: spread them over the SMs
+  // in 64-point CTAs of one tile each instead of a few 4-tile CTAs (1e4 points: 10 CTAs x 4 sequential tiles = 26.7 us
+  // -> 157 CTAs x 1 tile, profiles/r02d_latency.json)
+  const bool small = !COMPACT && a.count <= (int64_t)h->num_sms * 1024;
+  const int block = small ? 64 : 256;
   const int64_t ntile = (a.count + (int64_t)block * PPT - 1) / ((int64_t)block * PPT);
-  const int grid = grid_for(k, block, 0, h->num_sms, ntile);
+  const int grid = small ? (int)ntile : grid_for(k, block, 0, h->num_sms, ntile);
   dxm_small_strain_kernel<HARD, PERPOINT, PPT, DIAG, MINB, COMPACT><<<grid, block, 0, h->stream>>>(a);
   LAUNCH_CHECK();
   return 0;
@@ -169,8 +174,21 @@ double prop(const dxm_handle* h, int i) {
   return h->uni[i];
 }
 
+// where the launch's statistics go; `finalize`: this is the call's last launch, its last CTA folds and publishes
+// (2: it is also the call's only launch)
+StatSink stat_sink(const dxm_handle* h, int finalize) {
+  StatSink k{};
+  k.blk = h->d_statblk;
+  // multi-GPU: the record is all-gathered first and stats_publish_kernel writes the host record
+  k.out = (h->global_stats && dxm_comm::size() > 1) ? h->d_rec : h->h_rec;
+  k.seq = h->seq;
+  k.n_points = (unsigned long long)h->last.n_points;
+  k.finalize = finalize;
+  return k;
+}
+
 // launches the constitutive kernel for points [start, start+count) on h->stream
-int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
+int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt, int finalize) {
   (void)dt;  // rate-independent behaviours (the reference's FE path never passes dt: quadrature_map.py:321)
   if (count <= 0) return 0;
   double* s0 = h->gen[h->i0];
@@ -200,7 +218,7 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
     a.dsu = std::isfinite(d) ? d : 0.0;
     a.b = prop(h, 5);
     for (int i = 0; i < kNProp; ++i) a.pp[i] = h->pp ? h->pp + (int64_t)i * ld : nullptr;
-    a.stats = h->d_stats;
+    a.stats = stat_sink(h, finalize);
     a.vote = h->vote;
     a.d_flag = h->d_flag;
     a.d_iter = h->d_iter;
@@ -247,7 +265,7 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
   }
   a.table = h->table;
   a.ntab = h->ntab;
-  a.stats = h->d_stats;
+  a.stats = stat_sink(h, finalize);
   a.vote = h->vote;
   a.d_flag = h->d_flag;
   a.d_iter = h->d_iter;
@@ -310,43 +328,125 @@ int next_event_pair(dxm_handle* h, cudaEvent_t** pair) {
   return 0;
 }
 
-int timed_update(dxm_handle* h, int64_t start, int64_t count, double dt) {
+// multi-GPU: folds the all-gathered per-rank records (SUM of counts and points, MAX of iterations and residual) into
+// the mapped host record.  One warp; launched on the handle's stream right after the collective.
+__global__ void stats_publish_kernel(const StatRecord* __restrict__ gathered, int nranks, StatRecord* host_rec,
+                                     unsigned long long seq) {
+  const int l = threadIdx.x;
+  unsigned long long a = 0, b = 0, c = 0, d = 0, n = 0;
+  for (int r = l; r < nranks; r += 32) {
+    unsigned long long w[kStatWords], ra, rb_, rc, rd, rn;
+    for (int i = 0; i < kStatWords; ++i) w[i] = gathered[r].w[i];
+    stat_decode(w, ra, rb_, rc, rd, rn);
+    a += ra;
+    b += rb_;
+    c = rc > c ? rc : c;
+    d = rd > d ? rd : d;
+    n += rn;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    n += __shfl_xor_sync(0xffffffffu, n, o);
+    unsigned long long c2 = __shfl_xor_sync(0xffffffffu, c, o);
+    c = c2 > c ? c2 : c;
+    unsigned long long d2 = __shfl_xor_sync(0xffffffffu, d, o);
+    d = d2 > d ? d2 : d;
+  }
+  if (l == 0) publish_record(host_rec, a, b, c, d, n, seq);
+}
+
+// one kernel launch of the call; `finalize` marks the last one (it publishes the statistics, and the in-stream
+// all-gather + publish of a multi-GPU run follow it)
+int timed_update(dxm_handle* h, int64_t start, int64_t count, double dt, int finalize) {
+  const bool timing = h->timing > 0 || (h->timing < 0 && h->last.n_points >= kAutoTimingPoints);
   cudaEvent_t* ev = nullptr;
-  if (next_event_pair(h, &ev)) return -1;
-  CK(cudaEventRecord(ev[0], h->stream));
-  if (launch_update(h, start, count, dt)) return -1;
-  CK(cudaEventRecord(ev[1], h->stream));
+  if (timing) {
+    if (next_event_pair(h, &ev)) return -1;
+    CK(cudaEventRecord(ev[0], h->stream));
+  }
+  if (launch_update(h, start, count, dt, finalize)) return -1;
+  if (timing) CK(cudaEventRecord(ev[1], h->stream));
+  if (finalize) {
+    h->finalize_launched = true;
+    if (h->global_stats && dxm_comm::size() > 1) {
+      if (dxm_comm::all_gather(h->d_rec, h->d_gather, sizeof(StatRecord), h->stream)) return -1;
+      stats_publish_kernel<<<1, 32, 0, h->stream>>>(h->d_gather, dxm_comm::size(), h->h_rec, h->seq);
+      LAUNCH_CHECK();
+    }
+  }
   return 0;
 }
 
+// Waits for the call's published record: a spin on one word of page-locked memory the kernel writes last -- no stream
+// synchronisation, no copy.  The stream is queried now and then so that a failed launch cannot hang the caller.
 int finish_stats(dxm_handle* h) {
   if (!h->stats_pending) return 0;
-  CK(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(StatSlot) * kStatSlots, cudaMemcpyDeviceToHost,
-                     h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  dxm_stats s{};
-  s.n_points = h->last.n_points;
-  unsigned long long rb = 0;
-  for (int i = 0; i < kStatSlots; ++i) {
-    s.n_plastic += (int64_t)h->h_stats[i].n_plastic;
-    s.n_fail += (int64_t)h->h_stats[i].n_fail;
-    s.max_iter = std::max<int64_t>(s.max_iter, (int64_t)h->h_stats[i].max_iter);
-    rb = std::max(rb, h->h_stats[i].max_resid_bits);
+  h->stats_pending = false;
+  if (!h->finalize_launched) {  // the call broke off before its last launch: nothing will be published
+    cudaStreamSynchronize(h->stream);
+    cudaMemsetAsync(h->d_statblk, 0, sizeof(StatBlock), h->stream);
+    return fail("dxm: the previous integrate call did not complete; its statistics are lost");
   }
+  const unsigned long long tag = h->seq & 0xffffull;
+  volatile unsigned long long* rec = h->h_rec->w;
+  unsigned long long w[kStatWords];
+  for (unsigned spin = 0;; ++spin) {
+    bool ready = true;
+    for (int i = 0; i < kStatWords; ++i) {
+      w[i] = rec[i];
+      ready = ready && (w[i] >> 48) == tag;
+    }
+    if (ready) break;
+    if ((spin & 0x3ff) == 0x3ff) {
+      const cudaError_t q = cudaStreamQuery(h->stream);
+      if (q == cudaSuccess) {
+        ready = true;
+        for (int i = 0; i < kStatWords; ++i) {
+          w[i] = rec[i];
+          ready = ready && (w[i] >> 48) == tag;
+        }
+        if (ready) break;
+        return fail("dxm: the update kernel finished without publishing its statistics");
+      }
+      if (q != cudaErrorNotReady) CK(q);
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  dxm_stats s{};
+  unsigned long long np, nf, mi, rb, npts;
+  stat_decode(w, np, nf, mi, rb, npts);
+  s.n_points = (int64_t)npts;
+  s.n_plastic = (int64_t)np;
+  s.n_fail = (int64_t)nf;
+  s.max_iter = (int64_t)mi;
   std::memcpy(&s.max_residual, &rb, sizeof(double));
   double ms = 0;
-  for (int i = 0; i + 1 < h->n_ev_used; i += 2) {
-    float t = 0;
-    CK(cudaEventElapsedTime(&t, h->ev_k[i], h->ev_k[i + 1]));
-    ms += t;
+  if (h->n_ev_used > 0) {
+    // the record is published by the kernel's last CTA: the end event completes within a microsecond -- spin on it
+    // rather than sleep in cudaEventSynchronize
+    for (;;) {
+      const cudaError_t q = cudaEventQuery(h->ev_k[h->n_ev_used - 1]);
+      if (q == cudaSuccess) break;
+      if (q != cudaErrorNotReady) CK(q);
+    }
+    for (int i = 0; i + 1 < h->n_ev_used; i += 2) {
+      float t = 0;
+      CK(cudaEventElapsedTime(&t, h->ev_k[i], h->ev_k[i + 1]));
+      ms += t;
+    }
   }
   s.kernel_ms = ms;
   h->last = s;
+  // the launch heuristics (FeFp compaction, Hosford fused / tiled) key on the plastic fraction of the previous call
   h->prev_plastic = s.n_plastic;
   h->prev_points = s.n_points;
-  h->stats_pending = false;
   return 0;
 }
+
 
 }  // namespace
 
@@ -400,8 +500,10 @@ void free_handle(dxm_handle* h) {
   cudaFree(h->ct);
   cudaFree(h->pp);
   cudaFree(h->table);
-  cudaFree(h->d_stats);
-  cudaFreeHost(h->h_stats);
+  cudaFree(h->d_statblk);
+  cudaFree(h->d_rec);
+  cudaFree(h->d_gather);
+  cudaFreeHost(h->h_rec);
   for (int s = 0; s < 2; ++s) {
     cudaFree(h->d_in[s]);
     cudaFree(h->d_out[s]);
@@ -434,7 +536,7 @@ void release_handle(dxm_handle* h) {
 extern "C" {
 
 const char* dxm_last_error(void) { return g_err.c_str(); }
-const char* dxm_version(void) { return "dxm-b200 0.1 (sm_100a, fp64, -fmad=false)"; }
+const char* dxm_version(void) { return "dxm-b200 0.2 (sm_100a, fp64, hand-placed fma, -fmad=false)"; }
 int64_t dxm_launch_count(void) { return g_launches.load(); }
 
 int dxm_device_count(void) {
@@ -514,9 +616,15 @@ int dxm_create(int behaviour, int device, int64_t n, dxm_handle** out) {
   }
   CKH(cudaMalloc(&h->ct, sizeof(double) * h->nct_store * h->ld));
   CKH(cudaMemset(h->ct, 0, sizeof(double) * h->nct_store * h->ld));
-  CKH(cudaMalloc(&h->d_stats, sizeof(StatSlot) * kStatSlots));
-  CKH(cudaMemset(h->d_stats, 0, sizeof(StatSlot) * kStatSlots));
-  CKH(cudaMallocHost(&h->h_stats, sizeof(StatSlot) * kStatSlots));
+  CKH(cudaMalloc(&h->d_statblk, sizeof(StatBlock)));
+  CKH(cudaMemset(h->d_statblk, 0, sizeof(StatBlock)));
+  CKH(cudaMalloc(&h->d_rec, sizeof(StatRecord)));
+  CKH(cudaMemset(h->d_rec, 0, sizeof(StatRecord)));
+  CKH(cudaHostAlloc(&h->h_rec, sizeof(StatRecord), cudaHostAllocMapped | cudaHostAllocPortable));
+  std::memset(h->h_rec, 0, sizeof(StatRecord));
+  h->seq = 0x100;  // tags start away from the zero-filled record
+  env = std::getenv("DXM_TIMING");
+  h->timing = env ? std::atoi(env) : -1;
   CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   CKH(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
   CKH(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
@@ -787,10 +895,12 @@ static int integrate_impl(dxm_handle* h, int64_t start, int64_t count, const dou
   if (!whole && mem != DXM_MEM_HOST && !(mem == DXM_MEM_RESIDENT && !flux && !isv && !ct))
     return fail("dxm_integrate_range: partial ranges take host arrays, or resident gradients without outputs");
   if (finish_stats(h)) return -1;  // drain a previous asynchronous call
-  CK(cudaMemsetAsync(h->d_stats, 0, sizeof(StatSlot) * kStatSlots, h->stream));
   h->n_ev_used = 0;
   h->last = dxm_stats{};
   h->last.n_points = count;
+  ++h->seq;
+  h->finalize_launched = false;
+  h->stats_pending = true;  // from here on the accumulation slots may be dirty: finish_stats() cleans up after a failure
   double* s1 = h->gen[1 - h->i0];
   const int64_t ld = h->ld, n = count;
   const int isv_row = h->ngrad + h->nflux;
@@ -799,7 +909,7 @@ static int integrate_impl(dxm_handle* h, int64_t start, int64_t count, const dou
   if (mem == DXM_MEM_RESIDENT || mem == DXM_MEM_DEVICE) {
     if (mem == DXM_MEM_DEVICE)
       if (launch_aos_to_soa(h, h->stream, grad, h->ngrad, 0, s1, 0, n, h->ngrad)) return -1;
-    if (timed_update(h, start, n, dt)) return -1;
+    if (timed_update(h, start, n, dt, 2)) return -1;
     h->s1_valid = true;
     if (any_out) {
       if (out_mem == DXM_MEM_DEVICE) {
@@ -811,7 +921,6 @@ static int integrate_impl(dxm_handle* h, int64_t start, int64_t count, const dou
           return -1;
         if (ct && launch_soa_to_aos(h, h->stream, h->ct, 0, ct, h->nct, 0, n, h->nct, h->nct_store != h->nct)) return -1;
       } else if (out_mem == DXM_MEM_HOST) {
-        h->stats_pending = true;
         if (finish_stats(h)) return -1;
         const dxm_stats keep = h->last;
         if (flux && dxm_get_state(h, 1, h->fields[1].name, flux, DXM_MEM_HOST)) return -1;
@@ -873,7 +982,7 @@ static int integrate_impl(dxm_handle* h, int64_t start, int64_t count, const dou
       CK(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
       if (launch_aos_to_soa(h, h->stream, h->d_in[b], h->ngrad, 0, s1, start + s, m, h->ngrad)) return -1;
       CK(cudaEventRecord(h->ev_in_free[b], h->stream));
-      if (timed_update(h, start + s, m, dt)) return -1;
+      if (timed_update(h, start + s, m, dt, s + CH >= n ? (n <= CH ? 2 : 1) : 0)) return -1;
       if (any_out) {
         CK(cudaStreamWaitEvent(h->stream, h->ev_out_free[b], 0));
         double* o = h->d_out[b];
@@ -918,7 +1027,6 @@ static int integrate_impl(dxm_handle* h, int64_t start, int64_t count, const dou
   } else {
     return fail("dxm_integrate: bad mem kind");
   }
-  h->stats_pending = true;
   if (!stats) return 0;  // asynchronous: fetch later with dxm_last_stats
   if (finish_stats(h)) return -1;
   *stats = h->last;
@@ -947,6 +1055,24 @@ int dxm_update(dxm_handle* h) {
 int dxm_revert(dxm_handle* h) {
   if (!h) return fail("dxm_revert: NULL handle");
   h->s1_valid = false;  // s1 <- s0
+  return 0;
+}
+
+int dxm_use_global_stats(dxm_handle* h, int on) {
+  if (!h) return fail("dxm_use_global_stats: NULL handle");
+  if (set_device(h)) return -1;
+  if (finish_stats(h)) return -1;
+  if (on) {
+    if (dxm_comm::size() < 2) return fail("dxm_use_global_stats: no multi-rank communicator (dxm_comm_init)");
+    if (!h->d_gather) CK(cudaMalloc(&h->d_gather, sizeof(StatRecord) * dxm_comm::size()));
+  }
+  h->global_stats = on != 0;
+  return 0;
+}
+
+int dxm_enable_timing(dxm_handle* h, int mode) {
+  if (!h) return fail("dxm_enable_timing: NULL handle");
+  h->timing = mode;
   return 0;
 }
 

@@ -30,7 +30,7 @@ struct FeFpArgs {
   bool perpoint;
   double E, mu, kappa, sig0, H, dsu, b;
   const double* pp[6];  // per-point E, nu, sig0, H, sigu, b
-  StatSlot* stats;
+  StatSink stats;  // per-call statistics (dxm_canon.cuh)
   int vote;
   uint8_t* d_flag;
   int32_t* d_iter;
@@ -498,7 +498,9 @@ inline const void* fefp_kernel_ptr(bool perpoint, bool diag, bool compact = fals
 
 inline int launch_fefp(const FeFpArgs& a, bool diag, bool compact, int num_sms, cudaStream_t stream,
                        std::atomic<long long>* launches, std::string* err) {
-  const int block = 128;
+  // small batches: 64-point CTAs of one tile each over all SMs (latency-bound; see launch_small_strain)
+  const bool small = !compact && a.count <= (int64_t)num_sms * 128;
+  const int block = small ? 64 : 128;
   const int64_t ntile = (a.count + block - 1) / block;
   // DXM_FEFP_MINB: resident CTAs per SM the register allocation targets (3: <=168 regs, 4: <=128, 5: <=96)
   static const int minb = [] {
@@ -518,7 +520,7 @@ inline int launch_fefp(const FeFpArgs& a, bool diag, bool compact, int num_sms, 
     const int v = e ? std::atoi(e) : 2;
     return v > 0 ? v : 2;
   }();
-  int64_t grid = mult > 0 ? (int64_t)mult * num_sms : (ntile + tpb - 1) / tpb;
+  int64_t grid = small ? ntile : mult > 0 ? (int64_t)mult * num_sms : (ntile + tpb - 1) / tpb;
   if (grid > ntile) grid = ntile;
   if (grid > 0x7fffffff) grid = 0x7fffffff;
   if (grid < 1) grid = 1;

@@ -22,10 +22,13 @@ int launch_at2(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches) {
     CK(cudaGetLastError());
     return 0;
   }
-  const int64_t ntile = (a.count + kHosBlock - 1) / kHosBlock;
-  int64_t grid = (ntile + cfg.tiles_per_cta - 1) / cfg.tiles_per_cta;
+  // small batches: 32-point CTAs of one tile each over all SMs (latency-bound; see launch_small_strain in dxm_api.cu)
+  const bool small = a.count <= (int64_t)cfg.num_sms * 128;
+  const int block = small ? 32 : kHosBlock;
+  const int64_t ntile = (a.count + block - 1) / block;
+  int64_t grid = small ? ntile : (ntile + cfg.tiles_per_cta - 1) / cfg.tiles_per_cta;
   if (grid < 1) grid = 1;
-  dxm_hosford_kernel<AT, VOCE, MINB><<<(unsigned)grid, kHosBlock, 0, cfg.stream>>>(a);
+  dxm_hosford_kernel<AT, VOCE, MINB><<<(unsigned)grid, block, 0, cfg.stream>>>(a);
   ++*launches;
   CK(cudaGetLastError());
   return 0;

@@ -67,9 +67,15 @@ struct dxm_handle {
   double* table = nullptr;  // DXM_J2_TABLE: device [3][ntab] = p_k, sig_k, slope_k
   int ntab = 0;
   int hos_a = 10;  // DXM_HOSFORD_LINEAR: exponent (the demo's value by default)
-  // statistics
-  dxm::StatSlot* d_stats = nullptr;
-  dxm::StatSlot* h_stats = nullptr;  // pinned
+  // statistics (dxm_canon.cuh): accumulated, folded and published by the update kernel itself
+  dxm::StatBlock* d_statblk = nullptr;   // 32 accumulation slots + ticket, cleared by the kernel that folds them
+  dxm::StatRecord* d_rec = nullptr;      // this rank's record on the device (source of the in-stream all-gather)
+  dxm::StatRecord* d_gather = nullptr;   // [nranks] records after the all-gather
+  dxm::StatRecord* h_rec = nullptr;      // page-locked, mapped: the published record, polled by the host
+  unsigned long long seq = 0;            // sequence number of the last call launched on this handle
+  bool finalize_launched = false;        // the call's last launch (the one that publishes) has been enqueued
+  bool global_stats = false;             // reduce over the ranks of the library's communicator (dxm_comm_init)
+  int timing = -1;                       // kernel_ms events: -1 auto (batches >= 262144 points), 0 never, 1 always
   dxm_stats last{};
   bool stats_pending = false;
   // streams / events
@@ -99,6 +105,13 @@ struct dxm_handle {
   int64_t prev_plastic = 0, prev_points = 0;
   std::atomic<int> refs{1};
 };
+
+// the library's NCCL communicator (dxm_comm.cu): in-stream all-gather of the statistics records, nothing else
+namespace dxm_comm {
+int size();
+int rank();
+int all_gather(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t stream);
+}  // namespace dxm_comm
 
 inline int set_device(const dxm_handle* h) {
   CK(cudaSetDevice(h->device));

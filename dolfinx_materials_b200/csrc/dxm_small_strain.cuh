@@ -46,7 +46,7 @@ struct SmallStrainArgs {
   int ntab;
   int hos_a;  // DXM_HOSFORD_LINEAR: exponent of the Hosford criterion (even integer)
   double hos_bound;  // ... and sup sigma_eq / seq_Mises (1 + 1e-9): points below it are finished without a local solve
-  StatSlot* stats;
+  StatSink stats;  // per-call statistics (dxm_canon.cuh)
   int vote;  // 1: warp-vote (__any_sync) Newton loop exit, 0: per-lane exit (A/B knob DXM_VOTE)
   // optional diagnostics (DIAG == true)
   uint8_t* d_flag;

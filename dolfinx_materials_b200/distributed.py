@@ -53,6 +53,35 @@ def shard_start(n_per_rank, rank):
     return int(n_per_rank) * int(rank)
 
 
+def init_stats_comm(group=None, device=None):
+    """Create the library's own NCCL communicator over the ranks of the (already initialised) ``torch.distributed``
+    process group: rank 0 draws the unique id, ``broadcast_object_list`` carries it (works on gloo and nccl groups),
+    every rank joins.  After this ``CUDAMaterial.use_global_stats()`` makes a material's per-call statistics global
+    with one all-gather on the material's own stream -- no host-side collective, no synchronisation.
+    Returns the communicator size (1: nothing was created)."""
+    import ctypes
+
+    import torch.distributed as dist
+
+    from . import _lib
+    from ._lib import check
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 1
+    lib = _lib.load()
+    if lib.dxm_comm_size() > 1:
+        return lib.dxm_comm_size()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = ctypes.create_string_buffer(128)
+    if rank == 0:
+        check(lib.dxm_comm_unique_id(buf), "dxm_comm_unique_id")
+    box = [bytes(buf.raw)]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ident = ctypes.create_string_buffer(box[0], 128)
+    check(lib.dxm_comm_init(ident, rank, world, default_device() if device is None else int(device)), "dxm_comm_init")
+    return lib.dxm_comm_size()
+
+
 def allreduce_stats(stats, group=None, device=None):
     """Reduce :class:`IntegrationStats` over the process group: counts are summed, iteration count
     and residual are maximised; ``kernel_ms`` becomes the max over ranks."""

@@ -238,6 +238,10 @@ class CUDAMaterial:
         self._h = h
         self._n = int(ngauss)
         self._fin = weakref.finalize(self, lib.dxm_destroy, h)
+        # the resident call is latency-critical for small batches: bound function and reusable statistics struct
+        self._c_integrate = lib.dxm_integrate
+        self._c_stats = Stats()
+        self._c_stats_ref = ctypes.byref(self._c_stats)
         self._out = None
         self.data_manager = DeviceDataManager(self, ngauss)
         for key, value in self.material_properties.items():
@@ -295,8 +299,10 @@ class CUDAMaterial:
         return self._out
 
     def _finish(self, rc, stats):
-        check(rc, "dxm_integrate")
-        self.last_stats = IntegrationStats.from_c(stats)
+        if rc < 0:
+            check(rc, "dxm_integrate")
+        self.last_stats = IntegrationStats(stats.n_points, stats.n_plastic, stats.n_fail, stats.max_iter,
+                                           stats.max_residual, stats.kernel_ms)
         if rc > 0 and self.warn_on_failure:
             warnings.warn(
                 f"{rc} Gauss point(s) failed their local constitutive solve "
@@ -398,15 +404,13 @@ class CUDAMaterial:
     def integrate_resident(self, dt=0, wait=True):
         """Run the update on gradients already written into ``gradient_buffer()``; results stay in
         the SoA device buffers (``device_view``).  ``wait=False`` returns without synchronising."""
-        self._require_handle()
-        lib = _lib.load()
-        stats = Stats()
-        rc = lib.dxm_integrate(self._h, None, MEM_RESIDENT, float(dt), None, None, None, MEM_RESIDENT,
-                               ctypes.byref(stats) if wait else None)
+        if self._h is None:
+            self._require_handle()
         if wait:
-            self._finish(rc, stats)
+            rc = self._c_integrate(self._h, None, MEM_RESIDENT, dt, None, None, None, MEM_RESIDENT, self._c_stats_ref)
+            self._finish(rc, self._c_stats)
             return self.last_stats
-        check(rc, "dxm_integrate")
+        check(self._c_integrate(self._h, None, MEM_RESIDENT, dt, None, None, None, MEM_RESIDENT, None), "dxm_integrate")
         return None
 
     def fetch_stats(self):
@@ -459,6 +463,17 @@ class CUDAMaterial:
     def set_stream(self, cuda_stream):
         self._require_handle()
         check(_lib.load().dxm_set_stream(self._h, ctypes.c_void_p(cuda_stream)), "dxm_set_stream")
+
+    def enable_timing(self, mode=1):
+        """``kernel_ms`` of the statistics: 1 always, 0 never, -1 only for batches of >= 262144 points (default)."""
+        self._require_handle()
+        check(_lib.load().dxm_enable_timing(self._h, int(mode)), "dxm_enable_timing")
+
+    def use_global_stats(self, on=True):
+        """Statistics reduced over all ranks (``distributed.init_stats_comm`` first): one in-stream NCCL all-gather of
+        the 64-byte record after the update kernel; every rank must then call ``integrate`` on this material."""
+        self._require_handle()
+        check(_lib.load().dxm_use_global_stats(self._h, int(on)), "dxm_use_global_stats")
 
     def enable_diagnostics(self, on=True):
         self._require_handle()

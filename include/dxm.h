@@ -117,9 +117,30 @@ int dxm_integrate(dxm_handle* h, const double* grad, int mem, double dt, double*
 int dxm_integrate_range(dxm_handle* h, int64_t start, int64_t count, const double* grad, int mem, double dt,
                         double* flux, double* isv, double* ct, int out_mem, dxm_stats* stats);
 
-/* statistics of the last dxm_integrate (synchronises the handle's stream); use it after a call made
- * with stats == NULL, which returns without waiting for the device */
+/* statistics of the last dxm_integrate; use it after a call made with stats == NULL, which returns without waiting for
+ * the device.  The update kernel folds and publishes the record itself into page-locked mapped memory: reading it is a
+ * spin on one word, with no stream synchronisation, copy or memset on the host side of a call (this fused check replaces
+ * the three host NaN scans of quadrature_map.py:322-324). */
 int dxm_last_stats(dxm_handle* h, dxm_stats* stats);
+
+/* kernel_ms of dxm_stats costs two event records per launch: mode -1 = only for batches >= 262144 points (default),
+ * 0 = never, 1 = always */
+int dxm_enable_timing(dxm_handle* h, int mode);
+
+/* Multi-GPU statistics: one process per GPU, Gauss points sharded by contiguous cell blocks, no exchange in
+ * the update itself.  The library owns one NCCL communicator per process, used only to all-gather the 64-byte statistics
+ * record of each rank ON THE HANDLE'S STREAM right after the update kernel (SUM of failed / plastic counts, MAX of
+ * iterations / residual, folded by a one-warp kernel into the mapped host record): no host synchronisation is added.
+ * Replaces what `MPI.COMM_WORLD.allreduce` of a failure flag would do around QuadratureMap.update under dolfinx.
+ *   dxm_comm_unique_id : rank 0 fills a 128-byte id, the caller broadcasts it (torch.distributed / MPI_Bcast)
+ *   dxm_comm_init      : collective over all ranks; device = this rank's GPU
+ *   dxm_use_global_stats(h, 1) : this handle's dxm_stats become global (every rank must then call dxm_integrate on it) */
+int dxm_comm_unique_id(void* id128);
+int dxm_comm_init(const void* id128, int rank, int nranks, int device);
+int dxm_comm_size(void);
+int dxm_comm_rank(void);
+int dxm_comm_destroy(void);
+int dxm_use_global_stats(dxm_handle* h, int on);
 
 /* DataManager.update() / revert() (generic.py:212-216, jaxmat.py:39-43): O(1) generation swap */
 int dxm_update(dxm_handle* h);
