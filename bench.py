@@ -13,16 +13,20 @@ the state reached after the first three (exactly what each global Newton iterati
 quadrature_map.py:320-321), including the device-side statistics reduction and, for N > 1, the NCCL
 all-reduce of the failure / active-set counts and residual maximum.
 
-`value`  : device-resident throughput (inputs and outputs stay in HBM, SoA).
-`e2e`    : same metric through the reference-facing call `CUDAMaterial.integrate(host gradients)` ->
-           host (flux, isv, Ct): pinned host buffers, H2D + D2H inside the timed region.
-`roofline`: algorithmic bytes (592 B / Gauss point: the full 36-entry tangent of the reference boundary) /
-           average kernel time measured with CUDA events on the launching stream inside the timed region, against
-           MEASURED_PEAKS.json hbm_gbs.  The kernel stores each unique entry of the symmetric tangent once
-           (472 B / point of DRAM traffic, `traffic`), so `frac` can exceed 1; `moved_frac` is the fraction of the
-           HBM peak the bytes actually moved account for.
-`cpu_baseline`: the numpy oracle timed on the box's host cores on a bounded sample of the same workload
-           (`c_port`: the plain-C oracle on the same cores, for scale).
+`value`  : device-resident throughput (inputs and outputs stay in HBM, SoA); `sustained` repeats it for >= 3 s
+           (the timed region of `value` is a fraction of a second: a burst).
+`e2e`    : same metric, SAME number of points, through the reference-facing call with host arrays in and out
+           (`CUDAMaterial.integrate_range_into`, the ranged form of `integrate`: the 1e8 points cross the boundary in
+           ranges of `e2e_range_points`, gradients from a page-locked host array, flux / isv / full 36-entry tangent
+           into a page-locked window): H2D + D2H inside the timed region.  `e2e_exchange` is the drop-in path proper,
+           `QuadratureExchange.update` (what `QuadratureMap.update` calls per Newton iteration: flux + tangent to the
+           host, internal state stays on the GPU).
+`roofline`: the dominant kernel against MEASURED_PEAKS.json hbm_gbs, kernel time measured with CUDA events on the
+           launching stream inside the timed region.  `frac` counts the bytes the kernel MOVES (472 B / Gauss point:
+           25 doubles read, 34 written -- the symmetric tangent is stored once, 21 of its 36 entries);
+           `algorithmic_frac` counts SURVEY 8(d)'s 592 B (the reference boundary's full tangent) and can exceed 1.
+`cpu_baseline`: the plain-C oracle (the compiled CPU path: the reference's own back-end is XLA-compiled JAX) on all host
+           threads, on a bounded sample of the same workload; `numpy_port`: the numpy oracle on one process per core.
 """
 
 import argparse
@@ -138,10 +142,9 @@ class CpuArm:
             p.join(timeout=10)
 
 
-def c_port_rate(cores, points_per_core=400_000, passes=3):
-    """The plain-C restatement of the same update (oracle/c, gcc -O2 -ffp-contract=off, bit-identical to the numpy
-    oracle) on `cores` threads: one pass at increment KINC from the state after KINC - 1 increments.  Reported next
-    to the numpy figure because a compiled CPU path (the reference's JAX-CPU back-end is one) sits between the two."""
+def c_port_steps(cores, steps, warmup, points_per_core):
+    """`steps` timed passes of the plain-C oracle over a fixed sample on `cores` threads (state after KINC - 1
+    increments built once, untimed); returns (seconds, points per step, plastic fraction)."""
     from oracle import cport
     from oracle import small_strain as ss
     from oracle import synth
@@ -152,44 +155,48 @@ def c_port_rate(cores, points_per_core=400_000, passes=3):
     for k in range(1, KINC):
         st = ss.advance(cport.small_strain(synth.strain(n, SEED, AMP, k, KINC), st, PROPS))
     eps = synth.strain(n, SEED, AMP, KINC, KINC)
-    best = None
-    for _ in range(passes):
-        t0 = time.perf_counter()
+    for _ in range(warmup):
+        cport.small_strain(eps, st, PROPS)
+    t0 = time.perf_counter()
+    for _ in range(steps):
         out = cport.small_strain(eps, st, PROPS)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return {"value": n / best, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {n} points of the same workload, plain-C oracle on {cores} threads, best of {passes} passes at increment {KINC}/{KINC}",
-            "sample_plastic_fraction": float(out["flag"].mean())}
+    return time.perf_counter() - t0, n, float(out["flag"].mean())
+
+
+def numpy_port_rate(arm, budget_s=1.5):
+    """The numpy oracle on one process per core (workers forked before CUDA is touched): a bounded sample, one timed pass."""
+    cores = arm.cores
+    rate = arm.prepare(1)
+    cpc = max(1, min(4, int(rate * budget_s / arm.chunk)))
+    if cpc > 1:
+        arm.prepare(cpc)
+    arm.step()
+    wall, pts, res = arm.step()
+    arm.close()
+    return {"value": pts / wall, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {pts} points of the same workload ({cores} procs x {cpc} chunks x {arm.chunk}), numpy oracle, one pass at increment {KINC}/{KINC}",
+            "sample_plastic_fraction": sum(r[0] for r in res) / pts}
 
 
 def run_reference(args):
+    """CPU arm: the path on the box's host cores with all the threads it can use.  The reference's own back-end for this
+    path (jaxmat on JAX-CPU: XLA-compiled) is not installable offline, so the arm times the oracle -- its COMPILED
+    restatement (oracle/c, gcc -O2 -mfma, one thread per core), which is the fair stand-in for a compiled CPU path
+    and 6-7x faster than the numpy restatement (reported beside it)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # the CPU arm runs once per box
     cores = os.cpu_count() or 1
-    arm = CpuArm(cores)
-    # size the sample from a short untimed probe so that steps+warmup stay within ~2 minutes
-    rate = arm.prepare(1)  # GP/s per core, measured while building the state
-    budget = min(3.0, 100.0 / max(1, args.steps + args.warmup))
-    cpc = max(1, min(8, int(rate * budget / arm.chunk)))
-    if cpc > 1:
-        arm.prepare(cpc)
-    for _ in range(args.warmup):
-        arm.step()
-    t = 0.0
-    pts = 0
-    for _ in range(args.steps):
-        w, p, _ = arm.step()
-        t += w
-        pts += p
-    arm.close()
     try:
-        c_port = c_port_rate(cores)
-    except Exception as e:  # noqa: BLE001 - the C figure is an extra, the numpy arm is the line's value
-        c_port = {"unavailable": str(e)[:200]}
-    value = pts / t
-    sample = f"{pts // args.steps} points/step ({cores} procs x {cpc} chunks x {arm.chunk}), numpy oracle, increment {KINC}/{KINC} from the state after {KINC - 1} increments"
+        numpy_port = numpy_port_rate(CpuArm(cores))
+    except Exception as e:  # noqa: BLE001 - an extra; the C arm is the line's value
+        numpy_port = {"unavailable": str(e)[:200]}
+    # each step: a bounded sample sized so that steps + warmup stay within ~2 minutes
+    ppc = int(max(50_000, min(1_000_000, 2.5e6 * 100.0 / max(1, args.steps + args.warmup) / 25)))
+    t, pts, frac = c_port_steps(cores, args.steps, args.warmup, ppc)
+    value = pts * args.steps / t
+    sample = (f"{pts} points/step ({cores} threads x {ppc}), plain-C oracle (gcc -O2 -mfma -ffp-contract=off), increment "
+              f"{KINC}/{KINC} from the state after {KINC - 1} increments")
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -205,10 +212,11 @@ def run_reference(args):
         "dtype": "f64",
         "data": "synthetic",
         "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "c_port": c_port},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "sample_plastic_fraction": frac, "numpy_port": numpy_port},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference CPU path = numpy port of the reference algorithm (oracle/); the reference's own jaxmat/JAX back-end is not installable offline (DESIGN.md)",
+        "note": "reference CPU path = compiled (plain-C) port of the reference algorithm (oracle/c) on all host threads; the reference's own jaxmat/JAX back-end is not installable offline (DESIGN.md)",
     }
     print(json.dumps(line), flush=True)
 
@@ -281,8 +289,10 @@ def workload_config(args, world):
         "properties": PROPS,
         "history": f"counter-based recipe seed {SEED}, amp {AMP}, increment {KINC}/{KINC} after {KINC - 1} state updates",
         "l2": "inputs >> L2 (47.2 GB touched per step per GPU), no flush needed",
-        "parallelism": f"points sharded over {world} GPU(s), no data-path collective; NCCL all-reduce of 4 statistics per step",
-        "e2e_points_per_gpu": int(args.e2e_n),
+        "parallelism": f"points sharded over {world} GPU(s), no data-path collective; in-stream NCCL all-gather of the 64-byte statistics record per step",
+        "e2e_points_per_gpu": int(min(args.e2e_n, args.n)),
+        "e2e_range_points": int(min(args.e2e_range, args.e2e_n, args.n)),
+        "exchange_points_per_gpu": int(min(args.exchange_n, args.e2e_n, args.n)),
     }
 
 
@@ -327,7 +337,7 @@ def run_ours(args):
 
     import dolfinx_materials_b200 as jm
     from dolfinx_materials_b200 import _lib, build
-    from dolfinx_materials_b200.distributed import allreduce_stats, shard_start
+    from dolfinx_materials_b200.distributed import shard_start
     from dolfinx_materials_b200.material import PinnedArray
 
     rank = int(os.environ.get("RANK", "0"))
@@ -373,110 +383,176 @@ def run_ours(args):
         m.data_manager.update()
     m.synth_gradients(SEED, AMP, KINC, KINC, start=start)
 
+    if world > 1:
+        # statistics reduced over the ranks IN-STREAM: the library's own NCCL communicator all-gathers the 64-byte record
+        # right after the update kernel (no host-side collective, no synchronisation added)
+        from dolfinx_materials_b200.distributed import init_stats_comm
+
+        init_stats_comm()
+        m.use_global_stats()
+    m.enable_timing(1)
+
     def step():
-        s = m.integrate_resident()
-        return allreduce_stats(s) if world > 1 else s
+        return m.integrate_resident()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(steps):
+        """`steps` passes bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks"""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kernel_ms = []
+        barrier()
+        ev0.record(stream)
+        for _ in range(steps):
+            st = step()
+            kernel_ms.append(st.kernel_ms)
+        ev1.record(stream)
+        barrier()
+        ms_total, kms = ev0.elapsed_time(ev1), sum(kernel_ms) / len(kernel_ms)
+        if world > 1:
+            t = torch.tensor([ms_total, kms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_total, kms = t.tolist()
+        return ms_total, kms, st
+
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.start()
     launches0 = lib.dxm_launch_count()
-    kernel_ms = []
-    ev0.record(stream)
-    for _ in range(args.steps):
-        s = step()
-        kernel_ms.append(m.last_stats.kernel_ms)
-    ev1.record(stream)
-    barrier()
+    ms_total, kms, s = timed(args.steps)
     launches = lib.dxm_launch_count() - launches0
     clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms_total, sum(kernel_ms) / len(kernel_ms)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, kms = t.tolist()
-    else:
-        kms = sum(kernel_ms) / len(kernel_ms)
     ms_per_step = ms_total / args.steps
     value = world * n / (ms_per_step * 1e-3)
 
-    # ---- end to end through the reference-facing call (host buffers) ---------------------------
-    ne = int(min(args.e2e_n, n))
-    e2e = None
+    # ---- the same step repeated for >= args.sustain seconds (power / clock steady state) -------------------------
+    sustained = None
+    if args.sustain > 0:
+        nsus = max(args.steps, int(args.sustain * 1e3 / ms_per_step) + 1)
+        sampler2 = ClockSampler(local)
+        sampler2.start()
+        ms_sus, kms_sus, _ = timed(nsus)
+        sustained = {"value": world * n * nsus / (ms_sus * 1e-3), "unit": UNIT, "steps": nsus, "seconds": ms_sus * 1e-3,
+                     "ms_per_step": ms_sus / nsus, "kernel_ms": kms_sus, "clocks": sampler2.stop()}
+
+    # ---- end to end through the reference-facing call (host buffers), on the SAME points ---------------------------
+    # The handle's s1 holds increment KINC's gradients; they are copied to a page-locked host array once (untimed) and
+    # every timed step sends all of them back through the host boundary: H2D of the gradients, update, D2H of flux,
+    # internal state and the full 36-entry tangent into a page-locked window of `e2e_range` points.
+    e2e = e2e_x = None
+    ne = int(min(args.e2e_n, n)) if args.e2e_n > 0 else 0
     if ne > 0:
-        me = jm.CUDAMaterial(beh, device=local)
-        me.set_data_manager(ne)
-        # same history on the e2e points: state after 3 increments, then the timed call repeats increment 4
-        for k in range(1, KINC):
-            me.synth_gradients(SEED, AMP, k, KINC, start=start)
-            me.integrate_resident()
-            me.data_manager.update()
-        me.synth_gradients(SEED, AMP, KINC, KINC, start=start)
-        me.integrate_resident()
+        m.enable_timing(-1)
+        if world > 1:
+            m.use_global_stats(False)
+        rng_pts = int(min(args.e2e_range, ne)) & ~1
         grads = PinnedArray((ne, 6))
-        grads.array[...] = me.device_view("strain").T.cpu().numpy()
-        e_steps = max(2, min(args.steps, 5))
-        me.integrate(grads.array)  # warm-up: allocates staging + pinned outputs
+        gview = m.device_view("strain")
+        for lo in range(0, ne, 1 << 24):  # transpose on the device in slabs, copy down
+            hi = min(ne, lo + (1 << 24))
+            grads.array[lo:hi] = gview[:, lo:hi].T.contiguous().cpu().numpy()
+        flux, isv, ct = PinnedArray((rng_pts, 6)), PinnedArray((rng_pts, 7)), PinnedArray((rng_pts, 36))
+
+        def e2e_step():
+            nfail = 0
+            for lo in range(0, ne, rng_pts):
+                c = min(rng_pts, ne - lo)
+                st = m.integrate_range_into(lo, c, grads.array[lo:lo + c], flux.array[:c], isv.array[:c], ct.array[:c])
+                nfail += st.n_fail
+            return nfail
+
+        e_steps = max(2, min(args.steps, 3))
+        e2e_step()  # warm-up: allocates the staging buffers
         barrier()
         t0 = time.perf_counter()
         for _ in range(e_steps):
-            flux, isv, ct = me.integrate(grads.array)
+            e2e_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = t.item()
+        lo = ((ne - 1) // rng_pts) * rng_pts  # the window holds the last range: must equal the resident results
+        ok = bool(np.array_equal(flux.array[: ne - lo], m.device_view("stress")[:, lo:ne].T.cpu().numpy()))
         e2e = {
             "value": world * ne * e_steps / dt,
             "unit": UNIT,
             "h2d_bytes_per_step": ne * 6 * 8,
             "d2h_bytes_per_step": ne * (6 + 7 + 36) * 8,
             "points_per_gpu": ne,
+            "range_points": rng_pts,
             "steps": e_steps,
             "ms_per_step": 1e3 * dt / e_steps,
-            "api": "CUDAMaterial.integrate(host (n,6) gradients) -> host (flux, isv, Ct), pinned buffers",
+            "api": "CUDAMaterial.integrate_range_into(host (n,6) gradients) -> host (flux, isv, Ct) window, page-locked buffers; every point of the device-resident leg crosses the boundary each step",
+            "matches_resident": ok,
         }
-        # the e2e outputs must equal the resident results bit for bit
-        ok = bool(np.array_equal(flux, me.device_view("stress").T.cpu().numpy()))
-        e2e["matches_resident"] = ok
-        del me
+        del flux, isv, ct
 
-    # ---- CPU baseline + parity spot check on rank 0 at N = 1 -------------------------------------
+        # the drop-in path proper: QuadratureExchange.update (quadrature_map.py:297-334): flux + tangent to the
+        # Function arrays, internal state stays on the GPU until advance()
+        nx = int(min(args.exchange_n, ne)) & ~3
+        if nx > 0:
+            from dolfinx_materials_b200.exchange import QuadratureExchange
+
+            mx = jm.CUDAMaterial(beh, device=local)
+            gx, fx, jx = PinnedArray((nx * 6,)), PinnedArray((nx * 6,)), PinnedArray((nx * 36,))
+            ix = {"p": np.zeros(nx), "epsp": np.zeros(nx * 6)}
+            ex = QuadratureExchange(mx, nx // 4, 4, {"strain": gx.array}, {"stress": fx.array}, ix, jx.array, pin=False)
+            gx.array[:] = 0.0
+            ex.initialize_state()
+            for k in range(1, KINC):
+                mx.synth_gradients(SEED, AMP, k, KINC, start=start)
+                mx.integrate_resident()
+                mx.data_manager.update()
+            gx.array[:] = grads.array[:nx].ravel()
+            ex.update()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                ex.update()
+            torch.cuda.synchronize()
+            dtx = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dtx], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dtx = t.item()
+            e2e_x = {"value": world * nx * e_steps / dtx, "unit": UNIT, "h2d_bytes_per_step": nx * 6 * 8,
+                     "d2h_bytes_per_step": nx * (6 + 36) * 8, "points_per_gpu": nx, "steps": e_steps, "ms_per_step": 1e3 * dtx / e_steps,
+                     "api": "QuadratureExchange.update(): gradient array -> flux + tangent arrays (the QuadratureMap.update hand-off); internal state fetched in advance() only",
+                     "matches_e2e": bool(np.array_equal(fx.array.reshape(nx, 6)[-4:], m.device_view("stress")[:, nx - 4:nx].T.cpu().numpy()))}
+            ex.close()
+            del mx, ex
+        del grads
+
+    # ---- CPU baseline on rank 0 at N = 1: compiled C port on all threads (+ the numpy port, for scale) --------------
     cpu = None
     if arm is not None:
         cores = arm.cores
-        rate = arm.prepare(1)
-        cpc = max(1, min(4, int(rate * 1.5 / arm.chunk)))
-        if cpc > 1:
-            arm.prepare(cpc)
-        arm.step()
-        wall, pts, res = arm.step()
-        arm.close()
+        try:
+            numpy_port = numpy_port_rate(arm)
+        except Exception as e:  # noqa: BLE001
+            numpy_port = {"unavailable": str(e)[:200]}
+        tc, pc, fc = c_port_steps(cores, 3, 1, 400_000)
         cpu = {
-            "value": pts / wall,
+            "value": pc * 3 / tc,
             "unit": UNIT,
             "cores": cores,
             "kind": "port",
-            "sample": f"first {pts} points of the same workload ({cores} procs x {cpc} chunks x {arm.chunk}), numpy oracle, one pass at increment {KINC}/{KINC}",
-            "sample_plastic_fraction": sum(r[0] for r in res) / pts,
+            "sample": f"first {pc} points of the same workload, plain-C oracle (gcc -O2 -mfma -ffp-contract=off) on {cores} threads, 3 passes at increment {KINC}/{KINC}",
+            "sample_plastic_fraction": fc,
+            "numpy_port": numpy_port,
         }
-        try:
-            cpu["c_port"] = c_port_rate(cores)
-        except Exception as e:  # noqa: BLE001
-            cpu["c_port"] = {"unavailable": str(e)[:200]}
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        achieved = BYTES_PER_GP * n / (kms * 1e-3) / 1e9
+        achieved = BYTES_MOVED_PER_GP * n / (kms * 1e-3) / 1e9
+        algorithmic = BYTES_PER_GP * n / (kms * 1e-3) / 1e9
         traffic, traffic_src = load_traffic(n)
         line = {
             "metric": METRIC,
@@ -502,14 +578,19 @@ def run_ours(args):
                 "traffic_source": traffic_src,
                 "kernel": "dxm_small_strain_kernel<HARD_GENERAL,uniform,PPT=1>",
                 "kernel_ms": kms,
-                "algorithmic_bytes_per_launch": BYTES_PER_GP * n,
-                "moved_bytes_per_launch": BYTES_MOVED_PER_GP * n,
-                "moved_gbs": BYTES_MOVED_PER_GP * n / (kms * 1e-3) / 1e9,
-                "moved_frac": BYTES_MOVED_PER_GP * n / (kms * 1e-3) / 1e9 / peak,
+                "bytes_per_point": BYTES_MOVED_PER_GP,
+                "bytes_per_launch": BYTES_MOVED_PER_GP * n,
+                "note": "bytes the kernel moves: 25 doubles read + 34 written per point (symmetric tangent stored once); SURVEY 8(d)'s algorithmic count (592 B: the reference boundary's full 36-entry tangent) is in algorithmic_*",
+                "algorithmic_bytes_per_point": BYTES_PER_GP,
+                "algorithmic_achieved": algorithmic,
+                "algorithmic_frac": algorithmic / peak,
+                "sustained_frac": (BYTES_MOVED_PER_GP * n / (sustained["kernel_ms"] * 1e-3) / 1e9 / peak) if sustained else None,
                 "peak_source": peak_src,
             },
+            "sustained": sustained,
             "cpu_baseline": cpu,
             "e2e": e2e,
+            "e2e_exchange": e2e_x,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stats": {"plastic_fraction": s.n_plastic / (n * world), "n_fail": s.n_fail, "max_iter": s.max_iter,
@@ -527,10 +608,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=float, default=1e8, help="Gauss points per GPU")
-    ap.add_argument("--e2e-n", type=float, default=1e7, help="Gauss points per GPU for the host-buffer e2e leg")
+    ap.add_argument("--e2e-n", type=float, default=-1, help="Gauss points per GPU for the host-buffer e2e leg (default: --n, the same points as the device-resident leg; 0 skips it)")
+    ap.add_argument("--e2e-range", type=float, default=1e7, help="points per ranged call (= size of the page-locked output window) of the e2e leg")
+    ap.add_argument("--exchange-n", type=float, default=1e7, help="Gauss points per GPU for the QuadratureExchange.update leg (0 skips it)")
+    ap.add_argument("--sustain", type=float, default=3.0, help="seconds of the sustained repeat of the device-resident step (0 skips it)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.e2e_n < 0:
+        args.e2e_n = args.n
     if args.impl == "reference":
         run_reference(args)
     else:
