@@ -775,8 +775,12 @@ int dxm_set_state(dxm_handle* h, int gen, const char* field, const double* v, in
   const Field* f = find_field(h, field);
   if (!f) return fail(std::string("dxm_set_state: unknown field '") + field + "'");
   if (set_device(h)) return -1;
-  if (gen == 1 && !h->s1_valid) {  // materialise the alias before a partial write
-    CK(cudaMemcpyAsync(h->gen[1 - h->i0], h->gen[h->i0], sizeof(double) * h->nrows * h->ld,
+  if (gen == 1 && !h->s1_valid) {
+    // materialise the alias before a partial write: flux and internal-state rows only -- the gradient rows of s1 are the
+    // caller's to write even while s1 aliases s0 (dxm_device_ptr, GradientEvaluator) and must not be overwritten with
+    // the previous step's
+    const int64_t off = (int64_t)h->ngrad * h->ld;
+    CK(cudaMemcpyAsync(h->gen[1 - h->i0] + off, h->gen[h->i0] + off, sizeof(double) * (h->nrows - h->ngrad) * h->ld,
                        cudaMemcpyDeviceToDevice, h->stream));
     h->s1_valid = true;
   }
@@ -1145,19 +1149,40 @@ int dxm_host_alloc(void** ptr, int64_t bytes) {
   return 0;
 }
 
+// registrations made through this library: address -> (bytes, reference count).  Registering the same range again only
+// bumps the count; a range that overlaps someone else's registration is reported, not silently treated as valid.
+static std::mutex g_reg_mu;
+static std::map<void*, std::pair<int64_t, int>> g_reg;
+
 int dxm_host_register(void* ptr, int64_t bytes) {
   if (!ptr || bytes <= 0) return fail("dxm_host_register: bad argument");
+  std::lock_guard<std::mutex> lock(g_reg_mu);
+  auto it = g_reg.find(ptr);
+  if (it != g_reg.end()) {
+    if (it->second.first != bytes)
+      return fail("dxm_host_register: this address is already page-locked with a different size (" +
+                  std::to_string(it->second.first) + " bytes); unregister it first");
+    ++it->second.second;
+    return 0;
+  }
   cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
   if (e == cudaErrorHostMemoryAlreadyRegistered) {
     cudaGetLastError();
-    return 0;
+    return fail("dxm_host_register: the range overlaps memory page-locked by someone else (stale or partial "
+                "registration); it cannot be trusted to cover the array");
   }
   CK(e);
+  g_reg[ptr] = {bytes, 1};
   return 0;
 }
 
 int dxm_host_unregister(void* ptr) {
   if (!ptr) return 0;
+  std::lock_guard<std::mutex> lock(g_reg_mu);
+  auto it = g_reg.find(ptr);
+  if (it == g_reg.end()) return 0;  // not ours (or already released)
+  if (--it->second.second > 0) return 0;
+  g_reg.erase(it);
   cudaError_t e = cudaHostUnregister(ptr);
   if (e == cudaErrorHostMemoryNotRegistered) {
     cudaGetLastError();

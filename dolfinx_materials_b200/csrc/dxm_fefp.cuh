@@ -200,6 +200,9 @@ DXM_HD void fefp_point(const FeFpArgs& a, const int64_t i0, const bool live, con
     Bo[1][2] = Bo[2][1] = beo[5] * kRsqrt2;
   }
   const double p_old = ld_stream(a.p_old + i0);
+  // a singular or inverted elastic state (det be_bar <= 0; e.g. an all-zero be_bar that was never initialised to the
+  // identity) would give PK1 = 0 with every check green: such a point is counted as failed
+  const double det_bo = det3(Bo);
 
   double mu, kappa, sig0, H, dsu, b;
   if (PERPOINT) {
@@ -367,7 +370,7 @@ DXM_HD void fefp_point(const FeFpArgs& a, const int64_t i0, const bool live, con
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) chk = chk + fabs(P[i][j]);
-  if (!isfinite(chk)) fail = true;
+  if (!isfinite(chk) || !(det_bo > 0.0)) fail = true;
 
   // state and stress stores (the tangent follows)
 #pragma unroll

@@ -23,6 +23,7 @@ of numpy fancy indexing.  The class works on any objects exposing a flat float64
 
 import ctypes
 import warnings
+import weakref
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -41,6 +42,11 @@ def _scatter_cells(dst_flat, cells64, block, src):
     """dst[cells[c], :] = src[c, :] (``_update_vals`` with ``cells``, ``utils.py:136-143``), on the host pool."""
     _lib.check(_lib.load().dxm_host_scatter_rows(dst_flat.ctypes.data_as(ctypes.c_void_p), cells64.ctypes.data_as(ctypes.c_void_p),
                                                  len(cells64), block, src.ctypes.data_as(ctypes.c_void_p), 0), "dxm_host_scatter_rows")
+
+
+def _run_all(callbacks):
+    while callbacks:
+        callbacks.pop()()
 
 
 def _flat(fun):
@@ -95,6 +101,8 @@ class QuadratureExchange:
             for name, prop in material.material_properties.items():
                 material.update_material_property(name, np.asarray(prop))
         self._unpin = []
+        # the page-locked registrations are released with the exchange even when close() is never called
+        self._fin = weakref.finalize(self, _run_all, self._unpin)
         self._stage = None
         if self.identity and pin:
             for a in (self.grad, self.flux, self.jac, *self.isv.values()):
@@ -116,9 +124,7 @@ class QuadratureExchange:
         self.last_stats = None
 
     def close(self):
-        for u in self._unpin:
-            u()
-        self._unpin = []
+        _run_all(self._unpin)
         if getattr(self, "_host", None) is not None:
             self._host.shutdown()
             self._host = None
@@ -132,6 +138,18 @@ class QuadratureExchange:
         state = {self.gname: self._take(self.grad, self.gdim), self.fname: self._take(self.flux, self.fdim)}
         for k, d in self.material.internal_state_variables.items():
             state[k] = self._take(self.isv[k], d)
+        # Finite strain: jaxmat initialises be_bar (isochoric elastic left Cauchy-Green) to the IDENTITY by itself
+        # (behavior.init_state, jaxmat.py:35), and the reference's finite-strain demo relies on that when it never calls
+        # update_initial_state("be_bar").  A Function that was never initialised holds zeros -- a singular state that
+        # would silently give PK1 = 0 -- so an all-zero be_bar is seeded with the identity, in the Function too.
+        if "be_bar" in state and not state["be_bar"].any():
+            ident = np.array([1.0, 1.0, 1.0, 0.0, 0.0, 0.0])
+            vals = self.isv["be_bar"].reshape(-1, 6)
+            if self.identity:
+                vals[:] = ident
+            else:
+                vals[self.dofs] = ident
+            state["be_bar"] = self._take(self.isv["be_bar"], 6)
         self.material.set_initial_state_dict(state)
         self._initialized = True
 

@@ -59,18 +59,30 @@ class IntegrationStats:
         return cls(s.n_points, s.n_plastic, s.n_fail, s.max_iter, s.max_residual, s.kernel_ms)
 
 
+class _PinnedBlock:
+    """Owner of one page-locked allocation (``dxm_host_alloc``): freed when the last reference goes -- the
+    :class:`_Pinned` wrapper or ANY numpy view handed out from it (the views keep the block alive through their base)."""
+
+    def __init__(self, nbytes):
+        lib = _lib.load()
+        ptr = ctypes.c_void_p()
+        check(lib.dxm_host_alloc(ctypes.byref(ptr), int(nbytes)), "dxm_host_alloc")
+        self.ptr = ptr.value
+        self._fin = weakref.finalize(self, lib.dxm_host_free, ctypes.c_void_p(self.ptr))
+
+
 class _Pinned:
-    """A page-locked host array (``dxm_host_alloc``) viewed as numpy; freed with the object."""
+    """A page-locked host array viewed as numpy.  The array (and every view sliced from it, e.g. what ``integrate``
+    returns) holds a reference to the allocation, so dropping the material or re-creating its data manager never
+    leaves a caller with a dangling view (the reference returns ordinary owned arrays, ``generic.py:185-189``)."""
 
     def __init__(self, shape):
-        lib = _lib.load()
         size = int(np.prod(shape))
-        ptr = ctypes.c_void_p()
-        check(lib.dxm_host_alloc(ctypes.byref(ptr), size * 8), "dxm_host_alloc")
-        self.ptr = ptr.value
+        self.block = _PinnedBlock(size * 8)
+        self.ptr = self.block.ptr
         buf = (ctypes.c_double * max(size, 1)).from_address(self.ptr)
+        buf._dxm_owner = self.block  # numpy keeps `buf` as the base of the array: the block lives as long as any view
         self.array = np.ctypeslib.as_array(buf)[:size].reshape(shape)
-        self._fin = weakref.finalize(self, lib.dxm_host_free, ctypes.c_void_p(self.ptr))
 
 
 def pin_array(arr):
@@ -493,3 +505,43 @@ class CUDAMaterial:
             "dxm_get_diagnostics",
         )
         return flag, n_iter, resid, fail
+
+
+# ---- a true subclass of the reference's Material where the reference is importable ------------------------------------
+_PLAIN = CUDAMaterial
+_SUBCLASSES = {}
+
+
+def material_subclass(base=None):
+    """``CUDAMaterial`` as a subclass of the reference's ``dolfinx_materials.generic.Material`` (``generic.py:103-201``):
+    ``isinstance(mat, Material)`` holds, every protocol member is overridden by the CUDA-backed one, and the base
+    constructor runs (so ``mat.E``, ``mat.nu`` ... exist as on any reference material, ``generic.py:109-113``).
+    ``base`` defaults to the installed reference class; the package exports this subclass as ``CUDAMaterial`` whenever
+    ``dolfinx_materials`` can be imported, the plain protocol class otherwise."""
+    if base is None:
+        from dolfinx_materials.generic import Material as base  # the reference
+    cls = _SUBCLASSES.get(base)
+    if cls is None:
+
+        class CUDAMaterial(_PLAIN, base):  # noqa: F811 - same public name on purpose
+            __doc__ = _PLAIN.__doc__
+
+            def __init__(self, behavior, device=None, warn_on_failure=True):
+                base.__init__(self, **dict(behavior.properties()))
+                _PLAIN.__init__(self, behavior, device=device, warn_on_failure=warn_on_failure)
+
+            def default_properties(self):
+                return {}
+
+        CUDAMaterial.__qualname__ = "CUDAMaterial"
+        CUDAMaterial.__module__ = _PLAIN.__module__
+        cls = _SUBCLASSES[base] = CUDAMaterial
+    return cls
+
+
+try:  # the reference package is importable only where dolfinx is (it imports dolfinx.common at module level)
+    from dolfinx_materials.generic import Material as _ReferenceMaterial
+except Exception:  # noqa: BLE001
+    _ReferenceMaterial = None
+if _ReferenceMaterial is not None:
+    CUDAMaterial = material_subclass(_ReferenceMaterial)

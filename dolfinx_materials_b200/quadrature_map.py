@@ -54,6 +54,8 @@ def gpu_quadrature_map(base=None, strict=True, internal_state_every_update=False
             if self._xchg is None:
                 mat = self.material
                 if mat.rotation_matrix is not None:
+                    # rotate_gradients / rotate_fluxes / rotate_tangent_operator (quadrature_map.py:315-330,
+                    # mfront.py:336-343) are identities for the isotropic CUDA behaviours: nothing to rotate
                     raise NotImplementedError("CUDA materials are isotropic: rotation_matrix must be None")
                 missing = [g for g in mat.gradients if g not in self.gradients]
                 if missing:
@@ -96,7 +98,8 @@ def gpu_quadrature_map(base=None, strict=True, internal_state_every_update=False
             self._exchange().advance()
 
         def close(self):
-            """Release the page-locked registrations of the Function arrays (optional; also done at exit)."""
+            """Release the page-locked registrations of the Function arrays now (otherwise a finalizer of the exchange
+            does it when the map is garbage-collected)."""
             if self._xchg is not None:
                 self._xchg.close()
                 self._xchg = None

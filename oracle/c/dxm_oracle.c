@@ -187,6 +187,7 @@ void dxo_fefp(int64_t n, const double* F, const double* F_old, const double* p_o
     Bo[0][1] = Bo[1][0] = beo[3] * RSQRT2;
     Bo[0][2] = Bo[2][0] = beo[4] * RSQRT2;
     Bo[1][2] = Bo[2][1] = beo[5] * RSQRT2;
+    const double det_bo = det3(Bo); /* a singular / inverted elastic state is a failed point */
     double Aoi[3][3], f[3][3], M[3][3], B[3][3], D[3][3];
     inv3(Ao, Aoi);
     for (int i = 0; i < 3; ++i)
@@ -314,7 +315,7 @@ void dxo_fefp(int64_t n, const double* F, const double* F_old, const double* p_o
     for (int i = 0; i < 6; ++i) chk = chk + fabs(be[i]);
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) chk = chk + fabs(P[i][j]);
-    if (!isfinite(chk)) fail = 1;
+    if (!isfinite(chk) || !(det_bo > 0.0)) fail = 1;
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) P_o[pt * 9 + IDX9[i][j]] = P[i][j];
     p_o[pt] = p_new;

@@ -129,6 +129,10 @@ def integrate(F, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
         Bo[0][2] = Bo[2][0] = beo[:, 4] * RSQRT2
         Bo[1][2] = Bo[2][1] = beo[:, 5] * RSQRT2
 
+        # a singular / inverted elastic state (det be_bar <= 0, e.g. a be_bar left at zero instead of the identity)
+        # would give PK1 = 0 with every other check green: counted as a failed point
+        det_bo = _det3(Bo)
+
         # ---- trial state -------------------------------------------------------------------
         Aoi, _ = _inv3(Ao)
         f = [[_dot3(A[i][0], Aoi[0][j], A[i][1], Aoi[1][j], A[i][2], Aoi[2][j]) for j in range(3)] for i in range(3)]
@@ -276,7 +280,7 @@ def integrate(F, state, props, newton_cap=NEWTON_CAP, rtol=NEWTON_RTOL):
         for i in range(3):
             for j in range(3):
                 chk = chk + np.abs(P[i][j])
-        fail |= ~np.isfinite(chk)
+        fail |= ~np.isfinite(chk) | ~(det_bo > 0.0)
 
     PK1 = np.empty((n, 9))
     for i in range(3):

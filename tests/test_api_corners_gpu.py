@@ -118,3 +118,81 @@ def test_dlpack_view_outlives_material(jm):
     assert bool((view == expected).all())  # buffers are freed only when the last view dies
     del view
     gc.collect()
+
+
+def test_partial_state_write_keeps_gradients_written_into_s1(jm):
+    """After update() s1 aliases s0; a resident caller may already have written this step's gradients into s1's
+    gradient buffer (dxm_device_ptr / GradientEvaluator) when a partial set_state on generation 1 materialises the
+    alias: that must copy flux and internal state only, not the previous step's gradients over the new ones."""
+    from dolfinx_materials_b200 import _lib
+    from dolfinx_materials_b200._lib import check
+
+    n = 4096
+    m = voce(jm, n)
+    m.synth_gradients(0, 1.25e-2, 1, 2)
+    m.integrate_resident()
+    m.data_manager.update()  # s1 now aliases s0
+    m.synth_gradients(0, 1.25e-2, 2, 2)  # this step's gradients, written into s1's gradient buffer
+    want = synth.strain(n, 0, 1.25e-2, 2, 2)
+    p = np.full((n, 1), 0.125)
+    check(_lib.load().dxm_set_state(m._h, 1, b"p", p.ctypes.data_as(ctypes.c_void_p), _lib.MEM_HOST), "dxm_set_state")
+    assert np.array_equal(m.device_view("strain").T.cpu().numpy(), want)
+    assert np.array_equal(m.device_view("p").T.cpu().numpy(), p)
+    # ... while the flux rows did come over from s0
+    assert np.array_equal(m.device_view("stress", gen=1).cpu().numpy(), m.device_view("stress", gen=0).cpu().numpy())
+
+
+def test_returned_arrays_outlive_the_material(jm):
+    """integrate() hands out views of page-locked buffers: they keep the allocation alive (no dangling views when the
+    data manager is re-created or the material is dropped)."""
+    n = 3000
+    m = voce(jm, n)
+    eps = synth.strain(n, 2, 1.25e-2, 1, 1)
+    flux, isv, ct = m.integrate(eps)
+    ref = ss.integrate(eps, ss.zero_state(n), VOCE)
+    part = ct[100:200]  # a slice of a view
+    m.set_data_manager(n)  # drops the material's references to its output buffers
+    junk = [np.empty((n, 36)) for _ in range(4)]  # give a freed block a chance to be reused
+    del m
+    gc.collect()
+    assert np.array_equal(flux, ref["stress"]) and np.array_equal(part, ref["Ct"].reshape(n, 36)[100:200])
+    del junk
+
+
+def test_page_lock_registry(jm):
+    from dolfinx_materials_b200 import _lib
+    from dolfinx_materials_b200.material import pin_array
+
+    a = np.zeros(1 << 16)
+    u1 = pin_array(a)
+    u2 = pin_array(a)  # same range again: reference-counted
+    with pytest.raises(_lib.DxmError, match="different size"):
+        pin_array(a[: 1 << 12])  # same address, other size: reported, not swallowed
+    u1()
+    u2()
+    b = a[8:]
+    u3 = pin_array(a)
+    with pytest.raises(_lib.DxmError, match="overlaps"):
+        pin_array(b)  # overlaps a live registration at another address
+    u3()
+
+
+def test_singular_finite_strain_state_is_flagged(jm):
+    from oracle import fefp
+
+    n = 64
+    m = jm.CUDAMaterial(jm.FeFpJ2Plasticity(elasticity=jm.LinearElasticIsotropic(E=70e3, nu=0.3),
+                                            yield_stress=jm.VoceHardening(sig0=500.0, sigu=750.0, b=1000.0)), warn_on_failure=False)
+    m.set_data_manager(n)
+    be = np.tile([1.0, 1, 1, 0, 0, 0], (n, 1))
+    be[5] = 0.0
+    m.set_initial_state_dict({"be_bar": be})
+    F = synth.defgrad(n, 0, 3e-2, 1, 1)
+    m.enable_diagnostics()
+    P, isv, Ct = m.integrate(F)
+    st = fefp.virgin_state(n)
+    st["be_bar"] = be
+    ref = fefp.integrate(F, st, dict(E=70e3, nu=0.3, sig0=500.0, sigu=750.0, b=1000.0))
+    assert m.last_stats.n_fail == 1 and m.diagnostics()[3].tolist() == ref["fail"].tolist()
+    ok = np.arange(n) != 5
+    assert np.array_equal(P[ok], ref["PK1"][ok]) and np.array_equal(Ct[ok], ref["Ct"][ok])

@@ -77,3 +77,43 @@ def test_subset_cells_are_validated(jm, no_pinning):
         ex.QuadratureExchange(mat, 10, 1, cells=np.array([1, 1, 2]), pin=False, **arrs)
     with pytest.raises(ValueError):
         ex.QuadratureExchange(mat, 10, 1, cells=np.array([1, 12]), pin=False, **arrs)
+
+
+class _FiniteStrainStandIn:
+    """records what initialize_state pushes; finite-strain protocol names"""
+    gradients, fluxes, internal_state_variables = {"F": 9}, {"PK1": 9}, {"p": 1, "be_bar": 6}
+    material_properties = {}
+    _n = None
+
+    def set_data_manager(self, n):
+        self._n = n
+
+    def set_initial_state_dict(self, state):
+        self.pushed = {k: np.array(v, copy=True) for k, v in state.items()}
+
+
+@pytest.mark.parametrize("subset", [False, True])
+def test_uninitialised_be_bar_is_seeded_with_the_identity(jm, no_pinning, subset):
+    """jaxmat initialises be_bar to the identity by itself (behavior.init_state) and the reference's finite-strain demo
+    relies on it; a zero-filled be_bar Function must not overwrite that with a singular state (PK1 would silently be 0)."""
+    ex = no_pinning
+    ncell, nqp = 12, 4
+    ntot = ncell * nqp
+    cells = np.array([1, 4, 5, 9]) if subset else None
+    arrs = dict(gradients={"F": np.tile([1, 1, 1, 0, 0, 0, 0, 0, 0.0], ntot)}, fluxes={"PK1": np.zeros(ntot * 9)},
+                internal_state_variables={"p": np.zeros(ntot), "be_bar": np.zeros(ntot * 6)}, jacobian_flatten=np.zeros(ntot * 81))
+    mat = _FiniteStrainStandIn()
+    x = ex.QuadratureExchange(mat, ncell, nqp, cells=cells, pin=False, **arrs)
+    x.initialize_state()
+    ident = np.array([1, 1, 1, 0, 0, 0.0])
+    assert np.array_equal(mat.pushed["be_bar"], np.tile(ident, (x.n, 1)))
+    be = arrs["internal_state_variables"]["be_bar"].reshape(-1, 6)
+    if subset:
+        assert np.array_equal(be[x.dofs], np.tile(ident, (x.n, 1)))  # the Function agrees with the device state
+        assert not be[np.setdiff1d(np.arange(ntot), x.dofs)].any()  # other regions' points untouched
+    else:
+        assert np.array_equal(be, np.tile(ident, (ntot, 1)))
+    # a be_bar the caller did initialise is pushed as it is
+    be[:] = [2.0, 0.5, 1.0, 0.1, 0.0, 0.0]
+    x.initialize_state()
+    assert np.array_equal(mat.pushed["be_bar"], np.tile([2.0, 0.5, 1.0, 0.1, 0.0, 0.0], (x.n, 1)))

@@ -141,6 +141,22 @@ def test_inverted_element_is_flagged():
     assert out["fail"].tolist() == [0, 1, 0]
 
 
+def test_singular_elastic_state_is_a_failed_point():
+    """be_bar = 0 (a state Function that was never initialised to the identity) gives PK1 = 0 with every finiteness
+    check green; det(be_bar_old) <= 0 is therefore counted as a failure, in the oracle and the kernel alike."""
+    n = 4
+    F = np.tile([1.0, 1, 1, 0.01, 0, 0, 0, 0, 0], (n, 1))
+    st = fefp.virgin_state(n)
+    st["be_bar"][1] = 0.0  # singular
+    st["be_bar"][2] = [-1.0, 1, 1, 0, 0, 0]  # inverted
+    out = fefp.integrate(F, st, PROPS)
+    assert out["fail"].tolist() == [0, 1, 1, 0]
+    assert np.all(out["PK1"][1] == 0.0) and np.abs(out["PK1"][0]).max() > 100.0  # the silent result this guards against
+    from oracle import cport
+
+    assert cport.fefp(F, st, PROPS)["fail"].tolist() == [0, 1, 1, 0]
+
+
 def test_history_matches_reference_protocol_run():
     """tests/golden/fefp_history.npz: the reference's own Material.integrate / _vmap / DataManager drove a
     per-point FeFp material over a 3-increment history (make_golden.py); the batched oracle with explicit
