@@ -24,6 +24,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
+OUT = os.environ.get("DXM_GOLDEN_OUT", HERE)  # where the fixtures go (tests redirect it to a temporary directory)
 sys.path.insert(0, ROOT)
 if len(sys.argv) > 1:
     sys.path.insert(0, sys.argv[1])
@@ -99,7 +100,7 @@ def main():
     material = JAXMaterial(behavior)
     material.set_data_manager(n)
     res = drive(material, [synth.strain(n, 0, 1.25e-2, k, K) for k in range(1, K + 1)])
-    np.savez_compressed(os.path.join(HERE, "jaxmat_j2_voce.npz"), versions=versions(),
+    np.savez_compressed(os.path.join(OUT, "jaxmat_j2_voce.npz"), versions=versions(),
                         props=np.array(list(props.items()), dtype=object), **res)
     print("jaxmat_j2_voce.npz:", {k: v.shape for k, v in res.items()})
 
@@ -125,7 +126,7 @@ def main():
     m2 = make()
     m2.set_data_manager(n)
     rand = drive(m2, [synth.defgrad(n, 0, 3e-2, k, K) for k in range(1, K + 1)])
-    np.savez_compressed(os.path.join(HERE, "jaxmat_fefp.npz"), versions=versions(),
+    np.savez_compressed(os.path.join(OUT, "jaxmat_fefp.npz"), versions=versions(),
                         props=np.array(list(props.items()), dtype=object),
                         **{"script_" + k: v for k, v in script.items()}, **{"random_" + k: v for k, v in rand.items()})
     print("jaxmat_fefp.npz:", {k: v.shape for k, v in rand.items()})
