@@ -9,12 +9,21 @@
 // Either the element vectors / matrices are written out (MODE_ELEMENT: what MatSetValuesLocal takes), or they are
 // scatter-added straight into a global vector and a CSR value array (MODE_GLOBAL): the tangent (36 | 81 doubles
 // per point) then never leaves the device -- only the assembled system does.
-// Operation order == oracle/fe_forms.py (element level bit-exact; the global scatter uses fp64 atomics).
 //
-// Mapping: one thread per element-matrix row (cell, a, r); CPB = 256 / (ND*TDIM) cells per CTA.  The CTA stages
-// the flux and tangent rows of its CPB*nqp consecutive Gauss points in shared memory with coalesced loads (each
-// SoA row contributes one contiguous run), computes g once per cell, and in MODE_ELEMENT transposes the rows through
-// shared memory so that the (num_cells, ndof, ndof) output is written in full contiguous lines.
+// Round-2 kernel: ONE WARP PER CELL, ONE LANE PER ELEMENT-MATRIX COLUMN (b, s).
+//   * the CTA (8 warps = 8 consecutive cells) stages vol_q, g, vol_q g and the flux / tangent of its points as plain
+//     tensors S[r][j], A[(r,j)][(s,l)] in shared memory with coalesced loads (every SoA row is one contiguous run);
+//   * a lane keeps its own g[b][:] and U_q[(r,j)] = sum_l A_q[(r,j)][(s,l)] g_q[b][l] in registers (formed once per
+//     cell), and every entry of its column is then sum_q sum_j (vol_q g_q[a][j]) U_q[(r,j)]: 12 fused multiply-adds on
+//     three broadcast shared-memory operands -- 15 k DFMA per P2 tetrahedron instead of the 29 k DMUL + DADD and the
+//     ~130 shared-memory loads per row and point of the round-1 mapping (one thread per ROW);
+//   * a row of the element matrix leaves the warp as ONE reduction instruction whose lanes hit consecutive CSR entries
+//     (the three columns of a node are adjacent): ~11 L2 sectors per row instead of 30 scattered 8-byte atomics -- the
+//     round-1 kernel was bound by exactly that (597 M scattered fp64 atomics = 7.2 ms of its 7.2 ms).
+// Tensor cores: not used.  FP64 DMMA (mma.sync.m8n8k4.f64, the only fp64 tensor path of sm_100) would have to treat the
+// gradient operator G (9 x 30) as dense although two thirds of it are structural zeros (delta_ss'): 147 kflop issued per
+// cell and point set for 28 kflop of useful work, at a peak (~40 TFLOP/s) no higher than the DFMA pipe's on B200.
+// Operation order == oracle/fe_forms.py (element level bit-exact; the global scatter uses fp64 atomics).
 #pragma once
 #include "dxm_canon.cuh"
 
@@ -45,9 +54,11 @@ struct FeFormArgs {
   const double* lift;  // optional prescribed solution values on the constrained dofs: b -= A[:, bc] lift[bc]
   unsigned long long* missing;  // count of (row, col) pairs not found in the pattern
   const int32_t* off;  // optional (num_cells, nd, nd): offset of node b's column block inside node a's rows
+  const int32_t* cell_list;  // optional: the cells this launch handles, num_cells = its length
 };
 
 constexpr int kFeMaxNd = 20;  // generic path: up to P3 tetrahedra
+constexpr int kFeMaxQp = 8;   // Gauss points per cell the per-lane column state is sized for
 
 DXM_HD constexpr int idx9_c(int i, int j) {
   return i == j ? i : (i == 0 && j == 1) ? 3 : (i == 1 && j == 0) ? 4 : (i == 0 && j == 2) ? 5
@@ -112,32 +123,46 @@ __device__ __forceinline__ int64_t csr_find(const int32_t* colidx, int64_t lo, c
 
 struct FeFormSmem {
   int cpb, np, ndof;
-  size_t off_vol, off_g, off_flux, off_ct, off_out, bytes;
+  size_t off_vol, off_g, off_gv, off_flux, off_ct, bytes;
 };
 
+constexpr int kFeWarps = 4;  // cells per CTA: one per warp (4 CTAs of 4 warps per SM overlap staging and contraction better than 2 of 8)
+
+// S / A are staged as full tensors over the TDIM x TDIM gradient components: T2 = TDIM^2 entries per point for the flux,
+// T2 x T2 for the tangent, entry ((r*TDIM + j), (s*TDIM + l))
 inline FeFormSmem fe_form_smem(int tdim, int nd, int nqp, int kind, int mode, bool want_mat) {
+  (void)kind;
+  (void)mode;
   FeFormSmem s{};
+  const int t2 = tdim * tdim;
   s.ndof = nd * tdim;
-  s.cpb = 256 / s.ndof;
-  if (s.cpb < 1) s.cpb = 1;
+  s.cpb = kFeWarps;
   s.np = s.cpb * nqp;
-  const int nflux = kind == 0 ? 6 : 9, nct = kind == 0 ? kSym6Rows : 81;
   size_t o = 0;
   s.off_vol = o;
   o += sizeof(double) * s.np;
   s.off_g = o;
   o += sizeof(double) * (size_t)s.np * nd * tdim;
+  s.off_gv = o;
+  o += sizeof(double) * (size_t)s.np * nd * tdim;
   s.off_flux = o;
-  o += sizeof(double) * (size_t)nflux * s.np;
+  o += sizeof(double) * (size_t)t2 * s.np;
   s.off_ct = o;
-  o += want_mat ? sizeof(double) * (size_t)nct * s.np : 0;
-  s.off_out = o;
-  if (mode == MODE_ELEMENT && want_mat) o += sizeof(double) * (size_t)s.cpb * s.ndof * (s.ndof + 1);
+  o += want_mat ? sizeof(double) * (size_t)t2 * t2 * s.np : 0;
   s.bytes = o;
   return s;
 }
 
-// vol_q = w_q |det J| and g[a][j] = sum_m dphi[q][a][m] K[m][j] of Gauss point q of `cell` (the kernel's staging step)
+// g[a][j] = sum_m dphi[q][a][m] K[m][j]: physical gradient of basis function a at a Gauss point (dq = dphi of that point)
+template <int TDIM>
+DXM_HD double fe_form_g_entry(const double* dq, const double (&K)[TDIM][TDIM], const int n, const int j) {
+  double acc = dq[n * TDIM] * K[0][j];
+#pragma unroll
+  for (int m = 1; m < TDIM; ++m) acc = acc + dq[n * TDIM + m] * K[m][j];
+  return acc;
+}
+
+// vol_q = w_q |det J| and g[a][j] of Gauss point q of `cell` (the kernel stages the same entries item by item)
 template <int TDIM>
 DXM_HD void fe_form_point_geometry(const FeFormArgs& a, const int64_t cell, const int q, const int nd, double& vol,
                                    double* g) {
@@ -147,190 +172,433 @@ DXM_HD void fe_form_point_geometry(const FeFormArgs& a, const int64_t cell, cons
   const double* dq = a.dphi + (int64_t)q * nd * TDIM;
   for (int n = 0; n < nd; ++n) {
 #pragma unroll
-    for (int j = 0; j < TDIM; ++j) {
-      double acc = dq[n * TDIM] * K[0][j];
-#pragma unroll
-      for (int m = 1; m < TDIM; ++m) acc = acc + dq[n * TDIM + m] * K[m][j];
-      g[n * TDIM + j] = acc;
-    }
+    for (int j = 0; j < TDIM; ++j) g[n * TDIM + j] = fe_form_g_entry<TDIM>(dq, K, n, j);
   }
 }
 
-// Row (a, r) of the element vector / matrix of local cell `lc` from the staged arrays: vol [np], g [np][nd][TDIM],
-// flux [nflux][np], ct [nct][np] (shared memory in the kernel).  __host__ __device__ like the point routines of the
-// constitutive kernels, so that a CPU test can run it against the oracle (tests/fe_host_check.cu).
-template <int TDIM, int ND>
-DXM_HD void fe_form_row(const int kind, const bool want_mat, const int nqp, const int nd, const int np, const int lc,
-                        const int an, const int r, const double* s_vol, const double* s_g, const double* s_flux,
-                        const double* s_ct, double& fe, double* acc) {
+// ---- staging: SoA rows of the update -> tensors over the gradient components ------------------------------------------
+// tensor index pair(s) behind a Mandel index / a position of the reference's 9-vector
+DXM_HD void mandel_pair(const int m, int& i, int& j) {
+  i = m < 3 ? m : (m == 5 ? 1 : 0);
+  j = m < 3 ? m : (m == 3 ? 1 : 2);
+}
+DXM_HD void vec9_pair(const int p, int& i, int& j) {
+  // [11,22,33,12,21,13,31,23,32] (utils.py:173-186)
+  i = p < 3 ? p : (p == 3 || p == 5 ? 0 : (p == 4 || p == 7 ? 1 : 2));
+  j = p < 3 ? p : (p == 4 || p == 6 ? 0 : (p == 3 || p == 8 ? 1 : 2));
+}
+
+// Flux row `row` (Mandel 6 | reference 9-vector) of one point -> the S[r][j] entries it feeds (r, j < TDIM).
+template <int TDIM>
+DXM_HD void fe_stage_flux(const int kind, const int row, const double v, double* S /* [TDIM*TDIM] */) {
   constexpr double kR2 = 0.70710678118654752440;
-  constexpr int NDC = ND > 0 ? ND : kFeMaxNd;
-  for (int q = 0; q < nqp; ++q) {
-    const int pt = lc * nqp + q;
-    const double vol = s_vol[pt];
-    const double* g = s_g + (int64_t)pt * nd * TDIM;
-    double ga[TDIM];
-#pragma unroll
-    for (int j = 0; j < TDIM; ++j) ga[j] = g[an * TDIM + j];
-    // residual row
-    {
-      double t = 0.0;
-#pragma unroll
-      for (int j = 0; j < TDIM; ++j) {
-        double S;
-        if (kind == 1) {
-          S = s_flux[idx9_c(r, j) * np + pt];
-        } else {
-          S = s_flux[idx6_c(r, j) * np + pt];
-          if (r != j) S = S * kR2;
-        }
-        t = j == 0 ? S * ga[0] : t + S * ga[j];
-      }
-      fe = q == 0 ? vol * t : fe + vol * t;
+  int i, j;
+  if (kind == 1) {
+    vec9_pair(row, i, j);
+    if (i < TDIM && j < TDIM) S[i * TDIM + j] = v;
+    return;
+  }
+  mandel_pair(row, i, j);
+  if (i >= TDIM || j >= TDIM) return;
+  if (i == j) {
+    S[i * TDIM + i] = v;
+  } else {
+    const double w = v * kR2;
+    S[i * TDIM + j] = w;
+    S[j * TDIM + i] = w;
+  }
+}
+
+// Tangent row `row` (packed symmetric 21 | row-major 81) of one point -> the A[(r,j)][(s,l)] entries it feeds.
+template <int TDIM>
+DXM_HD void fe_stage_tangent(const int kind, const int row, const double v, double* A /* [T2*T2] */) {
+  constexpr double kR2 = 0.70710678118654752440;
+  constexpr int T2 = TDIM * TDIM;
+  int r, j, s, l;
+  if (kind == 1) {
+    vec9_pair(row / 9, r, j);
+    vec9_pair(row % 9, s, l);
+    if (r < TDIM && j < TDIM && s < TDIM && l < TDIM) A[(r * TDIM + j) * T2 + s * TDIM + l] = v;
+    return;
+  }
+  // packed row -> Mandel pair (m1 <= m2), row-major upper triangle
+  int m1 = 0, rem = row;
+  while (rem >= 6 - m1) {
+    rem -= 6 - m1;
+    ++m1;
+  }
+  const int m2 = m1 + rem;
+  mandel_pair(m1, r, j);
+  mandel_pair(m2, s, l);
+  if (r >= TDIM || j >= TDIM || s >= TDIM || l >= TDIM) return;
+  const int noff = (r != j ? 1 : 0) + (s != l ? 1 : 0);
+  const double w = noff == 0 ? v : (noff == 1 ? v * kR2 : v * 0.5);
+  // every tensor entry (r,j | j,r) x (s,l | l,s) of the pair, and its mirror (the 6x6 tangent is symmetric)
+  for (int t1 = 0; t1 < (r != j ? 2 : 1); ++t1)
+    for (int t2 = 0; t2 < (s != l ? 2 : 1); ++t2) {
+      const int rj = t1 ? j * TDIM + r : r * TDIM + j, sl = t2 ? l * TDIM + s : s * TDIM + l;
+      A[rj * T2 + sl] = w;
+      A[sl * T2 + rj] = w;
     }
-    if (!want_mat) continue;
-    // W[s][l] = sum_j g[a][j] A(rj, sl)
-    double W[TDIM][TDIM];
+}
+
+// ---- one column (b, s) of one cell, from the staged arrays of the cell's nqp points -----------------------------------
+// g, gv: [nqp][nd*TDIM]; S: [nqp][T2]; A: [nqp][T2*T2].  The kernel runs exactly these helpers, one lane per column;
+// __host__ __device__ so that a CPU test can run them against the oracle (tests/fe_host_check.cu).
+// gb[q][l] = g_q[b][l]
+template <int TDIM, int NQP>
+DXM_HD void fe_form_column_g(const int nqp_rt, const int nd, const int b, const double* g, double* gb /* [nqp][TDIM] */) {
+  const int nqp = NQP > 0 ? NQP : nqp_rt;
 #pragma unroll
-    for (int s = 0; s < TDIM; ++s)
+  for (int q = 0; q < (NQP > 0 ? NQP : kFeMaxQp); ++q) {
+    if (NQP == 0 && q >= nqp) break;
 #pragma unroll
-      for (int l = 0; l < TDIM; ++l) {
-        double w = 0.0;
+    for (int l = 0; l < TDIM; ++l) gb[q * TDIM + l] = g[(int64_t)q * nd * TDIM + b * TDIM + l];
+  }
+}
+
+// U[q][j] = sum_l A_q[(r,j)][(s,l)] g_q[b][l]   for the rows (., r) of the element matrix
+template <int TDIM, int NQP>
+DXM_HD void fe_form_column_u(const int nqp_rt, const int r, const int s, const double* gb, const double* A,
+                             double* U /* [nqp][TDIM] */) {
+  constexpr int T2 = TDIM * TDIM;
+  const int nqp = NQP > 0 ? NQP : nqp_rt;
 #pragma unroll
-        for (int j = 0; j < TDIM; ++j) {
-          double A;
-          if (kind == 1) {
-            A = s_ct[(idx9_c(r, j) * 9 + idx9_c(s, l)) * np + pt];
-          } else {
-            A = s_ct[sym6_packed(idx6_c(r, j) * 6 + idx6_c(s, l)) * np + pt];
-            const int noff = (r != j ? 1 : 0) + (s != l ? 1 : 0);
-            if (noff == 1) A = A * kR2;
-            if (noff == 2) A = A * 0.5;
-          }
-          w = j == 0 ? ga[0] * A : w + ga[j] * A;
-        }
-        W[s][l] = w;
-      }
+  for (int q = 0; q < (NQP > 0 ? NQP : kFeMaxQp); ++q) {
+    if (NQP == 0 && q >= nqp) break;
+    const double* Aq = A + (int64_t)q * T2 * T2;
 #pragma unroll
-    for (int b = 0; b < NDC; ++b) {
-      if (ND == 0 && b >= nd) break;
+    for (int j = 0; j < TDIM; ++j) {
+      const int rj = r * TDIM + j;
+      double u = Aq[rj * T2 + s * TDIM] * gb[q * TDIM];
 #pragma unroll
-      for (int s = 0; s < TDIM; ++s) {
-        double t2 = W[s][0] * g[b * TDIM];
-#pragma unroll
-        for (int l = 1; l < TDIM; ++l) t2 = t2 + W[s][l] * g[b * TDIM + l];
-        acc[b * TDIM + s] = q == 0 ? vol * t2 : acc[b * TDIM + s] + vol * t2;
-      }
+      for (int l = 1; l < TDIM; ++l) u = fma_c(Aq[rj * T2 + s * TDIM + l], gb[q * TDIM + l], u);
+      U[q * TDIM + j] = u;
     }
   }
 }
 
-template <int TDIM, int ND, int MODE>
-__global__ void __launch_bounds__(256) fe_forms_kernel(const FeFormArgs a, const FeFormSmem L) {
+// ke[(a,r),(b,s)] = sum_q sum_j (vol_q g_q[a][j]) U_q[j]   (q outer, j inner, one product then fused steps)
+template <int TDIM, int NQP>
+DXM_HD double fe_form_entry(const int nqp_rt, const int nd, const int a, const double* gv, const double* U) {
+  const int nqp = NQP > 0 ? NQP : nqp_rt;
+  double acc = 0.0;
+#pragma unroll
+  for (int q = 0; q < (NQP > 0 ? NQP : kFeMaxQp); ++q) {
+    if (NQP == 0 && q >= nqp) break;
+    const double* ga = gv + (int64_t)q * nd * TDIM + a * TDIM;
+#pragma unroll
+    for (int j = 0; j < TDIM; ++j) acc = (q == 0 && j == 0) ? ga[0] * U[0] : fma_c(ga[j], U[q * TDIM + j], acc);
+  }
+  return acc;
+}
+
+// fe[(b,s)] = sum_q sum_j S_q[s][j] (vol_q g_q[b][j])
+template <int TDIM, int NQP>
+DXM_HD double fe_form_vector_entry(const int nqp_rt, const int nd, const int b, const int s, const double* gv, const double* S) {
+  constexpr int T2 = TDIM * TDIM;
+  const int nqp = NQP > 0 ? NQP : nqp_rt;
+  double acc = 0.0;
+#pragma unroll
+  for (int q = 0; q < (NQP > 0 ? NQP : kFeMaxQp); ++q) {
+    if (NQP == 0 && q >= nqp) break;
+    const double* gbv = gv + (int64_t)q * nd * TDIM + b * TDIM;
+#pragma unroll
+    for (int j = 0; j < TDIM; ++j) {
+      const double sv = S[q * T2 + s * TDIM + j];
+      acc = (q == 0 && j == 0) ? sv * gbv[0] : fma_c(sv, gbv[j], acc);
+    }
+  }
+  return acc;
+}
+
+// NQP > 0: Gauss points per cell at compile time (the column state stays in registers); NQP == 0: run-time count up to
+// kFeMaxQp (local-memory arrays; uncommon rules)
+template <int TDIM, int ND, int NQP, int MODE>
+__global__ void __launch_bounds__(32 * kFeWarps, 4) fe_forms_kernel(const FeFormArgs a, const FeFormSmem L) {
   extern __shared__ double smem[];
+  constexpr int T2 = TDIM * TDIM;
+  constexpr int NDC = ND > 0 ? ND : kFeMaxNd;
   double* s_vol = smem + L.off_vol / sizeof(double);    // [np]
   double* s_g = smem + L.off_g / sizeof(double);        // [np][nd][TDIM]
-  double* s_flux = smem + L.off_flux / sizeof(double);  // [nflux][np]
-  double* s_ct = smem + L.off_ct / sizeof(double);      // [nct][np]
-  double* s_out = smem + L.off_out / sizeof(double);    // [cpb*ndof][ndof+1]
+  double* s_gv = smem + L.off_gv / sizeof(double);      // [np][nd][TDIM]   vol_q g
+  double* s_flux = smem + L.off_flux / sizeof(double);  // [np][T2]
+  double* s_ct = smem + L.off_ct / sizeof(double);      // [np][T2*T2]
   const int nd = ND > 0 ? ND : a.nd;
   const int ndof = nd * TDIM;
-  const int cpb = L.cpb, nqp = a.nqp, np = L.np;
+  const int nqp = a.nqp, np = L.np;
   const int nflux = a.kind == 0 ? 6 : 9, nct = a.kind == 0 ? kSym6Rows : 81;
-  const int64_t c0 = (int64_t)blockIdx.x * cpb;
-  const int ncell = (int)min((int64_t)cpb, a.num_cells - c0);
+  const int64_t c0 = (int64_t)blockIdx.x * kFeWarps;
+  const int ncell = (int)min((int64_t)kFeWarps, a.num_cells - c0);
   const int npv = ncell * nqp;
-  const int64_t p0 = c0 * nqp;
+  __shared__ int64_t s_cell[kFeWarps];  // the CTA's cells: consecutive, or taken from the launch's cell list
+  // first CSR entry of every global row the CTA's cells touch; -1: constrained row (left alone)
+  __shared__ int64_t s_rowlo[MODE == MODE_ELEMENT ? 1 : kFeWarps * kFeMaxNd * TDIM];
+  if (threadIdx.x < kFeWarps)
+    s_cell[threadIdx.x] = threadIdx.x < ncell ? (a.cell_list ? (int64_t)a.cell_list[c0 + threadIdx.x] : c0 + threadIdx.x) : 0;
+  __syncthreads();
 
-  // ---- stage: geometry -> vol_q, g[q][a][j]; flux / tangent rows of this CTA's points -------------------
-  for (int i = threadIdx.x; i < npv; i += blockDim.x) {
-    const int lc = i / nqp, q = i - lc * nqp;
-    fe_form_point_geometry<TDIM>(a, c0 + lc, q, nd, s_vol[i], s_g + (int64_t)i * nd * TDIM);
+  // ---- stage: geometry -> vol_q, g, vol_q g; flux / tangent rows of this CTA's points as tensors ------------------
+  __shared__ double s_K[kFeWarps][TDIM * TDIM + 1];  // J^-1 and |det J| of the CTA's cells
+  if (threadIdx.x < ncell) {
+    double K[TDIM][TDIM], det;
+    cell_geometry<TDIM>(a.coords, a.geom_dofs + s_cell[threadIdx.x] * (TDIM + 1), K, det);
+#pragma unroll
+    for (int i = 0; i < TDIM; ++i)
+#pragma unroll
+      for (int j = 0; j < TDIM; ++j) s_K[threadIdx.x][i * TDIM + j] = K[i][j];
+    s_K[threadIdx.x][TDIM * TDIM] = fabs(det);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npv * nd; i += blockDim.x) {  // one (point, basis function) per item
+    const int pt = i / nd, n = i - pt * nd;
+    const int lc = pt / nqp, q = pt - lc * nqp;
+    double K[TDIM][TDIM];
+#pragma unroll
+    for (int ii = 0; ii < TDIM; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < TDIM; ++jj) K[ii][jj] = s_K[lc][ii * TDIM + jj];
+    const double vol = a.weights[q] * s_K[lc][TDIM * TDIM];
+    const double* dq = a.dphi + (int64_t)q * nd * TDIM;
+#pragma unroll
+    for (int j = 0; j < TDIM; ++j) {
+      const double gk = fe_form_g_entry<TDIM>(dq, K, n, j);
+      s_g[(int64_t)i * TDIM + j] = gk;
+      s_gv[(int64_t)i * TDIM + j] = vol * gk;
+    }
+    if (n == 0) s_vol[pt] = vol;
   }
   for (int i = threadIdx.x; i < nflux * np; i += blockDim.x) {
     const int row = i / np, k = i - row * np;
-    if (k < npv) s_flux[i] = __ldcs(a.flux + (int64_t)row * a.ld + p0 + k);
+    if (k < npv) {
+      const int lc = k / nqp;
+      fe_stage_flux<TDIM>(a.kind, row, __ldcs(a.flux + (int64_t)row * a.ld + s_cell[lc] * nqp + (k - lc * nqp)),
+                          s_flux + (int64_t)k * T2);
+    }
   }
   if (a.want_mat) {
     for (int i = threadIdx.x; i < nct * np; i += blockDim.x) {
       const int row = i / np, k = i - row * np;
-      if (k < npv) s_ct[i] = __ldcs(a.ct + (int64_t)row * a.ld + p0 + k);
+      if (k < npv) {
+        const int lc = k / nqp;
+        fe_stage_tangent<TDIM>(a.kind, row, __ldcs(a.ct + (int64_t)row * a.ld + s_cell[lc] * nqp + (k - lc * nqp)),
+                               s_ct + (int64_t)k * T2 * T2);
+      }
+    }
+    if (MODE != MODE_ELEMENT) {
+      for (int i = threadIdx.x; i < ncell * ndof; i += blockDim.x) {
+        const int lc = i / ndof, row = i - lc * ndof;
+        const int64_t grow = (int64_t)a.u_dofs[s_cell[lc] * nd + row / TDIM] * TDIM + row % TDIM;
+        s_rowlo[lc * kFeMaxNd * TDIM + row] = (a.bc && a.bc[grow]) ? -1 : a.rowptr[grow];
+      }
     }
   }
   __syncthreads();
 
-  const int lc = threadIdx.x / ndof;
-  const int row = threadIdx.x - lc * ndof;
-  const int an = row / TDIM, r = row - an * TDIM;
-  const bool live = lc < ncell;
-  constexpr int NDC = ND > 0 ? ND : kFeMaxNd;
-  double fe = 0.0;
-  double acc[NDC * TDIM];
-  if (live) fe_form_row<TDIM, ND>(a.kind, a.want_mat != 0, nqp, nd, np, lc, an, r, s_vol, s_g, s_flux, s_ct, fe, acc);
+  const int lc = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lc >= ncell) return;
+  const int64_t cell = s_cell[lc];
+  const double* g = s_g + (int64_t)lc * nqp * nd * TDIM;
+  const double* gv = s_gv + (int64_t)lc * nqp * nd * TDIM;
+  const double* S = s_flux + (int64_t)lc * nqp * T2;
+  const double* A = s_ct + (int64_t)lc * nqp * T2 * T2;
+  const int32_t* ud = a.u_dofs + cell * nd;
+  const int64_t* rowlo = s_rowlo + (MODE == MODE_ELEMENT ? 0 : lc * kFeMaxNd * TDIM);
 
-  if (MODE == MODE_ELEMENT) {
-    if (live && a.want_vec) a.fe[(c0 + lc) * ndof + row] = fe;
-    if (a.want_mat) {
-      // transpose through shared memory: thread rows -> contiguous (cell, row, col) lines
-      if (live) {
-        double* o = s_out + (int64_t)threadIdx.x * (ndof + 1);
+  for (int cb = 0; cb < ndof; cb += 32) {  // columns in chunks of a warp (one chunk up to 10 nodes in 3-D)
+    const int col = cb + lane;
+    const bool live = col < ndof;
+    const int b = live ? col / TDIM : 0, s = live ? col - b * TDIM : 0;
+    double gb[kFeMaxQp * TDIM], U[kFeMaxQp * TDIM];
+    fe_form_column_g<TDIM, NQP>(nqp, nd, b, g, gb);
+
+    if (MODE == MODE_ELEMENT) {
+      if (live && a.want_vec) a.fe[cell * ndof + col] = fe_form_vector_entry<TDIM, NQP>(nqp, nd, b, s, gv, S);
+      if (!a.want_mat) continue;
 #pragma unroll
-        for (int k = 0; k < NDC * TDIM; ++k) {
-          if (ND == 0 && k >= ndof) break;
-          o[k] = acc[k];
+      for (int r = 0; r < TDIM; ++r) {
+        fe_form_column_u<TDIM, NQP>(nqp, r, s, gb, A, U);
+        for (int an = 0; an < nd; ++an) {
+          const double v = fe_form_entry<TDIM, NQP>(nqp, nd, an, gv, U);
+          if (live) __stcs(a.ke + (cell * ndof + an * TDIM + r) * ndof + col, v);  // a row is one contiguous line
         }
       }
-      __syncthreads();
-      const int total = ncell * ndof * ndof;
-      double* dst = a.ke + c0 * ndof * ndof;
-      for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int rw = i / ndof, cl = i - rw * ndof;
-        __stcs(dst + i, s_out[(int64_t)rw * (ndof + 1) + cl]);
+      continue;
+    }
+
+    const int64_t gcol = live ? (int64_t)ud[b] * TDIM + s : 0;
+    const bool col_bc = live && a.bc && a.bc[gcol];
+    if (live && a.want_vec && !col_bc) atomicAdd(a.b + gcol, fe_form_vector_entry<TDIM, NQP>(nqp, nd, b, s, gv, S));
+    if (!a.want_mat) continue;
+    const double lift = (col_bc && a.lift) ? a.lift[gcol] : 0.0;
+    const bool any_lift = a.lift && __any_sync(0xffffffffu, col_bc);
+    const bool writer = live && !col_bc;
+    // node-blocked patterns: the offset of (node a, node b) inside the rows of node a was found once (fe_offsets_kernel);
+    // the TDIM columns of node b are consecutive there.  Without the table: binary search per entry.
+    int32_t offs[NDC];
+#pragma unroll
+    for (int an = 0; an < NDC; ++an) {
+      if (ND == 0 && an >= nd) break;
+      offs[an] = (a.off && writer) ? a.off[(cell * nd + an) * nd + b] : -1;
+    }
+    unsigned miss = 0;
+#pragma unroll
+    for (int r = 0; r < TDIM; ++r) {
+      fe_form_column_u<TDIM, NQP>(nqp, r, s, gb, A, U);
+      int64_t pos[NDC];
+#pragma unroll
+      for (int an = 0; an < NDC; ++an) {
+        if (ND == 0 && an >= nd) break;
+        const int64_t lo = rowlo[an * TDIM + r];
+        int64_t p = -1;
+        if (writer && lo >= 0) {
+          if (a.off)
+            p = offs[an] >= 0 ? lo + offs[an] + s : -2;
+          else {
+            const int64_t grow = (int64_t)ud[an] * TDIM + r;
+            p = csr_find(a.colidx, lo, a.rowptr[grow + 1], (int32_t)gcol);
+            if (p < 0) p = -2;
+          }
+        }
+        pos[an] = p;  // -1: nothing to write, -2: no slot in the pattern
+      }
+#pragma unroll
+      for (int an = 0; an < NDC; ++an) {
+        if (ND == 0 && an >= nd) break;
+        if (rowlo[an * TDIM + r] < 0) continue;  // constrained row: untouched (unit diagonal set by the host API)
+        const double v = fe_form_entry<TDIM, NQP>(nqp, nd, an, gv, U);
+        if (any_lift) {
+          // constrained columns move to the right-hand side (apply_lifting): b[row] -= sum_bc K[row][col] lift[col]
+          double lf = col_bc ? v * lift : 0.0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) lf += __shfl_xor_sync(0xffffffffu, lf, o);
+          if (lane == 0 && lf != 0.0) atomicAdd(a.b + (int64_t)ud[an] * TDIM + r, -lf);
+        }
+        if (pos[an] == -2) ++miss;
+        if (pos[an] < 0) continue;
+        atomicAdd(a.vals + pos[an], v);  // result unused: a RED
+      }
+    }
+    if (miss) atomicAdd(a.missing, (unsigned long long)miss);
+  }
+}
+
+// ---- atomic-free assembly: element matrices -> CSR rows, node by node ---------------------------------------------------
+// The L2 retires ~90 G scalar fp64 reductions per second however they are grouped, which bounds the atomic scatter of the
+// 900 entries of a P2 tetrahedron at 6.5 ms for 663 k cells (profiles/r02g_fe_forms_assembly_experiments.json).  Instead:
+// fe_forms_kernel<MODE_ELEMENT> writes every element matrix as full contiguous lines, and ONE WARP PER MESH NODE then sums
+// the rows (a, r) of the cells around its node into a shared-memory image of the node's TDIM CSR rows -- cell after
+// cell in a fixed order, each lane owning distinct columns, so no atomics and bit-reproducible sums -- applies the
+// Dirichlet rows / columns (apply_lifting) and writes the rows out as whole lines.  Everything streams: element matrices
+// written once and read once, CSR values written once (no memset).
+struct FeGatherArgs {
+  const double* ke;        // (num_cells, ndof, ndof)
+  const double* fe;        // (num_cells, ndof)
+  const int64_t* nc_ptr;   // node -> [cells around it], CSR over the nodes
+  const int32_t* nc_cell;
+  const uint8_t* nc_loc;   // local index of the node in that cell
+  const int32_t* off;      // (num_cells, nd, nd): offset of node b's column block inside node a's rows
+  const int64_t* rowptr;
+  const int32_t* colidx;
+  double* vals;
+  double* rhs;
+  const uint8_t* bc;
+  const double* lift;
+  int64_t num_nodes;
+  int nd, want_vec, maxlen;
+};
+
+constexpr int kGatherWarps = 8;
+constexpr int kGatherAhead = 4;  // cells whose element-matrix rows are requested before the first is accumulated
+
+template <int TDIM>
+__global__ void __launch_bounds__(32 * kGatherWarps) fe_gather_kernel(const FeGatherArgs a) {
+  extern __shared__ double smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * kGatherWarps + w;
+  if (n >= a.num_nodes) return;
+  double* buf = smem + (size_t)w * TDIM * a.maxlen;  // [TDIM][maxlen]: the node's rows
+  const int nd = a.nd, ndof = nd * TDIM;
+  const int64_t lo0 = a.rowptr[n * TDIM];
+  const int len = (int)(a.rowptr[n * TDIM + 1] - lo0);  // node-blocked pattern: the TDIM rows of a node have one structure
+#pragma unroll
+  for (int r = 0; r < TDIM; ++r)
+    for (int k = lane; k < len; k += 32) buf[r * a.maxlen + k] = 0.0;
+  __syncwarp();
+  double facc = 0.0;  // lane r < TDIM: vector entry of row r
+  const int64_t e0 = a.nc_ptr[n], e1 = a.nc_ptr[n + 1];
+  if (ndof <= 32) {
+    // the usual elements: a row of the element matrix is one warp access; the loads of kGatherAhead cells are in flight
+    // before the first of them is accumulated (cell after cell: the summation order stays fixed)
+    const int col = lane;
+    const bool live = col < ndof;
+    const int b = live ? col / TDIM : 0, s = live ? col - b * TDIM : 0;
+    for (int64_t e = e0; e < e1; e += kGatherAhead) {
+      double v[kGatherAhead][TDIM], f[kGatherAhead];
+      int o[kGatherAhead];
+#pragma unroll
+      for (int u = 0; u < kGatherAhead; ++u) {
+        const bool on = e + u < e1;
+        const int64_t c = on ? a.nc_cell[e + u] : 0;
+        const int la = on ? a.nc_loc[e + u] : 0;
+        o[u] = (on && live) ? a.off[(c * nd + la) * nd + b] + s : -1;
+        const double* rows = a.ke + (c * ndof + (int64_t)la * TDIM) * ndof;
+#pragma unroll
+        for (int r = 0; r < TDIM; ++r) v[u][r] = o[u] >= 0 ? __ldcs(rows + (int64_t)r * ndof + col) : 0.0;
+        f[u] = (on && a.want_vec && lane < TDIM) ? __ldcs(a.fe + c * ndof + la * TDIM + lane) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kGatherAhead; ++u) {
+        if (o[u] >= 0) {
+#pragma unroll
+          for (int r = 0; r < TDIM; ++r) buf[r * a.maxlen + o[u]] += v[u][r];
+        }
+        facc += f[u];
+        __syncwarp();  // the next cell's lanes may own the same columns
       }
     }
   } else {
-    if (!live) return;
-    const int32_t* ud = a.u_dofs + (c0 + lc) * nd;
-    const int64_t grow = (int64_t)ud[an] * TDIM + r;
-    if (a.bc && a.bc[grow]) return;  // constrained row: untouched (unit diagonal set by the host API)
-    if (a.want_vec) atomicAdd(a.b + grow, fe);
-    if (!a.want_mat) return;
-    const int64_t lo = a.rowptr[grow], hi = a.rowptr[grow + 1];
-    unsigned miss = 0;
-    double lifted = 0.0;
+    for (int64_t e = e0; e < e1; ++e) {
+      const int64_t c = a.nc_cell[e];
+      const int la = a.nc_loc[e];
+      const double* rows = a.ke + (c * ndof + (int64_t)la * TDIM) * ndof;
+      for (int cb = 0; cb < ndof; cb += 32) {
+        const int col = cb + lane;
+        if (col < ndof) {
+          const int b = col / TDIM, s = col - b * TDIM;
+          const int o = a.off[(c * nd + la) * nd + b] + s;
 #pragma unroll
-    for (int b = 0; b < NDC; ++b) {
-      if (ND == 0 && b >= nd) break;
-      const int32_t cbase = ud[b] * TDIM;
-      // node-blocked patterns: the offset of (node a, node b) inside the row was found once (fe_offsets_kernel)
-      int64_t pos = a.off ? (a.off[((c0 + lc) * nd + an) * nd + b] >= 0 ? lo + a.off[((c0 + lc) * nd + an) * nd + b] : -1)
-                          : csr_find(a.colidx, lo, hi, cbase);
-#pragma unroll
-      for (int s = 0; s < TDIM; ++s) {
-        const int32_t gcol = cbase + s;
-        if (s > 0) {
-          if (a.off)
-            pos = pos >= 0 ? pos + 1 : -1;
-          // blocked pattern: the columns of one node are consecutive; fall back to a search otherwise
-          else if (pos >= 0 && pos + 1 < hi && a.colidx[pos + 1] == gcol)
-            pos = pos + 1;
-          else
-            pos = csr_find(a.colidx, lo, hi, gcol);
+          for (int r = 0; r < TDIM; ++r) buf[r * a.maxlen + o] += __ldcs(rows + (int64_t)r * ndof + col);
         }
-        if (a.bc && a.bc[gcol]) {
-          // constrained column: moved to the right-hand side (apply_lifting)
-          if (a.lift) lifted += acc[b * TDIM + s] * a.lift[gcol];
-          continue;
-        }
-        if (pos < 0) {
-          ++miss;
-          continue;
-        }
-        atomicAdd(a.vals + pos, acc[b * TDIM + s]);
       }
+      if (a.want_vec && lane < TDIM) facc += __ldcs(a.fe + c * ndof + la * TDIM + lane);
+      __syncwarp();
     }
-    if (a.lift && lifted != 0.0) atomicAdd(a.b + grow, -lifted);
-    if (miss) atomicAdd(a.missing, (unsigned long long)miss);
+  }
+#pragma unroll
+  for (int r = 0; r < TDIM; ++r) {
+    const int64_t i = n * TDIM + r, lo = a.rowptr[i];
+    const bool row_bc = a.bc && a.bc[i];
+    double lifted = 0.0;
+    for (int k = lane; k < len; k += 32) {
+      double v = buf[r * a.maxlen + k];
+      if (a.bc) {
+        const int32_t j = a.colidx[lo + k];
+        if (row_bc) {
+          v = 0.0;  // constrained row: empty here, unit diagonal set by fe_bc_diag_kernel
+        } else if (a.bc[j]) {
+          if (a.lift) lifted += v * a.lift[j];  // constrained column: moved to the right-hand side (apply_lifting)
+          v = 0.0;
+        }
+      }
+      __stcs(a.vals + lo + k, v);
+    }
+    if (a.want_vec) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lifted += __shfl_xor_sync(0xffffffffu, lifted, o);
+      const double f = __shfl_sync(0xffffffffu, facc, r);
+      if (lane == 0) a.rhs[i] = row_bc ? 0.0 : f - lifted;
+    }
   }
 }
 

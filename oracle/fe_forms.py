@@ -30,8 +30,8 @@ dense B-matrix / einsum formulation, the patch test, linearity for an elastic ma
 finite-difference tangent through the FeFp update (``tests/test_oracle_fe_forms.py``), and end to end by the Newton
 loop of ``tests/test_newton_bar_gpu.py`` (quadratic convergence only happens with a consistent residual / tangent pair).
 
-Operation order is canonical (explicit loops, no einsum) and shared with ``fe_forms_kernel``; element vectors and
-matrices therefore agree bit for bit.  Global assembly sums element contributions (order-dependent on the GPU:
+Operation order is canonical (explicit loops, no einsum, fused multiply-adds placed by hand: ``oracle/canon.py``) and
+shared with ``fe_forms_kernel``; element vectors and matrices therefore agree bit for bit.  Global assembly sums element contributions (order-dependent on the GPU:
 atomics), compared with a tolerance.
 """
 
@@ -98,7 +98,14 @@ def _tangent_tensor(ct, kind, q_pts, r, j, s, l):
 
 def element_forms(coords, geom_dofmap, u_dofmap, dphi, weights, flux, ct, kind, tdim, want_matrix=True):
     """flux (n, 6|9), ct (n, 36|81) or (n, nf, ng) with n = ncells*nqp.  Returns fe (ncells, nd*tdim) and
-    ke (ncells, nd*tdim, nd*tdim) (None if not wanted)."""
+    ke (ncells, nd*tdim, nd*tdim) (None if not wanted).
+
+    Canonical operation order (shared with ``fe_forms_kernel``, one warp lane per column ``(b, s)``):
+    ``gv_q[a][j] = vol_q g_q[a][j]``; ``U_q[(r,j)] = sum_l A_q[(r,j)][(s,l)] g_q[b][l]``;
+    ``ke[(a,r),(b,s)] = sum_q sum_j gv_q[a][j] U_q[(r,j)]`` and ``fe[(b,s)] = sum_q sum_j S_q[s][j] gv_q[b][j]``, every
+    sum one product followed by fused multiply-adds in the order written (q outer, j / l inner)."""
+    from .canon import fma
+
     ud = np.asarray(u_dofmap)
     dphi = np.asarray(dphi, dtype=np.float64)
     weights = np.asarray(weights, dtype=np.float64)
@@ -112,39 +119,45 @@ def element_forms(coords, geom_dofmap, u_dofmap, dphi, weights, flux, ct, kind, 
     fe = np.zeros((nc, ndof))
     ke = np.zeros((nc, ndof, ndof)) if want_matrix else None
     cells = np.arange(nc)
+    g, gv, pts = [], [], []
     for q in range(nqp):
-        pts = cells * nqp + q
+        pts.append(cells * nqp + q)
         vol = weights[q] * adet
-        g = [[None] * tdim for _ in range(nd)]
+        gq = [[None] * tdim for _ in range(nd)]
         for a in range(nd):
             for j in range(tdim):
                 acc = dphi[q, a, 0] * K[0][j]
                 for m in range(1, tdim):
                     acc = acc + dphi[q, a, m] * K[m][j]
-                g[a][j] = acc
-        for a in range(nd):
-            for r in range(tdim):
-                t = _flux_tensor(flux, kind, pts, r, 0) * g[a][0]
-                for j in range(1, tdim):
-                    t = t + _flux_tensor(flux, kind, pts, r, j) * g[a][j]
-                row = a * tdim + r
-                fe[:, row] = vol * t if q == 0 else fe[:, row] + vol * t
-                if not want_matrix:
-                    continue
-                W = [[None] * tdim for _ in range(tdim)]
-                for s in range(tdim):
-                    for l in range(tdim):
-                        acc = g[a][0] * _tangent_tensor(ct, kind, pts, r, 0, s, l)
-                        for j in range(1, tdim):
-                            acc = acc + g[a][j] * _tangent_tensor(ct, kind, pts, r, j, s, l)
-                        W[s][l] = acc
-                for b in range(nd):
-                    for s in range(tdim):
-                        t2 = W[s][0] * g[b][0]
+                gq[a][j] = acc
+        g.append(gq)
+        gv.append([[vol * gq[a][j] for j in range(tdim)] for a in range(nd)])
+    for b in range(nd):
+        for s in range(tdim):
+            col = b * tdim + s
+            acc = None
+            for q in range(nqp):
+                for j in range(tdim):
+                    sv = _flux_tensor(flux, kind, pts[q], s, j)
+                    acc = sv * gv[q][b][0] if acc is None else fma(sv, gv[q][b][j], acc)
+            fe[:, col] = acc
+            if not want_matrix:
+                continue
+            U = [[[None] * tdim for _ in range(tdim)] for _ in range(nqp)]
+            for q in range(nqp):
+                for r in range(tdim):
+                    for j in range(tdim):
+                        u = _tangent_tensor(ct, kind, pts[q], r, j, s, 0) * g[q][b][0]
                         for l in range(1, tdim):
-                            t2 = t2 + W[s][l] * g[b][l]
-                        col = b * tdim + s
-                        ke[:, row, col] = vol * t2 if q == 0 else ke[:, row, col] + vol * t2
+                            u = fma(_tangent_tensor(ct, kind, pts[q], r, j, s, l), g[q][b][l], u)
+                        U[q][r][j] = u
+            for a in range(nd):
+                for r in range(tdim):
+                    acc = None
+                    for q in range(nqp):
+                        for j in range(tdim):
+                            acc = gv[q][a][0] * U[q][r][0] if acc is None else fma(gv[q][a][j], U[q][r][j], acc)
+                    ke[:, a * tdim + r, col] = acc
     return fe, ke
 
 

@@ -1,5 +1,6 @@
-// CPU-side check of the FE kernels' per-cell / per-row routines (tests/test_fe_host.py): dxm::fe_gradient_cell,
-// dxm::fe_form_point_geometry and dxm::fe_form_row are __host__ __device__, so the very code the kernels run is
+// CPU-side check of the FE kernels' per-cell / per-column routines (tests/test_fe_host.py): dxm::fe_gradient_cell,
+// dxm::fe_form_point_geometry, fe_stage_flux / fe_stage_tangent, fe_form_column_g / fe_form_column_u, fe_form_entry and
+// fe_form_vector_entry are __host__ __device__, so the very code the kernels run is
 // executed here on the host and compared bit for bit with the oracles -- without a GPU.  The CTA-level staging of
 // fe_forms_kernel (shared-memory arrays of the CTA's points) is replayed with one cell per "CTA".
 // Test scaffolding only: nothing in the product calls this.
@@ -17,26 +18,36 @@ void grad_cells(const dxm::FeGradArgs& a) {
   for (int64_t c = 0; c < a.num_cells; ++c) dxm::fe_gradient_cell<TDIM, ND>(a, a.dphi, nd, c);
 }
 
-template <int TDIM, int ND>
+// one cell per "CTA": the kernel's staging (tensor flux / tangent, g, vol g) and its per-lane column routines, column by column
+template <int TDIM, int ND, int NQP>
 void form_cells(const dxm::FeFormArgs& a) {
-  const int nd = ND > 0 ? ND : a.nd, ndof = nd * TDIM, nqp = a.nqp, np = nqp;
+  constexpr int T2 = TDIM * TDIM;
+  const int nd = ND > 0 ? ND : a.nd, ndof = nd * TDIM, nqp = a.nqp;
   const int nflux = a.kind == 0 ? 6 : 9, nct = a.kind == 0 ? dxm::kSym6Rows : 81;
-  std::vector<double> vol(np), g((size_t)np * nd * TDIM), fl((size_t)nflux * np), ct((size_t)nct * np);
-  std::vector<double> acc(dxm::kFeMaxNd * TDIM);
+  std::vector<double> vol(nqp), g((size_t)nqp * nd * TDIM), gv((size_t)nqp * nd * TDIM), S((size_t)nqp * T2),
+      A((size_t)nqp * T2 * T2);
+  double gb[dxm::kFeMaxQp * TDIM], U[dxm::kFeMaxQp * TDIM];
   for (int64_t c = 0; c < a.num_cells; ++c) {
-    for (int q = 0; q < nqp; ++q) dxm::fe_form_point_geometry<TDIM>(a, c, q, nd, vol[q], g.data() + (size_t)q * nd * TDIM);
-    for (int row = 0; row < nflux; ++row)
-      for (int q = 0; q < nqp; ++q) fl[(size_t)row * np + q] = a.flux[(int64_t)row * a.ld + c * nqp + q];
-    if (a.want_mat)
-      for (int row = 0; row < nct; ++row)
-        for (int q = 0; q < nqp; ++q) ct[(size_t)row * np + q] = a.ct[(int64_t)row * a.ld + c * nqp + q];
-    for (int row = 0; row < ndof; ++row) {
-      double fe = 0.0;
-      dxm::fe_form_row<TDIM, ND>(a.kind, a.want_mat != 0, nqp, nd, np, 0, row / TDIM, row % TDIM, vol.data(), g.data(),
-                                 fl.data(), ct.data(), fe, acc.data());
-      a.fe[c * ndof + row] = fe;
+    for (int q = 0; q < nqp; ++q) {
+      double* gq = g.data() + (size_t)q * nd * TDIM;
+      dxm::fe_form_point_geometry<TDIM>(a, c, q, nd, vol[q], gq);
+      for (int k = 0; k < nd * TDIM; ++k) gv[(size_t)q * nd * TDIM + k] = vol[q] * gq[k];
+      for (int row = 0; row < nflux; ++row)
+        dxm::fe_stage_flux<TDIM>(a.kind, row, a.flux[(int64_t)row * a.ld + c * nqp + q], S.data() + (size_t)q * T2);
       if (a.want_mat)
-        for (int k = 0; k < ndof; ++k) a.ke[(c * ndof + row) * ndof + k] = acc[k];
+        for (int row = 0; row < nct; ++row)
+          dxm::fe_stage_tangent<TDIM>(a.kind, row, a.ct[(int64_t)row * a.ld + c * nqp + q], A.data() + (size_t)q * T2 * T2);
+    }
+    for (int col = 0; col < ndof; ++col) {
+      const int b = col / TDIM, s = col % TDIM;
+      dxm::fe_form_column_g<TDIM, NQP>(nqp, nd, b, g.data(), gb);
+      a.fe[c * ndof + col] = dxm::fe_form_vector_entry<TDIM, NQP>(nqp, nd, b, s, gv.data(), S.data());
+      if (a.want_mat)
+        for (int r = 0; r < TDIM; ++r) {
+          dxm::fe_form_column_u<TDIM, NQP>(nqp, r, s, gb, A.data(), U);
+          for (int an = 0; an < nd; ++an)
+            a.ke[(c * ndof + an * TDIM + r) * ndof + col] = dxm::fe_form_entry<TDIM, NQP>(nqp, nd, an, gv.data(), U);
+        }
     }
   }
 }
@@ -84,15 +95,19 @@ extern "C" int fe_forms_host(int tdim, int64_t num_cells, int nd, int nqp, int k
   a.want_mat = want_mat;
   a.fe = fe;
   a.ke = ke;
+  if (nqp > dxm::kFeMaxQp) return -1;
+  // same (nodes, Gauss points) dispatch as launch_fe_forms (dxm_fe_api.cu)
   if (tdim == 3) {
-    if (!generic && nd == 4) return form_cells<3, 4>(a), 0;
-    if (!generic && nd == 10) return form_cells<3, 10>(a), 0;
-    return form_cells<3, 0>(a), 0;
+    if (!generic && nd == 10 && nqp == 4) return form_cells<3, 10, 4>(a), 0;
+    if (!generic && nd == 4 && nqp == 1) return form_cells<3, 4, 1>(a), 0;
+    if (!generic && nd == 4 && nqp == 4) return form_cells<3, 4, 4>(a), 0;
+    return form_cells<3, 0, 0>(a), 0;
   }
   if (tdim == 2) {
-    if (!generic && nd == 3) return form_cells<2, 3>(a), 0;
-    if (!generic && nd == 6) return form_cells<2, 6>(a), 0;
-    return form_cells<2, 0>(a), 0;
+    if (!generic && nd == 6 && nqp == 3) return form_cells<2, 6, 3>(a), 0;
+    if (!generic && nd == 3 && nqp == 1) return form_cells<2, 3, 1>(a), 0;
+    if (!generic && nd == 3 && nqp == 3) return form_cells<2, 3, 3>(a), 0;
+    return form_cells<2, 0, 0>(a), 0;
   }
   return -1;
 }
