@@ -598,6 +598,9 @@ def run_ours(args):
         }
         emit(line)
     if world > 1:
+        dist.barrier()
+        del m
+        lib.dxm_comm_destroy()
         dist.destroy_process_group()
 
 

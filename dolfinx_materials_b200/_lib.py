@@ -9,9 +9,9 @@ import pathlib
 
 import os
 
-# DXM_FMAD=1: the contracted (fused multiply-add) build, see build.py
+# DXM_UNFUSED=1: the A/B build with the round-1 (un-fused) arithmetic, see build.py
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / (
-    "libdxm_cuda_fmad.so" if os.environ.get("DXM_FMAD", "0") not in ("", "0") else "libdxm_cuda.so")
+    "libdxm_cuda_unfused.so" if os.environ.get("DXM_UNFUSED", "0") not in ("", "0") else "libdxm_cuda.so")
 
 MEM_HOST, MEM_DEVICE, MEM_RESIDENT = 0, 1, 2
 

@@ -7,10 +7,11 @@ import subprocess
 
 ROOT = pathlib.Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
-# DXM_FMAD=1 selects the contracted build (fused multiply-add allowed): same kernels, ~40 % fewer FP64 instructions in
-# the finite-strain update, results within a few ulp of the canonical build instead of bit-identical to the oracle
-FMAD = os.environ.get("DXM_FMAD", "0") not in ("", "0")
-LIB = ROOT / "lib" / ("libdxm_cuda_fmad.so" if FMAD else "libdxm_cuda.so")
+# DXM_UNFUSED=1 selects the A/B build with every hand-placed fused multiply-add split into two roundings again
+# (-DDXM_UNFUSED, csrc/dxm_canon.cuh): the round-1 arithmetic -- bit-identical to the committed golden histories and to
+# oracle.canon.unfused(), ~40 % more FP64 instructions in the finite-strain update (tests/test_unfused_gpu.py)
+UNFUSED = os.environ.get("DXM_UNFUSED", "0") not in ("", "0")
+LIB = ROOT / "lib" / ("libdxm_cuda_unfused.so" if UNFUSED else "libdxm_cuda.so")
 
 NVCC_FLAGS = [
     "-gencode",
@@ -18,9 +19,10 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-O3",
     "-std=c++17",
-    # no fused multiply-add: every fp64 operation is individually rounded, in the order written,
-    # which is what makes kernel results bit-comparable with the CPU oracle
-    "-fmad=true" if FMAD else "-fmad=false",
+    # the compiler never fuses a product into an addition on its own: the canonical arithmetic places every fused
+    # multiply-add by hand (fma_c / fms_c / fnma_c), which is what makes kernel results bit-comparable with the CPU oracle
+    "-fmad=false",
+    *(["-DDXM_UNFUSED"] if UNFUSED else []),
     "-Xcompiler",
     "-fPIC",
 ]
@@ -52,7 +54,7 @@ def build_library(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     LIB.parent.mkdir(parents=True, exist_ok=True)
-    objdir = ROOT / "lib" / ("obj_fmad" if FMAD else "obj")
+    objdir = ROOT / "lib" / ("obj_unfused" if UNFUSED else "obj")
     objdir.mkdir(exist_ok=True)
     nvcc = _nvcc()
     procs = []

@@ -38,7 +38,8 @@ template <int AT, bool VOCE>
 int launch_at(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches) {
   // Registers: the fused kernel gains 6 % at 4 resident CTAs per SM (128 registers) now that only the Newton loop's own
   // state crosses the loop; the tiled kernel, whose streaming phase shares the allocation, loses 4-13 % there and stays
-  // at 3 CTAs (168 registers) -- profiles/r02c_hosford_ab_minb_fused_warpqueue.json.  DXM_HOS_MINB=3|4 forces either.
+  // at 3 CTAs (168 registers) -- profiles/r02c_hosford_ab_minb_fused_warpqueue.json; 5 CTAs (96 registers, 0.9 KB of
+  // spills) lose 9 % again (profiles/r02h_hosford_ab_minb5.json).  DXM_HOS_MINB=3|4 forces either.
   const int minb = cfg.minb ? cfg.minb : (cfg.tiled ? 3 : 4);
   if (minb == 3) return launch_at2<AT, VOCE, 3>(a, cfg, launches);
   return launch_at2<AT, VOCE, 4>(a, cfg, launches);

@@ -92,7 +92,7 @@ del mh, mb
 # tile + CTA-local candidate queue + packed local solves; r01g/r01h also ran a device-wide queue + second kernel: slower), (r01g also ran the local-solve kernel at 4 resident CTAs per SM / 128 registers: 0-20 % slower)
 mh = jm.CUDAMaterial(jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.LinearHardening(sig0=200.0, H=10.0)))
 mh.set_data_manager(n)
-for split, minb in (("0", "3"), ("1", "3")):
+for split, minb in (("0", "4"), ("1", "3")):  # register targets: the per-kernel defaults (dxm_hosford_api.cu)
     os.environ["DXM_HOS_SPLIT"] = split
     for amp in (2e-3, 4e-3, 8e-3, 1.25e-2, 5e-2):
         mh.data_manager.revert(); mh.synth_gradients(0, amp, 1, 1)

@@ -125,7 +125,7 @@ def run_gpu(nx, ny, nz, steps=3, strain=0.01, L=10.0, W=1.0, newton_rtol=1e-8, n
     import torch.distributed as dist
 
     import dolfinx_materials_b200 as jm
-    from dolfinx_materials_b200.distributed import allreduce_stats, shard_range
+    from dolfinx_materials_b200.distributed import init_stats_comm, shard_range
     from dolfinx_materials_b200.fe import AssembledSystem, ElementForms, GradientEvaluator
 
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -144,6 +144,12 @@ def run_gpu(nx, ny, nz, steps=3, strain=0.01, L=10.0, W=1.0, newton_rtol=1e-8, n
         elasticity=jm.LinearElasticIsotropic(E=props["E"], nu=props["nu"]),
         yield_stress=jm.VoceHardening(sig0=props["sig0"], sigu=props["sigu"], b=props["b"])), device=device)
     mat.set_data_manager(nc * nqp)
+    if world > 1:
+        # failure / active-set counts and residual maxima reduced over the ranks in-stream: the library's NCCL
+        # communicator all-gathers the 64-byte record right after the update kernel (no host-side collective)
+        init_stats_comm()
+        mat.use_global_stats()
+    mat.enable_timing(1)
     ge = GradientEvaluator(mat, coords, gd[c0:c1], ud[c0:c1], dphi, tdim=3, num_dofs=len(nodes))
     forms = ElementForms(ge, W_DEG2)
     rowptr, colidx = sparsity(ud, len(nodes))
@@ -165,7 +171,6 @@ def run_gpu(nx, ny, nz, steps=3, strain=0.01, L=10.0, W=1.0, newton_rtol=1e-8, n
             t = time.perf_counter(); ge.eval(u); timers["gradients"] += time.perf_counter() - t
             t = time.perf_counter(); st = mat.integrate_resident(); timers["update"] += time.perf_counter() - t
             kernel_ms += st.kernel_ms
-            st = allreduce_stats(st)
             if st.n_fail:
                 raise RuntimeError(f"{st.n_fail} local solves failed")
             t = time.perf_counter()
@@ -199,6 +204,25 @@ def run_gpu(nx, ny, nz, steps=3, strain=0.01, L=10.0, W=1.0, newton_rtol=1e-8, n
         mat.data_manager.update()
     t_total = time.perf_counter() - t_loop
     n_updates = len(history) + steps
+    # per-update wall time of the resident call (kernel + in-stream statistics all-gather + publish) without the timing
+    # events, next to the kernel's own time with them
+    mat.data_manager.revert()
+    mat.enable_timing(0)
+    for _ in range(20):
+        mat.integrate_resident()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(200):
+        mat.integrate_resident()
+    update_wall_us = (time.perf_counter() - t) / 200 * 1e6
+    mat.enable_timing(1)
+    update_kernel_us = min(mat.integrate_resident().kernel_ms for _ in range(20)) * 1e3
+    if world > 1:
+        tt = torch.tensor([update_wall_us, update_kernel_us], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        update_wall_us, update_kernel_us = tt.tolist()
     if world > 1:  # per-stage times: slowest rank
         tt = torch.tensor([timers[k] for k in sorted(timers)] + [kernel_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -208,7 +232,8 @@ def run_gpu(nx, ny, nz, steps=3, strain=0.01, L=10.0, W=1.0, newton_rtol=1e-8, n
     nc = nc_global
     info = dict(ranks=world, cells=nc, points=nc * nqp, dofs=u.size, nnz=int(system.nnz), steps=steps, strain=strain,
                 newton_iterations=len(history), constitutive_updates=n_updates, setup_s=t_setup, loop_s=t_total,
-                timers_s=timers, update_kernel_ms_total=kernel_ms,
+                timers_s=timers, update_kernel_ms_total=kernel_ms, update_wall_us=update_wall_us,
+                update_kernel_us=update_kernel_us,
                 constitutive_share=timers["update"] / t_total,
                 update_gps=nc * nqp * n_updates / max(timers["update"], 1e-12),
                 krylov_iterations_total=int(sum(h["krylov_iterations"] for h in history)),
@@ -238,6 +263,9 @@ if __name__ == "__main__":
     if world > 1:
         rank0 = dist.get_rank() == 0
         dist.barrier()
+        del mat
+        from dolfinx_materials_b200 import _lib
+        _lib.load().dxm_comm_destroy()
         dist.destroy_process_group()
         if not rank0:
             sys.exit(0)

@@ -1,0 +1,34 @@
+"""The A/B build with every hand-placed fused multiply-add split into two roundings again (DXM_UNFUSED=1: nvcc
+-DDXM_UNFUSED, lib/libdxm_cuda_unfused.so) is the round-1 arithmetic: on the GPU it reproduces the committed golden
+histories BIT FOR BIT, while the default (fused) build agrees with them to the north star's rtol 1e-10 and is not
+slower.  Each build runs in its own process (the library is loaded once per process)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(unfused):
+    env = dict(os.environ, DXM_UNFUSED="1" if unfused else "0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "unfused_check.py")], capture_output=True, text=True,
+                       env=env, timeout=1500, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_unfused_build_is_round1_and_fused_build_is_within_tolerance():
+    old, new = _run(True), _run(False)
+    assert old["unfused"] == "1" and new["unfused"] == "0"
+    for name, h in old["histories"].items():
+        assert h["bit_identical"], f"{name}: the un-fused build no longer reproduces the round-1 fixture"
+    for name, h in new["histories"].items():
+        assert h["max_rel_dev"] < 1e-10, (name, h)
+    assert not all(h["bit_identical"] for h in new["histories"].values())  # the two arithmetics do differ in the last bits
+    # fewer FP64 instructions: the fused build must not be slower (FeFp gains ~5 % in a burst, more when power-capped)
+    assert new["fefp_ms"] <= old["fefp_ms"] * 1.02 and new["hosford_ms"] <= old["hosford_ms"] * 1.02
+    print(json.dumps(dict(fused=new, unfused=old)))
