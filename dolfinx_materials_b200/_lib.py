@@ -58,6 +58,10 @@ SIGNATURES = {
     "dxm_enable_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "dxm_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
     "dxm_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "dxm_comm_p2p_handle": (ctypes.c_int, [ctypes.c_void_p]),
+    "dxm_comm_p2p_connect": (ctypes.c_int, [ctypes.c_void_p]),
+    "dxm_comm_p2p_enabled": (ctypes.c_int, []),
+    "dxm_comm_p2p_disable": (ctypes.c_int, []),
     "dxm_comm_size": (ctypes.c_int, []),
     "dxm_comm_rank": (ctypes.c_int, []),
     "dxm_comm_destroy": (ctypes.c_int, []),

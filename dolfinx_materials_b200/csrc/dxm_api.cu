@@ -179,8 +179,12 @@ double prop(const dxm_handle* h, int i) {
 StatSink stat_sink(const dxm_handle* h, int finalize) {
   StatSink k{};
   k.blk = h->d_statblk;
-  // multi-GPU: the record is all-gathered first and stats_publish_kernel writes the host record
-  k.out = (h->global_stats && dxm_comm::size() > 1) ? h->d_rec : h->h_rec;
+  const bool global = h->global_stats && dxm_comm::size() > 1;
+  const bool p2p = global && h->xslot >= 0 && dxm_comm::xchg();
+  // multi-GPU: over peer memory inside the kernel's epilogue, else all-gathered with NCCL and published by a second kernel
+  k.out = (global && !p2p) ? h->d_rec : h->h_rec;
+  k.xchg = p2p ? dxm_comm::xchg() : nullptr;
+  k.xslot = h->xslot;
   k.seq = h->seq;
   k.n_points = (unsigned long long)h->last.n_points;
   k.finalize = finalize;
@@ -370,7 +374,7 @@ int timed_update(dxm_handle* h, int64_t start, int64_t count, double dt, int fin
   if (timing) CK(cudaEventRecord(ev[1], h->stream));
   if (finalize) {
     h->finalize_launched = true;
-    if (h->global_stats && dxm_comm::size() > 1) {
+    if (h->global_stats && dxm_comm::size() > 1 && !(h->xslot >= 0 && dxm_comm::xchg())) {
       if (dxm_comm::all_gather(h->d_rec, h->d_gather, sizeof(StatRecord), h->stream)) return -1;
       stats_publish_kernel<<<1, 32, 0, h->stream>>>(h->d_gather, dxm_comm::size(), h->h_rec, h->seq);
       LAUNCH_CHECK();
@@ -421,6 +425,8 @@ int finish_stats(dxm_handle* h) {
   stat_decode(w, np, nf, mi, rb, npts);
   s.n_points = (int64_t)npts;
   s.n_plastic = (int64_t)np;
+  if (nf & kStatTimeoutBit)
+    return fail("dxm: a peer's statistics record never arrived (did every rank call integrate on this material?)");
   s.n_fail = (int64_t)nf;
   s.max_iter = (int64_t)mi;
   std::memcpy(&s.max_residual, &rb, sizeof(double));
@@ -1069,6 +1075,7 @@ int dxm_use_global_stats(dxm_handle* h, int on) {
   if (on) {
     if (dxm_comm::size() < 2) return fail("dxm_use_global_stats: no multi-rank communicator (dxm_comm_init)");
     if (!h->d_gather) CK(cudaMalloc(&h->d_gather, sizeof(StatRecord) * dxm_comm::size()));
+    if (h->xslot < 0 && dxm_comm::xchg()) h->xslot = dxm_comm::xchg_slot();  // same creation order on every rank
   }
   h->global_stats = on != 0;
   return 0;

@@ -161,12 +161,25 @@ struct StatRecord {  // 64 bytes
   unsigned long long w[kStatWords];  // tag<<48 | {n_plastic, n_fail, max_iter<<32 | resid_hi, resid_lo, n_points}
   unsigned long long pad[8 - kStatWords];
 };
+// Multi-GPU, one node: every rank maps every other rank's exchange buffer (cudaIpc, NVLink / NVSwitch peer memory).  The
+// CTA that publishes a call's record stores it into slot [xslot][my rank] of EVERY rank's buffer, waits until the records
+// of all ranks have arrived in its own buffer, folds them (SUM counts and points, MAX iterations / residual) and writes
+// the global record to the host -- the collective is part of the update kernel's epilogue: no NCCL call, no extra launch.
+constexpr int kXchgMaxRanks = 16;
+constexpr int kXchgSlots = 256;  // handles with global statistics per process
+struct StatXchg {
+  StatRecord* peer[kXchgMaxRanks];  // peer[r]: rank r's buffer [kXchgSlots][nranks], peer-mapped; peer[rank] is local
+  int nranks, rank;
+};
 struct StatSink {
   StatBlock* blk;
-  StatRecord* out;  // mapped host memory, or the device record a multi-GPU run all-gathers before publishing
+  StatRecord* out;  // mapped host memory, or the device record a multi-GPU run all-gathers with NCCL before publishing
   unsigned long long seq, n_points;
   int finalize;  // 1: this launch is the last one of the call; 2: ... and also its only one (clean slots)
+  const StatXchg* xchg;  // non-null: exchange the record over peer memory (then `out` is the mapped host record)
+  int xslot;
 };
+constexpr unsigned long long kStatTimeoutBit = 1ull << 47;  // set in n_fail when a peer's record never arrived
 
 struct PointStats {
   unsigned n_plastic = 0, n_fail = 0, max_iter = 0;
@@ -203,6 +216,52 @@ __device__ __forceinline__ void publish_record(StatRecord* r, unsigned long long
   for (int i = 0; i < kStatWords; ++i) *reinterpret_cast<volatile unsigned long long*>(&r->w[i]) = w[i];
 }
 
+// The publishing warp (all 32 lanes, each holding the call's totals): local record, or exchange + fold over peer memory.
+__device__ __forceinline__ void finish_record(const StatSink& sink, unsigned long long a, unsigned long long b,
+                                              unsigned long long c, unsigned long long d, const int l) {
+  if (!sink.xchg) {
+    if (l == 0) publish_record(sink.out, a, b, c, d, sink.n_points, sink.seq);
+    return;
+  }
+  const StatXchg& x = *sink.xchg;
+  const int nr = x.nranks;
+  // lane r stores this rank's record into rank r's buffer (self-validating words: no fence, any arrival order) ...
+  if (l < nr) publish_record(x.peer[l] + (size_t)sink.xslot * nr + x.rank, a, b, c, d, sink.n_points, sink.seq);
+  // ... and waits for rank r's record in this rank's own buffer (bounded: ~1 s, then the call is flagged)
+  unsigned long long ra = 0, rb = 0, rc = 0, rd = 0, rn = 0;
+  bool timed_out = false;
+  if (l < nr) {
+    const volatile unsigned long long* rec = (x.peer[x.rank] + (size_t)sink.xslot * nr + l)->w;
+    const unsigned long long tag = sink.seq & 0xffffull;
+    unsigned long long w[kStatWords];
+    bool ready = false;
+    for (unsigned spin = 0; spin < 4000000u && !ready; ++spin) {
+      ready = true;
+#pragma unroll
+      for (int i = 0; i < kStatWords; ++i) {
+        w[i] = rec[i];
+        ready = ready && (w[i] >> 48) == tag;
+      }
+    }
+    if (ready)
+      stat_decode(w, ra, rb, rc, rd, rn);
+    else
+      timed_out = true;
+  }
+  const bool any_timeout = __any_sync(0xffffffffu, timed_out);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ra += __shfl_xor_sync(0xffffffffu, ra, o);
+    rb += __shfl_xor_sync(0xffffffffu, rb, o);
+    rn += __shfl_xor_sync(0xffffffffu, rn, o);
+    const unsigned long long c2 = __shfl_xor_sync(0xffffffffu, rc, o);
+    rc = c2 > rc ? c2 : rc;
+    const unsigned long long d2 = __shfl_xor_sync(0xffffffffu, rd, o);
+    rd = d2 > rd ? d2 : rd;
+  }
+  if (l == 0) publish_record(sink.out, ra, any_timeout ? (rb | kStatTimeoutBit) : rb, rc, rd, rn, sink.seq);
+}
+
 __device__ __forceinline__ void block_reduce_stats(const PointStats& s, const StatSink& sink) {
   unsigned np = __reduce_add_sync(0xffffffffu, s.n_plastic);
   unsigned nf = __reduce_add_sync(0xffffffffu, s.n_fail);
@@ -237,12 +296,13 @@ __device__ __forceinline__ void block_reduce_stats(const PointStats& s, const St
       unsigned long long d2 = __shfl_xor_sync(0xffffffffu, d, o);
       d = d2 > d ? d2 : d;
     }
-    if (l == 0) {
+    if (sink.finalize == 2 && gridDim.x == 1) {
+      // the call is this one CTA: its totals are the record
+      finish_record(sink, a, b, c, d, l);
+      if (l == 0) s_last = 0;
+    } else if (l == 0) {
       int last = 0;
-      if (sink.finalize == 2 && gridDim.x == 1) {
-        // the call is this one CTA: its totals are the record
-        publish_record(sink.out, a, b, c, d, sink.n_points, sink.seq);
-      } else {
+      {
         StatSlot* s2 = sink.blk->slot + (blockIdx.x % kStatSlots);
         if (a) atomicAdd(&s2->n_plastic, a);
         if (b) atomicAdd(&s2->n_fail, b);
@@ -276,10 +336,8 @@ __device__ __forceinline__ void block_reduce_stats(const PointStats& s, const St
       unsigned long long d2 = __shfl_xor_sync(0xffffffffu, d, o);
       d = d2 > d ? d2 : d;
     }
-    if (l == 0) {
-      sink.blk->ticket = 0u;
-      publish_record(sink.out, a, b, c, d, sink.n_points, sink.seq);
-    }
+    if (l == 0) sink.blk->ticket = 0u;
+    finish_record(sink, a, b, c, d, l);
   }
 }
 

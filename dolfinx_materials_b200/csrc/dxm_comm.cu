@@ -4,6 +4,11 @@
 // (dxm_use_global_stats).  The constitutive update itself has no exchange step: Gauss points are
 // independent, state never leaves its GPU.
 //
+// On one node the all-gather does not go through NCCL at all: every rank maps every other rank's exchange buffer
+// (cudaIpc handles over NVLink / NVSwitch) and the update kernel's publishing CTA stores its record into all of them,
+// waits for the peers' records in its own buffer and folds them -- the collective is part of the kernel's epilogue
+// (csrc/dxm_canon.cuh::finish_record).  NCCL stays as the fallback when peer mapping is not available.
+//
 // NCCL is not linked: the functions are looked up at run time in the libnccl.so.2 already loaded into the process (the
 // one PyTorch ships, when the caller is a torch.distributed program) or found by the dynamic loader (DXM_NCCL_LIB
 // overrides the name).  The unique id travels between the ranks by whatever the caller has -- torch.distributed
@@ -29,6 +34,12 @@ struct Nccl {
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1, device = -1;
+  // peer-memory exchange
+  dxm::StatRecord* xchg_local = nullptr;            // [kXchgSlots][nranks]
+  dxm::StatRecord* xchg_peer[dxm::kXchgMaxRanks] = {};  // mapped peers (own entry = xchg_local)
+  dxm::StatXchg* d_desc = nullptr;                  // device copy of the descriptor the kernels read
+  bool p2p = false;
+  int next_slot = 0;
 } g;
 
 int load_nccl() {
@@ -56,6 +67,8 @@ int nccl_check(ncclResult_t r, const char* what) {
 }  // namespace
 
 namespace dxm_comm {
+const dxm::StatXchg* xchg() { return g.p2p ? g.d_desc : nullptr; }
+int xchg_slot() { return g.next_slot < dxm::kXchgSlots ? g.next_slot++ : -1; }
 int size() { return g.comm ? g.nranks : 1; }
 int rank() { return g.comm ? g.rank : 0; }
 
@@ -92,6 +105,65 @@ int dxm_comm_init(const void* id128, int rank, int nranks, int device) {
   return 0;
 }
 
+// Peer-memory exchange, step 1: allocate this rank's buffer and hand out its 64-byte cudaIpc handle.
+int dxm_comm_p2p_handle(void* handle64) {
+  if (!handle64) return fail("dxm_comm_p2p_handle: NULL argument");
+  if (!g.comm) return fail("dxm_comm_p2p_handle: no communicator (dxm_comm_init)");
+  if (g.nranks > dxm::kXchgMaxRanks) return fail("dxm_comm_p2p_handle: too many ranks for the peer-memory exchange");
+  CK(cudaSetDevice(g.device));
+  const size_t bytes = sizeof(dxm::StatRecord) * dxm::kXchgSlots * g.nranks;
+  if (!g.xchg_local) {
+    CK(cudaMalloc((void**)&g.xchg_local, bytes));
+    CK(cudaMemset(g.xchg_local, 0, bytes));
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t hd;
+  CK(cudaIpcGetMemHandle(&hd, g.xchg_local));
+  std::memcpy(handle64, &hd, 64);
+  return 0;
+}
+
+// Step 2 (after the caller gathered the handles of all ranks, rank order): map the peers.  On failure the exchange stays
+// off and global statistics go through NCCL.
+int dxm_comm_p2p_connect(const void* handles) {
+  if (!handles || !g.comm || !g.xchg_local) return fail("dxm_comm_p2p_connect: call dxm_comm_p2p_handle first");
+  CK(cudaSetDevice(g.device));
+  dxm::StatXchg desc{};
+  desc.nranks = g.nranks;
+  desc.rank = g.rank;
+  for (int r = 0; r < g.nranks; ++r) {
+    if (r == g.rank) {
+      g.xchg_peer[r] = g.xchg_local;
+    } else {
+      cudaIpcMemHandle_t hd;
+      std::memcpy(&hd, (const char*)handles + 64 * r, 64);
+      void* p = nullptr;
+      const cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        for (int q = 0; q < r; ++q)
+          if (q != g.rank && g.xchg_peer[q]) cudaIpcCloseMemHandle(g.xchg_peer[q]);
+        for (int q = 0; q < dxm::kXchgMaxRanks; ++q) g.xchg_peer[q] = nullptr;
+        return fail(std::string("dxm_comm_p2p_connect: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+      }
+      g.xchg_peer[r] = (dxm::StatRecord*)p;
+    }
+    desc.peer[r] = g.xchg_peer[r];
+  }
+  if (!g.d_desc) CK(cudaMalloc((void**)&g.d_desc, sizeof(dxm::StatXchg)));
+  CK(cudaMemcpy(g.d_desc, &desc, sizeof(desc), cudaMemcpyHostToDevice));
+  g.p2p = true;
+  return 0;
+}
+
+int dxm_comm_p2p_enabled(void) { return g.p2p ? 1 : 0; }
+
+// every rank must end up with the same answer: the caller switches the exchange off everywhere if any rank failed
+int dxm_comm_p2p_disable(void) {
+  g.p2p = false;
+  return 0;
+}
+
 int dxm_comm_size(void) { return dxm_comm::size(); }
 int dxm_comm_rank(void) { return dxm_comm::rank(); }
 
@@ -99,6 +171,16 @@ int dxm_comm_destroy(void) {
   if (!g.comm) return 0;
   cudaSetDevice(g.device);
   cudaDeviceSynchronize();
+  for (int q = 0; q < dxm::kXchgMaxRanks; ++q) {
+    if (q != g.rank && g.xchg_peer[q]) cudaIpcCloseMemHandle(g.xchg_peer[q]);
+    g.xchg_peer[q] = nullptr;
+  }
+  cudaFree(g.xchg_local);
+  cudaFree(g.d_desc);
+  g.xchg_local = nullptr;
+  g.d_desc = nullptr;
+  g.p2p = false;
+  g.next_slot = 0;
   const ncclResult_t r = g.CommDestroy(g.comm);
   g.comm = nullptr;
   g.nranks = 1;

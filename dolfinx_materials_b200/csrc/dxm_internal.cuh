@@ -77,6 +77,7 @@ struct dxm_handle {
   unsigned long long seq = 0;            // sequence number of the last call launched on this handle
   bool finalize_launched = false;        // the call's last launch (the one that publishes) has been enqueued
   bool global_stats = false;             // reduce over the ranks of the library's communicator (dxm_comm_init)
+  int xslot = -1;                        // >= 0: this handle's slot in the peer-memory exchange buffers (else: NCCL)
   int timing = -1;                       // kernel_ms events: -1 auto (batches >= 262144 points), 0 never, 1 always
   dxm_stats last{};
   bool stats_pending = false;
@@ -113,6 +114,8 @@ namespace dxm_comm {
 int size();
 int rank();
 int all_gather(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t stream);
+const dxm::StatXchg* xchg();  // device descriptor of the peer-memory exchange, or null (then: NCCL)
+int xchg_slot();              // next free exchange slot (same order on every rank), -1 when exhausted
 }  // namespace dxm_comm
 
 inline int set_device(const dxm_handle* h) {

@@ -79,6 +79,24 @@ def init_stats_comm(group=None, device=None):
     dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     ident = ctypes.create_string_buffer(box[0], 128)
     check(lib.dxm_comm_init(ident, rank, world, default_device() if device is None else int(device)), "dxm_comm_init")
+    # One node: exchange the records over peer memory inside the update kernel's epilogue instead of calling NCCL --
+    # every rank maps every other rank's exchange buffer (cudaIpc over NVLink).  All ranks or none.
+    import os
+
+    if os.environ.get("DXM_STATS_P2P", "1") not in ("", "0"):
+        hbuf = ctypes.create_string_buffer(64)
+        ok = lib.dxm_comm_p2p_handle(hbuf) == 0
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (ok, bytes(hbuf.raw)), group=group)
+        if all(g[0] for g in gathered):
+            blob = ctypes.create_string_buffer(b"".join(g[1] for g in gathered), 64 * world)
+            ok = lib.dxm_comm_p2p_connect(blob) == 0
+        else:
+            ok = False
+        flags = [None] * world
+        dist.all_gather_object(flags, ok, group=group)
+        if not all(flags):
+            lib.dxm_comm_p2p_disable()
     return lib.dxm_comm_size()
 
 

@@ -134,7 +134,16 @@ int dxm_enable_timing(dxm_handle* h, int mode);
  * Replaces what `MPI.COMM_WORLD.allreduce` of a failure flag would do around QuadratureMap.update under dolfinx.
  *   dxm_comm_unique_id : rank 0 fills a 128-byte id, the caller broadcasts it (torch.distributed / MPI_Bcast)
  *   dxm_comm_init      : collective over all ranks; device = this rank's GPU
- *   dxm_use_global_stats(h, 1) : this handle's dxm_stats become global (every rank must then call dxm_integrate on it) */
+ *   dxm_use_global_stats(h, 1) : this handle's dxm_stats become global (every rank must then call dxm_integrate on it)
+ * On one node the records do not even go through NCCL: dxm_comm_p2p_handle (64-byte cudaIpc handle of this rank's
+ * exchange buffer) -> the caller gathers the handles of all ranks, rank order -> dxm_comm_p2p_connect maps them; the
+ * update kernel's publishing CTA then stores its record into every peer's buffer over NVLink, waits for the peers'
+ * records and folds them itself -- no collective call, no extra launch.  If any rank cannot map its peers, call
+ * dxm_comm_p2p_disable on all ranks: NCCL stays the fallback. */
+int dxm_comm_p2p_handle(void* handle64);
+int dxm_comm_p2p_connect(const void* handles /* nranks x 64 bytes */);
+int dxm_comm_p2p_enabled(void);
+int dxm_comm_p2p_disable(void);
 int dxm_comm_unique_id(void* id128);
 int dxm_comm_init(const void* id128, int rank, int nranks, int device);
 int dxm_comm_size(void);
