@@ -18,7 +18,7 @@ std::atomic<long long> g_launches{0};
 namespace {
 constexpr int64_t kChunk = 1 << 19;  // points per pipeline chunk on the host path
 const char* kPropNames[kNProp] = {"E", "nu", "sig0", "H", "sigu", "b"};
-constexpr double kHosSplitMaxPlastic = 0.45;  // Hosford: fused kernel above this plastic fraction (previous call)
+constexpr double kHosSplitMaxPlastic = 0.30;  // Hosford: fused kernel above this plastic fraction (previous call)
 constexpr int64_t kAutoTimingPoints = 1 << 18;  // kernel_ms events by default only where two event records are noise
 constexpr bool kHostMirrorDefault = false;  // A/B on the B200 box: profiles/ (DXM_HOST_MIRROR overrides)
 }  // namespace
@@ -279,8 +279,8 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt, int fi
     a.hos_a = h->hos_a;
     a.hos_bound = hosford_bound(h->hos_a);
     // Tiled kernel (stream a tile, pack the candidates into full warps) or the fused one.  Tiling wins while a good
-    // part of the batch is elastic (6.5 vs 4.8 G points/s at 3 % plastic); when most points are plastic its extra
-    // pass costs more than the packing gains (crossover at 40-50 % plastic, profiles/r02c_hosford_ab_*.json), and small
+    // part of the batch is elastic (6.6 vs 5.3 G points/s at 3 % plastic); when more points are plastic its extra
+    // pass costs more than the packing gains (4.05 vs 4.25 G at 40 %: crossover near 30 %, profiles/r02l_configs.json), and small
     // batches are latency-bound either way: auto mode keys on the batch size and on the plastic fraction of the
     // previous call.  DXM_HOS_SPLIT=0|1 forces fused | tiled.  (A warp-private queue -- every heavy pass a full warp, no
     // block barrier -- was also measured in round 2: same times as the tiled kernel to 2-5 %; the local solves are bound

@@ -23,7 +23,13 @@ def close(a, b, what=""):
     np.testing.assert_allclose(a, b, rtol=RTOL, atol=RTOL * scale, err_msg=what)
 
 
-def same_active_set(out, ref):
+def same_active_set(out, ref, borderline=0.0):
+    """Identical active sets and local iteration counts.  ``borderline``: fraction of points whose count may differ by
+    ONE -- a local Newton whose residual lands within rounding of its tolerance stops one step earlier or later when the
+    last bits of the arithmetic change (fused vs un-fused); only the Hosford solve, with its 4 residuals, meets such
+    points (about 1 in 60 000)."""
     assert np.array_equal(out["flag"], ref["flag"]), "active sets differ"
-    assert np.array_equal(out["n_iter"], ref["n_iter"]), "local iteration counts differ"
+    diff = np.abs(out["n_iter"].astype(int) - ref["n_iter"].astype(int))
+    assert diff.max(initial=0) <= (1 if borderline else 0), "local iteration counts differ"
+    assert (diff != 0).mean() <= borderline, "local iteration counts differ"
     assert np.array_equal(out["fail"], ref["fail"])

@@ -67,7 +67,7 @@ def test_fused_vs_round1_arithmetic(kind):
             for k in fields + ("flag", "n_iter", "resid", "fail"):
                 assert np.array_equal(out_py[k], out[k]), k
                 assert np.array_equal(ref_py[k], ref[k]), k
-        same_active_set(out, ref)
+        same_active_set(out, ref, borderline=1e-4 if kind == "hosford" else 0.0)
         for k in fields:
             close(out[k], ref[k], k)
             worst = max(worst, float(np.max(np.abs(out[k] - ref[k])) / np.max(np.abs(ref[k]))))

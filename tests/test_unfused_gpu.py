@@ -25,7 +25,10 @@ def test_unfused_build_is_round1_and_fused_build_is_within_tolerance():
     old, new = _run(True), _run(False)
     assert old["unfused"] == "1" and new["unfused"] == "0"
     for name, h in old["histories"].items():
-        assert h["bit_identical"], f"{name}: the un-fused build no longer reproduces the round-1 fixture"
+        if name.startswith("hosford"):  # its a-th root iteration changed in round 2 (fixed count): tolerance, not bits
+            assert h["max_rel_dev"] < 1e-10, (name, h)
+        else:
+            assert h["bit_identical"], f"{name}: the un-fused build no longer reproduces the round-1 fixture"
     for name, h in new["histories"].items():
         assert h["max_rel_dev"] < 1e-10, (name, h)
     assert not all(h["bit_identical"] for h in new["histories"].values())  # the two arithmetics do differ in the last bits
