@@ -172,9 +172,9 @@ struct HosRes {
   double rs[3], r4, m2, dsy;
 };
 
-DXM_HD void hos_residual(const double (&x)[3], double dp, const double (&l)[3], double twomu, const HosHard& hd,
-                         int a, double inv_a, HosRes& o) {
-  hos_eval(x, a, inv_a, o.e);
+// residuals of the 4 unknowns (x, dp) from the criterion data o.e already evaluated at x
+DXM_HD void hos_residual_finish(const double (&x)[3], double dp, const double (&l)[3], double twomu, const HosHard& hd,
+                                HosRes& o) {
   const double c = twomu * dp;
 #pragma unroll
   for (int k = 0; k < 3; ++k) o.rs[k] = fma_c(c, o.e.n[k], x[k] - l[k]);
@@ -294,12 +294,15 @@ DXM_HD void hos_newton(const double (&l)[3], const double mu, const HosHard& hd,
   int ls = 0, stage = 0;
 #pragma unroll
   for (int k = 0; k < 3; ++k) xe[k] = l[k];
-  // One evaluation site for the three uses of the residual (trial state, start point, line-search candidates):
-  // stage 0 = yield check at the trial state, 1 = start point, 2 = line-search candidate of a Newton step.
+  // One evaluation site of the criterion for its two uses (trial state, line-search candidates of a Newton step):
+  // stage 0 = yield check at the trial state, 1 = start point, 2 = line-search candidate.  The start point is the trial
+  // state scaled radially onto the yield surface: the criterion is homogeneous of degree one, so its data there follow
+  // from the trial evaluation (phi scales, n / h / u do not change) -- no second evaluation.
   double m_prev = 0.0;
   for (;;) {
     // evaluated in place: once the step (dx, ddp) is formed only the merit value of the previous iterate is needed
-    hos_residual(xe, dpe, l, twomu, hd, a, inv_a, o.cur);
+    if (stage != 1) hos_eval(xe, a, inv_a, o.cur.e);
+    hos_residual_finish(xe, dpe, l, twomu, hd, o.cur);
     if (stage == 0) {
       const double f = o.cur.e.phi - sy0;
       o.flag = f > 0.0;
@@ -311,6 +314,8 @@ DXM_HD void hos_newton(const double (&l)[3], const double mu, const HosHard& hd,
       const double sc = sy1 / o.cur.e.phi;
 #pragma unroll
       for (int k = 0; k < 3; ++k) xe[k] = l[k] * sc;
+      o.cur.e.phi = o.cur.e.phi * sc;
+      o.cur.e.iphi = o.cur.e.iphi / sc;
       stage = 1;
       continue;
     }

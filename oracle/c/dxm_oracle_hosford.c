@@ -153,15 +153,20 @@ typedef struct {
   double rs[3], r4, phi, iphi, n[3], h[3], u[3], m2, dsy;
 } hres_t;
 
-static void hosford_residual(const double x[3], double dp, const double l[3], double twomu, const hard_t* hd, int a,
-                             double inv_a, hres_t* o) {
-  hosford_eval(x, a, inv_a, &o->phi, &o->iphi, o->n, o->h, o->u);
+/* residuals of the 4 unknowns (x, dp) from the criterion data (phi, n, ...) already evaluated at x */
+static void residual_finish(const double x[3], double dp, const double l[3], double twomu, const hard_t* hd, hres_t* o) {
   const double c = twomu * dp;
   for (int k = 0; k < 3; ++k) o->rs[k] = FMA(c, o->n[k], x[k] - l[k]);
   double sy;
   hard_eval(hd, dp, &sy, &o->dsy);
   o->r4 = o->phi - sy;
   o->m2 = FMA(o->r4, o->r4, FMA(o->rs[2], o->rs[2], FMA(o->rs[1], o->rs[1], o->rs[0] * o->rs[0])));
+}
+
+static void hosford_residual(const double x[3], double dp, const double l[3], double twomu, const hard_t* hd, int a,
+                             double inv_a, hres_t* o) {
+  hosford_eval(x, a, inv_a, &o->phi, &o->iphi, o->n, o->h, o->u);
+  residual_finish(x, dp, l, twomu, hd, o);
 }
 
 /* A = I + c k1 (M/2 - n n^T) (symmetric), its adjugate C and 1/det */
@@ -238,7 +243,11 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
         hard_eval(&hd, dp, &sy1, &dsy1);
         const double sc = sy1 / cur.phi;
         double x[3] = {l[0] * sc, l[1] * sc, l[2] * sc};
-        hosford_residual(x, dp, l, twomu, &hd, a, inv_a, &cur);
+        /* the criterion is homogeneous of degree one: its data at the radially scaled start point follow from the trial
+         * evaluation (phi scales, n / h / u do not change) -- no second evaluation */
+        cur.phi = cur.phi * sc;
+        cur.iphi = cur.iphi / sc;
+        residual_finish(x, dp, l, twomu, &hd, &cur);
         const double tol = rtol * seq;
         for (int it = 0;; ++it) {
           const double res = fmax(fmax(fabs(cur.rs[0]), fabs(cur.rs[1])), fmax(fabs(cur.rs[2]), fabs(cur.r4)));
