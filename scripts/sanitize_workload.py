@@ -31,3 +31,14 @@ coords, gd, ud, nodes = nb.bar_mesh(3, 1, 1)
 ge = GradientEvaluator(mat, coords, gd, ud, nb.p2_tet_dphi(nb.QP_DEG2)); ge.eval(u); mat.integrate_resident()
 ElementForms(ge, nb.W_DEG2).compute()
 print("sanitize workload ok", info["newton_iterations"])
+# round 2: the atomic-free per-node gather assembly, the asynchronous / ranged statistics paths, small-batch launches
+os.environ["DXM_FE_GATHER"] = "1"
+u2, mat2, info2, _ = nb.run_gpu(3, 2, 1, steps=1, strain=0.012, ksp_rtol=1e-10, verbose=False)
+del os.environ["DXM_FE_GATHER"]
+for nn in (1, 63, 64, 65, 5000):
+    ms = jm.CUDAMaterial(jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=jm.VoceHardening(sig0=350.0, sigu=500.0, b=1e3)))
+    ms.set_data_manager(nn); ms.synth_gradients(0, 1.25e-2, 1, 1)
+    ms.integrate_resident(); ms.integrate_resident(wait=False); ms.fetch_stats()
+    ms.enable_timing(1); ms.integrate_resident()
+ms.integrate_range_into(0, 2000, synth.strain(2000, 0, 1e-2, 1, 1), np.empty((2000, 6)), None, np.empty((2000, 36)))
+print("sanitize workload (round 2 additions) ok", info2["newton_iterations"])
