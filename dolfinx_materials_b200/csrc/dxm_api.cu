@@ -180,7 +180,7 @@ StatSink stat_sink(const dxm_handle* h, int finalize) {
   StatSink k{};
   k.blk = h->d_statblk;
   const bool global = h->global_stats && dxm_comm::size() > 1;
-  const bool p2p = global && h->xslot >= 0 && dxm_comm::xchg();
+  const bool p2p = global && h->xslot >= 0 && h->xgen == dxm_comm::generation() && dxm_comm::xchg();
   // multi-GPU: over peer memory inside the kernel's epilogue, else all-gathered with NCCL and published by a second kernel
   k.out = (global && !p2p) ? h->d_rec : h->h_rec;
   k.xchg = p2p ? dxm_comm::xchg() : nullptr;
@@ -374,7 +374,8 @@ int timed_update(dxm_handle* h, int64_t start, int64_t count, double dt, int fin
   if (timing) CK(cudaEventRecord(ev[1], h->stream));
   if (finalize) {
     h->finalize_launched = true;
-    if (h->global_stats && dxm_comm::size() > 1 && !(h->xslot >= 0 && dxm_comm::xchg())) {
+    if (h->global_stats && dxm_comm::size() > 1 &&
+        !(h->xslot >= 0 && h->xgen == dxm_comm::generation() && dxm_comm::xchg())) {
       if (dxm_comm::all_gather(h->d_rec, h->d_gather, sizeof(StatRecord), h->stream)) return -1;
       stats_publish_kernel<<<1, 32, 0, h->stream>>>(h->d_gather, dxm_comm::size(), h->h_rec, h->seq);
       LAUNCH_CHECK();
@@ -1075,7 +1076,15 @@ int dxm_use_global_stats(dxm_handle* h, int on) {
   if (on) {
     if (dxm_comm::size() < 2) return fail("dxm_use_global_stats: no multi-rank communicator (dxm_comm_init)");
     if (!h->d_gather) CK(cudaMalloc(&h->d_gather, sizeof(StatRecord) * dxm_comm::size()));
-    if (h->xslot < 0 && dxm_comm::xchg()) h->xslot = dxm_comm::xchg_slot();  // same creation order on every rank
+    if ((h->xslot < 0 || h->xgen != dxm_comm::generation()) && dxm_comm::xchg()) {
+      h->xslot = dxm_comm::xchg_slot();  // same order on every rank
+      h->xgen = dxm_comm::generation();
+    }
+    if (h->d_gather && h->xgen != dxm_comm::generation()) {  // a new communicator may have another size
+      cudaFree(h->d_gather);
+      h->d_gather = nullptr;
+      CK(cudaMalloc(&h->d_gather, sizeof(StatRecord) * dxm_comm::size()));
+    }
   }
   h->global_stats = on != 0;
   return 0;

@@ -168,7 +168,10 @@ struct StatRecord {  // 64 bytes
 constexpr int kXchgMaxRanks = 16;
 constexpr int kXchgSlots = 256;  // handles with global statistics per process
 struct StatXchg {
-  StatRecord* peer[kXchgMaxRanks];  // peer[r]: rank r's buffer [kXchgSlots][nranks], peer-mapped; peer[rank] is local
+  // peer[r]: rank r's buffer [kXchgSlots][2][nranks], peer-mapped; peer[rank] is local.  Two record sets per slot, used
+  // alternately by call parity: a fast rank's record of call k+1 can then never overwrite its record of call k while a
+  // slower rank is still reading it (k+2 needs the slower rank's k+1, which it sends only after finishing k).
+  StatRecord* peer[kXchgMaxRanks];
   int nranks, rank;
 };
 struct StatSink {
@@ -225,13 +228,14 @@ __device__ __forceinline__ void finish_record(const StatSink& sink, unsigned lon
   }
   const StatXchg& x = *sink.xchg;
   const int nr = x.nranks;
+  const size_t set = ((size_t)sink.xslot * 2 + (size_t)(sink.seq & 1ull)) * nr;
   // lane r stores this rank's record into rank r's buffer (self-validating words: no fence, any arrival order) ...
-  if (l < nr) publish_record(x.peer[l] + (size_t)sink.xslot * nr + x.rank, a, b, c, d, sink.n_points, sink.seq);
+  if (l < nr) publish_record(x.peer[l] + set + x.rank, a, b, c, d, sink.n_points, sink.seq);
   // ... and waits for rank r's record in this rank's own buffer (bounded: ~1 s, then the call is flagged)
   unsigned long long ra = 0, rb = 0, rc = 0, rd = 0, rn = 0;
   bool timed_out = false;
   if (l < nr) {
-    const volatile unsigned long long* rec = (x.peer[x.rank] + (size_t)sink.xslot * nr + l)->w;
+    const volatile unsigned long long* rec = (x.peer[x.rank] + set + l)->w;
     const unsigned long long tag = sink.seq & 0xffffull;
     unsigned long long w[kStatWords];
     bool ready = false;

@@ -35,7 +35,8 @@ struct Nccl {
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1, device = -1;
   // peer-memory exchange
-  dxm::StatRecord* xchg_local = nullptr;            // [kXchgSlots][nranks]
+  dxm::StatRecord* xchg_local = nullptr;            // [kXchgSlots][2][nranks]
+  unsigned generation = 0;                          // bumped by every dxm_comm_init: slots belong to one communicator
   dxm::StatRecord* xchg_peer[dxm::kXchgMaxRanks] = {};  // mapped peers (own entry = xchg_local)
   dxm::StatXchg* d_desc = nullptr;                  // device copy of the descriptor the kernels read
   bool p2p = false;
@@ -69,6 +70,7 @@ int nccl_check(ncclResult_t r, const char* what) {
 namespace dxm_comm {
 const dxm::StatXchg* xchg() { return g.p2p ? g.d_desc : nullptr; }
 int xchg_slot() { return g.next_slot < dxm::kXchgSlots ? g.next_slot++ : -1; }
+unsigned generation() { return g.generation; }
 int size() { return g.comm ? g.nranks : 1; }
 int rank() { return g.comm ? g.rank : 0; }
 
@@ -99,6 +101,7 @@ int dxm_comm_init(const void* id128, int rank, int nranks, int device) {
   ncclComm_t c = nullptr;
   if (nccl_check(g.CommInitRank(&c, nranks, id, rank), "ncclCommInitRank")) return -1;
   g.comm = c;
+  ++g.generation;
   g.rank = rank;
   g.nranks = nranks;
   g.device = device;
@@ -111,7 +114,7 @@ int dxm_comm_p2p_handle(void* handle64) {
   if (!g.comm) return fail("dxm_comm_p2p_handle: no communicator (dxm_comm_init)");
   if (g.nranks > dxm::kXchgMaxRanks) return fail("dxm_comm_p2p_handle: too many ranks for the peer-memory exchange");
   CK(cudaSetDevice(g.device));
-  const size_t bytes = sizeof(dxm::StatRecord) * dxm::kXchgSlots * g.nranks;
+  const size_t bytes = sizeof(dxm::StatRecord) * dxm::kXchgSlots * 2 * g.nranks;
   if (!g.xchg_local) {
     CK(cudaMalloc((void**)&g.xchg_local, bytes));
     CK(cudaMemset(g.xchg_local, 0, bytes));

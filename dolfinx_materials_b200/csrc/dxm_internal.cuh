@@ -78,6 +78,7 @@ struct dxm_handle {
   bool finalize_launched = false;        // the call's last launch (the one that publishes) has been enqueued
   bool global_stats = false;             // reduce over the ranks of the library's communicator (dxm_comm_init)
   int xslot = -1;                        // >= 0: this handle's slot in the peer-memory exchange buffers (else: NCCL)
+  unsigned xgen = 0;                     // communicator generation the slot was drawn from
   int timing = -1;                       // kernel_ms events: -1 auto (batches >= 262144 points), 0 never, 1 always
   dxm_stats last{};
   bool stats_pending = false;
@@ -116,6 +117,7 @@ int rank();
 int all_gather(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t stream);
 const dxm::StatXchg* xchg();  // device descriptor of the peer-memory exchange, or null (then: NCCL)
 int xchg_slot();              // next free exchange slot (same order on every rank), -1 when exhausted
+unsigned generation();        // which dxm_comm_init the slots belong to
 }  // namespace dxm_comm
 
 inline int set_device(const dxm_handle* h) {
