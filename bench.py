@@ -386,14 +386,17 @@ def run_ours(args):
     if world > 1:
         # statistics reduced over the ranks IN-STREAM: the library's own NCCL communicator all-gathers the 64-byte record
         # right after the update kernel (no host-side collective, no synchronisation added)
-        from dolfinx_materials_b200.distributed import init_stats_comm
+        from dolfinx_materials_b200.distributed import allreduce_stats, init_stats_comm
 
-        init_stats_comm()
-        m.use_global_stats()
+        in_stream = init_stats_comm() == world
+        if in_stream:
+            m.use_global_stats()
     m.enable_timing(1)
 
     def step():
-        return m.integrate_resident()
+        st = m.integrate_resident()
+        # fallback only (NCCL not loadable on this box): host-side reduction of the per-rank statistics
+        return allreduce_stats(st) if (world > 1 and not in_stream) else st
 
     def barrier():
         if world > 1:
@@ -448,7 +451,7 @@ def run_ours(args):
         """(e2e, e2e_exchange) with `ne` points per GPU crossing the host boundary every step"""
         e2e = e2e_x = None
         m.enable_timing(-1)
-        if world > 1:
+        if world > 1 and in_stream:
             m.use_global_stats(False)
         rng_pts = int(min(args.e2e_range, ne)) & ~1
         grads = PinnedArray((ne, 6))
@@ -634,7 +637,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=float, default=1e8, help="Gauss points per GPU")
+    ap.add_argument("--n", "--points", dest="n", type=float, default=1e8,
+                    help="Gauss points per GPU (under torchrun write --points: torchrun's own parser takes --n for an abbreviation)")
     ap.add_argument("--e2e-n", type=float, default=-1, help="Gauss points per GPU for the host-buffer e2e leg (default: --n, the same points as the device-resident leg; 0 skips it)")
     ap.add_argument("--e2e-range", type=float, default=1e7, help="points per ranged call (= size of the page-locked output window) of the e2e leg")
     ap.add_argument("--exchange-n", type=float, default=1e7, help="Gauss points per GPU for the QuadratureExchange.update leg (0 skips it)")

@@ -57,14 +57,15 @@ def init_stats_comm(group=None, device=None):
     """Create the library's own NCCL communicator over the ranks of the (already initialised) ``torch.distributed``
     process group: rank 0 draws the unique id, ``broadcast_object_list`` carries it (works on gloo and nccl groups),
     every rank joins.  After this ``CUDAMaterial.use_global_stats()`` makes a material's per-call statistics global
-    with one all-gather on the material's own stream -- no host-side collective, no synchronisation.
-    Returns the communicator size (1: nothing was created)."""
+    inside the update kernel's epilogue (records exchanged over peer memory) or, where peers cannot be mapped, with one
+    NCCL all-gather on the material's own stream -- no host-side collective, no synchronisation.
+    Returns the communicator size; 1 means nothing was created (single rank, or NCCL could not be loaded / joined on
+    some rank): callers then reduce on the host (``allreduce_stats``)."""
     import ctypes
 
     import torch.distributed as dist
 
     from . import _lib
-    from ._lib import check
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return 1
@@ -73,12 +74,22 @@ def init_stats_comm(group=None, device=None):
         return lib.dxm_comm_size()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     buf = ctypes.create_string_buffer(128)
-    if rank == 0:
-        check(lib.dxm_comm_unique_id(buf), "dxm_comm_unique_id")
-    box = [bytes(buf.raw)]
+    # every step is agreed on by all ranks: a rank that cannot load NCCL or join must not leave the others waiting in a
+    # collective -- the function then returns 1 everywhere and callers fall back to a host-side reduction
+    box = [None]
+    if rank == 0 and lib.dxm_comm_unique_id(buf) == 0:
+        box = [bytes(buf.raw)]
     dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if box[0] is None:
+        return 1
     ident = ctypes.create_string_buffer(box[0], 128)
-    check(lib.dxm_comm_init(ident, rank, world, default_device() if device is None else int(device)), "dxm_comm_init")
+    joined = lib.dxm_comm_init(ident, rank, world, default_device() if device is None else int(device)) == 0
+    flags = [None] * world
+    dist.all_gather_object(flags, joined, group=group)
+    if not all(flags):
+        if joined:
+            lib.dxm_comm_destroy()
+        return 1
     # One node: exchange the records over peer memory inside the update kernel's epilogue instead of calling NCCL --
     # every rank maps every other rank's exchange buffer (cudaIpc over NVLink).  All ranks or none.
     import os

@@ -147,8 +147,8 @@ def run_gpu(nx, ny, nz, steps=3, strain=0.01, L=10.0, W=1.0, newton_rtol=1e-8, n
     if world > 1:
         # failure / active-set counts and residual maxima reduced over the ranks in-stream: the library's NCCL
         # communicator all-gathers the 64-byte record right after the update kernel (no host-side collective)
-        init_stats_comm()
-        mat.use_global_stats()
+        if init_stats_comm() == world:
+            mat.use_global_stats()
     mat.enable_timing(1)
     ge = GradientEvaluator(mat, coords, gd[c0:c1], ud[c0:c1], dphi, tdim=3, num_dofs=len(nodes))
     forms = ElementForms(ge, W_DEG2)
