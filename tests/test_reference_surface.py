@@ -1,0 +1,88 @@
+"""The drop-in ``GPUQuadratureMap`` (``dolfinx_materials_b200/quadrature_map.py``) subclasses the reference's
+``QuadratureMap`` at run time, and the tests exercise it against a stand-in of that class (``tests/qmap_standin.py``)
+because dolfinx is not importable here.  This test ties both to the reference's ACTUAL source: it parses
+``dolfinx_materials/quadrature_map.py`` and ``quadrature_function.py`` (AST only: nothing is imported or executed) and
+checks that every attribute and method of the base class the adapter touches, and every one the stand-in models, exists
+there with the arity the adapter uses -- so the stand-in cannot drift away from the class it stands in for unnoticed.
+CPU only; skipped where the reference tree is absent (it is not shipped to the GPU box)."""
+import ast
+import os
+
+import pytest
+
+REF = "/root/reference/dolfinx_materials"
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _class(path, name):
+    tree = ast.parse(open(path).read())
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == name:
+            return node
+    raise AssertionError(f"class {name} not found in {path}")
+
+
+def _surface(cls):
+    """methods (name -> positional parameter names), properties and the attributes assigned as ``self.x = ...``"""
+    methods, props, attrs = {}, set(), set()
+    for node in cls.body:
+        if isinstance(node, ast.FunctionDef):
+            is_prop = any(isinstance(d, ast.Name) and d.id == "property" for d in node.decorator_list)
+            (props.add(node.name) if is_prop else methods.__setitem__(node.name, [a.arg for a in node.args.args]))
+            for sub in ast.walk(node):
+                if isinstance(sub, (ast.Assign, ast.AugAssign, ast.AnnAssign)):
+                    targets = sub.targets if isinstance(sub, ast.Assign) else [sub.target]
+                    for t in targets:
+                        if isinstance(t, ast.Attribute) and isinstance(t.value, ast.Name) and t.value.id == "self":
+                            attrs.add(t.attr)
+    return methods, props, attrs
+
+
+def _self_uses(path, class_or_func):
+    """names X of every ``self.X`` read or called inside the given class / function of our own source"""
+    tree = ast.parse(open(path).read())
+    node = next(n for n in ast.walk(tree) if isinstance(n, (ast.ClassDef, ast.FunctionDef)) and n.name == class_or_func)
+    return {n.attr for n in ast.walk(node) if isinstance(n, ast.Attribute) and isinstance(n.value, ast.Name) and n.value.id == "self"}
+
+
+@pytest.fixture(scope="module")
+def reference():
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not present")
+    qmap = _class(os.path.join(REF, "quadrature_map.py"), "QuadratureMap")
+    qexpr = _class(os.path.join(REF, "quadrature_function.py"), "QuadratureExpression")
+    return _surface(qmap), _surface(qexpr)
+
+
+def test_adapter_only_touches_what_the_reference_class_has(reference):
+    (methods, props, attrs), (emethods, _, eattrs) = reference
+    have = set(methods) | props | attrs
+    own = {"_xchg", "_exchange", "_eval_gradients", "last_stats", "close"}  # introduced by the adapter itself
+    used = _self_uses(os.path.join(ROOT, "dolfinx_materials_b200", "quadrature_map.py"), "GPUQuadratureMap") - own
+    missing = used - have
+    assert not missing, f"GPUQuadratureMap uses self.{sorted(missing)} which the reference QuadratureMap does not define"
+    # what it relies on in particular (reference quadrature_map.py:51-130, 220-226, 281-360)
+    for name in ("material", "gradients", "fluxes", "internal_state_variables", "jacobian_flatten", "cells", "_initialized"):
+        assert name in attrs, name
+    assert "quadrature_points" in props
+    for name, params in (("update", ["self"]), ("advance", ["self"]), ("initialize_state", ["self"]),
+                         ("update_external_state_variables", ["self"])):
+        assert methods[name] == params, (name, methods[name])
+    # gradients[name] is a QuadratureExpression: .function and .eval(cells) (quadrature_function.py:24-51)
+    assert "function" in eattrs and emethods["eval"] == ["self", "cells"]
+
+
+def test_stand_in_models_members_the_reference_class_has(reference):
+    (methods, props, attrs), _ = reference
+    have = set(methods) | props | attrs
+    sm, sp, sa = _surface(_class(os.path.join(HERE, "qmap_standin.py"), "StandInQuadratureMap"))
+    private = {n for n in set(sm) | sp | sa if n.startswith("_") and n != "_initialized"} | {"__init__"}
+    extra = (set(sm) | sp | sa) - have - private
+    assert not extra, f"the stand-in models members the reference class does not have: {sorted(extra)}"
+    for name in ("update", "advance", "initialize_state", "update_initial_state", "register_gradient"):
+        if name in sm:
+            assert sm[name][: len(methods[name])] == methods[name] or len(sm[name]) >= 1, name
+    # the three methods the adapter replaces exist in both, with the reference's arity
+    for name in ("update", "advance", "initialize_state"):
+        assert name in sm and sm[name] == methods[name]
