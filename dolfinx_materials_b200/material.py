@@ -158,9 +158,11 @@ class CUDAMaterial:
     """Converts a behaviour descriptor into a dolfinx_materials-compatible material running on a
     B200 (the role ``JAXMaterial(behavior)`` plays in the reference, ``jaxmat.py:141-156``)."""
 
-    def __init__(self, behavior, device=None, warn_on_failure=True):
-        """``device``: CUDA device index; ``None`` = this process's local rank modulo the number of devices (one MPI
-        rank / torchrun worker per GPU), 0 for a single process."""
+    def __init__(self, behavior, jit=True, device=None, warn_on_failure=True):
+        """``jit``: accepted for signature compatibility with ``JAXMaterial(behavior, jit=True)`` (``jaxmat.py:144``) and
+        ignored -- the kernels are compiled ahead of time.  ``device``: CUDA device index; ``None`` = this process's
+        local rank modulo the number of devices (one MPI rank / torchrun worker per GPU), 0 for a single process."""
+        del jit
         self.behavior = behavior
         if device is None:
             from .distributed import default_device
@@ -526,9 +528,9 @@ def material_subclass(base=None):
         class CUDAMaterial(_PLAIN, base):  # noqa: F811 - same public name on purpose
             __doc__ = _PLAIN.__doc__
 
-            def __init__(self, behavior, device=None, warn_on_failure=True):
+            def __init__(self, behavior, jit=True, device=None, warn_on_failure=True):
                 base.__init__(self, **dict(behavior.properties()))
-                _PLAIN.__init__(self, behavior, device=device, warn_on_failure=warn_on_failure)
+                _PLAIN.__init__(self, behavior, jit=jit, device=device, warn_on_failure=warn_on_failure)
 
             def default_properties(self):
                 return {}

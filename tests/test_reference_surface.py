@@ -86,3 +86,34 @@ def test_stand_in_models_members_the_reference_class_has(reference):
     # the three methods the adapter replaces exist in both, with the reference's arity
     for name in ("update", "advance", "initialize_state"):
         assert name in sm and sm[name] == methods[name]
+
+
+def test_cuda_material_covers_the_reference_jax_material():
+    """``CUDAMaterial(behavior)`` replaces ``JAXMaterial(behavior)`` (``dolfinx_materials/jaxmat.py:141-234``): every
+    public method / property of the reference class (and of the ``DataManager`` it pairs with, ``jaxmat.py:30-43``) exists
+    on ours with the same positional parameters -- checked on the reference's source, which needs jax to import."""
+    import inspect
+
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not present")
+    import dolfinx_materials_b200 as jm
+    from dolfinx_materials_b200.material import DeviceDataManager
+
+    methods, props, _ = _surface(_class(os.path.join(REF, "jaxmat.py"), "JAXMaterial"))
+    for name in props:
+        assert isinstance(inspect.getattr_static(jm.CUDAMaterial, name), property), name
+    internal = {"constitutive_update"}  # the per-point jax function behind the batched update: ours is the CUDA kernel
+    for name, params in methods.items():
+        if name.startswith("_") and name != "__init__" or name in internal:
+            continue
+        ours = list(inspect.signature(getattr(jm.CUDAMaterial, name)).parameters)
+        assert ours[: len(params)] == params, (name, ours, params)
+    assert list(inspect.signature(jm.CUDAMaterial.integrate).parameters) == ["self", "gradients", "dt"]
+    dm_methods, _, dm_attrs = _surface(_class(os.path.join(REF, "jaxmat.py"), "DataManager"))
+    for name in dm_methods:
+        if not name.startswith("_"):
+            assert hasattr(DeviceDataManager, name), name  # update / revert
+    for name in ("K", "s0", "s1"):
+        assert name in dm_attrs
+    dm = DeviceDataManager.__init__.__code__.co_names + DeviceDataManager.__init__.__code__.co_varnames
+    assert all(n in dm for n in ("K", "s0", "s1"))
