@@ -187,6 +187,19 @@ class CUDAMaterial:
     def rotation_matrix(self):
         return None
 
+    # The reference rotates gradients into the material frame and fluxes / tangent back out of it only when
+    # ``rotation_matrix`` is not None (``quadrature_map.py:315-330``; MFront orthotropic behaviours, ``mfront.py:336-343``).
+    # Every CUDA behaviour is isotropic -- its response is the same in any frame -- so ``rotation_matrix`` is None, the
+    # callers never reach these, and they are identities kept for the completeness of the protocol.
+    def rotate_gradients(self, gradient_vals, rotation_values):
+        return gradient_vals
+
+    def rotate_fluxes(self, flux_vals, rotation_values):
+        return flux_vals
+
+    def rotate_tangent_operator(self, Ct_vals, rotation_values):
+        return Ct_vals
+
     @property
     def gradients(self):
         return {"F": 9} if self.behavior.finite_strain else {"strain": 6}

@@ -159,3 +159,32 @@ def test_behaviour_descriptors_accept_every_reference_call_site():
     # the behaviours SURVEY 8(a) a9 lists are all met at least once
     for name in ("LinearElasticIsotropic", "VoceHardening", "vonMisesIsotropicHardening", "FeFpJ2Plasticity", "JAXMaterial"):
         assert name in seen, f"no call site of {name} found: {sorted(seen)}"
+
+
+def test_cuda_material_has_every_member_the_reference_callers_touch():
+    """Everything ``QuadratureMap`` and the solvers read or call on their material (``self.material.X`` in the reference's
+    ``quadrature_map.py`` / ``solvers.py``) exists on ``CUDAMaterial`` -- except the two external-state-variable
+    hooks, which the reference only calls for materials that register such variables (``quadrature_map.py:195,225``;
+    the CUDA behaviours have none)."""
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not present")
+    import dolfinx_materials_b200 as jm
+
+    touched = {}
+    for fname in ("quadrature_map.py", "solvers.py"):
+        tree = ast.parse(open(os.path.join(REF, fname)).read())
+        for node in ast.walk(tree):
+            # self.material.X   or   <something>.material.X
+            if isinstance(node, ast.Attribute) and isinstance(node.value, ast.Attribute) and node.value.attr == "material":
+                touched.setdefault(node.attr, f"{fname}:{node.lineno}")
+    assert {"integrate", "set_data_manager", "tangent_blocks", "fluxes", "gradients", "internal_state_variables",
+            "rotation_matrix", "material_properties", "update_material_property", "data_manager",
+            "get_final_state_dict", "set_initial_state_dict"} <= set(touched), sorted(touched)
+    optional = {"initialize_external_state_variable", "update_external_state_variable"}
+    beh = jm.vonMisesIsotropicHardening(elasticity=jm.LinearElasticIsotropic(E=1.0, nu=0.3),
+                                        yield_stress=jm.VoceHardening(sig0=1.0, sigu=2.0, b=1.0))
+    mat = jm.CUDAMaterial(beh, device=0)  # no handle is created before set_data_manager: works without a GPU
+    for name, where in touched.items():
+        if name in optional:
+            continue
+        assert hasattr(mat, name), f"{where}: material.{name} is used by the reference but missing on CUDAMaterial"
