@@ -9,9 +9,11 @@ import pathlib
 
 import os
 
-# DXM_UNFUSED=1: the A/B build with the round-1 (un-fused) arithmetic, see build.py
+# DXM_UNFUSED=1: the A/B build with the round-1 (un-fused) arithmetic; DXM_VARIANT=<name>: an experiment build
+# (lib/libdxm_cuda_<name>.so), see build.py
+_VARIANT = "unfused" if os.environ.get("DXM_UNFUSED", "0") not in ("", "0") else os.environ.get("DXM_VARIANT", "")
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / (
-    "libdxm_cuda_unfused.so" if os.environ.get("DXM_UNFUSED", "0") not in ("", "0") else "libdxm_cuda.so")
+    f"libdxm_cuda_{_VARIANT}.so" if _VARIANT else "libdxm_cuda.so")
 
 MEM_HOST, MEM_DEVICE, MEM_RESIDENT = 0, 1, 2
 

@@ -11,7 +11,11 @@ CSRC = ROOT / "csrc"
 # (-DDXM_UNFUSED, csrc/dxm_canon.cuh): the round-1 arithmetic -- bit-identical to the committed golden histories and to
 # oracle.canon.unfused(), ~40 % more FP64 instructions in the finite-strain update (tests/test_unfused_gpu.py)
 UNFUSED = os.environ.get("DXM_UNFUSED", "0") not in ("", "0")
-LIB = ROOT / "lib" / ("libdxm_cuda_unfused.so" if UNFUSED else "libdxm_cuda.so")
+# DXM_VARIANT=<name> [DXM_VARIANT_DEFS="-DA -DB"]: an experiment build lib/libdxm_cuda_<name>.so beside the product
+# library (kernel A/B runs on one box: the same variable selects it at load time, _lib.py)
+VARIANT = "unfused" if UNFUSED else os.environ.get("DXM_VARIANT", "")
+VARIANT_DEFS = os.environ.get("DXM_VARIANT_DEFS", "").split()
+LIB = ROOT / "lib" / (f"libdxm_cuda_{VARIANT}.so" if VARIANT else "libdxm_cuda.so")
 
 NVCC_FLAGS = [
     "-gencode",
@@ -23,6 +27,7 @@ NVCC_FLAGS = [
     # multiply-add by hand (fma_c / fms_c / fnma_c), which is what makes kernel results bit-comparable with the CPU oracle
     "-fmad=false",
     *(["-DDXM_UNFUSED"] if UNFUSED else []),
+    *VARIANT_DEFS,
     "-Xcompiler",
     "-fPIC",
 ]
@@ -54,7 +59,7 @@ def build_library(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     LIB.parent.mkdir(parents=True, exist_ok=True)
-    objdir = ROOT / "lib" / ("obj_unfused" if UNFUSED else "obj")
+    objdir = ROOT / "lib" / (f"obj_{VARIANT}" if VARIANT else "obj")
     objdir.mkdir(exist_ok=True)
     nvcc = _nvcc()
     procs = []

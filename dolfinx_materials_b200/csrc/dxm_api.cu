@@ -18,7 +18,7 @@ std::atomic<long long> g_launches{0};
 namespace {
 constexpr int64_t kChunk = 1 << 19;  // points per pipeline chunk on the host path
 const char* kPropNames[kNProp] = {"E", "nu", "sig0", "H", "sigu", "b"};
-constexpr double kHosSplitMaxPlastic = 0.30;  // Hosford: fused kernel above this plastic fraction (previous call)
+constexpr double kHosLowPlastic = 0.25;  // Hosford: 168-register build below this plastic fraction (previous call)
 constexpr int64_t kAutoTimingPoints = 1 << 18;  // kernel_ms events by default only where two event records are noise
 constexpr bool kHostMirrorDefault = false;  // A/B on the B200 box: profiles/ (DXM_HOST_MIRROR overrides)
 }  // namespace
@@ -278,20 +278,22 @@ int launch_update(dxm_handle* h, int64_t start, int64_t count, double dt, int fi
   if (h->behaviour == DXM_HOSFORD_LINEAR) {
     a.hos_a = h->hos_a;
     a.hos_bound = hosford_bound(h->hos_a);
-    // Tiled kernel (stream a tile, pack the candidates into full warps) or the fused one.  Tiling wins while a good
-    // part of the batch is elastic (6.6 vs 5.3 G points/s at 3 % plastic); when more points are plastic its extra
-    // pass costs more than the packing gains (4.05 vs 4.25 G at 40 %: crossover near 30 %, profiles/r02l_configs.json), and small
-    // batches are latency-bound either way: auto mode keys on the batch size and on the plastic fraction of the
-    // previous call.  DXM_HOS_SPLIT=0|1 forces fused | tiled.  (A warp-private queue -- every heavy pass a full warp, no
-    // block barrier -- was also measured in round 2: same times as the tiled kernel to 2-5 %; the local solves are bound
-    // by the latency of their dependent FP64 chains, not by idle lanes.  Not kept.)
+    // The fused kernel (every thread runs the whole routine on its own point) is the default at every plastic fraction
+    // since the eigen-decomposition became non-iterative: 6.5-6.9 G points/s at 3 % plastic, 4.9 G at 80 %
+    // (profiles/r02t_hosford_ab.json).  The tiled kernel (stream a tile, pack the candidates into full warps) won below
+    // ~30 % plastic while the local solve cost twice as much; now it only ties at 3 % (6.7 G) and loses 20-30 % above
+    // 10 %, so it stays as an opt-in: DXM_HOS_SPLIT=1 (0 forces fused).  Register target: 3 resident CTAs per SM
+    // (168 registers) while few points are plastic (previous call < 25 %), 4 (128) otherwise -- worth 2-5 % either way.
+    // (A warp-private queue -- every heavy pass a full warp, no block barrier -- was also measured in round 2: same
+    // times as the tiled kernel to 2-5 %.  Not kept.)
     const char* e = std::getenv("DXM_HOS_SPLIT");
-    bool tiled = count >= 32768;
-    if (tiled && h->prev_points > 0) tiled = (double)h->prev_plastic < kHosSplitMaxPlastic * (double)h->prev_points;
-    if (e) tiled = std::atoi(e) != 0;
+    const bool tiled = e ? std::atoi(e) != 0 : false;
     const char* mb = std::getenv("DXM_HOS_MINB");  // A/B knob, read per call like DXM_HOS_SPLIT
+    int minb = mb ? std::atoi(mb) : 0;
+    if (!minb && !tiled && h->prev_points > 0 && (double)h->prev_plastic < kHosLowPlastic * (double)h->prev_points)
+      minb = 3;
     // sigu is only ever set for a hardening law with a saturation term (VoceHardening); otherwise it follows sig0
-    HosLaunch cfg{h->num_sms, h->stream, h->set[4], tiled, kTilesPerCta, mb ? std::atoi(mb) : 0};
+    HosLaunch cfg{h->num_sms, h->stream, h->set[4], tiled, kTilesPerCta, minb};
     int launches = 0;
     const int rc = launch_hosford(a, cfg, &launches);
     g_launches.fetch_add(launches);

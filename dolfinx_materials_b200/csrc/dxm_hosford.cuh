@@ -10,8 +10,9 @@
 //
 // One Gauss point per thread.  Isotropy keeps the principal axes of the trial stress, so per point:
 //   * cheap rejection: sigma_eq <= max|s_i - s_j| <= 2/sqrt(3) seq_Mises  -> clearly elastic points skip the rest;
-//   * cyclic Jacobi eigen-decomposition of the trial deviator in registers (+ - * / sqrt only); the equivalent stress
-//     costs two divisions per evaluation (the a-th root is a division-free Newton on q^(-1/a));
+//   * non-iterative eigen-decomposition of the trial deviator in registers (hos_eig3: isolated root of the
+//     characteristic cubic, cross product, one Jacobi rotation in the normal plane; + - * / sqrt only); the equivalent
+//     stress costs one division per evaluation (the a-th root is a division-free fixed-count iteration on q^(-1/a));
 //   * 4-unknown Newton (3 principal deviatoric stresses + dp) from the radially scaled trial state, with a
 //     simple-decrease backtracking line search (plain Newton overshoots at the rounded corners of the surface);
 //     3x3 solves by the symmetric adjugate;
@@ -22,12 +23,13 @@
 // The point routine is __host__ __device__ so that a CPU test can run the very same code against the oracle
 // (tests/hosford_host_check.cu) -- the product only ever calls it from the kernels below.
 //
-// Launch structure (profiles/r01f_hosford_v1_ncu_*: a warp with ONE candidate lane pays the whole local solve):
-//   dxm_hosford_kernel        fused: every thread runs the full routine on its own point -- small batches and batches
-//                             where most points are plastic;
+// Launch structure:
+//   dxm_hosford_kernel        fused: every thread runs the full routine on its own point -- the default at every plastic
+//                             fraction since the eigen-decomposition became non-iterative (profiles/r02t_hosford_ab.json);
 //   dxm_hosford_tiled_kernel  each CTA streams a 1024-point tile, finishes the clearly elastic points and packs the
-//                             candidates into full warps through a shared-memory queue -- wins below ~55 % plastic.
-// Auto mode by batch size and the previous call's plastic fraction (DXM_HOS_SPLIT=0|1 forces fused | tiled).
+//                             candidates into full warps through a shared-memory queue -- won below ~30 % plastic while
+//                             a warp with ONE candidate lane paid a twice as expensive local solve
+//                             (profiles/r01f_hosford_v1_ncu_*); now an opt-in (DXM_HOS_SPLIT=1).
 #pragma once
 #include "dxm_canon.cuh"
 #include "dxm_small_strain.cuh"
@@ -37,7 +39,6 @@ namespace dxm {
 constexpr double kHosRSqrt2 = 0.7071067811865476;
 constexpr double kHosSqrt2 = 1.4142135623730951;
 constexpr int kHosfordLsMax = 10;
-constexpr int kJacobiSweeps = 8;
 
 // exp_c written for host and device: exp_hd of dxm_canon.cuh
 DXM_HD double hos_exp(double x) { return exp_hd(x); }
@@ -74,17 +75,23 @@ DXM_HD double hos_ipow2(double x, int k) {
 }
 
 // q^(-1/a), q in (0.5, 1], division free: second-order Taylor start in x = 1 - q (relative error <= 5 % for a = 2,
-// 0.8 % for a = 10), then a FIXED number of Newton steps on w^-a = q, w <- w (1 + (1 - q w^a)/a): the error goes
-// e -> (a+1)/2 e^2, i.e. below 1e-18 after four steps for every even a in [2, 64].  (Round 1 started from w = 1 and
-// iterated until rounding stopped the monotone sequence: 5-7 data-dependent trips on the critical path of every
-// evaluation of the criterion; the fixed count halves that chain and removes the divergent loop.)
-constexpr int kHosRootSteps = 4;
+// 0.8 % for a = 10), then a FIXED two steps of the third-order correction: with r = 1 - q w^a the exact root is
+// w (1 - r)^(-1/a) = w (1 + s r (1 + (s+1)/2 r (1 + (s+2)/3 r (...)))), s = 1/a; truncated after r^3 the error goes
+// e -> O(e^4): below 2e-18 after two steps for every even a in [2, 64] (scanned in tests/test_oracle_hosford.py).
+// History: round 1 started from w = 1 and ran plain Newton steps until rounding stopped the monotone sequence (5-7
+// data-dependent trips on the critical path of every evaluation of the criterion); then a fixed four Newton steps
+// (chain depth 3 + 4 x 7); now 3 + 2 x 9.
+constexpr int kHosRootSteps = 2;
 DXM_HD double hos_arootinv(double q, int a, double inv_a) {
   const double x = 1.0 - q;
   const double k2 = 0.5 * (1.0 + inv_a);
+  const double k3 = (2.0 + inv_a) / 3.0;
   double w = fma_c(x * inv_a, fma_c(x, k2, 1.0), 1.0);
 #pragma unroll
-  for (int it = 0; it < kHosRootSteps; ++it) w = w * fma_c(fnma_c(q, hos_ipow2(w, a / 2), 1.0), inv_a, 1.0);
+  for (int it = 0; it < kHosRootSteps; ++it) {
+    const double r = fnma_c(q, hos_ipow2(w, a / 2), 1.0);
+    w = w * fma_c(r * inv_a, fma_c(r * k2, fma_c(r, k3, 1.0), 1.0), 1.0);
+  }
   return w;
 }
 
@@ -99,7 +106,9 @@ DXM_HD void hos_eval(const double (&l)[3], int a, double inv_a, HosEval& e) {
   const double r0 = d0 * im, r1 = d1 * im, r2 = d2 * im;
   const double q = 0.5 * ((hos_ipow2(r0, a / 2) + hos_ipow2(r1, a / 2)) + hos_ipow2(r2, a / 2));
   const double w = hos_arootinv(q, a, inv_a);
-  e.phi = m / w;
+  // phi = m q^(1/a) = m q w^(a-1): a short product chain instead of the division m / w (relative error <= ~a ulp,
+  // three orders of magnitude below the Newton tolerance)
+  e.phi = m * (q * ((a > 2) ? hos_ipow2(w, (a - 2) / 2) * w : w));
   e.iphi = w * im;
   e.u[0] = r0 * w;
   e.u[1] = r1 * w;
@@ -123,48 +132,116 @@ DXM_HD double hos_divdiff(double x, double y, int a) {
   return t;
 }
 
-// Jacobi rotation annihilating a_pq (P < Q compile-time, so the eigenvector matrix stays in registers)
-template <int P, int Q>
-DXM_HD void hos_jrot(double& app, double& aqq, double& apq, double& arp, double& arq, double (&V)[3][3]) {
-  if (apq == 0.0) return;
-  const double g = 100.0 * fabs(apq);
-  if ((fabs(app) + g == fabs(app)) && (fabs(aqq) + g == fabs(aqq))) {
-    apq = 0.0;
-    return;
-  }
-  const double delta = (aqq - app) * 0.5;
-  double t = apq / (fabs(delta) + sqrt(fma_c(delta, delta, apq * apq)));
-  if (delta < 0.0) t = -t;
-  const double c = 1.0 / sqrt(fma_c(t, t, 1.0)), sn = t * c;
-  app = fnma_c(t, apq, app);
-  aqq = fma_c(t, apq, aqq);
-  apq = 0.0;
-  const double xp = arp, xq = arq;
-  arp = fms_c(c, xp, sn * xq);
-  arq = fma_c(sn, xp, c * xq);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const double vp = V[k][P], vq = V[k][Q];
-    V[k][P] = fms_c(c, vp, sn * vq);
-    V[k][Q] = fma_c(sn, vp, c * vq);
-  }
+// ---- symmetric 3x3 eigen-decomposition of a deviator, non-iterative -------------------------------------------------
+// (replaces the cyclic Jacobi sweeps of round 1 / early round 2: 4-5 sweeps x 3 rotations per warp, each rotation two
+// square roots and two divisions -- 19 % of the fused kernel's time at 80 % plastic points, profiles/r02r_*.)  With
+// B = A / p, p = sqrt(tr(A^2) / 6), the eigenvalues of B are 2 cos(theta + 2 pi j / 3), cos(3 theta) = det(B) / 2 =: k.
+// The eigenvalue on the side of the sign of k is ISOLATED (at least 0.866 * 2 from the other two, whatever the spectrum):
+//   1. y = cos(theta) in [sqrt(3)/2, 1] solves 4 y^3 - 3 y = |k|: cubic start polynomial + three division-free Newton
+//      steps (the reciprocal slope R is refined alongside, R <- R (2 - g' R)); beta0 = sgn(k) 2 y;
+//   2. its eigenvector n = the largest of the three cross products of rows of B - beta0 I, normalised (well conditioned
+//      because beta0 is isolated);
+//   3. an orthonormal basis (U, W) of the plane normal to n without a square root (Duff et al., "Building an orthonormal
+//      basis, revisited", JCGT 2017) and ONE exact Jacobi rotation of the 2x2 restriction of B to that plane; repeated or
+//      nearly repeated eigenvalues there are harmless (any rotation of an eigenplane is a valid basis).
+// Eigenvalues are Rayleigh quotients of the computed vectors.  Straight-line code, no data-dependent trip count; residual
+// |A V - V L| / |A| and |V^T V - I| <= ~1.5e-15 over random, axisymmetric, nearly degenerate and pure-shear spectra
+// (tests/test_oracle_hosford.py on the bit-identical C twin).
+constexpr double kEigCY0 = 0.8660615980506479, kEigCY1 = 0.16540585304875938, kEigCY2 = -0.04088323804684024,
+                 kEigCY3 = 0.009444179663245256;
+constexpr double kEigCR0 = 0.1660512323983123, kEigCR1 = -0.08345496691468178, kEigCR2 = 0.028968785247117986;
+constexpr double kEigSixth = 0.16666666666666666;
+
+DXM_HD void hos_cross3(const double (&u)[3], const double (&v)[3], double (&c)[3], double& d) {
+  c[0] = fms_c(u[1], v[2], u[2] * v[1]);
+  c[1] = fms_c(u[2], v[0], u[0] * v[2]);
+  c[2] = fms_c(u[0], v[1], u[1] * v[0]);
+  d = fma_c(c[2], c[2], fma_c(c[1], c[1], c[0] * c[0]));
 }
 
-DXM_HD void hos_jacobi3(const double (&s)[6], double (&l)[3], double (&V)[3][3]) {
-  double a00 = s[0], a11 = s[1], a22 = s[2], a01 = s[3] * kHosRSqrt2, a02 = s[4] * kHosRSqrt2, a12 = s[5] * kHosRSqrt2;
+DXM_HD double hos_dot3(const double (&u)[3], const double (&v)[3]) { return fma_c(u[2], v[2], fma_c(u[1], v[1], u[0] * v[0])); }
+
+// s: Mandel deviator; l: eigenvalues; V: eigenvectors in the columns
+DXM_HD void hos_eig3(const double (&s)[6], double (&l)[3], double (&V)[3][3]) {
+  const double a00 = s[0], a11 = s[1], a22 = s[2], a01 = s[3] * kHosRSqrt2, a02 = s[4] * kHosRSqrt2, a12 = s[5] * kHosRSqrt2;
+  const double dg = fma_c(a22, a22, fma_c(a11, a11, a00 * a00));
+  const double od = fma_c(a12, a12, fma_c(a02, a02, a01 * a01));
+  const double p2 = fma_c(2.0, od, dg) * kEigSixth;
+  if (p2 == 0.0) {  // zero deviator (never a candidate point)
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 3; ++i) {
+      l[i] = 0.0;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < kJacobiSweeps; ++sweep) {
-    if ((fabs(a01) + fabs(a02)) + fabs(a12) == 0.0) break;
-    hos_jrot<0, 1>(a00, a11, a01, a02, a12, V);
-    hos_jrot<0, 2>(a00, a22, a02, a01, a12, V);
-    hos_jrot<1, 2>(a11, a22, a12, a01, a02, V);
+      for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+    return;
   }
-  l[0] = a00;
-  l[1] = a11;
-  l[2] = a22;
+  const double p = sqrt(p2), ip = 1.0 / p;
+  const double b00 = a00 * ip, b11 = a11 * ip, b22 = a22 * ip, b01 = a01 * ip, b02 = a02 * ip, b12 = a12 * ip;
+  const double m0 = fms_c(b11, b22, b12 * b12), m1 = fms_c(b01, b22, b12 * b02), m2 = fms_c(b01, b12, b11 * b02);
+  const double hdet = 0.5 * fma_c(b02, m2, fms_c(b00, m0, b01 * m1));
+  const double sgn = (hdet >= 0.0) ? 1.0 : -1.0;
+  const double k = fmin(fabs(hdet), 1.0);
+  double y = fma_c(fma_c(fma_c(kEigCY3, k, kEigCY2), k, kEigCY1), k, kEigCY0);
+  double R = fma_c(fma_c(kEigCR2, k, kEigCR1), k, kEigCR0);
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const double y2 = y * y;
+    const double g = fms_c(fms_c(4.0, y2, 3.0), y, k);
+    const double gp = fms_c(12.0, y2, 3.0);
+    R = R * fnma_c(gp, R, 2.0);
+    y = fnma_c(g, R, y);
+  }
+  const double beta = sgn * (2.0 * y);
+  const double r0[3] = {b00 - beta, b01, b02}, r1[3] = {b01, b11 - beta, b12}, r2[3] = {b02, b12, b22 - beta};
+  double c[3], d, c2[3], d2;
+  hos_cross3(r0, r1, c, d);
+  hos_cross3(r0, r2, c2, d2);
+  if (d2 > d) {
+    c[0] = c2[0];
+    c[1] = c2[1];
+    c[2] = c2[2];
+    d = d2;
+  }
+  hos_cross3(r1, r2, c2, d2);
+  if (d2 > d) {
+    c[0] = c2[0];
+    c[1] = c2[1];
+    c[2] = c2[2];
+    d = d2;
+  }
+  const double inv = 1.0 / sqrt(d);
+  const double n[3] = {c[0] * inv, c[1] * inv, c[2] * inv};
+  const double sg = (n[2] >= 0.0) ? 1.0 : -1.0;
+  const double a = -1.0 / (sg + n[2]);
+  const double bq = (n[0] * n[1]) * a;
+  const double U[3] = {fma_c(sg * (n[0] * n[0]), a, 1.0), sg * bq, -(sg * n[0])};
+  const double W[3] = {bq, fma_c(n[1] * n[1], a, sg), -n[1]};
+  double Bn[3], BU[3], BW[3];
+#define DXM_EIG_MV(v, o)                                        \
+  o[0] = fma_c(b02, v[2], fma_c(b01, v[1], b00 * v[0]));        \
+  o[1] = fma_c(b12, v[2], fma_c(b11, v[1], b01 * v[0]));        \
+  o[2] = fma_c(b22, v[2], fma_c(b12, v[1], b02 * v[0]));
+  DXM_EIG_MV(n, Bn)
+  DXM_EIG_MV(U, BU)
+  DXM_EIG_MV(W, BW)
+#undef DXM_EIG_MV
+  const double l0 = hos_dot3(n, Bn), m00 = hos_dot3(U, BU), m01 = hos_dot3(U, BW), m11 = hos_dot3(W, BW);
+  // the Jacobi rotation of [[m00, m01], [m01, m11]]: t = tangent of the smaller angle, one division
+  const double delta = (m11 - m00) * 0.5;
+  const double den = fabs(delta) + sqrt(fma_c(delta, delta, m01 * m01));
+  double t = (den > 0.0) ? m01 / den : 0.0;
+  if (delta < 0.0) t = -t;
+  const double cs = 1.0 / sqrt(fma_c(t, t, 1.0)), sn = t * cs;
+  l[0] = l0 * p;
+  l[1] = fnma_c(t, m01, m00) * p;
+  l[2] = fma_c(t, m01, m11) * p;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    V[i][0] = n[i];
+    V[i][1] = fms_c(cs, U[i], sn * W[i]);
+    V[i][2] = fma_c(sn, U[i], cs * W[i]);
+  }
 }
 
 struct HosRes {
@@ -185,7 +262,7 @@ DXM_HD void hos_residual_finish(const double (&x)[3], double dp, const double (&
 }
 
 // A = I + c k1 (M/2 - n n^T): adjugate (6 unique cofactors) and 1/det
-DXM_HD void hos_system(const HosEval& r, double c, double k1, double (&Cf)[6], double& idet) {
+DXM_HD void hos_system(const HosEval& r, double c, double k1, double (&Cf)[6], double& det) {
   const double ck = c * k1;
   const double A00 = fma_c(ck, fnma_c(r.n[0], r.n[0], 0.5 * (r.h[0] + r.h[2])), 1.0);
   const double A11 = fma_c(ck, fnma_c(r.n[1], r.n[1], 0.5 * (r.h[0] + r.h[1])), 1.0);
@@ -199,14 +276,14 @@ DXM_HD void hos_system(const HosEval& r, double c, double k1, double (&Cf)[6], d
   Cf[3] = fms_c(A00, A22, A02 * A02);
   Cf[4] = fms_c(A01, A02, A00 * A12);
   Cf[5] = fms_c(A00, A11, A01 * A01);
-  const double det = fma_c(A02, Cf[2], fma_c(A01, Cf[1], A00 * Cf[0]));
-  idet = 1.0 / det;
+  det = fma_c(A02, Cf[2], fma_c(A01, Cf[1], A00 * Cf[0]));
 }
 
-DXM_HD void hos_apply(const double (&Cf)[6], double idet, const double (&v)[3], double (&o)[3]) {
-  o[0] = fma_c(Cf[2], v[2], fma_c(Cf[1], v[1], Cf[0] * v[0])) * idet;
-  o[1] = fma_c(Cf[4], v[2], fma_c(Cf[3], v[1], Cf[1] * v[0])) * idet;
-  o[2] = fma_c(Cf[5], v[2], fma_c(Cf[4], v[1], Cf[2] * v[0])) * idet;
+// adj(A) v (the caller scales by 1/det where it needs A^-1 v)
+DXM_HD void hos_apply(const double (&Cf)[6], const double (&v)[3], double (&o)[3]) {
+  o[0] = fma_c(Cf[2], v[2], fma_c(Cf[1], v[1], Cf[0] * v[0]));
+  o[1] = fma_c(Cf[4], v[2], fma_c(Cf[3], v[1], Cf[1] * v[0]));
+  o[2] = fma_c(Cf[5], v[2], fma_c(Cf[4], v[1], Cf[2] * v[0]));
 }
 
 // unit Mandel vector of sym(e_I e_J) (I != J) or of e_I e_I, from the eigenvector matrix
@@ -230,7 +307,7 @@ DXM_HD void hos_mandel_pair(const double (&V)[3][3], double (&m)[6]) {
 }
 
 // ---- one Gauss point, in four stages ---------------------------------------------------------------------------------
-// hos_trial -> hos_jacobi3 -> hos_newton -> hos_finish.  hosford_point() below runs them back to back (CPU harness,
+// hos_trial -> hos_eig3 -> hos_newton -> hos_finish.  hosford_point() below runs them back to back (CPU harness,
 // phase A of the tiled kernel); the local-solve kernels run the same stages but keep only what the Newton loop needs in
 // registers across it: the eigenvectors wait in shared memory and the trial stress / old plastic strain are re-formed
 // from the (L2-resident) inputs afterwards -- same operations on the same values, hence the same bits, with 128 instead
@@ -345,16 +422,19 @@ DXM_HD void hos_newton(const double (&l)[3], const double mu, const HosHard& hd,
       o.fail = true;
       break;
     }
-    double Cf[6], idet, y[3], z[3];
-    hos_system(o.cur.e, twomu * dp, am1 * o.cur.e.iphi, Cf, idet);
-    hos_apply(Cf, idet, o.cur.rs, y);
-    hos_apply(Cf, idet, o.cur.e.n, z);
+    // Schur complement on the adjugate: with y = adj(A) rs, z = adj(A) n (NOT divided by det A) the step in dp is
+    // (r4 det - n.y) / (2 mu n.z + dsy det) -- one division on the critical path, 1/det runs beside it
+    double Cf[6], det, y[3], z[3];
+    hos_system(o.cur.e, twomu * dp, am1 * o.cur.e.iphi, Cf, det);
+    hos_apply(Cf, o.cur.rs, y);
+    hos_apply(Cf, o.cur.e.n, z);
+    const double idet = 1.0 / det;
     const double ny = fma_c(o.cur.e.n[2], y[2], fma_c(o.cur.e.n[1], y[1], o.cur.e.n[0] * y[0]));
     const double nz = fma_c(o.cur.e.n[2], z[2], fma_c(o.cur.e.n[1], z[1], o.cur.e.n[0] * z[0]));
-    ddp = (o.cur.r4 - ny) / fma_c(twomu, nz, o.cur.dsy);
+    ddp = fms_c(o.cur.r4, det, ny) / fma_c(twomu, nz, o.cur.dsy * det);
     const double tz = twomu * ddp;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) dx[k] = -fma_c(tz, z[k], y[k]);
+    for (int k = 0; k < 3; ++k) dx[k] = -(fma_c(tz, z[k], y[k]) * idet);
     t = 1.0;
     ls = 0;
 #pragma unroll
@@ -403,10 +483,13 @@ DXM_HD void hos_finish(const double lam, const double mu, const HosTrial& tr, co
       for (int i = j; i < 6; ++i)
         ct21[sym6_packed(j * 6 + i)] = (i == j) ? ((i < 3) ? AB : twomu) : ((i < 3 && j < 3) ? lam : 0.0);
   } else {
-    double Cf[6], idet, z[3];
+    double Cf[6], det, z[3];
     const double c = twomu * dp, iphi = cur.e.iphi;
-    hos_system(cur.e, c, ((double)a - 1.0) * cur.e.iphi, Cf, idet);
-    hos_apply(Cf, idet, cur.e.n, z);
+    hos_system(cur.e, c, ((double)a - 1.0) * cur.e.iphi, Cf, det);
+    hos_apply(Cf, cur.e.n, z);
+    const double idet = 1.0 / det;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) z[k] = z[k] * idet;
     const double nz = fma_c(cur.e.n[2], z[2], fma_c(cur.e.n[1], z[1], cur.e.n[0] * z[0]));
     const double w = (twomu * twomu) / fma_c(twomu, nz, cur.dsy);
     const double ti = twomu * idet;
@@ -478,7 +561,7 @@ DXM_HD bool hosford_point(const double lam, const double mu, const double sig0, 
   double V[3][3];
   if (!LIGHT && candidate) {
     double l[3];
-    hos_jacobi3(tr.s, l, V);
+    hos_eig3(tr.s, l, V);
     hos_newton<AT>(l, mu, hd, sy0, dsy0, tr.seq, a_rt, so);
   }
   flag = so.flag;
@@ -597,7 +680,7 @@ __device__ __forceinline__ void hos_solve_point(const SmallStrainArgs& a, const 
     hos_trial(io.lam, io.mu, io.eps, io.e_old, io.s_old, tr);
     if (a.hos_bound * tr.seq > sy0) {
       double l[3], V[3][3];
-      hos_jacobi3(tr.s, l, V);
+      hos_eig3(tr.s, l, V);
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll

@@ -20,8 +20,8 @@
  *
  * Algorithm (operation order == csrc/dxm_hosford.cuh, compiled with -ffp-contract=off / -fmad=false):
  *   trial stress as in the J2 update; cheap rejection sigma_eq <= (2^(a-1)+1)^(1/a)/sqrt(3) seq_Mises (pure shear);
- *   cyclic Jacobi eigen-decomposition of the trial deviator (+, -, *, /, sqrt only; the equivalent stress costs two
- *   divisions per evaluation: the a-th root is a division-free Newton on q^(-1/a)); isotropy keeps the principal
+ *   non-iterative eigen-decomposition of the trial deviator (eig3 below; +, -, *, /, sqrt only; the equivalent stress
+ *   costs one division per evaluation: the a-th root is a division-free fixed-count iteration on q^(-1/a)); isotropy keeps the principal
  *   axes, so the return map is a 4-unknown Newton (3 principal deviatoric stresses + dp) started from the radially
  *   scaled trial state with a simple-decrease backtracking line search; the consistent tangent
  *   Xi - (Xi n)(Xi n)^T / (n Xi n + H), Xi = (C^-1 + dp dn/dsigma)^-1, is assembled from its spectral form: a 3x3
@@ -33,7 +33,6 @@
 #define RSQRT2 0.7071067811865476
 #define SQRT2 1.4142135623730951
 #define LS_MAX 10
-#define JACOBI_SWEEPS 8
 
 /* isotropic hardening sigma_Y(p) = sig0 + H p + dsu (1 - exp(-b p)) (the law of the J2 behaviours: linear for
  * dsu = 0, Voce for H = 0) and its slope, at p = p_old + dp */
@@ -64,19 +63,29 @@ static double ipow2(double x, int k) {
   return y;
 }
 
-/* q^(-1/a), q in (0.5, 1], division free: second-order Taylor start in x = 1 - q, then a fixed number of Newton steps on
- * w^-a = q, w <- w (1 + (1 - q w^a)/a) (error e -> (a+1)/2 e^2: below 1e-18 after four steps for every even a in [2, 64]) */
-#define ROOT_STEPS 4
+/* q^(-1/a), q in (0.5, 1], division free: second-order Taylor start in x = 1 - q, then a fixed two steps of the
+ * third-order correction: r = 1 - q w^a, exact root = w (1 - r)^(-1/a) = w (1 + s r (1 + (s+1)/2 r (1 + (s+2)/3 r ...))),
+ * s = 1/a, truncated after r^3 (error e -> O(e^4): below 2e-18 after two steps for every even a in [2, 64]) */
+#define ROOT_STEPS 2
 static double arootinv(double q, int a, double inv_a) {
   const double x = 1.0 - q;
   const double k2 = 0.5 * (1.0 + inv_a);
+  const double k3 = (2.0 + inv_a) / 3.0;
   double w = FMA(x * inv_a, FMA(x, k2, 1.0), 1.0);
-  for (int it = 0; it < ROOT_STEPS; ++it) w = w * FMA(FNMA(q, ipow2(w, a / 2), 1.0), inv_a, 1.0);
+  for (int it = 0; it < ROOT_STEPS; ++it) {
+    const double r = FNMA(q, ipow2(w, a / 2), 1.0);
+    w = w * FMA(r * inv_a, FMA(r * k2, FMA(r, k3, 1.0), 1.0), 1.0);
+  }
   return w;
 }
 
+/* the root alone, for the accuracy scan of tests/test_oracle_hosford.py */
+void dxo_hosford_root(int64_t n, const double* q, int a, double* w) {
+  for (int64_t i = 0; i < n; ++i) w[i] = arootinv(q[i], a, 1.0 / (double)a);
+}
+
 /* Hosford equivalent stress of principal values l, 1/phi, its gradient n, h_k = (d_k/phi)^(a-2), u_k = d_k/phi.
- * Two divisions: 1/max|d| and phi = max|d| / w. */
+ * One division: 1/max|d|. */
 static void hosford_eval(const double l[3], int a, double inv_a, double* phi, double* iphi, double n[3], double h[3],
                          double u[3]) {
   const double d0 = l[0] - l[1], d1 = l[1] - l[2], d2 = l[2] - l[0];
@@ -85,7 +94,7 @@ static void hosford_eval(const double l[3], int a, double inv_a, double* phi, do
   const double r0 = d0 * im, r1 = d1 * im, r2 = d2 * im;
   const double q = 0.5 * ((ipow2(r0, a / 2) + ipow2(r1, a / 2)) + ipow2(r2, a / 2));
   const double w = arootinv(q, a, inv_a);
-  *phi = m / w;
+  *phi = m * (q * ((a > 2) ? ipow2(w, (a - 2) / 2) * w : w)); /* m q^(1/a) = m q w^(a-1): no division */
   *iphi = w * im;
   u[0] = r0 * w;
   u[1] = r1 * w;
@@ -107,46 +116,117 @@ static double divdiff(double x, double y, int a) {
   return t;
 }
 
-/* one Jacobi rotation annihilating a_pq; r is the third index: arp = a_rp, arq = a_rq; Q columns p, q */
-static void jrot(double* app, double* aqq, double* apq, double* arp, double* arq, double Q[3][3], int p, int q) {
-  if (*apq == 0.0) return;
-  const double g = 100.0 * fabs(*apq);
-  if ((fabs(*app) + g == fabs(*app)) && (fabs(*aqq) + g == fabs(*aqq))) {
-    *apq = 0.0;
-    return;
-  }
-  /* t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = delta / a_pq, written with one division */
-  const double delta = (*aqq - *app) * 0.5;
-  double t = *apq / (fabs(delta) + sqrt(FMA(delta, delta, *apq * *apq)));
-  if (delta < 0.0) t = -t;
-  const double c = 1.0 / sqrt(FMA(t, t, 1.0)), sn = t * c;
-  *app = FNMA(t, *apq, *app);
-  *aqq = FMA(t, *apq, *aqq);
-  *apq = 0.0;
-  const double xp = *arp, xq = *arq;
-  *arp = FMS(c, xp, sn * xq);
-  *arq = FMA(sn, xp, c * xq);
-  for (int k = 0; k < 3; ++k) {
-    const double vp = Q[k][p], vq = Q[k][q];
-    Q[k][p] = FMS(c, vp, sn * vq);
-    Q[k][q] = FMA(sn, vp, c * vq);
-  }
+/* ---- symmetric 3x3 eigen-decomposition of a deviator, non-iterative ----------------------------------------------
+ * (replaces the cyclic Jacobi sweeps of round 1 / early round 2: 4-5 sweeps x 3 rotations, each with two square roots and
+ * two divisions -- a fifth of the update's time on the GPU.)  With B = A / p, p = sqrt(tr(A^2) / 6), the eigenvalues of B
+ * are 2 cos(theta + 2 pi j / 3), cos(3 theta) = det(B) / 2 =: k.  The eigenvalue on the side of the sign of k is ISOLATED
+ * (at least 0.866 * 2 away from the other two whatever the spectrum), so
+ *   1. y = cos(theta) in [sqrt(3)/2, 1] solves 4 y^3 - 3 y = |k|: cubic start polynomial + three division-free Newton
+ *      steps (the reciprocal slope R is refined alongside: R <- R (2 - g' R)); beta0 = sgn(k) 2 y;
+ *   2. its eigenvector n = the largest of the three cross products of rows of B - beta0 I, normalised (well conditioned
+ *      because beta0 is isolated);
+ *   3. an orthonormal basis (U, W) of the plane normal to n without a square root (Duff et al., "Building an orthonormal
+ *      basis, revisited", JCGT 2017), and ONE exact Jacobi rotation of the 2x2 restriction of B to that plane -- repeated
+ *      or nearly repeated eigenvalues there are harmless (any rotation of an eigenplane is a valid basis).
+ * Eigenvalues are Rayleigh quotients of the computed vectors.  Residual |A V - V L| / |A| and |V^T V - I| <= ~1e-15 over
+ * random, axisymmetric, nearly degenerate and pure-shear spectra (tests/test_oracle_hosford.py). */
+#define EIG_CY0 0.8660615980506479
+#define EIG_CY1 0.16540585304875938
+#define EIG_CY2 -0.04088323804684024
+#define EIG_CY3 0.009444179663245256
+#define EIG_CR0 0.1660512323983123
+#define EIG_CR1 -0.08345496691468178
+#define EIG_CR2 0.028968785247117986
+#define EIG_SIXTH 0.16666666666666666
+
+static void cross3(const double u[3], const double v[3], double c[3], double* d) {
+  c[0] = FMS(u[1], v[2], u[2] * v[1]);
+  c[1] = FMS(u[2], v[0], u[0] * v[2]);
+  c[2] = FMS(u[0], v[1], u[1] * v[0]);
+  *d = FMA(c[2], c[2], FMA(c[1], c[1], c[0] * c[0]));
 }
 
 /* symmetric 3x3 from a Mandel deviator: eigenvalues l, eigenvectors in the columns of Q */
-static void jacobi3(const double s[6], double l[3], double Q[3][3]) {
-  double a00 = s[0], a11 = s[1], a22 = s[2], a01 = s[3] * RSQRT2, a02 = s[4] * RSQRT2, a12 = s[5] * RSQRT2;
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) Q[i][j] = (i == j) ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < JACOBI_SWEEPS; ++sweep) {
-    if ((fabs(a01) + fabs(a02)) + fabs(a12) == 0.0) break;
-    jrot(&a00, &a11, &a01, &a02, &a12, Q, 0, 1);
-    jrot(&a00, &a22, &a02, &a01, &a12, Q, 0, 2);
-    jrot(&a11, &a22, &a12, &a01, &a02, Q, 1, 2);
+static void eig3(const double s[6], double l[3], double Q[3][3]) {
+  const double a00 = s[0], a11 = s[1], a22 = s[2], a01 = s[3] * RSQRT2, a02 = s[4] * RSQRT2, a12 = s[5] * RSQRT2;
+  const double dg = FMA(a22, a22, FMA(a11, a11, a00 * a00));
+  const double od = FMA(a12, a12, FMA(a02, a02, a01 * a01));
+  const double p2 = FMA(2.0, od, dg) * EIG_SIXTH;
+  if (p2 == 0.0) { /* zero deviator (never a candidate point) */
+    for (int i = 0; i < 3; ++i) {
+      l[i] = 0.0;
+      for (int j = 0; j < 3; ++j) Q[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+    return;
   }
-  l[0] = a00;
-  l[1] = a11;
-  l[2] = a22;
+  const double p = sqrt(p2), ip = 1.0 / p;
+  const double b00 = a00 * ip, b11 = a11 * ip, b22 = a22 * ip, b01 = a01 * ip, b02 = a02 * ip, b12 = a12 * ip;
+  const double m0 = FMS(b11, b22, b12 * b12), m1 = FMS(b01, b22, b12 * b02), m2 = FMS(b01, b12, b11 * b02);
+  const double hdet = 0.5 * FMA(b02, m2, FMS(b00, m0, b01 * m1));
+  const double sgn = (hdet >= 0.0) ? 1.0 : -1.0;
+  const double k = fmin(fabs(hdet), 1.0);
+  double y = FMA(FMA(FMA(EIG_CY3, k, EIG_CY2), k, EIG_CY1), k, EIG_CY0);
+  double R = FMA(FMA(EIG_CR2, k, EIG_CR1), k, EIG_CR0);
+  for (int it = 0; it < 3; ++it) {
+    const double y2 = y * y;
+    const double g = FMS(FMS(4.0, y2, 3.0), y, k);
+    const double gp = FMS(12.0, y2, 3.0);
+    R = R * FNMA(gp, R, 2.0);
+    y = FNMA(g, R, y);
+  }
+  const double beta = sgn * (2.0 * y);
+  const double r0[3] = {b00 - beta, b01, b02}, r1[3] = {b01, b11 - beta, b12}, r2[3] = {b02, b12, b22 - beta};
+  double c[3], d, c2[3], d2;
+  cross3(r0, r1, c, &d);
+  cross3(r0, r2, c2, &d2);
+  if (d2 > d) { c[0] = c2[0]; c[1] = c2[1]; c[2] = c2[2]; d = d2; }
+  cross3(r1, r2, c2, &d2);
+  if (d2 > d) { c[0] = c2[0]; c[1] = c2[1]; c[2] = c2[2]; d = d2; }
+  const double inv = 1.0 / sqrt(d);
+  const double n[3] = {c[0] * inv, c[1] * inv, c[2] * inv};
+  const double sg = (n[2] >= 0.0) ? 1.0 : -1.0;
+  const double a = -1.0 / (sg + n[2]);
+  const double bq = (n[0] * n[1]) * a;
+  const double U[3] = {FMA(sg * (n[0] * n[0]), a, 1.0), sg * bq, -(sg * n[0])};
+  const double W[3] = {bq, FMA(n[1] * n[1], a, sg), -n[1]};
+#define EIG_MV(v, o)                                        \
+  o[0] = FMA(b02, v[2], FMA(b01, v[1], b00 * v[0]));        \
+  o[1] = FMA(b12, v[2], FMA(b11, v[1], b01 * v[0]));        \
+  o[2] = FMA(b22, v[2], FMA(b12, v[1], b02 * v[0]));
+  double Bn[3], BU[3], BW[3];
+  EIG_MV(n, Bn)
+  EIG_MV(U, BU)
+  EIG_MV(W, BW)
+#undef EIG_MV
+  const double l0 = dot3(n[0], Bn[0], n[1], Bn[1], n[2], Bn[2]);
+  const double m00 = dot3(U[0], BU[0], U[1], BU[1], U[2], BU[2]);
+  const double m01 = dot3(U[0], BW[0], U[1], BW[1], U[2], BW[2]);
+  const double m11 = dot3(W[0], BW[0], W[1], BW[1], W[2], BW[2]);
+  /* the Jacobi rotation of [[m00, m01], [m01, m11]]: t = tan of the smaller angle, one division */
+  const double delta = (m11 - m00) * 0.5;
+  const double den = fabs(delta) + sqrt(FMA(delta, delta, m01 * m01));
+  double t = (den > 0.0) ? m01 / den : 0.0;
+  if (delta < 0.0) t = -t;
+  const double cs = 1.0 / sqrt(FMA(t, t, 1.0)), sn = t * cs;
+  l[0] = l0 * p;
+  l[1] = FNMA(t, m01, m00) * p;
+  l[2] = FMA(t, m01, m11) * p;
+  for (int i = 0; i < 3; ++i) {
+    Q[i][0] = n[i];
+    Q[i][1] = FMS(cs, U[i], sn * W[i]);
+    Q[i][2] = FMA(sn, U[i], cs * W[i]);
+  }
+}
+
+/* the eigen-decomposition alone, for the accuracy scan of tests/test_oracle_hosford.py: s (n, 6) Mandel deviators ->
+ * l (n, 3), Q (n, 3, 3) */
+void dxo_hosford_eig(int64_t n, const double* s, double* l, double* Q) {
+  for (int64_t i = 0; i < n; ++i) {
+    double Qi[3][3];
+    eig3(s + 6 * i, l + 3 * i, Qi);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) Q[9 * i + 3 * r + c] = Qi[r][c];
+  }
 }
 
 typedef struct {
@@ -169,8 +249,8 @@ static void hosford_residual(const double x[3], double dp, const double l[3], do
   residual_finish(x, dp, l, twomu, hd, o);
 }
 
-/* A = I + c k1 (M/2 - n n^T) (symmetric), its adjugate C and 1/det */
-static void hosford_system(const hres_t* r, double c, double k1, double Cf[6], double* idet) {
+/* A = I + c k1 (M/2 - n n^T) (symmetric), its adjugate C and det */
+static void hosford_system(const hres_t* r, double c, double k1, double Cf[6], double* det) {
   const double ck = c * k1;
   const double A00 = FMA(ck, FNMA(r->n[0], r->n[0], 0.5 * (r->h[0] + r->h[2])), 1.0);
   const double A11 = FMA(ck, FNMA(r->n[1], r->n[1], 0.5 * (r->h[0] + r->h[1])), 1.0);
@@ -184,14 +264,14 @@ static void hosford_system(const hres_t* r, double c, double k1, double Cf[6], d
   Cf[3] = FMS(A00, A22, A02 * A02); /* C11 */
   Cf[4] = FMS(A01, A02, A00 * A12); /* C12 */
   Cf[5] = FMS(A00, A11, A01 * A01); /* C22 */
-  const double det = FMA(A02, Cf[2], FMA(A01, Cf[1], A00 * Cf[0]));
-  *idet = 1.0 / det;
+  *det = FMA(A02, Cf[2], FMA(A01, Cf[1], A00 * Cf[0]));
 }
 
-static void sym3_apply(const double Cf[6], double idet, const double v[3], double o[3]) {
-  o[0] = FMA(Cf[2], v[2], FMA(Cf[1], v[1], Cf[0] * v[0])) * idet;
-  o[1] = FMA(Cf[4], v[2], FMA(Cf[3], v[1], Cf[1] * v[0])) * idet;
-  o[2] = FMA(Cf[5], v[2], FMA(Cf[4], v[1], Cf[2] * v[0])) * idet;
+/* adj(A) v: the caller scales by 1/det where it needs A^-1 v */
+static void sym3_apply(const double Cf[6], const double v[3], double o[3]) {
+  o[0] = FMA(Cf[2], v[2], FMA(Cf[1], v[1], Cf[0] * v[0]));
+  o[1] = FMA(Cf[4], v[2], FMA(Cf[3], v[1], Cf[1] * v[0]));
+  o[2] = FMA(Cf[5], v[2], FMA(Cf[4], v[1], Cf[2] * v[0]));
 }
 
 /* props: E, nu, sig0 (R0), H, sigu, b scalars or per point (pp/per as in dxm_oracle.c); a even integer >= 2 */
@@ -232,7 +312,7 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
     double l[3], Q[3][3];
     hres_t cur;
     if (bound * seq > sy0) { /* sigma_eq <= bound * seq (bound >= (2^(a-1)+1)^(1/a)/sqrt(3)): otherwise surely elastic */
-      jacobi3(s, l, Q);
+      eig3(s, l, Q);
       hosford_eval(l, a, inv_a, &cur.phi, &cur.iphi, cur.n, cur.h, cur.u);
       const double f = cur.phi - sy0;
       flag = f > 0.0;
@@ -253,15 +333,18 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
           const double res = fmax(fmax(fabs(cur.rs[0]), fabs(cur.rs[1])), fmax(fabs(cur.rs[2]), fabs(cur.r4)));
           if (res <= tol) { resid = res; break; }
           if (it == newton_cap || !(res == res)) { resid = res; fail = 1; break; }
-          double Cf[6], idet, y[3], z[3];
-          hosford_system(&cur, twomu * dp, am1 * cur.iphi, Cf, &idet);
-          sym3_apply(Cf, idet, cur.rs, y);
-          sym3_apply(Cf, idet, cur.n, z);
+          /* Schur complement on the adjugate (y, z not divided by det A): one division on the dependent chain */
+          double Cf[6], det, y[3], z[3];
+          hosford_system(&cur, twomu * dp, am1 * cur.iphi, Cf, &det);
+          sym3_apply(Cf, cur.rs, y);
+          sym3_apply(Cf, cur.n, z);
+          const double idet = 1.0 / det;
           const double ny = dot3(cur.n[0], y[0], cur.n[1], y[1], cur.n[2], y[2]);
           const double nz = dot3(cur.n[0], z[0], cur.n[1], z[1], cur.n[2], z[2]);
-          const double ddp = (cur.r4 - ny) / FMA(twomu, nz, cur.dsy);
+          const double ddp = FMS(cur.r4, det, ny) / FMA(twomu, nz, cur.dsy * det);
           const double tz = twomu * ddp;
-          const double dx[3] = {-FMA(tz, z[0], y[0]), -FMA(tz, z[1], y[1]), -FMA(tz, z[2], y[2])};
+          const double dx[3] = {-(FMA(tz, z[0], y[0]) * idet), -(FMA(tz, z[1], y[1]) * idet),
+                                -(FMA(tz, z[2], y[2]) * idet)};
           double t = 1.0;
           hres_t nxt;
           double xn[3], dpn;
@@ -313,10 +396,12 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
       for (int j = 0; j < 6; ++j)
         for (int i = 0; i < 6; ++i) ct[j * 6 + i] = (i == j) ? ((i < 3) ? AB : twomu) : ((i < 3 && j < 3) ? lam : 0.0);
     } else {
-      double Cf[6], idet, z[3];
+      double Cf[6], det, z[3];
       const double c = twomu * dp, iphi = cur.iphi;
-      hosford_system(&cur, c, am1 * cur.iphi, Cf, &idet);
-      sym3_apply(Cf, idet, cur.n, z);
+      hosford_system(&cur, c, am1 * cur.iphi, Cf, &det);
+      sym3_apply(Cf, cur.n, z);
+      const double idet = 1.0 / det;
+      for (int k = 0; k < 3; ++k) z[k] = z[k] * idet;
       const double nz = dot3(cur.n[0], z[0], cur.n[1], z[1], cur.n[2], z[2]);
       const double w = (twomu * twomu) / FMA(twomu, nz, cur.dsy); /* (2 mu z)(2 mu z)^T / (2 mu n.z + sigma_Y'(p)) */
       const double ti = twomu * idet;

@@ -133,6 +133,26 @@ def fefp(F, state, props, newton_cap=25, rtol=1e-12):
             "fail": fail}
 
 
+def hosford_root(q, a):
+    """``q**(-1/a)`` as the Hosford criterion computes it (division-free fixed-count iteration, q in (0.5, 1])."""
+    lib = load()
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    w = np.empty_like(q)
+    lib.dxo_hosford_root(ctypes.c_int64(q.size), _c(q, 0), ctypes.c_int(int(a)), _c(w, 0))
+    return w
+
+
+def hosford_eig(s):
+    """Eigenvalues ``(n, 3)`` and eigenvectors (columns of ``(n, 3, 3)``) of Mandel deviators ``s (n, 6)`` as the
+    Hosford update computes them (non-iterative: isolated root of the characteristic cubic, cross product, one Jacobi
+    rotation in the normal plane)."""
+    lib = load()
+    s = np.ascontiguousarray(s, dtype=np.float64).reshape(-1, 6)
+    l, Q = np.empty((s.shape[0], 3)), np.empty((s.shape[0], 3, 3))
+    lib.dxo_hosford_eig(ctypes.c_int64(s.shape[0]), _c(s, 0), _c(l, 0), _c(Q, 0))
+    return l, Q
+
+
 def hosford(eps, state, props, newton_cap=25, rtol=1e-12):
     """Small-strain Hosford plasticity (``oracle/c/dxm_oracle_hosford.c``); props: E, nu, sig0, H (scalars or per
     point) and the even integer exponent ``a``."""

@@ -12,7 +12,7 @@ out = []
 for minb in ("3", "4"):
     for split in ("0", "1"):
         os.environ["DXM_HOS_MINB"], os.environ["DXM_HOS_SPLIT"] = minb, split
-        for amp in (2e-3, 4e-3, 8e-3, 1.25e-2, 5e-2):
+        for amp in (2e-3, 2.5e-3, 3e-3, 4e-3, 8e-3, 1.25e-2, 5e-2):
             mh.data_manager.revert(); mh.synth_gradients(0, amp, 1, 1)
             ts = []
             for _ in range(7):

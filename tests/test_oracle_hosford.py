@@ -163,6 +163,56 @@ def test_per_point_properties_match_uniform_runs():
             assert np.array_equal(uni["stress"], mixed["stress"][sel]) and np.array_equal(uni["Ct"], mixed["Ct"][sel])
 
 
+def _mandel_deviators(S):
+    r2 = np.sqrt(2.0)
+    S = S - np.eye(3) * (np.trace(S, axis1=1, axis2=2) / 3.0)[:, None, None]
+    return S, np.stack([S[:, 0, 0], S[:, 1, 1], S[:, 2, 2], r2 * S[:, 0, 1], r2 * S[:, 0, 2], r2 * S[:, 1, 2]], 1)
+
+
+def test_noniterative_eigen_decomposition_is_backward_stable():
+    """The update's eigen-decomposition (isolated root of the characteristic cubic -> cross product -> one Jacobi
+    rotation in the normal plane) over random, nearly degenerate, pure-shear-like and exactly diagonal / axisymmetric
+    spectra: residual, orthogonality and eigenvalues (vs LAPACK) to a few ulp of |A|."""
+    from oracle import cport
+
+    rng = np.random.default_rng(1)
+    n = 50000
+    sym = lambda M: (M + np.swapaxes(M, 1, 2)) / 2
+    Q, _ = np.linalg.qr(rng.standard_normal((n, 3, 3)))
+    spectra = lambda L: sym(Q @ (L[:, :, None] * np.swapaxes(Q, 1, 2)))
+    e = 10.0 ** rng.uniform(-17, 0, n)
+    sg = rng.choice([-1.0, 1.0], n)
+    diag = np.array([np.diag(np.array(L, float)[list(perm)]) for L in ([2, -1, -1], [-2, 1, 1], [1, -1, 0], [1, 0, -1])
+                     for perm in ([0, 1, 2], [1, 2, 0], [2, 0, 1], [0, 2, 1])])
+    cases = {
+        "random": sym(rng.standard_normal((n, 3, 3))) * (10.0 ** rng.integers(-3, 9, n))[:, None, None],
+        "nearly repeated": 300.0 * spectra(np.stack([2 * sg, -sg + e, -sg - e], 1)),
+        "pure-shear-like": spectra(np.stack([np.ones(n), 0.1 * e, -1 - 0.1 * e], 1)),
+        "diagonal": diag,
+    }
+    for name, S in cases.items():
+        S, s6 = _mandel_deviators(S)
+        l, V = cport.hosford_eig(s6)
+        scale = np.linalg.norm(S, axis=(1, 2))
+        assert np.max(np.linalg.norm(S @ V - V * l[:, None, :], axis=(1, 2)) / scale) < 4e-15, name
+        assert np.max(np.linalg.norm(np.swapaxes(V, 1, 2) @ V - np.eye(3), axis=(1, 2))) < 4e-15, name
+        assert np.max(np.linalg.norm(np.sort(l, 1) - np.linalg.eigvalsh(S), axis=1) / scale) < 4e-15, name
+    l, V = cport.hosford_eig(np.zeros((1, 6)))  # zero deviator: never a candidate point, still well defined
+    assert np.array_equal(l, np.zeros((1, 3))) and np.array_equal(V[0], np.eye(3))
+
+
+def test_fixed_count_root_is_accurate_for_every_exponent():
+    """``q^(-1/a)`` of the criterion: Taylor start + two third-order steps, no division, no data-dependent trip count.
+    Scanned over q in (0.5, 1] for every even a in [2, 64] against extended precision: a few ulp."""
+    from oracle import cport
+
+    q = np.concatenate([np.linspace(0.5, 1.0, 20001)[1:], 0.5 + 2.0 ** -np.arange(2, 53), 1.0 - 2.0 ** -np.arange(2, 54)])
+    for a in range(2, 65, 2):
+        w = cport.hosford_root(q, a)
+        exact = q.astype(np.longdouble) ** (-np.longdouble(1.0) / a)
+        assert float(np.max(np.abs(w / exact - 1.0))) < 4 * np.finfo(float).eps, a
+
+
 @pytest.mark.parametrize("a", [2, 4, 6, 8, 10, 20, 64])
 def test_candidate_bound_is_the_pure_shear_ratio(a):
     """sup sigma_eq / seq_Mises over all stress states = (2^(a-1)+1)^(1/a)/sqrt(3) (pure shear): the kernels finish points
