@@ -514,13 +514,20 @@ DXM_HD void hos_finish(const double lam, const double mu, const HosTrial& tr, co
       wN1[cc] = fma_c(An12, mN2[cc], fma_c(An11, mN1[cc], An01 * mN0[cc]));
       wN2[cc] = fma_c(An22, mN2[cc], fma_c(An12, mN1[cc], An02 * mN0[cc]));
     }
+    // the tangent is Q^T D Q with Q = rows (mN, mS) and D = blockdiag(An, diag G): wN = An mN above, gS = G mS here
+    double gS0[6], gS1[6], gS2[6];
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) {
+      gS0[cc] = G0 * mS0[cc];
+      gS1[cc] = G1 * mS1[cc];
+      gS2[cc] = G2 * mS2[cc];
+    }
 #pragma unroll
     for (int j = 0; j < 6; ++j)
 #pragma unroll
       for (int i = j; i < 6; ++i) {
-        const double vn = fma_c(mN2[j], wN2[i], fma_c(mN1[j], wN1[i], mN0[j] * wN0[i]));
-        const double vs = fma_c(G2, mS2[j] * mS2[i], fma_c(G1, mS1[j] * mS1[i], G0 * (mS0[j] * mS0[i])));
-        ct21[sym6_packed(j * 6 + i)] = vn + vs;
+        const double vs = fma_c(mS2[j], gS2[i], fma_c(mS1[j], gS1[i], mS0[j] * gS0[i]));
+        ct21[sym6_packed(j * 6 + i)] = fma_c(mN2[j], wN2[i], fma_c(mN1[j], wN1[i], fma_c(mN0[j], wN0[i], vs)));
       }
   }
   double chk = (tr.seq + fabs(tr.pm)) + p_new;

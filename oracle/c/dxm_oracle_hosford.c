@@ -436,11 +436,13 @@ void dxo_hosford(int64_t n, const double* eps, const double* e_old, const double
       double wN[3][6]; /* wN_i = sum_j An_ij mN_j */
       for (int i = 0; i < 3; ++i)
         for (int cc = 0; cc < 6; ++cc) wN[i][cc] = dot3(An[i][0], mN[0][cc], An[i][1], mN[1][cc], An[i][2], mN[2][cc]);
+      double gS[3][6]; /* gS_k = G_k mS_k: the tangent is Q^T D Q, Q = rows (mN, mS), D = blockdiag(An, diag G) */
+      for (int k = 0; k < 3; ++k)
+        for (int cc = 0; cc < 6; ++cc) gS[k][cc] = G[k] * mS[k][cc];
       for (int j = 0; j < 6; ++j)
         for (int i = j; i < 6; ++i) {
-          const double vn = dot3(mN[0][j], wN[0][i], mN[1][j], wN[1][i], mN[2][j], wN[2][i]);
-          const double vs = FMA(G[2], mS[2][j] * mS[2][i], FMA(G[1], mS[1][j] * mS[1][i], G[0] * (mS[0][j] * mS[0][i])));
-          const double v = vn + vs;
+          const double vs = FMA(mS[2][j], gS[2][i], FMA(mS[1][j], gS[1][i], mS[0][j] * gS[0][i]));
+          const double v = FMA(mN[2][j], wN[2][i], FMA(mN[1][j], wN[1][i], FMA(mN[0][j], wN[0][i], vs)));
           ct[j * 6 + i] = v;
           ct[i * 6 + j] = v;
         }
