@@ -209,16 +209,20 @@ DXM_HD void fe_stage_flux(const int kind, const int row, const double v, double*
   }
 }
 
-// Tangent row `row` (packed symmetric 21 | row-major 81) of one point -> the A[(r,j)][(s,l)] entries it feeds.
+// Tangent row `row` (packed symmetric 21 | row-major 81) of one point -> the A[(r,j)][(s,l)] entries it feeds: their
+// positions in the T2 x T2 tensor (at most 8: the minor symmetries of a Mandel pair and the mirror of the symmetric 6x6
+// tangent), and the factor undoing the Mandel scaling.  The kernel evaluates this map once per CTA into shared memory.
 template <int TDIM>
-DXM_HD void fe_stage_tangent(const int kind, const int row, const double v, double* A /* [T2*T2] */) {
+DXM_HD void fe_tangent_map(const int kind, const int row, int16_t (&dst)[8], int& cnt, double& w) {
   constexpr double kR2 = 0.70710678118654752440;
   constexpr int T2 = TDIM * TDIM;
   int r, j, s, l;
+  cnt = 0;
+  w = 1.0;
   if (kind == 1) {
     vec9_pair(row / 9, r, j);
     vec9_pair(row % 9, s, l);
-    if (r < TDIM && j < TDIM && s < TDIM && l < TDIM) A[(r * TDIM + j) * T2 + s * TDIM + l] = v;
+    if (r < TDIM && j < TDIM && s < TDIM && l < TDIM) dst[cnt++] = (int16_t)((r * TDIM + j) * T2 + s * TDIM + l);
     return;
   }
   // packed row -> Mandel pair (m1 <= m2), row-major upper triangle
@@ -232,29 +236,59 @@ DXM_HD void fe_stage_tangent(const int kind, const int row, const double v, doub
   mandel_pair(m2, s, l);
   if (r >= TDIM || j >= TDIM || s >= TDIM || l >= TDIM) return;
   const int noff = (r != j ? 1 : 0) + (s != l ? 1 : 0);
-  const double w = noff == 0 ? v : (noff == 1 ? v * kR2 : v * 0.5);
+  w = noff == 0 ? 1.0 : (noff == 1 ? kR2 : 0.5);
   // every tensor entry (r,j | j,r) x (s,l | l,s) of the pair, and its mirror (the 6x6 tangent is symmetric)
   for (int t1 = 0; t1 < (r != j ? 2 : 1); ++t1)
     for (int t2 = 0; t2 < (s != l ? 2 : 1); ++t2) {
       const int rj = t1 ? j * TDIM + r : r * TDIM + j, sl = t2 ? l * TDIM + s : s * TDIM + l;
-      A[rj * T2 + sl] = w;
-      A[sl * T2 + rj] = w;
+      dst[cnt++] = (int16_t)(rj * T2 + sl);
+      dst[cnt++] = (int16_t)(sl * T2 + rj);
     }
 }
 
+template <int TDIM>
+DXM_HD void fe_stage_tangent(const int kind, const int row, const double v, double* A /* [T2*T2] */) {
+  int16_t dst[8];
+  int cnt;
+  double w;
+  fe_tangent_map<TDIM>(kind, row, dst, cnt, w);
+  const double vw = v * w;
+  for (int c = 0; c < cnt; ++c) A[dst[c]] = vw;
+}
+
 // ---- one column (b, s) of one cell, from the staged arrays of the cell's nqp points -----------------------------------
-// g, gv: [nqp][nd*TDIM]; S: [nqp][T2]; A: [nqp][T2*T2].  The kernel runs exactly these helpers, one lane per column;
-// __host__ __device__ so that a CPU test can run them against the oracle (tests/fe_host_check.cu).
+// g, gv: NODE-MAJOR [nd][nqp][TDIM] (the nqp*TDIM values of one basis function are one contiguous, 16-byte aligned run:
+// 128-bit shared-memory loads); S: [nqp][T2]; A: [nqp][T2*T2].  The kernel runs exactly these helpers, one lane per
+// column; __host__ __device__ so that a CPU test can run them against the oracle (tests/fe_host_check.cu).
+
+// N consecutive doubles from a 16-byte aligned address (N even on the device fast path)
+template <int N>
+DXM_HD void fe_load_run(const double* p, double* o) {
+#ifdef __CUDA_ARCH__
+  if (N % 2 == 0) {
+    const double2* p2 = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      const double2 v = p2[i];
+      o[2 * i] = v.x;
+      o[2 * i + 1] = v.y;
+    }
+    return;
+  }
+#endif
+#pragma unroll
+  for (int i = 0; i < N; ++i) o[i] = p[i];
+}
+
 // gb[q][l] = g_q[b][l]
 template <int TDIM, int NQP>
 DXM_HD void fe_form_column_g(const int nqp_rt, const int nd, const int b, const double* g, double* gb /* [nqp][TDIM] */) {
-  const int nqp = NQP > 0 ? NQP : nqp_rt;
-#pragma unroll
-  for (int q = 0; q < (NQP > 0 ? NQP : kFeMaxQp); ++q) {
-    if (NQP == 0 && q >= nqp) break;
-#pragma unroll
-    for (int l = 0; l < TDIM; ++l) gb[q * TDIM + l] = g[(int64_t)q * nd * TDIM + b * TDIM + l];
+  (void)nd;
+  if (NQP > 0) {
+    fe_load_run<(NQP > 0 ? NQP : 1) * TDIM>(g + (int64_t)b * NQP * TDIM, gb);
+    return;
   }
+  for (int i = 0; i < nqp_rt * TDIM; ++i) gb[i] = g[(int64_t)b * nqp_rt * TDIM + i];
 }
 
 // U[q][j] = sum_l A_q[(r,j)][(s,l)] g_q[b][l]   for the rows (., r) of the element matrix
@@ -281,14 +315,18 @@ DXM_HD void fe_form_column_u(const int nqp_rt, const int r, const int s, const d
 // ke[(a,r),(b,s)] = sum_q sum_j (vol_q g_q[a][j]) U_q[j]   (q outer, j inner, one product then fused steps)
 template <int TDIM, int NQP>
 DXM_HD double fe_form_entry(const int nqp_rt, const int nd, const int a, const double* gv, const double* U) {
+  (void)nd;
   const int nqp = NQP > 0 ? NQP : nqp_rt;
-  double acc = 0.0;
+  double ga[(NQP > 0 ? NQP : kFeMaxQp) * TDIM];
+  if (NQP > 0)
+    fe_load_run<(NQP > 0 ? NQP : 1) * TDIM>(gv + (int64_t)a * NQP * TDIM, ga);
+  else
+    for (int i = 0; i < nqp * TDIM; ++i) ga[i] = gv[(int64_t)a * nqp * TDIM + i];
+  double acc = ga[0] * U[0];
 #pragma unroll
-  for (int q = 0; q < (NQP > 0 ? NQP : kFeMaxQp); ++q) {
-    if (NQP == 0 && q >= nqp) break;
-    const double* ga = gv + (int64_t)q * nd * TDIM + a * TDIM;
-#pragma unroll
-    for (int j = 0; j < TDIM; ++j) acc = (q == 0 && j == 0) ? ga[0] * U[0] : fma_c(ga[j], U[q * TDIM + j], acc);
+  for (int i = 1; i < (NQP > 0 ? NQP : kFeMaxQp) * TDIM; ++i) {
+    if (NQP == 0 && i >= nqp * TDIM) break;
+    acc = fma_c(ga[i], U[i], acc);
   }
   return acc;
 }
@@ -296,13 +334,14 @@ DXM_HD double fe_form_entry(const int nqp_rt, const int nd, const int a, const d
 // fe[(b,s)] = sum_q sum_j S_q[s][j] (vol_q g_q[b][j])
 template <int TDIM, int NQP>
 DXM_HD double fe_form_vector_entry(const int nqp_rt, const int nd, const int b, const int s, const double* gv, const double* S) {
+  (void)nd;
   constexpr int T2 = TDIM * TDIM;
   const int nqp = NQP > 0 ? NQP : nqp_rt;
   double acc = 0.0;
 #pragma unroll
   for (int q = 0; q < (NQP > 0 ? NQP : kFeMaxQp); ++q) {
     if (NQP == 0 && q >= nqp) break;
-    const double* gbv = gv + (int64_t)q * nd * TDIM + b * TDIM;
+    const double* gbv = gv + ((int64_t)b * nqp + q) * TDIM;
 #pragma unroll
     for (int j = 0; j < TDIM; ++j) {
       const double sv = S[q * T2 + s * TDIM + j];
@@ -312,21 +351,23 @@ DXM_HD double fe_form_vector_entry(const int nqp_rt, const int nd, const int b, 
   return acc;
 }
 
+constexpr int kFeMinBlocks = 4;  // resident CTAs per SM the register allocation targets (16 warps)
+
 // NQP > 0: Gauss points per cell at compile time (the column state stays in registers); NQP == 0: run-time count up to
 // kFeMaxQp (local-memory arrays; uncommon rules)
 template <int TDIM, int ND, int NQP, int MODE>
-__global__ void __launch_bounds__(32 * kFeWarps, 4) fe_forms_kernel(const FeFormArgs a, const FeFormSmem L) {
-  extern __shared__ double smem[];
+__global__ void __launch_bounds__(32 * kFeWarps, kFeMinBlocks) fe_forms_kernel(const FeFormArgs a, const FeFormSmem L) {
+  extern __shared__ __align__(16) double smem[];
   constexpr int T2 = TDIM * TDIM;
   constexpr int NDC = ND > 0 ? ND : kFeMaxNd;
-  double* s_vol = smem + L.off_vol / sizeof(double);    // [np]
-  double* s_g = smem + L.off_g / sizeof(double);        // [np][nd][TDIM]
-  double* s_gv = smem + L.off_gv / sizeof(double);      // [np][nd][TDIM]   vol_q g
+  constexpr int NT = 32 * kFeWarps;
+  double* s_g = smem + L.off_g / sizeof(double);        // [cell][nd][nqp][TDIM]
+  double* s_gv = smem + L.off_gv / sizeof(double);      // [cell][nd][nqp][TDIM]   vol_q g
   double* s_flux = smem + L.off_flux / sizeof(double);  // [np][T2]
   double* s_ct = smem + L.off_ct / sizeof(double);      // [np][T2*T2]
   const int nd = ND > 0 ? ND : a.nd;
   const int ndof = nd * TDIM;
-  const int nqp = a.nqp, np = L.np;
+  const int nqp = NQP > 0 ? NQP : a.nqp, np = kFeWarps * nqp;
   const int nflux = a.kind == 0 ? 6 : 9, nct = a.kind == 0 ? kSym6Rows : 81;
   const int64_t c0 = (int64_t)blockIdx.x * kFeWarps;
   const int ncell = (int)min((int64_t)kFeWarps, a.num_cells - c0);
@@ -334,12 +375,42 @@ __global__ void __launch_bounds__(32 * kFeWarps, 4) fe_forms_kernel(const FeForm
   __shared__ int64_t s_cell[kFeWarps];  // the CTA's cells: consecutive, or taken from the launch's cell list
   // first CSR entry of every global row the CTA's cells touch; -1: constrained row (left alone)
   __shared__ int64_t s_rowlo[MODE == MODE_ELEMENT ? 1 : kFeWarps * kFeMaxNd * TDIM];
+  __shared__ double s_K[kFeWarps][TDIM * TDIM + 1];  // J^-1 and |det J| of the CTA's cells
+  // tangent row -> tensor positions (fe_tangent_map), evaluated once per CTA
+  __shared__ int16_t s_dst[81][8];
+  __shared__ double s_w[81];
+  __shared__ int8_t s_cnt[81];
   if (threadIdx.x < kFeWarps)
     s_cell[threadIdx.x] = threadIdx.x < ncell ? (a.cell_list ? (int64_t)a.cell_list[c0 + threadIdx.x] : c0 + threadIdx.x) : 0;
+  if (a.want_mat && threadIdx.x < nct) {
+    int cnt;
+    double w;
+    int16_t dst[8];
+    fe_tangent_map<TDIM>(a.kind, threadIdx.x, dst, cnt, w);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s_dst[threadIdx.x][c] = c < cnt ? dst[c] : (int16_t)0;
+    s_w[threadIdx.x] = w;
+    s_cnt[threadIdx.x] = (int8_t)cnt;
+  }
   __syncthreads();
 
-  // ---- stage: geometry -> vol_q, g, vol_q g; flux / tangent rows of this CTA's points as tensors ------------------
-  __shared__ double s_K[kFeWarps][TDIM * TDIM + 1];  // J^-1 and |det J| of the CTA's cells
+  // ---- stage: geometry -> g, vol_q g; flux / tangent rows of this CTA's points as tensors --------------------------
+  // The tangent loads go first and stay in flight while the geometry is worked out: thread t owns point k = t % np and
+  // the rows t / np, t / np + NT / np, ... -- every load instruction of a warp reads whole contiguous runs of SoA rows.
+  const int rpp = NT / np;                                   // tangent rows per pass of the CTA
+  const int tk = threadIdx.x % np, tr0 = threadIdx.x / np;   // this thread's point and first row
+  const bool tlive = a.want_mat && tr0 < rpp && tk < npv;
+  constexpr int kRpp = NQP > 0 ? NT / (kFeWarps * NQP) : 1;
+  constexpr int kMaxPass = (81 + kRpp - 1) / kRpp;  // passes that cover the 81 rows of the finite-strain tangent
+  double tv[NQP > 0 ? kMaxPass : 1];
+  const double* tsrc = a.ct + s_cell[tk / nqp] * nqp + (tk % nqp);
+  if (NQP > 0) {
+#pragma unroll
+    for (int m = 0; m < kMaxPass; ++m) {
+      const int row = tr0 + m * rpp;
+      tv[m] = (tlive && row < nct) ? __ldcs(tsrc + (int64_t)row * a.ld) : 0.0;
+    }
+  }
   if (threadIdx.x < ncell) {
     double K[TDIM][TDIM], det;
     cell_geometry<TDIM>(a.coords, a.geom_dofs + s_cell[threadIdx.x] * (TDIM + 1), K, det);
@@ -349,8 +420,23 @@ __global__ void __launch_bounds__(32 * kFeWarps, 4) fe_forms_kernel(const FeForm
       for (int j = 0; j < TDIM; ++j) s_K[threadIdx.x][i * TDIM + j] = K[i][j];
     s_K[threadIdx.x][TDIM * TDIM] = fabs(det);
   }
+  for (int i = threadIdx.x; i < nflux * np; i += NT) {
+    const int row = i / np, k = i - row * np;
+    if (k < npv) {
+      const int lc = k / nqp;
+      fe_stage_flux<TDIM>(a.kind, row, __ldcs(a.flux + (int64_t)row * a.ld + s_cell[lc] * nqp + (k - lc * nqp)),
+                          s_flux + (int64_t)k * T2);
+    }
+  }
+  if (a.want_mat && MODE != MODE_ELEMENT) {
+    for (int i = threadIdx.x; i < ncell * ndof; i += NT) {
+      const int lc = i / ndof, row = i - lc * ndof;
+      const int64_t grow = (int64_t)a.u_dofs[s_cell[lc] * nd + row / TDIM] * TDIM + row % TDIM;
+      s_rowlo[lc * kFeMaxNd * TDIM + row] = (a.bc && a.bc[grow]) ? -1 : a.rowptr[grow];
+    }
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < npv * nd; i += blockDim.x) {  // one (point, basis function) per item
+  for (int i = threadIdx.x; i < npv * nd; i += NT) {  // one (point, basis function) per item
     const int pt = i / nd, n = i - pt * nd;
     const int lc = pt / nqp, q = pt - lc * nqp;
     double K[TDIM][TDIM];
@@ -360,36 +446,36 @@ __global__ void __launch_bounds__(32 * kFeWarps, 4) fe_forms_kernel(const FeForm
       for (int jj = 0; jj < TDIM; ++jj) K[ii][jj] = s_K[lc][ii * TDIM + jj];
     const double vol = a.weights[q] * s_K[lc][TDIM * TDIM];
     const double* dq = a.dphi + (int64_t)q * nd * TDIM;
+    const int64_t o = (((int64_t)lc * nd + n) * nqp + q) * TDIM;
 #pragma unroll
     for (int j = 0; j < TDIM; ++j) {
       const double gk = fe_form_g_entry<TDIM>(dq, K, n, j);
-      s_g[(int64_t)i * TDIM + j] = gk;
-      s_gv[(int64_t)i * TDIM + j] = vol * gk;
-    }
-    if (n == 0) s_vol[pt] = vol;
-  }
-  for (int i = threadIdx.x; i < nflux * np; i += blockDim.x) {
-    const int row = i / np, k = i - row * np;
-    if (k < npv) {
-      const int lc = k / nqp;
-      fe_stage_flux<TDIM>(a.kind, row, __ldcs(a.flux + (int64_t)row * a.ld + s_cell[lc] * nqp + (k - lc * nqp)),
-                          s_flux + (int64_t)k * T2);
+      s_g[o + j] = gk;
+      s_gv[o + j] = vol * gk;
     }
   }
   if (a.want_mat) {
-    for (int i = threadIdx.x; i < nct * np; i += blockDim.x) {
-      const int row = i / np, k = i - row * np;
-      if (k < npv) {
-        const int lc = k / nqp;
-        fe_stage_tangent<TDIM>(a.kind, row, __ldcs(a.ct + (int64_t)row * a.ld + s_cell[lc] * nqp + (k - lc * nqp)),
-                               s_ct + (int64_t)k * T2 * T2);
+    if (NQP > 0) {
+      double* dstA = s_ct + (int64_t)tk * T2 * T2;
+#pragma unroll
+      for (int m = 0; m < kMaxPass; ++m) {
+        const int row = tr0 + m * rpp;
+        if (tlive && row < nct) {
+          const double vw = tv[m] * s_w[row];
+          const int cnt = s_cnt[row];
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c < cnt) dstA[s_dst[row][c]] = vw;
+        }
       }
-    }
-    if (MODE != MODE_ELEMENT) {
-      for (int i = threadIdx.x; i < ncell * ndof; i += blockDim.x) {
-        const int lc = i / ndof, row = i - lc * ndof;
-        const int64_t grow = (int64_t)a.u_dofs[s_cell[lc] * nd + row / TDIM] * TDIM + row % TDIM;
-        s_rowlo[lc * kFeMaxNd * TDIM + row] = (a.bc && a.bc[grow]) ? -1 : a.rowptr[grow];
+    } else {
+      for (int i = threadIdx.x; i < nct * np; i += NT) {
+        const int row = i / np, k = i - row * np;
+        if (k < npv) {
+          const int lc = k / nqp;
+          fe_stage_tangent<TDIM>(a.kind, row, __ldcs(a.ct + (int64_t)row * a.ld + s_cell[lc] * nqp + (k - lc * nqp)),
+                                 s_ct + (int64_t)k * T2 * T2);
+        }
       }
     }
   }
@@ -433,50 +519,65 @@ __global__ void __launch_bounds__(32 * kFeWarps, 4) fe_forms_kernel(const FeForm
     const double lift = (col_bc && a.lift) ? a.lift[gcol] : 0.0;
     const bool any_lift = a.lift && __any_sync(0xffffffffu, col_bc);
     const bool writer = live && !col_bc;
-    // node-blocked patterns: the offset of (node a, node b) inside the rows of node a was found once (fe_offsets_kernel);
-    // the TDIM columns of node b are consecutive there.  Without the table: binary search per entry.
-    int32_t offs[NDC];
-#pragma unroll
-    for (int an = 0; an < NDC; ++an) {
-      if (ND == 0 && an >= nd) break;
-      offs[an] = (a.off && writer) ? a.off[(cell * nd + an) * nd + b] : -1;
-    }
     unsigned miss = 0;
-#pragma unroll
-    for (int r = 0; r < TDIM; ++r) {
-      fe_form_column_u<TDIM, NQP>(nqp, r, s, gb, A, U);
-      int64_t pos[NDC];
+    if (a.off && !any_lift) {
+      // node-blocked pattern, no constrained column in this cell (all but the cells on a Dirichlet boundary): the offset
+      // of (node a, node b) inside the rows of node a was found once (fe_offsets_kernel) and the TDIM columns of node b
+      // are consecutive there -- a row of the element matrix leaves the warp as one predicated reduction instruction
+      int32_t offs[NDC];
 #pragma unroll
       for (int an = 0; an < NDC; ++an) {
         if (ND == 0 && an >= nd) break;
-        const int64_t lo = rowlo[an * TDIM + r];
-        int64_t p = -1;
-        if (writer && lo >= 0) {
-          if (a.off)
-            p = offs[an] >= 0 ? lo + offs[an] + s : -2;
-          else {
-            const int64_t grow = (int64_t)ud[an] * TDIM + r;
-            p = csr_find(a.colidx, lo, a.rowptr[grow + 1], (int32_t)gcol);
-            if (p < 0) p = -2;
+        offs[an] = writer ? a.off[(cell * nd + an) * nd + b] : -1;
+      }
+      // (r rolled on purpose: unrolled, the compiler keeps the r-invariant vol g rows of all nodes live across the three
+      // passes and spills them to local memory instead of reading shared memory again)
+#pragma unroll 1
+      for (int r = 0; r < TDIM; ++r) {
+        fe_form_column_u<TDIM, NQP>(nqp, r, s, gb, A, U);
+#pragma unroll
+        for (int an = 0; an < NDC; ++an) {
+          if (ND == 0 && an >= nd) break;
+          const int64_t lo = rowlo[an * TDIM + r];  // < 0: constrained row, untouched (unit diagonal set by the host API)
+          const double v = fe_form_entry<TDIM, NQP>(nqp, nd, an, gv, U);
+          const bool row_ok = writer && lo >= 0;
+          if (row_ok && offs[an] >= 0) atomicAdd(a.vals + (lo + offs[an] + s), v);  // result unused: a RED
+          miss += (row_ok && offs[an] < 0) ? 1u : 0u;
+        }
+      }
+    } else {
+      // cells with a constrained column (lifting) and patterns without an offset table (binary search of the column in
+      // the sorted CSR row, per entry): rolled loops
+#pragma unroll 1
+      for (int r = 0; r < TDIM; ++r) {
+        fe_form_column_u<TDIM, NQP>(nqp, r, s, gb, A, U);
+#pragma unroll 1
+        for (int an = 0; an < nd; ++an) {
+          const int64_t lo = rowlo[an * TDIM + r];
+          if (lo < 0) continue;
+          const double v = fe_form_entry<TDIM, NQP>(nqp, nd, an, gv, U);
+          if (any_lift) {
+            // constrained columns move to the right-hand side (apply_lifting): b[row] -= sum_bc K[row][col] lift[col]
+            double lf = col_bc ? v * lift : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) lf += __shfl_xor_sync(0xffffffffu, lf, o);
+            if (lane == 0 && lf != 0.0) atomicAdd(a.b + (int64_t)ud[an] * TDIM + r, -lf);
+          }
+          if (writer) {
+            int64_t p;
+            if (a.off) {
+              const int32_t o = a.off[(cell * nd + an) * nd + b];
+              p = o >= 0 ? lo + o + s : -1;
+            } else {
+              const int64_t grow = (int64_t)ud[an] * TDIM + r;
+              p = csr_find(a.colidx, lo, a.rowptr[grow + 1], (int32_t)gcol);
+            }
+            if (p >= 0)
+              atomicAdd(a.vals + p, v);
+            else
+              ++miss;
           }
         }
-        pos[an] = p;  // -1: nothing to write, -2: no slot in the pattern
-      }
-#pragma unroll
-      for (int an = 0; an < NDC; ++an) {
-        if (ND == 0 && an >= nd) break;
-        if (rowlo[an * TDIM + r] < 0) continue;  // constrained row: untouched (unit diagonal set by the host API)
-        const double v = fe_form_entry<TDIM, NQP>(nqp, nd, an, gv, U);
-        if (any_lift) {
-          // constrained columns move to the right-hand side (apply_lifting): b[row] -= sum_bc K[row][col] lift[col]
-          double lf = col_bc ? v * lift : 0.0;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) lf += __shfl_xor_sync(0xffffffffu, lf, o);
-          if (lane == 0 && lf != 0.0) atomicAdd(a.b + (int64_t)ud[an] * TDIM + r, -lf);
-        }
-        if (pos[an] == -2) ++miss;
-        if (pos[an] < 0) continue;
-        atomicAdd(a.vals + pos[an], v);  // result unused: a RED
       }
     }
     if (miss) atomicAdd(a.missing, (unsigned long long)miss);

@@ -28,10 +28,14 @@ void form_cells(const dxm::FeFormArgs& a) {
       A((size_t)nqp * T2 * T2);
   double gb[dxm::kFeMaxQp * TDIM], U[dxm::kFeMaxQp * TDIM];
   for (int64_t c = 0; c < a.num_cells; ++c) {
+    std::vector<double> gq((size_t)nd * TDIM);
     for (int q = 0; q < nqp; ++q) {
-      double* gq = g.data() + (size_t)q * nd * TDIM;
-      dxm::fe_form_point_geometry<TDIM>(a, c, q, nd, vol[q], gq);
-      for (int k = 0; k < nd * TDIM; ++k) gv[(size_t)q * nd * TDIM + k] = vol[q] * gq[k];
+      dxm::fe_form_point_geometry<TDIM>(a, c, q, nd, vol[q], gq.data());
+      for (int n = 0; n < nd; ++n)  // node-major staging, as the kernel lays g / vol g out in shared memory
+        for (int j = 0; j < TDIM; ++j) {
+          g[((size_t)n * nqp + q) * TDIM + j] = gq[n * TDIM + j];
+          gv[((size_t)n * nqp + q) * TDIM + j] = vol[q] * gq[n * TDIM + j];
+        }
       for (int row = 0; row < nflux; ++row)
         dxm::fe_stage_flux<TDIM>(a.kind, row, a.flux[(int64_t)row * a.ld + c * nqp + q], S.data() + (size_t)q * T2);
       if (a.want_mat)
