@@ -11,15 +11,17 @@
 // per point) then never leaves the device -- only the assembled system does.
 //
 // Round-2 kernel: ONE WARP PER CELL, ONE LANE PER ELEMENT-MATRIX COLUMN (b, s).
-//   * the CTA (8 warps = 8 consecutive cells) stages vol_q, g, vol_q g and the flux / tangent of its points as plain
-//     tensors S[r][j], A[(r,j)][(s,l)] in shared memory with coalesced loads (every SoA row is one contiguous run);
+//   * the CTA (4 warps = 4 consecutive cells) stages g, vol_q g (node-major: the nqp * TDIM values of a basis function are
+//     one 16-byte aligned run) and the flux / tangent of its points as plain tensors S[r][j], A[(r,j)][(s,l)] in shared
+//     memory; the tangent loads of a thread are issued back to back (every SoA row is one contiguous run) and scattered
+//     through a row -> tensor-position map evaluated once per CTA;
 //   * a lane keeps its own g[b][:] and U_q[(r,j)] = sum_l A_q[(r,j)][(s,l)] g_q[b][l] in registers (formed once per
-//     cell), and every entry of its column is then sum_q sum_j (vol_q g_q[a][j]) U_q[(r,j)]: 12 fused multiply-adds on
-//     three broadcast shared-memory operands -- 15 k DFMA per P2 tetrahedron instead of the 29 k DMUL + DADD and the
-//     ~130 shared-memory loads per row and point of the round-1 mapping (one thread per ROW);
-//   * a row of the element matrix leaves the warp as ONE reduction instruction whose lanes hit consecutive CSR entries
-//     (the three columns of a node are adjacent): ~11 L2 sectors per row instead of 30 scattered 8-byte atomics -- the
-//     round-1 kernel was bound by exactly that (597 M scattered fp64 atomics = 7.2 ms of its 7.2 ms).
+//     row direction), and every entry of its column is then sum_q sum_j (vol_q g_q[a][j]) U_q[(r,j)]: 12 fused
+//     multiply-adds on broadcast 128-bit shared-memory operands -- 15 k DFMA per P2 tetrahedron instead of the 29 k
+//     DMUL + DADD and the ~130 shared-memory loads per row and point of the round-1 mapping (one thread per ROW);
+//   * a row of the element matrix leaves the warp as ONE predicated reduction instruction (the three columns of a node
+//     are adjacent in the CSR row).  The scatter is bound by the SM's reduction issue rate (~0.77 fp64 reductions per
+//     cycle and SM: 192 G/s chip-wide, scripts/probe_bulk_red.cu); the kernel runs at ~1.15x that floor.
 // Tensor cores: not used.  FP64 DMMA (mma.sync.m8n8k4.f64, the only fp64 tensor path of sm_100) would have to treat the
 // gradient operator G (9 x 30) as dense although two thirds of it are structural zeros (delta_ss'): 147 kflop issued per
 // cell and point set for 28 kflop of useful work, at a peak (~40 TFLOP/s) no higher than the DFMA pipe's on B200.
@@ -351,7 +353,13 @@ DXM_HD double fe_form_vector_entry(const int nqp_rt, const int nd, const int b, 
   return acc;
 }
 
-constexpr int kFeMinBlocks = 4;  // resident CTAs per SM the register allocation targets (16 warps)
+// Resident CTAs per SM the register allocation targets: 5 (96 registers, no spills) -- 3.60 ms against 3.92 at 4 (120
+// registers); 6 / 7 CTAs need the largest shared-memory carve-out, whose smaller L1 costs more than the extra warps bring
+// (3.69-3.75 ms): the kernel is bound by the SM's reduction issue rate, not by latency (profiles/r02w_fe_forms_ab.json).
+#ifndef DXM_FE_MINB
+#define DXM_FE_MINB 5
+#endif
+constexpr int kFeMinBlocks = DXM_FE_MINB;
 
 // NQP > 0: Gauss points per cell at compile time (the column state stays in registers); NQP == 0: run-time count up to
 // kFeMaxQp (local-memory arrays; uncommon rules)

@@ -19,7 +19,11 @@ for name in names:
     env = dict(os.environ, DXM_VARIANT=name)
     env.pop("DXM_UNFUSED", None)
     print(f"==== variant '{name}'", flush=True)
-    r = subprocess.run([sys.executable, os.path.join(root, script), *args], env=env, cwd=root)
+    t0 = __import__("time").time()
+    r = subprocess.run([sys.executable, os.path.join(root, script), *args], env=env, cwd=root, stdout=subprocess.DEVNULL)
+    if not os.path.exists(produced) or os.path.getmtime(produced) < t0:  # the script's own file name: newest JSON
+        new = [p for p in glob.glob(os.path.join(root, "gpurun_out", "*.json")) if os.path.getmtime(p) >= t0]
+        produced = max(new, key=os.path.getmtime) if new else produced
     if r.returncode == 0 and os.path.exists(produced):
         res[name or "product"] = json.load(open(produced))
     else:
