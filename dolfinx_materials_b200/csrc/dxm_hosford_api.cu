@@ -42,7 +42,11 @@ int launch_at(const SmallStrainArgs& a, const HosLaunch& cfg, int* launches) {
   // spills) lose 9 % again (profiles/r02h_hosford_ab_minb5.json).  DXM_HOS_MINB=3|4 forces either.
   const int minb = cfg.minb ? cfg.minb : (cfg.tiled ? 3 : 4);
   if (minb == 3) return launch_at2<AT, VOCE, 3>(a, cfg, launches);
+#ifdef DXM_HOS_TRY_MINB  // experiment builds (DXM_VARIANT): another register target in place of the 128-register one
+  return launch_at2<AT, VOCE, DXM_HOS_TRY_MINB>(a, cfg, launches);
+#else
   return launch_at2<AT, VOCE, 4>(a, cfg, launches);
+#endif
 }
 }  // namespace
 
