@@ -19,6 +19,9 @@ namespace {
 constexpr int64_t kChunk = 1 << 19;  // points per pipeline chunk on the host path
 const char* kPropNames[kNProp] = {"E", "nu", "sig0", "H", "sigu", "b"};
 constexpr double kHosLowPlastic = 0.25;  // Hosford: 168-register build below this plastic fraction (previous call)
+// host arrays of at most this many points skip the copy engines: the transposition kernels read / write a mapped
+// page-locked staging block directly (no cudaMemcpyAsync, no event hand-offs between three streams: one stream, one wait)
+constexpr int64_t kSmallHostPoints = 2048;
 constexpr int64_t kAutoTimingPoints = 1 << 18;  // kernel_ms events by default only where two event records are noise
 constexpr bool kHostMirrorDefault = false;  // A/B on the B200 box: profiles/ (DXM_HOST_MIRROR overrides)
 }  // namespace
@@ -513,6 +516,7 @@ void free_handle(dxm_handle* h) {
   cudaFree(h->d_rec);
   cudaFree(h->d_gather);
   cudaFreeHost(h->h_rec);
+  if (h->h_small) cudaFreeHost(h->h_small);
   for (int s = 0; s < 2; ++s) {
     cudaFree(h->d_in[s]);
     cudaFree(h->d_out[s]);
@@ -958,6 +962,36 @@ static int integrate_impl(dxm_handle* h, int64_t start, int64_t count, const dou
   } else if (mem == DXM_MEM_HOST) {
     if (any_out && out_mem != DXM_MEM_HOST)
       return fail("dxm_integrate: host gradients require host outputs");
+    if (n <= kSmallHostPoints) {
+      // small batches (the reference's own test meshes hold 1 ... 16 points): latency, not bandwidth.  The gradients are
+      // copied by the CPU into a mapped page-locked block which the transposition kernel reads over the link, the packed
+      // outputs are written straight into that block by the device, and one stream wait ends the call.
+      const int nf = h->nflux, ni = h->nisv, nc = h->nct, ncs = h->nct_store;
+      const int64_t K = kSmallHostPoints;
+      if (!h->h_small) {
+        CK(cudaHostAlloc(&h->h_small, sizeof(double) * K * (h->ngrad + nf + ni + nc),
+                         cudaHostAllocMapped | cudaHostAllocPortable));
+      }
+      double* hin = h->h_small;
+      double* hfl = hin + K * h->ngrad;
+      double* his = hfl + K * nf;
+      double* hct = his + K * ni;
+      std::memcpy(hin, grad, sizeof(double) * n * h->ngrad);
+      if (launch_aos_to_soa(h, h->stream, hin, h->ngrad, 0, s1, start, n, h->ngrad)) return -1;
+      if (timed_update(h, start, n, dt, 2)) return -1;
+      if (flux && launch_soa_to_aos(h, h->stream, s1 + (int64_t)h->ngrad * ld, start, hfl, nf, 0, n, nf)) return -1;
+      if (isv && launch_soa_to_aos(h, h->stream, s1 + (int64_t)isv_row * ld, start, his, ni, 0, n, ni)) return -1;
+      if (ct && launch_soa_to_aos(h, h->stream, h->ct, start, hct, nc, 0, n, nc, ncs != nc)) return -1;
+      h->s1_valid = true;
+      CK(cudaStreamSynchronize(h->stream));
+      if (flux) std::memcpy(flux, hfl, sizeof(double) * n * nf);
+      if (isv) std::memcpy(isv, his, sizeof(double) * n * ni);
+      if (ct) std::memcpy(ct, hct, sizeof(double) * n * nc);
+      if (!stats) return 0;
+      if (finish_stats(h)) return -1;
+      *stats = h->last;
+      return (int)std::min<int64_t>(h->last.n_fail, 0x7fffffff);
+    }
     if (ensure_staging(h)) return -1;
     // 3-stage pipeline over chunks: H2D (s_in) | transpose + update + pack (stream) | D2H (s_out)
     // (+ a 4th stage on the host when the packed tangent is mirrored there, dxm_host_mirror.hpp)

@@ -92,6 +92,7 @@ struct dxm_handle {
   int64_t chunk = 0;
   double* d_in[2] = {nullptr, nullptr};
   double* d_out[2] = {nullptr, nullptr};
+  double* h_small = nullptr;  // mapped page-locked staging of the small-batch host path (dxm_api.cu: kSmallHostPoints)
   // host mirror of the packed tangent (dxm_host_mirror.hpp): page-locked ring of packed (chunk, 21) blocks
   static constexpr int kRing = 3;
   double* h_ctp[kRing] = {nullptr, nullptr, nullptr};
