@@ -206,6 +206,28 @@ int build_adjacency(dxm_mesh* m) {
 
 template <int MODE>
 int launch_fe_forms(dxm_mesh* m, dxm_handle* h, FeFormArgs& a) {
+  if (!a.want_mat && a.want_vec) {
+    // residual only: the thread-per-(cell, basis function) kernel where (nodes, Gauss points) are compile-time
+    const void* vk = nullptr;
+    if (m->tdim == 3)
+      vk = (m->nd == 10 && m->nqp == 4)  ? (const void*)fe_vector_kernel<3, 10, 4, MODE>
+           : (m->nd == 4 && m->nqp == 1) ? (const void*)fe_vector_kernel<3, 4, 1, MODE>
+           : (m->nd == 4 && m->nqp == 4) ? (const void*)fe_vector_kernel<3, 4, 4, MODE>
+                                         : nullptr;
+    else
+      vk = (m->nd == 6 && m->nqp == 3)   ? (const void*)fe_vector_kernel<2, 6, 3, MODE>
+           : (m->nd == 3 && m->nqp == 1) ? (const void*)fe_vector_kernel<2, 3, 1, MODE>
+           : (m->nd == 3 && m->nqp == 3) ? (const void*)fe_vector_kernel<2, 3, 3, MODE>
+                                         : nullptr;
+    if (vk) {
+      const int64_t grid = (a.num_cells * m->nd + kFeVecBlock - 1) / kFeVecBlock;
+      if (grid > 0x7fffffff) return fail("fe_forms: too many cells for one launch");
+      void* vargs[] = {(void*)&a};
+      CK(cudaLaunchKernel(vk, dim3((unsigned)grid), dim3(kFeVecBlock), vargs, 0, h->stream));
+      LAUNCH_CHECK();
+      return 0;
+    }
+  }
   const FeFormSmem L = fe_form_smem(m->tdim, m->nd, m->nqp, a.kind, MODE, a.want_mat != 0);
   // compile-time (nodes, Gauss points) for the hot-path elements: P2 / degree 2 and P1 / degree <= 1 simplices; anything
   // else runs the run-time instantiation

@@ -592,6 +592,61 @@ __global__ void __launch_bounds__(32 * kFeWarps, kFeMinBlocks) fe_forms_kernel(c
   }
 }
 
+// ---- residual only: one thread per (cell, basis function) -----------------------------------------------------------
+// fe[(b, s)] = sum_q sum_j S_q[s][j] (vol_q g_q[b][j]) needs no staging: 12 fused multiply-adds per component on values
+// the threads of a cell share through L1.  The warp-per-cell kernel above spends 0.86 ms on 663 552 P2 tetrahedra for this
+// (three block barriers and three dependent load phases per 4 cells); this one is bound by its 191 MB of flux reads.
+// Same operations in the same order as fe_form_vector_entry (bit-identical; tests/fe_host_check.cu compares the two).
+template <int TDIM, int ND, int NQP>
+DXM_HD void fe_vector_node(const FeFormArgs& a, const int64_t cell, const int n, double (&acc)[TDIM]) {
+  constexpr int T2 = TDIM * TDIM;
+  const int nflux = a.kind == 0 ? 6 : 9;
+  double K[TDIM][TDIM], det;
+  cell_geometry<TDIM>(a.coords, a.geom_dofs + cell * (TDIM + 1), K, det);
+  const double adet = fabs(det);
+#pragma unroll
+  for (int q = 0; q < NQP; ++q) {
+    const double vol = a.weights[q] * adet;
+    const double* dq = a.dphi + (int64_t)q * ND * TDIM;
+    double gv[TDIM], S[T2];
+#pragma unroll
+    for (int j = 0; j < TDIM; ++j) gv[j] = vol * fe_form_g_entry<TDIM>(dq, K, n, j);
+#pragma unroll
+    for (int i = 0; i < T2; ++i) S[i] = 0.0;
+#pragma unroll
+    for (int row = 0; row < 9; ++row)
+      if (row < nflux) fe_stage_flux<TDIM>(a.kind, row, a.flux[(int64_t)row * a.ld + cell * NQP + q], S);
+#pragma unroll
+    for (int s = 0; s < TDIM; ++s)
+#pragma unroll
+      for (int j = 0; j < TDIM; ++j) {
+        const double sv = S[s * TDIM + j];
+        acc[s] = (q == 0 && j == 0) ? sv * gv[0] : fma_c(sv, gv[j], acc[s]);
+      }
+  }
+}
+
+constexpr int kFeVecBlock = 256;
+template <int TDIM, int ND, int NQP, int MODE>
+__global__ void __launch_bounds__(kFeVecBlock) fe_vector_kernel(const FeFormArgs a) {
+  const int64_t t = (int64_t)blockIdx.x * kFeVecBlock + threadIdx.x;
+  const int64_t ci = t / ND;
+  const int n = (int)(t - ci * ND);
+  if (ci >= a.num_cells) return;
+  const int64_t cell = a.cell_list ? (int64_t)a.cell_list[ci] : ci;
+  double acc[TDIM];
+  fe_vector_node<TDIM, ND, NQP>(a, cell, n, acc);
+  if (MODE == MODE_ELEMENT) {
+#pragma unroll
+    for (int s = 0; s < TDIM; ++s) a.fe[(cell * ND + n) * TDIM + s] = acc[s];
+    return;
+  }
+  const int64_t g0 = (int64_t)a.u_dofs[cell * ND + n] * TDIM;
+#pragma unroll
+  for (int s = 0; s < TDIM; ++s)
+    if (!(a.bc && a.bc[g0 + s])) atomicAdd(a.b + g0 + s, acc[s]);
+}
+
 // ---- atomic-free assembly: element matrices -> CSR rows, node by node ---------------------------------------------------
 // The L2 retires ~90 G scalar fp64 reductions per second however they are grouped, which bounds the atomic scatter of the
 // 900 entries of a P2 tetrahedron at 6.5 ms for 663 k cells (profiles/r02g_fe_forms_assembly_experiments.json).  Instead:

@@ -5,12 +5,15 @@
 // fe_forms_kernel (shared-memory arrays of the CTA's points) is replayed with one cell per "CTA".
 // Test scaffolding only: nothing in the product calls this.
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "../dolfinx_materials_b200/csrc/dxm_fe_forms.cuh"
 #include "../dolfinx_materials_b200/csrc/dxm_fe_gradient.cuh"
 
 namespace {
+
+long g_vector_mismatch = 0;  // fe_vector_node vs fe_form_vector_entry, entries that differ
 
 template <int TDIM, int ND>
 void grad_cells(const dxm::FeGradArgs& a) {
@@ -53,6 +56,14 @@ void form_cells(const dxm::FeFormArgs& a) {
             a.ke[(c * ndof + an * TDIM + r) * ndof + col] = dxm::fe_form_entry<TDIM, NQP>(nqp, nd, an, gv.data(), U);
         }
     }
+    // the residual-only kernel's per-(cell, basis function) routine must give the same bits as the column routine
+    if (ND > 0 && NQP > 0)
+      for (int n = 0; n < nd; ++n) {
+        double acc[TDIM];
+        dxm::fe_vector_node<TDIM, (ND > 0 ? ND : 1), (NQP > 0 ? NQP : 1)>(a, c, n, acc);
+        for (int s = 0; s < TDIM; ++s)
+          if (std::memcmp(&acc[s], &a.fe[c * ndof + n * TDIM + s], sizeof(double)) != 0) ++g_vector_mismatch;
+      }
   }
 }
 
@@ -100,18 +111,21 @@ extern "C" int fe_forms_host(int tdim, int64_t num_cells, int nd, int nqp, int k
   a.fe = fe;
   a.ke = ke;
   if (nqp > dxm::kFeMaxQp) return -1;
-  // same (nodes, Gauss points) dispatch as launch_fe_forms (dxm_fe_api.cu)
+  g_vector_mismatch = 0;
+  // same (nodes, Gauss points) dispatch as launch_fe_forms (dxm_fe_api.cu); -2: the residual-only routine disagrees
   if (tdim == 3) {
-    if (!generic && nd == 10 && nqp == 4) return form_cells<3, 10, 4>(a), 0;
-    if (!generic && nd == 4 && nqp == 1) return form_cells<3, 4, 1>(a), 0;
-    if (!generic && nd == 4 && nqp == 4) return form_cells<3, 4, 4>(a), 0;
-    return form_cells<3, 0, 0>(a), 0;
+    if (!generic && nd == 10 && nqp == 4) form_cells<3, 10, 4>(a);
+    else if (!generic && nd == 4 && nqp == 1) form_cells<3, 4, 1>(a);
+    else if (!generic && nd == 4 && nqp == 4) form_cells<3, 4, 4>(a);
+    else form_cells<3, 0, 0>(a);
+    return g_vector_mismatch ? -2 : 0;
   }
   if (tdim == 2) {
-    if (!generic && nd == 6 && nqp == 3) return form_cells<2, 6, 3>(a), 0;
-    if (!generic && nd == 3 && nqp == 1) return form_cells<2, 3, 1>(a), 0;
-    if (!generic && nd == 3 && nqp == 3) return form_cells<2, 3, 3>(a), 0;
-    return form_cells<2, 0, 0>(a), 0;
+    if (!generic && nd == 6 && nqp == 3) form_cells<2, 6, 3>(a);
+    else if (!generic && nd == 3 && nqp == 1) form_cells<2, 3, 1>(a);
+    else if (!generic && nd == 3 && nqp == 3) form_cells<2, 3, 3>(a);
+    else form_cells<2, 0, 0>(a);
+    return g_vector_mismatch ? -2 : 0;
   }
   return -1;
 }
