@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -55,6 +56,21 @@ def test_no_cpu_fallback(jm):
         m.set_data_manager(8)
     with pytest.raises(RuntimeError):
         m.integrate([[0.0] * 6] * 8)
+
+
+def test_experiment_build_selection_fails_loudly_when_missing():
+    """``DXM_VARIANT=<name>`` selects ``lib/libdxm_cuda_<name>.so`` (kernel A/B runs, scripts/ab_variants.py); a variant
+    that was never built raises at the first use instead of silently loading the product library."""
+    code = ("import dolfinx_materials_b200 as jm, sys\n"
+            "from dolfinx_materials_b200 import _lib\n"
+            "assert _lib.LIB_PATH.name == 'libdxm_cuda_doesnotexist.so', _lib.LIB_PATH\n"
+            "try:\n    _lib.load()\nexcept RuntimeError as e:\n    assert 'missing' in str(e); sys.exit(0)\n"
+            "sys.exit(1)\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DXM_VARIANT="doesnotexist", PYTHONPATH=root)
+    env.pop("DXM_UNFUSED", None)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=root)
+    assert r.returncode == 0, r.stderr
 
 
 def test_product_never_imports_oracle():
