@@ -42,3 +42,18 @@ for nn in (1, 63, 64, 65, 5000):
     ms.enable_timing(1); ms.integrate_resident()
 ms.integrate_range_into(0, 2000, synth.strain(2000, 0, 1e-2, 1, 1), np.empty((2000, 6)), None, np.empty((2000, 36)))
 print("sanitize workload (round 2 additions) ok", info2["newton_iterations"])
+# last session of round 2: host arrays through the small-batch path (mapped page-locked staging, <= 2048 points), the
+# rewritten fe_forms_kernel (fast and rolled paths: run_gpu above assembles with constraints + lifting) and the
+# residual-only kernel
+for nn in (1, 16, 2048):
+    for beh in (jm.vonMisesIsotropicHardening(elasticity=el, yield_stress=jm.VoceHardening(sig0=350.0, sigu=500.0, b=1e3)),
+                jm.GeneralIsotropicHardening(elasticity=el, yield_stress=jm.LinearHardening(sig0=200.0, H=10.0))):
+        mh = jm.CUDAMaterial(beh); mh.set_data_manager(nn)
+        mh.integrate(synth.strain(nn, 0, 1.25e-2, 1, 1)); mh.data_manager.update(); mh.integrate(synth.strain(nn, 0, 2e-2, 1, 1))
+    mf = jm.CUDAMaterial(jm.FeFpJ2Plasticity(elasticity=el, yield_stress=jm.VoceHardening(sig0=500.0, sigu=750.0, b=1000.0)))
+    mf.set_data_manager(nn); mf.integrate(synth.defgrad(nn, 0, 2e-2, 1, 1))
+rowptr, colidx = nb.sparsity(ud, len(nodes))
+bc, top = nb.boundary_conditions(nodes, 10.0)
+system = AssembledSystem(ElementForms(ge, nb.W_DEG2), rowptr, colidx, bc=bc)
+system.assemble(matrix=False); system.assemble(); system.get()
+print("sanitize workload (last-session additions) ok")
