@@ -18,6 +18,7 @@ struct dxm_mesh {
   double *d_fe = nullptr, *d_ke = nullptr;  // element-form staging for host outputs (lazy)
   unsigned long long uid = 0;               // identity for caches keyed on a mesh (addresses get reused)
   std::vector<int32_t> h_u_dofs;  // host copy of the dofmap (node -> cells adjacency of the gather assembly)
+  std::vector<double> h_dphi, h_weights;  // host copies: passed by value to fe_forms_kernel (constant-bank operands)
   int64_t* nc_ptr = nullptr;      // device: node -> cells around it (CSR), built on first use
   int32_t* nc_cell = nullptr;
   uint8_t* nc_loc = nullptr;
@@ -72,6 +73,7 @@ int dxm_mesh_create(int device, int tdim, int64_t num_cells, int64_t num_nodes, 
   if (e == cudaSuccess) e = up((void**)&m->u_dofs, u_dofmap, sizeof(int32_t) * ndofs_cell * num_cells);
   m->h_u_dofs.assign(u_dofmap, u_dofmap + (size_t)ndofs_cell * num_cells);
   if (e == cudaSuccess) e = up((void**)&m->dphi, dphi, sizeof(double) * nqp * ndofs_cell * tdim);
+  m->h_dphi.assign(dphi, dphi + (size_t)nqp * ndofs_cell * tdim);
   if (e == cudaSuccess) e = cudaMalloc((void**)&m->u, sizeof(double) * num_dofs * tdim);
   if (e != cudaSuccess) {
     dxm_mesh_destroy(m);
@@ -154,6 +156,7 @@ int dxm_mesh_set_weights(dxm_mesh* m, const double* weights) {
   CK(cudaSetDevice(m->device));
   if (!m->weights) CK(cudaMalloc((void**)&m->weights, sizeof(double) * m->nqp));
   CK(cudaMemcpy(m->weights, weights, sizeof(double) * m->nqp, cudaMemcpyHostToDevice));
+  m->h_weights.assign(weights, weights + m->nqp);
   return 0;
 }
 
@@ -204,6 +207,22 @@ int build_adjacency(dxm_mesh* m) {
   return 0;
 }
 
+// one instantiation: the reference gradients / weights of the element travel as kernel parameters (by value)
+template <int TDIM, int ND, int NQP, int MODE>
+int launch_fe_forms_inst(dxm_mesh* m, dxm_handle* h, const FeFormArgs& a, const FeFormSmem& L, int64_t grid) {
+  FeTab<ND * NQP * TDIM, NQP> T{};
+  if (ND > 0) {
+    for (int i = 0; i < ND * NQP * TDIM; ++i) T.v[i] = m->h_dphi[i];
+    for (int q = 0; q < NQP; ++q) T.w[q] = m->h_weights[q];
+  }
+  if (L.bytes > 48 * 1024)
+    CK(cudaFuncSetAttribute(fe_forms_kernel<TDIM, ND, NQP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)L.bytes));
+  fe_forms_kernel<TDIM, ND, NQP, MODE><<<(unsigned)grid, 32 * kFeWarps, L.bytes, h->stream>>>(a, L, T);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 template <int MODE>
 int launch_fe_forms(dxm_mesh* m, dxm_handle* h, FeFormArgs& a) {
   if (!a.want_mat && a.want_vec) {
@@ -229,28 +248,21 @@ int launch_fe_forms(dxm_mesh* m, dxm_handle* h, FeFormArgs& a) {
     }
   }
   const FeFormSmem L = fe_form_smem(m->tdim, m->nd, m->nqp, a.kind, MODE, a.want_mat != 0);
-  // compile-time (nodes, Gauss points) for the hot-path elements: P2 / degree 2 and P1 / degree <= 1 simplices; anything
-  // else runs the run-time instantiation
-  const void* k;
-  if (m->tdim == 3)
-    k = (m->nd == 10 && m->nqp == 4)  ? (const void*)fe_forms_kernel<3, 10, 4, MODE>
-        : (m->nd == 4 && m->nqp == 1) ? (const void*)fe_forms_kernel<3, 4, 1, MODE>
-        : (m->nd == 4 && m->nqp == 4) ? (const void*)fe_forms_kernel<3, 4, 4, MODE>
-                                      : (const void*)fe_forms_kernel<3, 0, 0, MODE>;
-  else
-    k = (m->nd == 6 && m->nqp == 3)   ? (const void*)fe_forms_kernel<2, 6, 3, MODE>
-        : (m->nd == 3 && m->nqp == 1) ? (const void*)fe_forms_kernel<2, 3, 1, MODE>
-        : (m->nd == 3 && m->nqp == 3) ? (const void*)fe_forms_kernel<2, 3, 3, MODE>
-                                      : (const void*)fe_forms_kernel<2, 0, 0, MODE>;
   if (L.bytes > 227 * 1024) return fail("fe_forms: element too large for the shared-memory staging");
-  if (L.bytes > 48 * 1024)
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
   const int64_t grid = (a.num_cells + L.cpb - 1) / L.cpb;
   if (grid > 0x7fffffff) return fail("fe_forms: too many cells for one launch");
-  void* args[] = {(void*)&a, (void*)&L};
-  CK(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(32 * kFeWarps), args, L.bytes, h->stream));
-  LAUNCH_CHECK();
-  return 0;
+  // compile-time (nodes, Gauss points) for the hot-path elements: P2 / degree 2 and P1 / degree <= 1 simplices; anything
+  // else runs the run-time instantiation
+  if (m->tdim == 3) {
+    if (m->nd == 10 && m->nqp == 4) return launch_fe_forms_inst<3, 10, 4, MODE>(m, h, a, L, grid);
+    if (m->nd == 4 && m->nqp == 1) return launch_fe_forms_inst<3, 4, 1, MODE>(m, h, a, L, grid);
+    if (m->nd == 4 && m->nqp == 4) return launch_fe_forms_inst<3, 4, 4, MODE>(m, h, a, L, grid);
+    return launch_fe_forms_inst<3, 0, 0, MODE>(m, h, a, L, grid);
+  }
+  if (m->nd == 6 && m->nqp == 3) return launch_fe_forms_inst<2, 6, 3, MODE>(m, h, a, L, grid);
+  if (m->nd == 3 && m->nqp == 1) return launch_fe_forms_inst<2, 3, 1, MODE>(m, h, a, L, grid);
+  if (m->nd == 3 && m->nqp == 3) return launch_fe_forms_inst<2, 3, 3, MODE>(m, h, a, L, grid);
+  return launch_fe_forms_inst<2, 0, 0, MODE>(m, h, a, L, grid);
 }
 
 void fill_form_args(dxm_mesh* m, dxm_handle* h, int kind, FeFormArgs& a) {

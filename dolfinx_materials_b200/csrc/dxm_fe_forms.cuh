@@ -17,11 +17,14 @@
 //     through a row -> tensor-position map evaluated once per CTA;
 //   * a lane keeps its own g[b][:] and U_q[(r,j)] = sum_l A_q[(r,j)][(s,l)] g_q[b][l] in registers (formed once per
 //     row direction), and every entry of its column is then sum_q sum_j (vol_q g_q[a][j]) U_q[(r,j)]: 12 fused
-//     multiply-adds on broadcast 128-bit shared-memory operands -- 15 k DFMA per P2 tetrahedron instead of the 29 k
+//     multiply-adds -- 15 k DFMA per P2 tetrahedron instead of the 29 k
 //     DMUL + DADD and the ~130 shared-memory loads per row and point of the round-1 mapping (one thread per ROW);
+//   * the row operand of an entry is carried back to the reference cell (affine simplex: one K per cell), so it is the
+//     tabulated reference gradient dphi_q[a][m] -- passed to the kernel by value (constant bank), not read from shared
+//     memory: ke = sum_q sum_m dphi_q[a][m] Ut_q[m], Ut_q[m] = vol_q sum_j K[m][j] U_q[j];
 //   * a row of the element matrix leaves the warp as ONE predicated reduction instruction (the three columns of a node
-//     are adjacent in the CSR row).  The scatter is bound by the SM's reduction issue rate (~0.77 fp64 reductions per
-//     cycle and SM: 192 G/s chip-wide, scripts/probe_bulk_red.cu); the kernel runs at ~1.15x that floor.
+//     are adjacent in the CSR row).  Timing-only builds (profiles/r02z_fe_forms_diag.json): the kernel is bound by the
+//     issue slots / shared-memory traffic of the contraction, not by its reductions.
 // Tensor cores: not used.  FP64 DMMA (mma.sync.m8n8k4.f64, the only fp64 tensor path of sm_100) would have to treat the
 // gradient operator G (9 x 30) as dense although two thirds of it are structural zeros (delta_ss'): 147 kflop issued per
 // cell and point set for 28 kflop of useful work, at a peak (~40 TFLOP/s) no higher than the DFMA pipe's on B200.
@@ -314,21 +317,41 @@ DXM_HD void fe_form_column_u(const int nqp_rt, const int r, const int s, const d
   }
 }
 
-// ke[(a,r),(b,s)] = sum_q sum_j (vol_q g_q[a][j]) U_q[j]   (q outer, j inner, one product then fused steps)
+// Ut[q][m] = vol_q sum_j K[m][j] U_q[j]: U carried back to the reference cell (affine simplex: g_q[a][j] = sum_m
+// dphi_q[a][m] K[m][j] with ONE K per cell), so that the row operand of an entry is the tabulated reference gradient
+// dphi_q[a][m] -- the same numbers for every cell of the mesh: kernel-parameter constants instead of shared-memory rows.
+// Kv: K[m][j] row-major followed by |det J|; weights: the quadrature weights.
 template <int TDIM, int NQP>
-DXM_HD double fe_form_entry(const int nqp_rt, const int nd, const int a, const double* gv, const double* U) {
-  (void)nd;
+DXM_HD void fe_form_column_ut(const int nqp_rt, const double* Kv, const double* weights, const double* U,
+                              double* Ut /* [nqp][TDIM] */) {
   const int nqp = NQP > 0 ? NQP : nqp_rt;
-  double ga[(NQP > 0 ? NQP : kFeMaxQp) * TDIM];
-  if (NQP > 0)
-    fe_load_run<(NQP > 0 ? NQP : 1) * TDIM>(gv + (int64_t)a * NQP * TDIM, ga);
-  else
-    for (int i = 0; i < nqp * TDIM; ++i) ga[i] = gv[(int64_t)a * nqp * TDIM + i];
-  double acc = ga[0] * U[0];
+  const double adet = Kv[TDIM * TDIM];
 #pragma unroll
-  for (int i = 1; i < (NQP > 0 ? NQP : kFeMaxQp) * TDIM; ++i) {
-    if (NQP == 0 && i >= nqp * TDIM) break;
-    acc = fma_c(ga[i], U[i], acc);
+  for (int q = 0; q < (NQP > 0 ? NQP : kFeMaxQp); ++q) {
+    if (NQP == 0 && q >= nqp) break;
+    const double vol = weights[q] * adet;
+#pragma unroll
+    for (int m = 0; m < TDIM; ++m) {
+      double t = Kv[m * TDIM] * U[q * TDIM];
+#pragma unroll
+      for (int j = 1; j < TDIM; ++j) t = fma_c(Kv[m * TDIM + j], U[q * TDIM + j], t);
+      Ut[q * TDIM + m] = vol * t;
+    }
+  }
+}
+
+// ke[(a,r),(b,s)] = sum_q sum_m dphi_q[a][m] Ut_q[m]   (q outer, m inner, one product then fused steps); dphi: the
+// tabulated reference gradients [nqp][nd][TDIM]
+template <int TDIM, int NQP>
+DXM_HD double fe_form_entry(const int nqp_rt, const int nd, const int a, const double* dphi, const double* Ut) {
+  const int nqp = NQP > 0 ? NQP : nqp_rt;
+  double acc = dphi[a * TDIM] * Ut[0];
+#pragma unroll
+  for (int q = 0; q < (NQP > 0 ? NQP : kFeMaxQp); ++q) {
+    if (NQP == 0 && q >= nqp) break;
+#pragma unroll
+    for (int m = 0; m < TDIM; ++m)
+      if (q > 0 || m > 0) acc = fma_c(dphi[((int64_t)q * nd + a) * TDIM + m], Ut[q * TDIM + m], acc);
   }
   return acc;
 }
@@ -355,7 +378,7 @@ DXM_HD double fe_form_vector_entry(const int nqp_rt, const int nd, const int b, 
 
 // Resident CTAs per SM the register allocation targets: 5 (96 registers, no spills) -- 3.60 ms against 3.92 at 4 (120
 // registers); 6 / 7 CTAs need the largest shared-memory carve-out, whose smaller L1 costs more than the extra warps bring
-// (3.69-3.75 ms): the kernel is bound by the SM's reduction issue rate, not by latency (profiles/r02w_fe_forms_ab.json).
+// (3.69-3.75 ms; profiles/r02w_fe_forms_ab.json).
 #ifndef DXM_FE_MINB
 #define DXM_FE_MINB 5
 #endif
@@ -363,8 +386,17 @@ constexpr int kFeMinBlocks = DXM_FE_MINB;
 
 // NQP > 0: Gauss points per cell at compile time (the column state stays in registers); NQP == 0: run-time count up to
 // kFeMaxQp (local-memory arrays; uncommon rules)
+// reference gradients and quadrature weights of the compile-time elements, passed BY VALUE: kernel parameters live in the
+// constant bank, so with the row index unrolled they become immediate operands of the fused multiply-adds
+template <int N, int NQ>
+struct FeTab {
+  double v[N > 0 ? N : 1];
+  double w[NQ > 0 ? NQ : 1];
+};
+
 template <int TDIM, int ND, int NQP, int MODE>
-__global__ void __launch_bounds__(32 * kFeWarps, kFeMinBlocks) fe_forms_kernel(const FeFormArgs a, const FeFormSmem L) {
+__global__ void __launch_bounds__(32 * kFeWarps, kFeMinBlocks)
+    fe_forms_kernel(const FeFormArgs a, const FeFormSmem L, const FeTab<ND * NQP * TDIM, NQP> T) {
   extern __shared__ __align__(16) double smem[];
   constexpr int T2 = TDIM * TDIM;
   constexpr int NDC = ND > 0 ? ND : kFeMaxNd;
@@ -498,22 +530,28 @@ __global__ void __launch_bounds__(32 * kFeWarps, kFeMinBlocks) fe_forms_kernel(c
   const double* A = s_ct + (int64_t)lc * nqp * T2 * T2;
   const int32_t* ud = a.u_dofs + cell * nd;
   const int64_t* rowlo = s_rowlo + (MODE == MODE_ELEMENT ? 0 : lc * kFeMaxNd * TDIM);
+  const double* Kv = s_K[lc];                                   // K[m][j] row-major, |det J|
+  const double* tab = ND > 0 ? T.v : a.dphi;                    // reference gradients: constants | global memory
+  const double* wts = (ND > 0 && NQP > 0) ? T.w : a.weights;
 
   for (int cb = 0; cb < ndof; cb += 32) {  // columns in chunks of a warp (one chunk up to 10 nodes in 3-D)
     const int col = cb + lane;
     const bool live = col < ndof;
     const int b = live ? col / TDIM : 0, s = live ? col - b * TDIM : 0;
-    double gb[kFeMaxQp * TDIM], U[kFeMaxQp * TDIM];
+    double gb[kFeMaxQp * TDIM], U[kFeMaxQp * TDIM], Ut[kFeMaxQp * TDIM];
     fe_form_column_g<TDIM, NQP>(nqp, nd, b, g, gb);
 
     if (MODE == MODE_ELEMENT) {
       if (live && a.want_vec) a.fe[cell * ndof + col] = fe_form_vector_entry<TDIM, NQP>(nqp, nd, b, s, gv, S);
       if (!a.want_mat) continue;
-#pragma unroll
+#pragma unroll 1
       for (int r = 0; r < TDIM; ++r) {
         fe_form_column_u<TDIM, NQP>(nqp, r, s, gb, A, U);
-        for (int an = 0; an < nd; ++an) {
-          const double v = fe_form_entry<TDIM, NQP>(nqp, nd, an, gv, U);
+        fe_form_column_ut<TDIM, NQP>(nqp, Kv, wts, U, Ut);
+#pragma unroll
+        for (int an = 0; an < NDC; ++an) {
+          if (ND == 0 && an >= nd) break;
+          const double v = fe_form_entry<TDIM, NQP>(nqp, nd, an, tab, Ut);
           if (live) __stcs(a.ke + (cell * ndof + an * TDIM + r) * ndof + col, v);  // a row is one contiguous line
         }
       }
@@ -543,11 +581,12 @@ __global__ void __launch_bounds__(32 * kFeWarps, kFeMinBlocks) fe_forms_kernel(c
 #pragma unroll 1
       for (int r = 0; r < TDIM; ++r) {
         fe_form_column_u<TDIM, NQP>(nqp, r, s, gb, A, U);
+        fe_form_column_ut<TDIM, NQP>(nqp, Kv, wts, U, Ut);
 #pragma unroll
         for (int an = 0; an < NDC; ++an) {
           if (ND == 0 && an >= nd) break;
           const int64_t lo = rowlo[an * TDIM + r];  // < 0: constrained row, untouched (unit diagonal set by the host API)
-          const double v = fe_form_entry<TDIM, NQP>(nqp, nd, an, gv, U);
+          const double v = fe_form_entry<TDIM, NQP>(nqp, nd, an, tab, Ut);
           const bool row_ok = writer && lo >= 0;
           if (row_ok && offs[an] >= 0) atomicAdd(a.vals + (lo + offs[an] + s), v);  // result unused: a RED
           miss += (row_ok && offs[an] < 0) ? 1u : 0u;
@@ -559,11 +598,12 @@ __global__ void __launch_bounds__(32 * kFeWarps, kFeMinBlocks) fe_forms_kernel(c
 #pragma unroll 1
       for (int r = 0; r < TDIM; ++r) {
         fe_form_column_u<TDIM, NQP>(nqp, r, s, gb, A, U);
+        fe_form_column_ut<TDIM, NQP>(nqp, Kv, wts, U, Ut);
 #pragma unroll 1
         for (int an = 0; an < nd; ++an) {
           const int64_t lo = rowlo[an * TDIM + r];
           if (lo < 0) continue;
-          const double v = fe_form_entry<TDIM, NQP>(nqp, nd, an, gv, U);
+          const double v = fe_form_entry<TDIM, NQP>(nqp, nd, an, a.dphi, Ut);  // rolled: the table from global memory
           if (any_lift) {
             // constrained columns move to the right-hand side (apply_lifting): b[row] -= sum_bc K[row][col] lift[col]
             double lf = col_bc ? v * lift : 0.0;

@@ -102,8 +102,11 @@ def element_forms(coords, geom_dofmap, u_dofmap, dphi, weights, flux, ct, kind, 
 
     Canonical operation order (shared with ``fe_forms_kernel``, one warp lane per column ``(b, s)``):
     ``gv_q[a][j] = vol_q g_q[a][j]``; ``U_q[(r,j)] = sum_l A_q[(r,j)][(s,l)] g_q[b][l]``;
-    ``ke[(a,r),(b,s)] = sum_q sum_j gv_q[a][j] U_q[(r,j)]`` and ``fe[(b,s)] = sum_q sum_j S_q[s][j] gv_q[b][j]``, every
-    sum one product followed by fused multiply-adds in the order written (q outer, j / l inner)."""
+    ``Ut_q[(r,m)] = vol_q sum_j K[m][j] U_q[(r,j)]`` (U carried back to the reference cell: on an affine simplex
+    ``g_q[a][j] = sum_m dphi_q[a][m] K[m][j]`` with one ``K`` per cell, so the row operand of an entry is the tabulated
+    reference gradient -- the same numbers for every cell, constants of the kernel);
+    ``ke[(a,r),(b,s)] = sum_q sum_m dphi_q[a][m] Ut_q[(r,m)]`` and ``fe[(b,s)] = sum_q sum_j S_q[s][j] gv_q[b][j]``, every
+    sum one product followed by fused multiply-adds in the order written (q outer, j / l / m inner)."""
     from .canon import fma
 
     ud = np.asarray(u_dofmap)
@@ -151,12 +154,21 @@ def element_forms(coords, geom_dofmap, u_dofmap, dphi, weights, flux, ct, kind, 
                         for l in range(1, tdim):
                             u = fma(_tangent_tensor(ct, kind, pts[q], r, j, s, l), g[q][b][l], u)
                         U[q][r][j] = u
+            Ut = [[[None] * tdim for _ in range(tdim)] for _ in range(nqp)]
+            for q in range(nqp):
+                vol = weights[q] * adet
+                for r in range(tdim):
+                    for m in range(tdim):
+                        t = K[m][0] * U[q][r][0]
+                        for j in range(1, tdim):
+                            t = fma(K[m][j], U[q][r][j], t)
+                        Ut[q][r][m] = vol * t
             for a in range(nd):
                 for r in range(tdim):
                     acc = None
                     for q in range(nqp):
-                        for j in range(tdim):
-                            acc = gv[q][a][0] * U[q][r][0] if acc is None else fma(gv[q][a][j], U[q][r][j], acc)
+                        for m in range(tdim):
+                            acc = dphi[q, a, 0] * Ut[q][r][0] if acc is None else fma(dphi[q, a, m], Ut[q][r][m], acc)
                     ke[:, a * tdim + r, col] = acc
     return fe, ke
 

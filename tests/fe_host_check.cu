@@ -29,8 +29,14 @@ void form_cells(const dxm::FeFormArgs& a) {
   const int nflux = a.kind == 0 ? 6 : 9, nct = a.kind == 0 ? dxm::kSym6Rows : 81;
   std::vector<double> vol(nqp), g((size_t)nqp * nd * TDIM), gv((size_t)nqp * nd * TDIM), S((size_t)nqp * T2),
       A((size_t)nqp * T2 * T2);
-  double gb[dxm::kFeMaxQp * TDIM], U[dxm::kFeMaxQp * TDIM];
+  double gb[dxm::kFeMaxQp * TDIM], U[dxm::kFeMaxQp * TDIM], Ut[dxm::kFeMaxQp * TDIM];
   for (int64_t c = 0; c < a.num_cells; ++c) {
+    // K[m][j] row-major and |det J| of the cell, as the kernel keeps them in shared memory
+    double Kc[TDIM][TDIM], detc, Kv[TDIM * TDIM + 1];
+    dxm::cell_geometry<TDIM>(a.coords, a.geom_dofs + c * (TDIM + 1), Kc, detc);
+    for (int i = 0; i < TDIM; ++i)
+      for (int j = 0; j < TDIM; ++j) Kv[i * TDIM + j] = Kc[i][j];
+    Kv[TDIM * TDIM] = std::fabs(detc);
     std::vector<double> gq((size_t)nd * TDIM);
     for (int q = 0; q < nqp; ++q) {
       dxm::fe_form_point_geometry<TDIM>(a, c, q, nd, vol[q], gq.data());
@@ -52,8 +58,9 @@ void form_cells(const dxm::FeFormArgs& a) {
       if (a.want_mat)
         for (int r = 0; r < TDIM; ++r) {
           dxm::fe_form_column_u<TDIM, NQP>(nqp, r, s, gb, A.data(), U);
+          dxm::fe_form_column_ut<TDIM, NQP>(nqp, Kv, a.weights, U, Ut);
           for (int an = 0; an < nd; ++an)
-            a.ke[(c * ndof + an * TDIM + r) * ndof + col] = dxm::fe_form_entry<TDIM, NQP>(nqp, nd, an, gv.data(), U);
+            a.ke[(c * ndof + an * TDIM + r) * ndof + col] = dxm::fe_form_entry<TDIM, NQP>(nqp, nd, an, a.dphi, Ut);
         }
     }
     // the residual-only kernel's per-(cell, basis function) routine must give the same bits as the column routine
