@@ -188,3 +188,73 @@ def test_cuda_material_has_every_member_the_reference_callers_touch():
         if name in optional:
             continue
         assert hasattr(mat, name), f"{where}: material.{name} is used by the reference but missing on CUDAMaterial"
+
+
+# ---- the SEQUENCE of material- and Function-facing calls --------------------------------------------------------------
+def _dotted(node):
+    """``self.material.integrate`` -> 'self.material.integrate'; ``_update_vals`` -> '_update_vals'; else None"""
+    parts = []
+    while isinstance(node, ast.Attribute):
+        parts.append(node.attr)
+        node = node.value
+    if isinstance(node, ast.Name):
+        parts.append(node.id)
+        return ".".join(reversed(parts))
+    return None
+
+
+_WATCHED = ("self.material.", "_update_vals", "_get_vals", "self.get_gradient_vals", "self.update_external_state_variables",
+            "self.initialize_state", "self.update_fluxes", "self.update_internal_state_variables")
+
+
+def _call_sequence(cls, method, inline=("update_fluxes", "update_internal_state_variables")):
+    """The watched calls of ``cls.method`` in source order, the class's own small helpers inlined, rotation branches
+    (``rotation_matrix is not None``: never taken for the isotropic CUDA behaviours) left out."""
+    methods = {n.name: n for n in cls.body if isinstance(n, ast.FunctionDef)}
+
+    def visit(nodes, out):
+        for node in nodes:
+            if isinstance(node, ast.If) and "rotation_matrix" in ast.dump(node.test):
+                continue
+            calls = [c for c in ast.walk(node) if isinstance(c, ast.Call)] if not isinstance(
+                node, (ast.If, ast.For, ast.With, ast.While)) else None
+            if calls is None:  # compound statement: header expressions first, then the body in order
+                header = [getattr(node, "test", None), getattr(node, "iter", None)] + [i.context_expr for i in getattr(node, "items", [])]
+                for h in header:
+                    if h is not None:
+                        visit([ast.Expr(h)], out)
+                visit(node.body, out)
+                visit(getattr(node, "orelse", []), out)
+                continue
+            for c in sorted(calls, key=lambda c: (c.lineno, c.col_offset)):
+                name = _dotted(c.func)
+                if not name or not any(name == w or name.startswith(w) for w in _WATCHED):
+                    continue
+                if name.rsplit(".", 1)[-1] in ("keys", "items", "values"):  # dict views of the name -> size maps: reads
+                    continue
+                short = name.split(".")[-1]
+                if name.startswith("self.") and short in inline and short in methods:
+                    visit(methods[short].body, out)
+                else:
+                    out.append(name)
+        return out
+
+    return visit(methods[method].body, [])
+
+
+def test_stand_in_replays_the_reference_call_sequence():
+    """``update()``, ``advance()`` and ``initialize_state()`` of the stand-in the GPU adapter is tested against make the same
+    material-facing / Function-facing calls, in the same order, as the reference's ``QuadratureMap`` (AST of both
+    sources; ``update_fluxes`` / ``update_internal_state_variables`` inlined, rotation branches excluded)."""
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not present")
+    ref = _class(os.path.join(REF, "quadrature_map.py"), "QuadratureMap")
+    standin = _class(os.path.join(HERE, "qmap_standin.py"), "StandInQuadratureMap")
+    for method in ("update", "advance"):
+        a, b = _call_sequence(ref, method), _call_sequence(standin, method)
+        assert a == b, (method, a, b)
+        assert any(x.startswith("self.material.") for x in a)
+    # initialize_state: same set of state sources pushed through set_initial_state_dict
+    a, b = _call_sequence(ref, "initialize_state"), _call_sequence(standin, "initialize_state")
+    assert a[-1] == b[-1] == "self.material.set_initial_state_dict"
+    assert set(a) == set(b), (a, b)
