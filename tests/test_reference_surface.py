@@ -258,3 +258,17 @@ def test_stand_in_replays_the_reference_call_sequence():
     a, b = _call_sequence(ref, "initialize_state"), _call_sequence(standin, "initialize_state")
     assert a[-1] == b[-1] == "self.material.set_initial_state_dict"
     assert set(a) == set(b), (a, b)
+
+
+def test_replayed_reference_sequence_is_the_reference_sequence():
+    """``tests/qmap_replay.py`` -- the arm the GPU exchange is compared with bit for bit and timed against
+    (``scripts/bench_exchange.py``) -- gathers the gradient values itself (no UFL expression to evaluate, no external
+    state variables); everything else is the reference's sequence call for call."""
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not present")
+    ref = _class(os.path.join(REF, "quadrature_map.py"), "QuadratureMap")
+    replay = _class(os.path.join(HERE, "qmap_replay.py"), "QuadratureMapReplay")
+    assert _call_sequence(ref, "advance") == _call_sequence(replay, "advance")
+    expected = [("_get_vals" if x == "self.get_gradient_vals" else x) for x in _call_sequence(ref, "update")
+                if x != "self.update_external_state_variables"]
+    assert expected == _call_sequence(replay, "update")
