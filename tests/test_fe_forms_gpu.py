@@ -77,6 +77,12 @@ def test_tet_element_forms_and_assembly(jm, order, finite):
         A = sp.csr_matrix((vals, colidx, rowptr), shape=A_ref.shape)
         assert bc.any() and abs(A - A_ref).max() <= 1e-12 * scale
         assert np.all(b[bc] == 0) and np.allclose(b, b_ref, rtol=0, atol=1e-12 * np.abs(fe_ref).max())
+        # residual only (what SNES asks for at a function evaluation): the thread-per-(cell, basis function) kernel;
+        # the matrix values of the previous pass are left alone
+        system.assemble(matrix=False)
+        vals_kept, b_only = (x.copy() for x in system.get())
+        assert np.all(b_only[bc] == 0) and np.allclose(b_only, b_ref, rtol=0, atol=1e-12 * np.abs(fe_ref).max())
+        assert np.array_equal(vals_kept, vals)
         # inhomogeneous constraint: constrained columns move to the right-hand side (apply_lifting + set_bc)
         lift = np.where(bc, np.sin(np.arange(bc.size) * 0.37) * 1e-3, 0.0)
         system.set_lifting(lift)
