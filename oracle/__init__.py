@@ -35,6 +35,13 @@ PARITY STATUS
   independent statement of the implicit system, finite-difference tangents, a = 2 == the J2 oracle and the
   criterion's known yield points (``tests/test_oracle_hosford.py``).
 
+* distance to the EXACT solution (``oracle/jaxmat_form_mp.py``, ``oracle/hosford_mp.py``): jaxmat's branch-free
+  systems and the seven-unknown system of MFront's ``Implicit`` DSL solved point by point in 40-digit arithmetic
+  (``mpmath``), tangents as central differences of the solution map: the canonical arithmetic is within 2e-12 (stress),
+  the local Newton tolerance (plastic multiplier) and 1e-11 (tangent) of it
+  (``tests/test_oracle_jaxmat_form_mp.py``, ``tests/test_oracle_hosford_mp.py``).  That pins the mathematics, not the
+  dependencies' own floating-point output.
+
 Canonical arithmetic
 --------------------
 Every function is written component-wise with an explicit operation order and uses only
