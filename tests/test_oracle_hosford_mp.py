@@ -75,3 +75,18 @@ def test_consistent_tangent_vs_40_digit_derivative():
             assert err <= 1e-11, (props["a"], i, err)
             assert np.abs(C - C.T).max() <= 1e-20 * np.abs(C).max()  # associated flow: the exact tangent is symmetric
     assert worst > 0.0
+
+
+def test_extreme_regimes_vs_40_digit_solution():
+    """Steps of 35 x the yield strain, the largest supported exponent, nearly incompressible elasticity with stiff hardening."""
+    for props, amp in ((dict(DEMO), 1e-1), (dict(DEMO, a=64), 1e-2), (dict(E=210e3, nu=0.45, sig0=50.0, H=1e4, a=12), 3e-2)):
+        n = 5
+        st = ss.zero_state(n)
+        eps = synth.strain(n, 7, amp, 1, 1)
+        out = ho.integrate(eps, st, props)
+        assert out["fail"].sum() == 0 and out["flag"].all()
+        for i in range(n):
+            ref = hm.integrate_point(eps[i], st["strain"][i], st["epsp"][i], st["p"][i], props, start=_start(eps, st, out, i))
+            s = _f(ref["stress"])
+            assert np.abs(out["stress"][i] - s).max() <= 3e-12 * np.abs(s).max(), (props["a"], i)
+            assert abs(out["p"][i] - float(ref["p"])) <= 1e-11 * float(ref["p"]), (props["a"], i)
