@@ -281,7 +281,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def workload_config(args, world):
+def workload_config(args, world, stats_exchange=None):
+    if stats_exchange is None:
+        stats_exchange = "none (one GPU)" if world == 1 else "in the update kernel's epilogue over NVLink peer memory, or in-stream NCCL all-gather"
     return {
         "workload": "cfg2: 3D small-strain J2 plasticity + Voce hardening, fp64, synthetic proportional strain histories",
         "points_per_gpu": int(args.n),
@@ -289,7 +291,7 @@ def workload_config(args, world):
         "properties": PROPS,
         "history": f"counter-based recipe seed {SEED}, amp {AMP}, increment {KINC}/{KINC} after {KINC - 1} state updates",
         "l2": "inputs >> L2 (47.2 GB touched per step per GPU), no flush needed",
-        "parallelism": f"points sharded over {world} GPU(s), no data-path collective; in-stream NCCL all-gather of the 64-byte statistics record per step",
+        "parallelism": f"points sharded over {world} GPU(s), no data-path collective; exchange of the 64-byte statistics record per step: {stats_exchange}",
         "e2e_points_per_gpu": int(min(args.e2e_n, args.n)),
         "e2e_range_points": int(min(args.e2e_range, args.e2e_n, args.n)),
         "exchange_points_per_gpu": int(min(args.exchange_n, args.e2e_n, args.n)),
@@ -391,6 +393,11 @@ def run_ours(args):
         in_stream = init_stats_comm() == world
         if in_stream:
             m.use_global_stats()
+        stats_exchange = ("in the update kernel's epilogue over NVLink peer memory" if in_stream and lib.dxm_comm_p2p_enabled()
+                          else "in-stream NCCL all-gather on the handle's stream" if in_stream
+                          else "host-side all-gather (fallback: NCCL not loadable)")
+    else:
+        stats_exchange = "none (one GPU)"
     m.enable_timing(1)
 
     def step():
@@ -594,7 +601,7 @@ def run_ours(args):
             "vs_baseline": None,
             "dtype": "f64",
             "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": workload_config(args, world, stats_exchange),
             "roofline": {
                 "bound": "hbm",
                 "achieved": achieved,
