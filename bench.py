@@ -393,7 +393,11 @@ def run_ours(args):
         in_stream = init_stats_comm() == world
         if in_stream:
             m.use_global_stats()
-        stats_exchange = ("in the update kernel's epilogue over NVLink peer memory" if in_stream and lib.dxm_comm_p2p_enabled()
+        try:
+            p2p = bool(in_stream and lib.dxm_comm_p2p_enabled())
+        except Exception:  # noqa: BLE001 - a label only: never let it stop the run
+            p2p = False
+        stats_exchange = ("in the update kernel's epilogue over NVLink peer memory" if p2p
                           else "in-stream NCCL all-gather on the handle's stream" if in_stream
                           else "host-side all-gather (fallback: NCCL not loadable)")
     else:
