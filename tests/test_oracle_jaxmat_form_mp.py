@@ -91,3 +91,18 @@ def test_reference_fefp_script_vs_40_digit_solution():
         seen += int(out["flag"][0])
         st = fefp.advance(out)
     assert seen > 5
+
+
+def test_finite_strain_large_deformations_vs_40_digit_solution():
+    """|F - I| up to 0.3 per increment (every point plastic): the reduced 2x2 solve of the canonical oracle stays within
+    5e-12 of the exact solution of jaxmat's seven-unknown system."""
+    for amp in (0.1, 0.3):
+        n = 6
+        st = fefp.virgin_state(n)
+        for k in (1, 2):
+            F = synth.defgrad(n, 3, amp, k, 2)
+            out = fefp.integrate(F, st, FEFP)
+            assert out["fail"].sum() == 0 and out["flag"].all()
+            for i in range(n):
+                _fefp_check(F, st, out, i)
+            st = fefp.advance(out)
