@@ -208,6 +208,8 @@ int dxm_system_set_bc(dxm_system* s, const uint8_t* marker); /* host array of nr
  * NULL: homogeneous).  dxm_assemble then moves the constrained columns to the right-hand side,
  * rhs -= A[:, bc] x_bc, and sets rhs[bc] = x_bc (DOLFINx apply_lifting + set_bc, solvers.py:84-96) */
 int dxm_system_set_lifting(dxm_system* s, const double* values);
+/* want_matrix == 0: residual only (the SNES function evaluation, solvers.py:80-81) -- its own kernel, the matrix values of
+ * the previous pass are left alone; not available while lifting values are set (the lifting needs the matrix pass). */
 int dxm_assemble(dxm_mesh* m, dxm_handle* h, int kind, dxm_system* s, int want_vector, int want_matrix);
 int dxm_system_get(dxm_system* s, double* values, double* rhs, int mem); /* either may be NULL */
 /* Rank-sharded assembly (one process per GPU, each holding a contiguous block of cells): every rank
