@@ -190,11 +190,20 @@ def test_noniterative_eigen_decomposition_is_backward_stable():
         "pure-shear-like": spectra(np.stack([np.ones(n), 0.1 * e, -1 - 0.1 * e], 1)),
         "diagonal": diag,
     }
+    # entries graded over twelve orders of magnitude; nearly diagonal with off-diagonals from 1e-300 to 1e-1
+    grade = 10.0 ** rng.uniform(-6, 6, (n, 3))
+    cases["graded"] = sym(rng.standard_normal((n, 3, 3))) * grade[:, :, None] * grade[:, None, :]
+    near = np.zeros((n, 3, 3))
+    near[:, [0, 1, 2], [0, 1, 2]] = rng.standard_normal((n, 3))
+    for i, j in ((0, 1), (0, 2), (1, 2)):
+        near[:, i, j] = near[:, j, i] = 10.0 ** rng.uniform(-300, -1, n) * rng.choice([-1.0, 1.0], n)
+    cases["nearly diagonal"] = near
     for name, S in cases.items():
         S, s6 = _mandel_deviators(S)
         l, V = cport.hosford_eig(s6)
         scale = np.linalg.norm(S, axis=(1, 2))
-        assert np.max(np.linalg.norm(S @ V - V * l[:, None, :], axis=(1, 2)) / scale) < 4e-15, name
+        tol = 2e-14 if name == "nearly diagonal" else 4e-15
+        assert np.max(np.linalg.norm(S @ V - V * l[:, None, :], axis=(1, 2)) / scale) < tol, name
         assert np.max(np.linalg.norm(np.swapaxes(V, 1, 2) @ V - np.eye(3), axis=(1, 2))) < 4e-15, name
         assert np.max(np.linalg.norm(np.sort(l, 1) - np.linalg.eigvalsh(S), axis=1) / scale) < 4e-15, name
     l, V = cport.hosford_eig(np.zeros((1, 6)))  # zero deviator: never a candidate point, still well defined
