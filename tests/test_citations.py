@@ -41,3 +41,20 @@ def test_reference_citations_are_in_range():
             if a < 1 or a > b or b > lines:
                 bad.append((os.path.relpath(src, ROOT), m.group(0), lines))
     assert checked > 200 and not bad, bad[:10]
+
+
+HEADLINE = {  # the cited range holds the definition it is cited for
+    ("generic.py", 176, 189): "def integrate", ("generic.py", 10, 100): "def _vmap", ("generic.py", 204, 295): "class DataManager",
+    ("jaxmat.py", 208, 234): "def integrate", ("jaxmat.py", 158, 164): "def constitutive_update", ("jaxmat.py", 144, 156): "def __init__",
+    ("jaxmat.py", 30, 43): "class DataManager", ("quadrature_map.py", 297, 334): "def update", ("quadrature_map.py", 350, 360): "def advance",
+    ("quadrature_map.py", 281, 295): "def initialize_state", ("quadrature_map.py", 132, 158): "def derivative",
+    ("quadrature_function.py", 45, 51): "def eval",
+}
+
+
+def test_headline_citations_hold_the_definitions_they_name():
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not present")
+    for (name, a, b), needle in HEADLINE.items():
+        lines = open(os.path.join(REF, "dolfinx_materials", name)).read().splitlines()[a - 1:b]
+        assert any(needle in line for line in lines), (name, a, b, needle)
